@@ -1,0 +1,142 @@
+#!/usr/bin/env python
+"""Build oracle/_ref/libhamers_ref.so from the reference's OWN source files (test infrastructure).
+
+The HAMeRS build needs MPI + HDF5 + SAMRAI + Fortran, none of which exist in this image, so
+the reference cannot be built as a whole.  Its per-point `static inline` kernels, however, are
+SAMRAI-free.  This recipe reads them where they lie under /root/reference, wraps them in
+namespaces inside a generated translation unit under oracle/_ref/ (git-ignored, never
+committed), compiles it with the reference's own flags (g++ -std=c++11 -O3, CMakeLists.txt:80;
+HAMERS_EPSILON = 1.0e-15, include/HAMeRS_config.hpp.in:16) and deletes the generated source.
+The resulting library pins the oracle's WCNS5-JS interpolation and HLLC / HLLC-HLL kernels
+(tests/test_oracle_pinned.py).
+
+Nothing here is copied into the repository; if /root/reference is absent (the GPU box) the
+script does nothing and the prebuilt .so that travelled with the snapshot is used.
+"""
+from __future__ import annotations
+
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("HAMERS_REFERENCE", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+
+SOURCES = {
+    # namespace -> reference file holding `static inline` point kernels
+    "ref_weno": "src/flow/convective_flux_reconstructors/WCNS56/ConvectiveFluxReconstructorWCNS5-JS-HLLC-HLL.cpp",
+    "ref_ss_hllc": "src/flow/flow_models/single-species/Riemann_solvers/FlowModelRiemannSolverSingleSpeciesHLLC.cpp",
+    "ref_ss_hyb": "src/flow/flow_models/single-species/Riemann_solvers/FlowModelRiemannSolverSingleSpeciesHLLC-HLL.cpp",
+    "ref_fe_hllc": "src/flow/flow_models/five-eqn_Allaire/Riemann_solvers/FlowModelRiemannSolverFiveEqnAllaireHLLC.cpp",
+    "ref_fe_hyb": "src/flow/flow_models/five-eqn_Allaire/Riemann_solvers/FlowModelRiemannSolverFiveEqnAllaireHLLC-HLL.cpp",
+}
+
+
+def static_inline_functions(text: str) -> str:
+    """Return the concatenation of every `static inline ...` function definition in text."""
+    out = []
+    for m in re.finditer(r"^static inline[^\n]*\n?[^\n;{]*\(", text, flags=re.M):
+        start = m.start()
+        brace = text.index("{", m.end())
+        depth, i = 0, brace
+        while True:
+            ch = text[i]
+            if ch == "{":
+                depth += 1
+            elif ch == "}":
+                depth -= 1
+                if depth == 0:
+                    break
+            i += 1
+        out.append(text[start:i + 1])
+    return "\n\n".join(out)
+
+
+WRAPPERS = r"""
+extern "C" {
+
+/* WCNS5-JS point interpolation: performLocalWENOInterpolationMinus/Plus with idx_side = 0 */
+void ref_weno5js_point(const double U[6], int p, double* U_minus, double* U_plus)
+{
+    double vals[6]; double* Ua[6];
+    for (int m = 0; m < 6; m++) { vals[m] = U[m]; Ua[m] = &vals[m]; }
+    ref_weno::performLocalWENOInterpolationMinus(U_minus, Ua, 0, p);
+    ref_weno::performLocalWENOInterpolationPlus(U_plus, Ua, 0, p);
+}
+
+/* HLLC and HLLC-HLL point kernels on one face (idx = idx_flux = 0).  The midpoint normal velocity is
+ * the two-line driver formula (SingleSpeciesHLLC.cpp:3381-3388, FiveEqnAllaireHLLC.cpp:6034-6038). */
+int ref_riemann_point(int model, int dim, int ns, int dir,
+                      const double* V_L, const double* V_R,
+                      double rho_L, double rho_R, double c_L, double c_R, double eps_L, double eps_R,
+                      double* F_HLLC, double* F_HYB, double* vel_mid)
+{
+    const int neq = model == 0 ? dim + 2 : dim + 2*ns;
+    double vl[16], vr[16], f1[16], f2[16];
+    double *VL[16], *VR[16], *F1[16], *F2[16];
+    for (int e = 0; e < neq; e++) { vl[e] = V_L[e]; vr[e] = V_R[e]; VL[e] = &vl[e]; VR[e] = &vr[e]; F1[e] = &f1[e]; F2[e] = &f2[e]; }
+    double s_minus = 0, s_plus = 0, s_star = 0, Chi = 0;
+    double s_minus2 = 0, s_plus2 = 0, s_star2 = 0, Chi2 = 0;
+    const int key = model*100 + dim*10 + dir;
+    switch (key) {
+    case  20: ref_ss_hllc::computeLocalConvectiveFluxInXDirectionFromPrimitiveVariablesHLLC2D(F1, VL, VR, &c_L, &c_R, &eps_L, &eps_R, s_minus, s_plus, s_star, Chi, 0, 0);
+              ref_ss_hyb::computeLocalConvectiveFluxInXDirectionFromPrimitiveVariablesHLLC_HLL2D(F2, VL, VR, &c_L, &c_R, &eps_L, &eps_R, s_minus2, s_plus2, s_star2, Chi2, 0, 0); break;
+    case  21: ref_ss_hllc::computeLocalConvectiveFluxInYDirectionFromPrimitiveVariablesHLLC2D(F1, VL, VR, &c_L, &c_R, &eps_L, &eps_R, s_minus, s_plus, s_star, Chi, 0, 0);
+              ref_ss_hyb::computeLocalConvectiveFluxInYDirectionFromPrimitiveVariablesHLLC_HLL2D(F2, VL, VR, &c_L, &c_R, &eps_L, &eps_R, s_minus2, s_plus2, s_star2, Chi2, 0, 0); break;
+    case  30: ref_ss_hllc::computeLocalConvectiveFluxInXDirectionFromPrimitiveVariablesHLLC3D(F1, VL, VR, &c_L, &c_R, &eps_L, &eps_R, s_minus, s_plus, s_star, Chi, 0, 0);
+              ref_ss_hyb::computeLocalConvectiveFluxInXDirectionFromPrimitiveVariablesHLLC_HLL3D(F2, VL, VR, &c_L, &c_R, &eps_L, &eps_R, s_minus2, s_plus2, s_star2, Chi2, 0, 0); break;
+    case  31: ref_ss_hllc::computeLocalConvectiveFluxInYDirectionFromPrimitiveVariablesHLLC3D(F1, VL, VR, &c_L, &c_R, &eps_L, &eps_R, s_minus, s_plus, s_star, Chi, 0, 0);
+              ref_ss_hyb::computeLocalConvectiveFluxInYDirectionFromPrimitiveVariablesHLLC_HLL3D(F2, VL, VR, &c_L, &c_R, &eps_L, &eps_R, s_minus2, s_plus2, s_star2, Chi2, 0, 0); break;
+    case  32: ref_ss_hllc::computeLocalConvectiveFluxInZDirectionFromPrimitiveVariablesHLLC3D(F1, VL, VR, &c_L, &c_R, &eps_L, &eps_R, s_minus, s_plus, s_star, Chi, 0, 0);
+              ref_ss_hyb::computeLocalConvectiveFluxInZDirectionFromPrimitiveVariablesHLLC_HLL3D(F2, VL, VR, &c_L, &c_R, &eps_L, &eps_R, s_minus2, s_plus2, s_star2, Chi2, 0, 0); break;
+    case 120: ref_fe_hllc::computeLocalConvectiveFluxInXDirectionFromPrimitiveVariablesHLLC2D(F1, VL, VR, &rho_L, &rho_R, &c_L, &c_R, &eps_L, &eps_R, s_minus, s_plus, s_star, Chi, 0, 0, ns, neq);
+              ref_fe_hyb::computeLocalConvectiveFluxInXDirectionFromPrimitiveVariablesHLLC_HLL2D(F2, VL, VR, &rho_L, &rho_R, &c_L, &c_R, &eps_L, &eps_R, s_minus2, s_plus2, s_star2, Chi2, 0, 0, ns, neq); break;
+    case 121: ref_fe_hllc::computeLocalConvectiveFluxInYDirectionFromPrimitiveVariablesHLLC2D(F1, VL, VR, &rho_L, &rho_R, &c_L, &c_R, &eps_L, &eps_R, s_minus, s_plus, s_star, Chi, 0, 0, ns, neq);
+              ref_fe_hyb::computeLocalConvectiveFluxInYDirectionFromPrimitiveVariablesHLLC_HLL2D(F2, VL, VR, &rho_L, &rho_R, &c_L, &c_R, &eps_L, &eps_R, s_minus2, s_plus2, s_star2, Chi2, 0, 0, ns, neq); break;
+    case 130: ref_fe_hllc::computeLocalConvectiveFluxInXDirectionFromPrimitiveVariablesHLLC3D(F1, VL, VR, &rho_L, &rho_R, &c_L, &c_R, &eps_L, &eps_R, s_minus, s_plus, s_star, Chi, 0, 0, ns, neq);
+              ref_fe_hyb::computeLocalConvectiveFluxInXDirectionFromPrimitiveVariablesHLLC_HLL3D(F2, VL, VR, &rho_L, &rho_R, &c_L, &c_R, &eps_L, &eps_R, s_minus2, s_plus2, s_star2, Chi2, 0, 0, ns, neq); break;
+    case 131: ref_fe_hllc::computeLocalConvectiveFluxInYDirectionFromPrimitiveVariablesHLLC3D(F1, VL, VR, &rho_L, &rho_R, &c_L, &c_R, &eps_L, &eps_R, s_minus, s_plus, s_star, Chi, 0, 0, ns, neq);
+              ref_fe_hyb::computeLocalConvectiveFluxInYDirectionFromPrimitiveVariablesHLLC_HLL3D(F2, VL, VR, &rho_L, &rho_R, &c_L, &c_R, &eps_L, &eps_R, s_minus2, s_plus2, s_star2, Chi2, 0, 0, ns, neq); break;
+    case 132: ref_fe_hllc::computeLocalConvectiveFluxInZDirectionFromPrimitiveVariablesHLLC3D(F1, VL, VR, &rho_L, &rho_R, &c_L, &c_R, &eps_L, &eps_R, s_minus, s_plus, s_star, Chi, 0, 0, ns, neq);
+              ref_fe_hyb::computeLocalConvectiveFluxInZDirectionFromPrimitiveVariablesHLLC_HLL3D(F2, VL, VR, &rho_L, &rho_R, &c_L, &c_R, &eps_L, &eps_R, s_minus2, s_plus2, s_star2, Chi2, 0, 0, ns, neq); break;
+    default: return -1;
+    }
+    for (int e = 0; e < neq; e++) { F_HLLC[e] = f1[e]; F_HYB[e] = f2[e]; }
+    const int iun = (model == 0 ? 1 : ns) + dir;
+    if (s_star > double(0)) *vel_mid = vl[iun] + s_minus*(Chi - double(1));
+    else                    *vel_mid = vr[iun] + s_plus*(Chi - double(1));
+    return 0;
+}
+
+}
+"""
+
+
+def main() -> int:
+    if not os.path.isdir(REF):
+        print(f"[build_ref] {REF} not present: keeping any prebuilt oracle/_ref/libhamers_ref.so")
+        return 0
+    os.makedirs(OUT, exist_ok=True)
+    parts = ["#include <cmath>\n#include <algorithm>\n#define HAMERS_EPSILON 1.0e-15\n#define EPSILON HAMERS_EPSILON\n"]
+    for ns, rel in SOURCES.items():
+        with open(os.path.join(REF, rel)) as fh:
+            body = static_inline_functions(fh.read())
+        parts.append(f"namespace {ns} {{\n{body}\n}}\n")
+    parts.append(WRAPPERS)
+    gen = os.path.join(OUT, "_generated_ref_kernels.cpp")
+    with open(gen, "w") as fh:
+        fh.write("\n".join(parts))
+    so = os.path.join(OUT, "libhamers_ref.so")
+    cmd = ["g++", "-std=c++11", "-O3", "-Wno-deprecated", "-Wno-unused-function", "-fPIC", "-shared", "-o", so, gen]
+    try:
+        subprocess.check_call(cmd)
+    finally:
+        os.remove(gen)   # reference text never stays on disk outside /root/reference
+    print(f"[build_ref] built {so}")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

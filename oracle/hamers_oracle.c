@@ -1,0 +1,845 @@
+/*
+ * hamers_oracle.c -- CPU ORACLE (test infrastructure, NOT a product path).
+ * See hamers_oracle.h for scope and parity status.  Citations: path:line under
+ * /root/reference.  Arithmetic is written in the reference's association order;
+ * compile WITHOUT -ffast-math and without FMA contraction (-ffp-contract=off).
+ *
+ * Organisation mirrors the reference: full-array passes over freshly allocated
+ * temporaries (cell stage -> sensor -> per direction: projection, 6x characteristic
+ * transform, WENO, back-projection, bounds flags, fallback, HLLC, HLLC-HLL, sensor
+ * select -> face flux -> source), so that timing it is a fair stand-in for the
+ * reference's CPU cost structure.
+ */
+#include "hamers_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define EPSILON 1.0e-15   /* HAMERS_EPSILON, include/HAMeRS_config.hpp.in:16 */
+#define G ORC_GHOSTS
+
+int orc_num_eqn(const orc_desc* d)
+{
+    return d->model == ORC_SINGLE_SPECIES ? d->dim + 2 : d->dim + 2 * d->ns;
+}
+int orc_num_comp(const orc_desc* d)
+{
+    return d->model == ORC_SINGLE_SPECIES ? d->dim + 2 : d->dim + 2 * d->ns + 1;
+}
+static int nz_of(const orc_desc* d) { return d->dim == 3 ? d->n[2] : 1; }
+static int gz_of(const orc_desc* d) { return d->dim == 3 ? G : 0; }
+long orc_cell_ghost_size(const orc_desc* d)
+{
+    return (long)(d->n[0] + 2 * G) * (d->n[1] + 2 * G) * (nz_of(d) + 2 * gz_of(d));
+}
+long orc_cell_size(const orc_desc* d) { return (long)d->n[0] * d->n[1] * nz_of(d); }
+long orc_side_size(const orc_desc* d, int dir)
+{
+    long e[3] = {d->n[0], d->n[1], nz_of(d)};
+    e[dir] += 1;
+    return e[0] * e[1] * e[2];
+}
+
+/* ------------------------------------------------------------------------- */
+/* Point kernels                                                              */
+/* ------------------------------------------------------------------------- */
+
+/* ConvectiveFluxReconstructorWCNS5-JS-HLLC-HLL.cpp:9-18 */
+static inline double ipow_(double base, int e)
+{
+    double r = base;
+    for (int i = 1; i < e; i++) r *= base;
+    return r;
+}
+
+/* One-sided WCNS5-JS midpoint interpolation from (a,b,c,d,e) towards the face between c and d.
+ * beta: WCNS5-JS-HLLC-HLL.cpp:31-44 (mirror :58-71); weights :98-106; value :112-117. */
+static inline double weno5js_side(double a, double b, double c, double d, double e, int p)
+{
+    const double beta_0 = 1.0 / 3.0 * (a * (4.0 * a - 19.0 * b + 11.0 * c) + b * (25.0 * b - 31.0 * c) + 10.0 * c * c);
+    const double beta_1 = 1.0 / 3.0 * (b * (4.0 * b - 13.0 * c + 5.0 * d) + 13.0 * c * (c - d) + 4.0 * d * d);
+    const double beta_2 = 1.0 / 3.0 * (c * (10.0 * c - 31.0 * d + 11.0 * e) + d * (25.0 * d - 19.0 * e) + 4.0 * e * e);
+
+    double omega_0 = 1.0 / 16.0 / ipow_(beta_0 + EPSILON, p);
+    double omega_1 = 5.0 / 8.0 / ipow_(beta_1 + EPSILON, p);
+    double omega_2 = 5.0 / 16.0 / ipow_(beta_2 + EPSILON, p);
+
+    const double omega_sum = omega_0 + omega_1 + omega_2;
+    omega_0 = omega_0 / omega_sum;
+    omega_1 = omega_1 / omega_sum;
+    omega_2 = omega_2 / omega_sum;
+
+    return 3.0 / 8.0 * omega_0 * a +
+           (-10.0 / 8.0 * omega_0 - 1.0 / 8.0 * omega_1) * b +
+           (15.0 / 8.0 * omega_0 + 6.0 / 8.0 * omega_1 + 3.0 / 8.0 * omega_2) * c +
+           (3.0 / 8.0 * omega_1 + 6.0 / 8.0 * omega_2) * d -
+           1.0 / 8.0 * omega_2 * e;
+}
+
+void orc_weno5js_point(const double U[6], int p, double* U_minus, double* U_plus)
+{
+    /* minus: cells 0..4 (:78-118); plus: mirror image, cells 5..1 (:124-164) */
+    *U_minus = weno5js_side(U[0], U[1], U[2], U[3], U[4], p);
+    *U_plus = weno5js_side(U[5], U[4], U[3], U[2], U[1], p);
+}
+
+/* Side thermodynamics fed to the Riemann point kernels.
+ * single-species: EquationOfStateIdealGas.cpp:5909 (c), :6238 (epsilon), called from
+ *   FlowModelRiemannSolverSingleSpeciesHLLC.cpp:2991-3025.
+ * five-eqn: FlowModelRiemannSolverFiveEqnAllaireHLLC.cpp:5640-5970: rho = sum Z_rho, Y = Z_rho/rho,
+ *   mixture gamma from the ns-1 interpolated volume fractions
+ *   (EquationOfStateMixingRulesIdealGas.cpp:7599-7832, Z_last = 1 - sum Z_i, fill :5377-5576),
+ *   Gamma = gamma-1 (EquationOfStateIdealGas.cpp:8157), Psi_i = p/rho
+ *   (EquationOfStateMixingRulesIdealGas.cpp:6736), epsilon = p/((gamma-1)*rho) (:6414). */
+static inline void side_thermo(int model, int dim, int ns, const double* gamma, const double* V,
+                               double* rho_o, double* c_o, double* eps_o)
+{
+    if (model == ORC_SINGLE_SPECIES) {
+        const double rho = V[0];
+        const double p = V[dim + 1];
+        *rho_o = rho;
+        *c_o = sqrt(gamma[0] * p / rho);
+        *eps_o = p / ((gamma[0] - 1.0) * rho);
+    } else {
+        double rho = 0.0;
+        for (int si = 0; si < ns; si++) rho += V[si];
+        const double p = V[ns + dim];
+        double Y[ORC_MAX_SPECIES];
+        for (int si = 0; si < ns; si++) Y[si] = V[si] / rho;
+        double xi = 0.0, Z_last = 1.0;
+        for (int si = 0; si < ns - 1; si++) {
+            const double one_over_denominator = 1.0 / (gamma[si] - 1.0);
+            xi += V[ns + dim + 1 + si] * one_over_denominator;
+            Z_last -= V[ns + dim + 1 + si];
+        }
+        xi += Z_last / (gamma[ns - 1] - 1.0);
+        const double gamma_m = 1.0 / xi + 1.0;
+        const double Gamma = gamma_m - 1.0;
+        double c = Gamma * p / rho;
+        for (int si = 0; si < ns; si++) c += Y[si] * (p / rho);
+        *rho_o = rho;
+        *c_o = sqrt(c);
+        *eps_o = p / ((gamma_m - 1.0) * rho);
+    }
+}
+
+/* HLLC and HLLC-HLL point kernels, generic in direction `dir` and dimension.
+ * single-species: FlowModelRiemannSolverSingleSpeciesHLLC.cpp:604-1074,
+ *                 FlowModelRiemannSolverSingleSpeciesHLLC-HLL.cpp:889-1629;
+ * five-eqn:       FlowModelRiemannSolverFiveEqnAllaireHLLC.cpp:848-1591,
+ *                 FlowModelRiemannSolverFiveEqnAllaireHLLC-HLL.cpp:1283-2440.
+ * The HLLC part of the hybrid kernel is the same arithmetic as the pure HLLC kernel, so it
+ * is evaluated once.  vel_mid: HLLC.cpp:3381-3388 / FiveEqnAllaireHLLC.cpp:6034-6038. */
+static inline void riemann_kernel(int model, int dim, int ns, int dir,
+                                  const double* V_L, const double* V_R,
+                                  double rho_L, double rho_R, double c_L, double c_R,
+                                  double eps_L, double eps_R,
+                                  double* F_HLLC, double* F_HLLC_HLL, double* vel_mid)
+{
+    const int neq = (model == ORC_SINGLE_SPECIES) ? dim + 2 : dim + 2 * ns;
+    const int nm = (model == ORC_SINGLE_SPECIES) ? 1 : ns;     /* number of mass equations */
+    const int iv = nm;                                         /* first velocity index in V */
+    const int ip = nm + dim;                                   /* pressure index in V / energy in Q */
+
+    const double un_L = V_L[iv + dir];
+    const double un_R = V_R[iv + dir];
+    const double p_L = V_L[ip];
+    const double p_R = V_R[ip];
+
+    const double u_average = 1.0 / 2.0 * (un_L + un_R);
+    const double c_average = 1.0 / 2.0 * (c_L + c_R);
+
+    const double s_L = fmin(u_average - c_average, un_L - c_L);
+    const double s_R = fmax(u_average + c_average, un_R + c_R);
+
+    const double s_minus = fmin(0.0, s_L);
+    const double s_plus = fmax(0.0, s_R);
+
+    const double s_star = (p_R - p_L + rho_L * un_L * (s_L - un_L) - rho_R * un_R * (s_R - un_R)) /
+                          (rho_L * (s_L - un_L) - rho_R * (s_R - un_R));
+
+    double Q_L[ORC_MAX_EQ], Q_R[ORC_MAX_EQ], F_L[ORC_MAX_EQ], F_R[ORC_MAX_EQ];
+
+    /* conservative states and physical fluxes of both sides */
+    for (int side = 0; side < 2; side++) {
+        const double* V = side == 0 ? V_L : V_R;
+        double* Q = side == 0 ? Q_L : Q_R;
+        double* F = side == 0 ? F_L : F_R;
+        const double rho = side == 0 ? rho_L : rho_R;
+        const double eps = side == 0 ? eps_L : eps_R;
+        const double un = V[iv + dir];
+        const double p = V[ip];
+
+        double ke = V[iv] * V[iv];
+        for (int a = 1; a < dim; a++) ke = ke + V[iv + a] * V[iv + a];
+
+        if (model == ORC_SINGLE_SPECIES) {
+            Q[0] = V[0];
+            for (int a = 0; a < dim; a++) Q[1 + a] = V[0] * V[1 + a];
+            Q[ip] = V[0] * (eps + 1.0 / 2.0 * ke);
+
+            F[0] = Q[1 + dir];
+            for (int a = 0; a < dim; a++)
+                F[1 + a] = (a == dir) ? Q[1 + dir] * V[1 + a] + p : Q[1 + dir] * V[1 + a];
+            F[ip] = un * (Q[ip] + p);
+        } else {
+            for (int si = 0; si < ns; si++) Q[si] = V[si];
+            for (int a = 0; a < dim; a++) Q[iv + a] = rho * V[iv + a];
+            Q[ip] = rho * (eps + 1.0 / 2.0 * ke);
+            for (int si = 0; si < ns - 1; si++) Q[ip + 1 + si] = V[ip + 1 + si];
+
+            for (int si = 0; si < ns; si++) F[si] = un * V[si];
+            for (int a = 0; a < dim; a++)
+                F[iv + a] = (a == dir) ? un * Q[iv + a] + p : un * Q[iv + a];
+            F[ip] = un * (Q[ip] + p);
+            for (int si = 0; si < ns - 1; si++) F[ip + 1 + si] = un * V[ip + 1 + si];
+        }
+    }
+
+    /* HLLC */
+    double Chi_star;
+    {
+        const int left = (s_star > 0.0);
+        const double* V = left ? V_L : V_R;
+        const double* Q = left ? Q_L : Q_R;
+        const double* F = left ? F_L : F_R;
+        const double rho = left ? rho_L : rho_R;
+        const double s_K = left ? s_L : s_R;
+        const double s_mp = left ? s_minus : s_plus;
+        const double un = V[iv + dir];
+        const double p = V[ip];
+
+        Chi_star = (s_K - un) / (s_K - s_star);
+
+        double Q_star[ORC_MAX_EQ];
+        for (int si = 0; si < nm; si++) Q_star[si] = Chi_star * V[si];
+        for (int a = 0; a < dim; a++)
+            Q_star[iv + a] = (a == dir) ? Chi_star * rho * s_star : Chi_star * Q[iv + a];
+        Q_star[ip] = Chi_star * (Q[ip] + (s_star - un) * (rho * s_star + p / (s_K - un)));
+        for (int e = ip + 1; e < neq; e++) Q_star[e] = Chi_star * V[e];
+
+        for (int e = 0; e < neq; e++) F_HLLC[e] = F[e] + s_mp * (Q_star[e] - Q[e]);
+
+        if (vel_mid) *vel_mid = un + s_mp * (Chi_star - 1.0);
+    }
+
+    if (!F_HLLC_HLL) return;
+
+    /* HLL for mass, tangential momenta and volume fractions; upwind overrides */
+    double F_HLL[ORC_MAX_EQ];
+    for (int e = 0; e < neq; e++) {
+        const int is_normal_mom = (e == iv + dir);
+        const int is_energy = (e == ip);
+        if (is_normal_mom || is_energy) continue;
+        F_HLL[e] = (s_R * F_L[e] - s_L * F_R[e] + s_R * s_L * (Q_R[e] - Q_L[e])) / (s_R - s_L);
+        if (s_L > 0.0) F_HLL[e] = F_L[e];
+        if (s_R < 0.0) F_HLL[e] = F_R[e];
+    }
+
+    /* weights for hybridisation */
+    double diff[3] = {0.0, 0.0, 0.0};
+    for (int a = 0; a < dim; a++) diff[a] = V_R[iv + a] - V_L[iv + a];
+    double mag2 = diff[0] * diff[0];
+    for (int a = 1; a < dim; a++) mag2 = mag2 + diff[a] * diff[a];
+    const double vel_mag = sqrt(mag2);
+
+    double alpha_1, alpha_2;
+    if (vel_mag < EPSILON) {
+        alpha_1 = 1.0;
+        alpha_2 = 0.0;
+    } else {
+        alpha_1 = fabs(diff[dir]) / vel_mag;
+        alpha_2 = sqrt(1.0 - alpha_1 * alpha_1);
+    }
+    const double beta_1 = 1.0 / 2.0 * (1.0 + alpha_1 / (alpha_1 + alpha_2));
+    const double beta_2 = 1.0 - beta_1;
+
+    for (int e = 0; e < neq; e++) {
+        if (e == iv + dir || e == ip)
+            F_HLLC_HLL[e] = F_HLLC[e];
+        else
+            F_HLLC_HLL[e] = beta_1 * F_HLLC[e] + beta_2 * F_HLL[e];
+    }
+}
+
+void orc_riemann_point(int model, int dim, int ns, const double* gamma, int dir,
+                       const double* V_L, const double* V_R,
+                       double* F_HLLC, double* F_HLLC_HLL, double* vel_mid)
+{
+    double rho_L, rho_R, c_L, c_R, e_L, e_R;
+    side_thermo(model, dim, ns, gamma, V_L, &rho_L, &c_L, &e_L);
+    side_thermo(model, dim, ns, gamma, V_R, &rho_R, &c_R, &e_R);
+    riemann_kernel(model, dim, ns, dir, V_L, V_R, rho_L, rho_R, c_L, c_R, e_L, e_R,
+                   F_HLLC, F_HLLC_HLL, vel_mid);
+}
+
+/* Exposed so that tests can feed identical (rho, c, epsilon) to the reference's point kernels. */
+void orc_side_thermo(int model, int dim, int ns, const double* gamma, const double* V,
+                     double* rho, double* c, double* eps)
+{
+    side_thermo(model, dim, ns, gamma, V, rho, c, eps);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Patch-level passes                                                         */
+/* ------------------------------------------------------------------------- */
+
+typedef struct {
+    int dim, neq, ncomp, ns, model, nm;
+    int n[3], g[3], gd[3];          /* interior dims, ghost widths, ghost-box dims */
+    long cs[3];                     /* cell strides in the ghost box */
+    long ncell_g;
+} geom_t;
+
+static void make_geom(const orc_desc* d, geom_t* q)
+{
+    q->dim = d->dim;
+    q->model = d->model;
+    q->ns = d->model == ORC_SINGLE_SPECIES ? 1 : d->ns;
+    q->nm = q->ns;
+    q->neq = orc_num_eqn(d);
+    q->ncomp = orc_num_comp(d);
+    for (int a = 0; a < 3; a++) {
+        q->n[a] = (a < d->dim) ? d->n[a] : 1;
+        q->g[a] = (a < d->dim) ? G : 0;
+        q->gd[a] = q->n[a] + 2 * q->g[a];
+    }
+    q->cs[0] = 1;
+    q->cs[1] = q->gd[0];
+    q->cs[2] = (long)q->gd[0] * q->gd[1];
+    q->ncell_g = (long)q->gd[0] * q->gd[1] * q->gd[2];
+}
+
+/* linear index in the ghost box of logical cell (i,j,k), interior origin 0
+ * (FlowModelSingleSpecies.cpp:2815-2817) */
+static inline long cidx(const geom_t* q, int i, int j, int k)
+{
+    return (i + q->g[0]) + (long)(j + q->g[1]) * q->cs[1] + (long)(k + q->g[2]) * q->cs[2];
+}
+
+static double* dalloc(long n)
+{
+    double* p = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    return p;
+}
+
+/* Derived cell data on the whole ghost box.
+ * single-species: FlowModelSingleSpecies.cpp:2824-2826 (velocity), :3049-3051 (epsilon),
+ *   EquationOfStateIdealGas.cpp:5580 (p), :5909 (c).
+ * five-eqn: EquationOfStateMixingRules.cpp:735-900 (rho), FlowModelFiveEqnAllaire.cpp:3965 (Y),
+ *   :4428-4430 (epsilon), EquationOfStateMixingRulesIdealGas.cpp:7520-7587 (gamma_m from ALL ns
+ *   stored volume fractions), EquationOfStateIdealGas.cpp:5756 (p), FlowModelFiveEqnAllaire.cpp:4779-4853 (c). */
+static void cell_stage(const geom_t* q, const double* gam, const double* const* Q,
+                       double** vel, double* p, double* c, double* rho_m)
+{
+    const int dim = q->dim, ns = q->ns;
+    for (long x = 0; x < q->ncell_g; x++) {
+        if (q->model == ORC_SINGLE_SPECIES) {
+            const double rho = Q[0][x];
+            double ke = 0.0;
+            for (int a = 0; a < dim; a++) {
+                vel[a][x] = Q[1 + a][x] / rho;
+                ke = (a == 0) ? vel[a][x] * vel[a][x] : ke + vel[a][x] * vel[a][x];
+            }
+            const double epsilon = Q[dim + 1][x] / rho - 1.0 / 2.0 * ke;
+            p[x] = (gam[0] - 1.0) * rho * epsilon;
+            c[x] = sqrt(gam[0] * p[x] / rho);
+        } else {
+            double rho = 0.0;
+            for (int si = 0; si < ns; si++) rho += Q[si][x];
+            rho_m[x] = rho;
+            double Y[ORC_MAX_SPECIES];
+            for (int si = 0; si < ns; si++) Y[si] = Q[si][x] / rho;
+            double ke = 0.0;
+            for (int a = 0; a < dim; a++) {
+                vel[a][x] = Q[ns + a][x] / rho;
+                ke = (a == 0) ? vel[a][x] * vel[a][x] : ke + vel[a][x] * vel[a][x];
+            }
+            const double epsilon = Q[ns + dim][x] / rho - 1.0 / 2.0 * ke;
+            double xi = 0.0;
+            for (int si = 0; si < ns; si++) {
+                const double one_over_denominator = 1.0 / (gam[si] - 1.0);
+                xi += Q[ns + dim + 1 + si][x] * one_over_denominator;
+            }
+            const double gamma_m = 1.0 / xi + 1.0;
+            p[x] = (gamma_m - 1.0) * rho * epsilon;
+            const double Gamma = gamma_m - 1.0;
+            double cc = Gamma * p[x] / rho;
+            for (int si = 0; si < ns; si++) cc += Y[si] * (p[x] / rho);
+            c[x] = sqrt(cc);
+        }
+    }
+}
+
+/* node flux in direction dir at ghost-box cell x, equation e.
+ * single-species: FlowModelSingleSpecies.cpp:3388-3391, 3470-3474, 3611-3614, 3693-3697, 3856-3860;
+ * five-eqn: FlowModelFiveEqnAllaire.cpp:5206-5275, 5434-5482, 5559-5628, 5806-5875. */
+static inline double node_flux(const geom_t* q, const double* const* Q, double* const* vel,
+                               const double* p, int dir, int e, long x)
+{
+    const int dim = q->dim, ns = q->ns;
+    const double un = vel[dir][x];
+    if (q->model == ORC_SINGLE_SPECIES) {
+        if (e == 0) return Q[1 + dir][x];
+        if (e <= dim) return (e - 1 == dir) ? un * Q[e][x] + p[x] : un * Q[e][x];
+        return un * (Q[dim + 1][x] + p[x]);
+    } else {
+        if (e < ns) return un * Q[e][x];
+        if (e < ns + dim) return (e - ns == dir) ? un * Q[e][x] + p[x] : un * Q[e][x];
+        if (e == ns + dim) return un * (Q[e][x] + p[x]);
+        return un * Q[e][x];   /* volume fraction, e = ns+dim+1+si maps to stored Z_si */
+    }
+}
+
+int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, double dt,
+                                double* const* F, double* const* S,
+                                double* const* F_mid_dbg, double* const* sensor_dbg)
+{
+    geom_t qq;
+    make_geom(d, &qq);
+    const geom_t* q = &qq;
+    const int dim = q->dim, neq = q->neq, ns = q->ns, nm = q->nm;
+    const int iv = nm, ip = nm + dim;
+    const int p_exp = d->weno_p > 0 ? d->weno_p : 2;
+    const int has_adv = (q->model == ORC_FIVE_EQN_ALLAIRE);
+
+    /* ---- step 1: derived cell data (WCNS56-HLLC-HLL.cpp:1392-1410) ---- */
+    double* vel[3] = {0, 0, 0};
+    for (int a = 0; a < dim; a++) vel[a] = dalloc(q->ncell_g);
+    double* p = dalloc(q->ncell_g);
+    double* c = dalloc(q->ncell_g);
+    double* rho_m = has_adv ? dalloc(q->ncell_g) : 0;
+    cell_stage(q, d->gamma, Q, vel, p, c, rho_m);
+
+    /* primitive variable pointers (FlowModelSingleSpecies / FiveEqnAllaire getCellDataOfPrimitiveVariables) */
+    const double* V[ORC_MAX_EQ];
+    if (q->model == ORC_SINGLE_SPECIES) {
+        V[0] = Q[0];
+        for (int a = 0; a < dim; a++) V[1 + a] = vel[a];
+        V[dim + 1] = p;
+    } else {
+        for (int si = 0; si < ns; si++) V[si] = Q[si];
+        for (int a = 0; a < dim; a++) V[ns + a] = vel[a];
+        V[ns + dim] = p;
+        for (int si = 0; si < ns - 1; si++) V[ns + dim + 1 + si] = Q[ns + dim + 1 + si];
+    }
+    const double* rho_cell = has_adv ? rho_m : Q[0];
+
+    /* ---- step 2: velocity gradient, dilatation, vorticity (:1523-1659; 2D :663-731) ----
+     * arrays with 2 ghosts; derivative (1/2*(uR-uL))/dx, DerivativeFirstOrder.cpp:382,601 */
+    int g2[3], d2[3];
+    for (int a = 0; a < 3; a++) {
+        g2[a] = (a < dim) ? 2 : 0;
+        d2[a] = q->n[a] + 2 * g2[a];
+    }
+    const long n2 = (long)d2[0] * d2[1] * d2[2];
+    double* grad[9];
+    for (int m = 0; m < dim * dim; m++) grad[m] = dalloc(n2);
+    double* theta = dalloc(n2);
+    double* Omega = dalloc(n2);
+#define IDX2(i, j, k) ((i + g2[0]) + (long)(j + g2[1]) * d2[0] + (long)(k + g2[2]) * d2[0] * d2[1])
+    for (int a = 0; a < dim; a++) {
+        for (int b = 0; b < dim; b++) {
+            double* out = grad[dim * a + b];
+            for (int k = -g2[2]; k < q->n[2] + g2[2]; k++)
+                for (int j = -g2[1]; j < q->n[1] + g2[1]; j++)
+                    for (int i = -g2[0]; i < q->n[0] + g2[0]; i++) {
+                        const long x = cidx(q, i, j, k);
+                        out[IDX2(i, j, k)] = (1.0 / 2.0 * (vel[a][x + q->cs[b]] - vel[a][x - q->cs[b]])) / d->dx[b];
+                    }
+        }
+    }
+    for (long x = 0; x < n2; x++) {
+        if (dim == 2) {
+            theta[x] = grad[0][x] + grad[3][x];
+            Omega[x] = fabs(grad[2][x] - grad[1][x]);
+        } else {
+            theta[x] = grad[0][x] + grad[4][x] + grad[8][x];
+            const double omega_x = grad[7][x] - grad[5][x];
+            const double omega_y = grad[2][x] - grad[6][x];
+            const double omega_z = grad[3][x] - grad[1][x];
+            Omega[x] = sqrt(omega_x * omega_x + omega_y * omega_y + omega_z * omega_z);
+        }
+    }
+
+    /* HLLC midpoint normal velocities of all directions are needed together by the source */
+    double* vel_midpoint[3] = {0, 0, 0};
+    double* F_midpoint_all[3][ORC_MAX_EQ];
+    long sd_all[3][3];
+
+    for (int dir = 0; dir < dim; dir++) {
+        /* side arrays: faces -1..N+1 in the normal direction, interior tangentially */
+        long sd[3] = {q->n[0], q->n[1], q->n[2]};
+        sd[dir] += 3;
+        for (int a = 0; a < 3; a++) sd_all[dir][a] = sd[a];
+        const long nside = sd[0] * sd[1] * sd[2];
+        const long st = q->cs[dir];
+#define SIDX(i, j, k) ((i + (dir == 0)) + sd[0] * ((long)(j + (dir == 1)) + sd[1] * (long)(k + (dir == 2))))
+        const int lo[3] = {dir == 0 ? -1 : 0, dir == 1 ? -1 : 0, dir == 2 ? -1 : 0};
+        const int hi[3] = {q->n[0] + (dir == 0 ? 2 : 0), q->n[1] + (dir == 1 ? 2 : 0), q->n[2] + (dir == 2 ? 2 : 0)};
+#define FOR_FACES                                        \
+    for (int k = lo[2]; k < hi[2]; k++)                   \
+        for (int j = lo[1]; j < hi[1]; j++)               \
+            for (int i = lo[0]; i < hi[0]; i++)
+
+        /* ---- step 3: projection variables (SS :5000-5001; 5eq :7952,7995-7996) ---- */
+        double* Zrho_avg[ORC_MAX_SPECIES];
+        for (int si = 0; si < ns; si++) Zrho_avg[si] = has_adv ? dalloc(nside) : 0;
+        double* rho_avg = dalloc(nside);
+        double* c_avg = dalloc(nside);
+        FOR_FACES
+        {
+            const long xR = cidx(q, i, j, k), xL = xR - st, s = SIDX(i, j, k);
+            if (has_adv)
+                for (int si = 0; si < ns; si++) Zrho_avg[si][s] = 1.0 / 2.0 * (Q[si][xL] + Q[si][xR]);
+            rho_avg[s] = 1.0 / 2.0 * (rho_cell[xL] + rho_cell[xR]);
+            c_avg[s] = 1.0 / 2.0 * (c[xL] + c[xR]);
+        }
+
+        /* ---- step 4: characteristic variables of the six stencil cells (:1814-1822) ----
+         * SS: BasicUtilitiesSingleSpecies.cpp:6194-6198, 6237-6241, 6324-6329, 6379-6384, 6434-6439
+         * 5eq: BasicUtilitiesFiveEqnAllaire.cpp:8835-8921 (x) and the y/z permutations */
+        double* W[6][ORC_MAX_EQ];
+        for (int m = 0; m < 6; m++)
+            for (int e = 0; e < neq; e++) W[m][e] = dalloc(nside);
+        for (int m = 0; m < 6; m++) {
+            const long off = (long)(m - 3) * st;
+            FOR_FACES
+            {
+                const long x = cidx(q, i, j, k) + off, s = SIDX(i, j, k);
+                if (q->model == ORC_SINGLE_SPECIES) {
+                    W[m][0][s] = -1.0 / 2.0 * rho_avg[s] * c_avg[s] * V[1 + dir][x] + 1.0 / 2.0 * V[dim + 1][x];
+                    W[m][1][s] = V[0][x] - 1.0 / (c_avg[s] * c_avg[s]) * V[dim + 1][x];
+                    int w = 2;
+                    for (int a = 0; a < dim; a++)
+                        if (a != dir) W[m][w++][s] = V[1 + a][x];
+                    W[m][dim + 1][s] = 1.0 / 2.0 * rho_avg[s] * c_avg[s] * V[1 + dir][x] + 1.0 / 2.0 * V[dim + 1][x];
+                } else {
+                    W[m][0][s] = V[iv + dir][x] - 1.0 / (rho_avg[s] * c_avg[s]) * V[ip][x];
+                    for (int si = 0; si < ns; si++)
+                        W[m][1 + si][s] = V[si][x] - Zrho_avg[si][s] / (rho_avg[s] * c_avg[s] * c_avg[s]) * V[ip][x];
+                    int w = ns + 1;
+                    for (int a = 0; a < dim; a++)
+                        if (a != dir) W[m][w++][s] = V[iv + a][x];
+                    for (int si = 0; si < ns - 1; si++) W[m][ns + dim + si][s] = V[ip + 1 + si][x];
+                    W[m][neq - 1][s] = V[iv + dir][x] + 1.0 / (rho_avg[s] * c_avg[s]) * V[ip][x];
+                }
+            }
+        }
+
+        /* ---- step 5: WCNS5-JS interpolation (WCNS5-JS-HLLC-HLL.cpp:492-736) ---- */
+        double *W_minus[ORC_MAX_EQ], *W_plus[ORC_MAX_EQ], *V_minus[ORC_MAX_EQ], *V_plus[ORC_MAX_EQ];
+        for (int e = 0; e < neq; e++) {
+            W_minus[e] = dalloc(nside);
+            W_plus[e] = dalloc(nside);
+            V_minus[e] = dalloc(nside);
+            V_plus[e] = dalloc(nside);
+        }
+        for (int e = 0; e < neq; e++) {
+            FOR_FACES
+            {
+                const long s = SIDX(i, j, k);
+                double U[6];
+                for (int m = 0; m < 6; m++) U[m] = W[m][e][s];
+                orc_weno5js_point(U, p_exp, &W_minus[e][s], &W_plus[e][s]);
+            }
+        }
+
+        /* ---- step 6: back-projection (SS :7279-7284, 7318-7323, 7373-7379, 7418-7424, 7463-7469;
+         *      5eq :9700-9703, 9751-9759 and permutations) ---- */
+        for (int side = 0; side < 2; side++) {
+            double** Wc = side == 0 ? W_minus : W_plus;
+            double** Vs = side == 0 ? V_minus : V_plus;
+            FOR_FACES
+            {
+                const long s = SIDX(i, j, k);
+                if (q->model == ORC_SINGLE_SPECIES) {
+                    Vs[0][s] = 1.0 / (c_avg[s] * c_avg[s]) * Wc[0][s] + Wc[1][s] + 1.0 / (c_avg[s] * c_avg[s]) * Wc[dim + 1][s];
+                    int w = 2;
+                    for (int a = 0; a < dim; a++) {
+                        if (a == dir)
+                            Vs[1 + a][s] = -1.0 / (rho_avg[s] * c_avg[s]) * Wc[0][s] + 1.0 / (rho_avg[s] * c_avg[s]) * Wc[dim + 1][s];
+                        else
+                            Vs[1 + a][s] = Wc[w++][s];
+                    }
+                    Vs[dim + 1][s] = Wc[0][s] + Wc[dim + 1][s];
+                } else {
+                    for (int si = 0; si < ns; si++)
+                        Vs[si][s] = -1.0 / 2.0 * Zrho_avg[si][s] / c_avg[s] * Wc[0][s] + Wc[si + 1][s] +
+                                    1.0 / 2.0 * Zrho_avg[si][s] / c_avg[s] * Wc[neq - 1][s];
+                    int w = ns + 1;
+                    for (int a = 0; a < dim; a++) {
+                        if (a == dir)
+                            Vs[iv + a][s] = 1.0 / 2.0 * Wc[0][s] + 1.0 / 2.0 * Wc[neq - 1][s];
+                        else
+                            Vs[iv + a][s] = Wc[w++][s];
+                    }
+                    Vs[ip][s] = -1.0 / 2.0 * rho_avg[s] * c_avg[s] * Wc[0][s] + 1.0 / 2.0 * rho_avg[s] * c_avg[s] * Wc[neq - 1][s];
+                    for (int si = 0; si < ns - 1; si++) Vs[ip + 1 + si][s] = Wc[ns + dim + si][s];
+                }
+            }
+        }
+
+        /* ---- step 7: bounds flags (SS BasicUtilitiesSingleSpecies.cpp:3013-3433: rho>0 && p>0;
+         *      5eq BasicUtilitiesFiveEqnAllaire.cpp:5446-7340) ---- */
+        int* flag[2];
+        for (int side = 0; side < 2; side++) {
+            flag[side] = (int*)malloc(sizeof(int) * (size_t)nside);
+            double** Vs = side == 0 ? V_minus : V_plus;
+            FOR_FACES
+            {
+                const long s = SIDX(i, j, k);
+                int ok = 1;
+                if (q->model == ORC_SINGLE_SPECIES) {
+                    ok &= (Vs[0][s] > 0.0) ? 1 : 0;
+                    ok &= (Vs[neq - 1][s] > 0.0) ? 1 : 0;
+                } else {
+                    const double Z_lo = -1000.0, Z_up = 1000.0, Y_lo = -0.001, Y_up = 1.001;
+                    double Z[ORC_MAX_SPECIES];
+                    Z[ns - 1] = 1.0;
+                    for (int si = 0; si < ns - 1; si++) {
+                        Z[si] = Vs[ns + dim + 1 + si][s];
+                        Z[ns - 1] -= Z[si];
+                        ok &= (Z[si] > Z_lo && Z[si] < Z_up) ? 1 : 0;
+                    }
+                    ok &= (Z[ns - 1] > Z_lo && Z[ns - 1] < Z_up) ? 1 : 0;
+                    double rho = 0.0;
+                    for (int si = 0; si < ns; si++) rho += Vs[si][s];
+                    double Y[ORC_MAX_SPECIES];
+                    for (int si = 0; si < ns; si++) {
+                        Y[si] = Vs[si][s] / rho;
+                        ok &= (Y[si] > Y_lo && Y[si] < Y_up) ? 1 : 0;
+                    }
+                    for (int si = 0; si < ns; si++) ok &= (Vs[si][s] > 0.0) ? 1 : 0;
+                    const double pp = Vs[ns + dim][s];
+                    /* Gruneisen parameter from the FULL set of ns volume fractions
+                     * (data_volume_fractions has depth ns here, :5560-5573) */
+                    double xi = 0.0;
+                    for (int si = 0; si < ns; si++) {
+                        const double one_over_denominator = 1.0 / (d->gamma[si] - 1.0);
+                        xi += Z[si] * one_over_denominator;
+                    }
+                    const double gamma_m = 1.0 / xi + 1.0;
+                    const double Gamma = gamma_m - 1.0;
+                    double c_sq = Gamma * pp / rho;
+                    for (int si = 0; si < ns; si++) c_sq += Y[si] * (pp / rho);
+                    ok &= (c_sq > 0.0) ? 1 : 0;
+                }
+                flag[side][s] = ok;
+            }
+        }
+
+        /* ---- step 8: first-order fallback (WCNS56-HLLC-HLL.cpp:1884-2039) ---- */
+        for (int e = 0; e < neq; e++) {
+            FOR_FACES
+            {
+                const long xR = cidx(q, i, j, k), xL = xR - st, s = SIDX(i, j, k);
+                if (flag[0][s] == 0 || flag[1][s] == 0) {
+                    V_minus[e][s] = V[e][xL];
+                    V_plus[e][s] = V[e][xR];
+                }
+            }
+        }
+
+        /* ---- step 9: HLLC (+ midpoint velocity) and HLLC-HLL (:2045-2070 etc.) ---- */
+        double *F_HLLC[ORC_MAX_EQ], *F_HYB[ORC_MAX_EQ], *F_midpoint[ORC_MAX_EQ];
+        for (int e = 0; e < neq; e++) {
+            F_HLLC[e] = dalloc(nside);
+            F_HYB[e] = dalloc(nside);
+            F_midpoint[e] = dalloc(nside);
+            F_midpoint_all[dir][e] = F_midpoint[e];
+        }
+        if (has_adv) vel_midpoint[dir] = dalloc(nside);
+        double* sensor = dalloc(nside);
+        FOR_FACES
+        {
+            const long s = SIDX(i, j, k);
+            double VL[ORC_MAX_EQ], VR[ORC_MAX_EQ], FH[ORC_MAX_EQ], FB[ORC_MAX_EQ], vm;
+            for (int e = 0; e < neq; e++) {
+                VL[e] = V_minus[e][s];
+                VR[e] = V_plus[e][s];
+            }
+            orc_riemann_point(q->model, dim, ns, d->gamma, dir, VL, VR, FH, FB, &vm);
+            for (int e = 0; e < neq; e++) {
+                F_HLLC[e][s] = FH[e];
+                F_HYB[e][s] = FB[e];
+            }
+            if (has_adv) vel_midpoint[dir][s] = vm;
+        }
+
+        /* ---- step 10: Ducros-like sensor and flux selection (:2072-2134, 2167-2229, 2262-2324) ---- */
+        FOR_FACES
+        {
+            const long s = SIDX(i, j, k);
+            const long xR2 = IDX2(i, j, k);
+            const long st2 = dir == 0 ? 1 : (dir == 1 ? d2[0] : (long)d2[0] * d2[1]);
+            const long xL2 = xR2 - st2;
+            const double theta_avg = 0.5 * (theta[xL2] + theta[xR2]);
+            const double Omega_avg = 0.5 * (Omega[xL2] + Omega[xR2]);
+            sensor[s] = -theta_avg / (fabs(theta_avg) + Omega_avg + EPSILON);
+        }
+        for (int e = 0; e < neq; e++) {
+            FOR_FACES
+            {
+                const long s = SIDX(i, j, k);
+                if (sensor[s] > 0.65)
+                    F_midpoint[e][s] = F_HYB[e][s];
+                else
+                    F_midpoint[e][s] = F_HLLC[e][s];
+            }
+        }
+        if (F_mid_dbg)
+            for (int e = 0; e < neq; e++)
+                if (F_mid_dbg[dir * neq + e]) memcpy(F_mid_dbg[dir * neq + e], F_midpoint[e], sizeof(double) * (size_t)nside);
+        if (sensor_dbg && sensor_dbg[dir]) memcpy(sensor_dbg[dir], sensor, sizeof(double) * (size_t)nside);
+
+        /* ---- step 11: face flux (:2330-2489) ---- */
+        {
+            long fd[3] = {q->n[0], q->n[1], q->n[2]};
+            fd[dir] += 1;
+            const long sst = dir == 0 ? 1 : (dir == 1 ? sd[0] : sd[0] * sd[1]);
+            const int fhi[3] = {q->n[0] + (dir == 0), q->n[1] + (dir == 1), q->n[2] + (dir == 2)};
+            for (int e = 0; e < neq; e++) {
+                double* F_face = F[dir * neq + e];
+                for (int k = 0; k < fhi[2]; k++)
+                    for (int j = 0; j < fhi[1]; j++)
+                        for (int i = 0; i < fhi[0]; i++) {
+                            const long f = i + fd[0] * ((long)j + fd[1] * (long)k);
+                            const long s = SIDX(i, j, k);
+                            const long xR = cidx(q, i, j, k), xL = xR - st;
+                            F_face[f] = dt * (1.0 / 30.0 * (F_midpoint[e][s + sst] + F_midpoint[e][s - sst]) -
+                                              3.0 / 10.0 * (node_flux(q, Q, vel, p, dir, e, xR) + node_flux(q, Q, vel, p, dir, e, xL)) +
+                                              23.0 / 15.0 * F_midpoint[e][s]);
+                        }
+            }
+        }
+
+        /* free per-direction temporaries except the midpoint velocity */
+        for (int si = 0; si < ns; si++) free(Zrho_avg[si]);
+        free(rho_avg);
+        free(c_avg);
+        for (int m = 0; m < 6; m++)
+            for (int e = 0; e < neq; e++) free(W[m][e]);
+        for (int e = 0; e < neq; e++) {
+            free(W_minus[e]);
+            free(W_plus[e]);
+            free(V_minus[e]);
+            free(V_plus[e]);
+            free(F_HLLC[e]);
+            free(F_HYB[e]);
+        }
+        free(flag[0]);
+        free(flag[1]);
+        free(sensor);
+#undef FOR_FACES
+#undef SIDX
+    }
+
+    /* ---- step 12: source of the ADVECTIVE equations (:2495-2647; 2D :1240-1369) ---- */
+    if (has_adv) {
+        for (int si = 0; si < ns - 1; si++) {
+            const int e = ns + dim + 1 + si;
+            double* Se = S[e];
+            for (int k = 0; k < q->n[2]; k++)
+                for (int j = 0; j < q->n[1]; j++)
+                    for (int i = 0; i < q->n[0]; i++) {
+                        const long x = cidx(q, i, j, k);
+                        const long xs = i + (long)q->n[0] * ((long)j + (long)q->n[1] * (long)k);
+                        double acc = 0.0;
+                        for (int dir = 0; dir < dim; dir++) {
+                            const long* sd = sd_all[dir];
+                            const long s = (i + (dir == 0)) + sd[0] * ((long)(j + (dir == 1)) + sd[1] * (long)(k + (dir == 2)));
+                            const long sst = dir == 0 ? 1 : (dir == 1 ? sd[0] : sd[0] * sd[1]);
+                            const double* um = vel_midpoint[dir];
+                            /* faces: s = face at the low side of the cell ("L"), s+sst = "R" */
+                            const double term = (3.0 / 2.0 * (um[s + sst] - um[s]) -
+                                                 3.0 / 10.0 * (vel[dir][x + q->cs[dir]] - vel[dir][x - q->cs[dir]]) +
+                                                 1.0 / 30.0 * (um[s + 2 * sst] - um[s - sst])) / d->dx[dir];
+                            acc = (dir == 0) ? term : acc + term;
+                        }
+                        Se[xs] += dt * Q[e][x] * acc;
+                    }
+        }
+    }
+
+    for (int dir = 0; dir < dim; dir++) {
+        for (int e = 0; e < neq; e++) free(F_midpoint_all[dir][e]);
+        free(vel_midpoint[dir]);
+    }
+    for (int m = 0; m < dim * dim; m++) free(grad[m]);
+    free(theta);
+    free(Omega);
+    for (int a = 0; a < dim; a++) free(vel[a]);
+    free(p);
+    free(c);
+    free(rho_m);
+#undef IDX2
+    return 0;
+}
+
+/* Euler::advanceSingleStepOnPatch, Euler.cpp:1003-1679 (3D body :1424-1655);
+ * FlowModelFiveEqnAllaire::updateCellDataOfConservativeVariables, FlowModelFiveEqnAllaire.cpp:1739-1886. */
+int orc_advance_stage(const orc_desc* d, int ncoef,
+                      const double* alpha, const double* beta,
+                      const double* const* const* U_int,
+                      const double* const* const* F_int,
+                      const double* const* const* S_int,
+                      double* const* U_out)
+{
+    geom_t qq;
+    make_geom(d, &qq);
+    const geom_t* q = &qq;
+    const int dim = q->dim, neq = q->neq, ns = q->ns;
+
+    /* fillCellDataOfConservativeVariablesWithZero (all components, whole ghost box) */
+    for (int cix = 0; cix < q->ncomp; cix++) memset(U_out[cix], 0, sizeof(double) * (size_t)q->ncell_g);
+
+    for (int n = 0; n < ncoef; n++) {
+        if (alpha[n] != 0.0) {
+            for (int e = 0; e < neq; e++)
+                for (int k = 0; k < q->n[2]; k++)
+                    for (int j = 0; j < q->n[1]; j++)
+                        for (int i = 0; i < q->n[0]; i++) {
+                            const long x = cidx(q, i, j, k);
+                            U_out[e][x] += alpha[n] * U_int[n][e][x];
+                        }
+        }
+        if (beta[n] != 0.0) {
+            for (int e = 0; e < neq; e++) {
+                const double* Fx = F_int[n][0 * neq + e];
+                const double* Fy = F_int[n][1 * neq + e];
+                const double* Fz = dim == 3 ? F_int[n][2 * neq + e] : 0;
+                const double* Sn = S_int[n][e];
+                const long nx = q->n[0], ny = q->n[1];
+                for (int k = 0; k < q->n[2]; k++)
+                    for (int j = 0; j < q->n[1]; j++)
+                        for (int i = 0; i < q->n[0]; i++) {
+                            const long x = cidx(q, i, j, k);
+                            const long xs = i + nx * ((long)j + ny * (long)k);
+                            const long fxL = i + (nx + 1) * ((long)j + ny * (long)k);
+                            const long fyB = i + nx * ((long)j + (ny + 1) * (long)k);
+                            if (dim == 2) {
+                                U_out[e][x] += beta[n] * (-(Fx[fxL + 1] - Fx[fxL]) / d->dx[0] -
+                                                          (Fy[fyB + nx] - Fy[fyB]) / d->dx[1] + Sn[xs]);
+                            } else {
+                                const long fzB = xs;
+                                U_out[e][x] += beta[n] * (-(Fx[fxL + 1] - Fx[fxL]) / d->dx[0] -
+                                                          (Fy[fyB + nx] - Fy[fyB]) / d->dx[1] -
+                                                          (Fz[fzB + nx * ny] - Fz[fzB]) / d->dx[2] + Sn[xs]);
+                            }
+                        }
+            }
+            if (q->model == ORC_FIVE_EQN_ALLAIRE) {
+                const int iz = ns + dim + 1;
+                for (int k = 0; k < q->n[2]; k++)
+                    for (int j = 0; j < q->n[1]; j++)
+                        for (int i = 0; i < q->n[0]; i++) {
+                            const long x = cidx(q, i, j, k);
+                            U_out[iz + ns - 1][x] = 1.0;
+                            for (int si = 0; si < ns - 1; si++) U_out[iz + ns - 1][x] -= U_out[iz + si][x];
+                        }
+            }
+        }
+    }
+    return 0;
+}

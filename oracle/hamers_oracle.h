@@ -1,0 +1,90 @@
+/*
+ * hamers_oracle.h -- CPU ORACLE (test infrastructure, NOT a product path).
+ *
+ * A plain-C, scalar, FP64 restatement of HAMeRS's per-patch WCNS5-JS / HLLC-HLL
+ * convective-flux hot path in the reference's own operation order.  Only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library; the product (hamers_b200/) never links or calls it.
+ *
+ * Parity status: the point kernels for the WCNS5-JS interpolation and the HLLC /
+ * HLLC-HLL Riemann solvers are PINNED against the reference's own compiled
+ * `static inline` functions (oracle/_ref, built by oracle/build_ref.py from
+ * /root/reference).  Everything else (derived cell data, characteristic
+ * projection, bounds check / fallback, sensor, flux differencing, RK update) is a
+ * restatement of formulas cited below ("parity unpinned" for those pieces: the
+ * reference holds no golden vectors and cannot be built here without SAMRAI).
+ *
+ * All citations are path:line under /root/reference.
+ */
+#ifndef HAMERS_ORACLE_H
+#define HAMERS_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MAX_SPECIES 4
+#define ORC_MAX_EQ 12          /* dim + 2*ns <= 3 + 8 */
+#define ORC_GHOSTS 4           /* ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:22 */
+
+#define ORC_SINGLE_SPECIES 0
+#define ORC_FIVE_EQN_ALLAIRE 1
+
+typedef struct {
+    int dim;                         /* 2 or 3 */
+    int n[3];                        /* interior cells of the patch (n[2] ignored in 2D) */
+    int model;                       /* ORC_SINGLE_SPECIES | ORC_FIVE_EQN_ALLAIRE */
+    int ns;                          /* number of species (1 for single-species) */
+    double gamma[ORC_MAX_SPECIES];   /* species ratio of specific heats */
+    double dx[3];
+    int weno_p;                      /* constant_p, default 2 (WCNS5-JS-HLLC-HLL.cpp:188-191) */
+} orc_desc;
+
+/* d + 2 (single-species) or d + 2*ns (five-eqn): FlowModelFiveEqnAllaire.cpp:29 */
+int orc_num_eqn(const orc_desc* d);
+/* number of stored conservative components: num_eqn (+1 for the five-eqn Z_last) */
+int orc_num_comp(const orc_desc* d);
+/* number of doubles of one ghost-box cell component / one ghost-0 cell component / one side component */
+long orc_cell_ghost_size(const orc_desc* d);
+long orc_cell_size(const orc_desc* d);
+long orc_side_size(const orc_desc* d, int dir);
+
+/*
+ * ConvectiveFluxReconstructorWCNS56::computeConvectiveFluxAndSourceOnPatch
+ * (ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:39-2656).
+ *   Q[c]        : conservative components on the ghost box (g = 4), SAMRAI CellData layout
+ *   F[dir*neq+e]: output side flux (ghost 0), already multiplied by dt, fully overwritten
+ *   S[e]        : output cell source (ghost 0), "+=" for ADVECTIVE equations only
+ * Optional debug outputs (may be NULL): F_mid[dir*neq+e] on faces -1..N+1 (normal) x interior,
+ * sensor[dir] same shape.
+ */
+int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, double dt,
+                                double* const* F, double* const* S,
+                                double* const* F_mid_dbg, double* const* sensor_dbg);
+
+/*
+ * Euler::advanceSingleStepOnPatch (Euler.cpp:1003-1679) for one patch.
+ *   ncoef        : number of coefficients (= stage number + 1)
+ *   U_int[m][c]  : intermediate states (ghost box layout), m < ncoef
+ *   F_int[m][..] : intermediate fluxes (side layout as above), S_int[m][e] sources
+ *   U_out[c]     : SCRATCH state, ghost box layout; whole array zero-filled first
+ *                  (FlowModelSingleSpecies.cpp:1602-1620), interior then updated.
+ */
+int orc_advance_stage(const orc_desc* d, int ncoef,
+                      const double* alpha, const double* beta,
+                      const double* const* const* U_int,
+                      const double* const* const* F_int,
+                      const double* const* const* S_int,
+                      double* const* U_out);
+
+/* Point kernels exported for pinning against oracle/_ref (the reference's own functions). */
+void orc_weno5js_point(const double U[6], int p, double* U_minus, double* U_plus);
+/* V layout: single-species [rho, vel(d), p]; five-eqn [Zrho(ns), vel(d), p, Z(ns-1)] */
+void orc_riemann_point(int model, int dim, int ns, const double* gamma, int dir,
+                       const double* V_L, const double* V_R,
+                       double* F_HLLC, double* F_HLLC_HLL, double* vel_mid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,228 @@
+"""ctypes front end of the CPU ORACLE (test infrastructure, NOT a product path).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package (hamers_b200) never does.
+
+The C sources restate the reference's algorithm (see hamers_oracle.h for citations and the
+parity status).  This module only marshals numpy arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+G = 4
+MAX_SPECIES = 4
+SINGLE_SPECIES = 0
+FIVE_EQN_ALLAIRE = 1
+
+# SSP-RK3 default table, RungeKuttaLevelIntegrator.cpp:3894-3929
+SSPRK3_ALPHA = np.array([[1.0, 0.0, 0.0], [3.0 / 4.0, 1.0 / 4.0, 0.0], [1.0 / 3.0, 0.0, 2.0 / 3.0]])
+SSPRK3_BETA = np.array([[1.0, 0.0, 0.0], [0.0, 1.0 / 4.0, 0.0], [0.0, 0.0, 2.0 / 3.0]])
+
+
+class _Desc(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int),
+        ("n", C.c_int * 3),
+        ("model", C.c_int),
+        ("ns", C.c_int),
+        ("gamma", C.c_double * MAX_SPECIES),
+        ("dx", C.c_double * 3),
+        ("weno_p", C.c_int),
+    ]
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so with the reference's CI flags (gcc -O3, no SIMD pragmas, no FMA)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("hamers_oracle.c", "oracle_level.c", "hamers_oracle.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s)):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = C.CDLL(so)
+        _LIB.orc_num_eqn.argtypes = [C.POINTER(_Desc)]
+        _LIB.orc_num_comp.argtypes = [C.POINTER(_Desc)]
+        _LIB.orc_compute_flux_and_source.restype = C.c_int
+        _LIB.orc_advance_stage.restype = C.c_int
+        _LIB.orc_level_advance.restype = C.c_int
+    return _LIB
+
+
+@dataclass
+class PatchDesc:
+    """Mirror of orc_desc: one patch (or one level) of the hot path."""
+    dim: int
+    n: tuple
+    model: int = SINGLE_SPECIES
+    ns: int = 1
+    gamma: tuple = (1.4,)
+    dx: tuple = (1.0, 1.0, 1.0)
+    weno_p: int = 2
+    _c: _Desc = field(default=None, repr=False)
+
+    def c(self) -> _Desc:
+        d = _Desc()
+        d.dim = self.dim
+        for a in range(3):
+            d.n[a] = int(self.n[a]) if a < self.dim else 1
+            d.dx[a] = float(self.dx[a]) if a < self.dim else 1.0
+        d.model = self.model
+        d.ns = self.ns
+        for i, g in enumerate(self.gamma):
+            d.gamma[i] = float(g)
+        d.weno_p = self.weno_p
+        return d
+
+    @property
+    def neq(self) -> int:
+        return self.dim + 2 if self.model == SINGLE_SPECIES else self.dim + 2 * self.ns
+
+    @property
+    def ncomp(self) -> int:
+        return self.neq if self.model == SINGLE_SPECIES else self.neq + 1
+
+    @property
+    def ghost_shape(self):
+        """numpy shape (z, y, x) of one ghost-box component (x fastest, SAMRAI column-major)."""
+        return tuple(int(self.n[a]) + 2 * G for a in reversed(range(self.dim)))
+
+    @property
+    def cell_shape(self):
+        return tuple(int(self.n[a]) for a in reversed(range(self.dim)))
+
+    def side_shape(self, direction: int):
+        e = [int(self.n[a]) for a in range(self.dim)]
+        e[direction] += 1
+        return tuple(reversed(e))
+
+    def mid_shape(self, direction: int):
+        e = [int(self.n[a]) for a in range(self.dim)]
+        e[direction] += 3
+        return tuple(reversed(e))
+
+
+def _pp(arrs):
+    """array of double* from a list of contiguous float64 arrays (None -> NULL)."""
+    P = (C.POINTER(C.c_double) * len(arrs))()
+    for i, a in enumerate(arrs):
+        if a is not None:
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+            P[i] = a.ctypes.data_as(C.POINTER(C.c_double))
+    return P
+
+
+def compute_flux_and_source(desc: PatchDesc, Q: np.ndarray, dt: float, source=None, debug=False):
+    """Q: (ncomp, *ghost_shape).  Returns (F list per direction of (neq, *side_shape), S (neq, *cell_shape))
+    and, with debug=True, additionally (F_mid list, sensor list)."""
+    Q = np.ascontiguousarray(Q, dtype=np.float64)
+    assert Q.shape == (desc.ncomp,) + desc.ghost_shape, (Q.shape, desc.ghost_shape)
+    neq, dim = desc.neq, desc.dim
+    F = [np.full((neq,) + desc.side_shape(a), np.nan) for a in range(dim)]
+    S = np.zeros((neq,) + desc.cell_shape) if source is None else source
+    Fm = [np.full((neq,) + desc.mid_shape(a), np.nan) for a in range(dim)] if debug else None
+    sen = [np.full(desc.mid_shape(a), np.nan) for a in range(dim)] if debug else None
+    d = desc.c()
+    Fp = _pp([F[a][e] for a in range(dim) for e in range(neq)])
+    Sp = _pp([S[e] for e in range(neq)])
+    Qp = _pp([Q[c] for c in range(desc.ncomp)])
+    Fmp = _pp([Fm[a][e] for a in range(dim) for e in range(neq)]) if debug else None
+    sp = _pp(sen) if debug else None
+    rc = lib().orc_compute_flux_and_source(C.byref(d), Qp, C.c_double(dt), Fp, Sp, Fmp, sp)
+    assert rc == 0
+    if debug:
+        return F, S, Fm, sen
+    return F, S
+
+
+def advance_stage(desc: PatchDesc, alpha, beta, U_int, F_int, S_int):
+    """One Euler::advanceSingleStepOnPatch.  U_int: list of (ncomp,*ghost_shape); F_int: list (per m) of
+    lists (per dir) of (neq,*side_shape) or None; S_int likewise.  Returns U_out (ncomp,*ghost_shape)."""
+    ncoef = len(alpha)
+    neq, dim = desc.neq, desc.dim
+    U_out = np.zeros((desc.ncomp,) + desc.ghost_shape)
+    d = desc.c()
+    keep = []
+    PP = C.POINTER(C.POINTER(C.c_double))
+    Ut = (PP * ncoef)()
+    Ft = (PP * ncoef)()
+    St = (PP * ncoef)()
+    for m in range(ncoef):
+        Um = np.ascontiguousarray(U_int[m])
+        up = _pp([Um[c] for c in range(desc.ncomp)])
+        if F_int[m] is not None:
+            fp = _pp([F_int[m][a][e] for a in range(dim) for e in range(neq)])
+            sp = _pp([S_int[m][e] for e in range(neq)])
+        else:
+            fp = _pp([None] * (dim * neq))
+            sp = _pp([None] * neq)
+        keep += [Um, up, fp, sp]
+        Ut[m] = C.cast(up, PP)
+        Ft[m] = C.cast(fp, PP)
+        St[m] = C.cast(sp, PP)
+    a = (C.c_double * ncoef)(*[float(x) for x in alpha])
+    b = (C.c_double * ncoef)(*[float(x) for x in beta])
+    rc = lib().orc_advance_stage(C.byref(d), ncoef, a, b, Ut, Ft, St, _pp([U_out[c] for c in range(desc.ncomp)]))
+    assert rc == 0
+    return U_out
+
+
+def level_advance(level: PatchDesc, patch, U: np.ndarray, dt: float, nsteps: int,
+                  alpha=SSPRK3_ALPHA, beta=SSPRK3_BETA, nthreads: int = 0):
+    """Advance a periodic uniform level in place.  U: (ncomp, *cell_shape of the level)."""
+    assert U.dtype == np.float64 and U.flags["C_CONTIGUOUS"]
+    assert U.shape == (level.ncomp,) + level.cell_shape
+    nst = alpha.shape[0]
+    d = level.c()
+    p = (C.c_int * 3)(*[int(patch[a]) if a < level.dim else 1 for a in range(3)])
+    a = np.ascontiguousarray(alpha, dtype=np.float64)
+    b = np.ascontiguousarray(beta, dtype=np.float64)
+    rc = lib().orc_level_advance(C.byref(d), p, _pp([U[c] for c in range(level.ncomp)]), C.c_double(dt),
+                                 int(nsteps), int(nst), a.ctypes.data_as(C.POINTER(C.c_double)),
+                                 b.ctypes.data_as(C.POINTER(C.c_double)), int(nthreads))
+    if rc != 0:
+        raise RuntimeError(f"orc_level_advance failed: {rc}")
+    return U
+
+
+def weno5js_point(U, p=2):
+    Ua = (C.c_double * 6)(*[float(x) for x in U])
+    m, pl = C.c_double(), C.c_double()
+    lib().orc_weno5js_point(Ua, int(p), C.byref(m), C.byref(pl))
+    return m.value, pl.value
+
+
+def riemann_point(model, dim, ns, gamma, direction, V_L, V_R):
+    neq = dim + 2 if model == SINGLE_SPECIES else dim + 2 * ns
+    g = (C.c_double * MAX_SPECIES)(*[float(x) for x in gamma])
+    VL = (C.c_double * neq)(*[float(x) for x in V_L])
+    VR = (C.c_double * neq)(*[float(x) for x in V_R])
+    F1 = (C.c_double * neq)()
+    F2 = (C.c_double * neq)()
+    vm = C.c_double()
+    lib().orc_riemann_point(int(model), int(dim), int(ns), g, int(direction), VL, VR, F1, F2, C.byref(vm))
+    return np.array(F1[:]), np.array(F2[:]), vm.value
+
+
+def side_thermo(model, dim, ns, gamma, V):
+    neq = dim + 2 if model == SINGLE_SPECIES else dim + 2 * ns
+    g = (C.c_double * MAX_SPECIES)(*[float(x) for x in gamma])
+    Va = (C.c_double * neq)(*[float(x) for x in V])
+    r, c, e = C.c_double(), C.c_double(), C.c_double()
+    lib().orc_side_thermo(int(model), int(dim), int(ns), g, Va, C.byref(r), C.byref(c), C.byref(e))
+    return r.value, c.value, e.value
