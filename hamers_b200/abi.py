@@ -1,0 +1,295 @@
+"""ctypes binding of include/hamers_b200.h.
+
+PyTorch appears here only as plumbing: device memory (tensors own the HBM-resident patch data)
+and the CUDA stream the plan launches on.  All arithmetic happens in libhamers_b200.so.  There
+is no CPU fallback: if the library is missing or no CUDA device exists, plan creation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libhamers_b200.so")
+
+MAX_SPECIES = 4
+GHOSTS = 4
+SINGLE_SPECIES = 0
+FIVE_EQN_ALLAIRE = 1
+MATH_EXACT = 0
+MATH_FAST = 1
+
+# every symbol include/hamers_b200.h declares (tests check the library exports them all)
+SYMBOLS = [
+    "hb2_last_error", "hb2_version", "hb2_device_count", "hb2_num_eqn", "hb2_num_comp", "hb2_num_ghosts",
+    "hb2_cell_ghost_size", "hb2_cell_size", "hb2_side_size", "hb2_plan_create", "hb2_plan_destroy",
+    "hb2_plan_set_stream", "hb2_plan_synchronize", "hb2_plan_launch_count", "hb2_plan_workspace_bytes",
+    "hb2_compute_flux_and_source_dev", "hb2_advance_stage_dev", "hb2_fused_stage_dev",
+    "hb2_fill_ghosts_periodic_dev", "hb2_pack_box_dev", "hb2_unpack_box_dev", "hb2_max_wave_speed_dev",
+    "hb2_compute_flux_and_source_host", "hb2_fused_stage_host", "hb2_probe_fp64_peak", "hb2_probe_hbm_bandwidth",
+]
+
+
+class PatchDescC(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32),
+        ("n", C.c_int32 * 3),
+        ("flow_model", C.c_int32),
+        ("num_species", C.c_int32),
+        ("species_gamma", C.c_double * MAX_SPECIES),
+        ("dx", C.c_double * 3),
+        ("weno_p", C.c_int32),
+        ("math", C.c_int32),
+        ("device", C.c_int32),
+    ]
+
+
+class HamersB200Error(RuntimeError):
+    pass
+
+
+_LIB = None
+
+
+def load_library():
+    """Load libhamers_b200.so; raises (never falls back) when it is missing."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO):
+            raise HamersB200Error(
+                f"{SO} not found: build it with `python -m hamers_b200.build` (there is no CPU fallback)")
+        lib = C.CDLL(SO)
+        lib.hb2_last_error.restype = C.c_char_p
+        lib.hb2_version.restype = C.c_char_p
+        for f in ("hb2_cell_ghost_size", "hb2_cell_size", "hb2_side_size", "hb2_plan_launch_count",
+                  "hb2_plan_workspace_bytes"):
+            getattr(lib, f).restype = C.c_int64
+        lib.hb2_plan_create.argtypes = [C.POINTER(PatchDescC), C.POINTER(C.c_void_p)]
+        lib.hb2_plan_destroy.argtypes = [C.c_void_p]
+        lib.hb2_plan_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        lib.hb2_plan_synchronize.argtypes = [C.c_void_p]
+        lib.hb2_plan_launch_count.argtypes = [C.c_void_p]
+        lib.hb2_plan_workspace_bytes.argtypes = [C.c_void_p]
+        _LIB = lib
+    return _LIB
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise HamersB200Error(f"{what} failed ({rc}): {load_library().hb2_last_error().decode()}")
+
+
+def _ptr_table(ptrs: Sequence[Optional[int]]):
+    T = (C.c_void_p * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        T[i] = p if p else None
+    return T
+
+
+def _dev_ptrs(t, n):
+    """device pointers of the n leading-axis slices of a contiguous float64 CUDA tensor (or list of tensors)."""
+    import torch
+
+    if isinstance(t, (list, tuple)):
+        out = []
+        for x in t:
+            out += _dev_ptrs(x, x.shape[0]) if x is not None else []
+        return out
+    assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous(), "need a contiguous float64 CUDA tensor"
+    assert t.shape[0] == n, (t.shape, n)
+    stride = t[0].numel() * 8
+    base = t.data_ptr()
+    return [base + i * stride for i in range(n)]
+
+
+def _host_ptrs(a: np.ndarray, n):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.shape[0] == n
+    stride = a[0].size * 8
+    return [a.ctypes.data + i * stride for i in range(n)]
+
+
+class Plan:
+    """One patch shape of the hot path (mirrors hb2_plan_t).
+
+    Array conventions (numpy / torch views of the SAMRAI layouts, x fastest):
+      state  : (num_comp, [nz+8,] ny+8, nx+8)
+      flux d : (num_eqn, ...) with extent +1 along direction d, ghost 0
+      source : (num_eqn, [nz,] ny, nx)
+    """
+
+    def __init__(self, dim: int, n: Sequence[int], flow_model: int = SINGLE_SPECIES,
+                 species_gamma: Sequence[float] = (1.4,), dx: Sequence[float] = (1.0, 1.0, 1.0),
+                 weno_p: int = 2, math: int = MATH_EXACT, device: int = -1):
+        self.lib = load_library()
+        d = PatchDescC()
+        d.dim = dim
+        for a in range(3):
+            d.n[a] = int(n[a]) if a < dim else 1
+            d.dx[a] = float(dx[a]) if a < dim else 1.0
+        d.flow_model = flow_model
+        d.num_species = len(species_gamma) if flow_model == FIVE_EQN_ALLAIRE else 1
+        for i, g in enumerate(species_gamma):
+            d.species_gamma[i] = float(g)
+        d.weno_p = weno_p
+        d.math = math
+        d.device = device
+        self.desc = d
+        self.dim = dim
+        self.n = tuple(int(n[a]) for a in range(dim))
+        self.flow_model = flow_model
+        self.num_species = d.num_species
+        self.neq = dim + 2 if flow_model == SINGLE_SPECIES else dim + 2 * d.num_species
+        self.ncomp = self.neq if flow_model == SINGLE_SPECIES else self.neq + 1
+        self._h = C.c_void_p()
+        _check(self.lib.hb2_plan_create(C.byref(d), C.byref(self._h)), "hb2_plan_create")
+
+    # -- shapes ---------------------------------------------------------------------------
+    @property
+    def ghost_shape(self):
+        return tuple(self.n[a] + 2 * GHOSTS for a in reversed(range(self.dim)))
+
+    @property
+    def cell_shape(self):
+        return tuple(self.n[a] for a in reversed(range(self.dim)))
+
+    def side_shape(self, direction: int):
+        e = list(self.n)
+        e[direction] += 1
+        return tuple(reversed(e))
+
+    # -- lifetime -------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            self.lib.hb2_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def use_torch_stream(self):
+        """Launch on torch's current stream so that tensor ops and plan calls are ordered."""
+        import torch
+
+        _check(self.lib.hb2_plan_set_stream(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               "hb2_plan_set_stream")
+        return self
+
+    def synchronize(self):
+        _check(self.lib.hb2_plan_synchronize(self._h), "hb2_plan_synchronize")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.hb2_plan_launch_count(self._h))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.hb2_plan_workspace_bytes(self._h))
+
+    # -- device-resident hot path ----------------------------------------------------------
+    def compute_flux_and_source(self, Q, dt: float, flux, source=None):
+        """ConvectiveFluxReconstructor::computeConvectiveFluxAndSourceOnPatch on device tensors.
+        flux: list (per direction) of (neq, *side_shape) tensors; source: (neq, *cell_shape) or None."""
+        qp = _ptr_table(_dev_ptrs(Q, self.ncomp))
+        fp = _ptr_table([p for d in range(self.dim) for p in _dev_ptrs(flux[d], self.neq)])
+        sp = _ptr_table(_dev_ptrs(source, self.neq)) if source is not None else None
+        _check(self.lib.hb2_compute_flux_and_source_dev(self._h, qp, C.c_double(dt), fp, sp),
+               "hb2_compute_flux_and_source_dev")
+
+    def fused_stage(self, alpha, beta, U_int, dt: float, U_out):
+        """computeFluxesAndSourcesOnPatch + advanceSingleStepOnPatch without materialising fluxes."""
+        ncoef = len(alpha)
+        tab = _ptr_table([p for m in range(ncoef) for p in _dev_ptrs(U_int[m], self.ncomp)])
+        a = (C.c_double * ncoef)(*[float(x) for x in alpha])
+        b = (C.c_double * ncoef)(*[float(x) for x in beta])
+        _check(self.lib.hb2_fused_stage_dev(self._h, ncoef, a, b, tab, C.c_double(dt),
+                                            _ptr_table(_dev_ptrs(U_out, self.ncomp))), "hb2_fused_stage_dev")
+
+    def advance_stage(self, alpha, beta, U_int, F_int, S_int, U_out, gamma=None, F_acc=None, S_acc=None):
+        """Euler::advanceSingleStepOnPatch from materialised fluxes.  F_int[m]: list per direction or None."""
+        ncoef = len(alpha)
+        nf = self.dim * self.neq
+        ut = _ptr_table([p for m in range(ncoef) for p in _dev_ptrs(U_int[m], self.ncomp)])
+        fl, sl = [], []
+        for m in range(ncoef):
+            if F_int[m] is None:
+                fl += [None] * nf
+                sl += [None] * self.neq
+            else:
+                fl += [p for d in range(self.dim) for p in _dev_ptrs(F_int[m][d], self.neq)]
+                sl += _dev_ptrs(S_int[m], self.neq) if S_int[m] is not None else [None] * self.neq
+        a = (C.c_double * ncoef)(*[float(x) for x in alpha])
+        b = (C.c_double * ncoef)(*[float(x) for x in beta])
+        g = (C.c_double * ncoef)(*[float(x) for x in (gamma if gamma is not None else [0.0] * ncoef)])
+        fa = _ptr_table([p for d in range(self.dim) for p in _dev_ptrs(F_acc[d], self.neq)]) if F_acc is not None else None
+        sa = _ptr_table(_dev_ptrs(S_acc, self.neq)) if S_acc is not None else None
+        _check(self.lib.hb2_advance_stage_dev(self._h, ncoef, a, b, g, ut, _ptr_table(fl), _ptr_table(sl),
+                                              _ptr_table(_dev_ptrs(U_out, self.ncomp)), fa, sa),
+               "hb2_advance_stage_dev")
+
+    def fill_ghosts_periodic(self, U, mask: int = 7):
+        _check(self.lib.hb2_fill_ghosts_periodic_dev(self._h, _ptr_table(_dev_ptrs(U, self.ncomp)), int(mask)),
+               "hb2_fill_ghosts_periodic_dev")
+
+    def pack_box(self, U, lo, hi, buffer):
+        l = (C.c_int32 * 3)(*[int(lo[a]) if a < self.dim else 0 for a in range(3)])
+        h = (C.c_int32 * 3)(*[int(hi[a]) if a < self.dim else 1 for a in range(3)])
+        _check(self.lib.hb2_pack_box_dev(self._h, _ptr_table(_dev_ptrs(U, self.ncomp)), l, h,
+                                         C.c_void_p(buffer.data_ptr())), "hb2_pack_box_dev")
+
+    def unpack_box(self, U, lo, hi, buffer):
+        l = (C.c_int32 * 3)(*[int(lo[a]) if a < self.dim else 0 for a in range(3)])
+        h = (C.c_int32 * 3)(*[int(hi[a]) if a < self.dim else 1 for a in range(3)])
+        _check(self.lib.hb2_unpack_box_dev(self._h, _ptr_table(_dev_ptrs(U, self.ncomp)), l, h,
+                                           C.c_void_p(buffer.data_ptr())), "hb2_unpack_box_dev")
+
+    def max_wave_speed(self, Q, out):
+        _check(self.lib.hb2_max_wave_speed_dev(self._h, _ptr_table(_dev_ptrs(Q, self.ncomp)),
+                                               C.c_void_p(out.data_ptr())), "hb2_max_wave_speed_dev")
+
+    # -- host-buffer hot path (numpy in, numpy out; H2D/D2H inside the call) -----------------
+    def compute_flux_and_source_host(self, Q: np.ndarray, dt: float, flux=None, source=None):
+        if flux is None:
+            flux = [np.empty((self.neq,) + self.side_shape(d)) for d in range(self.dim)]
+        if source is None:
+            source = np.zeros((self.neq,) + self.cell_shape)
+        qp = _ptr_table(_host_ptrs(Q, self.ncomp))
+        fp = _ptr_table([p for d in range(self.dim) for p in _host_ptrs(flux[d], self.neq)])
+        sp = _ptr_table(_host_ptrs(source, self.neq))
+        _check(self.lib.hb2_compute_flux_and_source_host(self._h, qp, C.c_double(dt), fp, sp),
+               "hb2_compute_flux_and_source_host")
+        return flux, source
+
+    def fused_stage_host(self, alpha, beta, U_int, dt: float, U_out: Optional[np.ndarray] = None):
+        ncoef = len(alpha)
+        if U_out is None:
+            U_out = np.zeros((self.ncomp,) + self.ghost_shape)
+        tab = _ptr_table([p for m in range(ncoef) for p in _host_ptrs(U_int[m], self.ncomp)])
+        a = (C.c_double * ncoef)(*[float(x) for x in alpha])
+        b = (C.c_double * ncoef)(*[float(x) for x in beta])
+        _check(self.lib.hb2_fused_stage_host(self._h, ncoef, a, b, tab, C.c_double(dt),
+                                             _ptr_table(_host_ptrs(U_out, self.ncomp))), "hb2_fused_stage_host")
+        return U_out
+
+
+def device_count() -> int:
+    n = C.c_int32()
+    load_library().hb2_device_count(C.byref(n))
+    return n.value
+
+
+def probe_fp64_peak(device: int = -1, seconds_hint: float = 1.0) -> float:
+    v = C.c_double()
+    _check(load_library().hb2_probe_fp64_peak(int(device), C.c_double(seconds_hint), C.byref(v)), "hb2_probe_fp64_peak")
+    return v.value
+
+
+def probe_hbm_bandwidth(device: int = -1, nbytes: int = 1 << 30) -> float:
+    v = C.c_double()
+    _check(load_library().hb2_probe_hbm_bandwidth(int(device), C.c_int64(nbytes), C.byref(v)), "hb2_probe_hbm_bandwidth")
+    return v.value

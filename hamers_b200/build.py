@@ -1,0 +1,71 @@
+"""Build libhamers_b200.so (the C-ABI product library) in-tree with nvcc for sm_100a.
+
+    python -m hamers_b200.build [--force]
+
+Three translation units: the sweeps are compiled twice (exact: -fmad=false, reference operation
+order; fast: FMA contraction + reciprocal sharing) and linked with the ABI layer.  nvcc
+cross-compiles without a GPU.  The .so is git-ignored but travels to the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+ROOT = os.path.dirname(HERE)
+BUILD = os.path.join(ROOT, "build")
+SO = os.path.join(HERE, "libhamers_b200.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include")]
+
+UNITS = [
+    ("hb2_sweeps_exact.o", "hb2_sweeps.cu", ["-DHB2_MATH=0", "-fmad=false"]),
+    ("hb2_sweeps_fast.o", "hb2_sweeps.cu", ["-DHB2_MATH=1", "-fmad=true"]),
+    ("hb2_abi.o", "hb2_abi.cu", ["-fmad=false"]),
+]
+DEPS = ["hb2_core.cuh", "hb2_ops.h", "hb2_sweeps.cu", "hb2_abi.cu", os.path.join(ROOT, "include", "hamers_b200.h")]
+
+
+def _mtime(p):
+    return os.path.getmtime(p) if os.path.exists(p) else 0.0
+
+
+def needs_build() -> bool:
+    if not os.path.exists(SO):
+        return True
+    newest = max(_mtime(d if os.path.isabs(d) else os.path.join(CSRC, d)) for d in DEPS)
+    return newest > _mtime(SO)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return SO
+    os.makedirs(BUILD, exist_ok=True)
+
+    def compile_one(unit):
+        obj, src, flags = unit
+        cmd = [NVCC] + COMMON + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", os.path.join(BUILD, obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src} {flags}:\n{r.stdout}\n{r.stderr}")
+        return r.stderr
+
+    with ThreadPoolExecutor(max_workers=3) as ex:
+        logs = list(ex.map(compile_one, UNITS))
+    if verbose:
+        for lg in logs:
+            print(lg)
+    link = [NVCC] + ARCH + ["-shared", "-o", SO] + [os.path.join(BUILD, u[0]) for u in UNITS]
+    r = subprocess.run(link, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return SO
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,921 @@
+/*
+ * hb2_core.cuh -- arithmetic core of the B200 WCNS5-JS / HLLC-HLL path.
+ *
+ * Everything here is `__host__ __device__` so that the SAME code is (a) inlined into the
+ * sm_100a kernels of hb2_kernels.cu and (b) compiled by g++ into the test-only host emulation
+ * harness (tests/host_emu) that checks indexing and arithmetic against the oracle in a
+ * container without a GPU.  (b) is never linked into the product library.
+ *
+ * Reference behaviour restated here (path:line under the reference tree):
+ *   cell stage      FlowModelSingleSpecies.cpp:2824-2826, 3049-3051; EquationOfStateIdealGas.cpp:5580, 5909;
+ *                   FlowModelFiveEqnAllaire.cpp:3965, 4428-4430, 4779-4853;
+ *                   EquationOfStateMixingRulesIdealGas.cpp:7520-7587
+ *   projection      FlowModelBasicUtilitiesSingleSpecies.cpp:5000-5001, 6324-6329, 7373-7379;
+ *                   FlowModelBasicUtilitiesFiveEqnAllaire.cpp:7952-7996, 8835-8921, 9700-9759
+ *   WCNS5-JS        ConvectiveFluxReconstructorWCNS5-JS-HLLC-HLL.cpp:9-164
+ *   bounds/fallback FlowModelBasicUtilitiesSingleSpecies.cpp:3013-3433; ...FiveEqnAllaire.cpp:5446-7340;
+ *                   ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:1884-2039
+ *   Riemann         FlowModelRiemannSolverSingleSpeciesHLLC.cpp:604-1074, ...HLLC-HLL.cpp:889-1629;
+ *                   FlowModelRiemannSolverFiveEqnAllaireHLLC.cpp:848-1591, 5640-6040, ...HLLC-HLL.cpp:1283-2440
+ *   sensor/select   ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:2072-2134
+ *   face flux       ...WCNS56-HLLC-HLL.cpp:2330-2489;  source :2495-2647
+ *   RK update       Euler.cpp:1424-1655; FlowModelFiveEqnAllaire.cpp:1739-1886
+ *
+ * Design (B200-first, not a translation): the reference makes ~35 full-patch passes over
+ * ~70 temporaries; here one thread produces a midpoint flux entirely in registers from six
+ * stencil cells, converting conservative to primitive variables on the fly.  y/z sweeps march
+ * along the sweep axis with lanes across the contiguous x axis (register-rotating stencil,
+ * every cell converted once per sweep); the x sweep stages a linear run of cells in shared
+ * memory and exchanges midpoint fluxes through it.
+ */
+#pragma once
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define HB2_HD __host__ __device__ __forceinline__
+#else
+#define HB2_HD inline
+#endif
+
+#define HB2_G 4
+#define HB2_EPS 1.0e-15 /* HAMERS_EPSILON, include/HAMeRS_config.hpp.in:16 */
+
+namespace hb2 {
+
+enum { SS = 0, FE = 1 };
+enum { MODE_EMIT = 0, MODE_FUSED = 1 };
+
+template <int MODEL_, int DIM_, int NS_>
+struct Traits {
+    static constexpr int MODEL = MODEL_;
+    static constexpr int DIM = DIM_;
+    static constexpr int NS = (MODEL_ == SS) ? 1 : NS_;
+    static constexpr int NM = NS;                                  /* mass equations */
+    static constexpr int NEQ = (MODEL_ == SS) ? DIM_ + 2 : DIM_ + 2 * NS_;
+    static constexpr int NCOMP = (MODEL_ == SS) ? NEQ : NEQ + 1;   /* + stored Z_last */
+    static constexpr int IV = NM;                                  /* first velocity index */
+    static constexpr int IP = NM + DIM_;                           /* pressure (V) / energy (Q) index */
+    static constexpr bool ADV = (MODEL_ == FE);                    /* has advective equations */
+};
+
+struct Geom {
+    int dim;
+    int n[3];        /* interior cells */
+    int g[3];        /* ghost width per direction (0 in the unused 3rd direction of 2D) */
+    int gd[3];       /* ghost-box dims */
+    long long cs[3]; /* cell strides in the ghost box */
+    long long ncell_g;
+    double dx[3];
+};
+
+struct Consts {
+    double gamma[4];
+    double inv_gm1[4]; /* 1/(gamma_i - 1), EquationOfStateMixingRulesIdealGas.cpp:7523 */
+    int weno_p;
+};
+
+#define HB2_MAXC 13
+#define HB2_MAXE 12
+#define HB2_MAXS 4
+
+struct DirArgs {
+    Geom G;
+    Consts K;
+    const double* Q[HB2_MAXC]; /* conservative components of the state the flux is evaluated on */
+    const double* theta;       /* dilatation, ghost-box layout, valid on cells -2..N+1 */
+    const double* Omega;       /* vorticity magnitude, same */
+    int mode;                  /* MODE_EMIT | MODE_FUSED */
+    double dt;
+    double* F[HB2_MAXE];       /* EMIT: side flux arrays of THIS direction */
+    double* S[HB2_MAXE];       /* EMIT, last direction: cell sources (+=), advective equations only */
+    double* R[HB2_MAXE];       /* FUSED: running -(dFx/dx) - (dFy/dy) ... per equation, interior layout */
+    double* T;                 /* five-eqn: running sum of the velocity-divergence terms, interior layout */
+    int ncoef;                 /* FUSED, last direction: RK update */
+    double alpha[HB2_MAXS];
+    double beta;
+    const double* Uint[HB2_MAXS][HB2_MAXC];
+    double* Uout[HB2_MAXC];
+    int seg_len;               /* cells per marching segment (y/z sweeps) */
+};
+
+HB2_HD long long cidx(const Geom& G, int i, int j, int k)
+{
+    return (i + G.g[0]) + (long long)(j + G.g[1]) * G.cs[1] + (long long)(k + G.g[2]) * G.cs[2];
+}
+/* ghost-0 cell (interior layout) */
+HB2_HD long long iidx(const Geom& G, int i, int j, int k)
+{
+    return i + (long long)G.n[0] * (j + (long long)G.n[1] * k);
+}
+/* ghost-0 side array of direction dir: extent n+1 in dir */
+template <int DIR>
+HB2_HD long long sidx(const Geom& G, int i, int j, int k)
+{
+    const long long e0 = G.n[0] + (DIR == 0 ? 1 : 0);
+    const long long e1 = G.n[1] + (DIR == 1 ? 1 : 0);
+    return i + e0 * (j + e1 * (long long)k);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * cell stage: conservative -> primitive + sound speed
+ * ---------------------------------------------------------------------------------------- */
+template <class Tr>
+HB2_HD void cons_to_prim(const double (&q)[Tr::NCOMP], const Consts& K, double (&V)[Tr::NEQ], double& c)
+{
+    constexpr int DIM = Tr::DIM, NS = Tr::NS;
+    if (Tr::MODEL == SS) {
+        const double rho = q[0];
+        V[0] = rho;
+        double ke = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+            V[1 + a] = q[1 + a] / rho;
+            ke = (a == 0) ? V[1 + a] * V[1 + a] : ke + V[1 + a] * V[1 + a];
+        }
+        const double epsilon = q[DIM + 1] / rho - 0.5 * ke;
+        const double p = (K.gamma[0] - 1.0) * rho * epsilon;
+        V[DIM + 1] = p;
+        c = sqrt(K.gamma[0] * p / rho);
+    } else {
+        double rho = 0.0;
+#pragma unroll
+        for (int si = 0; si < NS; si++) rho += q[si];
+        double Y[NS];
+#pragma unroll
+        for (int si = 0; si < NS; si++) {
+            V[si] = q[si];
+            Y[si] = q[si] / rho;
+        }
+        double ke = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+            V[NS + a] = q[NS + a] / rho;
+            ke = (a == 0) ? V[NS + a] * V[NS + a] : ke + V[NS + a] * V[NS + a];
+        }
+        const double epsilon = q[NS + DIM] / rho - 0.5 * ke;
+        double xi = 0.0;
+#pragma unroll
+        for (int si = 0; si < NS; si++) xi += q[NS + DIM + 1 + si] * K.inv_gm1[si];
+        const double gamma_m = 1.0 / xi + 1.0;
+        const double p = (gamma_m - 1.0) * rho * epsilon;
+        V[NS + DIM] = p;
+        const double Gamma = gamma_m - 1.0;
+        double cc = Gamma * p / rho;
+#pragma unroll
+        for (int si = 0; si < NS; si++) cc += Y[si] * (p / rho);
+        c = sqrt(cc);
+#pragma unroll
+        for (int si = 0; si < NS - 1; si++) V[NS + DIM + 1 + si] = q[NS + DIM + 1 + si];
+    }
+}
+
+/* node flux of one cell in direction DIR from its conservative (q) and primitive (V) variables */
+template <class Tr, int DIR>
+HB2_HD void node_flux(const double (&q)[Tr::NCOMP], const double (&V)[Tr::NEQ], double (&Fn)[Tr::NEQ])
+{
+    constexpr int DIM = Tr::DIM, NS = Tr::NS, IV = Tr::IV, IP = Tr::IP;
+    const double un = V[IV + DIR];
+    const double p = V[IP];
+    if (Tr::MODEL == SS) {
+        Fn[0] = q[1 + DIR];
+#pragma unroll
+        for (int a = 0; a < DIM; a++) Fn[1 + a] = (a == DIR) ? un * q[1 + a] + p : un * q[1 + a];
+        Fn[DIM + 1] = un * (q[DIM + 1] + p);
+    } else {
+#pragma unroll
+        for (int si = 0; si < NS; si++) Fn[si] = un * q[si];
+#pragma unroll
+        for (int a = 0; a < DIM; a++) Fn[NS + a] = (a == DIR) ? un * q[NS + a] + p : un * q[NS + a];
+        Fn[NS + DIM] = un * (q[NS + DIM] + p);
+#pragma unroll
+        for (int si = 0; si < NS - 1; si++) Fn[NS + DIM + 1 + si] = un * q[NS + DIM + 1 + si];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * WCNS5-JS one-sided midpoint interpolation
+ * ---------------------------------------------------------------------------------------- */
+HB2_HD double ipow_(double base, int e)
+{
+    double r = base;
+    for (int i = 1; i < e; i++) r *= base;
+    return r;
+}
+
+template <int MATH>
+HB2_HD double weno5js_side(double a, double b, double c, double d, double e, int p)
+{
+    const double beta_0 = 1.0 / 3.0 * (a * (4.0 * a - 19.0 * b + 11.0 * c) + b * (25.0 * b - 31.0 * c) + 10.0 * c * c);
+    const double beta_1 = 1.0 / 3.0 * (b * (4.0 * b - 13.0 * c + 5.0 * d) + 13.0 * c * (c - d) + 4.0 * d * d);
+    const double beta_2 = 1.0 / 3.0 * (c * (10.0 * c - 31.0 * d + 11.0 * e) + d * (25.0 * d - 19.0 * e) + 4.0 * e * e);
+
+    if (MATH == 0) {
+        const double b0 = beta_0 + HB2_EPS, b1 = beta_1 + HB2_EPS, b2 = beta_2 + HB2_EPS;
+        double omega_0 = 1.0 / 16.0 / (p == 2 ? b0 * b0 : ipow_(b0, p));
+        double omega_1 = 5.0 / 8.0 / (p == 2 ? b1 * b1 : ipow_(b1, p));
+        double omega_2 = 5.0 / 16.0 / (p == 2 ? b2 * b2 : ipow_(b2, p));
+        const double omega_sum = omega_0 + omega_1 + omega_2;
+        omega_0 = omega_0 / omega_sum;
+        omega_1 = omega_1 / omega_sum;
+        omega_2 = omega_2 / omega_sum;
+        return 3.0 / 8.0 * omega_0 * a + (-10.0 / 8.0 * omega_0 - 1.0 / 8.0 * omega_1) * b +
+               (15.0 / 8.0 * omega_0 + 6.0 / 8.0 * omega_1 + 3.0 / 8.0 * omega_2) * c +
+               (3.0 / 8.0 * omega_1 + 6.0 / 8.0 * omega_2) * d - 1.0 / 8.0 * omega_2 * e;
+    } else {
+        /* One division instead of six: with b_k = (beta_k + eps)^p the normalised weights are
+         * omega_k = d_k * prod_{j != k} b_j / sum_k(d_k * prod_{j != k} b_j).  Algebraically
+         * identical to the reference; differs by a few ulp of re-association (FP64 range is
+         * ample: b_k >= 1e-30 for p = 2). */
+        const double e0 = beta_0 + HB2_EPS, e1 = beta_1 + HB2_EPS, e2 = beta_2 + HB2_EPS;
+        const double b0 = (p == 2 ? e0 * e0 : ipow_(e0, p));
+        const double b1 = (p == 2 ? e1 * e1 : ipow_(e1, p));
+        const double b2 = (p == 2 ? e2 * e2 : ipow_(e2, p));
+        const double a0 = (1.0 / 16.0) * (b1 * b2);
+        const double a1 = (5.0 / 8.0) * (b0 * b2);
+        const double a2 = (5.0 / 16.0) * (b0 * b1);
+        const double inv = 1.0 / (a0 + a1 + a2);
+        /* sub-stencil midpoint values */
+        const double P0 = 0.375 * a - 1.25 * b + 1.875 * c;
+        const double P1 = -0.125 * b + 0.75 * c + 0.375 * d;
+        const double P2 = 0.375 * c + 0.75 * d - 0.125 * e;
+        return (a0 * P0 + a1 * P1 + a2 * P2) * inv;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * side thermodynamics for the Riemann solvers
+ * ---------------------------------------------------------------------------------------- */
+template <class Tr>
+HB2_HD void side_thermo(const double (&V)[Tr::NEQ], const Consts& K, double& rho, double& c, double& eps)
+{
+    constexpr int DIM = Tr::DIM, NS = Tr::NS;
+    if (Tr::MODEL == SS) {
+        rho = V[0];
+        const double p = V[DIM + 1];
+        c = sqrt(K.gamma[0] * p / rho);
+        eps = p / ((K.gamma[0] - 1.0) * rho);
+    } else {
+        double r = 0.0;
+#pragma unroll
+        for (int si = 0; si < NS; si++) r += V[si];
+        const double p = V[NS + DIM];
+        double xi = 0.0, Z_last = 1.0;
+#pragma unroll
+        for (int si = 0; si < NS - 1; si++) {
+            xi += V[NS + DIM + 1 + si] * K.inv_gm1[si];
+            Z_last -= V[NS + DIM + 1 + si];
+        }
+        xi += Z_last / (K.gamma[NS - 1] - 1.0);
+        const double gamma_m = 1.0 / xi + 1.0;
+        const double Gamma = gamma_m - 1.0;
+        double cc = Gamma * p / r;
+#pragma unroll
+        for (int si = 0; si < NS; si++) cc += (V[si] / r) * (p / r);
+        rho = r;
+        c = sqrt(cc);
+        eps = p / ((gamma_m - 1.0) * r);
+    }
+}
+
+/* bounded flag of one interpolated side */
+template <class Tr>
+HB2_HD int side_bounded(const double (&V)[Tr::NEQ], const Consts& K)
+{
+    constexpr int DIM = Tr::DIM, NS = Tr::NS, NEQ = Tr::NEQ;
+    int ok = 1;
+    if (Tr::MODEL == SS) {
+        ok &= (V[0] > 0.0) ? 1 : 0;
+        ok &= (V[NEQ - 1] > 0.0) ? 1 : 0;
+    } else {
+        const double Z_lo = -1000.0, Z_up = 1000.0, Y_lo = -0.001, Y_up = 1.001;
+        double Z[NS];
+        Z[NS - 1] = 1.0;
+#pragma unroll
+        for (int si = 0; si < NS - 1; si++) {
+            Z[si] = V[NS + DIM + 1 + si];
+            Z[NS - 1] -= Z[si];
+            ok &= (Z[si] > Z_lo && Z[si] < Z_up) ? 1 : 0;
+        }
+        ok &= (Z[NS - 1] > Z_lo && Z[NS - 1] < Z_up) ? 1 : 0;
+        double rho = 0.0;
+#pragma unroll
+        for (int si = 0; si < NS; si++) rho += V[si];
+        double Y[NS];
+#pragma unroll
+        for (int si = 0; si < NS; si++) {
+            Y[si] = V[si] / rho;
+            ok &= (Y[si] > Y_lo && Y[si] < Y_up) ? 1 : 0;
+        }
+#pragma unroll
+        for (int si = 0; si < NS; si++) ok &= (V[si] > 0.0) ? 1 : 0;
+        const double p = V[NS + DIM];
+        double xi = 0.0;
+#pragma unroll
+        for (int si = 0; si < NS; si++) xi += Z[si] * K.inv_gm1[si];
+        const double gamma_m = 1.0 / xi + 1.0;
+        const double Gamma = gamma_m - 1.0;
+        double c_sq = Gamma * p / rho;
+#pragma unroll
+        for (int si = 0; si < NS; si++) c_sq += Y[si] * (p / rho);
+        ok &= (c_sq > 0.0) ? 1 : 0;
+    }
+    return ok;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * HLLC (always) and HLLC-HLL (when `hybrid`) midpoint flux + HLLC midpoint normal velocity
+ * ---------------------------------------------------------------------------------------- */
+template <class Tr, int DIR>
+HB2_HD void riemann(const double (&V_L)[Tr::NEQ], const double (&V_R)[Tr::NEQ], const Consts& K, bool hybrid,
+                    double (&Fm)[Tr::NEQ], double& vel_mid)
+{
+    constexpr int DIM = Tr::DIM, NS = Tr::NS, NEQ = Tr::NEQ, NM = Tr::NM, IV = Tr::IV, IP = Tr::IP;
+
+    double rho_L, rho_R, c_L, c_R, eps_L, eps_R;
+    side_thermo<Tr>(V_L, K, rho_L, c_L, eps_L);
+    side_thermo<Tr>(V_R, K, rho_R, c_R, eps_R);
+
+    const double un_L = V_L[IV + DIR], un_R = V_R[IV + DIR];
+    const double p_L = V_L[IP], p_R = V_R[IP];
+
+    const double u_average = 0.5 * (un_L + un_R);
+    const double c_average = 0.5 * (c_L + c_R);
+    const double s_L = fmin(u_average - c_average, un_L - c_L);
+    const double s_R = fmax(u_average + c_average, un_R + c_R);
+    const double s_minus = fmin(0.0, s_L);
+    const double s_plus = fmax(0.0, s_R);
+    const double s_star = (p_R - p_L + rho_L * un_L * (s_L - un_L) - rho_R * un_R * (s_R - un_R)) /
+                          (rho_L * (s_L - un_L) - rho_R * (s_R - un_R));
+
+    /* conservative state and physical flux of one side */
+    auto side_QF = [&](const double (&V)[NEQ], double rho, double eps, double (&Q)[NEQ], double (&F)[NEQ]) {
+        const double un = V[IV + DIR];
+        const double p = V[IP];
+        double ke = V[IV] * V[IV];
+#pragma unroll
+        for (int a = 1; a < DIM; a++) ke = ke + V[IV + a] * V[IV + a];
+        if (Tr::MODEL == SS) {
+            Q[0] = V[0];
+#pragma unroll
+            for (int a = 0; a < DIM; a++) Q[1 + a] = V[0] * V[1 + a];
+            Q[IP] = V[0] * (eps + 0.5 * ke);
+            F[0] = Q[1 + DIR];
+#pragma unroll
+            for (int a = 0; a < DIM; a++) F[1 + a] = (a == DIR) ? Q[1 + DIR] * V[1 + a] + p : Q[1 + DIR] * V[1 + a];
+            F[IP] = un * (Q[IP] + p);
+        } else {
+#pragma unroll
+            for (int si = 0; si < NS; si++) Q[si] = V[si];
+#pragma unroll
+            for (int a = 0; a < DIM; a++) Q[IV + a] = rho * V[IV + a];
+            Q[IP] = rho * (eps + 0.5 * ke);
+#pragma unroll
+            for (int si = 0; si < NS - 1; si++) Q[IP + 1 + si] = V[IP + 1 + si];
+#pragma unroll
+            for (int si = 0; si < NS; si++) F[si] = un * V[si];
+#pragma unroll
+            for (int a = 0; a < DIM; a++) F[IV + a] = (a == DIR) ? un * Q[IV + a] + p : un * Q[IV + a];
+            F[IP] = un * (Q[IP] + p);
+#pragma unroll
+            for (int si = 0; si < NS - 1; si++) F[IP + 1 + si] = un * V[IP + 1 + si];
+        }
+    };
+
+    /* HLLC star state on the upwind side of the contact */
+    auto hllc = [&](const double (&V)[NEQ], const double (&Q)[NEQ], const double (&F)[NEQ], double rho, double s_K,
+                    double s_mp) {
+        const double un = V[IV + DIR];
+        const double p = V[IP];
+        const double Chi = (s_K - un) / (s_K - s_star);
+        double Qs[NEQ];
+#pragma unroll
+        for (int si = 0; si < NM; si++) Qs[si] = Chi * V[si];
+#pragma unroll
+        for (int a = 0; a < DIM; a++) Qs[IV + a] = (a == DIR) ? Chi * rho * s_star : Chi * Q[IV + a];
+        Qs[IP] = Chi * (Q[IP] + (s_star - un) * (rho * s_star + p / (s_K - un)));
+#pragma unroll
+        for (int e = IP + 1; e < NEQ; e++) Qs[e] = Chi * V[e];
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) Fm[e] = F[e] + s_mp * (Qs[e] - Q[e]);
+        vel_mid = un + s_mp * (Chi - 1.0);
+    };
+
+    if (!hybrid) {
+        double Q[NEQ], F[NEQ];
+        if (s_star > 0.0) {
+            side_QF(V_L, rho_L, eps_L, Q, F);
+            hllc(V_L, Q, F, rho_L, s_L, s_minus);
+        } else {
+            side_QF(V_R, rho_R, eps_R, Q, F);
+            hllc(V_R, Q, F, rho_R, s_R, s_plus);
+        }
+        return;
+    }
+
+    double Q_L[NEQ], Q_R[NEQ], F_L[NEQ], F_R[NEQ];
+    side_QF(V_L, rho_L, eps_L, Q_L, F_L);
+    side_QF(V_R, rho_R, eps_R, Q_R, F_R);
+    if (s_star > 0.0)
+        hllc(V_L, Q_L, F_L, rho_L, s_L, s_minus);
+    else
+        hllc(V_R, Q_R, F_R, rho_R, s_R, s_plus);
+
+    double diff[DIM];
+#pragma unroll
+    for (int a = 0; a < DIM; a++) diff[a] = V_R[IV + a] - V_L[IV + a];
+    double mag2 = diff[0] * diff[0];
+#pragma unroll
+    for (int a = 1; a < DIM; a++) mag2 = mag2 + diff[a] * diff[a];
+    const double vel_mag = sqrt(mag2);
+    double alpha_1, alpha_2;
+    if (vel_mag < HB2_EPS) {
+        alpha_1 = 1.0;
+        alpha_2 = 0.0;
+    } else {
+        alpha_1 = fabs(diff[DIR]) / vel_mag;
+        alpha_2 = sqrt(1.0 - alpha_1 * alpha_1);
+    }
+    const double beta_1 = 0.5 * (1.0 + alpha_1 / (alpha_1 + alpha_2));
+    const double beta_2 = 1.0 - beta_1;
+
+#pragma unroll
+    for (int e = 0; e < NEQ; e++) {
+        if (e == IV + DIR || e == IP) continue;
+        double F_HLL = (s_R * F_L[e] - s_L * F_R[e] + s_R * s_L * (Q_R[e] - Q_L[e])) / (s_R - s_L);
+        if (s_L > 0.0) F_HLL = F_L[e];
+        if (s_R < 0.0) F_HLL = F_R[e];
+        Fm[e] = beta_1 * Fm[e] + beta_2 * F_HLL;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * One midpoint flux from the six stencil cells f-3..f+2 (primitive variables + sound speed of
+ * cells L = 2 and R = 3, dilatation / vorticity magnitude of L and R).
+ * ---------------------------------------------------------------------------------------- */
+template <class Tr, int DIR, int MATH>
+HB2_HD void face_midpoint(const double (&V)[6][Tr::NEQ], double c_cellL, double c_cellR, double th_L, double th_R,
+                          double Om_L, double Om_R, const Consts& K, double (&Fm)[Tr::NEQ], double& vel_mid)
+{
+    constexpr int DIM = Tr::DIM, NS = Tr::NS, NEQ = Tr::NEQ, IV = Tr::IV, IP = Tr::IP;
+    const int p = K.weno_p;
+
+    double V_minus[NEQ], V_plus[NEQ];
+    const double c_avg = 0.5 * (c_cellL + c_cellR);
+
+    if (Tr::MODEL == SS) {
+        const double rho_avg = 0.5 * (V[2][0] + V[3][0]);
+        const double kn = -0.5 * rho_avg * c_avg; /* (-1/2*rho_avg)*c_avg */
+        const double kp = 0.5 * rho_avg * c_avg;
+        const double r_cc = 1.0 / (c_avg * c_avg);
+        const double r_rc = 1.0 / (rho_avg * c_avg);
+        double W[6], W0m, W0p, W1m, W1p, WLm, WLp;
+        /* field 0 */
+#pragma unroll
+        for (int m = 0; m < 6; m++) W[m] = kn * V[m][1 + DIR] + 0.5 * V[m][IP];
+        W0m = weno5js_side<MATH>(W[0], W[1], W[2], W[3], W[4], p);
+        W0p = weno5js_side<MATH>(W[5], W[4], W[3], W[2], W[1], p);
+        /* field 1 */
+#pragma unroll
+        for (int m = 0; m < 6; m++) W[m] = V[m][0] - r_cc * V[m][IP];
+        W1m = weno5js_side<MATH>(W[0], W[1], W[2], W[3], W[4], p);
+        W1p = weno5js_side<MATH>(W[5], W[4], W[3], W[2], W[1], p);
+        /* last field */
+#pragma unroll
+        for (int m = 0; m < 6; m++) W[m] = kp * V[m][1 + DIR] + 0.5 * V[m][IP];
+        WLm = weno5js_side<MATH>(W[0], W[1], W[2], W[3], W[4], p);
+        WLp = weno5js_side<MATH>(W[5], W[4], W[3], W[2], W[1], p);
+        /* tangential velocities are their own characteristic fields */
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+            if (a == DIR) continue;
+            V_minus[1 + a] = weno5js_side<MATH>(V[0][1 + a], V[1][1 + a], V[2][1 + a], V[3][1 + a], V[4][1 + a], p);
+            V_plus[1 + a] = weno5js_side<MATH>(V[5][1 + a], V[4][1 + a], V[3][1 + a], V[2][1 + a], V[1][1 + a], p);
+        }
+        V_minus[0] = r_cc * W0m + W1m + r_cc * WLm;
+        V_plus[0] = r_cc * W0p + W1p + r_cc * WLp;
+        V_minus[1 + DIR] = -r_rc * W0m + r_rc * WLm;
+        V_plus[1 + DIR] = -r_rc * W0p + r_rc * WLp;
+        V_minus[IP] = W0m + WLm;
+        V_plus[IP] = W0p + WLp;
+    } else {
+        double rho_L = 0.0, rho_R = 0.0;
+#pragma unroll
+        for (int si = 0; si < NS; si++) {
+            rho_L += V[2][si];
+            rho_R += V[3][si];
+        }
+        const double rho_avg = 0.5 * (rho_L + rho_R);
+        const double rc = rho_avg * c_avg;
+        const double r_rc = 1.0 / rc;
+        double W[6], W0m, W0p, WLm, WLp;
+#pragma unroll
+        for (int m = 0; m < 6; m++) W[m] = V[m][IV + DIR] - r_rc * V[m][IP];
+        W0m = weno5js_side<MATH>(W[0], W[1], W[2], W[3], W[4], p);
+        W0p = weno5js_side<MATH>(W[5], W[4], W[3], W[2], W[1], p);
+#pragma unroll
+        for (int m = 0; m < 6; m++) W[m] = V[m][IV + DIR] + r_rc * V[m][IP];
+        WLm = weno5js_side<MATH>(W[0], W[1], W[2], W[3], W[4], p);
+        WLp = weno5js_side<MATH>(W[5], W[4], W[3], W[2], W[1], p);
+#pragma unroll
+        for (int si = 0; si < NS; si++) {
+            const double Zrho_avg = 0.5 * (V[2][si] + V[3][si]);
+            const double zc = Zrho_avg / (rc * c_avg);
+#pragma unroll
+            for (int m = 0; m < 6; m++) W[m] = V[m][si] - zc * V[m][IP];
+            const double Wm = weno5js_side<MATH>(W[0], W[1], W[2], W[3], W[4], p);
+            const double Wp = weno5js_side<MATH>(W[5], W[4], W[3], W[2], W[1], p);
+            const double yn = -0.5 * Zrho_avg / c_avg;
+            const double yp = 0.5 * Zrho_avg / c_avg;
+            V_minus[si] = yn * W0m + Wm + yp * WLm;
+            V_plus[si] = yn * W0p + Wp + yp * WLp;
+        }
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+            if (a == DIR) continue;
+            V_minus[IV + a] = weno5js_side<MATH>(V[0][IV + a], V[1][IV + a], V[2][IV + a], V[3][IV + a], V[4][IV + a], p);
+            V_plus[IV + a] = weno5js_side<MATH>(V[5][IV + a], V[4][IV + a], V[3][IV + a], V[2][IV + a], V[1][IV + a], p);
+        }
+#pragma unroll
+        for (int si = 0; si < NS - 1; si++) {
+            const int e = IP + 1 + si;
+            V_minus[e] = weno5js_side<MATH>(V[0][e], V[1][e], V[2][e], V[3][e], V[4][e], p);
+            V_plus[e] = weno5js_side<MATH>(V[5][e], V[4][e], V[3][e], V[2][e], V[1][e], p);
+        }
+        V_minus[IV + DIR] = 0.5 * W0m + 0.5 * WLm;
+        V_plus[IV + DIR] = 0.5 * W0p + 0.5 * WLp;
+        const double kn = -0.5 * rho_avg * c_avg;
+        const double kp = 0.5 * rho_avg * c_avg;
+        V_minus[IP] = kn * W0m + kp * WLm;
+        V_plus[IP] = kn * W0p + kp * WLp;
+    }
+
+    /* bounds check and first-order fallback */
+    const int ok = side_bounded<Tr>(V_minus, K) & side_bounded<Tr>(V_plus, K);
+    if (!ok) {
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) {
+            V_minus[e] = V[2][e];
+            V_plus[e] = V[3][e];
+        }
+    }
+
+    /* Ducros-like sensor */
+    const double theta_avg = 0.5 * (th_L + th_R);
+    const double Omega_avg = 0.5 * (Om_L + Om_R);
+    const double s = -theta_avg / (fabs(theta_avg) + Omega_avg + HB2_EPS);
+
+    riemann<Tr, DIR>(V_minus, V_plus, K, s > 0.65, Fm, vel_mid);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * helpers shared by the sweeps
+ * ---------------------------------------------------------------------------------------- */
+template <class Tr>
+HB2_HD void load_cons(const DirArgs& A, long long x, double (&q)[Tr::NCOMP])
+{
+#pragma unroll
+    for (int cix = 0; cix < Tr::NCOMP; cix++) q[cix] = A.Q[cix][x];
+}
+
+/* RK update of one interior cell from the complete right-hand side (FUSED, last direction).
+ * Order of Euler.cpp:1479, 1544-1548: zero; += alpha_n*U_n for alpha_n != 0; += beta*(...). */
+template <class Tr>
+HB2_HD void rk_update_cell(const DirArgs& A, long long x, const double (&rhs)[Tr::NEQ])
+{
+    constexpr int NEQ = Tr::NEQ, NS = Tr::NS, DIM = Tr::DIM;
+    double Unew[NEQ];
+#pragma unroll
+    for (int e = 0; e < NEQ; e++) {
+        double u = 0.0;
+        for (int n = 0; n < A.ncoef; n++)
+            if (A.alpha[n] != 0.0) u += A.alpha[n] * A.Uint[n][e][x];
+        u += A.beta * rhs[e];
+        Unew[e] = u;
+        A.Uout[e][x] = u;
+    }
+    if (Tr::MODEL == FE) {
+        double zl = 1.0;
+#pragma unroll
+        for (int si = 0; si < NS - 1; si++) zl -= Unew[NS + DIM + 1 + si];
+        A.Uout[NEQ][x] = zl;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * y / z sweep: one thread marches one pencil segment.
+ *   i  : x index of the pencil (lanes run along x -> coalesced)
+ *   t  : the other transverse index (k for a y sweep, j for a z sweep; 0 in 2D)
+ *   seg: segment number along the sweep axis
+ * ---------------------------------------------------------------------------------------- */
+template <class Tr, int DIR, int MATH>
+HB2_HD void march_pencil(const DirArgs& A, int i, int t, int seg)
+{
+    constexpr int DIM = Tr::DIM, NEQ = Tr::NEQ, NCOMP = Tr::NCOMP, IV = Tr::IV, IP = Tr::IP, NS = Tr::NS;
+    constexpr bool LAST = (DIR == DIM - 1);
+    static_assert(DIR >= 1, "march_pencil handles the strided sweeps");
+    const Geom& G = A.G;
+    const int N = G.n[DIR];
+    const int c0 = seg * A.seg_len;
+    if (c0 >= N) return;
+    const int c1 = (c0 + A.seg_len < N) ? c0 + A.seg_len : N;
+    const bool fused = (A.mode == MODE_FUSED);
+
+    /* coordinates of sweep cell 0 */
+    const int j0 = (DIR == 1) ? 0 : t;
+    const int k0 = (DIR == 2) ? 0 : ((DIM == 3) ? t : 0);
+    const long long base = cidx(G, i, j0, k0);
+    const long long st = G.cs[DIR];
+    const double dxd = G.dx[DIR];
+
+    double V[6][NEQ];
+    double cs_[6];
+    double q[NCOMP];
+    /* preload cells c0-4 .. c0 into stencil positions 1..5 */
+#pragma unroll
+    for (int m = 1; m < 6; m++) {
+        load_cons<Tr>(A, base + (long long)(c0 - 5 + m) * st, q);
+        cons_to_prim<Tr>(q, A.K, V[m], cs_[m]);
+    }
+#pragma unroll
+    for (int e = 0; e < NEQ; e++) V[0][e] = V[1][e];
+    cs_[0] = cs_[1];
+
+    double Fm_p[NEQ], Fm_pp[NEQ], Fn_prev[NEQ], Ff_prev[NEQ];
+    double um_1 = 0.0, um_2 = 0.0, um_3 = 0.0; /* u_mid of faces f-1, f-2, f-3 */
+#pragma unroll
+    for (int e = 0; e < NEQ; e++) Fm_p[e] = Fm_pp[e] = Fn_prev[e] = Ff_prev[e] = 0.0;
+
+    for (int f = c0 - 1; f <= c1 + 1; f++) {
+        /* rotate the stencil and bring in cell f+2 */
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+#pragma unroll
+            for (int e = 0; e < NEQ; e++) V[m][e] = V[m + 1][e];
+            cs_[m] = cs_[m + 1];
+        }
+        const long long xR = base + (long long)f * st; /* cell f (R of face f) */
+        load_cons<Tr>(A, xR + 2 * st, q);
+        cons_to_prim<Tr>(q, A.K, V[5], cs_[5]);
+
+        double Fm[NEQ], um;
+        face_midpoint<Tr, DIR, MATH>(V, cs_[2], cs_[3], A.theta[xR - st], A.theta[xR], A.Omega[xR - st], A.Omega[xR],
+                                     A.K, Fm, um);
+
+        if (f >= c0 + 1) {
+            /* face g = f-1 is complete: cells g-1 (stencil pos 1) and g (pos 2) */
+            const int g = f - 1;
+            const long long xg = xR - st;
+            double Fn[NEQ];
+            load_cons<Tr>(A, xg, q);
+            node_flux<Tr, DIR>(q, V[2], Fn);
+            if (g == c0) {
+                double ql[NCOMP];
+                load_cons<Tr>(A, xg - st, ql);
+                node_flux<Tr, DIR>(ql, V[1], Fn_prev);
+            }
+            double Ff[NEQ];
+#pragma unroll
+            for (int e = 0; e < NEQ; e++)
+                Ff[e] = A.dt * (1.0 / 30.0 * (Fm[e] + Fm_pp[e]) - 3.0 / 10.0 * (Fn[e] + Fn_prev[e]) + 23.0 / 15.0 * Fm_p[e]);
+
+            if (!fused) {
+                if (g < c1 || g == N) {
+                    const int ii = i, jj = (DIR == 1) ? g : j0, kk = (DIR == 2) ? g : k0;
+                    const long long sx = sidx<DIR>(G, ii, jj, kk);
+#pragma unroll
+                    for (int e = 0; e < NEQ; e++) A.F[e][sx] = Ff[e];
+                }
+            }
+            if (g >= c0 + 1) {
+                /* cell cc = g-1 = f-2 (stencil pos 1) has both faces */
+                const int cc = g - 1;
+                const int jj = (DIR == 1) ? cc : j0, kk = (DIR == 2) ? cc : k0;
+                const long long ix = iidx(G, i, jj, kk);
+                double Tsum = 0.0;
+                if (Tr::ADV) {
+                    const double Td = (3.0 / 2.0 * (um_1 - um_2) - 3.0 / 10.0 * (V[2][IV + DIR] - V[0][IV + DIR]) +
+                                       1.0 / 30.0 * (um - um_3)) / dxd;
+                    Tsum = A.T[ix] + Td;
+                    if (!LAST) A.T[ix] = Tsum;
+                }
+                if (fused) {
+                    double rhs[NEQ];
+#pragma unroll
+                    for (int e = 0; e < NEQ; e++) rhs[e] = A.R[e][ix] - (Ff[e] - Ff_prev[e]) / dxd;
+                    if (LAST) {
+                        if (Tr::ADV) {
+#pragma unroll
+                            for (int si = 0; si < NS - 1; si++) {
+                                const int e = IP + 1 + si;
+                                rhs[e] = rhs[e] + A.dt * V[1][e] * Tsum;
+                            }
+                        }
+                        rk_update_cell<Tr>(A, xg - st, rhs);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < NEQ; e++) A.R[e][ix] = rhs[e];
+                    }
+                } else if (LAST && Tr::ADV) {
+#pragma unroll
+                    for (int si = 0; si < NS - 1; si++) {
+                        const int e = IP + 1 + si;
+                        A.S[e][ix] += A.dt * V[1][e] * Tsum;
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < NEQ; e++) {
+                Fn_prev[e] = Fn[e];
+                Ff_prev[e] = Ff[e];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) {
+            Fm_pp[e] = Fm_p[e];
+            Fm_p[e] = Fm[e];
+        }
+        um_3 = um_2;
+        um_2 = um_1;
+        um_1 = um;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * x sweep: a block works on BX consecutive linear positions of the ghost-box array (rows of
+ * the same k-plane are contiguous, so a run may cross row ends; positions whose face index is
+ * outside -1..N+1 are skipped).  Position p <-> face whose RIGHT cell has linear index p.
+ *   tile owns positions p0+1 .. p0+BX-3.
+ * Shared arrays (doubles):  sV[NEQ+1][BX+5]  primitive variables + sound speed of cells p0-3..p0+BX+1
+ *                           sN[NEQ][BX+5]    node fluxes of those cells
+ *                           sM[NEQ+1][BX]    midpoint fluxes + HLLC midpoint velocity
+ *                           sF[NEQ][BX]      face fluxes
+ * The phase functions are called for every thread index with a barrier between phases.
+ * ---------------------------------------------------------------------------------------- */
+template <class Tr>
+struct XSmem {
+    static constexpr int NEQ = Tr::NEQ;
+    HB2_HD static long long doubles(int BX) { return (long long)(2 * NEQ + 1) * (BX + 5) + (long long)(2 * NEQ + 1) * BX; }
+    double* sV;
+    double* sN;
+    double* sM;
+    double* sF;
+    int BX;
+    HB2_HD XSmem(double* base, int bx) : BX(bx)
+    {
+        sV = base;
+        sN = sV + (long long)(NEQ + 1) * (BX + 5);
+        sM = sN + (long long)NEQ * (BX + 5);
+        sF = sM + (long long)(NEQ + 1) * BX;
+    }
+};
+
+/* decode a linear position inside plane k (row-contiguous) into the x index i (may be a ghost) and row j */
+HB2_HD void xpos_decode(const Geom& G, long long p, int k, int& i, int& j)
+{
+    const long long plane0 = (long long)(k + G.g[2]) * G.cs[2];
+    const long long r = p - plane0;
+    j = (int)(r / G.gd[0]) - G.g[1];
+    i = (int)(r % G.gd[0]) - G.g[0];
+}
+
+template <class Tr, int MATH>
+HB2_HD void xsweep_phase_load(const DirArgs& A, const XSmem<Tr>& sm, long long p0, int idx)
+{
+    constexpr int NEQ = Tr::NEQ, NCOMP = Tr::NCOMP;
+    if (idx >= sm.BX + 5) return;
+    long long x = p0 - 3 + idx;
+    /* clamp: positions outside the allocation are never used by a valid face */
+    if (x < 0) x = 0;
+    if (x >= A.G.ncell_g) x = A.G.ncell_g - 1;
+    double q[NCOMP], V[NEQ], c, Fn[NEQ];
+    load_cons<Tr>(A, x, q);
+    cons_to_prim<Tr>(q, A.K, V, c);
+    node_flux<Tr, 0>(q, V, Fn);
+#pragma unroll
+    for (int e = 0; e < NEQ; e++) {
+        sm.sV[(long long)e * (sm.BX + 5) + idx] = V[e];
+        sm.sN[(long long)e * (sm.BX + 5) + idx] = Fn[e];
+    }
+    sm.sV[(long long)NEQ * (sm.BX + 5) + idx] = c;
+}
+
+template <class Tr, int MATH>
+HB2_HD void xsweep_phase_mid(const DirArgs& A, const XSmem<Tr>& sm, long long p0, int k, int t)
+{
+    constexpr int NEQ = Tr::NEQ;
+    const int W = sm.BX + 5;
+    const long long p = p0 + t;
+    int i, j;
+    xpos_decode(A.G, p, k, i, j);
+    if (i < -1 || i > A.G.n[0] + 1 || j < 0 || j >= A.G.n[1]) return;
+    double V[6][NEQ];
+#pragma unroll
+    for (int m = 0; m < 6; m++)
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) V[m][e] = sm.sV[(long long)e * W + t + m]; /* cell p-3+m <-> idx t+m */
+    const double cL = sm.sV[(long long)NEQ * W + t + 2], cR = sm.sV[(long long)NEQ * W + t + 3];
+    double Fm[NEQ], um;
+    face_midpoint<Tr, 0, MATH>(V, cL, cR, A.theta[p - 1], A.theta[p], A.Omega[p - 1], A.Omega[p], A.K, Fm, um);
+#pragma unroll
+    for (int e = 0; e < NEQ; e++) sm.sM[(long long)e * sm.BX + t] = Fm[e];
+    sm.sM[(long long)NEQ * sm.BX + t] = um;
+}
+
+template <class Tr, int MATH>
+HB2_HD void xsweep_phase_face(const DirArgs& A, const XSmem<Tr>& sm, long long p0, int k, int t)
+{
+    constexpr int NEQ = Tr::NEQ;
+    const int W = sm.BX + 5;
+    if (t < 1 || t > sm.BX - 2) return;
+    const long long p = p0 + t;
+    int i, j;
+    xpos_decode(A.G, p, k, i, j);
+    if (i < 0 || i > A.G.n[0] || j < 0 || j >= A.G.n[1]) return;
+    const bool owned = (t <= sm.BX - 3);
+    const int kk = (Tr::DIM == 3) ? k : 0;
+#pragma unroll
+    for (int e = 0; e < NEQ; e++) {
+        const double* M = sm.sM + (long long)e * sm.BX;
+        const double* Nf = sm.sN + (long long)e * W;
+        const double Ff = A.dt * (1.0 / 30.0 * (M[t + 1] + M[t - 1]) - 3.0 / 10.0 * (Nf[t + 3] + Nf[t + 2]) + 23.0 / 15.0 * M[t]);
+        sm.sF[(long long)e * sm.BX + t] = Ff;
+        if (A.mode == MODE_EMIT && owned) A.F[e][sidx<0>(A.G, i, j, kk)] = Ff;
+    }
+}
+
+template <class Tr, int MATH>
+HB2_HD void xsweep_phase_cell(const DirArgs& A, const XSmem<Tr>& sm, long long p0, int k, int t)
+{
+    constexpr int NEQ = Tr::NEQ, IV = Tr::IV;
+    const int W = sm.BX + 5;
+    if (t < 1 || t > sm.BX - 3) return;
+    const long long p = p0 + t;
+    int i, j;
+    xpos_decode(A.G, p, k, i, j);
+    if (i < 0 || i >= A.G.n[0] || j < 0 || j >= A.G.n[1]) return;
+    const int kk = (Tr::DIM == 3) ? k : 0;
+    const long long ix = iidx(A.G, i, j, kk);
+    const double dxd = A.G.dx[0];
+    if (Tr::ADV) {
+        const double* um = sm.sM + (long long)NEQ * sm.BX;
+        const double* un = sm.sV + (long long)(IV + 0) * W;
+        /* cell p <-> idx t+3; neighbours idx t+4 / t+2.  faces: t = low face of the cell */
+        const double Td = (3.0 / 2.0 * (um[t + 1] - um[t]) - 3.0 / 10.0 * (un[t + 4] - un[t + 2]) +
+                           1.0 / 30.0 * (um[t + 2] - um[t - 1])) / dxd;
+        A.T[ix] = Td;
+    }
+    if (A.mode == MODE_FUSED) {
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) {
+            const double* F = sm.sF + (long long)e * sm.BX;
+            A.R[e][ix] = -(F[t + 1] - F[t]) / dxd;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * sensor inputs: dilatation and vorticity magnitude of cell (i,j,k), i,j,k in -2..N+1
+ * (ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:1523-1659, 2D :663-731;
+ *  DerivativeFirstOrder.cpp:382, 601).  Velocities are exact quotients so that the hard
+ *  s > 0.65 switch sees the reference's bits.
+ * ---------------------------------------------------------------------------------------- */
+template <class Tr>
+HB2_HD void sensor_cell(const Geom& G, const double* const* Q, long long x, double& theta, double& Omega)
+{
+    constexpr int DIM = Tr::DIM, NM = Tr::NM;
+    double grad[DIM][DIM]; /* grad[a][b] = d u_a / d x_b */
+#pragma unroll
+    for (int b = 0; b < DIM; b++) {
+        const long long xp = x + G.cs[b], xm = x - G.cs[b];
+        double rp = 0.0, rm = 0.0;
+        if (Tr::MODEL == SS) {
+            rp = Q[0][xp];
+            rm = Q[0][xm];
+        } else {
+#pragma unroll
+            for (int si = 0; si < NM; si++) {
+                rp += Q[si][xp];
+                rm += Q[si][xm];
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+            const double up = Q[NM + a][xp] / rp;
+            const double um = Q[NM + a][xm] / rm;
+            grad[a][b] = (0.5 * (up - um)) / G.dx[b];
+        }
+    }
+    if (DIM == 2) {
+        theta = grad[0][0] + grad[1][1];
+        Omega = fabs(grad[1][0] - grad[0][1]);
+    } else {
+        theta = grad[0][0] + grad[1][1] + grad[2 % DIM][2 % DIM];
+        const double omega_x = grad[2 % DIM][1] - grad[1][2 % DIM];
+        const double omega_y = grad[0][2 % DIM] - grad[2 % DIM][0];
+        const double omega_z = grad[1][0] - grad[0][1];
+        Omega = sqrt(omega_x * omega_x + omega_y * omega_y + omega_z * omega_z);
+    }
+}
+
+}  // namespace hb2

@@ -1,0 +1,46 @@
+/*
+ * hb2_ops.h -- internal launch table shared by hb2_sweeps.cu (compiled twice: exact / fast
+ * arithmetic) and hb2_abi.cu.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include "hb2_core.cuh"
+
+namespace hb2 {
+
+struct AdvanceArgs {
+    Geom G;
+    int model, ns, neq, ncomp;
+    int ncoef;
+    double alpha[HB2_MAXS], beta[HB2_MAXS], gamma[HB2_MAXS];
+    const double* Uint[HB2_MAXS][HB2_MAXC];
+    const double* Fint[HB2_MAXS][3 * HB2_MAXE];
+    const double* Sint[HB2_MAXS][HB2_MAXE];
+    double* Uout[HB2_MAXC];
+    double* Facc[3 * HB2_MAXE]; /* may be null */
+    double* Sacc[HB2_MAXE];
+};
+
+struct QTab {
+    const double* p[HB2_MAXC];
+};
+
+struct LaunchCfg {
+    int model, dim, ns;
+    int bx;          /* x-sweep block width */
+    int march_block; /* threads per block of the marching sweeps */
+};
+
+struct Ops {
+    /* theta / Omega on cells -2..N+1 (always exact arithmetic) */
+    int (*sensor)(const LaunchCfg&, const Geom&, const QTab& Q, double* theta, double* Omega, cudaStream_t);
+    /* one direction sweep */
+    int (*sweep)(const LaunchCfg&, int dir, const DirArgs&, cudaStream_t);
+    /* Euler::advanceSingleStepOnPatch from materialised fluxes */
+    int (*advance)(const AdvanceArgs&, cudaStream_t);
+};
+
+const Ops* ops_exact();
+const Ops* ops_fast();
+
+}  // namespace hb2

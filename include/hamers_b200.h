@@ -1,0 +1,158 @@
+/*
+ * hamers_b200.h -- C ABI of the B200-native WCNS5-JS / HLLC-HLL convective-flux path.
+ *
+ * This is the drop-in boundary for ONE hot path of HAMeRS (all citations are path:line under
+ * the reference tree):
+ *
+ *   ConvectiveFluxReconstructor::computeConvectiveFluxAndSourceOnPatch
+ *       include/flow/convective_flux_reconstructors/ConvectiveFluxReconstructor.hpp:73-81
+ *       (implementation replaced: src/flow/convective_flux_reconstructors/WCNS56/
+ *        ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:39-2656 with the WCNS5-JS interpolator
+ *        ConvectiveFluxReconstructorWCNS5-JS-HLLC-HLL.cpp:234-737)
+ *   RungeKuttaPatchStrategy::{computeFluxesAndSourcesOnPatch, advanceSingleStepOnPatch}
+ *       include/algs/patch_strategy/RungeKuttaPatchStrategy.hpp:149-190
+ *       (Euler.cpp:904-999 and :1003-1679)
+ *   the same-level ghost fill that RungeKuttaLevelIntegrator::advanceLevel triggers per stage
+ *       src/algs/integrator/RungeKuttaLevelIntegrator.cpp:1568, :1701
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every entry point returns 0 on success and a negative
+ *     code on failure, with a message available from hb2_last_error() (the C++ wrapper turns
+ *     non-zero into TBOX_ERROR, the reference's only error convention).
+ *   - arrays are SAMRAI pdat layouts: cell data with ghost width g = 4,
+ *     x fastest, one pointer per depth component; side data ghost 0, one pointer per
+ *     (direction, component): flux[dir*num_eqn + e].
+ *   - conservative components, in order:
+ *       single-species : rho, rho*u, rho*v, (rho*w), E                      (num_comp = dim+2)
+ *       five-eqn       : Zrho_1..Zrho_ns, rho*u, rho*v, (rho*w), E, Z_1..Z_ns (num_comp = dim+2ns+1;
+ *                        the last volume fraction is stored but is not an equation)
+ *   - pointers in the *_dev calls are DEVICE pointers on the plan's device and must stay valid
+ *     until the plan's stream has been synchronised; the *_host calls take HOST pointers and do
+ *     the H2D / D2H copies themselves (the reference-facing, host-memory drop-in).
+ *   - a plan is not re-entrant (the reference's FlowModel is a stateful singleton too,
+ *     FlowModelSingleSpecies.cpp:706-712); use one plan per patch shape per calling thread.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef HAMERS_B200_H
+#define HAMERS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB2_MAX_SPECIES 4
+#define HB2_MAX_EQ 12
+#define HB2_MAX_COMP 13
+#define HB2_MAX_STAGES 4
+#define HB2_GHOSTS 4            /* ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:22 */
+
+#define HB2_SINGLE_SPECIES 0    /* FlowModelManager.cpp:20 "SINGLE_SPECIES" */
+#define HB2_FIVE_EQN_ALLAIRE 1  /* FlowModelManager.cpp:44 "FIVE_EQN_ALLAIRE" */
+
+/* arithmetic variants */
+#define HB2_MATH_EXACT 0        /* reference operation order, no FMA contraction: bit-identical to the oracle */
+#define HB2_MATH_FAST 1         /* FMA contraction + reciprocal sharing: <= 1e-12 relative of the oracle */
+
+typedef struct hb2_patch_desc {
+    int32_t dim;                              /* 2 or 3 */
+    int32_t n[3];                             /* interior cells of the patch */
+    int32_t flow_model;                       /* HB2_SINGLE_SPECIES | HB2_FIVE_EQN_ALLAIRE */
+    int32_t num_species;                      /* 1, or 2 for five-eqn */
+    double species_gamma[HB2_MAX_SPECIES];    /* Equation_of_state_mixing_rules{species_gamma} */
+    double dx[3];                             /* CartesianPatchGeometry::getDx() */
+    int32_t weno_p;                           /* Convective_flux_reconstructor{constant_p}, default 2 */
+    int32_t math;                             /* HB2_MATH_EXACT | HB2_MATH_FAST */
+    int32_t device;                           /* CUDA device ordinal, -1 = current */
+} hb2_patch_desc;
+
+typedef struct hb2_plan_s* hb2_plan_t;
+
+/* ---- introspection ------------------------------------------------------------------ */
+const char* hb2_last_error(void);
+const char* hb2_version(void);
+int hb2_device_count(int32_t* count);
+int hb2_num_eqn(const hb2_patch_desc* d, int32_t* num_eqn);      /* FlowModel::getNumberOfEquations() */
+int hb2_num_comp(const hb2_patch_desc* d, int32_t* num_comp);
+/* ConvectiveFluxReconstructor::getConvectiveFluxNumberOfGhostCells(): 4 in every direction */
+int hb2_num_ghosts(const hb2_patch_desc* d, int32_t ghosts[3]);
+/* element counts of one component: ghost-box cell data, ghost-0 cell data, ghost-0 side data */
+int64_t hb2_cell_ghost_size(const hb2_patch_desc* d);
+int64_t hb2_cell_size(const hb2_patch_desc* d);
+int64_t hb2_side_size(const hb2_patch_desc* d, int32_t dir);
+
+/* ---- plan --------------------------------------------------------------------------- */
+int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* plan);
+int hb2_plan_destroy(hb2_plan_t plan);
+/* cudaStream_t to launch on (NULL = the plan's own stream). */
+int hb2_plan_set_stream(hb2_plan_t plan, void* cuda_stream);
+int hb2_plan_synchronize(hb2_plan_t plan);
+/* number of kernels this plan has launched since creation (bench.py's gpu_launches) */
+int64_t hb2_plan_launch_count(hb2_plan_t plan);
+/* bytes of device workspace the plan owns */
+int64_t hb2_plan_workspace_bytes(hb2_plan_t plan);
+
+/* ---- the hot path, device-resident data ------------------------------------------------ */
+
+/* computeConvectiveFluxAndSourceOnPatch.  Q: num_comp ghost-box components (ghosts filled by
+ * the caller).  flux: dim*num_eqn side arrays, fully overwritten on faces 0..N of each
+ * direction, ALREADY multiplied by dt.  source: num_eqn ghost-0 cell arrays, "+=" and only for
+ * ADVECTIVE equations (the five-eqn volume fractions); entries of non-advective equations may
+ * be NULL. */
+int hb2_compute_flux_and_source_dev(hb2_plan_t plan, const double* const* Q, double dt,
+                                    double* const* flux, double* const* source);
+
+/* advanceSingleStepOnPatch.  ncoef = RK stage number + 1.  U_int[m*num_comp + c] are the
+ * intermediate states (ghost-box layout), F_int[m*dim*num_eqn + dir*num_eqn + e] and
+ * S_int[m*num_eqn + e] their fluxes / sources (rows with beta[m] == 0 and gamma[m] == 0 may be
+ * NULL).  U_out: the SCRATCH state; its interior is overwritten (ghosts are left untouched: they
+ * are refilled before they are next read).  F_acc / S_acc (may be NULL): the gamma-weighted
+ * accumulation used by AMR flux correction, "+=". */
+int hb2_advance_stage_dev(hb2_plan_t plan, int32_t ncoef,
+                          const double* alpha, const double* beta, const double* gamma,
+                          const double* const* U_int, const double* const* F_int,
+                          const double* const* S_int, double* const* U_out,
+                          double* const* F_acc, double* const* S_acc);
+
+/* computeFluxesAndSourcesOnPatch + advanceSingleStepOnPatch in one pass that never writes the
+ * side fluxes to HBM (uniform level, no AMR flux sums).  Requires beta[m] == 0 for m < ncoef-1
+ * (true for SSP-RK3 and every "newest flux only" table); the flux is evaluated on
+ * U_int[ncoef-1].  U_out must not alias any U_int. */
+int hb2_fused_stage_dev(hb2_plan_t plan, int32_t ncoef, const double* alpha, const double* beta,
+                        const double* const* U_int, double dt, double* const* U_out);
+
+/* Same-level periodic ghost fill of one patch that covers the whole periodic level in the
+ * directions flagged in periodic_mask (bit d).  All 4-cell ghosts incl. edges and corners. */
+int hb2_fill_ghosts_periodic_dev(hb2_plan_t plan, double* const* U, int32_t periodic_mask);
+
+/* Halo exchange building blocks for GPU-resident neighbouring patches: copy the box
+ * [lo, hi) (cell indices relative to the interior origin, may extend into ghosts) of every
+ * component to / from a contiguous buffer (component-major, x fastest). */
+int hb2_pack_box_dev(hb2_plan_t plan, const double* const* U, const int32_t lo[3],
+                     const int32_t hi[3], double* buffer);
+int hb2_unpack_box_dev(hb2_plan_t plan, double* const* U, const int32_t lo[3],
+                       const int32_t hi[3], const double* buffer);
+
+/* Euler::computeSpectralRadiusesAndStableDtOnPatch building block:
+ * max over the interior of (|u_d| + c)/dx_d per direction, result in out_dev[0..dim-1]. */
+int hb2_max_wave_speed_dev(hb2_plan_t plan, const double* const* Q, double* out_dev);
+
+/* ---- the hot path, HOST buffers (H2D + kernels + D2H inside the call) ------------------- */
+int hb2_compute_flux_and_source_host(hb2_plan_t plan, const double* const* Q_host, double dt,
+                                     double* const* flux_host, double* const* source_host);
+/* One RK stage on host memory: uploads U_int rows (ghost-filled by the caller), runs the fused
+ * stage, downloads U_out (whole ghost box; only its interior is meaningful). */
+int hb2_fused_stage_host(hb2_plan_t plan, int32_t ncoef, const double* alpha, const double* beta,
+                         const double* const* U_int_host, double dt, double* const* U_out_host);
+
+/* ---- measurement helpers --------------------------------------------------------------- */
+/* Dependent-free DFMA loop on every SM; returns achieved FP64 FLOP/s (2 per FMA). */
+int hb2_probe_fp64_peak(int32_t device, double seconds_hint, double* flops_per_s);
+/* device-to-device copy bandwidth, bytes read + written per second */
+int hb2_probe_hbm_bandwidth(int32_t device, int64_t bytes, double* bytes_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAMERS_B200_H */

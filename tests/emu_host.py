@@ -1,0 +1,80 @@
+"""ctypes front end of the TEST-ONLY host emulation of the CUDA sweeps (tests/host_emu/emu.cpp)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "host_emu", "libhb2_emu.so")
+_SRC = os.path.join(_HERE, "host_emu", "emu.cpp")
+_CORE = os.path.join(_HERE, "..", "hamers_b200", "csrc", "hb2_core.cuh")
+_LIB = None
+
+
+class EmuDesc(C.Structure):
+    _fields_ = [("dim", C.c_int), ("n", C.c_int * 3), ("model", C.c_int), ("ns", C.c_int),
+                ("gamma", C.c_double * 4), ("dx", C.c_double * 3), ("weno_p", C.c_int),
+                ("math", C.c_int), ("bx", C.c_int), ("seg_len", C.c_int)]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        stale = (not os.path.exists(_SO)) or any(
+            os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_SO) for s in (_SRC, _CORE))
+        if stale:
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
+                                   "-Wno-unknown-pragmas", "-o", _SO, _SRC])
+        _LIB = C.CDLL(_SO)
+    return _LIB
+
+
+def _pp(arrs):
+    P = (C.POINTER(C.c_double) * len(arrs))()
+    for i, a in enumerate(arrs):
+        if a is not None:
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+            P[i] = a.ctypes.data_as(C.POINTER(C.c_double))
+    return P
+
+
+def _desc(desc, math, bx, seg_len):
+    d = EmuDesc()
+    d.dim = desc.dim
+    for a in range(3):
+        d.n[a] = int(desc.n[a]) if a < desc.dim else 1
+        d.dx[a] = float(desc.dx[a]) if a < desc.dim else 1.0
+    d.model, d.ns = desc.model, desc.ns
+    for i, g in enumerate(desc.gamma):
+        d.gamma[i] = g
+    d.weno_p, d.math, d.bx, d.seg_len = desc.weno_p, math, bx, seg_len
+    return d
+
+
+def flux_and_source(desc, Q, dt, math=0, bx=128, seg_len=0, source=None):
+    neq, dim = desc.neq, desc.dim
+    F = [np.full((neq,) + desc.side_shape(a), np.nan) for a in range(dim)]
+    S = np.zeros((neq,) + desc.cell_shape) if source is None else source
+    d = _desc(desc, math, bx, seg_len)
+    Q = np.ascontiguousarray(Q)
+    rc = lib().emu_flux_and_source(C.byref(d), _pp([Q[c] for c in range(desc.ncomp)]), C.c_double(dt),
+                                   _pp([F[a][e] for a in range(dim) for e in range(neq)]),
+                                   _pp([S[e] for e in range(neq)]))
+    assert rc == 0
+    return F, S
+
+
+def fused_stage(desc, alpha, beta, U_int, dt, math=0, bx=128, seg_len=0):
+    ncoef = len(alpha)
+    U_out = np.zeros((desc.ncomp,) + desc.ghost_shape)
+    d = _desc(desc, math, bx, seg_len)
+    Us = [np.ascontiguousarray(u) for u in U_int]
+    tab = _pp([Us[m][c] for m in range(ncoef) for c in range(desc.ncomp)])
+    a = (C.c_double * ncoef)(*[float(x) for x in alpha])
+    b = (C.c_double * ncoef)(*[float(x) for x in beta])
+    rc = lib().emu_fused_stage(C.byref(d), ncoef, a, b, tab, C.c_double(dt), _pp([U_out[c] for c in range(desc.ncomp)]))
+    assert rc == 0
+    return U_out

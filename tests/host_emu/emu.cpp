@@ -1,0 +1,147 @@
+/*
+ * emu.cpp -- TEST-ONLY host emulation of the CUDA sweeps (never part of the product library).
+ *
+ * Compiles hamers_b200/csrc/hb2_core.cuh with g++ and drives the very same per-thread functions
+ * the kernels call (march_pencil, xsweep_phase_*, sensor_cell) from plain loops that stand in
+ * for the CUDA grid.  It exists because this container has no GPU: it lets the CPU test suite
+ * check the kernels' indexing and arithmetic against the oracle before any GPU time is spent.
+ * The GPU parity tests (pytest -m gpu) remain the parity tests proper.
+ */
+#include "../../hamers_b200/csrc/hb2_core.cuh"
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace hb2;
+
+struct EmuDesc {
+    int dim, n[3], model, ns;
+    double gamma[4], dx[3];
+    int weno_p, math, bx, seg_len;
+};
+
+static void make_geom(const EmuDesc* d, Geom* G)
+{
+    G->dim = d->dim;
+    for (int a = 0; a < 3; a++) {
+        G->n[a] = (a < d->dim) ? d->n[a] : 1;
+        G->g[a] = (a < d->dim) ? HB2_G : 0;
+        G->gd[a] = G->n[a] + 2 * G->g[a];
+        G->dx[a] = (a < d->dim) ? d->dx[a] : 1.0;
+    }
+    G->cs[0] = 1;
+    G->cs[1] = G->gd[0];
+    G->cs[2] = (long long)G->gd[0] * G->gd[1];
+    G->ncell_g = (long long)G->gd[0] * G->gd[1] * G->gd[2];
+}
+
+template <class Tr, int MATH>
+static void run_sweeps(DirArgs A0, int bx, int seg_len, double* const* F_all, int mode)
+{
+    const Geom& G = A0.G;
+    /* sensor */
+    std::vector<double> theta(G.ncell_g, 0.0), Omega(G.ncell_g, 0.0);
+    const int k_lo = (Tr::DIM == 3) ? -2 : 0, k_hi = (Tr::DIM == 3) ? G.n[2] + 2 : 1;
+    for (int k = k_lo; k < k_hi; k++)
+        for (int j = -2; j < G.n[1] + 2; j++)
+            for (int i = -2; i < G.n[0] + 2; i++) {
+                const long long x = cidx(G, i, j, k);
+                sensor_cell<Tr>(G, A0.Q, x, theta[x], Omega[x]);
+            }
+    A0.theta = theta.data();
+    A0.Omega = Omega.data();
+    A0.mode = mode;
+
+    for (int dir = 0; dir < Tr::DIM; dir++) {
+        DirArgs A = A0;
+        if (mode == MODE_EMIT)
+            for (int e = 0; e < Tr::NEQ; e++) A.F[e] = F_all[dir * Tr::NEQ + e];
+        if (dir != Tr::DIM - 1) A.ncoef = 0;
+        A.seg_len = seg_len > 0 ? seg_len : G.n[dir];
+        if (dir == 0) {
+            const int BX = bx;
+            std::vector<double> smem(XSmem<Tr>::doubles(BX));
+            const long long run = (long long)G.n[1] * G.gd[0];
+            const long long tiles = (run + (BX - 3) - 1) / (BX - 3);
+            const int planes = (Tr::DIM == 3) ? G.n[2] : 1;
+            for (int k = 0; k < planes; k++)
+                for (long long tile = 0; tile < tiles; tile++) {
+                    XSmem<Tr> sm(smem.data(), BX);
+                    const long long pstart = cidx(G, -G.g[0], 0, k);
+                    const long long p0 = pstart - 1 + tile * (long long)(BX - 3);
+                    for (int idx = 0; idx < BX + 5; idx++) xsweep_phase_load<Tr, MATH>(A, sm, p0, idx);
+                    for (int t = 0; t < BX; t++) xsweep_phase_mid<Tr, MATH>(A, sm, p0, k, t);
+                    for (int t = 0; t < BX; t++) xsweep_phase_face<Tr, MATH>(A, sm, p0, k, t);
+                    for (int t = 0; t < BX; t++) xsweep_phase_cell<Tr, MATH>(A, sm, p0, k, t);
+                }
+        } else {
+            const int N = G.n[dir];
+            const int nseg = (N + A.seg_len - 1) / A.seg_len;
+            const int nt = (dir == 1) ? ((Tr::DIM == 3) ? G.n[2] : 1) : G.n[1];
+            for (int seg = 0; seg < nseg; seg++)
+                for (int t = 0; t < nt; t++)
+                    for (int i = 0; i < G.n[0]; i++) {
+                        if (dir == 1)
+                            march_pencil<Tr, 1, MATH>(A, i, t, seg);
+                        else
+                            march_pencil<Tr, (Tr::DIM == 3 ? 2 : 1), MATH>(A, i, t, seg);
+                    }
+        }
+    }
+}
+
+#define EMU_DISPATCH(d, CALL)                                                                     \
+    do {                                                                                          \
+        if ((d)->model == SS && (d)->dim == 2) { using Tr = Traits<SS, 2, 1>; if ((d)->math == 0) { constexpr int MATH = 0; CALL; } else { constexpr int MATH = 1; CALL; } return 0; } \
+        if ((d)->model == SS && (d)->dim == 3) { using Tr = Traits<SS, 3, 1>; if ((d)->math == 0) { constexpr int MATH = 0; CALL; } else { constexpr int MATH = 1; CALL; } return 0; } \
+        if ((d)->model == FE && (d)->dim == 2) { using Tr = Traits<FE, 2, 2>; if ((d)->math == 0) { constexpr int MATH = 0; CALL; } else { constexpr int MATH = 1; CALL; } return 0; } \
+        if ((d)->model == FE && (d)->dim == 3) { using Tr = Traits<FE, 3, 2>; if ((d)->math == 0) { constexpr int MATH = 0; CALL; } else { constexpr int MATH = 1; CALL; } return 0; } \
+    } while (0)
+
+static void fill_common(const EmuDesc* d, DirArgs* A, const double* const* Q, double dt, std::vector<double>& T)
+{
+    memset(A, 0, sizeof(*A));
+    make_geom(d, &A->G);
+    for (int s = 0; s < 4; s++) {
+        A->K.gamma[s] = (s < d->ns) ? d->gamma[s] : 1.4;
+        A->K.inv_gm1[s] = 1.0 / (A->K.gamma[s] - 1.0);
+    }
+    A->K.weno_p = d->weno_p > 0 ? d->weno_p : 2;
+    const int ncomp = d->model == SS ? d->dim + 2 : d->dim + 2 * d->ns + 1;
+    for (int c = 0; c < ncomp; c++) A->Q[c] = Q[c];
+    A->dt = dt;
+    T.assign((size_t)A->G.n[0] * A->G.n[1] * A->G.n[2], 0.0);
+    A->T = T.data();
+}
+
+extern "C" int emu_flux_and_source(const EmuDesc* d, const double* const* Q, double dt, double* const* F, double* const* S)
+{
+    DirArgs A;
+    std::vector<double> T;
+    fill_common(d, &A, Q, dt, T);
+    const int neq = d->model == SS ? d->dim + 2 : d->dim + 2 * d->ns;
+    for (int e = 0; e < neq; e++) A.S[e] = S ? S[e] : nullptr;
+    EMU_DISPATCH(d, (run_sweeps<Tr, MATH>(A, d->bx, d->seg_len, F, MODE_EMIT)));
+    return -1;
+}
+
+extern "C" int emu_fused_stage(const EmuDesc* d, int ncoef, const double* alpha, const double* beta,
+                               const double* const* U_int, double dt, double* const* U_out)
+{
+    const int ncomp = d->model == SS ? d->dim + 2 : d->dim + 2 * d->ns + 1;
+    const int neq = d->model == SS ? d->dim + 2 : d->dim + 2 * d->ns;
+    DirArgs A;
+    std::vector<double> T;
+    fill_common(d, &A, U_int + (size_t)(ncoef - 1) * ncomp, dt, T);
+    std::vector<std::vector<double>> R(neq, std::vector<double>(T.size(), 0.0));
+    for (int e = 0; e < neq; e++) A.R[e] = R[e].data();
+    A.ncoef = ncoef;
+    for (int m = 0; m < ncoef; m++) {
+        A.alpha[m] = alpha[m];
+        for (int c = 0; c < ncomp; c++) A.Uint[m][c] = U_int[m * ncomp + c];
+    }
+    A.beta = beta[ncoef - 1];
+    for (int c = 0; c < ncomp; c++) A.Uout[c] = U_out[c];
+    EMU_DISPATCH(d, (run_sweeps<Tr, MATH>(A, d->bx, d->seg_len, nullptr, MODE_FUSED)));
+    return -1;
+}
