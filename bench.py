@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native WCNS5-JS / HLLC-HLL path.
+
+Metric (BASELINE.json): FP64 cell-updates/s per RK3 stage, WCNS5-JS 3D Euler, single-species,
+512^3 periodic uniform level (tests/3D_convergence_test_single_species scaled up, SURVEY.md 8d "M1").
+One cell-update = one interior cell advanced through one RK stage (flux in all directions + update).
+A "step" here is one SSP-RK3 time step = three passes of the hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size 512] [--math fast|exact]
+                  [--scaling strong|weak] [--model ss|fe] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); the level is cut into one box per rank and
+the width-4 halos are exchanged over NVLink every stage.  `--impl reference` times the CPU oracle
+(a restatement of the reference's algorithm; the real reference needs SAMRAI+MPI+HDF5 and cannot be
+built here) on the host cores, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic work per cell-update, single-species 3D / five-eqn 3D
+ALGO = {
+    "ss": {"flops": 3.8e3, "bytes": 106.7, "flops_sweep": 1.217e3, "flops_sensor": 73.0, "flops_rk": 75.0},
+    "fe": {"flops": 5.6e3, "bytes": 165.0, "flops_sweep": 1.80e3, "flops_sensor": 90.0, "flops_rk": 110.0},
+}
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_ic_device(level, model):
+    """Convergence-test IC (ConvergenceSingleSpecies.cpp:145-174 / ConvergenceFiveEqnAllaire.cpp:176-219) of this
+    rank's box, generated on the device (synthetic data)."""
+    import torch
+
+    xs = [torch.as_tensor(c, dtype=torch.float64, device="cuda") for c in level.local_coordinates()]
+    s = (xs[0][None, None, :] + xs[1][None, :, None]) + xs[2][:, None, None]
+    sin = torch.sin(np.pi * s)
+    dim = 3
+    if model == "ss":
+        rho = 1.0 + 0.5 * sin
+        E = 1.0 / (7.0 / 5.0 - 1.0) + 0.5 * rho * float(dim)
+        comps = [rho, rho, rho, rho, E]
+    else:
+        Z1 = 0.5 + 0.25 * sin
+        Z2 = 1.0 - Z1
+        Zr1, Zr2 = Z1 * 2.0, Z2 * 1.0
+        rho = Zr1 + Zr2
+        gm = 1.0 / (Z1 / (8.0 / 5.0 - 1.0) + Z2 / (7.0 / 5.0 - 1.0)) + 1.0
+        E = 1.0 / (gm - 1.0) + 0.5 * rho * float(dim)
+        comps = [Zr1, Zr2, rho, rho, rho, E, Z1, Z2]
+    inter = level.interior()
+    for c, v in enumerate(comps):
+        inter[c].copy_(v)
+    del sin, s
+
+
+def run_reference(args):
+    """CPU arm: the oracle (reference-structured restatement, gcc -O3, one OpenMP thread per core standing in
+    for one MPI rank, 32^3 patches) on a bounded sample of the same workload."""
+    rank, _, world = env_rank()
+    if rank != 0:
+        return
+    from hamers_b200 import problems as pb
+    from oracle import oracle as orc
+
+    orc.build()
+    cores = os.cpu_count() or 1
+    N = args.ref_size
+    model = 0 if args.model == "ss" else 1
+    if model == 0:
+        U, dx, gam = pb.convergence_single_species(3, N)
+    else:
+        U, dx, gam = pb.convergence_five_eqn(3, N)
+    lvl = orc.PatchDesc(dim=3, n=(N,) * 3, model=model, ns=len(gam), gamma=gam, dx=dx)
+    dt = 0.001 * dx[0]
+    patch = (min(32, N),) * 3
+    for _ in range(args.warmup if args.warmup > 0 else 0):
+        orc.level_advance(lvl, patch, U, dt, 1, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.level_advance(lvl, patch, U, dt, 1, nthreads=cores)
+    el = time.perf_counter() - t0
+    value = N ** 3 * 3 * args.steps / el
+    sample = f"{N}^3 box in {patch[0]}^3 patches, {args.steps} SSP-RK3 steps ({3 * args.steps} stages), {cores} OpenMP threads"
+    line = {
+        "impl": "reference", "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, sample_override=sample),
+        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, sample_override=None):
+    name = ("3D single-species Euler" if args.model == "ss" else "3D five-equation Allaire") + \
+           f", WCNS5_JS_HLLC_HLL, SSP-RK3, periodic uniform level {args.size}^3 (convergence-test IC scaled up)"
+    cfg = {"workload": name, "size": args.size, "math": args.math, "dt": "0.001*dx", "ghosts": 4,
+           "l2_policy": "inputs (>= 5 GB per state) exceed the 126 MB L2; no flush needed",
+           "step": "one SSP-RK3 time step = 3 hot-path passes (ghost fill + sensor + x/y/z sweeps with fused RK update)"}
+    if sample_override:
+        cfg["sample"] = sample_override
+    return cfg
+
+
+def run_ours(args):
+    import torch
+
+    rank, local_rank, world = env_rank()
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    from hamers_b200 import abi
+    from hamers_b200.level import PROCESS_GRIDS, UniformLevel
+
+    flow_model = abi.SINGLE_SPECIES if args.model == "ss" else abi.FIVE_EQN_ALLAIRE
+    gam = (7.0 / 5.0,) if args.model == "ss" else (8.0 / 5.0, 7.0 / 5.0)
+    math = abi.MATH_FAST if args.math == "fast" else abi.MATH_EXACT
+    grid = PROCESS_GRIDS[3][world]
+    if args.scaling == "strong":
+        Nglob = (args.size,) * 3
+    else:
+        Nglob = tuple(args.size * g for g in grid)
+    domain_len = 2.0
+    level = UniformLevel(3, Nglob, flow_model=flow_model, species_gamma=gam, math=math)
+    # keep dx = 2/size in weak scaling too (same physics per cell)
+    make_ic_device(level, args.model)
+    dx = level.dx[0]
+    dt = 0.001 * dx
+    ncell_local = int(np.prod(level.decomp.n))
+    ncell_global = int(np.prod(Nglob))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        level.rk_step(dt)
+    barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = level.plan.launch_count
+    level.plan.set_profiling(True)
+    level.plan.get_profile(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        level.rk_step(dt)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    prof = level.plan.get_profile(reset=True)
+    level.plan.set_profiling(False)
+    launches = level.plan.launch_count - launches0
+    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms = float(tmax[0])
+        launches = int(tsum[1])
+    sec = ms * 1e-3
+    value = ncell_global * 3 * args.steps / sec
+
+    # sanity of the run itself: the solution must stay finite and close to the advected wave
+    rho_min = float(level.interior()[0].min())
+    rho_max = float(level.interior()[0].max())
+    finite = bool(torch.isfinite(level.interior()).all())
+
+    line = None
+    if rank == 0:
+        algo = ALGO[args.model]
+        # FP64 and HBM peaks
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        fp64_peak = abi.probe_fp64_peak(local_rank, 1.0) / 1e12
+        # dominant kernel = the slowest sweep
+        sweeps = {k: prof[k] for k in ("xsweep", "ysweep", "zsweep") if prof[k][1] > 0}
+        dom = max(sweeps, key=lambda k: sweeps[k][0] / sweeps[k][1])
+        dom_ms = sweeps[dom][0] / sweeps[dom][1]
+        dom_flops = (algo["flops_sweep"] + (algo["flops_rk"] if dom == "zsweep" else 0.0)) * ncell_local
+        kern = {k: {"avg_ms": v[0] / v[1], "launches": v[1], "share": v[0] / max(1e-30, sum(x[0] for x in prof.values()))}
+                for k, v in prof.items() if v[1] > 0}
+        per_rank_rate = value / world
+        roofline = {
+            "bound": "fp64", "kernel": dom, "achieved": dom_flops / (dom_ms * 1e-3) / 1e12, "peak": fp64_peak,
+            "unit": "TFLOP/s", "traffic": None,
+            "peak_source": "in-run DFMA probe (hb2_probe_fp64_peak); MEASURED_PEAKS.json has no FP64 figure; "
+                           "bound is the FP64 pipe (AI ~36 FLOP/B >> ridge), 'hbm' view given beside it",
+            "algorithmic_flops_per_launch": dom_flops,
+            "stage": {"fp64_achieved_tflops": algo["flops"] * per_rank_rate / 1e12,
+                      "fp64_frac": algo["flops"] * per_rank_rate / 1e12 / fp64_peak,
+                      "hbm_achieved_gbs": algo["bytes"] * per_rank_rate / 1e9, "hbm_peak_gbs": hbm_peak,
+                      "hbm_frac": algo["bytes"] * per_rank_rate / 1e9 / hbm_peak, "hbm_peak_source": hbm_src},
+            "kernels": kern,
+        }
+        roofline["frac"] = roofline["achieved"] / roofline["peak"]
+        line = {
+            "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(args), global_cells=list(Nglob), process_grid=list(grid),
+                           cells_per_gpu=ncell_local, parallelism=f"box{world}"),
+            "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
+            "sanity": {"finite": finite, "rho_min": rho_min, "rho_max": rho_max},
+        }
+
+    # ---- end-to-end: host buffers through the C ABI (N = 1: advanceLevel on host memory) ----------
+    if world == 1 and not args.no_e2e:
+        n = args.e2e_size
+        plan = abi.Plan(3, (n,) * 3, flow_model=flow_model, species_gamma=gam, dx=(domain_len / n,) * 3, math=math)
+        ncomp = plan.ncomp
+        host = torch.empty((ncomp,) + plan.ghost_shape, dtype=torch.float64).pin_memory()
+        lvl2 = level if n == args.size else None
+        if lvl2 is not None:
+            host.copy_(level.S[level.cur])
+        else:
+            from hamers_b200 import problems as pb
+
+            U, _, _ = (pb.convergence_single_species(3, n) if args.model == "ss" else pb.convergence_five_eqn(3, n))
+            host.copy_(torch.from_numpy(pb.pad_periodic(U)))
+        level.close()
+        del level
+        torch.cuda.empty_cache()
+        hnp = host.numpy()
+        dte = 0.001 * domain_len / n
+        for _ in range(1):
+            plan.advance_level_host(hnp, dte)
+        k0 = plan.launch_count
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            plan.advance_level_host(hnp, dte)
+        el = time.perf_counter() - t0
+        nbytes = host.numel() * 8
+        line["e2e"] = {"value": n ** 3 * 3 * args.e2e_steps / el, "unit": "cell-updates/s",
+                       "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": args.e2e_steps,
+                       "size": n, "ms_per_step": 1e3 * el / args.e2e_steps, "launches": plan.launch_count - k0,
+                       "api": "hb2_advance_level_host (advanceLevel on pinned host memory: H2D U^n, 3 stages on device, D2H U^{n+1})"}
+        plan.close()
+    elif rank == 0:
+        line["e2e"] = None
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from hamers_b200 import problems as pb
+        from oracle import oracle as orc
+
+        orc.build()
+        cores = os.cpu_count() or 1
+        N = args.ref_size
+        model = 0 if args.model == "ss" else 1
+        U, dxr, gr = (pb.convergence_single_species(3, N) if model == 0 else pb.convergence_five_eqn(3, N))
+        lv = orc.PatchDesc(dim=3, n=(N,) * 3, model=model, ns=len(gr), gamma=gr, dx=dxr)
+        patch = (min(32, N),) * 3
+        orc.level_advance(lv, patch, U, 0.001 * dxr[0], 1, nthreads=cores)
+        nst, t0 = 0, time.perf_counter()
+        while True:
+            orc.level_advance(lv, patch, U, 0.001 * dxr[0], 1, nthreads=cores)
+            nst += 1
+            el = time.perf_counter() - t0
+            if el > args.cpu_seconds or nst >= 50:
+                break
+        line["cpu_baseline"] = {"value": N ** 3 * 3 * nst / el, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+                                "sample": f"{N}^3 box in {patch[0]}^3 patches, {nst} SSP-RK3 steps, {cores} OpenMP threads, "
+                                          "oracle = reference-structured CPU restatement (real reference needs SAMRAI/MPI/HDF5)"}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--model", default="ss", choices=["ss", "fe"])
+    ap.add_argument("--math", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--ref-size", type=int, default=128)
+    ap.add_argument("--e2e-size", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.e2e_size <= 0:
+        args.e2e_size = args.size
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = max(args.warmup, 3)   # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

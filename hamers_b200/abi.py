@@ -26,11 +26,18 @@ MATH_FAST = 1
 SYMBOLS = [
     "hb2_last_error", "hb2_version", "hb2_device_count", "hb2_num_eqn", "hb2_num_comp", "hb2_num_ghosts",
     "hb2_cell_ghost_size", "hb2_cell_size", "hb2_side_size", "hb2_plan_create", "hb2_plan_destroy",
-    "hb2_plan_set_stream", "hb2_plan_synchronize", "hb2_plan_launch_count", "hb2_plan_workspace_bytes",
+    "hb2_plan_set_stream", "hb2_plan_use_own_stream", "hb2_plan_synchronize", "hb2_plan_launch_count", "hb2_plan_workspace_bytes",
     "hb2_compute_flux_and_source_dev", "hb2_advance_stage_dev", "hb2_fused_stage_dev",
     "hb2_fill_ghosts_periodic_dev", "hb2_pack_box_dev", "hb2_unpack_box_dev", "hb2_max_wave_speed_dev",
     "hb2_compute_flux_and_source_host", "hb2_fused_stage_host", "hb2_probe_fp64_peak", "hb2_probe_hbm_bandwidth",
+    "hb2_plan_set_profiling", "hb2_plan_get_profile", "hb2_advance_level_dev", "hb2_advance_level_host",
 ]
+
+KERNEL_KINDS = ("sensor", "xsweep", "ysweep", "zsweep", "advance", "fill_periodic", "pack", "unpack")
+
+# SSP-RK3(3,3), the reference's default table (RungeKuttaLevelIntegrator.cpp:3894-3929), row-major [stage][m]
+SSPRK3_ALPHA = np.array([[1.0, 0.0, 0.0], [3.0 / 4.0, 1.0 / 4.0, 0.0], [1.0 / 3.0, 0.0, 2.0 / 3.0]])
+SSPRK3_BETA = np.array([[1.0, 0.0, 0.0], [0.0, 1.0 / 4.0, 0.0], [0.0, 0.0, 2.0 / 3.0]])
 
 
 class PatchDescC(C.Structure):
@@ -73,6 +80,8 @@ def load_library():
         lib.hb2_plan_synchronize.argtypes = [C.c_void_p]
         lib.hb2_plan_launch_count.argtypes = [C.c_void_p]
         lib.hb2_plan_workspace_bytes.argtypes = [C.c_void_p]
+        lib.hb2_plan_set_profiling.argtypes = [C.c_void_p, C.c_int32]
+        lib.hb2_plan_get_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]
         _LIB = lib
     return _LIB
 
@@ -190,6 +199,36 @@ class Plan:
     @property
     def workspace_bytes(self) -> int:
         return int(self.lib.hb2_plan_workspace_bytes(self._h))
+
+    def set_profiling(self, on: bool = True):
+        _check(self.lib.hb2_plan_set_profiling(self._h, 1 if on else 0), "hb2_plan_set_profiling")
+
+    def get_profile(self, reset: bool = True):
+        """{kind: (total ms, launches)} measured with CUDA events on the launching stream."""
+        ms = (C.c_double * len(KERNEL_KINDS))()
+        n = (C.c_int64 * len(KERNEL_KINDS))()
+        _check(self.lib.hb2_plan_get_profile(self._h, ms, n, 1 if reset else 0), "hb2_plan_get_profile")
+        return {k: (ms[i], int(n[i])) for i, k in enumerate(KERNEL_KINDS)}
+
+    def advance_level(self, U, dt: float, alpha=None, beta=None, periodic_mask: int = 7):
+        """RungeKuttaLevelIntegrator::advanceLevel stage loop for one patch covering a periodic level."""
+        alpha = SSPRK3_ALPHA if alpha is None else np.ascontiguousarray(alpha, dtype=np.float64)
+        beta = SSPRK3_BETA if beta is None else np.ascontiguousarray(beta, dtype=np.float64)
+        nst = alpha.shape[0]
+        _check(self.lib.hb2_advance_level_dev(self._h, nst, alpha.ctypes.data_as(C.POINTER(C.c_double)),
+                                              beta.ctypes.data_as(C.POINTER(C.c_double)), C.c_double(dt),
+                                              int(periodic_mask), _ptr_table(_dev_ptrs(U, self.ncomp))),
+               "hb2_advance_level_dev")
+
+    def advance_level_host(self, U: np.ndarray, dt: float, alpha=None, beta=None, periodic_mask: int = 7):
+        alpha = SSPRK3_ALPHA if alpha is None else np.ascontiguousarray(alpha, dtype=np.float64)
+        beta = SSPRK3_BETA if beta is None else np.ascontiguousarray(beta, dtype=np.float64)
+        nst = alpha.shape[0]
+        _check(self.lib.hb2_advance_level_host(self._h, nst, alpha.ctypes.data_as(C.POINTER(C.c_double)),
+                                               beta.ctypes.data_as(C.POINTER(C.c_double)), C.c_double(dt),
+                                               int(periodic_mask), _ptr_table(_host_ptrs(U, self.ncomp))),
+               "hb2_advance_level_host")
+        return U
 
     # -- device-resident hot path ----------------------------------------------------------
     def compute_flux_and_source(self, Q, dt: float, flux, source=None):

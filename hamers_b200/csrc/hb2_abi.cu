@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 using namespace hb2;
 
@@ -63,7 +64,42 @@ struct hb2_plan_s {
     long long launches;
     long long ws_bytes;
     int seg_len[3];
+    /* per-kernel-kind device timing (CUDA events on the launching stream) */
+    int profiling;
+    struct ProfRec {
+        int kind;
+        cudaEvent_t e0, e1;
+    };
+    std::vector<ProfRec>* prof;
+    double prof_ms[HB2_NUM_KERNEL_KINDS];
+    long long prof_n[HB2_NUM_KERNEL_KINDS];
+    /* intermediate states owned by the plan for hb2_advance_level_* */
+    double* lvl[2][HB2_MAXC];
 };
+
+namespace {
+struct ProfScope {
+    hb2_plan_t p;
+    int kind;
+    cudaEvent_t e0, e1;
+    ProfScope(hb2_plan_t p_, int kind_) : p(p_), kind(kind_), e0(nullptr), e1(nullptr)
+    {
+        p->launches++;
+        if (p->profiling) {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, p->stream);
+        }
+    }
+    ~ProfScope()
+    {
+        if (p->profiling) {
+            cudaEventRecord(e1, p->stream);
+            p->prof->push_back({kind, e0, e1});
+        }
+    }
+};
+}  // namespace
 
 namespace {
 
@@ -285,8 +321,11 @@ int run_sensor(hb2_plan_t p, const double* const* Q)
     memset(&qt, 0, sizeof(qt));
     for (int c = 0; c < p->ncomp; c++) qt.p[c] = Q[c];
     /* the sensor feeds a hard switch: always the exact-arithmetic build */
-    const int rc = ops_exact()->sensor(p->cfg, p->G, qt, p->theta, p->Omega, p->stream);
-    p->launches++;
+    int rc;
+    {
+        ProfScope ps(p, 0);
+        rc = ops_exact()->sensor(p->cfg, p->G, qt, p->theta, p->Omega, p->stream);
+    }
     if (rc) return fail(-200, std::string("sensor kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
     return 0;
 }
@@ -416,6 +455,7 @@ int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* out)
         return fail(-100 - (int)e, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     }
     p->stream = p->own_stream;
+    p->prof = new std::vector<hb2_plan_s::ProfRec>();
     *out = p;
     return 0;
 }
@@ -434,6 +474,15 @@ int hb2_plan_destroy(hb2_plan_t p)
     for (int c = 0; c < HB2_MAXC; c++) cudaFree(p->stOut[c]);
     for (int q = 0; q < 3 * HB2_MAXE; q++) cudaFree(p->stF[q]);
     for (int q = 0; q < HB2_MAXE; q++) cudaFree(p->stS[q]);
+    for (int m = 0; m < 2; m++)
+        for (int c = 0; c < HB2_MAXC; c++) cudaFree(p->lvl[m][c]);
+    if (p->prof) {
+        for (auto& r : *p->prof) {
+            cudaEventDestroy(r.e0);
+            cudaEventDestroy(r.e1);
+        }
+        delete p->prof;
+    }
     cudaStreamDestroy(p->own_stream);
     delete p;
     return 0;
@@ -442,7 +491,16 @@ int hb2_plan_destroy(hb2_plan_t p)
 int hb2_plan_set_stream(hb2_plan_t p, void* s)
 {
     if (!p) return fail(-1, "null plan");
-    p->stream = s ? (cudaStream_t)s : p->own_stream;
+    /* any cudaStream_t, including 0 (the legacy default stream, which is what torch's current stream is by
+     * default); hb2_plan_use_own_stream() goes back to the plan's private non-blocking stream */
+    p->stream = (cudaStream_t)s;
+    return 0;
+}
+
+int hb2_plan_use_own_stream(hb2_plan_t p)
+{
+    if (!p) return fail(-1, "null plan");
+    p->stream = p->own_stream;
     return 0;
 }
 
@@ -480,8 +538,11 @@ int hb2_compute_flux_and_source_dev(hb2_plan_t p, const double* const* Q, double
             for (int si = 0; si < p->d.num_species - 1; si++)
                 if (!A.S[p->d.num_species + p->d.dim + 1 + si]) return fail(-14, "null source pointer of an advective equation");
         A.seg_len = p->seg_len[dir];
-        const int lrc = p->ops->sweep(p->cfg, dir, A, p->stream);
-        p->launches++;
+        int lrc;
+        {
+            ProfScope ps(p, 1 + dir);
+            lrc = p->ops->sweep(p->cfg, dir, A, p->stream);
+        }
         if (lrc) return fail(-201, std::string("sweep kernel launch failed: ") + cudaGetErrorString((cudaError_t)lrc));
     }
     return 0;
@@ -499,11 +560,12 @@ int hb2_fused_stage_dev(hb2_plan_t p, int32_t ncoef, const double* alpha, const 
     int rc = ensure_ws(p, true);
     if (rc) return rc;
     const double* const* Q = U_int + (size_t)(ncoef - 1) * p->ncomp;
-    /* U_out may reuse the storage of an intermediate state that is not read (alpha == 0, not the flux state) */
+    /* U_out may reuse the storage of an older intermediate state: those enter only through the cell-local
+     * alpha term (read, then written by the same thread).  The flux state is read with stencils and must
+     * stay intact. */
     for (int c = 0; c < p->ncomp; c++)
-        for (int m = 0; m < ncoef; m++)
-            if ((const double*)U_out[c] == U_int[m * p->ncomp + c] && (alpha[m] != 0.0 || m == ncoef - 1))
-                return fail(-17, "U_out must not alias an intermediate state that the stage reads");
+        if ((const double*)U_out[c] == U_int[(ncoef - 1) * p->ncomp + c])
+            return fail(-17, "U_out must not alias the state the flux is evaluated on");
     rc = run_sensor(p, Q);
     if (rc) return rc;
     for (int dir = 0; dir < p->d.dim; dir++) {
@@ -521,8 +583,11 @@ int hb2_fused_stage_dev(hb2_plan_t p, int32_t ncoef, const double* alpha, const 
             for (int c = 0; c < p->ncomp; c++) A.Uout[c] = U_out[c];
         }
         A.seg_len = p->seg_len[dir];
-        const int lrc = p->ops->sweep(p->cfg, dir, A, p->stream);
-        p->launches++;
+        int lrc;
+        {
+            ProfScope ps(p, 1 + dir);
+            lrc = p->ops->sweep(p->cfg, dir, A, p->stream);
+        }
         if (lrc) return fail(-201, std::string("sweep kernel launch failed: ") + cudaGetErrorString((cudaError_t)lrc));
     }
     return 0;
@@ -563,8 +628,11 @@ int hb2_advance_stage_dev(hb2_plan_t p, int32_t ncoef, const double* alpha, cons
         for (int q = 0; q < nf; q++) P.Facc[q] = F_acc[q];
     if (S_acc)
         for (int e = 0; e < p->neq; e++) P.Sacc[e] = S_acc[e];
-    const int lrc = p->ops->advance(P, p->stream);
-    p->launches++;
+    int lrc;
+    {
+        ProfScope ps(p, 4);
+        lrc = p->ops->advance(P, p->stream);
+    }
     if (lrc) return fail(-202, std::string("advance kernel launch failed: ") + cudaGetErrorString((cudaError_t)lrc));
     return 0;
 }
@@ -576,8 +644,10 @@ int hb2_fill_ghosts_periodic_dev(hb2_plan_t p, double* const* U, int32_t mask)
     PtrTab t;
     memset(&t, 0, sizeof(t));
     for (int c = 0; c < p->ncomp; c++) t.p[c] = U[c];
-    k_fill_periodic<<<grid_for(p->G.ncell_g, 256), 256, 0, p->stream>>>(p->G, t, p->ncomp, mask & ((1 << p->d.dim) - 1));
-    p->launches++;
+    {
+        ProfScope ps(p, 5);
+        k_fill_periodic<<<grid_for(p->G.ncell_g, 256), 256, 0, p->stream>>>(p->G, t, p->ncomp, mask & ((1 << p->d.dim) - 1));
+    }
     HB2_CUDA(cudaGetLastError());
     return 0;
 }
@@ -604,8 +674,10 @@ int hb2_pack_box_dev(hb2_plan_t p, const double* const* U, const int32_t lo[3], 
     memset(&t, 0, sizeof(t));
     for (int c = 0; c < p->ncomp; c++) t.p[c] = U[c];
     const long long n = (long long)B.ext[0] * B.ext[1] * B.ext[2] * p->ncomp;
-    k_pack<<<grid_for(n, 256), 256, 0, p->stream>>>(p->G, t, p->ncomp, B, buffer);
-    p->launches++;
+    {
+        ProfScope ps(p, 6);
+        k_pack<<<grid_for(n, 256), 256, 0, p->stream>>>(p->G, t, p->ncomp, B, buffer);
+    }
     HB2_CUDA(cudaGetLastError());
     return 0;
 }
@@ -621,8 +693,10 @@ int hb2_unpack_box_dev(hb2_plan_t p, double* const* U, const int32_t lo[3], cons
     memset(&t, 0, sizeof(t));
     for (int c = 0; c < p->ncomp; c++) t.p[c] = U[c];
     const long long n = (long long)B.ext[0] * B.ext[1] * B.ext[2] * p->ncomp;
-    k_unpack<<<grid_for(n, 256), 256, 0, p->stream>>>(p->G, t, p->ncomp, B, buffer);
-    p->launches++;
+    {
+        ProfScope ps(p, 7);
+        k_unpack<<<grid_for(n, 256), 256, 0, p->stream>>>(p->G, t, p->ncomp, B, buffer);
+    }
     HB2_CUDA(cudaGetLastError());
     return 0;
 }
@@ -643,6 +717,118 @@ int hb2_max_wave_speed_dev(hb2_plan_t p, const double* const* Q, double* out_dev
     if (p->cfg.model == FE && p->cfg.dim == 3) k_wave_speed<Traits<FE, 3, 2>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
     p->launches++;
     HB2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int hb2_plan_set_profiling(hb2_plan_t p, int32_t on)
+{
+    if (!p) return fail(-1, "null plan");
+    p->profiling = on ? 1 : 0;
+    return 0;
+}
+
+int hb2_plan_get_profile(hb2_plan_t p, double* ms_total, int64_t* launches, int32_t reset)
+{
+    if (!p) return fail(-1, "null plan");
+    HB2_CUDA(cudaSetDevice(p->device));
+    HB2_CUDA(cudaStreamSynchronize(p->stream));
+    for (auto& r : *p->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        p->prof_ms[r.kind] += ms;
+        p->prof_n[r.kind] += 1;
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    p->prof->clear();
+    for (int k = 0; k < HB2_NUM_KERNEL_KINDS; k++) {
+        if (ms_total) ms_total[k] = p->prof_ms[k];
+        if (launches) launches[k] = p->prof_n[k];
+        if (reset) {
+            p->prof_ms[k] = 0.0;
+            p->prof_n[k] = 0;
+        }
+    }
+    return 0;
+}
+
+/* RungeKuttaLevelIntegrator::advanceLevel stage loop (RungeKuttaLevelIntegrator.cpp:1672-1745) for ONE
+ * patch that covers a periodic level: per stage fill the ghosts of the newest state, then the fused
+ * flux + update.  U holds U^n on entry and U^{n+1} (interior) on return.  The plan owns the two
+ * intermediate states. */
+int hb2_advance_level_dev(hb2_plan_t p, int32_t nstages, const double* alpha, const double* beta, double dt,
+                          int32_t periodic_mask, double* const* U)
+{
+    if (!p || !alpha || !beta || !U) return fail(-1, "null argument");
+    if (nstages < 1 || nstages > 3) return fail(-20, "hb2_advance_level supports 1..3 stages (SSP-RK3 is the reference default)");
+    HB2_CUDA(cudaSetDevice(p->device));
+    const size_t gb = sizeof(double) * (size_t)p->G.ncell_g;
+    for (int m = 0; m < 2; m++)
+        for (int c = 0; c < p->ncomp; c++)
+            if (!p->lvl[m][c]) {
+                HB2_CUDA(cudaMalloc(&p->lvl[m][c], gb));
+                p->ws_bytes += (long long)gb;
+            }
+    /* storage rotation: S[0] = U (U^n), S[1], S[2] plan-owned.  Stage sn writes into the first buffer that is
+     * neither read by this stage nor the flux state; the final stage result is copied back into U if needed. */
+    double* S[3][HB2_MAXC];
+    for (int c = 0; c < p->ncomp; c++) {
+        S[0][c] = U[c];
+        S[1][c] = p->lvl[0][c];
+        S[2][c] = p->lvl[1][c];
+    }
+    int where[HB2_MAXS];   /* buffer index holding intermediate state m */
+    where[0] = 0;
+    for (int sn = 0; sn < nstages; sn++) {
+        const double* a = alpha + sn * nstages;
+        const double* b = beta + sn * nstages;
+        /* ghost fill of the flux state */
+        int rc = hb2_fill_ghosts_periodic_dev(p, S[where[sn]], periodic_mask);
+        if (rc) return rc;
+        /* pick the output buffer */
+        int out = -1;
+        for (int cand = 0; cand < 3 && out < 0; cand++) {
+            bool used = false;
+            if (where[sn] == cand) used = true;   /* the flux state */
+            /* do not clobber a state a LATER stage still needs */
+            for (int m = 0; m <= sn && !used; m++)
+                if (where[m] == cand)
+                    for (int s2 = sn + 1; s2 < nstages; s2++)
+                        if (alpha[s2 * nstages + m] != 0.0 || beta[s2 * nstages + m] != 0.0) used = true;
+            if (!used) out = cand;
+        }
+        if (out < 0) return fail(-21, "RK table needs more than three state buffers");
+        const double* tab[HB2_MAXS * HB2_MAXC];
+        for (int m = 0; m <= sn; m++)
+            for (int c = 0; c < p->ncomp; c++) tab[m * p->ncomp + c] = S[where[m]][c];
+        rc = hb2_fused_stage_dev(p, sn + 1, a, b, tab, dt, S[out]);
+        if (rc) return rc;
+        where[sn + 1 < HB2_MAXS ? sn + 1 : sn] = out;
+        if (sn == nstages - 1 && out != 0)
+            for (int c = 0; c < p->ncomp; c++)
+                HB2_CUDA(cudaMemcpyAsync(U[c], S[out][c], gb, cudaMemcpyDeviceToDevice, p->stream));
+    }
+    return 0;
+}
+
+int hb2_advance_level_host(hb2_plan_t p, int32_t nstages, const double* alpha, const double* beta, double dt,
+                           int32_t periodic_mask, double* const* U_host)
+{
+    if (!p || !U_host) return fail(-1, "null argument");
+    HB2_CUDA(cudaSetDevice(p->device));
+    const size_t gb = sizeof(double) * (size_t)p->G.ncell_g;
+    for (int c = 0; c < p->ncomp; c++) {
+        if (!p->stOut[c]) {
+            HB2_CUDA(cudaMalloc(&p->stOut[c], gb));
+            p->ws_bytes += (long long)gb;
+        }
+        HB2_CUDA(cudaMemcpyAsync(p->stOut[c], U_host[c], gb, cudaMemcpyHostToDevice, p->stream));
+    }
+    int rc = hb2_advance_level_dev(p, nstages, alpha, beta, dt, periodic_mask, p->stOut);
+    if (rc) return rc;
+    for (int c = 0; c < p->ncomp; c++)
+        HB2_CUDA(cudaMemcpyAsync(U_host[c], p->stOut[c], gb, cudaMemcpyDeviceToHost, p->stream));
+    HB2_CUDA(cudaStreamSynchronize(p->stream));
     return 0;
 }
 

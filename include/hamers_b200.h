@@ -85,13 +85,21 @@ int64_t hb2_side_size(const hb2_patch_desc* d, int32_t dir);
 /* ---- plan --------------------------------------------------------------------------- */
 int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* plan);
 int hb2_plan_destroy(hb2_plan_t plan);
-/* cudaStream_t to launch on (NULL = the plan's own stream). */
+/* cudaStream_t to launch on; 0 is the legacy default stream.  A new plan launches on a private
+ * non-blocking stream; hb2_plan_use_own_stream() returns to it. */
 int hb2_plan_set_stream(hb2_plan_t plan, void* cuda_stream);
+int hb2_plan_use_own_stream(hb2_plan_t plan);
 int hb2_plan_synchronize(hb2_plan_t plan);
 /* number of kernels this plan has launched since creation (bench.py's gpu_launches) */
 int64_t hb2_plan_launch_count(hb2_plan_t plan);
 /* bytes of device workspace the plan owns */
 int64_t hb2_plan_workspace_bytes(hb2_plan_t plan);
+/* Per-kernel device timing with CUDA events on the launching stream (the analogue of the reference's
+ * tbox::TimerManager timers t_compute_fluxes_sources / t_advance_step, Euler.cpp:44-52).
+ * kinds: 0 sensor, 1 x sweep, 2 y sweep, 3 z sweep, 4 advance, 5 periodic fill, 6 pack, 7 unpack */
+#define HB2_NUM_KERNEL_KINDS 8
+int hb2_plan_set_profiling(hb2_plan_t plan, int32_t on);
+int hb2_plan_get_profile(hb2_plan_t plan, double* ms_total, int64_t* launches, int32_t reset);
 
 /* ---- the hot path, device-resident data ------------------------------------------------ */
 
@@ -118,13 +126,20 @@ int hb2_advance_stage_dev(hb2_plan_t plan, int32_t ncoef,
 /* computeFluxesAndSourcesOnPatch + advanceSingleStepOnPatch in one pass that never writes the
  * side fluxes to HBM (uniform level, no AMR flux sums).  Requires beta[m] == 0 for m < ncoef-1
  * (true for SSP-RK3 and every "newest flux only" table); the flux is evaluated on
- * U_int[ncoef-1].  U_out must not alias any U_int. */
+ * U_int[ncoef-1].  U_out must not alias U_int[ncoef-1] (older states may be overwritten in place). */
 int hb2_fused_stage_dev(hb2_plan_t plan, int32_t ncoef, const double* alpha, const double* beta,
                         const double* const* U_int, double dt, double* const* U_out);
 
 /* Same-level periodic ghost fill of one patch that covers the whole periodic level in the
  * directions flagged in periodic_mask (bit d).  All 4-cell ghosts incl. edges and corners. */
 int hb2_fill_ghosts_periodic_dev(hb2_plan_t plan, double* const* U, int32_t periodic_mask);
+
+/* RungeKuttaLevelIntegrator::advanceLevel stage loop (RungeKuttaLevelIntegrator.cpp:1672-1745) for one
+ * patch covering a periodic level: per stage a periodic ghost fill of the newest state, then the fused
+ * stage.  alpha/beta: row-major [nstages][nstages] (SSP-RK3 default: :3894-3929).  U: U^n in, U^{n+1}
+ * (interior) out; nstages <= 3. */
+int hb2_advance_level_dev(hb2_plan_t plan, int32_t nstages, const double* alpha, const double* beta,
+                          double dt, int32_t periodic_mask, double* const* U);
 
 /* Halo exchange building blocks for GPU-resident neighbouring patches: copy the box
  * [lo, hi) (cell indices relative to the interior origin, may extend into ghosts) of every
@@ -145,6 +160,10 @@ int hb2_compute_flux_and_source_host(hb2_plan_t plan, const double* const* Q_hos
  * stage, downloads U_out (whole ghost box; only its interior is meaningful). */
 int hb2_fused_stage_host(hb2_plan_t plan, int32_t ncoef, const double* alpha, const double* beta,
                          const double* const* U_int_host, double dt, double* const* U_out_host);
+
+/* advanceLevel on host memory: H2D of U^n, all stages on the device, D2H of U^{n+1}. */
+int hb2_advance_level_host(hb2_plan_t plan, int32_t nstages, const double* alpha, const double* beta,
+                           double dt, int32_t periodic_mask, double* const* U_host);
 
 /* ---- measurement helpers --------------------------------------------------------------- */
 /* Dependent-free DFMA loop on every SM; returns achieved FP64 FLOP/s (2 per FMA). */
