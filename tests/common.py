@@ -47,3 +47,31 @@ def rel_err(a, b):
 def interior(desc, U, g=4):
     sl = (slice(None),) + tuple(slice(g, -g) for _ in range(desc.dim))
     return U[sl]
+
+
+# Fast-arithmetic variant: FMA contraction and reciprocal sharing re-associate the reference's formulas.  On
+# well-conditioned faces that is <= RTOL.  A handful of faces of the white-noise branch-coverage state are
+# ILL-CONDITIONED IN THE REFERENCE'S OWN FORMULAS (e.g. the HLLC-HLL blend weights alpha_1 = |du_n|/|du|,
+# alpha_2 = sqrt(1 - alpha_1^2) are built from differences of the two one-sided interpolants: when those nearly
+# coincide a 1-ulp change upstream moves beta_1 by ~1e-11; the oracle itself moves by that much under 1-ulp input
+# perturbations, see tests/test_oracle_conditioning.py).  Such faces are counted and bounded separately.
+OUTLIER_FRACTION = 1.0e-3   # at most this share of the entries may exceed RTOL ...
+OUTLIER_RTOL = 1.0e-9       # ... and none may exceed this (a wrong formula is off by >= 1e-6)
+
+
+def rel_err_field(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    axes = tuple(range(1, b.ndim))
+    scale = np.abs(b).max(axis=axes, keepdims=True) if b.ndim > 1 else np.abs(b).max()
+    scale = np.where(scale == 0.0, 1.0, scale)
+    return np.abs(a - b) / (np.abs(b) + scale)
+
+
+def assert_fast_parity(a, b, what=""):
+    r = rel_err_field(a, b)
+    assert np.isfinite(r).all(), f"{what}: non-finite entries"
+    n_out = int((r > RTOL).sum())
+    assert n_out <= max(8, int(OUTLIER_FRACTION * r.size)), f"{what}: {n_out} of {r.size} entries exceed {RTOL}, max {r.max():.3e}"
+    assert r.max() <= OUTLIER_RTOL, f"{what}: max relative error {r.max():.3e}"
+    return float(r.max()), n_out

@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""Generate tests/golden/point_kernels.npz from the REFERENCE's own compiled point kernels (oracle/_ref,
+built by oracle/build_ref.py from /root/reference).  Run in the build container (where /root/reference
+exists); the .npz is committed so that the GPU box, which has no reference tree, can still pin the oracle.
+
+    python tests/golden/make_golden.py
+
+Contents (all float64, seeded):
+  weno_U      (n, 6)   six-point stencils (smooth, random, shock-like, constant, tiny-variation)
+  weno_minus  (n,)     performLocalWENOInterpolationMinus  (ConvectiveFluxReconstructorWCNS5-JS-HLLC-HLL.cpp:78-118)
+  weno_plus   (n,)     performLocalWENOInterpolationPlus   (:124-164)
+  rp_<case>_{VL,VR,thermo,F_HLLC,F_HYB,vel_mid} for case in ss2d{0,1}, ss3d{0,1,2}, fe2d{0,1}, fe3d{0,1,2}:
+                       computeLocal...HLLC{2D,3D} / ...HLLC_HLL{2D,3D} of the reference
+                       (FlowModelRiemannSolverSingleSpeciesHLLC.cpp:604-1079, ...HLLC-HLL.cpp:889-1629,
+                        FlowModelRiemannSolverFiveEqnAllaireHLLC.cpp:712-1591, ...HLLC-HLL.cpp:1283-2440)
+                       thermo = (rho_L, rho_R, c_L, c_R, eps_L, eps_R) as fed to the reference kernels
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import oracle as orc  # noqa: E402
+
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libhamers_ref.so")
+
+
+def ref_lib():
+    lib = C.CDLL(REF_SO)
+    lib.ref_riemann_point.restype = C.c_int
+    return lib
+
+
+def weno_inputs(rng, n=400):
+    U = []
+    for _ in range(n // 5):
+        x0 = rng.uniform(-1, 1)
+        h = 10.0 ** rng.uniform(-3, -0.5)
+        U.append(np.sin(np.pi * (x0 + h * np.arange(6))) + 1.5)                  # smooth
+        U.append(rng.uniform(0.1, 3.0, 6))                                       # rough
+        s = rng.uniform(0.5, 2.0, 6)
+        s[rng.integers(1, 5):] *= rng.uniform(3.0, 20.0)                         # jump inside the stencil
+        U.append(s)
+        U.append(np.full(6, rng.uniform(-2, 2)))                                 # constant
+        U.append(rng.uniform(0.5, 2.0) * (1.0 + 1e-9 * rng.standard_normal(6)))  # round-off level variation
+    return np.array(U)
+
+
+def ref_weno(lib, U, p=2):
+    m, pl = C.c_double(), C.c_double()
+    lib.ref_weno5js_point((C.c_double * 6)(*U), int(p), C.byref(m), C.byref(pl))
+    return m.value, pl.value
+
+
+def riemann_inputs(rng, model, dim, ns, n=120):
+    neq = dim + 2 if model == 0 else dim + 2 * ns
+    VL, VR = np.zeros((n, neq)), np.zeros((n, neq))
+    for V in (VL, VR):
+        nm = 1 if model == 0 else ns
+        V[:, :nm] = rng.uniform(0.2, 3.0, (n, nm))
+        V[:, nm:nm + dim] = rng.uniform(-3.0, 3.0, (n, dim))
+        V[:, nm + dim] = rng.uniform(0.2, 10.0, n)
+        if model == 1:
+            V[:, nm + dim + 1:] = rng.uniform(0.05, 0.95, (n, ns - 1))
+    # identical velocities (|du| < eps branch), supersonic both ways (upwind overrides), strong compression
+    VR[0, :] = VL[0, :]
+    iv = 1 if model == 0 else ns
+    VL[1, iv:iv + dim] = 8.0
+    VR[1, iv:iv + dim] = 8.5
+    VL[2, iv:iv + dim] = -8.0
+    VR[2, iv:iv + dim] = -8.5
+    VL[3, iv:iv + dim] = 2.5
+    VR[3, iv:iv + dim] = -2.5
+    return VL, VR
+
+
+def ref_riemann(lib, model, dim, ns, gamma, direction, VL, VR):
+    neq = VL.shape[0]
+    rL, cL, eL = orc.side_thermo(model, dim, ns, gamma, VL)
+    rR, cR, eR = orc.side_thermo(model, dim, ns, gamma, VR)
+    F1, F2, vm = (C.c_double * neq)(), (C.c_double * neq)(), C.c_double()
+    rc = lib.ref_riemann_point(model, dim, ns, direction, (C.c_double * neq)(*VL), (C.c_double * neq)(*VR),
+                               C.c_double(rL), C.c_double(rR), C.c_double(cL), C.c_double(cR),
+                               C.c_double(eL), C.c_double(eR), F1, F2, C.byref(vm))
+    assert rc == 0
+    return np.array(F1[:]), np.array(F2[:]), vm.value, (rL, rR, cL, cR, eL, eR)
+
+
+CASES = [("ss", 0, 2, 1, (1.4,)), ("ss", 0, 3, 1, (1.4,)), ("fe", 1, 2, 2, (1.6, 1.4)), ("fe", 1, 3, 2, (1.6, 1.4))]
+
+
+def main():
+    if not os.path.exists(REF_SO):
+        raise SystemExit("oracle/_ref/libhamers_ref.so missing: run oracle/build_ref.py where /root/reference exists")
+    orc.build()
+    lib = ref_lib()
+    rng = np.random.default_rng(20261017)
+    out = {}
+    U = weno_inputs(rng)
+    res = np.array([ref_weno(lib, u) for u in U])
+    out["weno_U"], out["weno_minus"], out["weno_plus"] = U, res[:, 0], res[:, 1]
+    res3 = np.array([ref_weno(lib, u, 3) for u in U])
+    out["weno_minus_p3"], out["weno_plus_p3"] = res3[:, 0], res3[:, 1]
+    for tag, model, dim, ns, gam in CASES:
+        for d in range(dim):
+            VL, VR = riemann_inputs(rng, model, dim, ns)
+            F1s, F2s, vms, ths = [], [], [], []
+            for a, b in zip(VL, VR):
+                F1, F2, vm, th = ref_riemann(lib, model, dim, ns, gam, d, a, b)
+                F1s.append(F1), F2s.append(F2), vms.append(vm), ths.append(th)
+            key = f"rp_{tag}{dim}d{d}"
+            out[key + "_VL"], out[key + "_VR"] = VL, VR
+            out[key + "_thermo"] = np.array(ths)
+            out[key + "_F_HLLC"], out[key + "_F_HYB"], out[key + "_vel_mid"] = np.array(F1s), np.array(F2s), np.array(vms)
+    path = os.path.join(HERE, "point_kernels.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: v.shape for k, v in out.items() if k.startswith("weno")})
+
+
+if __name__ == "__main__":
+    main()

@@ -3,7 +3,7 @@ same seeded inputs.  Exact-arithmetic build: bit-identical.  Fast build: <= 1e-1
 import numpy as np
 import pytest
 
-from common import CASES, RTOL, interior, make_case, rel_err
+from common import CASES, RTOL, assert_fast_parity, interior, make_case, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -46,12 +46,12 @@ def test_flux_and_source_device(name, math, kind, oracle_lib, product_lib):
         if math == 0:
             assert np.array_equal(Fg, Fo[a]), f"dir {a}: exact build must be bit-identical, max diff {np.abs(Fg - Fo[a]).max()}"
         else:
-            assert rel_err(Fg, Fo[a]) <= RTOL
+            assert_fast_parity(Fg, Fo[a])
     Sg = Sd.cpu().numpy()
     if math == 0:
         assert np.array_equal(Sg, So)
     else:
-        assert rel_err(Sg, So) <= RTOL
+        assert_fast_parity(Sg, So)
     plan.close()
 
 
@@ -70,8 +70,8 @@ def test_flux_and_source_host_buffers(name, math, oracle_lib, product_lib):
         if math == 0:
             assert np.array_equal(Fg[a], Fo[a])
         else:
-            assert rel_err(Fg[a], Fo[a]) <= RTOL
-    assert rel_err(Sg, So) <= RTOL
+            assert_fast_parity(Fg[a], Fo[a])
+    assert_fast_parity(Sg, So)
     plan.close()
 
 

@@ -1,0 +1,65 @@
+"""CPU check of the CUDA kernels' indexing and arithmetic: tests/host_emu compiles the very same
+`__host__ __device__` thread functions the sm_100a kernels call (hamers_b200/csrc/hb2_core.cuh) with g++ and
+drives them from loops standing in for the CUDA grid.  Compared against the oracle: bit-identical for the
+exact-arithmetic variant, <= 1e-12 for the fast variant.  (The GPU parity tests remain the parity tests proper;
+this catches mistakes before GPU time is spent.  The emulation is never linked into the product.)"""
+import numpy as np
+import pytest
+
+import emu_host
+from common import CASES, RTOL, assert_fast_parity, interior, make_case, rel_err
+from hamers_b200 import problems as pb
+
+SSPRK3_ALPHA = [[1.0], [3.0 / 4.0, 1.0 / 4.0], [1.0 / 3.0, 0.0, 2.0 / 3.0]]
+SSPRK3_BETA = [[1.0], [0.0, 1.0 / 4.0], [0.0, 0.0, 2.0 / 3.0]]
+
+
+@pytest.mark.parametrize("kind", ["random", "smooth"])
+@pytest.mark.parametrize("math", [0, 1])
+@pytest.mark.parametrize("name", list(CASES))
+def test_emulated_flux_and_source(name, math, kind, oracle_lib):
+    desc, U = make_case(name, kind)
+    Q = pb.pad_periodic(U)
+    dt = 1.0e-3
+    S0 = np.random.default_rng(7).standard_normal((desc.neq,) + desc.cell_shape)
+    Fo, So = oracle_lib.compute_flux_and_source(desc, Q, dt, source=S0.copy())
+    Fe, Se = emu_host.flux_and_source(desc, Q, dt, math=math, source=S0.copy())
+    for a in range(desc.dim):
+        assert not np.isnan(Fe[a]).any()
+        if math == 0:
+            assert np.array_equal(Fe[a], Fo[a]), f"dir {a}: max diff {np.abs(Fe[a] - Fo[a]).max()}"
+        else:
+            assert_fast_parity(Fe[a], Fo[a])
+    if math == 0:
+        assert np.array_equal(Se, So)
+    else:
+        assert_fast_parity(Se, So)
+
+
+@pytest.mark.parametrize("math", [0, 1])
+@pytest.mark.parametrize("name", list(CASES))
+def test_emulated_fused_stages(name, math, oracle_lib):
+    desc, U = make_case(name, "random")
+    dt = 5.0e-4
+    states = [pb.pad_periodic(U)]
+    for sn in range(3):
+        F, S = oracle_lib.compute_flux_and_source(desc, states[-1], dt)
+        n = sn + 1
+        Uo = oracle_lib.advance_stage(desc, SSPRK3_ALPHA[sn], SSPRK3_BETA[sn], states, [None] * (n - 1) + [F], [None] * (n - 1) + [S])
+        Ue = emu_host.fused_stage(desc, SSPRK3_ALPHA[sn], SSPRK3_BETA[sn], states, dt, math=math)
+        if math == 0:
+            assert np.array_equal(interior(desc, Ue), interior(desc, Uo)), f"stage {sn}"
+        else:
+            assert rel_err(interior(desc, Ue), interior(desc, Uo)) <= RTOL, f"stage {sn}"
+        states.append(pb.pad_periodic(np.ascontiguousarray(interior(desc, Uo))))
+
+
+@pytest.mark.parametrize("seg_len,bx", [(5, 32), (3, 64), (0, 128)])
+def test_emulated_tiling_is_invisible(seg_len, bx, oracle_lib):
+    """Segment / tile sizes are launch parameters only: results must not depend on them."""
+    desc, U = make_case("ss3d", "random")
+    Q = pb.pad_periodic(U)
+    Fo, _ = oracle_lib.compute_flux_and_source(desc, Q, 1e-3)
+    Fe, _ = emu_host.flux_and_source(desc, Q, 1e-3, math=0, bx=bx, seg_len=seg_len)
+    for a in range(3):
+        assert np.array_equal(Fe[a], Fo[a])

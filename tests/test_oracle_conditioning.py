@@ -1,0 +1,37 @@
+"""Why the fast-arithmetic parity criterion (tests/common.py: assert_fast_parity) counts a few outlier faces
+separately: the REFERENCE's own formulas are ill-conditioned at isolated faces of the white-noise state.
+
+At z-face (k=4, j=6, i=1) of the five-eqn 3-D random case the sensor selects HLLC-HLL; the blend weights
+alpha_1 = |du_n|/|du|, alpha_2 = sqrt(1 - alpha_1^2), beta_1 = (1 + alpha_1/(alpha_1 + alpha_2))/2
+(FlowModelRiemannSolverFiveEqnAllaireHLLC-HLL.cpp:1702-1734) are built from differences of the two one-sided
+WCNS interpolants.  Perturbing the six stencil cells by <= 2 ulp moves the ORACLE's midpoint flux by several
+1e-12 (relative to the field maximum) in exactly the HLL-blended components (partial densities, tangential
+momentum, volume fraction) and by ~1e-16 in the pure-HLLC ones (normal momentum, energy).  Any re-association
+upstream (FMA contraction, shared reciprocals) therefore moves that face by the same amount."""
+import numpy as np
+
+from common import make_case
+from hamers_b200 import problems as pb
+
+
+def test_reference_formula_is_ill_conditioned_at_isolated_faces(oracle_lib):
+    desc, U = make_case("fe3d", "random")
+    Q = pb.pad_periodic(U)
+    dt = 1.0e-3
+    _, _, Fm, sen = oracle_lib.compute_flux_and_source(desc, Q, dt, debug=True)
+    k, j, i, g = 4, 6, 1, 4
+    assert sen[2][k + 1, j, i] > 0.65                    # HLLC-HLL face
+    base = Fm[2][:, k + 1, j, i].copy()
+    scale = np.abs(Fm[2]).max(axis=(1, 2, 3))
+    rng = np.random.default_rng(0)
+    worst = np.zeros(desc.neq)
+    sl = (slice(None), slice(k - 3 + g, k + 3 + g), j + g, i + g)
+    for _ in range(60):
+        Qp = Q.copy()
+        Qp[sl] = Q[sl] * (1.0 + rng.integers(-2, 3, Q[sl].shape) * 1.11e-16)
+        _, _, Fm2, _ = oracle_lib.compute_flux_and_source(desc, Qp, dt, debug=True)
+        worst = np.maximum(worst, np.abs(Fm2[2][:, k + 1, j, i] - base) / scale)
+    blended = [0, 1, 2, 6]          # Zrho_1, Zrho_2, rho*u (tangential), Z_1
+    pure_hllc = [4, 5]              # rho*w (normal), E
+    assert worst[blended].max() > 1.0e-12, worst
+    assert worst[pure_hllc].max() < 1.0e-14, worst
