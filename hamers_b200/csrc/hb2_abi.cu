@@ -54,6 +54,7 @@ struct hb2_plan_s {
     long long nside[3];
     double* theta;
     double* Omega;
+    unsigned char* hyb;            /* per-cell shock-sensor decisions of the three low faces */
     double* R[HB2_MAXE];
     double* T;
     /* staging for the host-buffer entry points */
@@ -284,11 +285,11 @@ int ensure_ws(hb2_plan_t p, bool fused)
     if (!p->theta) {
         HB2_CUDA(cudaMalloc(&p->theta, sizeof(double) * p->G.ncell_g));
         HB2_CUDA(cudaMalloc(&p->Omega, sizeof(double) * p->G.ncell_g));
-        /* the sweeps read theta/Omega only where the sensor kernel writes them, but the x sweep
-         * may touch skipped positions' neighbours: keep the arrays defined */
+        HB2_CUDA(cudaMalloc(&p->hyb, (size_t)p->G.ncell_g));
         HB2_CUDA(cudaMemsetAsync(p->theta, 0, sizeof(double) * p->G.ncell_g, p->stream));
         HB2_CUDA(cudaMemsetAsync(p->Omega, 0, sizeof(double) * p->G.ncell_g, p->stream));
-        p->ws_bytes += 2 * sizeof(double) * p->G.ncell_g;
+        HB2_CUDA(cudaMemsetAsync(p->hyb, 0, (size_t)p->G.ncell_g, p->stream));
+        p->ws_bytes += 2 * sizeof(double) * p->G.ncell_g + p->G.ncell_g;
     }
     if (p->d.flow_model == HB2_FIVE_EQN_ALLAIRE && !p->T) {
         HB2_CUDA(cudaMalloc(&p->T, sizeof(double) * p->ncell_i));
@@ -309,8 +310,7 @@ void base_args(hb2_plan_t p, const double* const* Q, double dt, DirArgs* A)
     A->G = p->G;
     A->K = p->K;
     for (int c = 0; c < p->ncomp; c++) A->Q[c] = Q[c];
-    A->theta = p->theta;
-    A->Omega = p->Omega;
+    A->hyb = p->hyb;
     A->dt = dt;
     A->T = p->T;
 }
@@ -320,11 +320,14 @@ int run_sensor(hb2_plan_t p, const double* const* Q)
     QTab qt;
     memset(&qt, 0, sizeof(qt));
     for (int c = 0; c < p->ncomp; c++) qt.p[c] = Q[c];
-    /* the sensor feeds a hard switch: always the exact-arithmetic build */
+    /* two launches: theta/Omega, then the per-face decisions.  The fast build evaluates the velocity gradients with
+     * reciprocal multiplications: the decision s > 0.65 can then differ from the oracle's only where s is within a few
+     * ulp of the threshold. */
     int rc;
     {
         ProfScope ps(p, 0);
-        rc = ops_exact()->sensor(p->cfg, p->G, qt, p->theta, p->Omega, p->stream);
+        p->launches++;
+        rc = p->ops->sensor(p->cfg, p->G, qt, p->theta, p->Omega, p->hyb, p->stream);
     }
     if (rc) return fail(-200, std::string("sensor kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
     return 0;
@@ -425,10 +428,6 @@ int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* out)
     p->cfg.model = d->flow_model;
     p->cfg.dim = d->dim;
     p->cfg.ns = d->num_species;
-    p->cfg.bx = env_int("HB2_BX", 128);
-    if (p->cfg.bx < 32 || p->cfg.bx > 1024 || (p->cfg.bx % 32)) p->cfg.bx = 128;
-    p->cfg.march_block = env_int("HB2_MARCH_BLOCK", 128);
-    if (p->cfg.march_block < 32 || p->cfg.march_block > 128 || (p->cfg.march_block % 32)) p->cfg.march_block = 128;
     p->ops = (d->math == HB2_MATH_EXACT) ? ops_exact() : ops_fast();
     p->ncell_i = (long long)p->G.n[0] * p->G.n[1] * p->G.n[2];
     for (int a = 0; a < 3; a++) {
@@ -436,12 +435,14 @@ int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* out)
         ee[a] += 1;
         p->nside[a] = ee[0] * ee[1] * ee[2];
     }
-    /* marching segment length: enough threads for >= ~4 waves of 148 SMs x 256 threads, segments >= 16 cells */
-    const long long target = 148LL * 256 * 4;
-    for (int a = 1; a < d->dim; a++) {
-        const long long pencils = p->ncell_i / p->G.n[a];
-        long long nseg = (target + pencils - 1) / pencils;
-        const long long maxseg = p->G.n[a] / 16 > 0 ? p->G.n[a] / 16 : 1;
+    /* marching segment length per direction: enough blocks for >= ~4 waves of 148 SMs x 3 resident blocks, segments
+     * of at least 64 cells (every segment costs one extra chunk of pipeline fill) */
+    for (int a = 0; a < d->dim; a++) {
+        const long long per_seg = (a == 0) ? ((p->G.n[1] + 7) / 8) * (long long)p->G.n[2]
+                                           : ((p->G.n[0] + 31) / 32) * (long long)(p->ncell_i / p->G.n[0] / p->G.n[a]);
+        const long long target = 148LL * 3 * 4;
+        long long nseg = (target + per_seg - 1) / per_seg;
+        const long long maxseg = p->G.n[a] / 64 > 0 ? p->G.n[a] / 64 : 1;
         if (nseg > maxseg) nseg = maxseg;
         if (nseg < 1) nseg = 1;
         int sl = (int)((p->G.n[a] + nseg - 1) / nseg);
@@ -467,6 +468,7 @@ int hb2_plan_destroy(hb2_plan_t p)
     cudaStreamSynchronize(p->stream);
     cudaFree(p->theta);
     cudaFree(p->Omega);
+    cudaFree(p->hyb);
     cudaFree(p->T);
     for (int e = 0; e < HB2_MAXE; e++) cudaFree(p->R[e]);
     for (int m = 0; m < HB2_MAXS; m++)

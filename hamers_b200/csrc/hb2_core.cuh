@@ -2,7 +2,7 @@
  * hb2_core.cuh -- arithmetic core of the B200 WCNS5-JS / HLLC-HLL path.
  *
  * Everything here is `__host__ __device__` so that the SAME code is (a) inlined into the
- * sm_100a kernels of hb2_kernels.cu and (b) compiled by g++ into the test-only host emulation
+ * sm_100a kernels of hb2_sweeps.cu and (b) compiled by g++ into the test-only host emulation
  * harness (tests/host_emu) that checks indexing and arithmetic against the oracle in a
  * container without a GPU.  (b) is never linked into the product library.
  *
@@ -21,12 +21,9 @@
  *   face flux       ...WCNS56-HLLC-HLL.cpp:2330-2489;  source :2495-2647
  *   RK update       Euler.cpp:1424-1655; FlowModelFiveEqnAllaire.cpp:1739-1886
  *
- * Design (B200-first, not a translation): the reference makes ~35 full-patch passes over
- * ~70 temporaries; here one thread produces a midpoint flux entirely in registers from six
- * stencil cells, converting conservative to primitive variables on the fly.  y/z sweeps march
- * along the sweep axis with lanes across the contiguous x axis (register-rotating stencil,
- * every cell converted once per sweep); the x sweep stages a linear run of cells in shared
- * memory and exchanges midpoint fluxes through it.
+ * This header holds the point arithmetic in the REFERENCE'S OPERATION ORDER (the exact-arithmetic build
+ * is bit-identical to the oracle); hb2_fast.cuh holds the re-associated fast variants and hb2_sweep.cuh
+ * maps threads of a marching thread block onto them.
  */
 #pragma once
 
@@ -83,8 +80,8 @@ struct DirArgs {
     Geom G;
     Consts K;
     const double* Q[HB2_MAXC]; /* conservative components of the state the flux is evaluated on */
-    const double* theta;       /* dilatation, ghost-box layout, valid on cells -2..N+1 */
-    const double* Omega;       /* vorticity magnitude, same */
+    const unsigned char* hyb;  /* per-cell shock-sensor decisions, ghost-box layout: bit d = face between cells
+                                  (c - e_d, c) uses HLLC-HLL (s > 0.65); valid on cells -1..N+1 */
     int mode;                  /* MODE_EMIT | MODE_FUSED */
     double dt;
     double* F[HB2_MAXE];       /* EMIT: side flux arrays of THIS direction */
@@ -96,7 +93,7 @@ struct DirArgs {
     double beta;
     const double* Uint[HB2_MAXS][HB2_MAXC];
     double* Uout[HB2_MAXC];
-    int seg_len;               /* cells per marching segment (y/z sweeps) */
+    int seg_len;               /* cells per marching segment along the sweep axis */
 };
 
 HB2_HD long long cidx(const Geom& G, int i, int j, int k)
@@ -451,11 +448,11 @@ HB2_HD void riemann(const double (&V_L)[Tr::NEQ], const double (&V_R)[Tr::NEQ], 
 
 /* ------------------------------------------------------------------------------------------
  * One midpoint flux from the six stencil cells f-3..f+2 (primitive variables + sound speed of
- * cells L = 2 and R = 3, dilatation / vorticity magnitude of L and R).
+ * cells L = 2 and R = 3; `hybrid` = the face's shock-sensor decision, see face_sensor below).
  * ---------------------------------------------------------------------------------------- */
 template <class Tr, int DIR, int MATH>
-HB2_HD void face_midpoint(const double (&V)[6][Tr::NEQ], double c_cellL, double c_cellR, double th_L, double th_R,
-                          double Om_L, double Om_R, const Consts& K, double (&Fm)[Tr::NEQ], double& vel_mid)
+HB2_HD void face_midpoint(const double (&V)[6][Tr::NEQ], double c_cellL, double c_cellR, bool hybrid, const Consts& K,
+                          double (&Fm)[Tr::NEQ], double& vel_mid)
 {
     constexpr int DIM = Tr::DIM, NS = Tr::NS, NEQ = Tr::NEQ, IV = Tr::IV, IP = Tr::IP;
     const int p = K.weno_p;
@@ -560,12 +557,7 @@ HB2_HD void face_midpoint(const double (&V)[6][Tr::NEQ], double c_cellL, double 
         }
     }
 
-    /* Ducros-like sensor */
-    const double theta_avg = 0.5 * (th_L + th_R);
-    const double Omega_avg = 0.5 * (Om_L + Om_R);
-    const double s = -theta_avg / (fabs(theta_avg) + Omega_avg + HB2_EPS);
-
-    riemann<Tr, DIR>(V_minus, V_plus, K, s > 0.65, Fm, vel_mid);
+    riemann<Tr, DIR>(V_minus, V_plus, K, hybrid, Fm, vel_mid);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -599,278 +591,6 @@ HB2_HD void rk_update_cell(const DirArgs& A, long long x, const double (&rhs)[Tr
 #pragma unroll
         for (int si = 0; si < NS - 1; si++) zl -= Unew[NS + DIM + 1 + si];
         A.Uout[NEQ][x] = zl;
-    }
-}
-
-/* ------------------------------------------------------------------------------------------
- * y / z sweep: one thread marches one pencil segment.
- *   i  : x index of the pencil (lanes run along x -> coalesced)
- *   t  : the other transverse index (k for a y sweep, j for a z sweep; 0 in 2D)
- *   seg: segment number along the sweep axis
- * ---------------------------------------------------------------------------------------- */
-template <class Tr, int DIR, int MATH>
-HB2_HD void march_pencil(const DirArgs& A, int i, int t, int seg)
-{
-    constexpr int DIM = Tr::DIM, NEQ = Tr::NEQ, NCOMP = Tr::NCOMP, IV = Tr::IV, IP = Tr::IP, NS = Tr::NS;
-    constexpr bool LAST = (DIR == DIM - 1);
-    static_assert(DIR >= 1, "march_pencil handles the strided sweeps");
-    const Geom& G = A.G;
-    const int N = G.n[DIR];
-    const int c0 = seg * A.seg_len;
-    if (c0 >= N) return;
-    const int c1 = (c0 + A.seg_len < N) ? c0 + A.seg_len : N;
-    const bool fused = (A.mode == MODE_FUSED);
-
-    /* coordinates of sweep cell 0 */
-    const int j0 = (DIR == 1) ? 0 : t;
-    const int k0 = (DIR == 2) ? 0 : ((DIM == 3) ? t : 0);
-    const long long base = cidx(G, i, j0, k0);
-    const long long st = G.cs[DIR];
-    const double dxd = G.dx[DIR];
-
-    double V[6][NEQ];
-    double cs_[6];
-    double q[NCOMP];
-    /* preload cells c0-4 .. c0 into stencil positions 1..5 */
-#pragma unroll
-    for (int m = 1; m < 6; m++) {
-        load_cons<Tr>(A, base + (long long)(c0 - 5 + m) * st, q);
-        cons_to_prim<Tr>(q, A.K, V[m], cs_[m]);
-    }
-#pragma unroll
-    for (int e = 0; e < NEQ; e++) V[0][e] = V[1][e];
-    cs_[0] = cs_[1];
-
-    double Fm_p[NEQ], Fm_pp[NEQ], Fn_prev[NEQ], Ff_prev[NEQ];
-    double um_1 = 0.0, um_2 = 0.0, um_3 = 0.0; /* u_mid of faces f-1, f-2, f-3 */
-#pragma unroll
-    for (int e = 0; e < NEQ; e++) Fm_p[e] = Fm_pp[e] = Fn_prev[e] = Ff_prev[e] = 0.0;
-
-    for (int f = c0 - 1; f <= c1 + 1; f++) {
-        /* rotate the stencil and bring in cell f+2 */
-#pragma unroll
-        for (int m = 0; m < 5; m++) {
-#pragma unroll
-            for (int e = 0; e < NEQ; e++) V[m][e] = V[m + 1][e];
-            cs_[m] = cs_[m + 1];
-        }
-        const long long xR = base + (long long)f * st; /* cell f (R of face f) */
-        load_cons<Tr>(A, xR + 2 * st, q);
-        cons_to_prim<Tr>(q, A.K, V[5], cs_[5]);
-
-        double Fm[NEQ], um;
-        face_midpoint<Tr, DIR, MATH>(V, cs_[2], cs_[3], A.theta[xR - st], A.theta[xR], A.Omega[xR - st], A.Omega[xR],
-                                     A.K, Fm, um);
-
-        if (f >= c0 + 1) {
-            /* face g = f-1 is complete: cells g-1 (stencil pos 1) and g (pos 2) */
-            const int g = f - 1;
-            const long long xg = xR - st;
-            double Fn[NEQ];
-            load_cons<Tr>(A, xg, q);
-            node_flux<Tr, DIR>(q, V[2], Fn);
-            if (g == c0) {
-                double ql[NCOMP];
-                load_cons<Tr>(A, xg - st, ql);
-                node_flux<Tr, DIR>(ql, V[1], Fn_prev);
-            }
-            double Ff[NEQ];
-#pragma unroll
-            for (int e = 0; e < NEQ; e++)
-                Ff[e] = A.dt * (1.0 / 30.0 * (Fm[e] + Fm_pp[e]) - 3.0 / 10.0 * (Fn[e] + Fn_prev[e]) + 23.0 / 15.0 * Fm_p[e]);
-
-            if (!fused) {
-                if (g < c1 || g == N) {
-                    const int ii = i, jj = (DIR == 1) ? g : j0, kk = (DIR == 2) ? g : k0;
-                    const long long sx = sidx<DIR>(G, ii, jj, kk);
-#pragma unroll
-                    for (int e = 0; e < NEQ; e++) A.F[e][sx] = Ff[e];
-                }
-            }
-            if (g >= c0 + 1) {
-                /* cell cc = g-1 = f-2 (stencil pos 1) has both faces */
-                const int cc = g - 1;
-                const int jj = (DIR == 1) ? cc : j0, kk = (DIR == 2) ? cc : k0;
-                const long long ix = iidx(G, i, jj, kk);
-                double Tsum = 0.0;
-                if (Tr::ADV) {
-                    const double Td = (3.0 / 2.0 * (um_1 - um_2) - 3.0 / 10.0 * (V[2][IV + DIR] - V[0][IV + DIR]) +
-                                       1.0 / 30.0 * (um - um_3)) / dxd;
-                    Tsum = A.T[ix] + Td;
-                    if (!LAST) A.T[ix] = Tsum;
-                }
-                if (fused) {
-                    double rhs[NEQ];
-#pragma unroll
-                    for (int e = 0; e < NEQ; e++) rhs[e] = A.R[e][ix] - (Ff[e] - Ff_prev[e]) / dxd;
-                    if (LAST) {
-                        if (Tr::ADV) {
-#pragma unroll
-                            for (int si = 0; si < NS - 1; si++) {
-                                const int e = IP + 1 + si;
-                                rhs[e] = rhs[e] + A.dt * V[1][e] * Tsum;
-                            }
-                        }
-                        rk_update_cell<Tr>(A, xg - st, rhs);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < NEQ; e++) A.R[e][ix] = rhs[e];
-                    }
-                } else if (LAST && Tr::ADV) {
-#pragma unroll
-                    for (int si = 0; si < NS - 1; si++) {
-                        const int e = IP + 1 + si;
-                        A.S[e][ix] += A.dt * V[1][e] * Tsum;
-                    }
-                }
-            }
-#pragma unroll
-            for (int e = 0; e < NEQ; e++) {
-                Fn_prev[e] = Fn[e];
-                Ff_prev[e] = Ff[e];
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < NEQ; e++) {
-            Fm_pp[e] = Fm_p[e];
-            Fm_p[e] = Fm[e];
-        }
-        um_3 = um_2;
-        um_2 = um_1;
-        um_1 = um;
-    }
-}
-
-/* ------------------------------------------------------------------------------------------
- * x sweep: a block works on BX consecutive linear positions of the ghost-box array (rows of
- * the same k-plane are contiguous, so a run may cross row ends; positions whose face index is
- * outside -1..N+1 are skipped).  Position p <-> face whose RIGHT cell has linear index p.
- *   tile owns positions p0+1 .. p0+BX-3.
- * Shared arrays (doubles):  sV[NEQ+1][BX+5]  primitive variables + sound speed of cells p0-3..p0+BX+1
- *                           sN[NEQ][BX+5]    node fluxes of those cells
- *                           sM[NEQ+1][BX]    midpoint fluxes + HLLC midpoint velocity
- *                           sF[NEQ][BX]      face fluxes
- * The phase functions are called for every thread index with a barrier between phases.
- * ---------------------------------------------------------------------------------------- */
-template <class Tr>
-struct XSmem {
-    static constexpr int NEQ = Tr::NEQ;
-    HB2_HD static long long doubles(int BX) { return (long long)(2 * NEQ + 1) * (BX + 5) + (long long)(2 * NEQ + 1) * BX; }
-    double* sV;
-    double* sN;
-    double* sM;
-    double* sF;
-    int BX;
-    HB2_HD XSmem(double* base, int bx) : BX(bx)
-    {
-        sV = base;
-        sN = sV + (long long)(NEQ + 1) * (BX + 5);
-        sM = sN + (long long)NEQ * (BX + 5);
-        sF = sM + (long long)(NEQ + 1) * BX;
-    }
-};
-
-/* decode a linear position inside plane k (row-contiguous) into the x index i (may be a ghost) and row j */
-HB2_HD void xpos_decode(const Geom& G, long long p, int k, int& i, int& j)
-{
-    const long long plane0 = (long long)(k + G.g[2]) * G.cs[2];
-    const long long r = p - plane0;
-    j = (int)(r / G.gd[0]) - G.g[1];
-    i = (int)(r % G.gd[0]) - G.g[0];
-}
-
-template <class Tr, int MATH>
-HB2_HD void xsweep_phase_load(const DirArgs& A, const XSmem<Tr>& sm, long long p0, int idx)
-{
-    constexpr int NEQ = Tr::NEQ, NCOMP = Tr::NCOMP;
-    if (idx >= sm.BX + 5) return;
-    long long x = p0 - 3 + idx;
-    /* clamp: positions outside the allocation are never used by a valid face */
-    if (x < 0) x = 0;
-    if (x >= A.G.ncell_g) x = A.G.ncell_g - 1;
-    double q[NCOMP], V[NEQ], c, Fn[NEQ];
-    load_cons<Tr>(A, x, q);
-    cons_to_prim<Tr>(q, A.K, V, c);
-    node_flux<Tr, 0>(q, V, Fn);
-#pragma unroll
-    for (int e = 0; e < NEQ; e++) {
-        sm.sV[(long long)e * (sm.BX + 5) + idx] = V[e];
-        sm.sN[(long long)e * (sm.BX + 5) + idx] = Fn[e];
-    }
-    sm.sV[(long long)NEQ * (sm.BX + 5) + idx] = c;
-}
-
-template <class Tr, int MATH>
-HB2_HD void xsweep_phase_mid(const DirArgs& A, const XSmem<Tr>& sm, long long p0, int k, int t)
-{
-    constexpr int NEQ = Tr::NEQ;
-    const int W = sm.BX + 5;
-    const long long p = p0 + t;
-    int i, j;
-    xpos_decode(A.G, p, k, i, j);
-    if (i < -1 || i > A.G.n[0] + 1 || j < 0 || j >= A.G.n[1]) return;
-    double V[6][NEQ];
-#pragma unroll
-    for (int m = 0; m < 6; m++)
-#pragma unroll
-        for (int e = 0; e < NEQ; e++) V[m][e] = sm.sV[(long long)e * W + t + m]; /* cell p-3+m <-> idx t+m */
-    const double cL = sm.sV[(long long)NEQ * W + t + 2], cR = sm.sV[(long long)NEQ * W + t + 3];
-    double Fm[NEQ], um;
-    face_midpoint<Tr, 0, MATH>(V, cL, cR, A.theta[p - 1], A.theta[p], A.Omega[p - 1], A.Omega[p], A.K, Fm, um);
-#pragma unroll
-    for (int e = 0; e < NEQ; e++) sm.sM[(long long)e * sm.BX + t] = Fm[e];
-    sm.sM[(long long)NEQ * sm.BX + t] = um;
-}
-
-template <class Tr, int MATH>
-HB2_HD void xsweep_phase_face(const DirArgs& A, const XSmem<Tr>& sm, long long p0, int k, int t)
-{
-    constexpr int NEQ = Tr::NEQ;
-    const int W = sm.BX + 5;
-    if (t < 1 || t > sm.BX - 2) return;
-    const long long p = p0 + t;
-    int i, j;
-    xpos_decode(A.G, p, k, i, j);
-    if (i < 0 || i > A.G.n[0] || j < 0 || j >= A.G.n[1]) return;
-    const bool owned = (t <= sm.BX - 3);
-    const int kk = (Tr::DIM == 3) ? k : 0;
-#pragma unroll
-    for (int e = 0; e < NEQ; e++) {
-        const double* M = sm.sM + (long long)e * sm.BX;
-        const double* Nf = sm.sN + (long long)e * W;
-        const double Ff = A.dt * (1.0 / 30.0 * (M[t + 1] + M[t - 1]) - 3.0 / 10.0 * (Nf[t + 3] + Nf[t + 2]) + 23.0 / 15.0 * M[t]);
-        sm.sF[(long long)e * sm.BX + t] = Ff;
-        if (A.mode == MODE_EMIT && owned) A.F[e][sidx<0>(A.G, i, j, kk)] = Ff;
-    }
-}
-
-template <class Tr, int MATH>
-HB2_HD void xsweep_phase_cell(const DirArgs& A, const XSmem<Tr>& sm, long long p0, int k, int t)
-{
-    constexpr int NEQ = Tr::NEQ, IV = Tr::IV;
-    const int W = sm.BX + 5;
-    if (t < 1 || t > sm.BX - 3) return;
-    const long long p = p0 + t;
-    int i, j;
-    xpos_decode(A.G, p, k, i, j);
-    if (i < 0 || i >= A.G.n[0] || j < 0 || j >= A.G.n[1]) return;
-    const int kk = (Tr::DIM == 3) ? k : 0;
-    const long long ix = iidx(A.G, i, j, kk);
-    const double dxd = A.G.dx[0];
-    if (Tr::ADV) {
-        const double* um = sm.sM + (long long)NEQ * sm.BX;
-        const double* un = sm.sV + (long long)(IV + 0) * W;
-        /* cell p <-> idx t+3; neighbours idx t+4 / t+2.  faces: t = low face of the cell */
-        const double Td = (3.0 / 2.0 * (um[t + 1] - um[t]) - 3.0 / 10.0 * (un[t + 4] - un[t + 2]) +
-                           1.0 / 30.0 * (um[t + 2] - um[t - 1])) / dxd;
-        A.T[ix] = Td;
-    }
-    if (A.mode == MODE_FUSED) {
-#pragma unroll
-        for (int e = 0; e < NEQ; e++) {
-            const double* F = sm.sF + (long long)e * sm.BX;
-            A.R[e][ix] = -(F[t + 1] - F[t]) / dxd;
-        }
     }
 }
 
@@ -916,6 +636,16 @@ HB2_HD void sensor_cell(const Geom& G, const double* const* Q, long long x, doub
         const double omega_z = grad[1][0] - grad[0][1];
         Omega = sqrt(omega_x * omega_x + omega_y * omega_y + omega_z * omega_z);
     }
+}
+
+/* Shock-sensor decision of the face between cells L and R (ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:2088-2123):
+ * s = -theta_avg/(|theta_avg| + Omega_avg + eps); HLLC-HLL iff s > 0.65. */
+HB2_HD bool face_sensor(double th_L, double th_R, double Om_L, double Om_R)
+{
+    const double theta_avg = 0.5 * (th_L + th_R);
+    const double Omega_avg = 0.5 * (Om_L + Om_R);
+    const double s = -theta_avg / (fabs(theta_avg) + Omega_avg + HB2_EPS);
+    return s > 0.65;
 }
 
 }  // namespace hb2

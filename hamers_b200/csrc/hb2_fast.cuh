@@ -1,0 +1,513 @@
+/*
+ * hb2_fast.cuh -- re-associated ("fast") arithmetic of the WCNS5-JS / HLLC-HLL path for the FP64 pipe of B200.
+ *
+ * Measured on B200 (tools/ubench_fp64.cu, profiles/r01_b_ubench_fp64.txt): DFMA latency 8.2 cycles, one warp
+ * instruction per 2 cycles per SM sub-partition (64 lanes/clk/SM, 36.7 TFLOP/s); `1.0/x` costs 7.4 issue slots,
+ * `a/x` 11.7, `sqrt` 12.5, while MUFU.RCP64H / RSQ64H + two Newton steps cost 4.5 / 7.  The path is bound by the
+ * FP64 pipe, so the fast variant is written to MINIMISE FP64 INSTRUCTIONS while staying an
+ * algebraic re-statement of the reference formulas (<= 1e-12 relative of the oracle on well-conditioned faces):
+ *   - WCNS5-JS: the smoothness indicators in their sum-of-squares form 13/12 (a-2b+c)^2 + 1/4 (..)^2 (the
+ *     polynomial the reference expands, ConvectiveFluxReconstructorWCNS5-JS-HLLC-HLL.cpp:31-44, :58-71), scaled by 4
+ *     (the normalised weights are invariant when beta and epsilon are scaled together); the second differences are
+ *     shared between the minus and the plus side; the six divisions of the normalised weights become ONE reciprocal:
+ *     omega_k = d_k prod_{j!=k} b_j / sum_k(d_k prod_{j!=k} b_j), b_k = (beta_k + eps)^p;
+ *   - characteristic projection constants from one reciprocal of rho c^2;
+ *   - HLLC written on the upwind side only; passive components (mass, tangential momentum, volume fractions) are
+ *     q_K * u_mid with u_mid = u_K + s(chi - 1) (identical to F_K + s(Q*_K - Q_K)); rho_K eps_K = p_K/(gamma-1);
+ *   - reciprocals / square roots by MUFU seed + two Newton steps (~1 ulp, no special-case branches);
+ *   - flux differencing in difference form 3/2 (Fm[c+1]-Fm[c]) + 1/30 (Fm[c+2]-Fm[c-1]) - 3/10 (Fn[c+1]-Fn[c-1]).
+ * Everything is `__host__ __device__` (tests/host_emu runs it on the CPU; there the seeds are plain 1/x, 1/sqrt).
+ *
+ * Reference formulas restated: see the citations in hb2_core.cuh (same functions, reference operation order).
+ */
+#pragma once
+#include "hb2_core.cuh"
+
+namespace hb2 {
+
+HB2_HD double rcp_fast(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+
+/* sqrt(x) for x > 0 (x == 0 gives 0) */
+HB2_HD double sqrt_fast(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    /* Goldschmidt: g -> sqrt(x), h -> 1/(2 sqrt(x)) */
+    double g = x * y;
+    double h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    /* final residual correction */
+    h = fma(h, r, h);
+    r = fma(-g, g, x);
+    g = fma(r, h, g);
+    return (x == 0.0) ? 0.0 : g;
+#else
+    return sqrt(x);
+#endif
+}
+
+/* ------------------------------------------------------------------------------------------
+ * cell stage
+ * ---------------------------------------------------------------------------------------- */
+template <class Tr>
+HB2_HD void cons_to_prim_fast(const double (&q)[Tr::NCOMP], const Consts& K, double (&V)[Tr::NEQ], double& c)
+{
+    constexpr int DIM = Tr::DIM, NS = Tr::NS;
+    if (Tr::MODEL == SS) {
+        const double rho = q[0];
+        const double r = rcp_fast(rho);
+        V[0] = rho;
+        double ke = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+            V[1 + a] = q[1 + a] * r;
+            ke = fma(V[1 + a], V[1 + a], ke);
+        }
+        const double p = (K.gamma[0] - 1.0) * fma(-0.5 * rho, ke, q[DIM + 1]);
+        V[DIM + 1] = p;
+        c = sqrt_fast(K.gamma[0] * p * r);
+    } else {
+        double rho = q[0];
+#pragma unroll
+        for (int si = 1; si < NS; si++) rho += q[si];
+        const double r = rcp_fast(rho);
+#pragma unroll
+        for (int si = 0; si < NS; si++) V[si] = q[si];
+        double ke = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+            V[NS + a] = q[NS + a] * r;
+            ke = fma(V[NS + a], V[NS + a], ke);
+        }
+        double xi = 0.0;
+#pragma unroll
+        for (int si = 0; si < NS; si++) xi = fma(q[NS + DIM + 1 + si], K.inv_gm1[si], xi);
+        const double Gamma = rcp_fast(xi); /* gamma_m - 1 */
+        const double p = Gamma * fma(-0.5 * rho, ke, q[NS + DIM]);
+        V[NS + DIM] = p;
+        /* c^2 = Gamma p/rho + sum_i Y_i p/rho with sum_i Y_i = 1 */
+        c = sqrt_fast((Gamma + 1.0) * p * r);
+#pragma unroll
+        for (int si = 0; si < NS - 1; si++) V[NS + DIM + 1 + si] = q[NS + DIM + 1 + si];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * WCNS5-JS: minus-side and plus-side midpoint values from the six stencil values w0..w5
+ * ---------------------------------------------------------------------------------------- */
+HB2_HD void weno5js_pair_fast(double w0, double w1, double w2, double w3, double w4, double w5, int p, double& wm,
+                              double& wp)
+{
+    const double eps4 = 4.0 * HB2_EPS;
+    /* second differences of the four 3-cell sub-stencils, shared by both sides */
+    const double s012 = (w0 + w2) - 2.0 * w1;
+    const double s123 = (w1 + w3) - 2.0 * w2;
+    const double s234 = (w2 + w4) - 2.0 * w3;
+    const double s345 = (w3 + w5) - 2.0 * w4;
+    const double t012 = (13.0 / 3.0) * s012, t123 = (13.0 / 3.0) * s123, t234 = (13.0 / 3.0) * s234,
+                 t345 = (13.0 / 3.0) * s345;
+    /* minus side (cell 2 is the upwind cell): 4*beta_k = 13/3 s^2 + f^2 */
+    const double f0 = fma(3.0, w2, fma(-4.0, w1, w0));
+    const double f1 = w1 - w3;
+    const double f2 = fma(3.0, w2, fma(-4.0, w3, w4));
+    double b0 = fma(t012, s012, f0 * f0) + eps4;
+    double b1 = fma(t123, s123, f1 * f1) + eps4;
+    double b2 = fma(t234, s234, f2 * f2) + eps4;
+    /* plus side (cell 3 is the upwind cell), mirrored */
+    const double g0 = fma(3.0, w3, fma(-4.0, w4, w5));
+    const double g1 = w4 - w2;
+    const double g2 = fma(3.0, w3, fma(-4.0, w2, w1));
+    double c0 = fma(t345, s345, g0 * g0) + eps4;
+    double c1 = fma(t234, s234, g1 * g1) + eps4;
+    double c2 = fma(t123, s123, g2 * g2) + eps4;
+    if (p == 2) {
+        b0 *= b0; b1 *= b1; b2 *= b2;
+        c0 *= c0; c1 *= c1; c2 *= c2;
+    } else {
+        b0 = ipow_(b0, p); b1 = ipow_(b1, p); b2 = ipow_(b2, p);
+        c0 = ipow_(c0, p); c1 = ipow_(c1, p); c2 = ipow_(c2, p);
+    }
+    /* un-normalised weights (x16): a0 = b1 b2, a1 = 10 b0 b2, a2 = 5 b0 b1; sub-stencil values with the linear-weight
+     * ratios folded in */
+    {
+        const double a0 = b1 * b2, a1 = b0 * b2, a2 = b0 * b1;
+        const double sum = fma(5.0, a2, fma(10.0, a1, a0));
+        const double P0 = fma(1.875, w2, fma(-1.25, w1, 0.375 * w0));
+        const double P1 = fma(3.75, w3, fma(7.5, w2, -1.25 * w1));   /* 10 * (-1/8 w1 + 6/8 w2 + 3/8 w3) */
+        const double P2 = fma(-0.625, w4, fma(3.75, w3, 1.875 * w2)); /* 5 * (3/8 w2 + 6/8 w3 - 1/8 w4) */
+        wm = fma(a2, P2, fma(a1, P1, a0 * P0)) * rcp_fast(sum);
+    }
+    {
+        const double a0 = c1 * c2, a1 = c0 * c2, a2 = c0 * c1;
+        const double sum = fma(5.0, a2, fma(10.0, a1, a0));
+        const double P0 = fma(1.875, w3, fma(-1.25, w4, 0.375 * w5));
+        const double P1 = fma(3.75, w2, fma(7.5, w3, -1.25 * w4));
+        const double P2 = fma(-0.625, w1, fma(3.75, w2, 1.875 * w3));
+        wp = fma(a2, P2, fma(a1, P1, a0 * P0)) * rcp_fast(sum);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * HLLC (always) and HLLC-HLL (when `hybrid`) midpoint flux from the two interpolated states
+ * ---------------------------------------------------------------------------------------- */
+template <class Tr, int DIR>
+HB2_HD void riemann_fast(const double (&V_L)[Tr::NEQ], const double (&V_R)[Tr::NEQ], const Consts& K, bool hybrid,
+                         double (&Fm)[Tr::NEQ], double& vel_mid)
+{
+    constexpr int DIM = Tr::DIM, NS = Tr::NS, NEQ = Tr::NEQ, IV = Tr::IV, IP = Tr::IP;
+
+    /* side thermodynamics: rho, c, and pe = rho*eps = p/(gamma_m - 1) */
+    double rho_L, rho_R, g1_L, g1_R; /* g1 = 1/(gamma_m - 1) */
+    if (Tr::MODEL == SS) {
+        rho_L = V_L[0];
+        rho_R = V_R[0];
+        g1_L = g1_R = K.inv_gm1[0];
+    } else {
+        rho_L = V_L[0];
+        rho_R = V_R[0];
+#pragma unroll
+        for (int si = 1; si < NS; si++) {
+            rho_L += V_L[si];
+            rho_R += V_R[si];
+        }
+        double zl_L = 1.0, zl_R = 1.0;
+        g1_L = 0.0;
+        g1_R = 0.0;
+#pragma unroll
+        for (int si = 0; si < NS - 1; si++) {
+            g1_L = fma(V_L[IP + 1 + si], K.inv_gm1[si], g1_L);
+            g1_R = fma(V_R[IP + 1 + si], K.inv_gm1[si], g1_R);
+            zl_L -= V_L[IP + 1 + si];
+            zl_R -= V_R[IP + 1 + si];
+        }
+        g1_L = fma(zl_L, K.inv_gm1[NS - 1], g1_L);
+        g1_R = fma(zl_R, K.inv_gm1[NS - 1], g1_R);
+    }
+    const double p_L = V_L[IP], p_R = V_R[IP];
+    const double un_L = V_L[IV + DIR], un_R = V_R[IV + DIR];
+    /* c^2 = gamma_m p/rho, gamma_m = 1 + 1/g1 */
+    const double rr = rcp_fast(rho_L * rho_R);
+    double gam_L, gam_R;
+    if (Tr::MODEL == SS) {
+        gam_L = gam_R = K.gamma[0];
+    } else {
+        const double rg = rcp_fast(g1_L * g1_R);
+        gam_L = fma(rg, g1_R, 1.0);
+        gam_R = fma(rg, g1_L, 1.0);
+    }
+    const double c_L = sqrt_fast(gam_L * p_L * (rr * rho_R));
+    const double c_R = sqrt_fast(gam_R * p_R * (rr * rho_L));
+
+    const double u_average = 0.5 * (un_L + un_R);
+    const double c_average = 0.5 * (c_L + c_R);
+    const double s_L = fmin(u_average - c_average, un_L - c_L);
+    const double s_R = fmax(u_average + c_average, un_R + c_R);
+    const double m_L = rho_L * (s_L - un_L);
+    const double m_R = rho_R * (s_R - un_R);
+    const double s_star = fma(m_L, un_L, fma(-m_R, un_R, p_R - p_L)) * rcp_fast(m_L - m_R);
+
+    /* upwind side of the contact */
+    const bool left = s_star > 0.0;
+    const double rho_K = left ? rho_L : rho_R;
+    const double un_K = left ? un_L : un_R;
+    const double p_K = left ? p_L : p_R;
+    const double s_K = left ? s_L : s_R;
+    const double g1_K = left ? g1_L : g1_R;
+    const double s_mp = left ? fmin(0.0, s_L) : fmax(0.0, s_R);
+    const double d_K = s_K - un_K;
+    const double d_S = s_K - s_star;
+    const double rdd = rcp_fast(d_K * d_S);
+    const double Chi = d_K * d_K * rdd;  /* (s_K - u_K)/(s_K - s*) */
+    const double pd = p_K * d_S * rdd;   /* p_K/(s_K - u_K) */
+    const double u_mid = fma(s_mp, Chi - 1.0, un_K);
+    vel_mid = u_mid;
+
+    double ke = 0.0;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) {
+        const double v = left ? V_L[IV + a] : V_R[IV + a];
+        ke = fma(v, v, ke);
+    }
+    const double E_K = fma(0.5 * rho_K, ke, p_K * g1_K);
+    const double ru = rho_K * u_mid;
+    /* passive components: q_K * u_mid */
+#pragma unroll
+    for (int si = 0; si < Tr::NM; si++) Fm[si] = (Tr::MODEL == SS ? rho_K : (left ? V_L[si] : V_R[si])) * u_mid;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) {
+        if (a == DIR) continue;
+        Fm[IV + a] = ru * (left ? V_L[IV + a] : V_R[IV + a]);
+    }
+#pragma unroll
+    for (int e = IP + 1; e < NEQ; e++) Fm[e] = (left ? V_L[e] : V_R[e]) * u_mid;
+    /* normal momentum: rho u^2 + p + s(chi rho s* - rho u) */
+    const double run = rho_K * un_K;
+    const double cr = Chi * rho_K;
+    Fm[IV + DIR] = fma(s_mp, fma(cr, s_star, -run), fma(run, un_K, p_K));
+    /* energy: u(E + p) + s(chi(E + (s* - u)(rho s* + p/(s_K - u))) - E) */
+    const double Es = Chi * fma(s_star - un_K, fma(rho_K, s_star, pd), E_K);
+    Fm[IP] = fma(s_mp, Es - E_K, un_K * (E_K + p_K));
+
+    if (!hybrid) return;
+
+    /* HLLC-HLL: blend the passive components with the HLL flux */
+    double diff[DIM];
+    double mag2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) {
+        diff[a] = V_R[IV + a] - V_L[IV + a];
+        mag2 = fma(diff[a], diff[a], mag2);
+    }
+    const double vel_mag = sqrt(mag2);
+    double alpha_1, alpha_2;
+    if (vel_mag < HB2_EPS) {
+        alpha_1 = 1.0;
+        alpha_2 = 0.0;
+    } else {
+        alpha_1 = fabs(diff[DIR]) / vel_mag;
+        alpha_2 = sqrt(1.0 - alpha_1 * alpha_1);
+    }
+    const double beta_1 = 0.5 * (1.0 + alpha_1 / (alpha_1 + alpha_2));
+    const double beta_2 = 1.0 - beta_1;
+    const double rs = 1.0 / (s_R - s_L);
+#pragma unroll
+    for (int e = 0; e < NEQ; e++) {
+        if (e == IV + DIR || e == IP) continue;
+        /* conservative value of the component on each side */
+        double Q_L, Q_R;
+        if (e < Tr::NM) {
+            Q_L = (Tr::MODEL == SS) ? rho_L : V_L[e];
+            Q_R = (Tr::MODEL == SS) ? rho_R : V_R[e];
+        } else if (e < IP) {
+            Q_L = rho_L * V_L[e];
+            Q_R = rho_R * V_R[e];
+        } else {
+            Q_L = V_L[e];
+            Q_R = V_R[e];
+        }
+        const double F_L = un_L * Q_L, F_R = un_R * Q_R;
+        double F_HLL = (s_R * F_L - s_L * F_R + s_R * s_L * (Q_R - Q_L)) * rs;
+        if (s_L > 0.0) F_HLL = F_L;
+        if (s_R < 0.0) F_HLL = F_R;
+        Fm[e] = beta_1 * Fm[e] + beta_2 * F_HLL;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * One midpoint flux, stencil read from shared memory.
+ *   sV  : primitive variables + sound speed, component-major: sV[comp*CS + so[m]] is component `comp` of
+ *         stencil cell m (m = 0..5 <-> cells f-3..f+2); comp NEQ is the sound speed.
+ * The characteristic fields are processed by a loop that is NOT unrolled, so that the WCNS5-JS body exists once
+ * in the instruction stream (the hot loop stays inside the instruction cache).
+ * ---------------------------------------------------------------------------------------- */
+template <class Tr, int DIR>
+HB2_HD void face_midpoint_fast(const double* sV, int CS, const int (&so)[6], bool hybrid, const Consts& K,
+                               double (&Fm)[Tr::NEQ], double& vel_mid)
+{
+    constexpr int DIM = Tr::DIM, NS = Tr::NS, NEQ = Tr::NEQ, IV = Tr::IV, IP = Tr::IP;
+    static_assert(NS <= 2, "fast path is written for at most two species");
+    const int p = K.weno_p;
+    /* tangential velocity components in index order */
+    constexpr int T0 = (DIR == 0) ? 1 : 0;
+    constexpr int T1 = (DIR == 2) ? 1 : 2;
+
+    double V_minus[NEQ], V_plus[NEQ];
+    const double c_avg = 0.5 * (sV[NEQ * CS + so[2]] + sV[NEQ * CS + so[3]]);
+
+    if (Tr::MODEL == SS) {
+        const double rho_avg = 0.5 * (sV[so[2]] + sV[so[3]]);
+        const double kp = 0.5 * rho_avg * c_avg;
+        const double r_rcc = rcp_fast(rho_avg * c_avg * c_avg);
+        const double r_cc = r_rcc * rho_avg; /* 1/c^2 */
+        const double r_rc = r_rcc * c_avg;   /* 1/(rho c) */
+        double rm = 0.0, rp = 0.0, um = 0.0, up = 0.0, pm = 0.0, pp = 0.0, t0m = 0.0, t0p = 0.0, t1m = 0.0, t1p = 0.0;
+#pragma unroll 1
+        for (int f = 0; f < NEQ; f++) {
+            int xc;
+            double a = 1.0, b = 0.0;
+            if (f == 0) {
+                xc = 1 + DIR; a = -kp; b = 0.5;
+            } else if (f == 1) {
+                xc = 0; b = -r_cc;
+            } else if (f == NEQ - 1) {
+                xc = 1 + DIR; a = kp; b = 0.5;
+            } else {
+                xc = 1 + ((f == 2) ? T0 : T1);
+            }
+            const double* X = sV + xc * CS;
+            double w[6];
+#pragma unroll
+            for (int m = 0; m < 6; m++) w[m] = X[so[m]];
+            if (b != 0.0) {
+                const double* Y = sV + IP * CS;
+#pragma unroll
+                for (int m = 0; m < 6; m++) w[m] = fma(a, w[m], b * Y[so[m]]);
+            }
+            double wm, wp;
+            weno5js_pair_fast(w[0], w[1], w[2], w[3], w[4], w[5], p, wm, wp);
+            if (f == 0) {
+                rm = r_cc * wm; rp = r_cc * wp;
+                um = -r_rc * wm; up = -r_rc * wp;
+                pm = wm; pp = wp;
+            } else if (f == 1) {
+                rm += wm; rp += wp;
+            } else if (f == NEQ - 1) {
+                rm = fma(r_cc, wm, rm); rp = fma(r_cc, wp, rp);
+                um = fma(r_rc, wm, um); up = fma(r_rc, wp, up);
+                pm += wm; pp += wp;
+            } else if (f == 2) {
+                t0m = wm; t0p = wp;
+            } else {
+                t1m = wm; t1p = wp;
+            }
+        }
+        V_minus[0] = rm; V_plus[0] = rp;
+        V_minus[1 + DIR] = um; V_plus[1 + DIR] = up;
+        V_minus[IP] = pm; V_plus[IP] = pp;
+        V_minus[1 + T0] = t0m; V_plus[1 + T0] = t0p;
+        if (DIM == 3) {
+            V_minus[1 + (T1 % DIM)] = t1m; V_plus[1 + (T1 % DIM)] = t1p;
+        }
+    } else {
+        double Zr_avg[2];
+        double rho_avg = 0.0;
+#pragma unroll
+        for (int si = 0; si < NS; si++) {
+            Zr_avg[si] = 0.5 * (sV[si * CS + so[2]] + sV[si * CS + so[3]]);
+            rho_avg += Zr_avg[si];
+        }
+        const double rc = rho_avg * c_avg;
+        const double r_rcc = rcp_fast(rc * c_avg);
+        const double r_rc = r_rcc * c_avg;  /* 1/(rho c) */
+        const double r_c = r_rcc * rc;      /* 1/c */
+        const double zc0 = Zr_avg[0] * r_rcc, zc1 = Zr_avg[NS - 1] * r_rcc; /* (Z rho)_avg/(rho c^2) */
+        const double yh0 = 0.5 * Zr_avg[0] * r_c, yh1 = 0.5 * Zr_avg[NS - 1] * r_c;
+        double z0m = 0.0, z0p = 0.0, z1m = 0.0, z1p = 0.0, um = 0.0, up = 0.0, pm = 0.0, pp = 0.0;
+        double t0m = 0.0, t0p = 0.0, t1m = 0.0, t1p = 0.0, zzm = 0.0, zzp = 0.0;
+        /* field order of the reference: u_n - p/(rho c) | Z_i rho_i - .. p (NS) | tangential (DIM-1) | Z_i (NS-1) | u_n + p/(rho c) */
+        constexpr int F_T = 1 + NS, F_Z = F_T + (DIM - 1);
+#pragma unroll 1
+        for (int f = 0; f < NEQ; f++) {
+            int xc;
+            double b = 0.0;
+            if (f == 0) {
+                xc = IV + DIR; b = -r_rc;
+            } else if (f <= NS) {
+                xc = f - 1; b = (f == 1) ? -zc0 : -zc1;
+            } else if (f < F_Z) {
+                xc = IV + ((f == F_T) ? T0 : T1);
+            } else if (f < NEQ - 1) {
+                xc = IP + 1 + (f - F_Z);
+            } else {
+                xc = IV + DIR; b = r_rc;
+            }
+            const double* X = sV + xc * CS;
+            double w[6];
+#pragma unroll
+            for (int m = 0; m < 6; m++) w[m] = X[so[m]];
+            if (b != 0.0) {
+                const double* Y = sV + IP * CS;
+#pragma unroll
+                for (int m = 0; m < 6; m++) w[m] = fma(b, Y[so[m]], w[m]);
+            }
+            double wm, wp;
+            weno5js_pair_fast(w[0], w[1], w[2], w[3], w[4], w[5], p, wm, wp);
+            if (f == 0) {
+                z0m = -yh0 * wm; z0p = -yh0 * wp;
+                z1m = -yh1 * wm; z1p = -yh1 * wp;
+                um = 0.5 * wm; up = 0.5 * wp;
+                pm = -0.5 * rc * wm; pp = -0.5 * rc * wp;
+            } else if (f == 1) {
+                z0m += wm; z0p += wp;
+            } else if (f <= NS) {
+                z1m += wm; z1p += wp;
+            } else if (f == F_T) {
+                t0m = wm; t0p = wp;
+            } else if (f < F_Z) {
+                t1m = wm; t1p = wp;
+            } else if (f < NEQ - 1) {
+                zzm = wm; zzp = wp;
+            } else {
+                z0m = fma(yh0, wm, z0m); z0p = fma(yh0, wp, z0p);
+                z1m = fma(yh1, wm, z1m); z1p = fma(yh1, wp, z1p);
+                um = fma(0.5, wm, um); up = fma(0.5, wp, up);
+                pm = fma(0.5 * rc, wm, pm); pp = fma(0.5 * rc, wp, pp);
+            }
+        }
+        V_minus[0] = z0m; V_plus[0] = z0p;
+        if (NS == 2) {
+            V_minus[NS - 1] = z1m; V_plus[NS - 1] = z1p;
+            V_minus[IP + 1] = zzm; V_plus[IP + 1] = zzp;
+        }
+        V_minus[IV + DIR] = um; V_plus[IV + DIR] = up;
+        V_minus[IP] = pm; V_plus[IP] = pp;
+        V_minus[IV + T0] = t0m; V_plus[IV + T0] = t0p;
+        if (DIM == 3) {
+            V_minus[IV + (T1 % DIM)] = t1m; V_plus[IV + (T1 % DIM)] = t1p;
+        }
+    }
+
+    /* bounds check and first-order fallback (rare) */
+    const int ok = side_bounded<Tr>(V_minus, K) & side_bounded<Tr>(V_plus, K);
+    if (!ok) {
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) {
+            V_minus[e] = sV[e * CS + so[2]];
+            V_plus[e] = sV[e * CS + so[3]];
+        }
+    }
+    riemann_fast<Tr, DIR>(V_minus, V_plus, K, hybrid, Fm, vel_mid);
+}
+
+/* sensor inputs with reciprocal multiplications (same quantities as sensor_cell) */
+template <class Tr>
+HB2_HD void sensor_cell_fast(const Geom& G, const double* const* Q, long long x, const double (&hidx)[3], double& theta,
+                             double& Omega)
+{
+    constexpr int DIM = Tr::DIM, NM = Tr::NM;
+    double grad[DIM][DIM];
+#pragma unroll
+    for (int b = 0; b < DIM; b++) {
+        const long long xp = x + G.cs[b], xm = x - G.cs[b];
+        double rp = Q[0][xp], rm = Q[0][xm];
+#pragma unroll
+        for (int si = 1; si < NM; si++) {
+            rp += Q[si][xp];
+            rm += Q[si][xm];
+        }
+        const double rr = rcp_fast(rp * rm);
+        const double ip = rr * rm * hidx[b], im = rr * rp * hidx[b]; /* (1/rho_+-) * 0.5/dx_b */
+#pragma unroll
+        for (int a = 0; a < DIM; a++) grad[a][b] = fma(Q[NM + a][xp], ip, -Q[NM + a][xm] * im);
+    }
+    if (DIM == 2) {
+        theta = grad[0][0] + grad[1][1];
+        Omega = fabs(grad[1][0] - grad[0][1]);
+    } else {
+        theta = grad[0][0] + grad[1][1] + grad[2 % DIM][2 % DIM];
+        const double omega_x = grad[2 % DIM][1] - grad[1][2 % DIM];
+        const double omega_y = grad[0][2 % DIM] - grad[2 % DIM][0];
+        const double omega_z = grad[1][0] - grad[0][1];
+        Omega = sqrt_fast(fma(omega_x, omega_x, fma(omega_y, omega_y, omega_z * omega_z)));
+    }
+}
+
+}  // namespace hb2

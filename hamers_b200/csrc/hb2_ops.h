@@ -27,13 +27,12 @@ struct QTab {
 
 struct LaunchCfg {
     int model, dim, ns;
-    int bx;          /* x-sweep block width */
-    int march_block; /* threads per block of the marching sweeps */
 };
 
 struct Ops {
-    /* theta / Omega on cells -2..N+1 (always exact arithmetic) */
-    int (*sensor)(const LaunchCfg&, const Geom&, const QTab& Q, double* theta, double* Omega, cudaStream_t);
+    /* theta / Omega on cells -2..N+1, then the per-face s > 0.65 decisions (one byte per cell) on cells -1..N+1 */
+    int (*sensor)(const LaunchCfg&, const Geom&, const QTab& Q, double* theta, double* Omega, unsigned char* hyb,
+                  cudaStream_t);
     /* one direction sweep */
     int (*sweep)(const LaunchCfg&, int dir, const DirArgs&, cudaStream_t);
     /* Euler::advanceSingleStepOnPatch from materialised fluxes */

@@ -3,19 +3,18 @@
  *
  * Compiled TWICE into the product library:
  *   -DHB2_MATH=0 -fmad=false : reference operation order, bit-identical to the oracle
- *   -DHB2_MATH=1 -fmad=true  : FMA contraction + one-division WENO weights (<= 1e-12 relative)
- * The arithmetic lives in hb2_core.cuh; this file only maps threads onto it.
+ *   -DHB2_MATH=1 -fmad=true  : FP64-instruction-minimal re-association (hb2_fast.cuh), <= 1e-12 relative
+ * The arithmetic lives in hb2_core.cuh / hb2_fast.cuh, the thread mapping in hb2_sweep.cuh; this file holds the
+ * __global__ entry points and their launchers.
  *
- * Kernel shapes
- *   k_sensor  : thread per cell of the (N+4)^d box, dilatation + vorticity magnitude.
- *   k_xsweep  : block = BX consecutive linear positions of one k-plane staged in shared memory
- *               (primitive variables + node fluxes, converted once per cell), thread per midpoint
- *               flux, midpoint/face fluxes exchanged through shared memory.
- *   k_march   : y / z sweeps; lanes along x (coalesced 8-byte loads, 256 B per warp row), each thread
- *               marches a pencil segment with a register-rotating 6-cell stencil.
+ * Kernels
+ *   k_sensor  : thread per cell of the (N+4)^d box: dilatation + vorticity magnitude.
+ *   k_flags   : thread per cell of the (N+3)^d box: the s > 0.65 decision of the cell's three low faces (one byte).
+ *   k_sweep   : one direction: a 256-thread block marches along the sweep axis (hb2_sweep.cuh).
  *   k_advance : RK update from materialised side fluxes (API-preserving mode).
  */
 #include "hb2_ops.h"
+#include "hb2_sweep.cuh"
 
 #ifndef HB2_MATH
 #error "compile with -DHB2_MATH=0 (exact) or -DHB2_MATH=1 (fast)"
@@ -33,44 +32,75 @@ __global__ void __launch_bounds__(256) k_sensor(const __grid_constant__ Geom G, 
     const double* const* Q = Qtab.p;
     const int e0 = G.n[0] + 4, e1 = G.n[1] + 4, e2 = (Tr::DIM == 3) ? G.n[2] + 4 : 1;
     const long long total = (long long)e0 * e1 * e2;
+    const double hidx[3] = {0.5 / G.dx[0], 0.5 / G.dx[1], 0.5 / G.dx[2]};
     for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total;
          id += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(id % e0) - 2;
-        const int j = (int)((id / e0) % e1) - 2;
-        const int k = (Tr::DIM == 3) ? (int)(id / ((long long)e0 * e1)) - 2 : 0;
+        const long long r = id / e0;
+        const int j = (int)(r % e1) - 2;
+        const int k = (Tr::DIM == 3) ? (int)(r / e1) - 2 : 0;
         const long long x = cidx(G, i, j, k);
         double th, Om;
-        sensor_cell<Tr>(G, Q, x, th, Om);
+        if (MATH == 0)
+            sensor_cell<Tr>(G, Q, x, th, Om);
+        else
+            sensor_cell_fast<Tr>(G, Q, x, hidx, th, Om);
         theta[x] = th;
         Omega[x] = Om;
     }
 }
 
-template <class Tr>
-__global__ void __launch_bounds__(128) k_xsweep(const __grid_constant__ DirArgs A, int BX, long long tiles_per_plane)
+/* bit d of hyb[cell] = shock-sensor decision of the face between cells (cell - e_d) and cell, for cells -1..N+1 */
+template <int DIM>
+__global__ void __launch_bounds__(256) k_flags(const __grid_constant__ Geom G, const double* __restrict__ theta,
+                                               const double* __restrict__ Omega, unsigned char* __restrict__ hyb)
 {
-    extern __shared__ double smem[];
-    XSmem<Tr> sm(smem, BX);
-    const long long tile = blockIdx.x % tiles_per_plane;
-    const int k = (int)(blockIdx.x / tiles_per_plane);
-    const long long pstart = cidx(A.G, -A.G.g[0], 0, k);
-    const long long p0 = pstart - 1 + tile * (long long)(BX - 3);
-    const int t = threadIdx.x;
-    for (int idx = t; idx < BX + 5; idx += blockDim.x) xsweep_phase_load<Tr, MATH>(A, sm, p0, idx);
-    __syncthreads();
-    xsweep_phase_mid<Tr, MATH>(A, sm, p0, k, t);
-    __syncthreads();
-    xsweep_phase_face<Tr, MATH>(A, sm, p0, k, t);
-    __syncthreads();
-    xsweep_phase_cell<Tr, MATH>(A, sm, p0, k, t);
+    const int e0 = G.n[0] + 3, e1 = G.n[1] + 3, e2 = (DIM == 3) ? G.n[2] + 3 : 1;
+    const long long total = (long long)e0 * e1 * e2;
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total;
+         id += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(id % e0) - 1;
+        const long long r = id / e0;
+        const int j = (int)(r % e1) - 1;
+        const int k = (DIM == 3) ? (int)(r / e1) - 1 : 0;
+        const long long x = cidx(G, i, j, k);
+        const double th = theta[x], Om = Omega[x];
+        unsigned char f = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            const long long xl = x - G.cs[d];
+            if (face_sensor(theta[xl], th, Omega[xl], Om)) f |= (unsigned char)(1u << d);
+        }
+        hyb[x] = f;
+    }
 }
 
 template <class Tr, int DIR>
-__global__ void __launch_bounds__(128) k_march(const __grid_constant__ DirArgs A)
+__global__ void __launch_bounds__(256) k_sweep(const __grid_constant__ DirArgs A)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.G.n[0]) return;
-    march_pencil<Tr, DIR, MATH>(A, i, (int)blockIdx.y, (int)blockIdx.z);
+    using Sh = SweepShape<Tr, DIR>;
+    extern __shared__ double smem[];
+    const BlockId b = {(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z};
+    const PencilCtx c = pencil_ctx<Tr, DIR>(A, b, (int)threadIdx.x);
+    const int nsteps = Sh::nsteps(c.c1 - c.c0);
+    double q[Tr::NCOMP];
+    int s;
+    bool have = load_wanted<Tr, DIR>(c, 0, s);
+    if (have) load_cons<Tr>(A, c.base + (long long)s * c.st, q);
+    for (int t = 0; t < nsteps; t++) {
+        if (have) phase_commit<Tr, DIR, MATH>(A, smem, c, s, q);
+        __syncthreads();
+        /* issue the loads of the next chunk; they complete behind the FP64-bound face phase */
+        int s_next = 0;
+        const bool have_next = (t + 1 < nsteps) && load_wanted<Tr, DIR>(c, t + 1, s_next);
+        if (have_next) load_cons<Tr>(A, c.base + (long long)s_next * c.st, q);
+        phase_face<Tr, DIR, MATH>(A, smem, c, t);
+        __syncthreads();
+        phase_update<Tr, DIR, MATH>(A, smem, c, t);
+        __syncthreads();
+        have = have_next;
+        s = s_next;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_advance(const __grid_constant__ AdvanceArgs P)
@@ -141,48 +171,56 @@ __global__ void __launch_bounds__(256) k_advance(const __grid_constant__ Advance
     }
 }
 
+
 /* ---- host-side launchers ------------------------------------------------------------- */
 
 template <class Tr>
-int launch_sensor_t(const Geom& G, const QTab& Qtab_dev, double* theta, double* Omega, cudaStream_t st)
+int launch_sensor_t(const Geom& G, const QTab& Qtab_dev, double* theta, double* Omega, unsigned char* hyb, cudaStream_t st)
 {
     const long long total = (long long)(G.n[0] + 4) * (G.n[1] + 4) * (Tr::DIM == 3 ? G.n[2] + 4 : 1);
     long long blocks = (total + 255) / 256;
     if (blocks > 148LL * 64) blocks = 148LL * 64;
     k_sensor<Tr><<<(unsigned)blocks, 256, 0, st>>>(G, Qtab_dev, theta, Omega);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    k_flags<Tr::DIM><<<(unsigned)blocks, 256, 0, st>>>(G, theta, Omega, hyb);
+    return (int)cudaGetLastError();
+}
+
+template <class Tr, int DIR>
+int launch_dir(const DirArgs& A, cudaStream_t st)
+{
+    using Sh = SweepShape<Tr, DIR>;
+    const Geom& G = A.G;
+    const size_t smem = (size_t)Sh::SMEM_DOUBLES * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_sweep<Tr, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int nseg = (G.n[DIR] + A.seg_len - 1) / A.seg_len;
+    dim3 grid(1, 1, nseg);
+    if (DIR == 0) {
+        grid.x = (G.n[1] + Sh::P - 1) / Sh::P;
+        grid.y = (Tr::DIM == 3) ? G.n[2] : 1;
+    } else if (DIR == 1) {
+        grid.x = (G.n[0] + 31) / 32;
+        grid.y = (Tr::DIM == 3) ? G.n[2] : 1;
+    } else {
+        grid.x = (G.n[0] + 31) / 32;
+        grid.y = G.n[1];
+    }
+    k_sweep<Tr, DIR><<<grid, Sh::NT, smem, st>>>(A);
     return (int)cudaGetLastError();
 }
 
 template <class Tr>
-int launch_sweep_t(const LaunchCfg& cfg, int dir, const DirArgs& A, cudaStream_t st)
+int launch_sweep_t(const LaunchCfg&, int dir, const DirArgs& A, cudaStream_t st)
 {
-    const Geom& G = A.G;
-    if (dir == 0) {
-        const int BX = cfg.bx;
-        const long long run = (long long)G.n[1] * G.gd[0];
-        const long long tiles = (run + (BX - 3) - 1) / (BX - 3);
-        const long long planes = (Tr::DIM == 3) ? G.n[2] : 1;
-        const size_t smem = (size_t)XSmem<Tr>::doubles(BX) * sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(k_xsweep<Tr>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_set = true;
-        }
-        k_xsweep<Tr><<<(unsigned)(tiles * planes), BX, smem, st>>>(A, BX, tiles);
-        return (int)cudaGetLastError();
-    }
-    const int nthr = cfg.march_block;
-    const int N = G.n[dir];
-    const int nseg = (N + A.seg_len - 1) / A.seg_len;
-    dim3 grid((G.n[0] + nthr - 1) / nthr, 1, nseg);
-    if (dir == 1) {
-        grid.y = (Tr::DIM == 3) ? G.n[2] : 1;
-        k_march<Tr, 1><<<grid, nthr, 0, st>>>(A);
-    } else {
-        grid.y = G.n[1];
-        k_march<Tr, (Tr::DIM == 3 ? 2 : 1)><<<grid, nthr, 0, st>>>(A);
-    }
-    return (int)cudaGetLastError();
+    if (dir == 0) return launch_dir<Tr, 0>(A, st);
+    if (dir == 1) return launch_dir<Tr, 1>(A, st);
+    return launch_dir<Tr, (Tr::DIM == 3 ? 2 : 1)>(A, st);
 }
 
 #define HB2_DISPATCH(cfg, CALL)                                                       \
@@ -193,9 +231,10 @@ int launch_sweep_t(const LaunchCfg& cfg, int dir, const DirArgs& A, cudaStream_t
         if ((cfg).model == FE && (cfg).dim == 3 && (cfg).ns == 2) { using Tr = Traits<FE, 3, 2>; CALL; } \
     } while (0)
 
-int op_sensor(const LaunchCfg& cfg, const Geom& G, const QTab& Qtab_dev, double* theta, double* Omega, cudaStream_t st)
+int op_sensor(const LaunchCfg& cfg, const Geom& G, const QTab& Qtab_dev, double* theta, double* Omega, unsigned char* hyb,
+              cudaStream_t st)
 {
-    HB2_DISPATCH(cfg, return launch_sensor_t<Tr>(G, Qtab_dev, theta, Omega, st));
+    HB2_DISPATCH(cfg, return launch_sensor_t<Tr>(G, Qtab_dev, theta, Omega, hyb, st));
     return -1;
 }
 

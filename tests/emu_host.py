@@ -10,7 +10,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "host_emu", "libhb2_emu.so")
 _SRC = os.path.join(_HERE, "host_emu", "emu.cpp")
-_CORE = os.path.join(_HERE, "..", "hamers_b200", "csrc", "hb2_core.cuh")
+_CORE = [os.path.join(_HERE, "..", "hamers_b200", "csrc", f) for f in ("hb2_core.cuh", "hb2_fast.cuh", "hb2_sweep.cuh")]
 _LIB = None
 
 
@@ -24,7 +24,7 @@ def lib():
     global _LIB
     if _LIB is None:
         stale = (not os.path.exists(_SO)) or any(
-            os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_SO) for s in (_SRC, _CORE))
+            os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_SO) for s in [_SRC] + _CORE)
         if stale:
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
                                    "-Wno-unknown-pragmas", "-o", _SO, _SRC])

@@ -2,12 +2,12 @@
  * emu.cpp -- TEST-ONLY host emulation of the CUDA sweeps (never part of the product library).
  *
  * Compiles hamers_b200/csrc/hb2_core.cuh with g++ and drives the very same per-thread functions
- * the kernels call (march_pencil, xsweep_phase_*, sensor_cell) from plain loops that stand in
+ * the kernels call (pencil_ctx, phase_commit, phase_face, phase_update, sensor_cell, face_sensor) from plain loops that stand in
  * for the CUDA grid.  It exists because this container has no GPU: it lets the CPU test suite
  * check the kernels' indexing and arithmetic against the oracle before any GPU time is spent.
  * The GPU parity tests (pytest -m gpu) remain the parity tests proper.
  */
-#include "../../hamers_b200/csrc/hb2_core.cuh"
+#include "../../hamers_b200/csrc/hb2_sweep.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -35,21 +35,82 @@ static void make_geom(const EmuDesc* d, Geom* G)
     G->ncell_g = (long long)G->gd[0] * G->gd[1] * G->gd[2];
 }
 
+/* one direction: the loops below stand in for the CUDA grid, the barriers become loop boundaries */
+template <class Tr, int DIR, int MATH>
+static void run_dir(const DirArgs& A)
+{
+    using Sh = SweepShape<Tr, DIR>;
+    const Geom& G = A.G;
+    const int nseg = (G.n[DIR] + A.seg_len - 1) / A.seg_len;
+    int gx, gy;
+    if (DIR == 0) {
+        gx = (G.n[1] + Sh::P - 1) / Sh::P;
+        gy = (Tr::DIM == 3) ? G.n[2] : 1;
+    } else if (DIR == 1) {
+        gx = (G.n[0] + 31) / 32;
+        gy = (Tr::DIM == 3) ? G.n[2] : 1;
+    } else {
+        gx = (G.n[0] + 31) / 32;
+        gy = G.n[1];
+    }
+    std::vector<double> smem(Sh::SMEM_DOUBLES);
+    for (int bz = 0; bz < nseg; bz++)
+        for (int by = 0; by < gy; by++)
+            for (int bx = 0; bx < gx; bx++) {
+                const BlockId b = {bx, by, bz};
+                /* poison the rings: reading a slot that was never written must show up */
+                for (auto& v : smem) v = std::nan("");
+                PencilCtx c0 = pencil_ctx<Tr, DIR>(A, b, 0);
+                const int nsteps = Sh::nsteps(c0.c1 - c0.c0);
+                for (int t = 0; t < nsteps; t++) {
+                    for (int tid = 0; tid < Sh::NT; tid++) {
+                        const PencilCtx c = pencil_ctx<Tr, DIR>(A, b, tid);
+                        int s;
+                        if (load_wanted<Tr, DIR>(c, t, s)) {
+                            double q[Tr::NCOMP];
+                            load_cons<Tr>(A, c.base + (long long)s * c.st, q);
+                            phase_commit<Tr, DIR, MATH>(A, smem.data(), c, s, q);
+                        }
+                    }
+                    for (int tid = 0; tid < Sh::NT; tid++)
+                        phase_face<Tr, DIR, MATH>(A, smem.data(), pencil_ctx<Tr, DIR>(A, b, tid), t);
+                    for (int tid = 0; tid < Sh::NT; tid++)
+                        phase_update<Tr, DIR, MATH>(A, smem.data(), pencil_ctx<Tr, DIR>(A, b, tid), t);
+                }
+            }
+}
+
 template <class Tr, int MATH>
-static void run_sweeps(DirArgs A0, int bx, int seg_len, double* const* F_all, int mode)
+static void run_sweeps(DirArgs A0, int /*bx*/, int seg_len, double* const* F_all, int mode)
 {
     const Geom& G = A0.G;
-    /* sensor */
-    std::vector<double> theta(G.ncell_g, 0.0), Omega(G.ncell_g, 0.0);
-    const int k_lo = (Tr::DIM == 3) ? -2 : 0, k_hi = (Tr::DIM == 3) ? G.n[2] + 2 : 1;
-    for (int k = k_lo; k < k_hi; k++)
+    /* sensor: theta / Omega on cells -2..N+1, decisions on cells -1..N+1 */
+    std::vector<double> theta(G.ncell_g, std::nan("")), Omega(G.ncell_g, std::nan(""));
+    std::vector<unsigned char> hyb(G.ncell_g, 0);
+    const double hidx[3] = {0.5 / G.dx[0], 0.5 / G.dx[1], 0.5 / G.dx[2]};
+    const int k2 = (Tr::DIM == 3) ? 2 : 0;
+    for (int k = -k2; k < ((Tr::DIM == 3) ? G.n[2] + 2 : 1); k++)
         for (int j = -2; j < G.n[1] + 2; j++)
             for (int i = -2; i < G.n[0] + 2; i++) {
                 const long long x = cidx(G, i, j, k);
-                sensor_cell<Tr>(G, A0.Q, x, theta[x], Omega[x]);
+                if (MATH == 0)
+                    sensor_cell<Tr>(G, A0.Q, x, theta[x], Omega[x]);
+                else
+                    sensor_cell_fast<Tr>(G, A0.Q, x, hidx, theta[x], Omega[x]);
             }
-    A0.theta = theta.data();
-    A0.Omega = Omega.data();
+    const int k1 = (Tr::DIM == 3) ? 1 : 0;
+    for (int k = -k1; k < ((Tr::DIM == 3) ? G.n[2] + 2 : 1); k++)
+        for (int j = -1; j < G.n[1] + 2; j++)
+            for (int i = -1; i < G.n[0] + 2; i++) {
+                const long long x = cidx(G, i, j, k);
+                unsigned char f = 0;
+                for (int d = 0; d < Tr::DIM; d++) {
+                    const long long xl = x - G.cs[d];
+                    if (face_sensor(theta[xl], theta[x], Omega[xl], Omega[x])) f |= (unsigned char)(1u << d);
+                }
+                hyb[x] = f;
+            }
+    A0.hyb = hyb.data();
     A0.mode = mode;
 
     for (int dir = 0; dir < Tr::DIM; dir++) {
@@ -58,35 +119,12 @@ static void run_sweeps(DirArgs A0, int bx, int seg_len, double* const* F_all, in
             for (int e = 0; e < Tr::NEQ; e++) A.F[e] = F_all[dir * Tr::NEQ + e];
         if (dir != Tr::DIM - 1) A.ncoef = 0;
         A.seg_len = seg_len > 0 ? seg_len : G.n[dir];
-        if (dir == 0) {
-            const int BX = bx;
-            std::vector<double> smem(XSmem<Tr>::doubles(BX));
-            const long long run = (long long)G.n[1] * G.gd[0];
-            const long long tiles = (run + (BX - 3) - 1) / (BX - 3);
-            const int planes = (Tr::DIM == 3) ? G.n[2] : 1;
-            for (int k = 0; k < planes; k++)
-                for (long long tile = 0; tile < tiles; tile++) {
-                    XSmem<Tr> sm(smem.data(), BX);
-                    const long long pstart = cidx(G, -G.g[0], 0, k);
-                    const long long p0 = pstart - 1 + tile * (long long)(BX - 3);
-                    for (int idx = 0; idx < BX + 5; idx++) xsweep_phase_load<Tr, MATH>(A, sm, p0, idx);
-                    for (int t = 0; t < BX; t++) xsweep_phase_mid<Tr, MATH>(A, sm, p0, k, t);
-                    for (int t = 0; t < BX; t++) xsweep_phase_face<Tr, MATH>(A, sm, p0, k, t);
-                    for (int t = 0; t < BX; t++) xsweep_phase_cell<Tr, MATH>(A, sm, p0, k, t);
-                }
-        } else {
-            const int N = G.n[dir];
-            const int nseg = (N + A.seg_len - 1) / A.seg_len;
-            const int nt = (dir == 1) ? ((Tr::DIM == 3) ? G.n[2] : 1) : G.n[1];
-            for (int seg = 0; seg < nseg; seg++)
-                for (int t = 0; t < nt; t++)
-                    for (int i = 0; i < G.n[0]; i++) {
-                        if (dir == 1)
-                            march_pencil<Tr, 1, MATH>(A, i, t, seg);
-                        else
-                            march_pencil<Tr, (Tr::DIM == 3 ? 2 : 1), MATH>(A, i, t, seg);
-                    }
-        }
+        if (dir == 0)
+            run_dir<Tr, 0, MATH>(A);
+        else if (dir == 1)
+            run_dir<Tr, 1, MATH>(A);
+        else
+            run_dir<Tr, (Tr::DIM == 3 ? 2 : 1), MATH>(A);
     }
 }
 
