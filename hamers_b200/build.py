@@ -25,7 +25,7 @@ COMMON = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-I", 
 
 UNITS = [
     ("hb2_sweeps_exact.o", "hb2_sweeps.cu", ["-DHB2_MATH=0", "-fmad=false"]),
-    ("hb2_sweeps_fast.o", "hb2_sweeps.cu", ["-DHB2_MATH=1", "-fmad=true"]),
+    ("hb2_sweeps_fast.o", "hb2_sweeps.cu", ["-DHB2_MATH=1", "-fmad=true"] + os.environ.get("HB2_FAST_FLAGS", "").split()),
     ("hb2_abi.o", "hb2_abi.cu", ["-fmad=false"]),
 ]
 DEPS = ["hb2_core.cuh", "hb2_fast.cuh", "hb2_sweep.cuh", "hb2_ops.h", "hb2_sweeps.cu", "hb2_abi.cu", os.path.join(ROOT, "include", "hamers_b200.h")]

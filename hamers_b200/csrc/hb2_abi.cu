@@ -428,7 +428,8 @@ int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* out)
     p->cfg.model = d->flow_model;
     p->cfg.dim = d->dim;
     p->cfg.ns = d->num_species;
-    p->ops = (d->math == HB2_MATH_EXACT) ? ops_exact() : ops_fast();
+    /* the fast kernels are written for constant_p = 2 (the reference default); other exponents use the exact build */
+    p->ops = (d->math == HB2_MATH_EXACT || p->d.weno_p != 2) ? ops_exact() : ops_fast();
     p->ncell_i = (long long)p->G.n[0] * p->G.n[1] * p->G.n[2];
     for (int a = 0; a < 3; a++) {
         long long ee[3] = {p->G.n[0], p->G.n[1], p->G.n[2]};

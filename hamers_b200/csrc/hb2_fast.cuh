@@ -23,7 +23,17 @@
 #pragma once
 #include "hb2_core.cuh"
 
+/* Unroll factor of the characteristic-field loop of face_midpoint_fast.  Measured on B200 (256^3, x sweep): the rolled
+ * loop (1) costs ~115 M extra warp instructions for the field switch and register shuffles (783 M vs 667 M) and the
+ * warp schedulers sustain only ~0.57 instructions/clk here, so the fully unrolled loop is 14 % faster; its code
+ * (29 KB) still fits the 32 KB instruction cache. */
+#ifndef HB2_FIELD_UNROLL
+#define HB2_FIELD_UNROLL 8
+#endif
+
 namespace hb2 {
+
+constexpr int kFieldUnroll = HB2_FIELD_UNROLL;
 
 HB2_HD double rcp_fast(double x)
 {
@@ -110,58 +120,92 @@ HB2_HD void cons_to_prim_fast(const double (&q)[Tr::NCOMP], const Consts& K, dou
     }
 }
 
+/* node flux of a cell from its PRIMITIVE variables (cell[comp*CS]); E_stored: the stored total energy (five-eqn) */
+template <class Tr, int DIR, int CS>
+HB2_HD void node_flux_prim(const double* cell, double E_stored, const Consts& K, double (&Fn)[Tr::NEQ])
+{
+    constexpr int DIM = Tr::DIM, NS = Tr::NS, IV = Tr::IV, IP = Tr::IP;
+    double u[DIM];
+    double ke = 0.0;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) {
+        u[a] = cell[(IV + a) * CS];
+        ke = fma(u[a], u[a], ke);
+    }
+    const double p = cell[IP * CS];
+    const double un = u[DIR];
+    double rho, E;
+    if (Tr::MODEL == SS) {
+        rho = cell[0];
+        E = fma(0.5 * rho, ke, p * K.inv_gm1[0]);
+        Fn[0] = rho * un;
+    } else {
+        rho = 0.0;
+#pragma unroll
+        for (int si = 0; si < NS; si++) {
+            const double zr = cell[si * CS];
+            rho += zr;
+            Fn[si] = un * zr;
+        }
+        E = E_stored;
+#pragma unroll
+        for (int si = 0; si < NS - 1; si++) Fn[IP + 1 + si] = un * cell[(IP + 1 + si) * CS];
+    }
+    const double ru = rho * un;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) Fn[IV + a] = (a == DIR) ? fma(ru, u[a], p) : ru * u[a];
+    Fn[IP] = un * (E + p);
+}
+
 /* ------------------------------------------------------------------------------------------
  * WCNS5-JS: minus-side and plus-side midpoint values from the six stencil values w0..w5
  * ---------------------------------------------------------------------------------------- */
-HB2_HD void weno5js_pair_fast(double w0, double w1, double w2, double w3, double w4, double w5, int p, double& wm,
-                              double& wp)
+HB2_HD void weno5js_pair_fast(double w0, double w1, double w2, double w3, double w4, double w5, double eps4,
+                              double& wm, double& wp)
 {
-    const double eps4 = 4.0 * HB2_EPS;
+    /* eps4 = 4*eps*(scale of w)^2: the caller may hand in characteristic variables scaled by a constant (the
+     * normalised weights are invariant when beta and epsilon are scaled together) */
     /* second differences of the four 3-cell sub-stencils, shared by both sides */
-    const double s012 = (w0 + w2) - 2.0 * w1;
-    const double s123 = (w1 + w3) - 2.0 * w2;
-    const double s234 = (w2 + w4) - 2.0 * w3;
-    const double s345 = (w3 + w5) - 2.0 * w4;
+    const double s012 = fma(-2.0, w1, w0 + w2);
+    const double s123 = fma(-2.0, w2, w1 + w3);
+    const double s234 = fma(-2.0, w3, w2 + w4);
+    const double s345 = fma(-2.0, w4, w3 + w5);
     const double t012 = (13.0 / 3.0) * s012, t123 = (13.0 / 3.0) * s123, t234 = (13.0 / 3.0) * s234,
                  t345 = (13.0 / 3.0) * s345;
     /* minus side (cell 2 is the upwind cell): 4*beta_k = 13/3 s^2 + f^2 */
     const double f0 = fma(3.0, w2, fma(-4.0, w1, w0));
     const double f1 = w1 - w3;
     const double f2 = fma(3.0, w2, fma(-4.0, w3, w4));
-    double b0 = fma(t012, s012, f0 * f0) + eps4;
-    double b1 = fma(t123, s123, f1 * f1) + eps4;
-    double b2 = fma(t234, s234, f2 * f2) + eps4;
+    double b0 = fma(t012, s012, fma(f0, f0, eps4));
+    double b1 = fma(t123, s123, fma(f1, f1, eps4));
+    double b2 = fma(t234, s234, fma(f2, f2, eps4));
     /* plus side (cell 3 is the upwind cell), mirrored */
     const double g0 = fma(3.0, w3, fma(-4.0, w4, w5));
     const double g1 = w4 - w2;
     const double g2 = fma(3.0, w3, fma(-4.0, w2, w1));
-    double c0 = fma(t345, s345, g0 * g0) + eps4;
-    double c1 = fma(t234, s234, g1 * g1) + eps4;
-    double c2 = fma(t123, s123, g2 * g2) + eps4;
-    if (p == 2) {
-        b0 *= b0; b1 *= b1; b2 *= b2;
-        c0 *= c0; c1 *= c1; c2 *= c2;
-    } else {
-        b0 = ipow_(b0, p); b1 = ipow_(b1, p); b2 = ipow_(b2, p);
-        c0 = ipow_(c0, p); c1 = ipow_(c1, p); c2 = ipow_(c2, p);
-    }
-    /* un-normalised weights (x16): a0 = b1 b2, a1 = 10 b0 b2, a2 = 5 b0 b1; sub-stencil values with the linear-weight
-     * ratios folded in */
+    double c0 = fma(t345, s345, fma(g0, g0, eps4));
+    double c1 = fma(t234, s234, fma(g1, g1, eps4));
+    double c2 = fma(t123, s123, fma(g2, g2, eps4));
+    /* constant_p = 2 (the reference's default, ConvectiveFluxReconstructorWCNS5-JS-HLLC-HLL.cpp:188-191); plans with
+     * another exponent run the exact-arithmetic kernels */
+    b0 *= b0; b1 *= b1; b2 *= b2;
+    c0 *= c0; c1 *= c1; c2 *= c2;
+    /* un-normalised weights (x16): a0 = b1 b2, 10 a1 = 10 b0 b2, 5 a2 = 5 b0 b1;
+     * value = P1 + (a0 (P0 - P1) + 5 a2 (P2 - P1))/sum, and the sub-stencil differences are third differences:
+     * P0 - P1 = 3/8 (s012 - s123), P2 - P1 = 1/8 (s123 - s234) (mirrored on the plus side) */
     {
         const double a0 = b1 * b2, a1 = b0 * b2, a2 = b0 * b1;
         const double sum = fma(5.0, a2, fma(10.0, a1, a0));
-        const double P0 = fma(1.875, w2, fma(-1.25, w1, 0.375 * w0));
-        const double P1 = fma(3.75, w3, fma(7.5, w2, -1.25 * w1));   /* 10 * (-1/8 w1 + 6/8 w2 + 3/8 w3) */
-        const double P2 = fma(-0.625, w4, fma(3.75, w3, 1.875 * w2)); /* 5 * (3/8 w2 + 6/8 w3 - 1/8 w4) */
-        wm = fma(a2, P2, fma(a1, P1, a0 * P0)) * rcp_fast(sum);
+        const double P1 = fma(0.375, w3, fma(0.75, w2, -0.125 * w1));
+        const double u0 = a0 * (s012 - s123), u2 = a2 * (s123 - s234);
+        wm = fma(fma(0.625, u2, 0.375 * u0), rcp_fast(sum), P1);
     }
     {
         const double a0 = c1 * c2, a1 = c0 * c2, a2 = c0 * c1;
         const double sum = fma(5.0, a2, fma(10.0, a1, a0));
-        const double P0 = fma(1.875, w3, fma(-1.25, w4, 0.375 * w5));
-        const double P1 = fma(3.75, w2, fma(7.5, w3, -1.25 * w4));
-        const double P2 = fma(-0.625, w1, fma(3.75, w2, 1.875 * w3));
-        wp = fma(a2, P2, fma(a1, P1, a0 * P0)) * rcp_fast(sum);
+        const double P1 = fma(0.375, w2, fma(0.75, w3, -0.125 * w4));
+        const double u0 = a0 * (s345 - s234), u2 = a2 * (s234 - s123);
+        wp = fma(fma(0.625, u2, 0.375 * u0), rcp_fast(sum), P1);
     }
 }
 
@@ -313,66 +357,69 @@ HB2_HD void riemann_fast(const double (&V_L)[Tr::NEQ], const double (&V_R)[Tr::N
 
 /* ------------------------------------------------------------------------------------------
  * One midpoint flux, stencil read from shared memory.
- *   sV  : primitive variables + sound speed, component-major: sV[comp*CS + so[m]] is component `comp` of
- *         stencil cell m (m = 0..5 <-> cells f-3..f+2); comp NEQ is the sound speed.
- * The characteristic fields are processed by a loop that is NOT unrolled, so that the WCNS5-JS body exists once
- * in the instruction stream (the hot loop stays inside the instruction cache).
+ *   win : points at component 0 of stencil cell 0 (cell f-3); component `comp` of stencil cell m is
+ *         win[comp*CS + m*MS] (CS, MS compile-time: the loads become LDS [base + uniform + immediate]);
+ *         component NEQ is the sound speed.
+ * The characteristic fields are processed by one loop (unrolled by kFieldUnroll) whose body is the same for every
+ * field: w = X + b*Y on the six stencil cells, WCNS5-JS pair, accumulate into the primitive variables.
  * ---------------------------------------------------------------------------------------- */
-template <class Tr, int DIR>
-HB2_HD void face_midpoint_fast(const double* sV, int CS, const int (&so)[6], bool hybrid, const Consts& K,
-                               double (&Fm)[Tr::NEQ], double& vel_mid)
+template <class Tr, int DIR, int CS, int MS>
+HB2_HD void face_midpoint_fast(const double* win, bool hybrid, const Consts& K, double (&Fm)[Tr::NEQ], double& vel_mid)
 {
     constexpr int DIM = Tr::DIM, NS = Tr::NS, NEQ = Tr::NEQ, IV = Tr::IV, IP = Tr::IP;
     static_assert(NS <= 2, "fast path is written for at most two species");
-    const int p = K.weno_p;
+    const double eps4 = 4.0 * HB2_EPS;
     /* tangential velocity components in index order */
     constexpr int T0 = (DIR == 0) ? 1 : 0;
     constexpr int T1 = (DIR == 2) ? 1 : 2;
 
     double V_minus[NEQ], V_plus[NEQ];
-    const double c_avg = 0.5 * (sV[NEQ * CS + so[2]] + sV[NEQ * CS + so[3]]);
+    const double c_avg = 0.5 * (win[NEQ * CS + 2 * MS] + win[NEQ * CS + 3 * MS]);
 
     if (Tr::MODEL == SS) {
-        const double rho_avg = 0.5 * (sV[so[2]] + sV[so[3]]);
-        const double kp = 0.5 * rho_avg * c_avg;
-        const double r_rcc = rcp_fast(rho_avg * c_avg * c_avg);
-        const double r_cc = r_rcc * rho_avg; /* 1/c^2 */
-        const double r_rc = r_rcc * c_avg;   /* 1/(rho c) */
+        /* characteristic variables scaled by 2 where that saves a multiplication:
+         *   W0' = p - rho c u_n, W1 = rho - p/c^2, tangential velocities, W4' = p + rho c u_n  (W0 = W0'/2, W4 = W4'/2) */
+        const double rho_avg = 0.5 * (win[2 * MS] + win[3 * MS]);
+        const double rc = rho_avg * c_avg;
+        const double r_rcc = rcp_fast(rc * c_avg);
+        const double r_cc = r_rcc * rho_avg;      /* 1/c^2 */
+        const double h_cc = 0.5 * r_cc;
+        const double h_rc = 0.5 * r_rcc * c_avg;  /* 1/(2 rho c) */
         double rm = 0.0, rp = 0.0, um = 0.0, up = 0.0, pm = 0.0, pp = 0.0, t0m = 0.0, t0p = 0.0, t1m = 0.0, t1p = 0.0;
-#pragma unroll 1
+#pragma unroll kFieldUnroll
         for (int f = 0; f < NEQ; f++) {
-            int xc;
-            double a = 1.0, b = 0.0;
+            int xc, yc = 1 + DIR;
+            double b = 0.0, e4 = eps4;
             if (f == 0) {
-                xc = 1 + DIR; a = -kp; b = 0.5;
+                xc = IP; b = -rc; e4 = 4.0 * eps4;
             } else if (f == 1) {
-                xc = 0; b = -r_cc;
+                xc = 0; yc = IP; b = -r_cc;
             } else if (f == NEQ - 1) {
-                xc = 1 + DIR; a = kp; b = 0.5;
+                xc = IP; b = rc; e4 = 4.0 * eps4;
             } else {
                 xc = 1 + ((f == 2) ? T0 : T1);
             }
-            const double* X = sV + xc * CS;
+            const double* X = win + xc * CS;
             double w[6];
 #pragma unroll
-            for (int m = 0; m < 6; m++) w[m] = X[so[m]];
+            for (int m = 0; m < 6; m++) w[m] = X[m * MS];
             if (b != 0.0) {
-                const double* Y = sV + IP * CS;
+                const double* Y = win + yc * CS;
 #pragma unroll
-                for (int m = 0; m < 6; m++) w[m] = fma(a, w[m], b * Y[so[m]]);
+                for (int m = 0; m < 6; m++) w[m] = fma(b, Y[m * MS], w[m]);
             }
             double wm, wp;
-            weno5js_pair_fast(w[0], w[1], w[2], w[3], w[4], w[5], p, wm, wp);
+            weno5js_pair_fast(w[0], w[1], w[2], w[3], w[4], w[5], e4, wm, wp);
             if (f == 0) {
-                rm = r_cc * wm; rp = r_cc * wp;
-                um = -r_rc * wm; up = -r_rc * wp;
-                pm = wm; pp = wp;
+                rm = h_cc * wm; rp = h_cc * wp;
+                um = -h_rc * wm; up = -h_rc * wp;
+                pm = 0.5 * wm; pp = 0.5 * wp;
             } else if (f == 1) {
                 rm += wm; rp += wp;
             } else if (f == NEQ - 1) {
-                rm = fma(r_cc, wm, rm); rp = fma(r_cc, wp, rp);
-                um = fma(r_rc, wm, um); up = fma(r_rc, wp, up);
-                pm += wm; pp += wp;
+                rm = fma(h_cc, wm, rm); rp = fma(h_cc, wp, rp);
+                um = fma(h_rc, wm, um); up = fma(h_rc, wp, up);
+                pm = fma(0.5, wm, pm); pp = fma(0.5, wp, pp);
             } else if (f == 2) {
                 t0m = wm; t0p = wp;
             } else {
@@ -391,7 +438,7 @@ HB2_HD void face_midpoint_fast(const double* sV, int CS, const int (&so)[6], boo
         double rho_avg = 0.0;
 #pragma unroll
         for (int si = 0; si < NS; si++) {
-            Zr_avg[si] = 0.5 * (sV[si * CS + so[2]] + sV[si * CS + so[3]]);
+            Zr_avg[si] = 0.5 * (win[si * CS + 2 * MS] + win[si * CS + 3 * MS]);
             rho_avg += Zr_avg[si];
         }
         const double rc = rho_avg * c_avg;
@@ -404,7 +451,7 @@ HB2_HD void face_midpoint_fast(const double* sV, int CS, const int (&so)[6], boo
         double t0m = 0.0, t0p = 0.0, t1m = 0.0, t1p = 0.0, zzm = 0.0, zzp = 0.0;
         /* field order of the reference: u_n - p/(rho c) | Z_i rho_i - .. p (NS) | tangential (DIM-1) | Z_i (NS-1) | u_n + p/(rho c) */
         constexpr int F_T = 1 + NS, F_Z = F_T + (DIM - 1);
-#pragma unroll 1
+#pragma unroll kFieldUnroll
         for (int f = 0; f < NEQ; f++) {
             int xc;
             double b = 0.0;
@@ -419,17 +466,17 @@ HB2_HD void face_midpoint_fast(const double* sV, int CS, const int (&so)[6], boo
             } else {
                 xc = IV + DIR; b = r_rc;
             }
-            const double* X = sV + xc * CS;
+            const double* X = win + xc * CS;
             double w[6];
 #pragma unroll
-            for (int m = 0; m < 6; m++) w[m] = X[so[m]];
+            for (int m = 0; m < 6; m++) w[m] = X[m * MS];
             if (b != 0.0) {
-                const double* Y = sV + IP * CS;
+                const double* Y = win + IP * CS;
 #pragma unroll
-                for (int m = 0; m < 6; m++) w[m] = fma(b, Y[so[m]], w[m]);
+                for (int m = 0; m < 6; m++) w[m] = fma(b, Y[m * MS], w[m]);
             }
             double wm, wp;
-            weno5js_pair_fast(w[0], w[1], w[2], w[3], w[4], w[5], p, wm, wp);
+            weno5js_pair_fast(w[0], w[1], w[2], w[3], w[4], w[5], eps4, wm, wp);
             if (f == 0) {
                 z0m = -yh0 * wm; z0p = -yh0 * wp;
                 z1m = -yh1 * wm; z1p = -yh1 * wp;
@@ -470,8 +517,8 @@ HB2_HD void face_midpoint_fast(const double* sV, int CS, const int (&so)[6], boo
     if (!ok) {
 #pragma unroll
         for (int e = 0; e < NEQ; e++) {
-            V_minus[e] = sV[e * CS + so[2]];
-            V_plus[e] = sV[e * CS + so[3]];
+            V_minus[e] = win[e * CS + 2 * MS];
+            V_plus[e] = win[e * CS + 3 * MS];
         }
     }
     riemann_fast<Tr, DIR>(V_minus, V_plus, K, hybrid, Fm, vel_mid);

@@ -5,19 +5,22 @@
  * P*C = 256 threads, one thread per (pencil, position in the chunk):
  *     y / z sweep : P = 32 pencils = 32 consecutive x (lanes -> 256-byte coalesced rows), C = 8 (one row per warp)
  *     x sweep     : P = 8 pencils = 8 consecutive y rows (one per warp), C = 32 consecutive x (lanes)
- * Per step t the block runs three phases separated by barriers; all hand-over goes through shared-memory RINGS
- * indexed by the position along the sweep axis (slot = position mod RING):
- *     L(t)  load    cells  c0-4+tC+o  : conservative -> primitive variables, sound speed, node flux   -> sV, sN
+ * The work of a pencil is a three-stage software pipeline whose hand-over goes through shared-memory RINGS indexed
+ * by the position along the sweep axis (slot = position mod RING):
+ *     L(t)  load    cells  c0-4+tC+o  : conservative -> primitive variables, sound speed              -> sV (, sN)
  *     F(t)  face    faces  c0-6+tC+o  : characteristic projection, WCNS5-JS, bounds check, HLLC/HLLC-HLL -> sM
  *     U(t)  update  cells  c0-8+tC+o  : 6th-order midpoint-and-node flux difference, advective source, then either
  *                                       the side flux (EMIT) or the running right-hand side / fused RK update (FUSED)
  * so every cell is converted once and every midpoint flux is computed once per sweep (the reference writes ~70
  * patch-sized temporaries instead), and nothing but the final result leaves the SM.
- * Global loads of step t+1 are issued before phase F(t) and committed to the ring after it (latency hidden
- * behind the FP64-bound phase).
+ * Iteration t of a block executes  L(t+1) ; F(t) ; U(t-1)  in every thread and ends with ONE barrier: the rings are
+ * long enough (3C+5 cells, 2C+3 faces) that nothing written in an iteration is read by another thread before the
+ * barrier.  The global loads of L(t+2) and of U(t-1) are issued before F(t), so their latency hides behind the
+ * FP64-bound face phase, and every phase keeps the FP64 pipe busy (no load-only or store-only phases).
  *
  * The phase bodies are `__host__ __device__` functions of (block coordinates, thread id): the CUDA kernel calls them
- * with barriers in between, tests/host_emu calls them from loops.
+ * with the barrier in between, tests/host_emu calls them from loops (in forward and in reverse thread order, to
+ * expose any intra-iteration hazard).
  *
  * Reference behaviour: ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:1378-2655 (3D), :546-1376 (2D);
  * Euler.cpp:1424-1655 (RK update).
@@ -27,19 +30,35 @@
 
 namespace hb2 {
 
-template <class Tr, int DIR>
+template <class Tr, int DIR, int MATH>
 struct SweepShape {
     static constexpr int NT = 256;
     static constexpr int NW = NT / 32;
-    static constexpr int P = (DIR == 0) ? NW : 32;    /* pencils per block */
-    static constexpr int C = (DIR == 0) ? 32 : NW;    /* cells per chunk along the sweep axis */
-    static constexpr int RING = (DIR == 0) ? 64 : 16; /* ring slots along the sweep axis (>= C + 5, power of two) */
-    static constexpr int CS = RING * P;               /* doubles per ring component */
-    static constexpr int NV = Tr::NEQ + 1;            /* primitive variables + sound speed */
-    static constexpr int NN = Tr::NEQ;                /* node flux */
+    static constexpr int P = (DIR == 0) ? NW : 32;     /* pencils per block */
+    static constexpr int C = (DIR == 0) ? 32 : NW;     /* cells per chunk along the sweep axis */
+    /* ring slots along the sweep axis: one iteration touches 3C+5 consecutive cells and 2C+3 consecutive faces */
+    static constexpr int RING = (DIR == 0) ? 128 : 32;
+    static constexpr int CS = RING * P;                /* doubles per ring component (midpoint flux, node flux) */
+    /* The primitive-variable ring is MIRRORED: its first DUP slots are stored a second time behind the last slot, so
+     * that the six stencil cells of a face are always at base + m*MS (no wrap inside a stencil window). */
+    static constexpr int DUP = (DIR == 0) ? 8 : 5;
+    static constexpr int RINGV = RING + DUP;
+    static constexpr int CSV = RINGV * P;              /* doubles per component of the primitive-variable ring */
+    static constexpr int MS = (DIR == 0) ? 1 : 32;     /* stride between consecutive cells of a pencil */
+    /* primitive variables + sound speed (+ total energy for the five-eqn model, whose node flux needs the stored one) */
+    static constexpr int IC = Tr::NEQ;                 /* sound speed */
+    static constexpr int IE = Tr::NEQ + 1;             /* total energy (five-eqn only) */
+    static constexpr int NV = Tr::NEQ + 1 + ((MATH == 1 && Tr::MODEL == FE) ? 1 : 0);
+    /* exact arithmetic keeps the node flux of the conservative variables (bit-identical to the reference); the fast
+     * variant re-evaluates it from the primitive ring in the update phase and saves the ring */
+    static constexpr int NN = (MATH == 0) ? Tr::NEQ : 0;
     static constexpr int NMID = Tr::NEQ + (Tr::ADV ? 1 : 0); /* midpoint flux (+ HLLC midpoint velocity) */
-    static constexpr int SMEM_DOUBLES = (NV + NN + NMID) * CS;
+    static constexpr int OFF_N = NV * CSV;
+    static constexpr int OFF_M = OFF_N + NN * CS;
+    static constexpr int SMEM_DOUBLES = OFF_M + NMID * CS;
     HB2_HD static int slot(int pp, int s) { return (DIR == 0) ? pp * RING + (s & (RING - 1)) : (s & (RING - 1)) * 32 + pp; }
+    /* primitive-variable ring: r = ring position in [0, RINGV) */
+    HB2_HD static int slotv(int pp, int r) { return (DIR == 0) ? pp * RINGV + r : r * 32 + pp; }
     HB2_HD static int nsteps(int ncells) { return (ncells + 8 + C - 1) / C; }
 };
 
@@ -58,10 +77,10 @@ struct PencilCtx {
     long long st;    /* ghost-box stride along the sweep axis */
 };
 
-template <class Tr, int DIR>
+template <class Tr, int DIR, int MATH>
 HB2_HD PencilCtx pencil_ctx(const DirArgs& A, const BlockId& b, int tid)
 {
-    using Sh = SweepShape<Tr, DIR>;
+    using Sh = SweepShape<Tr, DIR, MATH>;
     const Geom& G = A.G;
     PencilCtx c;
     const int lane = tid & 31, w = tid >> 5;
@@ -89,11 +108,11 @@ HB2_HD PencilCtx pencil_ctx(const DirArgs& A, const BlockId& b, int tid)
     return c;
 }
 
-/* ---- phase L: load ---------------------------------------------------------------------- */
-template <class Tr, int DIR>
+/* ---- load / commit: chunk t = cells c0-4+tC+o ------------------------------------------------- */
+template <class Tr, int DIR, int MATH>
 HB2_HD bool load_wanted(const PencilCtx& c, int t, int& s)
 {
-    using Sh = SweepShape<Tr, DIR>;
+    using Sh = SweepShape<Tr, DIR, MATH>;
     s = c.c0 - 4 + t * Sh::C + c.o;
     return c.valid && s <= c.c1 + 3;
 }
@@ -101,49 +120,58 @@ HB2_HD bool load_wanted(const PencilCtx& c, int t, int& s)
 template <class Tr, int DIR, int MATH>
 HB2_HD void phase_commit(const DirArgs& A, double* smem, const PencilCtx& c, int s, const double (&q)[Tr::NCOMP])
 {
-    using Sh = SweepShape<Tr, DIR>;
+    using Sh = SweepShape<Tr, DIR, MATH>;
     constexpr int NEQ = Tr::NEQ;
-    double V[NEQ], cs, Fn[NEQ];
+    double V[NEQ], cs;
     if (MATH == 0)
         cons_to_prim<Tr>(q, A.K, V, cs);
     else
         cons_to_prim_fast<Tr>(q, A.K, V, cs);
-    node_flux<Tr, DIR>(q, V, Fn);
     double* sV = smem;
-    double* sN = smem + Sh::NV * Sh::CS;
-    const int sl = Sh::slot(c.pp, s);
+    const int r = s & (Sh::RING - 1);
+    const int sv = Sh::slotv(c.pp, r);
 #pragma unroll
-    for (int e = 0; e < NEQ; e++) {
-        sV[e * Sh::CS + sl] = V[e];
-        sN[e * Sh::CS + sl] = Fn[e];
+    for (int e = 0; e < NEQ; e++) sV[e * Sh::CSV + sv] = V[e];
+    sV[Sh::IC * Sh::CSV + sv] = cs;
+    if (Sh::NV > NEQ + 1) sV[Sh::IE * Sh::CSV + sv] = q[Tr::IP];
+    if (r < Sh::DUP) {
+        const int sv2 = Sh::slotv(c.pp, r + Sh::RING);
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) sV[e * Sh::CSV + sv2] = V[e];
+        sV[Sh::IC * Sh::CSV + sv2] = cs;
     }
-    sV[NEQ * Sh::CS + sl] = cs;
+    if (MATH == 0) {
+        double Fn[NEQ];
+        node_flux<Tr, DIR>(q, V, Fn);
+        double* sN = smem + Sh::OFF_N;
+        const int sl = Sh::slot(c.pp, s);
+#pragma unroll
+        for (int e = 0; e < NEQ; e++) sN[e * Sh::CS + sl] = Fn[e];
+    }
 }
 
-/* ---- phase F: midpoint flux --------------------------------------------------------------- */
+/* ---- face phase: midpoint fluxes of faces c0-6+tC+o --------------------------------------------- */
 template <class Tr, int DIR, int MATH>
 HB2_HD void phase_face(const DirArgs& A, double* smem, const PencilCtx& c, int t)
 {
-    using Sh = SweepShape<Tr, DIR>;
+    using Sh = SweepShape<Tr, DIR, MATH>;
     constexpr int NEQ = Tr::NEQ;
     const int f = c.c0 - 6 + t * Sh::C + c.o;
     if (!c.valid || f < c.c0 - 1 || f > c.c1 + 1) return;
     const bool hybrid = (A.hyb[c.base + (long long)f * c.st] >> DIR) & 1;
-    const double* sV = smem;
-    double* sM = smem + (Sh::NV + Sh::NN) * Sh::CS;
-    int so[6];
-#pragma unroll
-    for (int m = 0; m < 6; m++) so[m] = Sh::slot(c.pp, f - 3 + m);
+    double* sM = smem + Sh::OFF_M;
+    /* stencil window: cells f-3..f+2 at win[comp*CSV + m*MS] */
+    const double* win = smem + Sh::slotv(c.pp, (f - 3) & (Sh::RING - 1));
     double Fm[NEQ], um;
     if (MATH == 0) {
         double V[6][NEQ];
 #pragma unroll
         for (int m = 0; m < 6; m++)
 #pragma unroll
-            for (int e = 0; e < NEQ; e++) V[m][e] = sV[e * Sh::CS + so[m]];
-        face_midpoint<Tr, DIR, 0>(V, sV[NEQ * Sh::CS + so[2]], sV[NEQ * Sh::CS + so[3]], hybrid, A.K, Fm, um);
+            for (int e = 0; e < NEQ; e++) V[m][e] = win[e * Sh::CSV + m * Sh::MS];
+        face_midpoint<Tr, DIR, 0>(V, win[Sh::IC * Sh::CSV + 2 * Sh::MS], win[Sh::IC * Sh::CSV + 3 * Sh::MS], hybrid, A.K, Fm, um);
     } else {
-        face_midpoint_fast<Tr, DIR>(sV, Sh::CS, so, hybrid, A.K, Fm, um);
+        face_midpoint_fast<Tr, DIR, Sh::CSV, Sh::MS>(win, hybrid, A.K, Fm, um);
     }
     const int sl = Sh::slot(c.pp, f);
 #pragma unroll
@@ -151,21 +179,53 @@ HB2_HD void phase_face(const DirArgs& A, double* smem, const PencilCtx& c, int t
     if (Tr::ADV) sM[NEQ * Sh::CS + sl] = um;
 }
 
-/* ---- phase U: flux difference, source, output ------------------------------------------------ */
+/* ---- update phase: cells c0-8+tC+o ---------------------------------------------------------------- */
+template <class Tr>
+struct UpdateIn {          /* global inputs of the update phase, fetched before the face phase of the same iteration */
+    double R[Tr::NEQ];     /* running right-hand side of the previous directions (FUSED, DIR > 0) */
+    double T;              /* running velocity-divergence sum (five-eqn, DIR > 0) */
+};
+
 template <class Tr, int DIR, int MATH>
-HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& c, int t)
+HB2_HD bool update_wanted(const PencilCtx& c, int t, int& cc)
 {
-    using Sh = SweepShape<Tr, DIR>;
+    using Sh = SweepShape<Tr, DIR, MATH>;
+    cc = c.c0 - 8 + t * Sh::C + c.o;
+    return t >= 0 && c.valid && cc >= c.c0 && cc < c.c1;
+}
+
+template <class Tr, int DIR>
+HB2_HD long long update_index(const DirArgs& A, const PencilCtx& c, int cc)
+{
+    const int ci = (DIR == 0) ? cc : c.i, cj = (DIR == 1) ? cc : c.j, ck = (DIR == 2) ? cc : c.k;
+    return iidx(A.G, ci, cj, ck);
+}
+
+template <class Tr, int DIR>
+HB2_HD void update_fetch(const DirArgs& A, const PencilCtx& c, int cc, UpdateIn<Tr>& in)
+{
+    const long long ix = update_index<Tr, DIR>(A, c, cc);
+    if (DIR > 0 && A.mode == MODE_FUSED) {
+#pragma unroll
+        for (int e = 0; e < Tr::NEQ; e++) in.R[e] = A.R[e][ix];
+    }
+    in.T = (Tr::ADV && DIR > 0) ? A.T[ix] : 0.0;
+}
+
+template <class Tr, int DIR, int MATH>
+HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& c, int cc, const UpdateIn<Tr>& in)
+{
+    using Sh = SweepShape<Tr, DIR, MATH>;
     constexpr int DIM = Tr::DIM, NEQ = Tr::NEQ, NS = Tr::NS, IV = Tr::IV, IP = Tr::IP;
     constexpr bool LAST = (DIR == DIM - 1);
-    const int cc = c.c0 - 8 + t * Sh::C + c.o;
-    if (!c.valid || cc < c.c0 || cc >= c.c1) return;
     const Geom& G = A.G;
     const double* sV = smem;
-    const double* sN = smem + Sh::NV * Sh::CS;
-    const double* sM = smem + (Sh::NV + Sh::NN) * Sh::CS;
+    const double* sM = smem + Sh::OFF_M;
     const int m_m1 = Sh::slot(c.pp, cc - 1), m_0 = Sh::slot(c.pp, cc), m_p1 = Sh::slot(c.pp, cc + 1),
               m_p2 = Sh::slot(c.pp, cc + 2);
+    /* the same cells in the primitive-variable ring (primary copies) */
+    const int v_m1 = Sh::slotv(c.pp, (cc - 1) & (Sh::RING - 1)), v_0 = Sh::slotv(c.pp, cc & (Sh::RING - 1)),
+              v_p1 = Sh::slotv(c.pp, (cc + 1) & (Sh::RING - 1));
     const bool fused = (A.mode == MODE_FUSED);
     const double dxd = G.dx[DIR];
     const int ci = (DIR == 0) ? cc : c.i, cj = (DIR == 1) ? cc : c.j, ck = (DIR == 2) ? cc : c.k;
@@ -175,26 +235,44 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
     double Tsum = 0.0;
     if (Tr::ADV) {
         const double* um = sM + NEQ * Sh::CS;
-        const double* un = sV + (IV + DIR) * Sh::CS;
-        const double Td = (3.0 / 2.0 * (um[m_p1] - um[m_0]) - 3.0 / 10.0 * (un[m_p1] - un[m_m1]) +
+        const double* un = sV + (IV + DIR) * Sh::CSV;
+        const double Td = (3.0 / 2.0 * (um[m_p1] - um[m_0]) - 3.0 / 10.0 * (un[v_p1] - un[v_m1]) +
                            1.0 / 30.0 * (um[m_p2] - um[m_m1])) / dxd;
-        Tsum = (DIR == 0) ? Td : A.T[ix] + Td;
+        Tsum = (DIR == 0) ? Td : in.T + Td;
         if (!LAST) A.T[ix] = Tsum;
     }
 
     double rhs[NEQ];
-    if (MATH == 1 && fused) {
-        /* difference form: F[c+1] - F[c] = dt (3/2 (M[c+1]-M[c]) + 1/30 (M[c+2]-M[c-1]) - 3/10 (N[c+1]-N[c-1])) */
-        const double k0 = A.dt / dxd;
-        const double k1 = 1.5 * k0, k2 = (1.0 / 30.0) * k0, k3 = (3.0 / 10.0) * k0;
+    if (MATH == 1) {
+        /* node fluxes from the primitive ring */
+        double Np[NEQ], Nm[NEQ];
+        node_flux_prim<Tr, DIR, Sh::CSV>(sV + v_p1, sV[(Sh::NV - 1) * Sh::CSV + v_p1], A.K, Np);
+        node_flux_prim<Tr, DIR, Sh::CSV>(sV + v_m1, sV[(Sh::NV - 1) * Sh::CSV + v_m1], A.K, Nm);
+        if (fused) {
+            /* difference form: F[c+1] - F[c] = dt (3/2 (M[c+1]-M[c]) + 1/30 (M[c+2]-M[c-1]) - 3/10 (N[c+1]-N[c-1])) */
+            const double k0 = A.dt / dxd;
+            const double k1 = 1.5 * k0, k2 = (1.0 / 30.0) * k0, k3 = (3.0 / 10.0) * k0;
 #pragma unroll
-        for (int e = 0; e < NEQ; e++) {
-            const double* M = sM + e * Sh::CS;
-            const double* Nf = sN + e * Sh::CS;
-            const double r0 = (DIR == 0) ? 0.0 : A.R[e][ix];
-            rhs[e] = fma(k3, Nf[m_p1] - Nf[m_m1], fma(-k2, M[m_p2] - M[m_m1], fma(-k1, M[m_p1] - M[m_0], r0)));
+            for (int e = 0; e < NEQ; e++) {
+                const double* M = sM + e * Sh::CS;
+                const double r0 = (DIR == 0) ? 0.0 : in.R[e];
+                rhs[e] = fma(k3, Np[e] - Nm[e], fma(-k2, M[m_p2] - M[m_m1], fma(-k1, M[m_p1] - M[m_0], r0)));
+            }
+        } else {
+            double N0[NEQ];
+            node_flux_prim<Tr, DIR, Sh::CSV>(sV + v_0, sV[(Sh::NV - 1) * Sh::CSV + v_0], A.K, N0);
+#pragma unroll
+            for (int e = 0; e < NEQ; e++) {
+                const double* M = sM + e * Sh::CS;
+                A.F[e][sidx<DIR>(G, ci, cj, ck)] =
+                    A.dt * (1.0 / 30.0 * (M[m_p1] + M[m_m1]) - 3.0 / 10.0 * (N0[e] + Nm[e]) + 23.0 / 15.0 * M[m_0]);
+                if (cc + 1 == G.n[DIR])
+                    A.F[e][sidx<DIR>(G, ci + (DIR == 0), cj + (DIR == 1), ck + (DIR == 2))] =
+                        A.dt * (1.0 / 30.0 * (M[m_p2] + M[m_0]) - 3.0 / 10.0 * (Np[e] + N0[e]) + 23.0 / 15.0 * M[m_p1]);
+            }
         }
     } else {
+        const double* sN = smem + Sh::OFF_N;
 #pragma unroll
         for (int e = 0; e < NEQ; e++) {
             const double* M = sM + e * Sh::CS;
@@ -207,7 +285,7 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
                     A.F[e][sidx<DIR>(G, ci + (DIR == 0), cj + (DIR == 1), ck + (DIR == 2))] = F_hi;
             } else {
                 const double dF = (F_hi - F_lo) / dxd;
-                rhs[e] = (DIR == 0) ? -dF : A.R[e][ix] - dF;
+                rhs[e] = (DIR == 0) ? -dF : in.R[e] - dF;
             }
         }
     }
@@ -218,7 +296,7 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
 #pragma unroll
                 for (int si = 0; si < NS - 1; si++) {
                     const int e = IP + 1 + si;
-                    rhs[e] = rhs[e] + A.dt * sV[e * Sh::CS + m_0] * Tsum;
+                    rhs[e] = rhs[e] + A.dt * sV[e * Sh::CSV + v_0] * Tsum;
                 }
             }
             rk_update_cell<Tr>(A, c.base + (long long)cc * c.st, rhs);
@@ -230,9 +308,46 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
 #pragma unroll
         for (int si = 0; si < NS - 1; si++) {
             const int e = IP + 1 + si;
-            A.S[e][ix] += A.dt * sV[e * Sh::CS + m_0] * Tsum;
+            A.S[e][ix] += A.dt * sV[e * Sh::CSV + v_0] * Tsum;
         }
     }
+}
+
+/* ---- one iteration of the marching pipeline (no barrier inside) -------------------------------------
+ * iteration t, t = 0..nsteps:  commit chunk t+1 (loaded during iteration t-1), fetch chunk t+2 and the update inputs,
+ * face phase t, update phase t-1.  Everything an iteration reads from the rings was written in EARLIER iterations,
+ * and nothing it writes is read by another thread in the same iteration, so ONE barrier per iteration suffices. */
+template <class Tr>
+struct PipeRegs {
+    double q[Tr::NCOMP];
+    int s;
+    bool have;
+};
+
+template <class Tr, int DIR, int MATH>
+HB2_HD void pipeline_prologue(const DirArgs& A, double* smem, const PencilCtx& c, PipeRegs<Tr>& pr)
+{
+    int s;
+    if (load_wanted<Tr, DIR, MATH>(c, 0, s)) {
+        load_cons<Tr>(A, c.base + (long long)s * c.st, pr.q);
+        phase_commit<Tr, DIR, MATH>(A, smem, c, s, pr.q);
+    }
+    pr.have = load_wanted<Tr, DIR, MATH>(c, 1, pr.s);
+    if (pr.have) load_cons<Tr>(A, c.base + (long long)pr.s * c.st, pr.q);
+}
+
+template <class Tr, int DIR, int MATH>
+HB2_HD void pipeline_iteration(const DirArgs& A, double* smem, const PencilCtx& c, int t, int nsteps, PipeRegs<Tr>& pr)
+{
+    if (pr.have) phase_commit<Tr, DIR, MATH>(A, smem, c, pr.s, pr.q);
+    pr.have = load_wanted<Tr, DIR, MATH>(c, t + 2, pr.s);
+    if (pr.have) load_cons<Tr>(A, c.base + (long long)pr.s * c.st, pr.q);
+    int cc;
+    const bool do_update = update_wanted<Tr, DIR, MATH>(c, t - 1, cc);
+    UpdateIn<Tr> uin;
+    if (do_update) update_fetch<Tr, DIR>(A, c, cc, uin);
+    if (t < nsteps) phase_face<Tr, DIR, MATH>(A, smem, c, t);
+    if (do_update) phase_update<Tr, DIR, MATH>(A, smem, c, cc, uin);
 }
 
 }  // namespace hb2

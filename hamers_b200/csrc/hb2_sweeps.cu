@@ -10,7 +10,8 @@
  * Kernels
  *   k_sensor  : thread per cell of the (N+4)^d box: dilatation + vorticity magnitude.
  *   k_flags   : thread per cell of the (N+3)^d box: the s > 0.65 decision of the cell's three low faces (one byte).
- *   k_sweep   : one direction: a 256-thread block marches along the sweep axis (hb2_sweep.cuh).
+ *   k_sweep   : one direction: a 256-thread block marches along the sweep axis, one barrier per iteration
+ *               (hb2_sweep.cuh).
  *   k_advance : RK update from materialised side fluxes (API-preserving mode).
  */
 #include "hb2_ops.h"
@@ -75,31 +76,24 @@ __global__ void __launch_bounds__(256) k_flags(const __grid_constant__ Geom G, c
     }
 }
 
+#ifndef HB2_MINB
+#define HB2_MINB 2
+#endif
+
 template <class Tr, int DIR>
-__global__ void __launch_bounds__(256) k_sweep(const __grid_constant__ DirArgs A)
+__global__ void __launch_bounds__(256, (MATH == 1 && Tr::MODEL == SS) ? HB2_MINB : 1) k_sweep(const __grid_constant__ DirArgs A)
 {
-    using Sh = SweepShape<Tr, DIR>;
+    using Sh = SweepShape<Tr, DIR, MATH>;
     extern __shared__ double smem[];
     const BlockId b = {(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z};
-    const PencilCtx c = pencil_ctx<Tr, DIR>(A, b, (int)threadIdx.x);
+    const PencilCtx c = pencil_ctx<Tr, DIR, MATH>(A, b, (int)threadIdx.x);
     const int nsteps = Sh::nsteps(c.c1 - c.c0);
-    double q[Tr::NCOMP];
-    int s;
-    bool have = load_wanted<Tr, DIR>(c, 0, s);
-    if (have) load_cons<Tr>(A, c.base + (long long)s * c.st, q);
-    for (int t = 0; t < nsteps; t++) {
-        if (have) phase_commit<Tr, DIR, MATH>(A, smem, c, s, q);
+    PipeRegs<Tr> pr;
+    pipeline_prologue<Tr, DIR, MATH>(A, smem, c, pr);
+    __syncthreads();
+    for (int t = 0; t <= nsteps; t++) {
+        pipeline_iteration<Tr, DIR, MATH>(A, smem, c, t, nsteps, pr);
         __syncthreads();
-        /* issue the loads of the next chunk; they complete behind the FP64-bound face phase */
-        int s_next = 0;
-        const bool have_next = (t + 1 < nsteps) && load_wanted<Tr, DIR>(c, t + 1, s_next);
-        if (have_next) load_cons<Tr>(A, c.base + (long long)s_next * c.st, q);
-        phase_face<Tr, DIR, MATH>(A, smem, c, t);
-        __syncthreads();
-        phase_update<Tr, DIR, MATH>(A, smem, c, t);
-        __syncthreads();
-        have = have_next;
-        s = s_next;
     }
 }
 
@@ -190,12 +184,14 @@ int launch_sensor_t(const Geom& G, const QTab& Qtab_dev, double* theta, double* 
 template <class Tr, int DIR>
 int launch_dir(const DirArgs& A, cudaStream_t st)
 {
-    using Sh = SweepShape<Tr, DIR>;
+    using Sh = SweepShape<Tr, DIR, MATH>;
     const Geom& G = A.G;
     const size_t smem = (size_t)Sh::SMEM_DOUBLES * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_sweep<Tr, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(k_sweep<Tr, DIR>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }

@@ -2,7 +2,7 @@
  * emu.cpp -- TEST-ONLY host emulation of the CUDA sweeps (never part of the product library).
  *
  * Compiles hamers_b200/csrc/hb2_core.cuh with g++ and drives the very same per-thread functions
- * the kernels call (pencil_ctx, phase_commit, phase_face, phase_update, sensor_cell, face_sensor) from plain loops that stand in
+ * the kernels call (pencil_ctx, pipeline_prologue, pipeline_iteration, sensor_cell, face_sensor) from plain loops that stand in
  * for the CUDA grid.  It exists because this container has no GPU: it lets the CPU test suite
  * check the kernels' indexing and arithmetic against the oracle before any GPU time is spent.
  * The GPU parity tests (pytest -m gpu) remain the parity tests proper.
@@ -35,11 +35,13 @@ static void make_geom(const EmuDesc* d, Geom* G)
     G->ncell_g = (long long)G->gd[0] * G->gd[1] * G->gd[2];
 }
 
-/* one direction: the loops below stand in for the CUDA grid, the barriers become loop boundaries */
+/* one direction: the loops below stand in for the CUDA grid, the barrier becomes the boundary between iterations.
+ * Within an iteration the threads run one after the other -- in forward order for even blocks and in REVERSE order for
+ * odd blocks -- so that a write that another thread still reads in the same iteration (a ring hazard) changes results. */
 template <class Tr, int DIR, int MATH>
 static void run_dir(const DirArgs& A)
 {
-    using Sh = SweepShape<Tr, DIR>;
+    using Sh = SweepShape<Tr, DIR, MATH>;
     const Geom& G = A.G;
     const int nseg = (G.n[DIR] + A.seg_len - 1) / A.seg_len;
     int gx, gy;
@@ -54,29 +56,26 @@ static void run_dir(const DirArgs& A)
         gy = G.n[1];
     }
     std::vector<double> smem(Sh::SMEM_DOUBLES);
+    std::vector<PipeRegs<Tr>> regs(Sh::NT);
+    int nblock = 0;
     for (int bz = 0; bz < nseg; bz++)
         for (int by = 0; by < gy; by++)
-            for (int bx = 0; bx < gx; bx++) {
+            for (int bx = 0; bx < gx; bx++, nblock++) {
                 const BlockId b = {bx, by, bz};
                 /* poison the rings: reading a slot that was never written must show up */
                 for (auto& v : smem) v = std::nan("");
-                PencilCtx c0 = pencil_ctx<Tr, DIR>(A, b, 0);
+                const PencilCtx c0 = pencil_ctx<Tr, DIR, MATH>(A, b, 0);
                 const int nsteps = Sh::nsteps(c0.c1 - c0.c0);
-                for (int t = 0; t < nsteps; t++) {
-                    for (int tid = 0; tid < Sh::NT; tid++) {
-                        const PencilCtx c = pencil_ctx<Tr, DIR>(A, b, tid);
-                        int s;
-                        if (load_wanted<Tr, DIR>(c, t, s)) {
-                            double q[Tr::NCOMP];
-                            load_cons<Tr>(A, c.base + (long long)s * c.st, q);
-                            phase_commit<Tr, DIR, MATH>(A, smem.data(), c, s, q);
-                        }
-                    }
-                    for (int tid = 0; tid < Sh::NT; tid++)
-                        phase_face<Tr, DIR, MATH>(A, smem.data(), pencil_ctx<Tr, DIR>(A, b, tid), t);
-                    for (int tid = 0; tid < Sh::NT; tid++)
-                        phase_update<Tr, DIR, MATH>(A, smem.data(), pencil_ctx<Tr, DIR>(A, b, tid), t);
+                const bool rev = (nblock & 1);
+                for (int n = 0; n < Sh::NT; n++) {
+                    const int tid = rev ? Sh::NT - 1 - n : n;
+                    pipeline_prologue<Tr, DIR, MATH>(A, smem.data(), pencil_ctx<Tr, DIR, MATH>(A, b, tid), regs[tid]);
                 }
+                for (int t = 0; t <= nsteps; t++)
+                    for (int n = 0; n < Sh::NT; n++) {
+                        const int tid = rev ? Sh::NT - 1 - n : n;
+                        pipeline_iteration<Tr, DIR, MATH>(A, smem.data(), pencil_ctx<Tr, DIR, MATH>(A, b, tid), t, nsteps, regs[tid]);
+                    }
             }
 }
 

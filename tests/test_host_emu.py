@@ -63,3 +63,26 @@ def test_emulated_tiling_is_invisible(seg_len, bx, oracle_lib):
     Fe, _ = emu_host.flux_and_source(desc, Q, 1e-3, math=0, bx=bx, seg_len=seg_len)
     for a in range(3):
         assert np.array_equal(Fe[a], Fo[a])
+
+
+@pytest.mark.parametrize("model,dim,N,seg_len", [(0, 2, (150, 40), 0), (0, 2, (150, 40), 70), (1, 2, (135, 37), 0),
+                                                 (0, 3, (36, 40, 34), 0), (1, 3, (34, 33, 40), 0)])
+def test_emulated_ring_wraparound(model, dim, N, seg_len, oracle_lib):
+    """Pencils longer than the shared-memory rings (32 slots in y/z, 128 in x): the rings wrap several times while a
+    block marches, so a slot reused too early (or a stale mirrored slot) changes the result."""
+    U, dx, gam = pb.random_state(dim, N, model=model, seed=17, shock=True)
+    desc = oracle_lib.PatchDesc(dim=dim, n=N, model=model, ns=len(gam), gamma=gam, dx=dx)
+    Q = pb.pad_periodic(U)
+    dt = 1.0e-3
+    Fo, So = oracle_lib.compute_flux_and_source(desc, Q, dt)
+    Fe, Se = emu_host.flux_and_source(desc, Q, dt, math=0, seg_len=seg_len)
+    for a in range(dim):
+        assert np.array_equal(Fe[a], Fo[a]), f"dir {a}"
+    assert np.array_equal(Se, So)
+    Uo = oracle_lib.advance_stage(desc, [1.0], [1.0], [Q], [Fo], [So])
+    for math in (0, 1):
+        Ue = emu_host.fused_stage(desc, [1.0], [1.0], [Q], dt, math=math, seg_len=seg_len)
+        if math == 0:
+            assert np.array_equal(interior(desc, Ue), interior(desc, Uo))
+        else:
+            assert_fast_parity(interior(desc, Ue), interior(desc, Uo))
