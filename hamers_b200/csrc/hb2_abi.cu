@@ -583,6 +583,14 @@ int hb2_fused_stage_dev(hb2_plan_t p, int32_t ncoef, const double* alpha, const 
                 for (int c = 0; c < p->ncomp; c++) A.Uint[m][c] = U_int[m * p->ncomp + c];
             }
             A.beta = beta[ncoef - 1];
+            A.nterm = 0;
+            for (int m = 0; m < ncoef; m++)
+                if (alpha[m] != 0.0) {
+                    if (A.nterm == HB2_MAXT) return fail(-22, "fused stage supports at most 3 states with alpha != 0");
+                    A.alpha_t[A.nterm] = alpha[m];
+                    for (int c = 0; c < p->ncomp; c++) A.Ut[A.nterm][c] = U_int[m * p->ncomp + c];
+                    A.nterm++;
+                }
             for (int c = 0; c < p->ncomp; c++) A.Uout[c] = U_out[c];
         }
         A.seg_len = p->seg_len[dir];

@@ -75,6 +75,7 @@ struct Consts {
 #define HB2_MAXC 13
 #define HB2_MAXE 12
 #define HB2_MAXS 4
+#define HB2_MAXT 3 /* states with alpha != 0 in one fused RK stage */
 
 struct DirArgs {
     Geom G;
@@ -92,6 +93,9 @@ struct DirArgs {
     double alpha[HB2_MAXS];
     double beta;
     const double* Uint[HB2_MAXS][HB2_MAXC];
+    int nterm;                 /* FUSED, last direction: the states with alpha != 0, compacted in stage order */
+    double alpha_t[HB2_MAXT];
+    const double* Ut[HB2_MAXT][HB2_MAXC];
     double* Uout[HB2_MAXC];
     int seg_len;               /* cells per marching segment along the sweep axis */
 };
@@ -573,15 +577,13 @@ HB2_HD void load_cons(const DirArgs& A, long long x, double (&q)[Tr::NCOMP])
 /* RK update of one interior cell from the complete right-hand side (FUSED, last direction).
  * Order of Euler.cpp:1479, 1544-1548: zero; += alpha_n*U_n for alpha_n != 0; += beta*(...). */
 template <class Tr>
-HB2_HD void rk_update_cell(const DirArgs& A, long long x, const double (&rhs)[Tr::NEQ])
+HB2_HD void rk_update_cell(const DirArgs& A, long long x, const double (&ua)[Tr::NEQ], const double (&rhs)[Tr::NEQ])
 {
     constexpr int NEQ = Tr::NEQ, NS = Tr::NS, DIM = Tr::DIM;
     double Unew[NEQ];
 #pragma unroll
     for (int e = 0; e < NEQ; e++) {
-        double u = 0.0;
-        for (int n = 0; n < A.ncoef; n++)
-            if (A.alpha[n] != 0.0) u += A.alpha[n] * A.Uint[n][e][x];
+        double u = ua[e]; /* sum_n alpha_n U_n, accumulated in the reference's order by the caller */
         u += A.beta * rhs[e];
         Unew[e] = u;
         A.Uout[e][x] = u;

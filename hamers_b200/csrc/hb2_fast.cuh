@@ -35,6 +35,21 @@ namespace hb2 {
 
 constexpr int kFieldUnroll = HB2_FIELD_UNROLL;
 
+/* min / max without the NaN bookkeeping of fmin / fmax (3 instead of ~6 instructions; the operands are finite) */
+HB2_HD double min_fast(double a, double b) { return (a < b) ? a : b; }
+HB2_HD double max_fast(double a, double b) { return (a > b) ? a : b; }
+
+/* true if the predicate holds for ANY thread of the (converged part of the) warp: lets a warp skip a rarely needed,
+ * if-converted block with one vote.  On the host (tests/host_emu) it is the predicate itself. */
+HB2_HD bool warp_any(bool pred)
+{
+#if defined(__CUDA_ARCH__)
+    return __any_sync(__activemask(), pred);
+#else
+    return pred;
+#endif
+}
+
 HB2_HD double rcp_fast(double x)
 {
 #if defined(__CUDA_ARCH__)
@@ -50,25 +65,22 @@ HB2_HD double rcp_fast(double x)
 #endif
 }
 
-/* sqrt(x) for x > 0 (x == 0 gives 0) */
+/* sqrt(x) for x > 0: MUFU.RSQ64H seed (2^-22) + two coupled Goldschmidt steps (-> ~2^-88 before rounding).
+ * GUARD: also return 0 for x == 0 (the seed is +inf there). */
+template <bool GUARD>
 HB2_HD double sqrt_fast(double x)
 {
 #if defined(__CUDA_ARCH__)
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    /* Goldschmidt: g -> sqrt(x), h -> 1/(2 sqrt(x)) */
-    double g = x * y;
-    double h = 0.5 * y;
+    double g = x * y;      /* -> sqrt(x) */
+    double h = 0.5 * y;    /* -> 1/(2 sqrt(x)) */
     double r = fma(-h, g, 0.5);
     g = fma(g, r, g);
     h = fma(h, r, h);
     r = fma(-h, g, 0.5);
     g = fma(g, r, g);
-    /* final residual correction */
-    h = fma(h, r, h);
-    r = fma(-g, g, x);
-    g = fma(r, h, g);
-    return (x == 0.0) ? 0.0 : g;
+    return (GUARD && x == 0.0) ? 0.0 : g;
 #else
     return sqrt(x);
 #endif
@@ -93,7 +105,7 @@ HB2_HD void cons_to_prim_fast(const double (&q)[Tr::NCOMP], const Consts& K, dou
         }
         const double p = (K.gamma[0] - 1.0) * fma(-0.5 * rho, ke, q[DIM + 1]);
         V[DIM + 1] = p;
-        c = sqrt_fast(K.gamma[0] * p * r);
+        c = sqrt_fast<true>(K.gamma[0] * p * r);
     } else {
         double rho = q[0];
 #pragma unroll
@@ -114,7 +126,7 @@ HB2_HD void cons_to_prim_fast(const double (&q)[Tr::NCOMP], const Consts& K, dou
         const double p = Gamma * fma(-0.5 * rho, ke, q[NS + DIM]);
         V[NS + DIM] = p;
         /* c^2 = Gamma p/rho + sum_i Y_i p/rho with sum_i Y_i = 1 */
-        c = sqrt_fast((Gamma + 1.0) * p * r);
+        c = sqrt_fast<true>((Gamma + 1.0) * p * r);
 #pragma unroll
         for (int si = 0; si < NS - 1; si++) V[NS + DIM + 1 + si] = q[NS + DIM + 1 + si];
     }
@@ -257,13 +269,13 @@ HB2_HD void riemann_fast(const double (&V_L)[Tr::NEQ], const double (&V_R)[Tr::N
         gam_L = fma(rg, g1_R, 1.0);
         gam_R = fma(rg, g1_L, 1.0);
     }
-    const double c_L = sqrt_fast(gam_L * p_L * (rr * rho_R));
-    const double c_R = sqrt_fast(gam_R * p_R * (rr * rho_L));
+    const double c_L = sqrt_fast<false>(gam_L * p_L * (rr * rho_R));
+    const double c_R = sqrt_fast<false>(gam_R * p_R * (rr * rho_L));
 
     const double u_average = 0.5 * (un_L + un_R);
     const double c_average = 0.5 * (c_L + c_R);
-    const double s_L = fmin(u_average - c_average, un_L - c_L);
-    const double s_R = fmax(u_average + c_average, un_R + c_R);
+    const double s_L = min_fast(u_average - c_average, un_L - c_L);
+    const double s_R = max_fast(u_average + c_average, un_R + c_R);
     const double m_L = rho_L * (s_L - un_L);
     const double m_R = rho_R * (s_R - un_R);
     const double s_star = fma(m_L, un_L, fma(-m_R, un_R, p_R - p_L)) * rcp_fast(m_L - m_R);
@@ -275,7 +287,7 @@ HB2_HD void riemann_fast(const double (&V_L)[Tr::NEQ], const double (&V_R)[Tr::N
     const double p_K = left ? p_L : p_R;
     const double s_K = left ? s_L : s_R;
     const double g1_K = left ? g1_L : g1_R;
-    const double s_mp = left ? fmin(0.0, s_L) : fmax(0.0, s_R);
+    const double s_mp = left ? min_fast(0.0, s_L) : max_fast(0.0, s_R);
     const double d_K = s_K - un_K;
     const double d_S = s_K - s_star;
     const double rdd = rcp_fast(d_K * d_S);
@@ -390,6 +402,7 @@ HB2_HD void face_midpoint_fast(const double* win, bool hybrid, const Consts& K, 
         for (int f = 0; f < NEQ; f++) {
             int xc, yc = 1 + DIR;
             double b = 0.0, e4 = eps4;
+            bool has_y = true;
             if (f == 0) {
                 xc = IP; b = -rc; e4 = 4.0 * eps4;
             } else if (f == 1) {
@@ -397,13 +410,13 @@ HB2_HD void face_midpoint_fast(const double* win, bool hybrid, const Consts& K, 
             } else if (f == NEQ - 1) {
                 xc = IP; b = rc; e4 = 4.0 * eps4;
             } else {
-                xc = 1 + ((f == 2) ? T0 : T1);
+                xc = 1 + ((f == 2) ? T0 : T1); has_y = false;
             }
             const double* X = win + xc * CS;
             double w[6];
 #pragma unroll
             for (int m = 0; m < 6; m++) w[m] = X[m * MS];
-            if (b != 0.0) {
+            if (has_y) {
                 const double* Y = win + yc * CS;
 #pragma unroll
                 for (int m = 0; m < 6; m++) w[m] = fma(b, Y[m * MS], w[m]);
@@ -455,14 +468,15 @@ HB2_HD void face_midpoint_fast(const double* win, bool hybrid, const Consts& K, 
         for (int f = 0; f < NEQ; f++) {
             int xc;
             double b = 0.0;
+            bool has_y = true;
             if (f == 0) {
                 xc = IV + DIR; b = -r_rc;
             } else if (f <= NS) {
                 xc = f - 1; b = (f == 1) ? -zc0 : -zc1;
             } else if (f < F_Z) {
-                xc = IV + ((f == F_T) ? T0 : T1);
+                xc = IV + ((f == F_T) ? T0 : T1); has_y = false;
             } else if (f < NEQ - 1) {
-                xc = IP + 1 + (f - F_Z);
+                xc = IP + 1 + (f - F_Z); has_y = false;
             } else {
                 xc = IV + DIR; b = r_rc;
             }
@@ -470,7 +484,7 @@ HB2_HD void face_midpoint_fast(const double* win, bool hybrid, const Consts& K, 
             double w[6];
 #pragma unroll
             for (int m = 0; m < 6; m++) w[m] = X[m * MS];
-            if (b != 0.0) {
+            if (has_y) {
                 const double* Y = win + IP * CS;
 #pragma unroll
                 for (int m = 0; m < 6; m++) w[m] = fma(b, Y[m * MS], w[m]);
@@ -514,7 +528,7 @@ HB2_HD void face_midpoint_fast(const double* win, bool hybrid, const Consts& K, 
 
     /* bounds check and first-order fallback (rare) */
     const int ok = side_bounded<Tr>(V_minus, K) & side_bounded<Tr>(V_plus, K);
-    if (!ok) {
+    if (warp_any(!ok) && !ok) {
 #pragma unroll
         for (int e = 0; e < NEQ; e++) {
             V_minus[e] = win[e * CS + 2 * MS];
@@ -553,7 +567,7 @@ HB2_HD void sensor_cell_fast(const Geom& G, const double* const* Q, long long x,
         const double omega_x = grad[2 % DIM][1] - grad[1][2 % DIM];
         const double omega_y = grad[0][2 % DIM] - grad[2 % DIM][0];
         const double omega_z = grad[1][0] - grad[0][1];
-        Omega = sqrt_fast(fma(omega_x, omega_x, fma(omega_y, omega_y, omega_z * omega_z)));
+        Omega = sqrt_fast<true>(fma(omega_x, omega_x, fma(omega_y, omega_y, omega_z * omega_z)));
     }
 }
 

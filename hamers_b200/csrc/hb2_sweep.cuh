@@ -28,6 +28,18 @@
 #pragma once
 #include "hb2_fast.cuh"
 
+/* Prefetch switches, chosen by measurement on B200 at 256^3 (ms per sweep x / y / z; the kernels sit at the
+ * 128-register limit of two resident blocks, so every extra value held across the face phase can tip into spills):
+ *   HB2_PREFETCH_R    1: fetch the running right-hand side of the update phase before the face phase, 0: after it
+ *   HB2_PREFETCH_FLAG 1: fetch the sensor byte of the face one iteration ahead, 0: at the start of its face phase
+ *     FLAG=0 R=1 : 1.10 / 1.06 / 1.25      FLAG=0 R=0 : 1.10 / 1.11 / 1.26      FLAG=1 R=1 : 1.07 / 1.36 / 1.21 */
+#ifndef HB2_PREFETCH_FLAG
+#define HB2_PREFETCH_FLAG 0
+#endif
+#ifndef HB2_PREFETCH_R
+#define HB2_PREFETCH_R 1
+#endif
+
 namespace hb2 {
 
 template <class Tr, int DIR, int MATH>
@@ -75,6 +87,8 @@ struct PencilCtx {
     int i, j, k;     /* coordinates of sweep cell 0 of the pencil */
     long long base;  /* ghost-box index of sweep cell 0 */
     long long st;    /* ghost-box stride along the sweep axis */
+    long long ibase; /* ghost-0 (interior layout) index of sweep cell 0 */
+    long long ist;   /* interior-layout stride along the sweep axis */
 };
 
 template <class Tr, int DIR, int MATH>
@@ -105,6 +119,8 @@ HB2_HD PencilCtx pencil_ctx(const DirArgs& A, const BlockId& b, int tid)
     c.c1 = (c.c0 + A.seg_len < N) ? c.c0 + A.seg_len : N;
     c.base = cidx(G, c.i, c.j, c.k);
     c.st = G.cs[DIR];
+    c.ibase = iidx(G, c.i, c.j, c.k);
+    c.ist = (DIR == 0) ? 1 : ((DIR == 1) ? (long long)G.n[0] : (long long)G.n[0] * G.n[1]);
     return c;
 }
 
@@ -152,13 +168,30 @@ HB2_HD void phase_commit(const DirArgs& A, double* smem, const PencilCtx& c, int
 
 /* ---- face phase: midpoint fluxes of faces c0-6+tC+o --------------------------------------------- */
 template <class Tr, int DIR, int MATH>
-HB2_HD void phase_face(const DirArgs& A, double* smem, const PencilCtx& c, int t)
+HB2_HD bool face_wanted(const PencilCtx& c, int t, int& f)
+{
+    using Sh = SweepShape<Tr, DIR, MATH>;
+    f = c.c0 - 6 + t * Sh::C + c.o;
+    return c.valid && f >= c.c0 - 1 && f <= c.c1 + 1;
+}
+
+/* the shock-sensor decision byte of the face's right cell (fetched one iteration ahead) */
+template <class Tr, int DIR, int MATH>
+HB2_HD unsigned int face_flag_fetch(const DirArgs& A, const PencilCtx& c, int t)
+{
+    int f;
+    if (!face_wanted<Tr, DIR, MATH>(c, t, f)) return 0;
+    return A.hyb[c.base + (long long)f * c.st];
+}
+
+template <class Tr, int DIR, int MATH>
+HB2_HD void phase_face(const DirArgs& A, double* smem, const PencilCtx& c, int t, unsigned int flag)
 {
     using Sh = SweepShape<Tr, DIR, MATH>;
     constexpr int NEQ = Tr::NEQ;
-    const int f = c.c0 - 6 + t * Sh::C + c.o;
-    if (!c.valid || f < c.c0 - 1 || f > c.c1 + 1) return;
-    const bool hybrid = (A.hyb[c.base + (long long)f * c.st] >> DIR) & 1;
+    int f;
+    if (!face_wanted<Tr, DIR, MATH>(c, t, f)) return;
+    const bool hybrid = (flag >> DIR) & 1;
     double* sM = smem + Sh::OFF_M;
     /* stencil window: cells f-3..f+2 at win[comp*CSV + m*MS] */
     const double* win = smem + Sh::slotv(c.pp, (f - 3) & (Sh::RING - 1));
@@ -197,8 +230,7 @@ HB2_HD bool update_wanted(const PencilCtx& c, int t, int& cc)
 template <class Tr, int DIR>
 HB2_HD long long update_index(const DirArgs& A, const PencilCtx& c, int cc)
 {
-    const int ci = (DIR == 0) ? cc : c.i, cj = (DIR == 1) ? cc : c.j, ck = (DIR == 2) ? cc : c.k;
-    return iidx(A.G, ci, cj, ck);
+    return c.ibase + (long long)cc * c.ist;
 }
 
 template <class Tr, int DIR>
@@ -212,7 +244,9 @@ HB2_HD void update_fetch(const DirArgs& A, const PencilCtx& c, int cc, UpdateIn<
     in.T = (Tr::ADV && DIR > 0) ? A.T[ix] : 0.0;
 }
 
-template <class Tr, int DIR, int MATH>
+/* NTERM: number of states in the RK linear combination (compile-time, so that their loads are unconditional and are
+ * all issued up front); 0 for the directions / modes without the RK update */
+template <class Tr, int DIR, int MATH, int NTERM>
 HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& c, int cc, const UpdateIn<Tr>& in)
 {
     using Sh = SweepShape<Tr, DIR, MATH>;
@@ -229,7 +263,18 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
     const bool fused = (A.mode == MODE_FUSED);
     const double dxd = G.dx[DIR];
     const int ci = (DIR == 0) ? cc : c.i, cj = (DIR == 1) ? cc : c.j, ck = (DIR == 2) ? cc : c.k;
-    const long long ix = iidx(G, ci, cj, ck);
+    const long long ix = c.ibase + (long long)cc * c.ist;
+
+    /* last direction of a fused stage: the states of the RK linear combination (the states with alpha != 0, compacted
+     * by the host).  All loads are issued here, before the shared-memory work below, and consumed at the very end. */
+    double ut[NTERM > 0 ? NTERM : 1][NEQ];
+    if (NTERM > 0) {
+        const long long x = c.base + (long long)cc * c.st;
+#pragma unroll
+        for (int k = 0; k < NTERM; k++)
+#pragma unroll
+            for (int e = 0; e < NEQ; e++) ut[k][e] = A.Ut[k][e][x];
+    }
 
     /* velocity-divergence contribution of this direction (advective equations of the five-eqn model) */
     double Tsum = 0.0;
@@ -299,7 +344,16 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
                     rhs[e] = rhs[e] + A.dt * sV[e * Sh::CSV + v_0] * Tsum;
                 }
             }
-            rk_update_cell<Tr>(A, c.base + (long long)cc * c.st, rhs);
+            /* Euler.cpp:1479, 1544-1548: zero; += alpha_n*U_n for alpha_n != 0; += beta*(...) */
+            double ua[NEQ];
+#pragma unroll
+            for (int e = 0; e < NEQ; e++) {
+                double u = 0.0;
+#pragma unroll
+                for (int k = 0; k < NTERM; k++) u += A.alpha_t[k] * ut[k][e];
+                ua[e] = u;
+            }
+            rk_update_cell<Tr>(A, c.base + (long long)cc * c.st, ua, rhs);
         } else {
 #pragma unroll
             for (int e = 0; e < NEQ; e++) A.R[e][ix] = rhs[e];
@@ -321,7 +375,9 @@ template <class Tr>
 struct PipeRegs {
     double q[Tr::NCOMP];
     int s;
-    bool have;
+    int have;
+    unsigned int flag;    /* sensor byte of the NEXT face phase (32-bit: a byte would be packed with `have`, which
+                             makes the pack instruction wait for the load) */
 };
 
 template <class Tr, int DIR, int MATH>
@@ -334,9 +390,10 @@ HB2_HD void pipeline_prologue(const DirArgs& A, double* smem, const PencilCtx& c
     }
     pr.have = load_wanted<Tr, DIR, MATH>(c, 1, pr.s);
     if (pr.have) load_cons<Tr>(A, c.base + (long long)pr.s * c.st, pr.q);
+    pr.flag = face_flag_fetch<Tr, DIR, MATH>(A, c, 0);
 }
 
-template <class Tr, int DIR, int MATH>
+template <class Tr, int DIR, int MATH, int NTERM>
 HB2_HD void pipeline_iteration(const DirArgs& A, double* smem, const PencilCtx& c, int t, int nsteps, PipeRegs<Tr>& pr)
 {
     if (pr.have) phase_commit<Tr, DIR, MATH>(A, smem, c, pr.s, pr.q);
@@ -345,9 +402,17 @@ HB2_HD void pipeline_iteration(const DirArgs& A, double* smem, const PencilCtx& 
     int cc;
     const bool do_update = update_wanted<Tr, DIR, MATH>(c, t - 1, cc);
     UpdateIn<Tr> uin;
-    if (do_update) update_fetch<Tr, DIR>(A, c, cc, uin);
-    if (t < nsteps) phase_face<Tr, DIR, MATH>(A, smem, c, t);
-    if (do_update) phase_update<Tr, DIR, MATH>(A, smem, c, cc, uin);
+    if (HB2_PREFETCH_R && do_update) update_fetch<Tr, DIR>(A, c, cc, uin);
+    unsigned int flag;
+    if (HB2_PREFETCH_FLAG) {
+        flag = pr.flag;
+        pr.flag = (t + 1 < nsteps) ? face_flag_fetch<Tr, DIR, MATH>(A, c, t + 1) : 0u;
+    } else {
+        flag = (t < nsteps) ? face_flag_fetch<Tr, DIR, MATH>(A, c, t) : 0u;
+    }
+    if (t < nsteps) phase_face<Tr, DIR, MATH>(A, smem, c, t, flag);
+    if (!HB2_PREFETCH_R && do_update) update_fetch<Tr, DIR>(A, c, cc, uin);
+    if (do_update) phase_update<Tr, DIR, MATH, NTERM>(A, smem, c, cc, uin);
 }
 
 }  // namespace hb2

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) k_flags(const __grid_constant__ Geom G, c
 #define HB2_MINB 2
 #endif
 
-template <class Tr, int DIR>
+template <class Tr, int DIR, int NTERM>
 __global__ void __launch_bounds__(256, (MATH == 1 && Tr::MODEL == SS) ? HB2_MINB : 1) k_sweep(const __grid_constant__ DirArgs A)
 {
     using Sh = SweepShape<Tr, DIR, MATH>;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256, (MATH == 1 && Tr::MODEL == SS) ? HB2_MINB
     pipeline_prologue<Tr, DIR, MATH>(A, smem, c, pr);
     __syncthreads();
     for (int t = 0; t <= nsteps; t++) {
-        pipeline_iteration<Tr, DIR, MATH>(A, smem, c, t, nsteps, pr);
+        pipeline_iteration<Tr, DIR, MATH, NTERM>(A, smem, c, t, nsteps, pr);
         __syncthreads();
     }
 }
@@ -181,17 +181,17 @@ int launch_sensor_t(const Geom& G, const QTab& Qtab_dev, double* theta, double* 
     return (int)cudaGetLastError();
 }
 
-template <class Tr, int DIR>
-int launch_dir(const DirArgs& A, cudaStream_t st)
+template <class Tr, int DIR, int NTERM>
+int launch_dir_n(const DirArgs& A, cudaStream_t st)
 {
     using Sh = SweepShape<Tr, DIR, MATH>;
     const Geom& G = A.G;
     const size_t smem = (size_t)Sh::SMEM_DOUBLES * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_sweep<Tr, DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_sweep<Tr, DIR, NTERM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(k_sweep<Tr, DIR>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(k_sweep<Tr, DIR, NTERM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
@@ -207,8 +207,21 @@ int launch_dir(const DirArgs& A, cudaStream_t st)
         grid.x = (G.n[0] + 31) / 32;
         grid.y = G.n[1];
     }
-    k_sweep<Tr, DIR><<<grid, Sh::NT, smem, st>>>(A);
+    k_sweep<Tr, DIR, NTERM><<<grid, Sh::NT, smem, st>>>(A);
     return (int)cudaGetLastError();
+}
+
+template <class Tr, int DIR>
+int launch_dir(const DirArgs& A, cudaStream_t st)
+{
+    /* the RK linear combination exists only in the last direction of a fused stage */
+    if (DIR == Tr::DIM - 1 && A.mode == MODE_FUSED) {
+        if (A.nterm == 1) return launch_dir_n<Tr, DIR, 1>(A, st);
+        if (A.nterm == 2) return launch_dir_n<Tr, DIR, 2>(A, st);
+        if (A.nterm == 3) return launch_dir_n<Tr, DIR, 3>(A, st);
+        return (int)cudaErrorInvalidValue;
+    }
+    return launch_dir_n<Tr, DIR, 0>(A, st);
 }
 
 template <class Tr>

@@ -38,8 +38,8 @@ static void make_geom(const EmuDesc* d, Geom* G)
 /* one direction: the loops below stand in for the CUDA grid, the barrier becomes the boundary between iterations.
  * Within an iteration the threads run one after the other -- in forward order for even blocks and in REVERSE order for
  * odd blocks -- so that a write that another thread still reads in the same iteration (a ring hazard) changes results. */
-template <class Tr, int DIR, int MATH>
-static void run_dir(const DirArgs& A)
+template <class Tr, int DIR, int MATH, int NTERM>
+static void run_dir_n(const DirArgs& A)
 {
     using Sh = SweepShape<Tr, DIR, MATH>;
     const Geom& G = A.G;
@@ -74,9 +74,20 @@ static void run_dir(const DirArgs& A)
                 for (int t = 0; t <= nsteps; t++)
                     for (int n = 0; n < Sh::NT; n++) {
                         const int tid = rev ? Sh::NT - 1 - n : n;
-                        pipeline_iteration<Tr, DIR, MATH>(A, smem.data(), pencil_ctx<Tr, DIR, MATH>(A, b, tid), t, nsteps, regs[tid]);
+                        pipeline_iteration<Tr, DIR, MATH, NTERM>(A, smem.data(), pencil_ctx<Tr, DIR, MATH>(A, b, tid), t, nsteps, regs[tid]);
                     }
             }
+}
+
+template <class Tr, int DIR, int MATH>
+static void run_dir(const DirArgs& A)
+{
+    if (DIR == Tr::DIM - 1 && A.mode == MODE_FUSED) {
+        if (A.nterm == 1) return run_dir_n<Tr, DIR, MATH, 1>(A);
+        if (A.nterm == 2) return run_dir_n<Tr, DIR, MATH, 2>(A);
+        return run_dir_n<Tr, DIR, MATH, 3>(A);
+    }
+    run_dir_n<Tr, DIR, MATH, 0>(A);
 }
 
 template <class Tr, int MATH>
@@ -178,6 +189,13 @@ extern "C" int emu_fused_stage(const EmuDesc* d, int ncoef, const double* alpha,
         for (int c = 0; c < ncomp; c++) A.Uint[m][c] = U_int[m * ncomp + c];
     }
     A.beta = beta[ncoef - 1];
+    A.nterm = 0;
+    for (int m = 0; m < ncoef; m++)
+        if (alpha[m] != 0.0) {
+            A.alpha_t[A.nterm] = alpha[m];
+            for (int c = 0; c < ncomp; c++) A.Ut[A.nterm][c] = U_int[m * ncomp + c];
+            A.nterm++;
+        }
     for (int c = 0; c < ncomp; c++) A.Uout[c] = U_out[c];
     EMU_DISPATCH(d, (run_sweeps<Tr, MATH>(A, d->bx, d->seg_len, nullptr, MODE_FUSED)));
     return -1;
