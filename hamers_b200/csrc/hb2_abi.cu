@@ -845,6 +845,23 @@ int hb2_advance_level_host(hb2_plan_t p, int32_t nstages, const double* alpha, c
 
 /* ---- host-buffer entry points ---------------------------------------------------------- */
 
+/* device -> host copy of the INTERIOR of one ghost-box component (the ghost cells of the host array stay untouched,
+ * like Euler::advanceSingleStepOnPatch, which only writes the interior of the SCRATCH state) */
+static int copy_interior_d2h(hb2_plan_t p, double* dst_host, const double* src_dev)
+{
+    const Geom& G = p->G;
+    cudaMemcpy3DParms q;
+    memset(&q, 0, sizeof(q));
+    q.srcPtr = make_cudaPitchedPtr((void*)src_dev, sizeof(double) * G.gd[0], G.gd[0], G.gd[1]);
+    q.dstPtr = make_cudaPitchedPtr((void*)dst_host, sizeof(double) * G.gd[0], G.gd[0], G.gd[1]);
+    q.srcPos = make_cudaPos(sizeof(double) * G.g[0], G.g[1], G.g[2]);
+    q.dstPos = q.srcPos;
+    q.extent = make_cudaExtent(sizeof(double) * G.n[0], G.n[1], G.n[2]);
+    q.kind = cudaMemcpyDeviceToHost;
+    HB2_CUDA(cudaMemcpy3DAsync(&q, p->stream));
+    return 0;
+}
+
 static int stage_alloc(double** slot, size_t bytes, hb2_plan_t p)
 {
     if (*slot) return 0;
@@ -916,7 +933,7 @@ int hb2_fused_stage_host(hb2_plan_t p, int32_t ncoef, const double* alpha, const
     rc = hb2_fused_stage_dev(p, ncoef, alpha, beta, tab, dt, p->stOut);
     if (rc) return rc;
     for (int c = 0; c < p->ncomp; c++)
-        HB2_CUDA(cudaMemcpyAsync(U_out_host[c], p->stOut[c], gb, cudaMemcpyDeviceToHost, p->stream));
+        if ((rc = copy_interior_d2h(p, U_out_host[c], p->stOut[c]))) return rc;
     HB2_CUDA(cudaStreamSynchronize(p->stream));
     return 0;
 }

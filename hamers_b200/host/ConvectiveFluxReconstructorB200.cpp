@@ -1,0 +1,177 @@
+/*
+ * ConvectiveFluxReconstructorB200.cpp -- see the header.  Marshalling only: every number is produced by
+ * libhamers_b200.so on the GPU (there is no CPU fallback; a missing device surfaces as TBOX_ERROR).
+ */
+#include "ConvectiveFluxReconstructorB200.hpp"
+
+#include <cstring>
+
+FlowModel::FlowModel(const std::string& object_name, const tbox::Dimension& dim, const FLOW_MODEL::TYPE& type, int num_species,
+                     const HAMERS_SHARED_PTR<tbox::Database>& flow_model_db)
+    : d_object_name(object_name), d_dim(dim), d_type(type), d_num_species(num_species), d_num_eqn(0)
+{
+    const int d = dim.getValue();
+    /* Flow_model { Equation_of_state_mixing_rules { species_gamma = ... } } */
+    d_species_gamma = flow_model_db->getDoubleVector("species_gamma");
+    if ((int)d_species_gamma.size() != num_species)
+        TBOX_ERROR(d_object_name << ": number of 'species_gamma' entries is not equal to the number of species." << std::endl);
+    if (type == FLOW_MODEL::SINGLE_SPECIES) {
+        if (num_species != 1) TBOX_ERROR(d_object_name << ": single-species flow model needs num_species = 1." << std::endl);
+        d_num_eqn = d + 2; /* FlowModelSingleSpecies.cpp:29 */
+        d_cons.push_back(HAMERS_SHARED_PTR<pdat::CellVariable<double> >(new pdat::CellVariable<double>(dim, "density", 1)));
+        d_cons.push_back(HAMERS_SHARED_PTR<pdat::CellVariable<double> >(new pdat::CellVariable<double>(dim, "momentum", d)));
+        d_cons.push_back(HAMERS_SHARED_PTR<pdat::CellVariable<double> >(new pdat::CellVariable<double>(dim, "total energy", 1)));
+    } else if (type == FLOW_MODEL::FIVE_EQN_ALLAIRE) {
+        d_num_eqn = d + 2 * num_species; /* FlowModelFiveEqnAllaire.cpp:29 */
+        d_cons.push_back(HAMERS_SHARED_PTR<pdat::CellVariable<double> >(new pdat::CellVariable<double>(dim, "partial densities", num_species)));
+        d_cons.push_back(HAMERS_SHARED_PTR<pdat::CellVariable<double> >(new pdat::CellVariable<double>(dim, "momentum", d)));
+        d_cons.push_back(HAMERS_SHARED_PTR<pdat::CellVariable<double> >(new pdat::CellVariable<double>(dim, "total energy", 1)));
+        d_cons.push_back(HAMERS_SHARED_PTR<pdat::CellVariable<double> >(new pdat::CellVariable<double>(dim, "volume fractions", num_species)));
+    } else {
+        TBOX_ERROR(d_object_name << ": the B200 convective-flux path is built for SINGLE_SPECIES and FIVE_EQN_ALLAIRE." << std::endl);
+    }
+}
+
+int FlowModel::getNumberOfStoredComponents() const
+{
+    int n = 0;
+    for (size_t v = 0; v < d_cons.size(); v++) n += d_cons[v]->getDepth();
+    return n;
+}
+
+ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200(
+    const std::string& object_name, const tbox::Dimension& dim, const HAMERS_SHARED_PTR<geom::CartesianGridGeometry>& grid_geometry,
+    const int& num_eqn, const FLOW_MODEL::TYPE& flow_model_type, const HAMERS_SHARED_PTR<FlowModel>& flow_model,
+    const HAMERS_SHARED_PTR<tbox::Database>& convective_flux_reconstructor_db)
+    : ConvectiveFluxReconstructor(object_name, dim, grid_geometry, num_eqn, flow_model_type, flow_model, convective_flux_reconstructor_db),
+      d_math(HB2_MATH_EXACT)
+{
+    /* ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:22: four ghost cells in every direction */
+    d_num_conv_ghosts = hier::IntVector::getOne(d_dim) * HB2_GHOSTS;
+    /* ConvectiveFluxReconstructorWCNS5-JS-HLLC-HLL.cpp:188-191 */
+    d_constant_p = d_convective_flux_reconstructor_db->getIntegerWithDefault("constant_p", 2);
+    d_constant_p = d_convective_flux_reconstructor_db->getIntegerWithDefault("d_constant_p", d_constant_p);
+    if (num_eqn != flow_model->getNumberOfEquations())
+        TBOX_ERROR(d_object_name << ": num_eqn does not match the flow model." << std::endl);
+    if (dim.getValue() < 2)
+        TBOX_ERROR(d_object_name << ": the 1D branch of WCNS56 has no shock sensor and is not on the B200 path." << std::endl);
+}
+
+ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::~ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200()
+{
+    for (std::map<std::vector<double>, hb2_plan_t>::iterator it = d_plans.begin(); it != d_plans.end(); ++it) hb2_plan_destroy(it->second);
+}
+
+void ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::printClassData(std::ostream& os) const
+{
+    os << "\nPrint ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200 object..." << std::endl;
+    os << std::endl;
+    os << "ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200: this = " << (const void*)this << std::endl;
+    os << "d_object_name = " << d_object_name << std::endl;
+    os << "d_constant_p = " << d_constant_p << std::endl;
+    os << "backend = " << hb2_version() << std::endl;
+}
+
+void ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::putToRestart(const HAMERS_SHARED_PTR<tbox::Database>& restart_db) const
+{
+    restart_db->putInteger("d_constant_p", d_constant_p);
+}
+
+hb2_plan_t ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::getPlan(const hier::Patch& patch)
+{
+    const int dim = d_dim.getValue();
+    const hier::IntVector interior_dims = patch.getBox().numberCells();
+    const HAMERS_SHARED_PTR<geom::CartesianPatchGeometry> patch_geom(
+        HAMERS_SHARED_PTR_CAST<geom::CartesianPatchGeometry, hier::PatchGeometry>(patch.getPatchGeometry()));
+    if (!patch_geom) TBOX_ERROR(d_object_name << ": patch has no Cartesian patch geometry." << std::endl);
+    const double* const dx = patch_geom->getDx();
+    std::vector<double> key;
+    for (int a = 0; a < dim; a++) {
+        key.push_back(interior_dims[a]);
+        key.push_back(dx[a]);
+    }
+    key.push_back(d_math);
+    std::map<std::vector<double>, hb2_plan_t>::iterator it = d_plans.find(key);
+    if (it != d_plans.end()) return it->second;
+
+    hb2_patch_desc desc;
+    std::memset(&desc, 0, sizeof(desc));
+    desc.dim = dim;
+    for (int a = 0; a < 3; a++) {
+        desc.n[a] = a < dim ? interior_dims[a] : 1;
+        desc.dx[a] = a < dim ? dx[a] : 1.0;
+    }
+    desc.flow_model = d_flow_model_type == FLOW_MODEL::SINGLE_SPECIES ? HB2_SINGLE_SPECIES : HB2_FIVE_EQN_ALLAIRE;
+    desc.num_species = d_flow_model->getNumberOfSpecies();
+    for (int s = 0; s < desc.num_species && s < HB2_MAX_SPECIES; s++) desc.species_gamma[s] = d_flow_model->getSpeciesGamma()[s];
+    desc.weno_p = d_constant_p;
+    desc.math = d_math;
+    desc.device = -1;
+    hb2_plan_t plan = 0;
+    if (hb2_plan_create(&desc, &plan) != 0) TBOX_ERROR(d_object_name << ": " << hb2_last_error() << std::endl);
+    d_plans[key] = plan;
+    return plan;
+}
+
+void ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::gatherConservative(hier::Patch& patch,
+                                                                         const HAMERS_SHARED_PTR<hier::VariableContext>& ctx,
+                                                                         std::vector<double*>& ptrs) const
+{
+    const std::vector<HAMERS_SHARED_PTR<pdat::CellVariable<double> > >& vars = d_flow_model->getConservativeVariables();
+    for (size_t v = 0; v < vars.size(); v++) {
+        HAMERS_SHARED_PTR<pdat::CellData<double> > data(
+            HAMERS_SHARED_PTR_CAST<pdat::CellData<double>, hier::PatchData>(patch.getPatchData(vars[v], ctx)));
+        if (!data) TBOX_ERROR(d_object_name << ": conservative variable '" << vars[v]->getName() << "' is not cell data." << std::endl);
+        if (!(data->getGhostCellWidth() == d_num_conv_ghosts))
+            TBOX_ERROR(d_object_name << ": conservative variables need " << HB2_GHOSTS << " ghost cells." << std::endl);
+        for (int d = 0; d < data->getDepth(); d++) ptrs.push_back(data->getPointer(d));
+    }
+}
+
+void ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::computeConvectiveFluxAndSourceOnPatch(
+    hier::Patch& patch, const HAMERS_SHARED_PTR<pdat::SideVariable<double> >& variable_convective_flux,
+    const HAMERS_SHARED_PTR<pdat::CellVariable<double> >& variable_source, const HAMERS_SHARED_PTR<hier::VariableContext>& data_context,
+    const double time, const double dt, const int RK_step_number)
+{
+    NULL_USE(time);
+    NULL_USE(RK_step_number);
+    const int dim = d_dim.getValue();
+    hb2_plan_t plan = getPlan(patch);
+
+    HAMERS_SHARED_PTR<pdat::SideData<double> > convective_flux(
+        HAMERS_SHARED_PTR_CAST<pdat::SideData<double>, hier::PatchData>(patch.getPatchData(variable_convective_flux, data_context)));
+    HAMERS_SHARED_PTR<pdat::CellData<double> > source(
+        HAMERS_SHARED_PTR_CAST<pdat::CellData<double>, hier::PatchData>(patch.getPatchData(variable_source, data_context)));
+    TBOX_ASSERT(convective_flux);
+    TBOX_ASSERT(convective_flux->getGhostCellWidth() == hier::IntVector::getZero(d_dim));
+    TBOX_ASSERT(convective_flux->getDepth() == d_num_eqn);
+    TBOX_ASSERT(source);
+    TBOX_ASSERT(source->getGhostCellWidth() == hier::IntVector::getZero(d_dim));
+    TBOX_ASSERT(source->getDepth() == d_num_eqn);
+
+    std::vector<double*> Q;
+    gatherConservative(patch, data_context, Q);
+    std::vector<double*> F, S;
+    for (int n = 0; n < dim; n++)
+        for (int e = 0; e < d_num_eqn; e++) F.push_back(convective_flux->getPointer(n, e));
+    for (int e = 0; e < d_num_eqn; e++) S.push_back(source->getPointer(e));
+
+    if (hb2_compute_flux_and_source_host(plan, (const double* const*)Q.data(), dt, F.data(), S.data()) != 0)
+        TBOX_ERROR(d_object_name << ": " << hb2_last_error() << std::endl);
+}
+
+void ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::advanceFusedStageOnPatch(
+    hier::Patch& patch, const double dt, const std::vector<double>& alpha, const std::vector<double>& beta,
+    const std::vector<HAMERS_SHARED_PTR<hier::VariableContext> >& intermediate_contexts,
+    const HAMERS_SHARED_PTR<hier::VariableContext>& output_context)
+{
+    const size_t ncoef = alpha.size();
+    if (beta.size() != ncoef || intermediate_contexts.size() != ncoef || ncoef == 0)
+        TBOX_ERROR(d_object_name << ": alpha, beta and the intermediate contexts must have the same, non-zero length." << std::endl);
+    hb2_plan_t plan = getPlan(patch);
+    std::vector<double*> U_int, U_out;
+    for (size_t m = 0; m < ncoef; m++) gatherConservative(patch, intermediate_contexts[m], U_int);
+    gatherConservative(patch, output_context, U_out);
+    if (hb2_fused_stage_host(plan, (int32_t)ncoef, alpha.data(), beta.data(), (const double* const*)U_int.data(), dt, U_out.data()) != 0)
+        TBOX_ERROR(d_object_name << ": " << hb2_last_error() << std::endl);
+}

@@ -157,7 +157,7 @@ int hb2_max_wave_speed_dev(hb2_plan_t plan, const double* const* Q, double* out_
 int hb2_compute_flux_and_source_host(hb2_plan_t plan, const double* const* Q_host, double dt,
                                      double* const* flux_host, double* const* source_host);
 /* One RK stage on host memory: uploads U_int rows (ghost-filled by the caller), runs the fused
- * stage, downloads U_out (whole ghost box; only its interior is meaningful). */
+ * stage, downloads the INTERIOR of U_out (the ghost cells of the host arrays are left untouched). */
 int hb2_fused_stage_host(hb2_plan_t plan, int32_t ncoef, const double* alpha, const double* beta,
                          const double* const* U_int_host, double dt, double* const* U_out_host);
 
