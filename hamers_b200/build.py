@@ -28,7 +28,7 @@ UNITS = [
     ("hb2_sweeps_fast.o", "hb2_sweeps.cu", ["-DHB2_MATH=1", "-fmad=true"] + os.environ.get("HB2_FAST_FLAGS", "").split()),
     ("hb2_abi.o", "hb2_abi.cu", ["-fmad=false"]),
 ]
-DEPS = ["hb2_core.cuh", "hb2_fast.cuh", "hb2_sweep.cuh", "hb2_ops.h", "hb2_sweeps.cu", "hb2_abi.cu", os.path.join(ROOT, "include", "hamers_b200.h")]
+DEPS = ["hb2_core.cuh", "hb2_fast.cuh", "hb2_sweep.cuh", "hb2_sensor.cuh", "hb2_ops.h", "hb2_sweeps.cu", "hb2_abi.cu", os.path.join(ROOT, "include", "hamers_b200.h")]
 
 
 def _mtime(p):

@@ -52,8 +52,6 @@ struct hb2_plan_s {
     cudaStream_t own_stream, stream;
     long long ncell_i;             /* interior cells */
     long long nside[3];
-    double* theta;
-    double* Omega;
     unsigned char* hyb;            /* per-cell shock-sensor decisions of the three low faces */
     double* R[HB2_MAXE];
     double* T;
@@ -65,6 +63,7 @@ struct hb2_plan_s {
     long long launches;
     long long ws_bytes;
     int seg_len[3];
+    int sensor_seg_len;
     /* per-kernel-kind device timing (CUDA events on the launching stream) */
     int profiling;
     struct ProfRec {
@@ -150,43 +149,70 @@ struct CPtrTab {
     const double* p[HB2_MAXC];
 };
 
-/* Same-level periodic fill: every ghost cell (faces, edges, corners) takes the value of its
- * periodic image in the interior. */
+/* Same-level periodic fill: every ghost cell (faces, edges, corners) of the periodic directions in `mask` takes the
+ * value of its periodic image in the interior.  Only the ghost slabs are enumerated: the z slabs (full ghost-box planes),
+ * then the y slabs of the remaining planes, then the x slabs of the remaining rows. */
+struct FillArgs {
+    long long count[3]; /* cells of the x / y / z slab class */
+    int lo[3], ext[3];  /* per direction: first coordinate and extent of the range the LOWER classes iterate over */
+};
+
 __global__ void __launch_bounds__(256) k_fill_periodic(const __grid_constant__ Geom G, const __grid_constant__ PtrTab U,
-                                                       int ncomp, int mask)
+                                                       int ncomp, int mask, const __grid_constant__ FillArgs F)
 {
-    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < G.ncell_g;
+    const long long total = F.count[0] + F.count[1] + F.count[2];
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total;
          id += (long long)gridDim.x * blockDim.x) {
+        int cls;
+        long long r = id;
+        if (r < F.count[2]) {
+            cls = 2;
+        } else if ((r -= F.count[2]) < F.count[1]) {
+            cls = 1;
+        } else {
+            r -= F.count[1];
+            cls = 0;
+        }
+        /* extents of this class: the slab direction has 2g cells, lower directions the full ghost box, higher
+         * directions the range left over by the higher classes */
+        int e[3], l[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            if (a == cls) {
+                e[a] = 2 * G.g[a];
+                l[a] = 0;
+            } else if (a < cls) {
+                e[a] = G.gd[a];
+                l[a] = -G.g[a];
+            } else {
+                e[a] = F.ext[a];
+                l[a] = F.lo[a];
+            }
+        }
         int c[3];
-        c[0] = (int)(id % G.gd[0]) - G.g[0];
-        c[1] = (int)((id / G.gd[0]) % G.gd[1]) - G.g[1];
-        c[2] = (int)(id / ((long long)G.gd[0] * G.gd[1])) - G.g[2];
-        bool ghost = false;
+        c[0] = (int)(r % e[0]);
+        c[1] = (int)((r / e[0]) % e[1]);
+        c[2] = (int)(r / ((long long)e[0] * e[1]));
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            if (a == cls)
+                c[a] = (c[a] < G.g[a]) ? c[a] - G.g[a] : G.n[a] + (c[a] - G.g[a]);
+            else
+                c[a] += l[a];
+        }
         int s[3];
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             s[a] = c[a];
             if ((mask >> a) & 1) {
-                if (c[a] < 0) {
-                    s[a] = c[a] + G.n[a];
-                    ghost = true;
-                } else if (c[a] >= G.n[a]) {
-                    s[a] = c[a] - G.n[a];
-                    ghost = true;
-                }
-            }
-        }
-        if (!ghost) continue;
-        /* patches narrower than the ghost width wrap more than once */
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            if ((mask >> a) & 1) {
+                /* patches narrower than the ghost width wrap more than once */
                 s[a] %= G.n[a];
                 if (s[a] < 0) s[a] += G.n[a];
             }
         }
+        const long long dst = cidx(G, c[0], c[1], c[2]);
         const long long src = cidx(G, s[0], s[1], s[2]);
-        for (int q = 0; q < ncomp; q++) U.p[q][id] = U.p[q][src];
+        for (int q = 0; q < ncomp; q++) U.p[q][dst] = U.p[q][src];
     }
 }
 
@@ -282,14 +308,10 @@ int grid_for(long long n, int block, int cap_per_sm = 32)
 
 int ensure_ws(hb2_plan_t p, bool fused)
 {
-    if (!p->theta) {
-        HB2_CUDA(cudaMalloc(&p->theta, sizeof(double) * p->G.ncell_g));
-        HB2_CUDA(cudaMalloc(&p->Omega, sizeof(double) * p->G.ncell_g));
+    if (!p->hyb) {
         HB2_CUDA(cudaMalloc(&p->hyb, (size_t)p->G.ncell_g));
-        HB2_CUDA(cudaMemsetAsync(p->theta, 0, sizeof(double) * p->G.ncell_g, p->stream));
-        HB2_CUDA(cudaMemsetAsync(p->Omega, 0, sizeof(double) * p->G.ncell_g, p->stream));
         HB2_CUDA(cudaMemsetAsync(p->hyb, 0, (size_t)p->G.ncell_g, p->stream));
-        p->ws_bytes += 2 * sizeof(double) * p->G.ncell_g + p->G.ncell_g;
+        p->ws_bytes += p->G.ncell_g;
     }
     if (p->d.flow_model == HB2_FIVE_EQN_ALLAIRE && !p->T) {
         HB2_CUDA(cudaMalloc(&p->T, sizeof(double) * p->ncell_i));
@@ -317,17 +339,19 @@ void base_args(hb2_plan_t p, const double* const* Q, double dt, DirArgs* A)
 
 int run_sensor(hb2_plan_t p, const double* const* Q)
 {
-    QTab qt;
-    memset(&qt, 0, sizeof(qt));
-    for (int c = 0; c < p->ncomp; c++) qt.p[c] = Q[c];
-    /* two launches: theta/Omega, then the per-face decisions.  The fast build evaluates the velocity gradients with
-     * reciprocal multiplications: the decision s > 0.65 can then differ from the oracle's only where s is within a few
-     * ulp of the threshold. */
+    SensorArgs S;
+    memset(&S, 0, sizeof(S));
+    S.G = p->G;
+    for (int c = 0; c < p->ncomp; c++) S.Q[c] = Q[c];
+    S.hyb = p->hyb;
+    S.seg_len = p->sensor_seg_len;
+    /* one launch.  The fast build evaluates the velocity gradients with reciprocal multiplications and the threshold
+     * without the division: the decision s > 0.65 can then differ from the oracle's only where s is within a few ulp
+     * of the threshold. */
     int rc;
     {
         ProfScope ps(p, 0);
-        p->launches++;
-        rc = p->ops->sensor(p->cfg, p->G, qt, p->theta, p->Omega, p->hyb, p->stream);
+        rc = p->ops->sensor(p->cfg, S, p->stream);
     }
     if (rc) return fail(-200, std::string("sensor kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc));
     return 0;
@@ -451,6 +475,18 @@ int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* out)
         if (forced > 0) sl = forced;
         p->seg_len[a] = sl;
     }
+    {
+        /* sensor pass: 64 x 8 tiles marching along z; enough segments for ~4 waves of 3 resident blocks per SM, at
+         * least 16 planes each (every segment re-reads 3 planes) */
+        const long long tiles = (long long)((p->G.n[0] + 3 + 63) / 64) * ((p->G.n[1] + 3 + 7) / 8);
+        long long nseg = (148LL * 3 * 4 + tiles - 1) / tiles;
+        const long long planes = p->G.n[2] + 3;
+        const long long maxseg = planes / 16 > 0 ? planes / 16 : 1;
+        if (nseg > maxseg) nseg = maxseg;
+        p->sensor_seg_len = (int)((planes + nseg - 1) / nseg);
+        const int forced = env_int("HB2_SENSOR_SEG_LEN", 0);
+        if (forced > 0) p->sensor_seg_len = forced;
+    }
     e = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete p;
@@ -467,8 +503,6 @@ int hb2_plan_destroy(hb2_plan_t p)
     if (!p) return 0;
     cudaSetDevice(p->device);
     cudaStreamSynchronize(p->stream);
-    cudaFree(p->theta);
-    cudaFree(p->Omega);
     cudaFree(p->hyb);
     cudaFree(p->T);
     for (int e = 0; e < HB2_MAXE; e++) cudaFree(p->R[e]);
@@ -655,9 +689,24 @@ int hb2_fill_ghosts_periodic_dev(hb2_plan_t p, double* const* U, int32_t mask)
     PtrTab t;
     memset(&t, 0, sizeof(t));
     for (int c = 0; c < p->ncomp; c++) t.p[c] = U[c];
+    mask &= (1 << p->d.dim) - 1;
+    FillArgs F;
+    memset(&F, 0, sizeof(F));
+    const Geom& G = p->G;
+    for (int a = 0; a < 3; a++) {
+        /* a periodic direction is covered by its own slab class: the lower classes see only its interior */
+        const bool per = (mask >> a) & 1;
+        F.lo[a] = per ? 0 : -G.g[a];
+        F.ext[a] = per ? G.n[a] : G.gd[a];
+    }
+    if (mask & 4) F.count[2] = 2LL * G.g[2] * G.gd[0] * G.gd[1];
+    if (mask & 2) F.count[1] = 2LL * G.g[1] * G.gd[0] * F.ext[2];
+    if (mask & 1) F.count[0] = 2LL * G.g[0] * F.ext[1] * F.ext[2];
+    const long long total = F.count[0] + F.count[1] + F.count[2];
+    if (total == 0) return 0;
     {
         ProfScope ps(p, 5);
-        k_fill_periodic<<<grid_for(p->G.ncell_g, 256), 256, 0, p->stream>>>(p->G, t, p->ncomp, mask & ((1 << p->d.dim) - 1));
+        k_fill_periodic<<<grid_for(total, 256), 256, 0, p->stream>>>(p->G, t, p->ncomp, mask, F);
     }
     HB2_CUDA(cudaGetLastError());
     return 0;

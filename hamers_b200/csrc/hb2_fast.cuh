@@ -50,22 +50,33 @@ HB2_HD bool warp_any(bool pred)
 #endif
 }
 
+/* 1/x: MUFU.RCP64H seed r0 (relative error e0 ~ 2^-22) + ONE third-order step r0 (1 + e + e^2), e = 1 - x r0
+ * (remaining error e0^3 ~ 2^-66, i.e. the result is rounded from a value good to ~1 ulp): 3 FP64 instructions instead
+ * of the 4 of two Newton steps, and ~10 instead of the library division */
+/* keeps a warp-uniform, rarely taken block a real branch (the compiler otherwise if-converts it into predicated
+ * instructions that are issued every time) */
+HB2_HD void uniform_branch_fence()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("" ::: "memory");
+#endif
+}
+
 HB2_HD double rcp_fast(double x)
 {
 #if defined(__CUDA_ARCH__)
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 #else
     return 1.0 / x;
 #endif
 }
 
-/* sqrt(x) for x > 0: MUFU.RSQ64H seed (2^-22) + two coupled Goldschmidt steps (-> ~2^-88 before rounding).
+/* sqrt(x) for x > 0: MUFU.RSQ64H seed y0 = (1 + e0)/sqrt(x), e0 ~ 2^-22; g = x y0, r = 1/2 - g y0/2 = -(e0 + e0^2/2);
+ * sqrt(x) = g/(1 + e0) = g (1 + r + 3/2 r^2) + O(e0^3): 6 FP64 instructions instead of the 7 of two coupled steps.
  * GUARD: also return 0 for x == 0 (the seed is +inf there). */
 template <bool GUARD>
 HB2_HD double sqrt_fast(double x)
@@ -73,14 +84,12 @@ HB2_HD double sqrt_fast(double x)
 #if defined(__CUDA_ARCH__)
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double g = x * y;      /* -> sqrt(x) */
-    double h = 0.5 * y;    /* -> 1/(2 sqrt(x)) */
-    double r = fma(-h, g, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-h, g, 0.5);
-    g = fma(g, r, g);
-    return (GUARD && x == 0.0) ? 0.0 : g;
+    const double g = x * y;
+    const double h = 0.5 * y;
+    const double r = fma(-h, g, 0.5);
+    const double t = fma(1.5 * r, r, r);
+    const double q = fma(g, t, g);
+    return (GUARD && x == 0.0) ? 0.0 : q;
 #else
     return sqrt(x);
 #endif
@@ -182,42 +191,48 @@ HB2_HD void weno5js_pair_fast(double w0, double w1, double w2, double w3, double
     const double s123 = fma(-2.0, w2, w1 + w3);
     const double s234 = fma(-2.0, w3, w2 + w4);
     const double s345 = fma(-2.0, w4, w3 + w5);
-    const double t012 = (13.0 / 3.0) * s012, t123 = (13.0 / 3.0) * s123, t234 = (13.0 / 3.0) * s234,
-                 t345 = (13.0 / 3.0) * s345;
-    /* minus side (cell 2 is the upwind cell): 4*beta_k = 13/3 s^2 + f^2 */
+    /* 4*beta_k + 4*eps = 13/3 s^2 + f^2 + eps4: the s-part of the two middle sub-stencils serves both sides */
+    const double q012 = fma((13.0 / 3.0) * s012, s012, eps4);
+    const double q123 = fma((13.0 / 3.0) * s123, s123, eps4);
+    const double q234 = fma((13.0 / 3.0) * s234, s234, eps4);
+    const double q345 = fma((13.0 / 3.0) * s345, s345, eps4);
+    /* minus side (cell 2 is the upwind cell) */
     const double f0 = fma(3.0, w2, fma(-4.0, w1, w0));
     const double f1 = w1 - w3;
     const double f2 = fma(3.0, w2, fma(-4.0, w3, w4));
-    double b0 = fma(t012, s012, fma(f0, f0, eps4));
-    double b1 = fma(t123, s123, fma(f1, f1, eps4));
-    double b2 = fma(t234, s234, fma(f2, f2, eps4));
+    double b0 = fma(f0, f0, q012);
+    double b1 = fma(f1, f1, q123);
+    double b2 = fma(f2, f2, q234);
     /* plus side (cell 3 is the upwind cell), mirrored */
     const double g0 = fma(3.0, w3, fma(-4.0, w4, w5));
-    const double g1 = w4 - w2;
     const double g2 = fma(3.0, w3, fma(-4.0, w2, w1));
-    double c0 = fma(t345, s345, fma(g0, g0, eps4));
-    double c1 = fma(t234, s234, fma(g1, g1, eps4));
-    double c2 = fma(t123, s123, fma(g2, g2, eps4));
+    const double g1 = w4 - w2;
+    double c0 = fma(g0, g0, q345);
+    double c1 = fma(g1, g1, q234);
+    double c2 = fma(g2, g2, q123);
     /* constant_p = 2 (the reference's default, ConvectiveFluxReconstructorWCNS5-JS-HLLC-HLL.cpp:188-191); plans with
      * another exponent run the exact-arithmetic kernels */
     b0 *= b0; b1 *= b1; b2 *= b2;
     c0 *= c0; c1 *= c1; c2 *= c2;
     /* un-normalised weights (x16): a0 = b1 b2, 10 a1 = 10 b0 b2, 5 a2 = 5 b0 b1;
-     * value = P1 + (a0 (P0 - P1) + 5 a2 (P2 - P1))/sum, and the sub-stencil differences are third differences:
-     * P0 - P1 = 3/8 (s012 - s123), P2 - P1 = 1/8 (s123 - s234) (mirrored on the plus side) */
+     * value = P1 + (a0 (P0 - P1) + 5 a2 (P2 - P1))/sum, the sub-stencil differences are third differences:
+     * P0 - P1 = 3/8 (s012 - s123), P2 - P1 = 1/8 (s123 - s234) (mirrored on the plus side), and the central
+     * sub-stencil value is P1 = (w2 + w3)/2 - s123/8 (plus side: - s234/8) */
+    const double d1 = s012 - s123, d2 = s123 - s234, d3 = s234 - s345;
+    const double h = 0.5 * (w2 + w3);
     {
         const double a0 = b1 * b2, a1 = b0 * b2, a2 = b0 * b1;
         const double sum = fma(5.0, a2, fma(10.0, a1, a0));
-        const double P1 = fma(0.375, w3, fma(0.75, w2, -0.125 * w1));
-        const double u0 = a0 * (s012 - s123), u2 = a2 * (s123 - s234);
+        const double P1 = fma(-0.125, s123, h);
+        const double u0 = a0 * d1, u2 = a2 * d2;
         wm = fma(fma(0.625, u2, 0.375 * u0), rcp_fast(sum), P1);
     }
     {
         const double a0 = c1 * c2, a1 = c0 * c2, a2 = c0 * c1;
         const double sum = fma(5.0, a2, fma(10.0, a1, a0));
-        const double P1 = fma(0.375, w2, fma(0.75, w3, -0.125 * w4));
-        const double u0 = a0 * (s345 - s234), u2 = a2 * (s234 - s123);
-        wp = fma(fma(0.625, u2, 0.375 * u0), rcp_fast(sum), P1);
+        const double P1 = fma(-0.125, s234, h);
+        const double u0 = a0 * d3, u2 = a2 * d2;
+        wp = fma(-fma(0.625, u2, 0.375 * u0), rcp_fast(sum), P1);
     }
 }
 
@@ -528,11 +543,14 @@ HB2_HD void face_midpoint_fast(const double* win, bool hybrid, const Consts& K, 
 
     /* bounds check and first-order fallback (rare) */
     const int ok = side_bounded<Tr>(V_minus, K) & side_bounded<Tr>(V_plus, K);
-    if (warp_any(!ok) && !ok) {
+    if (warp_any(!ok)) {
+        uniform_branch_fence();
+        if (!ok) {
 #pragma unroll
-        for (int e = 0; e < NEQ; e++) {
-            V_minus[e] = win[e * CS + 2 * MS];
-            V_plus[e] = win[e * CS + 3 * MS];
+            for (int e = 0; e < NEQ; e++) {
+                V_minus[e] = win[e * CS + 2 * MS];
+                V_plus[e] = win[e * CS + 3 * MS];
+            }
         }
     }
     riemann_fast<Tr, DIR>(V_minus, V_plus, K, hybrid, Fm, vel_mid);

@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "hb2_core.cuh"
+#include "hb2_sensor.cuh"
 
 namespace hb2 {
 
@@ -21,18 +22,13 @@ struct AdvanceArgs {
     double* Sacc[HB2_MAXE];
 };
 
-struct QTab {
-    const double* p[HB2_MAXC];
-};
-
 struct LaunchCfg {
     int model, dim, ns;
 };
 
 struct Ops {
-    /* theta / Omega on cells -2..N+1, then the per-face s > 0.65 decisions (one byte per cell) on cells -1..N+1 */
-    int (*sensor)(const LaunchCfg&, const Geom&, const QTab& Q, double* theta, double* Omega, unsigned char* hyb,
-                  cudaStream_t);
+    /* the per-face s > 0.65 decisions (one byte per cell) on cells -1..N+1 */
+    int (*sensor)(const LaunchCfg&, const SensorArgs&, cudaStream_t);
     /* one direction sweep */
     int (*sweep)(const LaunchCfg&, int dir, const DirArgs&, cudaStream_t);
     /* Euler::advanceSingleStepOnPatch from materialised fluxes */

@@ -34,7 +34,7 @@
  *   HB2_PREFETCH_FLAG 1: fetch the sensor byte of the face one iteration ahead, 0: at the start of its face phase
  *     FLAG=0 R=1 : 1.10 / 1.06 / 1.25      FLAG=0 R=0 : 1.10 / 1.11 / 1.26      FLAG=1 R=1 : 1.07 / 1.36 / 1.21 */
 #ifndef HB2_PREFETCH_FLAG
-#define HB2_PREFETCH_FLAG 0
+#define HB2_PREFETCH_FLAG 1
 #endif
 #ifndef HB2_PREFETCH_R
 #define HB2_PREFETCH_R 1
@@ -67,7 +67,11 @@ struct SweepShape {
     static constexpr int NMID = Tr::NEQ + (Tr::ADV ? 1 : 0); /* midpoint flux (+ HLLC midpoint velocity) */
     static constexpr int OFF_N = NV * CSV;
     static constexpr int OFF_M = OFF_N + NN * CS;
-    static constexpr int SMEM_DOUBLES = OFF_M + NMID * CS;
+    /* staging area of the load phase: the conservative variables of the cell a thread fetched with cp.async one
+     * iteration ago, [component][thread]; every thread reads back only its own slots, so no barrier is involved and no
+     * register is held across the face phase */
+    static constexpr int OFF_Q = OFF_M + NMID * CS;
+    static constexpr int SMEM_DOUBLES = OFF_Q + Tr::NCOMP * NT;
     HB2_HD static int slot(int pp, int s) { return (DIR == 0) ? pp * RING + (s & (RING - 1)) : (s & (RING - 1)) * 32 + pp; }
     /* primitive-variable ring: r = ring position in [0, RINGV) */
     HB2_HD static int slotv(int pp, int r) { return (DIR == 0) ? pp * RINGV + r : r * 32 + pp; }
@@ -80,6 +84,7 @@ struct BlockId {
 
 /* what one thread needs to know about its pencil */
 struct PencilCtx {
+    int tid;         /* thread index inside the block */
     int pp;          /* pencil index inside the block */
     int o;           /* position inside the chunk */
     bool valid;      /* pencil exists */
@@ -98,6 +103,7 @@ HB2_HD PencilCtx pencil_ctx(const DirArgs& A, const BlockId& b, int tid)
     const Geom& G = A.G;
     PencilCtx c;
     const int lane = tid & 31, w = tid >> 5;
+    c.tid = tid;
     c.pp = (DIR == 0) ? w : lane;
     c.o = (DIR == 0) ? lane : w;
     c.i = c.j = c.k = 0;
@@ -122,6 +128,41 @@ HB2_HD PencilCtx pencil_ctx(const DirArgs& A, const BlockId& b, int tid)
     c.ibase = iidx(G, c.i, c.j, c.k);
     c.ist = (DIR == 0) ? 1 : ((DIR == 1) ? (long long)G.n[0] : (long long)G.n[0] * G.n[1]);
     return c;
+}
+
+/* ---- asynchronous global -> shared staging (LDGSTS): 8 bytes per call, completion awaited by the issuing thread ---- */
+HB2_HD void stage_async8(double* dst_smem, const double* src)
+{
+#if defined(__CUDA_ARCH__)
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+#else
+    *dst_smem = *src;
+#endif
+}
+HB2_HD void stage_wait_all()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
+template <class Tr, int DIR, int MATH>
+HB2_HD void stage_cons(const DirArgs& A, double* smem, const PencilCtx& c, long long x)
+{
+    using Sh = SweepShape<Tr, DIR, MATH>;
+    double* sQ = smem + Sh::OFF_Q + c.tid;
+#pragma unroll
+    for (int cix = 0; cix < Tr::NCOMP; cix++) stage_async8(sQ + cix * Sh::NT, A.Q[cix] + x);
+}
+
+template <class Tr, int DIR, int MATH>
+HB2_HD void staged_cons(const double* smem, const PencilCtx& c, double (&q)[Tr::NCOMP])
+{
+    using Sh = SweepShape<Tr, DIR, MATH>;
+    const double* sQ = smem + Sh::OFF_Q + c.tid;
+#pragma unroll
+    for (int cix = 0; cix < Tr::NCOMP; cix++) q[cix] = sQ[cix * Sh::NT];
 }
 
 /* ---- load / commit: chunk t = cells c0-4+tC+o ------------------------------------------------- */
@@ -373,7 +414,6 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
  * and nothing it writes is read by another thread in the same iteration, so ONE barrier per iteration suffices. */
 template <class Tr>
 struct PipeRegs {
-    double q[Tr::NCOMP];
     int s;
     int have;
     unsigned int flag;    /* sensor byte of the NEXT face phase (32-bit: a byte would be packed with `have`, which
@@ -385,20 +425,26 @@ HB2_HD void pipeline_prologue(const DirArgs& A, double* smem, const PencilCtx& c
 {
     int s;
     if (load_wanted<Tr, DIR, MATH>(c, 0, s)) {
-        load_cons<Tr>(A, c.base + (long long)s * c.st, pr.q);
-        phase_commit<Tr, DIR, MATH>(A, smem, c, s, pr.q);
+        double q[Tr::NCOMP];
+        load_cons<Tr>(A, c.base + (long long)s * c.st, q);
+        phase_commit<Tr, DIR, MATH>(A, smem, c, s, q);
     }
     pr.have = load_wanted<Tr, DIR, MATH>(c, 1, pr.s);
-    if (pr.have) load_cons<Tr>(A, c.base + (long long)pr.s * c.st, pr.q);
+    if (pr.have) stage_cons<Tr, DIR, MATH>(A, smem, c, c.base + (long long)pr.s * c.st);
     pr.flag = face_flag_fetch<Tr, DIR, MATH>(A, c, 0);
 }
 
 template <class Tr, int DIR, int MATH, int NTERM>
 HB2_HD void pipeline_iteration(const DirArgs& A, double* smem, const PencilCtx& c, int t, int nsteps, PipeRegs<Tr>& pr)
 {
-    if (pr.have) phase_commit<Tr, DIR, MATH>(A, smem, c, pr.s, pr.q);
+    if (pr.have) {
+        double q[Tr::NCOMP];
+        stage_wait_all();
+        staged_cons<Tr, DIR, MATH>(smem, c, q);
+        phase_commit<Tr, DIR, MATH>(A, smem, c, pr.s, q);
+    }
     pr.have = load_wanted<Tr, DIR, MATH>(c, t + 2, pr.s);
-    if (pr.have) load_cons<Tr>(A, c.base + (long long)pr.s * c.st, pr.q);
+    if (pr.have) stage_cons<Tr, DIR, MATH>(A, smem, c, c.base + (long long)pr.s * c.st);
     int cc;
     const bool do_update = update_wanted<Tr, DIR, MATH>(c, t - 1, cc);
     UpdateIn<Tr> uin;

@@ -8,14 +8,15 @@
  * __global__ entry points and their launchers.
  *
  * Kernels
- *   k_sensor  : thread per cell of the (N+4)^d box: dilatation + vorticity magnitude.
- *   k_flags   : thread per cell of the (N+3)^d box: the s > 0.65 decision of the cell's three low faces (one byte).
+ *   k_sensor  : the s > 0.65 decision of every cell's low faces (one byte per cell) in one pass: a block marches
+ *               along z with velocity and theta/Omega planes in shared-memory rings (hb2_sensor.cuh).
  *   k_sweep   : one direction: a 256-thread block marches along the sweep axis, one barrier per iteration
  *               (hb2_sweep.cuh).
  *   k_advance : RK update from materialised side fluxes (API-preserving mode).
  */
 #include "hb2_ops.h"
 #include "hb2_sweep.cuh"
+#include "hb2_sensor.cuh"
 
 #ifndef HB2_MATH
 #error "compile with -DHB2_MATH=0 (exact) or -DHB2_MATH=1 (fast)"
@@ -26,53 +27,27 @@ namespace {
 
 constexpr int MATH = HB2_MATH;
 
+/* the shock-sensor decisions of the whole patch in one pass (hb2_sensor.cuh) */
 template <class Tr>
-__global__ void __launch_bounds__(256) k_sensor(const __grid_constant__ Geom G, const __grid_constant__ QTab Qtab,
-                                                double* __restrict__ theta, double* __restrict__ Omega)
+__global__ void __launch_bounds__(256, 3) k_sensor(const __grid_constant__ SensorArgs A)
 {
-    const double* const* Q = Qtab.p;
-    const int e0 = G.n[0] + 4, e1 = G.n[1] + 4, e2 = (Tr::DIM == 3) ? G.n[2] + 4 : 1;
-    const long long total = (long long)e0 * e1 * e2;
-    const double hidx[3] = {0.5 / G.dx[0], 0.5 / G.dx[1], 0.5 / G.dx[2]};
-    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total;
-         id += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(id % e0) - 2;
-        const long long r = id / e0;
-        const int j = (int)(r % e1) - 2;
-        const int k = (Tr::DIM == 3) ? (int)(r / e1) - 2 : 0;
-        const long long x = cidx(G, i, j, k);
-        double th, Om;
-        if (MATH == 0)
-            sensor_cell<Tr>(G, Q, x, th, Om);
-        else
-            sensor_cell_fast<Tr>(G, Q, x, hidx, th, Om);
-        theta[x] = th;
-        Omega[x] = Om;
-    }
-}
-
-/* bit d of hyb[cell] = shock-sensor decision of the face between cells (cell - e_d) and cell, for cells -1..N+1 */
-template <int DIM>
-__global__ void __launch_bounds__(256) k_flags(const __grid_constant__ Geom G, const double* __restrict__ theta,
-                                               const double* __restrict__ Omega, unsigned char* __restrict__ hyb)
-{
-    const int e0 = G.n[0] + 3, e1 = G.n[1] + 3, e2 = (DIM == 3) ? G.n[2] + 3 : 1;
-    const long long total = (long long)e0 * e1 * e2;
-    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total;
-         id += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(id % e0) - 1;
-        const long long r = id / e0;
-        const int j = (int)(r % e1) - 1;
-        const int k = (DIM == 3) ? (int)(r / e1) - 1 : 0;
-        const long long x = cidx(G, i, j, k);
-        const double th = theta[x], Om = Omega[x];
-        unsigned char f = 0;
-#pragma unroll
-        for (int d = 0; d < DIM; d++) {
-            const long long xl = x - G.cs[d];
-            if (face_sensor(theta[xl], th, Omega[xl], Om)) f |= (unsigned char)(1u << d);
+    extern __shared__ double smem[];
+    const int tid = (int)threadIdx.x;
+    const SensorTile T = sensor_tile<Tr>(A, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
+    if (Tr::DIM == 3) {
+        for (int t = T.kb - 2; t <= T.ke; t++) {
+            sensor_phase_velocity<Tr, MATH>(A, smem, T, tid, t);
+            __syncthreads();
+            if (t >= T.kb) sensor_phase_gradient<Tr, MATH>(A, smem, T, tid, t - 1);
+            __syncthreads();
+            if (t >= T.kb + 1) sensor_phase_decision<Tr, MATH>(A, smem, T, tid, t - 1);
         }
-        hyb[x] = f;
+    } else {
+        sensor_phase_velocity<Tr, MATH>(A, smem, T, tid, 0);
+        __syncthreads();
+        sensor_phase_gradient<Tr, MATH>(A, smem, T, tid, 0);
+        __syncthreads();
+        sensor_phase_decision<Tr, MATH>(A, smem, T, tid, 0);
     }
 }
 
@@ -169,15 +144,18 @@ __global__ void __launch_bounds__(256) k_advance(const __grid_constant__ Advance
 /* ---- host-side launchers ------------------------------------------------------------- */
 
 template <class Tr>
-int launch_sensor_t(const Geom& G, const QTab& Qtab_dev, double* theta, double* Omega, unsigned char* hyb, cudaStream_t st)
+int launch_sensor_t(const SensorArgs& A, cudaStream_t st)
 {
-    const long long total = (long long)(G.n[0] + 4) * (G.n[1] + 4) * (Tr::DIM == 3 ? G.n[2] + 4 : 1);
-    long long blocks = (total + 255) / 256;
-    if (blocks > 148LL * 64) blocks = 148LL * 64;
-    k_sensor<Tr><<<(unsigned)blocks, 256, 0, st>>>(G, Qtab_dev, theta, Omega);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
-    k_flags<Tr::DIM><<<(unsigned)blocks, 256, 0, st>>>(G, theta, Omega, hyb);
+    using Sh = SensorShape<Tr>;
+    const size_t smem = (size_t)Sh::SMEM_DOUBLES * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_sensor<Tr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    dim3 grid(Sh::tiles_x(A.G), Sh::tiles_y(A.G), Sh::segments(A.G, A.seg_len));
+    k_sensor<Tr><<<grid, Sh::NT, smem, st>>>(A);
     return (int)cudaGetLastError();
 }
 
@@ -240,10 +218,9 @@ int launch_sweep_t(const LaunchCfg&, int dir, const DirArgs& A, cudaStream_t st)
         if ((cfg).model == FE && (cfg).dim == 3 && (cfg).ns == 2) { using Tr = Traits<FE, 3, 2>; CALL; } \
     } while (0)
 
-int op_sensor(const LaunchCfg& cfg, const Geom& G, const QTab& Qtab_dev, double* theta, double* Omega, unsigned char* hyb,
-              cudaStream_t st)
+int op_sensor(const LaunchCfg& cfg, const SensorArgs& A, cudaStream_t st)
 {
-    HB2_DISPATCH(cfg, return launch_sensor_t<Tr>(G, Qtab_dev, theta, Omega, hyb, st));
+    HB2_DISPATCH(cfg, return launch_sensor_t<Tr>(A, st));
     return -1;
 }
 

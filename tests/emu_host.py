@@ -10,7 +10,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "host_emu", "libhb2_emu.so")
 _SRC = os.path.join(_HERE, "host_emu", "emu.cpp")
-_CORE = [os.path.join(_HERE, "..", "hamers_b200", "csrc", f) for f in ("hb2_core.cuh", "hb2_fast.cuh", "hb2_sweep.cuh")]
+_CORE = [os.path.join(_HERE, "..", "hamers_b200", "csrc", f) for f in ("hb2_core.cuh", "hb2_fast.cuh", "hb2_sweep.cuh", "hb2_sensor.cuh")]
 _LIB = None
 
 
@@ -54,7 +54,7 @@ def _desc(desc, math, bx, seg_len):
     return d
 
 
-def flux_and_source(desc, Q, dt, math=0, bx=128, seg_len=0, source=None):
+def flux_and_source(desc, Q, dt, math=0, bx=0, seg_len=0, source=None):
     neq, dim = desc.neq, desc.dim
     F = [np.full((neq,) + desc.side_shape(a), np.nan) for a in range(dim)]
     S = np.zeros((neq,) + desc.cell_shape) if source is None else source
@@ -67,7 +67,7 @@ def flux_and_source(desc, Q, dt, math=0, bx=128, seg_len=0, source=None):
     return F, S
 
 
-def fused_stage(desc, alpha, beta, U_int, dt, math=0, bx=128, seg_len=0):
+def fused_stage(desc, alpha, beta, U_int, dt, math=0, bx=0, seg_len=0):
     ncoef = len(alpha)
     U_out = np.zeros((desc.ncomp,) + desc.ghost_shape)
     d = _desc(desc, math, bx, seg_len)

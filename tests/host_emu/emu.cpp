@@ -2,12 +2,13 @@
  * emu.cpp -- TEST-ONLY host emulation of the CUDA sweeps (never part of the product library).
  *
  * Compiles hamers_b200/csrc/hb2_core.cuh with g++ and drives the very same per-thread functions
- * the kernels call (pencil_ctx, pipeline_prologue, pipeline_iteration, sensor_cell, face_sensor) from plain loops that stand in
+ * the kernels call (pencil_ctx, pipeline_prologue, pipeline_iteration, sensor_phase_*) from plain loops that stand in
  * for the CUDA grid.  It exists because this container has no GPU: it lets the CPU test suite
  * check the kernels' indexing and arithmetic against the oracle before any GPU time is spent.
  * The GPU parity tests (pytest -m gpu) remain the parity tests proper.
  */
 #include "../../hamers_b200/csrc/hb2_sweep.cuh"
+#include "../../hamers_b200/csrc/hb2_sensor.cuh"
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -91,35 +92,44 @@ static void run_dir(const DirArgs& A)
 }
 
 template <class Tr, int MATH>
-static void run_sweeps(DirArgs A0, int /*bx*/, int seg_len, double* const* F_all, int mode)
+static void run_sweeps(DirArgs A0, int sensor_seg_len, int seg_len, double* const* F_all, int mode)
 {
     const Geom& G = A0.G;
-    /* sensor: theta / Omega on cells -2..N+1, decisions on cells -1..N+1 */
-    std::vector<double> theta(G.ncell_g, std::nan("")), Omega(G.ncell_g, std::nan(""));
+    /* sensor decisions on cells -1..N+1: the phase functions of k_sensor, the loops stand in for grid and barriers
+     * (threads in reverse order in odd blocks; rings poisoned) */
     std::vector<unsigned char> hyb(G.ncell_g, 0);
-    const double hidx[3] = {0.5 / G.dx[0], 0.5 / G.dx[1], 0.5 / G.dx[2]};
-    const int k2 = (Tr::DIM == 3) ? 2 : 0;
-    for (int k = -k2; k < ((Tr::DIM == 3) ? G.n[2] + 2 : 1); k++)
-        for (int j = -2; j < G.n[1] + 2; j++)
-            for (int i = -2; i < G.n[0] + 2; i++) {
-                const long long x = cidx(G, i, j, k);
-                if (MATH == 0)
-                    sensor_cell<Tr>(G, A0.Q, x, theta[x], Omega[x]);
-                else
-                    sensor_cell_fast<Tr>(G, A0.Q, x, hidx, theta[x], Omega[x]);
-            }
-    const int k1 = (Tr::DIM == 3) ? 1 : 0;
-    for (int k = -k1; k < ((Tr::DIM == 3) ? G.n[2] + 2 : 1); k++)
-        for (int j = -1; j < G.n[1] + 2; j++)
-            for (int i = -1; i < G.n[0] + 2; i++) {
-                const long long x = cidx(G, i, j, k);
-                unsigned char f = 0;
-                for (int d = 0; d < Tr::DIM; d++) {
-                    const long long xl = x - G.cs[d];
-                    if (face_sensor(theta[xl], theta[x], Omega[xl], Omega[x])) f |= (unsigned char)(1u << d);
+    {
+        using Sh = SensorShape<Tr>;
+        SensorArgs S;
+        memset(&S, 0, sizeof(S));
+        S.G = G;
+        for (int c = 0; c < Tr::NCOMP; c++) S.Q[c] = A0.Q[c];
+        S.hyb = hyb.data();
+        S.seg_len = sensor_seg_len > 0 ? sensor_seg_len : G.n[2] + 3;
+        std::vector<double> sm(Sh::SMEM_DOUBLES);
+        int nblock = 0;
+        for (int bz = 0; bz < Sh::segments(G, S.seg_len); bz++)
+            for (int by = 0; by < Sh::tiles_y(G); by++)
+                for (int bx = 0; bx < Sh::tiles_x(G); bx++, nblock++) {
+                    for (auto& v : sm) v = std::nan("");
+                    const SensorTile T = sensor_tile<Tr>(S, bx, by, bz);
+                    const bool rev = (nblock & 1);
+                    auto each = [&](auto fn) {
+                        for (int n = 0; n < Sh::NT; n++) fn(rev ? Sh::NT - 1 - n : n);
+                    };
+                    if (Tr::DIM == 3) {
+                        for (int t = T.kb - 2; t <= T.ke; t++) {
+                            each([&](int tid) { sensor_phase_velocity<Tr, MATH>(S, sm.data(), T, tid, t); });
+                            if (t >= T.kb) each([&](int tid) { sensor_phase_gradient<Tr, MATH>(S, sm.data(), T, tid, t - 1); });
+                            if (t >= T.kb + 1) each([&](int tid) { sensor_phase_decision<Tr, MATH>(S, sm.data(), T, tid, t - 1); });
+                        }
+                    } else {
+                        each([&](int tid) { sensor_phase_velocity<Tr, MATH>(S, sm.data(), T, tid, 0); });
+                        each([&](int tid) { sensor_phase_gradient<Tr, MATH>(S, sm.data(), T, tid, 0); });
+                        each([&](int tid) { sensor_phase_decision<Tr, MATH>(S, sm.data(), T, tid, 0); });
+                    }
                 }
-                hyb[x] = f;
-            }
+    }
     A0.hyb = hyb.data();
     A0.mode = mode;
 
