@@ -309,8 +309,9 @@ int grid_for(long long n, int block, int cap_per_sm = 32)
 int ensure_ws(hb2_plan_t p, bool fused)
 {
     if (!p->hyb) {
-        HB2_CUDA(cudaMalloc(&p->hyb, (size_t)p->G.ncell_g));
-        HB2_CUDA(cudaMemsetAsync(p->hyb, 0, (size_t)p->G.ncell_g, p->stream));
+        /* + 4: the sweeps fetch the aligned 32-bit word around a decision byte */
+        HB2_CUDA(cudaMalloc(&p->hyb, (size_t)p->G.ncell_g + 4));
+        HB2_CUDA(cudaMemsetAsync(p->hyb, 0, (size_t)p->G.ncell_g + 4, p->stream));
         p->ws_bytes += p->G.ncell_g;
     }
     if (p->d.flow_model == HB2_FIVE_EQN_ALLAIRE && !p->T) {
@@ -476,9 +477,9 @@ int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* out)
         p->seg_len[a] = sl;
     }
     {
-        /* sensor pass: 64 x 8 tiles marching along z; enough segments for ~4 waves of 3 resident blocks per SM, at
+        /* sensor pass: 61 x 8 tiles marching along z; enough segments for ~4 waves of 3 resident blocks per SM, at
          * least 16 planes each (every segment re-reads 3 planes) */
-        const long long tiles = (long long)((p->G.n[0] + 3 + 63) / 64) * ((p->G.n[1] + 3 + 7) / 8);
+        const long long tiles = (long long)((p->G.n[0] + 3 + 60) / 61) * ((p->G.n[1] + 3 + 7) / 8);
         long long nseg = (148LL * 3 * 4 + tiles - 1) / tiles;
         const long long planes = p->G.n[2] + 3;
         const long long maxseg = planes / 16 > 0 ? planes / 16 : 1;

@@ -567,6 +567,28 @@ HB2_HD void face_midpoint(const double (&V)[6][Tr::NEQ], double c_cellL, double 
 /* ------------------------------------------------------------------------------------------
  * helpers shared by the sweeps
  * ---------------------------------------------------------------------------------------- */
+/* streaming accesses of data touched once per sweep (running right-hand side, RK states): HB2_STREAM_HINTS=1 uses the
+ * evict-first / no-allocate cache hints */
+#ifndef HB2_STREAM_HINTS
+#define HB2_STREAM_HINTS 0
+#endif
+HB2_HD double load_stream(const double* p)
+{
+#if defined(__CUDA_ARCH__) && HB2_STREAM_HINTS
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+HB2_HD void store_stream(double* p, double v)
+{
+#if defined(__CUDA_ARCH__) && HB2_STREAM_HINTS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 template <class Tr>
 HB2_HD void load_cons(const DirArgs& A, long long x, double (&q)[Tr::NCOMP])
 {
@@ -586,7 +608,7 @@ HB2_HD void rk_update_cell(const DirArgs& A, long long x, const double (&ua)[Tr:
         double u = ua[e]; /* sum_n alpha_n U_n, accumulated in the reference's order by the caller */
         u += A.beta * rhs[e];
         Unew[e] = u;
-        A.Uout[e][x] = u;
+        store_stream(A.Uout[e] + x, u);
     }
     if (Tr::MODEL == FE) {
         double zl = 1.0;

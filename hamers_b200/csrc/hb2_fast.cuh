@@ -186,27 +186,27 @@ HB2_HD void weno5js_pair_fast(double w0, double w1, double w2, double w3, double
 {
     /* eps4 = 4*eps*(scale of w)^2: the caller may hand in characteristic variables scaled by a constant (the
      * normalised weights are invariant when beta and epsilon are scaled together) */
-    /* second differences of the four 3-cell sub-stencils, shared by both sides */
-    const double s012 = fma(-2.0, w1, w0 + w2);
-    const double s123 = fma(-2.0, w2, w1 + w3);
-    const double s234 = fma(-2.0, w3, w2 + w4);
-    const double s345 = fma(-2.0, w4, w3 + w5);
+    /* first differences, then the second differences of the four 3-cell sub-stencils (shared by both sides) */
+    const double e01 = w1 - w0, e12 = w2 - w1, e23 = w3 - w2, e34 = w4 - w3, e45 = w5 - w4;
+    const double s012 = e12 - e01, s123 = e23 - e12, s234 = e34 - e23, s345 = e45 - e34;
     /* 4*beta_k + 4*eps = 13/3 s^2 + f^2 + eps4: the s-part of the two middle sub-stencils serves both sides */
     const double q012 = fma((13.0 / 3.0) * s012, s012, eps4);
     const double q123 = fma((13.0 / 3.0) * s123, s123, eps4);
     const double q234 = fma((13.0 / 3.0) * s234, s234, eps4);
     const double q345 = fma((13.0 / 3.0) * s345, s345, eps4);
-    /* minus side (cell 2 is the upwind cell) */
-    const double f0 = fma(3.0, w2, fma(-4.0, w1, w0));
-    const double f1 = w1 - w3;
-    const double f2 = fma(3.0, w2, fma(-4.0, w3, w4));
+    /* minus side (cell 2 is the upwind cell): f0 = w0 - 4 w1 + 3 w2 = s012 + 2 e12, f1 = w1 - w3,
+     * f2 = 3 w2 - 4 w3 + w4 = s234 - 2 e23 */
+    const double f0 = fma(2.0, e12, s012);
+    const double f1 = e12 + e23; /* sign irrelevant: squared */
+    const double f2 = fma(-2.0, e23, s234);
     double b0 = fma(f0, f0, q012);
     double b1 = fma(f1, f1, q123);
     double b2 = fma(f2, f2, q234);
-    /* plus side (cell 3 is the upwind cell), mirrored */
-    const double g0 = fma(3.0, w3, fma(-4.0, w4, w5));
-    const double g2 = fma(3.0, w3, fma(-4.0, w2, w1));
-    const double g1 = w4 - w2;
+    /* plus side (cell 3 is the upwind cell), mirrored: g0 = 3 w3 - 4 w4 + w5 = s345 - 2 e34, g1 = w4 - w2,
+     * g2 = w1 - 4 w2 + 3 w3 = s123 + 2 e23 */
+    const double g0 = fma(-2.0, e34, s345);
+    const double g1 = e23 + e34;
+    const double g2 = fma(2.0, e23, s123);
     double c0 = fma(g0, g0, q345);
     double c1 = fma(g1, g1, q234);
     double c2 = fma(g2, g2, q123);
@@ -219,7 +219,7 @@ HB2_HD void weno5js_pair_fast(double w0, double w1, double w2, double w3, double
      * P0 - P1 = 3/8 (s012 - s123), P2 - P1 = 1/8 (s123 - s234) (mirrored on the plus side), and the central
      * sub-stencil value is P1 = (w2 + w3)/2 - s123/8 (plus side: - s234/8) */
     const double d1 = s012 - s123, d2 = s123 - s234, d3 = s234 - s345;
-    const double h = 0.5 * (w2 + w3);
+    const double h = fma(0.5, e23, w2);
     {
         const double a0 = b1 * b2, a1 = b0 * b2, a2 = b0 * b1;
         const double sum = fma(5.0, a2, fma(10.0, a1, a0));

@@ -7,6 +7,8 @@
  * where s > 0.65 (:2072-2134).  Here a 256-thread block owns a TX x TY tile of cells and MARCHES along z:
  *
  *     A(t)  velocities of plane t      on the tile + halo (2 low, 1 high)  -> 3-plane shared-memory ring
+ *           (density and momentum of plane t+1 are fetched into registers before B(t), so the HBM latency hides behind
+ *           the work on plane t)
  *     B(t)  theta, Omega of plane t-1  on the tile + 1 low halo            -> 2-plane shared-memory ring
  *     C(t)  decisions of plane t-1     bit d = face between cells (c - e_d) and c, one byte per cell  -> HBM
  *
@@ -31,10 +33,12 @@ struct SensorArgs {
 template <class Tr>
 struct SensorShape {
     static constexpr int NT = 256;
-    static constexpr int TX = 64, TY = 8;          /* cells whose decisions the block produces per plane */
-    static constexpr int VX = TX + 3, VY = TY + 3; /* velocity tile: cells i0-2 .. i0+TX */
+    static constexpr int NX = 64, NY = NT / NX;    /* thread layout: tx = tid % 64 along x, ty = tid / 64 */
+    static constexpr int VX = NX, VY = 11;         /* velocity tile: cells i0-2 .. i0+TX, one row of threads wide */
+    static constexpr int TX = VX - 3, TY = VY - 3; /* cells whose decisions the block produces per plane (61 x 8) */
     static constexpr int SX = TX + 1, SY = TY + 1; /* theta/Omega tile: cells i0-1 .. i0+TX-1 */
     static constexpr int VP = VX * VY, SP = SX * SY;
+    static constexpr int KY = (VY + NY - 1) / NY;  /* rows per thread */
     static constexpr int NVP = (Tr::DIM == 3) ? 3 : 1;
     static constexpr int NSP = (Tr::DIM == 3) ? 2 : 1;
     static constexpr int OFF_S = Tr::DIM * NVP * VP;
@@ -50,6 +54,14 @@ struct SensorShape {
 struct SensorTile {
     int i0, j0; /* first cell of the tile */
     int kb, ke; /* planes [kb, ke) of decisions */
+};
+
+/* density and momentum of the cells a thread fetched for the next velocity plane (in flight while the block works on
+ * the current plane) */
+template <class Tr>
+struct SensorRegs {
+    double rho[SensorShape<Tr>::KY];
+    double m[SensorShape<Tr>::KY][Tr::DIM];
 };
 
 template <class Tr>
@@ -69,29 +81,53 @@ HB2_HD SensorTile sensor_tile(const SensorArgs& A, int bx, int by, int bz)
     return T;
 }
 
-/* A: velocities of plane t on the tile + halo.  Exact build: the reference's quotients m/rho. */
-template <class Tr, int MATH>
-HB2_HD void sensor_phase_velocity(const SensorArgs& A, double* smem, const SensorTile& T, int tid, int t)
+/* A1: fetch density and momentum of plane t on the tile + halo into registers */
+template <class Tr>
+HB2_HD void sensor_phase_fetch(const SensorArgs& A, const SensorTile& T, int tid, int t, SensorRegs<Tr>& R)
 {
     using Sh = SensorShape<Tr>;
     constexpr int DIM = Tr::DIM, NM = Tr::NM;
     const Geom& G = A.G;
-    double* sV = smem + Sh::vslot(t) * DIM * Sh::VP;
-    for (int idx = tid; idx < Sh::VP; idx += Sh::NT) {
-        const int li = idx % Sh::VX, lj = idx / Sh::VX;
-        const int i = T.i0 - 2 + li, j = T.j0 - 2 + lj;
-        if (i > G.n[0] + 3 || j > G.n[1] + 3) continue;
+    const int tx = tid % Sh::NX, ty = tid / Sh::NX;
+    const int i = T.i0 - 2 + tx;
+#pragma unroll
+    for (int k = 0; k < Sh::KY; k++) {
+        const int lj = ty + k * Sh::NY;
+        const int j = T.j0 - 2 + lj;
+        R.rho[k] = 1.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) R.m[k][a] = 0.0;
+        if (lj >= Sh::VY || i > G.n[0] + 3 || j > G.n[1] + 3) continue;
         const long long x = cidx(G, i, j, t);
         double rho = A.Q[0][x];
 #pragma unroll
         for (int si = 1; si < NM; si++) rho += A.Q[si][x];
+        R.rho[k] = rho;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) R.m[k][a] = A.Q[NM + a][x];
+    }
+}
+
+/* A2: velocities of plane t into the ring.  Exact build: the reference's quotients m/rho. */
+template <class Tr, int MATH>
+HB2_HD void sensor_phase_velocity(double* smem, int tid, int t, const SensorRegs<Tr>& R)
+{
+    using Sh = SensorShape<Tr>;
+    constexpr int DIM = Tr::DIM;
+    double* sV = smem + Sh::vslot(t) * DIM * Sh::VP;
+    const int tx = tid % Sh::NX, ty = tid / Sh::NX;
+#pragma unroll
+    for (int k = 0; k < Sh::KY; k++) {
+        const int lj = ty + k * Sh::NY;
+        if (lj >= Sh::VY) continue;
+        const int idx = lj * Sh::VX + tx;
         if (MATH == 0) {
 #pragma unroll
-            for (int a = 0; a < DIM; a++) sV[a * Sh::VP + idx] = A.Q[NM + a][x] / rho;
+            for (int a = 0; a < DIM; a++) sV[a * Sh::VP + idx] = R.m[k][a] / R.rho[k];
         } else {
-            const double r = rcp_fast(rho);
+            const double r = rcp_fast(R.rho[k]);
 #pragma unroll
-            for (int a = 0; a < DIM; a++) sV[a * Sh::VP + idx] = A.Q[NM + a][x] * r;
+            for (int a = 0; a < DIM; a++) sV[a * Sh::VP + idx] = R.m[k][a] * r;
         }
     }
 }
@@ -108,10 +144,14 @@ HB2_HD void sensor_phase_gradient(const SensorArgs& A, double* smem, const Senso
     const double* Vp = smem + Sh::vslot(tc + 1) * DIM * Sh::VP;
     double* sS = smem + Sh::OFF_S + Sh::sslot(tc) * 2 * Sh::SP;
     const double hidx[3] = {0.5 / G.dx[0], 0.5 / G.dx[1], 0.5 / G.dx[2]};
-    for (int idx = tid; idx < Sh::SP; idx += Sh::NT) {
-        const int li = idx % Sh::SX, lj = idx / Sh::SX;
-        const int i = T.i0 - 1 + li, j = T.j0 - 1 + lj;
-        if (i > G.n[0] + 1 || j > G.n[1] + 1) continue;
+    const int li = tid % Sh::NX, ty = tid / Sh::NX;
+    const int i = T.i0 - 1 + li;
+    if (li >= Sh::SX || i > G.n[0] + 1) return;
+#pragma unroll
+    for (int k = 0; k < Sh::KY; k++) {
+        const int lj = ty + k * Sh::NY;
+        const int j = T.j0 - 1 + lj;
+        if (lj >= Sh::SY || j > G.n[1] + 1) continue;
         const int vc = (lj + 1) * Sh::VX + (li + 1);
         double grad[DIM][DIM]; /* grad[a][b] = d u_a / d x_b */
 #pragma unroll
@@ -144,6 +184,7 @@ HB2_HD void sensor_phase_gradient(const SensorArgs& A, double* smem, const Senso
             else
                 Omega = sqrt_fast<true>(fma(omega_x, omega_x, fma(omega_y, omega_y, omega_z * omega_z)));
         }
+        const int idx = lj * Sh::SX + li;
         sS[idx] = theta;
         sS[Sh::SP + idx] = Omega;
     }
@@ -166,10 +207,14 @@ HB2_HD void sensor_phase_decision(const SensorArgs& A, const double* smem, const
     const Geom& G = A.G;
     const double* cur = smem + Sh::OFF_S + Sh::sslot(tc) * 2 * Sh::SP;
     const double* prev = smem + Sh::OFF_S + Sh::sslot(tc - 1) * 2 * Sh::SP;
-    for (int idx = tid; idx < Sh::TX * Sh::TY; idx += Sh::NT) {
-        const int li = idx % Sh::TX, lj = idx / Sh::TX;
-        const int i = T.i0 + li, j = T.j0 + lj;
-        if (i > G.n[0] + 1 || j > G.n[1] + 1) continue;
+    const int li = tid % Sh::NX, ty = tid / Sh::NX;
+    const int i = T.i0 + li;
+    if (li >= Sh::TX || i > G.n[0] + 1) return;
+#pragma unroll
+    for (int k = 0; k < Sh::KY; k++) {
+        const int lj = ty + k * Sh::NY;
+        const int j = T.j0 + lj;
+        if (lj >= Sh::TY || j > G.n[1] + 1) continue;
         const int sc = (lj + 1) * Sh::SX + (li + 1);
         const double th = cur[sc], Om = cur[Sh::SP + sc];
         double thl[DIM], Oml[DIM];

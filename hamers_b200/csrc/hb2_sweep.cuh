@@ -32,12 +32,17 @@
  * 128-register limit of two resident blocks, so every extra value held across the face phase can tip into spills):
  *   HB2_PREFETCH_R    1: fetch the running right-hand side of the update phase before the face phase, 0: after it
  *   HB2_PREFETCH_FLAG 1: fetch the sensor byte of the face one iteration ahead, 0: at the start of its face phase
- *     FLAG=0 R=1 : 1.10 / 1.06 / 1.25      FLAG=0 R=0 : 1.10 / 1.11 / 1.26      FLAG=1 R=1 : 1.07 / 1.36 / 1.21 */
+ *     FLAG=0 R=1 : 1.10 / 1.06 / 1.25      FLAG=0 R=0 : 1.10 / 1.11 / 1.26      FLAG=1 R=1 : 1.07 / 1.36 / 1.21
+ * Since the conservative variables of the load phase are staged with cp.async (no register held across the face
+ * phase) FLAG=1 no longer spills and is the default: 0.94 / 0.99 / 1.13.  Staging the sensor byte with cp.async as
+ * well was measured too (0.95 / 1.00 / 1.14) and dropped.  With the spills gone R=0 became the better choice at 512^3
+ * (ms per sweep x / y / z: R=1 6.85 / 7.62 / 8.75, R=0 6.84 / 7.27 / 8.52; the evict-first hints of
+ * HB2_STREAM_HINTS make no difference). */
 #ifndef HB2_PREFETCH_FLAG
 #define HB2_PREFETCH_FLAG 1
 #endif
 #ifndef HB2_PREFETCH_R
-#define HB2_PREFETCH_R 1
+#define HB2_PREFETCH_R 0
 #endif
 
 namespace hb2 {
@@ -85,6 +90,8 @@ struct BlockId {
 /* what one thread needs to know about its pencil */
 struct PencilCtx {
     int tid;         /* thread index inside the block */
+    unsigned sq;     /* device: shared-window address of the thread's first staging slot (set once by the kernel; the
+                        generic -> shared conversion costs an S2R when left inside the loop) */
     int pp;          /* pencil index inside the block */
     int o;           /* position inside the chunk */
     bool valid;      /* pencil exists */
@@ -104,6 +111,7 @@ HB2_HD PencilCtx pencil_ctx(const DirArgs& A, const BlockId& b, int tid)
     PencilCtx c;
     const int lane = tid & 31, w = tid >> 5;
     c.tid = tid;
+    c.sq = 0;
     c.pp = (DIR == 0) ? w : lane;
     c.o = (DIR == 0) ? lane : w;
     c.i = c.j = c.k = 0;
@@ -131,11 +139,10 @@ HB2_HD PencilCtx pencil_ctx(const DirArgs& A, const BlockId& b, int tid)
 }
 
 /* ---- asynchronous global -> shared staging (LDGSTS): 8 bytes per call, completion awaited by the issuing thread ---- */
-HB2_HD void stage_async8(double* dst_smem, const double* src)
+HB2_HD void stage_async8(double* dst_smem, unsigned dst_shared, const double* src)
 {
 #if defined(__CUDA_ARCH__)
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_shared), "l"(src) : "memory");
 #else
     *dst_smem = *src;
 #endif
@@ -153,7 +160,8 @@ HB2_HD void stage_cons(const DirArgs& A, double* smem, const PencilCtx& c, long 
     using Sh = SweepShape<Tr, DIR, MATH>;
     double* sQ = smem + Sh::OFF_Q + c.tid;
 #pragma unroll
-    for (int cix = 0; cix < Tr::NCOMP; cix++) stage_async8(sQ + cix * Sh::NT, A.Q[cix] + x);
+    for (int cix = 0; cix < Tr::NCOMP; cix++)
+        stage_async8(sQ + cix * Sh::NT, c.sq + (unsigned)(cix * Sh::NT * sizeof(double)), A.Q[cix] + x);
 }
 
 template <class Tr, int DIR, int MATH>
@@ -280,7 +288,7 @@ HB2_HD void update_fetch(const DirArgs& A, const PencilCtx& c, int cc, UpdateIn<
     const long long ix = update_index<Tr, DIR>(A, c, cc);
     if (DIR > 0 && A.mode == MODE_FUSED) {
 #pragma unroll
-        for (int e = 0; e < Tr::NEQ; e++) in.R[e] = A.R[e][ix];
+        for (int e = 0; e < Tr::NEQ; e++) in.R[e] = load_stream(A.R[e] + ix);
     }
     in.T = (Tr::ADV && DIR > 0) ? A.T[ix] : 0.0;
 }
@@ -314,7 +322,7 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
 #pragma unroll
         for (int k = 0; k < NTERM; k++)
 #pragma unroll
-            for (int e = 0; e < NEQ; e++) ut[k][e] = A.Ut[k][e][x];
+            for (int e = 0; e < NEQ; e++) ut[k][e] = load_stream(A.Ut[k][e] + x);
     }
 
     /* velocity-divergence contribution of this direction (advective equations of the five-eqn model) */
@@ -397,7 +405,7 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
             rk_update_cell<Tr>(A, c.base + (long long)cc * c.st, ua, rhs);
         } else {
 #pragma unroll
-            for (int e = 0; e < NEQ; e++) A.R[e][ix] = rhs[e];
+            for (int e = 0; e < NEQ; e++) store_stream(A.R[e] + ix, rhs[e]);
         }
     } else if (LAST && Tr::ADV) {
 #pragma unroll

@@ -34,16 +34,24 @@ __global__ void __launch_bounds__(256, 3) k_sensor(const __grid_constant__ Senso
     extern __shared__ double smem[];
     const int tid = (int)threadIdx.x;
     const SensorTile T = sensor_tile<Tr>(A, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
+    SensorRegs<Tr> R;
     if (Tr::DIM == 3) {
-        for (int t = T.kb - 2; t <= T.ke; t++) {
-            sensor_phase_velocity<Tr, MATH>(A, smem, T, tid, t);
+        for (int t = T.kb - 2; t < T.kb; t++) {
+            sensor_phase_fetch<Tr>(A, T, tid, t, R);
+            sensor_phase_velocity<Tr, MATH>(smem, tid, t, R);
+        }
+        sensor_phase_fetch<Tr>(A, T, tid, T.kb, R);
+        for (int t = T.kb; t <= T.ke; t++) {
+            sensor_phase_velocity<Tr, MATH>(smem, tid, t, R);
+            if (t < T.ke) sensor_phase_fetch<Tr>(A, T, tid, t + 1, R);
             __syncthreads();
-            if (t >= T.kb) sensor_phase_gradient<Tr, MATH>(A, smem, T, tid, t - 1);
+            sensor_phase_gradient<Tr, MATH>(A, smem, T, tid, t - 1);
             __syncthreads();
             if (t >= T.kb + 1) sensor_phase_decision<Tr, MATH>(A, smem, T, tid, t - 1);
         }
     } else {
-        sensor_phase_velocity<Tr, MATH>(A, smem, T, tid, 0);
+        sensor_phase_fetch<Tr>(A, T, tid, 0, R);
+        sensor_phase_velocity<Tr, MATH>(smem, tid, 0, R);
         __syncthreads();
         sensor_phase_gradient<Tr, MATH>(A, smem, T, tid, 0);
         __syncthreads();
@@ -61,7 +69,8 @@ __global__ void __launch_bounds__(256, (MATH == 1 && Tr::MODEL == SS) ? HB2_MINB
     using Sh = SweepShape<Tr, DIR, MATH>;
     extern __shared__ double smem[];
     const BlockId b = {(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z};
-    const PencilCtx c = pencil_ctx<Tr, DIR, MATH>(A, b, (int)threadIdx.x);
+    PencilCtx c = pencil_ctx<Tr, DIR, MATH>(A, b, (int)threadIdx.x);
+    c.sq = (unsigned)__cvta_generic_to_shared(smem + Sh::OFF_Q + threadIdx.x);
     const int nsteps = Sh::nsteps(c.c1 - c.c0);
     PipeRegs<Tr> pr;
     pipeline_prologue<Tr, DIR, MATH>(A, smem, c, pr);

@@ -117,14 +117,27 @@ static void run_sweeps(DirArgs A0, int sensor_seg_len, int seg_len, double* cons
                     auto each = [&](auto fn) {
                         for (int n = 0; n < Sh::NT; n++) fn(rev ? Sh::NT - 1 - n : n);
                     };
+                    std::vector<SensorRegs<Tr>> R(Sh::NT);
                     if (Tr::DIM == 3) {
-                        for (int t = T.kb - 2; t <= T.ke; t++) {
-                            each([&](int tid) { sensor_phase_velocity<Tr, MATH>(S, sm.data(), T, tid, t); });
-                            if (t >= T.kb) each([&](int tid) { sensor_phase_gradient<Tr, MATH>(S, sm.data(), T, tid, t - 1); });
+                        for (int t = T.kb - 2; t < T.kb; t++)
+                            each([&](int tid) {
+                                sensor_phase_fetch<Tr>(S, T, tid, t, R[tid]);
+                                sensor_phase_velocity<Tr, MATH>(sm.data(), tid, t, R[tid]);
+                            });
+                        each([&](int tid) { sensor_phase_fetch<Tr>(S, T, tid, T.kb, R[tid]); });
+                        for (int t = T.kb; t <= T.ke; t++) {
+                            each([&](int tid) {
+                                sensor_phase_velocity<Tr, MATH>(sm.data(), tid, t, R[tid]);
+                                if (t < T.ke) sensor_phase_fetch<Tr>(S, T, tid, t + 1, R[tid]);
+                            });
+                            each([&](int tid) { sensor_phase_gradient<Tr, MATH>(S, sm.data(), T, tid, t - 1); });
                             if (t >= T.kb + 1) each([&](int tid) { sensor_phase_decision<Tr, MATH>(S, sm.data(), T, tid, t - 1); });
                         }
                     } else {
-                        each([&](int tid) { sensor_phase_velocity<Tr, MATH>(S, sm.data(), T, tid, 0); });
+                        each([&](int tid) {
+                            sensor_phase_fetch<Tr>(S, T, tid, 0, R[tid]);
+                            sensor_phase_velocity<Tr, MATH>(sm.data(), tid, 0, R[tid]);
+                        });
                         each([&](int tid) { sensor_phase_gradient<Tr, MATH>(S, sm.data(), T, tid, 0); });
                         each([&](int tid) { sensor_phase_decision<Tr, MATH>(S, sm.data(), T, tid, 0); });
                     }
