@@ -619,13 +619,20 @@ int hb2_fused_stage_dev(hb2_plan_t p, int32_t ncoef, const double* alpha, const 
             }
             A.beta = beta[ncoef - 1];
             A.nterm = 0;
-            for (int m = 0; m < ncoef; m++)
+            /* fast build: the flux state (m = ncoef-1) is rebuilt from the primitive ring instead of being loaded */
+            const bool qrec = (p->ops == ops_fast());
+            A.alpha_q = alpha[ncoef - 1];
+            for (int m = 0; m < (qrec ? ncoef - 1 : ncoef); m++)
                 if (alpha[m] != 0.0) {
                     if (A.nterm == HB2_MAXT) return fail(-22, "fused stage supports at most 3 states with alpha != 0");
                     A.alpha_t[A.nterm] = alpha[m];
                     for (int c = 0; c < p->ncomp; c++) A.Ut[A.nterm][c] = U_int[m * p->ncomp + c];
                     A.nterm++;
                 }
+            if (qrec) {
+                if (A.nterm > 2) return fail(-22, "fused stage supports at most 3 states with alpha != 0");
+                A.nterm += HB2_NTERM_QREC;
+            }
             for (int c = 0; c < p->ncomp; c++) A.Uout[c] = U_out[c];
         }
         A.seg_len = p->seg_len[dir];

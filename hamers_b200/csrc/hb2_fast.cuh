@@ -178,6 +178,30 @@ HB2_HD void node_flux_prim(const double* cell, double E_stored, const Consts& K,
     Fn[IP] = un * (E + p);
 }
 
+/* conservative variables of a cell from its PRIMITIVE variables (cell[comp*CS]); E_stored: the stored total energy
+ * (five-eqn: kept in the ring; single-species: rebuilt, p/(gamma-1) + rho |u|^2/2, good to an ulp or two) */
+template <class Tr, int CS>
+HB2_HD void prim_to_cons(const double* cell, double E_stored, const Consts& K, double (&q)[Tr::NEQ])
+{
+    constexpr int DIM = Tr::DIM, NS = Tr::NS, IV = Tr::IV, IP = Tr::IP;
+    double rho = 0.0;
+#pragma unroll
+    for (int si = 0; si < NS; si++) {
+        q[si] = cell[si * CS];
+        rho += q[si];
+    }
+    double ke = 0.0;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) {
+        const double u = cell[(IV + a) * CS];
+        q[IV + a] = rho * u;
+        ke = fma(u, u, ke);
+    }
+    q[IP] = (Tr::MODEL == SS) ? fma(0.5 * rho, ke, cell[IP * CS] * K.inv_gm1[0]) : E_stored;
+#pragma unroll
+    for (int si = 0; si < NS - 1; si++) q[IP + 1 + si] = cell[(IP + 1 + si) * CS];
+}
+
 /* ------------------------------------------------------------------------------------------
  * WCNS5-JS: minus-side and plus-side midpoint values from the six stencil values w0..w5
  * ---------------------------------------------------------------------------------------- */

@@ -316,11 +316,13 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
 
     /* last direction of a fused stage: the states of the RK linear combination (the states with alpha != 0, compacted
      * by the host).  All loads are issued here, before the shared-memory work below, and consumed at the very end. */
-    double ut[NTERM > 0 ? NTERM : 1][NEQ];
-    if (NTERM > 0) {
+    constexpr bool QREC = (NTERM >= HB2_NTERM_QREC);
+    constexpr int NLOAD = QREC ? NTERM - HB2_NTERM_QREC : NTERM;
+    double ut[NLOAD > 0 ? NLOAD : 1][NEQ];
+    if (NLOAD > 0) {
         const long long x = c.base + (long long)cc * c.st;
 #pragma unroll
-        for (int k = 0; k < NTERM; k++)
+        for (int k = 0; k < NLOAD; k++)
 #pragma unroll
             for (int e = 0; e < NEQ; e++) ut[k][e] = load_stream(A.Ut[k][e] + x);
     }
@@ -395,11 +397,15 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
             }
             /* Euler.cpp:1479, 1544-1548: zero; += alpha_n*U_n for alpha_n != 0; += beta*(...) */
             double ua[NEQ];
+            double qc[NEQ];
+            if (QREC) prim_to_cons<Tr, Sh::CSV>(sV + v_0, sV[(Sh::NV - 1) * Sh::CSV + v_0], A.K, qc);
 #pragma unroll
             for (int e = 0; e < NEQ; e++) {
                 double u = 0.0;
 #pragma unroll
-                for (int k = 0; k < NTERM; k++) u += A.alpha_t[k] * ut[k][e];
+                for (int k = 0; k < NLOAD; k++) u += A.alpha_t[k] * ut[k][e];
+                /* the flux state is the newest one: last term of the reference's sum */
+                if (QREC) u = fma(A.alpha_q, qc[e], u);
                 ua[e] = u;
             }
             rk_update_cell<Tr>(A, c.base + (long long)cc * c.st, ua, rhs);

@@ -206,6 +206,11 @@ int launch_dir(const DirArgs& A, cudaStream_t st)
         if (A.nterm == 1) return launch_dir_n<Tr, DIR, 1>(A, st);
         if (A.nterm == 2) return launch_dir_n<Tr, DIR, 2>(A, st);
         if (A.nterm == 3) return launch_dir_n<Tr, DIR, 3>(A, st);
+        if constexpr (MATH == 1) {
+            if (A.nterm == HB2_NTERM_QREC) return launch_dir_n<Tr, DIR, HB2_NTERM_QREC>(A, st);
+            if (A.nterm == HB2_NTERM_QREC + 1) return launch_dir_n<Tr, DIR, HB2_NTERM_QREC + 1>(A, st);
+            if (A.nterm == HB2_NTERM_QREC + 2) return launch_dir_n<Tr, DIR, HB2_NTERM_QREC + 2>(A, st);
+        }
         return (int)cudaErrorInvalidValue;
     }
     return launch_dir_n<Tr, DIR, 0>(A, st);

@@ -86,6 +86,12 @@ static void run_dir(const DirArgs& A)
     if (DIR == Tr::DIM - 1 && A.mode == MODE_FUSED) {
         if (A.nterm == 1) return run_dir_n<Tr, DIR, MATH, 1>(A);
         if (A.nterm == 2) return run_dir_n<Tr, DIR, MATH, 2>(A);
+        if (MATH == 1 && A.nterm >= HB2_NTERM_QREC) {
+            constexpr int Q0 = (MATH == 1) ? HB2_NTERM_QREC : 1;
+            if (A.nterm == HB2_NTERM_QREC) return run_dir_n<Tr, DIR, MATH, Q0>(A);
+            if (A.nterm == HB2_NTERM_QREC + 1) return run_dir_n<Tr, DIR, MATH, Q0 + 1>(A);
+            return run_dir_n<Tr, DIR, MATH, Q0 + 2>(A);
+        }
         return run_dir_n<Tr, DIR, MATH, 3>(A);
     }
     run_dir_n<Tr, DIR, MATH, 0>(A);
@@ -213,12 +219,16 @@ extern "C" int emu_fused_stage(const EmuDesc* d, int ncoef, const double* alpha,
     }
     A.beta = beta[ncoef - 1];
     A.nterm = 0;
-    for (int m = 0; m < ncoef; m++)
+    /* fast build: like hb2_fused_stage_dev, the flux state is rebuilt from the primitive ring */
+    const bool qrec = (d->math == 1);
+    A.alpha_q = alpha[ncoef - 1];
+    for (int m = 0; m < (qrec ? ncoef - 1 : ncoef); m++)
         if (alpha[m] != 0.0) {
             A.alpha_t[A.nterm] = alpha[m];
             for (int c = 0; c < ncomp; c++) A.Ut[A.nterm][c] = U_int[m * ncomp + c];
             A.nterm++;
         }
+    if (qrec) A.nterm += HB2_NTERM_QREC;
     for (int c = 0; c < ncomp; c++) A.Uout[c] = U_out[c];
     EMU_DISPATCH(d, (run_sweeps<Tr, MATH>(A, d->bx, d->seg_len, nullptr, MODE_FUSED)));
     return -1;
