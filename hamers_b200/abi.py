@@ -28,7 +28,9 @@ SYMBOLS = [
     "hb2_cell_ghost_size", "hb2_cell_size", "hb2_side_size", "hb2_plan_create", "hb2_plan_destroy",
     "hb2_plan_set_stream", "hb2_plan_use_own_stream", "hb2_plan_synchronize", "hb2_plan_launch_count", "hb2_plan_workspace_bytes",
     "hb2_compute_flux_and_source_dev", "hb2_advance_stage_dev", "hb2_fused_stage_dev",
-    "hb2_fill_ghosts_periodic_dev", "hb2_pack_box_dev", "hb2_unpack_box_dev", "hb2_max_wave_speed_dev",
+    "hb2_fill_ghosts_periodic_dev", "hb2_pack_box_dev", "hb2_unpack_box_dev", "hb2_pack_boxes_dev", "hb2_unpack_boxes_dev",
+    "hb2_max_wave_speed_dev", "hb2_fused_stage_push_dev", "hb2_device_malloc", "hb2_device_free", "hb2_ipc_export",
+    "hb2_ipc_open", "hb2_ipc_close",
     "hb2_compute_flux_and_source_host", "hb2_fused_stage_host", "hb2_probe_fp64_peak", "hb2_probe_hbm_bandwidth",
     "hb2_plan_set_profiling", "hb2_plan_get_profile", "hb2_advance_level_dev", "hb2_advance_level_host",
 ]
@@ -240,14 +242,27 @@ class Plan:
         _check(self.lib.hb2_compute_flux_and_source_dev(self._h, qp, C.c_double(dt), fp, sp),
                "hb2_compute_flux_and_source_dev")
 
-    def fused_stage(self, alpha, beta, U_int, dt: float, U_out):
-        """computeFluxesAndSourcesOnPatch + advanceSingleStepOnPatch without materialising fluxes."""
+    def fused_stage(self, alpha, beta, U_int, dt: float, U_out, push=None):
+        """computeFluxesAndSourcesOnPatch + advanceSingleStepOnPatch without materialising fluxes.
+        push: optional ctypes table from push_table() -- the ghost fill of the new state fused into the update."""
         ncoef = len(alpha)
         tab = _ptr_table([p for m in range(ncoef) for p in _dev_ptrs(U_int[m], self.ncomp)])
         a = (C.c_double * ncoef)(*[float(x) for x in alpha])
         b = (C.c_double * ncoef)(*[float(x) for x in beta])
-        _check(self.lib.hb2_fused_stage_dev(self._h, ncoef, a, b, tab, C.c_double(dt),
-                                            _ptr_table(_dev_ptrs(U_out, self.ncomp))), "hb2_fused_stage_dev")
+        _check(self.lib.hb2_fused_stage_push_dev(self._h, ncoef, a, b, tab, C.c_double(dt),
+                                                 _ptr_table(_dev_ptrs(U_out, self.ncomp)), push), "hb2_fused_stage_push_dev")
+
+    def push_table(self, base_by_offset):
+        """base_by_offset: {(ox, oy[, oz]): device address of component 0 of the neighbour's U_out} (components are
+        one ghost box apart); missing offsets get NULL entries."""
+        tab = (C.c_void_p * (27 * self.ncomp))()
+        comp_bytes = 8 * int(np.prod(self.ghost_shape))
+        for o, base in base_by_offset.items():
+            o3 = tuple(o) + (0,) * (3 - len(o))
+            code = (o3[0] + 1) + 3 * (o3[1] + 1) + 9 * (o3[2] + 1)
+            for c in range(self.ncomp):
+                tab[code * self.ncomp + c] = int(base) + c * comp_bytes
+        return tab
 
     def advance_stage(self, alpha, beta, U_int, F_int, S_int, U_out, gamma=None, F_acc=None, S_acc=None):
         """Euler::advanceSingleStepOnPatch from materialised fluxes.  F_int[m]: list per direction or None."""
@@ -287,6 +302,28 @@ class Plan:
         _check(self.lib.hb2_unpack_box_dev(self._h, _ptr_table(_dev_ptrs(U, self.ncomp)), l, h,
                                            C.c_void_p(buffer.data_ptr())), "hb2_unpack_box_dev")
 
+    def box_table(self, boxes, offsets):
+        """ctypes tables of a list of (lo, hi) boxes and their buffer offsets (in doubles) for pack_boxes / unpack_boxes."""
+        n = len(boxes)
+        lo = (C.c_int32 * (3 * n))()
+        hi = (C.c_int32 * (3 * n))()
+        for b, (l, h) in enumerate(boxes):
+            for a in range(3):
+                lo[3 * b + a] = int(l[a]) if a < self.dim else 0
+                hi[3 * b + a] = int(h[a]) if a < self.dim else 1
+        off = (C.c_int64 * n)(*[int(o) for o in offsets])
+        return n, lo, hi, off
+
+    def pack_boxes(self, U, table, buffer):
+        n, lo, hi, off = table
+        _check(self.lib.hb2_pack_boxes_dev(self._h, _ptr_table(_dev_ptrs(U, self.ncomp)), n, lo, hi, off,
+                                           C.c_void_p(buffer.data_ptr())), "hb2_pack_boxes_dev")
+
+    def unpack_boxes(self, U, table, buffer):
+        n, lo, hi, off = table
+        _check(self.lib.hb2_unpack_boxes_dev(self._h, _ptr_table(_dev_ptrs(U, self.ncomp)), n, lo, hi, off,
+                                             C.c_void_p(buffer.data_ptr())), "hb2_unpack_boxes_dev")
+
     def max_wave_speed(self, Q, out):
         _check(self.lib.hb2_max_wave_speed_dev(self._h, _ptr_table(_dev_ptrs(Q, self.ncomp)),
                                                C.c_void_p(out.data_ptr())), "hb2_max_wave_speed_dev")
@@ -314,6 +351,49 @@ class Plan:
         _check(self.lib.hb2_fused_stage_host(self._h, ncoef, a, b, tab, C.c_double(dt),
                                              _ptr_table(_host_ptrs(U_out, self.ncomp))), "hb2_fused_stage_host")
         return U_out
+
+
+def device_malloc(nbytes: int) -> int:
+    p = C.c_void_p()
+    _check(load_library().hb2_device_malloc(C.c_int64(int(nbytes)), C.byref(p)), "hb2_device_malloc")
+    return p.value
+
+
+def device_free(ptr: int):
+    _check(load_library().hb2_device_free(C.c_void_p(ptr)), "hb2_device_free")
+
+
+def ipc_export(ptr: int) -> bytes:
+    h = (C.c_uint8 * 64)()
+    _check(load_library().hb2_ipc_export(C.c_void_p(ptr), h), "hb2_ipc_export")
+    return bytes(h)
+
+
+def ipc_open(handle: bytes) -> int:
+    h = (C.c_uint8 * 64)(*handle)
+    p = C.c_void_p()
+    _check(load_library().hb2_ipc_open(h, C.byref(p)), "hb2_ipc_open")
+    return p.value
+
+
+def ipc_close(ptr: int):
+    _check(load_library().hb2_ipc_close(C.c_void_p(ptr)), "hb2_ipc_close")
+
+
+class DeviceArray:
+    """A cudaMalloc'ed float64 array that torch can view (torch.as_tensor(DeviceArray)) and peers can open over IPC."""
+
+    def __init__(self, shape):
+        self.shape = tuple(int(x) for x in shape)
+        self.nbytes = 8 * int(np.prod(self.shape))
+        self.ptr = device_malloc(self.nbytes)
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": "<f8", "data": (self.ptr, False), "version": 3,
+                                         "strides": None}
+
+    def free(self):
+        if self.ptr:
+            device_free(self.ptr)
+            self.ptr = 0
 
 
 def device_count() -> int:

@@ -75,6 +75,13 @@ struct hb2_plan_s {
     long long prof_n[HB2_NUM_KERNEL_KINDS];
     /* intermediate states owned by the plan for hb2_advance_level_* */
     double* lvl[2][HB2_MAXC];
+    /* device copies of push tables (hb2_fused_stage_push_dev), keyed by their host content */
+    struct PushTab {
+        double* host[27 * HB2_MAXC];
+        double** dev;
+    };
+    PushTab pushtab[4];
+    int npushtab;
 };
 
 namespace {
@@ -247,6 +254,38 @@ __global__ void __launch_bounds__(256) k_unpack(const __grid_constant__ Geom G, 
         const int j = (int)((r / B.ext[0]) % B.ext[1]) + B.lo[1];
         const int k = (int)(r / ((long long)B.ext[0] * B.ext[1])) + B.lo[2];
         U.p[q][cidx(G, i, j, k)] = buf[id];
+    }
+}
+
+/* several boxes per launch: element id -> box by a scan of the (<= 32) prefix sums */
+struct MultiBoxArgs {
+    int nbox;
+    int lo[HB2_MAX_BOXES][3], ext[HB2_MAX_BOXES][3];
+    long long first[HB2_MAX_BOXES + 1]; /* first element id of box b in the launch (elements = cells x components) */
+    long long offset[HB2_MAX_BOXES];    /* position of box b in the buffer */
+};
+
+template <bool PACK>
+__global__ void __launch_bounds__(256) k_multibox(const __grid_constant__ Geom G, const __grid_constant__ PtrTab U, int ncomp,
+                                                  const __grid_constant__ MultiBoxArgs B, double* __restrict__ buf)
+{
+    const long long total = B.first[B.nbox];
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total;
+         id += (long long)gridDim.x * blockDim.x) {
+        int b = 0;
+        while (b + 1 < B.nbox && id >= B.first[b + 1]) b++;
+        const long long r0 = id - B.first[b];
+        const long long nb = (long long)B.ext[b][0] * B.ext[b][1] * B.ext[b][2];
+        const int q = (int)(r0 / nb);
+        const long long r = r0 % nb;
+        const int i = (int)(r % B.ext[b][0]) + B.lo[b][0];
+        const int j = (int)((r / B.ext[b][0]) % B.ext[b][1]) + B.lo[b][1];
+        const int k = (int)(r / ((long long)B.ext[b][0] * B.ext[b][1])) + B.lo[b][2];
+        const long long x = cidx(G, i, j, k);
+        if (PACK)
+            buf[B.offset[b] + r0] = U.p[q][x];
+        else
+            U.p[q][x] = buf[B.offset[b] + r0];
     }
 }
 
@@ -514,6 +553,7 @@ int hb2_plan_destroy(hb2_plan_t p)
     for (int q = 0; q < HB2_MAXE; q++) cudaFree(p->stS[q]);
     for (int m = 0; m < 2; m++)
         for (int c = 0; c < HB2_MAXC; c++) cudaFree(p->lvl[m][c]);
+    for (int t = 0; t < 4; t++) cudaFree(p->pushtab[t].dev);
     if (p->prof) {
         for (auto& r : *p->prof) {
             cudaEventDestroy(r.e0);
@@ -586,8 +626,33 @@ int hb2_compute_flux_and_source_dev(hb2_plan_t p, const double* const* Q, double
     return 0;
 }
 
+static int push_table_dev(hb2_plan_t p, double* const* push, double* const** out)
+{
+    const int n = 27 * p->ncomp;
+    for (int t = 0; t < p->npushtab; t++)
+        if (memcmp(p->pushtab[t].host, push, sizeof(double*) * n) == 0) {
+            *out = p->pushtab[t].dev;
+            return 0;
+        }
+    /* a level rotates over three state buffers: a fourth table replaces the oldest */
+    int t = p->npushtab < 4 ? p->npushtab++ : 0;
+    if (!p->pushtab[t].dev) HB2_CUDA(cudaMalloc(&p->pushtab[t].dev, sizeof(double*) * 27 * HB2_MAXC));
+    memcpy(p->pushtab[t].host, push, sizeof(double*) * n);
+    /* synchronous on purpose: the (pageable) source may change right after the call */
+    HB2_CUDA(cudaStreamSynchronize(p->stream));
+    HB2_CUDA(cudaMemcpy(p->pushtab[t].dev, push, sizeof(double*) * n, cudaMemcpyHostToDevice));
+    *out = p->pushtab[t].dev;
+    return 0;
+}
+
 int hb2_fused_stage_dev(hb2_plan_t p, int32_t ncoef, const double* alpha, const double* beta,
                         const double* const* U_int, double dt, double* const* U_out)
+{
+    return hb2_fused_stage_push_dev(p, ncoef, alpha, beta, U_int, dt, U_out, nullptr);
+}
+
+int hb2_fused_stage_push_dev(hb2_plan_t p, int32_t ncoef, const double* alpha, const double* beta,
+                             const double* const* U_int, double dt, double* const* U_out, double* const* push)
 {
     if (!p || !alpha || !beta || !U_int || !U_out) return fail(-1, "null argument");
     if (ncoef < 1 || ncoef > HB2_MAX_STAGES) return fail(-15, "ncoef out of range");
@@ -604,6 +669,11 @@ int hb2_fused_stage_dev(hb2_plan_t p, int32_t ncoef, const double* alpha, const 
     for (int c = 0; c < p->ncomp; c++)
         if ((const double*)U_out[c] == U_int[(ncoef - 1) * p->ncomp + c])
             return fail(-17, "U_out must not alias the state the flux is evaluated on");
+    double* const* push_dev = nullptr;
+    if (push) {
+        rc = push_table_dev(p, push, &push_dev);
+        if (rc) return rc;
+    }
     rc = run_sensor(p, Q);
     if (rc) return rc;
     for (int dir = 0; dir < p->d.dim; dir++) {
@@ -634,6 +704,7 @@ int hb2_fused_stage_dev(hb2_plan_t p, int32_t ncoef, const double* alpha, const 
                 A.nterm += HB2_NTERM_QREC;
             }
             for (int c = 0; c < p->ncomp; c++) A.Uout[c] = U_out[c];
+            A.push = push_dev;
         }
         A.seg_len = p->seg_len[dir];
         int lrc;
@@ -643,6 +714,44 @@ int hb2_fused_stage_dev(hb2_plan_t p, int32_t ncoef, const double* alpha, const 
         }
         if (lrc) return fail(-201, std::string("sweep kernel launch failed: ") + cudaGetErrorString((cudaError_t)lrc));
     }
+    return 0;
+}
+
+int hb2_device_malloc(int64_t bytes, void** ptr)
+{
+    if (!ptr || bytes <= 0) return fail(-1, "bad argument");
+    HB2_CUDA(cudaMalloc(ptr, (size_t)bytes));
+    return 0;
+}
+
+int hb2_device_free(void* ptr)
+{
+    HB2_CUDA(cudaFree(ptr));
+    return 0;
+}
+
+int hb2_ipc_export(const void* ptr, uint8_t handle[HB2_IPC_HANDLE_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == HB2_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!ptr || !handle) return fail(-1, "null argument");
+    cudaIpcMemHandle_t h;
+    HB2_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)));
+    memcpy(handle, &h, sizeof(h));
+    return 0;
+}
+
+int hb2_ipc_open(const uint8_t handle[HB2_IPC_HANDLE_BYTES], void** ptr)
+{
+    if (!ptr || !handle) return fail(-1, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    HB2_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int hb2_ipc_close(void* ptr)
+{
+    HB2_CUDA(cudaIpcCloseMemHandle(ptr));
     return 0;
 }
 
@@ -767,6 +876,52 @@ int hb2_unpack_box_dev(hb2_plan_t p, double* const* U, const int32_t lo[3], cons
     }
     HB2_CUDA(cudaGetLastError());
     return 0;
+}
+
+static int multibox(hb2_plan_t p, double* const* U, int32_t nbox, const int32_t* lo, const int32_t* hi,
+                    const int64_t* offsets, double* buffer, bool pack)
+{
+    if (!p || !U || !lo || !hi || !offsets || !buffer) return fail(-1, "null argument");
+    if (nbox < 1 || nbox > HB2_MAX_BOXES) return fail(-23, "nbox must be in 1..HB2_MAX_BOXES");
+    HB2_CUDA(cudaSetDevice(p->device));
+    MultiBoxArgs M;
+    memset(&M, 0, sizeof(M));
+    M.nbox = nbox;
+    for (int b = 0; b < nbox; b++) {
+        BoxArgs B;
+        int rc = box_args(p, lo + 3 * b, hi + 3 * b, &B);
+        if (rc) return rc;
+        for (int a = 0; a < 3; a++) {
+            M.lo[b][a] = B.lo[a];
+            M.ext[b][a] = B.ext[a];
+        }
+        M.first[b + 1] = M.first[b] + (long long)B.ext[0] * B.ext[1] * B.ext[2] * p->ncomp;
+        M.offset[b] = offsets[b];
+    }
+    PtrTab t;
+    memset(&t, 0, sizeof(t));
+    for (int c = 0; c < p->ncomp; c++) t.p[c] = U[c];
+    {
+        ProfScope ps(p, pack ? 6 : 7);
+        if (pack)
+            k_multibox<true><<<grid_for(M.first[nbox], 256), 256, 0, p->stream>>>(p->G, t, p->ncomp, M, buffer);
+        else
+            k_multibox<false><<<grid_for(M.first[nbox], 256), 256, 0, p->stream>>>(p->G, t, p->ncomp, M, buffer);
+    }
+    HB2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int hb2_pack_boxes_dev(hb2_plan_t p, const double* const* U, int32_t nbox, const int32_t* lo, const int32_t* hi,
+                       const int64_t* offsets, double* buffer)
+{
+    return multibox(p, const_cast<double* const*>(reinterpret_cast<const double* const*>(U)), nbox, lo, hi, offsets, buffer, true);
+}
+
+int hb2_unpack_boxes_dev(hb2_plan_t p, double* const* U, int32_t nbox, const int32_t* lo, const int32_t* hi,
+                         const int64_t* offsets, const double* buffer)
+{
+    return multibox(p, U, nbox, lo, hi, offsets, const_cast<double*>(buffer), false);
 }
 
 int hb2_max_wave_speed_dev(hb2_plan_t p, const double* const* Q, double* out_dev)

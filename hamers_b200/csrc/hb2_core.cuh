@@ -99,6 +99,12 @@ struct DirArgs {
     double* Uout[HB2_MAXC];
     int seg_len;               /* cells per marching segment along the sweep axis */
     double alpha_q;            /* fast build, FUSED, last direction: coefficient of the flux state (see HB2_NTERM_QREC) */
+    /* FUSED, last direction: ghost fill fused into the update.  push[code * NCOMP + comp], code = (ox+1) + 3 (oy+1) +
+     * 9 (oz+1), is the address of component `comp` of U_out ON THE PATCH AT OFFSET o (a peer GPU's memory mapped over
+     * NVLink, or this patch itself where it is its own periodic neighbour); a cell within the ghost width of a face
+     * is also stored into the ghost box of every neighbour that needs it.  NULL table: no push; NULL entry: no
+     * neighbour there.  The table lives in device memory. */
+    double* const* push;
 };
 /* Fast build: nterm = HB2_NTERM_QREC + k means "k states in Ut are loaded from HBM and the flux state itself enters
  * the RK combination with alpha_q, rebuilt from the primitive-variable ring" -- 40 B/cell less HBM traffic in the last
@@ -603,11 +609,50 @@ HB2_HD void load_cons(const DirArgs& A, long long x, double (&q)[Tr::NCOMP])
 
 /* RK update of one interior cell from the complete right-hand side (FUSED, last direction).
  * Order of Euler.cpp:1479, 1544-1548: zero; += alpha_n*U_n for alpha_n != 0; += beta*(...). */
+/* Same-level ghost fill (xfer::RefineSchedule::fillData, RungeKuttaLevelIntegrator.cpp:1568/1701) fused into the
+ * producer: the new values of a cell within the ghost width of a patch face go straight into the ghost cells of the
+ * neighbouring patches (all equal-sized boxes of a regular decomposition; neighbour at offset o sees my cell c at
+ * c - o * n). */
+/* table: the push addresses (DirArgs::push), staged in shared memory by the kernel (a cell near an x face is 4
+ * lanes of a warp: the dependent global loads of the table made the whole warp wait, +17 % on the last sweep at 256^3) */
 template <class Tr>
-HB2_HD void rk_update_cell(const DirArgs& A, long long x, const double (&ua)[Tr::NEQ], const double (&rhs)[Tr::NEQ])
+HB2_HD void push_cell(const Geom& G, double* const* table, int ci, int cj, int ck, const double (&v)[Tr::NCOMP])
+{
+    constexpr int DIM = Tr::DIM, NCOMP = Tr::NCOMP;
+    const int c[3] = {ci, cj, ck};
+    bool lo[3], hi[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        lo[a] = (a < DIM) && c[a] < HB2_G;
+        hi[a] = (a < DIM) && c[a] >= G.n[a] - HB2_G;
+    }
+    for (int oz = (lo[2] ? -1 : 0); oz <= (hi[2] ? 1 : 0); oz++)
+        for (int oy = (lo[1] ? -1 : 0); oy <= (hi[1] ? 1 : 0); oy++)
+            for (int ox = (lo[0] ? -1 : 0); ox <= (hi[0] ? 1 : 0); ox++) {
+                if (!(ox | oy | oz)) continue;
+                double* const* T = table + ((ox + 1) + 3 * (oy + 1) + 9 * (oz + 1)) * NCOMP;
+                if (!T[0]) continue;
+                const long long x = cidx(G, ci - ox * G.n[0], cj - oy * G.n[1], ck - oz * G.n[2]);
+#pragma unroll
+                for (int q = 0; q < NCOMP; q++) T[q][x] = v[q];
+            }
+}
+
+/* true for cells within the ghost width of a patch face */
+template <class Tr>
+HB2_HD bool near_face(const Geom& G, int ci, int cj, int ck)
+{
+    bool near = (unsigned)(ci - HB2_G) >= (unsigned)(G.n[0] - 2 * HB2_G) || (unsigned)(cj - HB2_G) >= (unsigned)(G.n[1] - 2 * HB2_G);
+    if (Tr::DIM == 3) near = near || (unsigned)(ck - HB2_G) >= (unsigned)(G.n[2] - 2 * HB2_G);
+    return near;
+}
+
+template <class Tr>
+HB2_HD void rk_update_cell(const DirArgs& A, double* const* push_table, long long x, int ci, int cj, int ck,
+                           const double (&ua)[Tr::NEQ], const double (&rhs)[Tr::NEQ])
 {
     constexpr int NEQ = Tr::NEQ, NS = Tr::NS, DIM = Tr::DIM;
-    double Unew[NEQ];
+    double Unew[Tr::NCOMP];
 #pragma unroll
     for (int e = 0; e < NEQ; e++) {
         double u = ua[e]; /* sum_n alpha_n U_n, accumulated in the reference's order by the caller */
@@ -620,7 +665,9 @@ HB2_HD void rk_update_cell(const DirArgs& A, long long x, const double (&ua)[Tr:
 #pragma unroll
         for (int si = 0; si < NS - 1; si++) zl -= Unew[NS + DIM + 1 + si];
         A.Uout[NEQ][x] = zl;
+        Unew[Tr::NCOMP - 1] = zl;
     }
+    if (A.push && near_face<Tr>(A.G, ci, cj, ck)) push_cell<Tr>(A.G, push_table, ci, cj, ck, Unew);
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -76,7 +76,9 @@ struct SweepShape {
      * iteration ago, [component][thread]; every thread reads back only its own slots, so no barrier is involved and no
      * register is held across the face phase */
     static constexpr int OFF_Q = OFF_M + NMID * CS;
-    static constexpr int SMEM_DOUBLES = OFF_Q + Tr::NCOMP * NT;
+    /* the push addresses of the fused ghost fill (DirArgs::push), 27 neighbours x components */
+    static constexpr int OFF_P = OFF_Q + Tr::NCOMP * NT;
+    static constexpr int SMEM_DOUBLES = OFF_P + 27 * Tr::NCOMP;
     HB2_HD static int slot(int pp, int s) { return (DIR == 0) ? pp * RING + (s & (RING - 1)) : (s & (RING - 1)) * 32 + pp; }
     /* primitive-variable ring: r = ring position in [0, RINGV) */
     HB2_HD static int slotv(int pp, int r) { return (DIR == 0) ? pp * RINGV + r : r * 32 + pp; }
@@ -408,7 +410,8 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
                 if (QREC) u = fma(A.alpha_q, qc[e], u);
                 ua[e] = u;
             }
-            rk_update_cell<Tr>(A, c.base + (long long)cc * c.st, ua, rhs);
+            rk_update_cell<Tr>(A, reinterpret_cast<double* const*>(smem + Sh::OFF_P), c.base + (long long)cc * c.st, ci, cj,
+                               ck, ua, rhs);
         } else {
 #pragma unroll
             for (int e = 0; e < NEQ; e++) store_stream(A.R[e] + ix, rhs[e]);
@@ -437,6 +440,11 @@ struct PipeRegs {
 template <class Tr, int DIR, int MATH>
 HB2_HD void pipeline_prologue(const DirArgs& A, double* smem, const PencilCtx& c, PipeRegs<Tr>& pr)
 {
+    using Sh = SweepShape<Tr, DIR, MATH>;
+    if (DIR == Tr::DIM - 1 && A.push) {
+        double** sP = reinterpret_cast<double**>(smem + Sh::OFF_P);
+        for (int n = c.tid; n < 27 * Tr::NCOMP; n += Sh::NT) sP[n] = A.push[n];
+    }
     int s;
     if (load_wanted<Tr, DIR, MATH>(c, 0, s)) {
         double q[Tr::NCOMP];

@@ -130,6 +130,26 @@ int hb2_advance_stage_dev(hb2_plan_t plan, int32_t ncoef,
 int hb2_fused_stage_dev(hb2_plan_t plan, int32_t ncoef, const double* alpha, const double* beta,
                         const double* const* U_int, double dt, double* const* U_out);
 
+/* hb2_fused_stage_dev with the same-level ghost fill of the NEW state (what the next stage's
+ * xfer::RefineSchedule::fillData would do, RungeKuttaLevelIntegrator.cpp:1568/1701) fused into the update: every new
+ * cell value within the ghost width of a patch face is also stored into the ghost box of each neighbouring patch.
+ * push: 27 * ncomp device addresses, push[code * ncomp + c] with code = (ox+1) + 3 (oy+1) + 9 (oz+1) = component c of
+ * U_out of the equal-sized patch at offset (ox,oy,oz) -- memory of a peer GPU opened with hb2_ipc_open (stores
+ * travel over NVLink) or this patch's own U_out where the level is periodic over a single patch; NULL entries: no
+ * neighbour.  The caller orders stages across GPUs (one barrier between a stage and the next). */
+int hb2_fused_stage_push_dev(hb2_plan_t plan, int32_t ncoef, const double* alpha, const double* beta,
+                             const double* const* U_int, double dt, double* const* U_out,
+                             double* const* push);
+
+/* Device memory that can be shared between the one-process-per-GPU ranks of a box (CUDA IPC): allocate, export
+ * a 64-byte handle, open a peer's handle, close it. */
+#define HB2_IPC_HANDLE_BYTES 64
+int hb2_device_malloc(int64_t bytes, void** ptr);
+int hb2_device_free(void* ptr);
+int hb2_ipc_export(const void* ptr, uint8_t handle[HB2_IPC_HANDLE_BYTES]);
+int hb2_ipc_open(const uint8_t handle[HB2_IPC_HANDLE_BYTES], void** ptr);
+int hb2_ipc_close(void* ptr);
+
 /* Same-level periodic ghost fill of one patch that covers the whole periodic level in the
  * directions flagged in periodic_mask (bit d).  All 4-cell ghosts incl. edges and corners. */
 int hb2_fill_ghosts_periodic_dev(hb2_plan_t plan, double* const* U, int32_t periodic_mask);
@@ -148,6 +168,15 @@ int hb2_pack_box_dev(hb2_plan_t plan, const double* const* U, const int32_t lo[3
                      const int32_t hi[3], double* buffer);
 int hb2_unpack_box_dev(hb2_plan_t plan, double* const* U, const int32_t lo[3],
                        const int32_t hi[3], const double* buffer);
+
+/* The same for up to HB2_MAX_BOXES boxes in ONE launch (what one same-level ghost fill of
+ * xfer::RefineSchedule::fillData, RungeKuttaLevelIntegrator.cpp:1568/1701, moves between a patch and its up to 26
+ * neighbours): box b = [lo + 3b, hi + 3b) is copied to / from buffer + offsets[b] (offsets in doubles). */
+#define HB2_MAX_BOXES 32
+int hb2_pack_boxes_dev(hb2_plan_t plan, const double* const* U, int32_t nbox, const int32_t* lo,
+                       const int32_t* hi, const int64_t* offsets, double* buffer);
+int hb2_unpack_boxes_dev(hb2_plan_t plan, double* const* U, int32_t nbox, const int32_t* lo,
+                         const int32_t* hi, const int64_t* offsets, const double* buffer);
 
 /* Euler::computeSpectralRadiusesAndStableDtOnPatch building block:
  * max over the interior of (|u_d| + c)/dx_d per direction, result in out_dev[0..dim-1]. */

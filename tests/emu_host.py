@@ -67,7 +67,7 @@ def flux_and_source(desc, Q, dt, math=0, bx=0, seg_len=0, source=None):
     return F, S
 
 
-def fused_stage(desc, alpha, beta, U_int, dt, math=0, bx=0, seg_len=0):
+def fused_stage(desc, alpha, beta, U_int, dt, math=0, bx=0, seg_len=0, push=False):
     ncoef = len(alpha)
     U_out = np.zeros((desc.ncomp,) + desc.ghost_shape)
     d = _desc(desc, math, bx, seg_len)
@@ -75,6 +75,7 @@ def fused_stage(desc, alpha, beta, U_int, dt, math=0, bx=0, seg_len=0):
     tab = _pp([Us[m][c] for m in range(ncoef) for c in range(desc.ncomp)])
     a = (C.c_double * ncoef)(*[float(x) for x in alpha])
     b = (C.c_double * ncoef)(*[float(x) for x in beta])
-    rc = lib().emu_fused_stage(C.byref(d), ncoef, a, b, tab, C.c_double(dt), _pp([U_out[c] for c in range(desc.ncomp)]))
+    rc = lib().emu_fused_stage_push(C.byref(d), ncoef, a, b, tab, C.c_double(dt), _pp([U_out[c] for c in range(desc.ncomp)]),
+                                    1 if push else 0)
     assert rc == 0
     return U_out

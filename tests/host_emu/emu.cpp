@@ -202,8 +202,18 @@ extern "C" int emu_flux_and_source(const EmuDesc* d, const double* const* Q, dou
     return -1;
 }
 
+extern "C" int emu_fused_stage_push(const EmuDesc* d, int ncoef, const double* alpha, const double* beta,
+                                    const double* const* U_int, double dt, double* const* U_out, int push);
+
 extern "C" int emu_fused_stage(const EmuDesc* d, int ncoef, const double* alpha, const double* beta,
                                const double* const* U_int, double dt, double* const* U_out)
+{
+    return emu_fused_stage_push(d, ncoef, alpha, beta, U_int, dt, U_out, 0);
+}
+
+/* push != 0: the patch is its own periodic neighbour in every direction (self-push table, like a one-box level) */
+extern "C" int emu_fused_stage_push(const EmuDesc* d, int ncoef, const double* alpha, const double* beta,
+                                    const double* const* U_int, double dt, double* const* U_out, int push)
 {
     const int ncomp = d->model == SS ? d->dim + 2 : d->dim + 2 * d->ns + 1;
     const int neq = d->model == SS ? d->dim + 2 : d->dim + 2 * d->ns;
@@ -230,6 +240,17 @@ extern "C" int emu_fused_stage(const EmuDesc* d, int ncoef, const double* alpha,
         }
     if (qrec) A.nterm += HB2_NTERM_QREC;
     for (int c = 0; c < ncomp; c++) A.Uout[c] = U_out[c];
+    std::vector<double*> table(27 * ncomp, nullptr);
+    if (push) {
+        for (int oz = (d->dim == 3 ? -1 : 0); oz <= (d->dim == 3 ? 1 : 0); oz++)
+            for (int oy = -1; oy <= 1; oy++)
+                for (int ox = -1; ox <= 1; ox++) {
+                    if (!(ox | oy | oz)) continue;
+                    const int code = (ox + 1) + 3 * (oy + 1) + 9 * (oz + 1);
+                    for (int c = 0; c < ncomp; c++) table[code * ncomp + c] = U_out[c];
+                }
+        A.push = table.data();
+    }
     EMU_DISPATCH(d, (run_sweeps<Tr, MATH>(A, d->bx, d->seg_len, nullptr, MODE_FUSED)));
     return -1;
 }

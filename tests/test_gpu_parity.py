@@ -184,6 +184,49 @@ def test_periodic_fill_and_pack_unpack(name, product_lib):
     plan.close()
 
 
+def test_pack_unpack_many_boxes(product_lib):
+    """hb2_pack_boxes_dev / hb2_unpack_boxes_dev: several boxes (interior slabs, ghost regions, an edge bar) in one
+    launch, at arbitrary positions of one buffer."""
+    import torch
+    from hamers_b200 import problems as pb
+
+    desc, U = make_case("ss3d", "random")
+    plan = _plan(desc, 0)
+    ref = pb.pad_periodic(U)
+    Wd = _to_dev(ref)
+    n = desc.n
+    boxes = [((0, 0, 0), (4, n[1], n[2])), ((n[0] - 4, 0, 0), (n[0], n[1], n[2])), ((-4, -4, 0), (0, 0, n[2])),
+             ((0, n[1], n[2]), (n[0], n[1] + 4, n[2] + 4)), ((5, 3, 1), (6, 4, 2))]
+    sizes = [desc.ncomp * int(np.prod([h - l for l, h in zip(lo, hi)])) for lo, hi in boxes]
+    # deliberately not back to back
+    offsets, pos = [], 7
+    for sz in sizes:
+        offsets.append(pos)
+        pos += sz + 3
+    buf = torch.full((pos,), -1.0, dtype=torch.float64, device="cuda")
+    table = plan.box_table(boxes, offsets)
+    plan.pack_boxes(Wd, table, buf)
+    torch.cuda.synchronize()
+    b = buf.cpu().numpy()
+    mask = np.ones(pos, dtype=bool)
+    for (lo, hi), off, sz in zip(boxes, offsets, sizes):
+        box = tuple(slice(l + 4, h + 4) for l, h in reversed(list(zip(lo, hi))))
+        expect = ref[(slice(None),) + box]
+        assert np.array_equal(b[off:off + sz].reshape(expect.shape), expect)
+        mask[off:off + sz] = False
+    assert (b[mask] == -1.0).all()
+    Z = torch.zeros_like(Wd)
+    plan.unpack_boxes(Z, table, buf)
+    torch.cuda.synchronize()
+    z = Z.cpu().numpy()
+    for lo, hi in boxes:
+        box = (slice(None),) + tuple(slice(l + 4, h + 4) for l, h in reversed(list(zip(lo, hi))))
+        assert np.array_equal(z[box], ref[box])
+        z[box] = 0.0
+    assert not z.any()
+    plan.close()
+
+
 def test_error_behaviour(product_lib):
     """Error convention: non-zero return + message (the C++ wrapper maps it to TBOX_ERROR)."""
     import torch

@@ -86,3 +86,16 @@ def test_emulated_ring_wraparound(model, dim, N, seg_len, oracle_lib):
             assert np.array_equal(interior(desc, Ue), interior(desc, Uo))
         else:
             assert_fast_parity(interior(desc, Ue), interior(desc, Uo))
+
+
+@pytest.mark.parametrize("name", ["ss2d", "ss3d", "fe3d"])
+def test_emulated_push_fills_the_ghosts(name, oracle_lib):
+    """Ghost fill fused into the update (push_cell): with the patch as its own periodic neighbour every ghost cell of
+    the new state -- faces, edges, corners -- must be the periodic image of the new interior, and the interior must
+    be what the stage without push produces."""
+    desc, U = make_case(name, "random")
+    Q = pb.pad_periodic(U)
+    plain = emu_host.fused_stage(desc, [1.0], [1.0], [Q], 5.0e-4, math=0)
+    pushed = emu_host.fused_stage(desc, [1.0], [1.0], [Q], 5.0e-4, math=0, push=True)
+    assert np.array_equal(interior(desc, pushed), interior(desc, plain))
+    assert np.array_equal(pushed, pb.pad_periodic(np.ascontiguousarray(interior(desc, pushed))))

@@ -8,7 +8,7 @@ import socket
 import numpy as np
 import pytest
 
-from hamers_b200.level import BoxDecomposition, exchange_halos
+from hamers_b200.level import BoxDecomposition, exchange_halos, exchange_halos_oneshot, oneshot_schedule
 
 G = 4
 
@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, dim, N, ncomp, q):
+def _worker(rank, world, port, dim, N, ncomp, q, oneshot=False):
     import torch
     import torch.distributed as dist
 
@@ -67,7 +67,20 @@ def _worker(rank, world, port, dim, N, ncomp, q):
                 bufs[key] = torch.empty(numel, dtype=torch.float64)
             return bufs[key]
 
-        exchange_halos(dec.halo_schedule(), ncomp, pack, unpack, fill_local, new_buffer, dist)
+        if oneshot:
+            def pack_many(boxes, offsets, buf):
+                for (lo, hi), off in zip(boxes, offsets):
+                    v = np.ascontiguousarray(U[region(lo, hi)]).reshape(-1)
+                    buf[off:off + v.size].copy_(torch.from_numpy(v))
+
+            def unpack_many(boxes, offsets, buf):
+                for (lo, hi), off in zip(boxes, offsets):
+                    shp = U[region(lo, hi)].shape
+                    U[region(lo, hi)] = buf[off:off + int(np.prod(shp))].numpy().reshape(shp)
+
+            exchange_halos_oneshot(oneshot_schedule(dec, ncomp), ncomp, pack_many, unpack_many, fill_local, new_buffer, dist)
+        else:
+            exchange_halos(dec.halo_schedule(), ncomp, pack, unpack, fill_local, new_buffer, dist)
         # expected: periodic image of the global array
         idx = [np.arange(dec.lo[a] - G, dec.lo[a] + n[a] + G) % N[a] for a in range(dim)]
         expect = full[(slice(None),) + np.ix_(*reversed(idx))]
@@ -77,14 +90,15 @@ def _worker(rank, world, port, dim, N, ncomp, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("oneshot", [False, True])
 @pytest.mark.parametrize("dim,N,world", [(3, (16, 12, 8), 2), (2, (16, 24), 2), (3, (16, 16, 8), 4)])
-def test_halo_exchange_gloo(dim, N, world):
+def test_halo_exchange_gloo(dim, N, world, oneshot):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, dim, N, 3, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, dim, N, 3, q, oneshot)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(world)]
@@ -92,6 +106,18 @@ def test_halo_exchange_gloo(dim, N, world):
         p.join(timeout=60)
     for rank, ok, nans in res:
         assert ok, f"rank {rank}: ghost box differs from the periodic image ({nans} cells never filled)"
+
+
+def test_oneshot_schedule_matches_between_ranks():
+    """What rank A packs for rank B is, box by box, what B expects from A (NCCL matches messages by order only)."""
+    for dim, N, world in ((3, (16, 16, 16), 8), (3, (16, 16, 8), 4), (2, (16, 24), 2), (2, (32, 16), 8)):
+        sched = [oneshot_schedule(BoxDecomposition(dim, N, world, r), 5) for r in range(world)]
+        for a in range(world):
+            for t in sched[a][0]:
+                back = [u for u in sched[t.peer][1] if u.peer == a]
+                assert len(back) == 1 and back[0].numel == t.numel
+                assert [tuple(h - l for l, h in zip(lo, hi)) for lo, hi in t.boxes] == \
+                       [tuple(h - l for l, h in zip(lo, hi)) for lo, hi in back[0].boxes]
 
 
 def test_decomposition_covers_level_once():
