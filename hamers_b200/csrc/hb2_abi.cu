@@ -295,7 +295,7 @@ template <class Tr>
 __global__ void __launch_bounds__(256) k_wave_speed(const __grid_constant__ Geom G, const __grid_constant__ CPtrTab U,
                                                     const __grid_constant__ Consts K, unsigned long long* out)
 {
-    double m[3] = {0.0, 0.0, 0.0};
+    double m[4] = {0.0, 0.0, 0.0, 0.0};
     const long long ncell = (long long)G.n[0] * G.n[1] * G.n[2];
     for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < ncell;
          id += (long long)gridDim.x * blockDim.x) {
@@ -308,10 +308,17 @@ __global__ void __launch_bounds__(256) k_wave_speed(const __grid_constant__ Geom
         for (int cix = 0; cix < Tr::NCOMP; cix++) q[cix] = U.p[cix][x];
         cons_to_prim<Tr>(q, K, V, c);
 #pragma unroll
-        for (int a = 0; a < Tr::DIM; a++) m[a] = fmax(m[a], (fabs(V[Tr::IV + a]) + c) / G.dx[a]);
+        double sum = 0.0;
+#pragma unroll
+        for (int a = 0; a < Tr::DIM; a++) {
+            const double sr = (fabs(V[Tr::IV + a]) + c) / G.dx[a];
+            m[a] = fmax(m[a], sr);
+            sum = (a == 0) ? sr : sum + sr;
+        }
+        m[3] = fmax(m[3], sum);
     }
 #pragma unroll
-    for (int a = 0; a < Tr::DIM; a++) {
+    for (int a = 0; a < 4; a++) {
         double v = m[a];
         for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
         if ((threadIdx.x & 31) == 0) atomicMax(out + a, (unsigned long long)__double_as_longlong(v));
@@ -931,7 +938,7 @@ int hb2_max_wave_speed_dev(hb2_plan_t p, const double* const* Q, double* out_dev
     CPtrTab t;
     memset(&t, 0, sizeof(t));
     for (int c = 0; c < p->ncomp; c++) t.p[c] = Q[c];
-    HB2_CUDA(cudaMemsetAsync(out_dev, 0, 3 * sizeof(double), p->stream));
+    HB2_CUDA(cudaMemsetAsync(out_dev, 0, 4 * sizeof(double), p->stream));
     const int grid = grid_for(p->ncell_i, 256, 8);
     unsigned long long* o = (unsigned long long*)out_dev;
     if (p->cfg.model == SS && p->cfg.dim == 2) k_wave_speed<Traits<SS, 2, 1>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);

@@ -110,6 +110,9 @@ struct DirArgs {
  * the RK combination with alpha_q, rebuilt from the primitive-variable ring" -- 40 B/cell less HBM traffic in the last
  * sweep of every stage (measured: every 5 doubles per cell loaded in a sweep cost it ~1.3 ms at 512^3). */
 #define HB2_NTERM_QREC 4
+/* NTERM of a launch that materialises the side fluxes (MODE_EMIT): the mode is a compile-time property of the kernel so
+ * that neither variant carries the other's code (the sweeps sit at ~30 KB of instructions). */
+#define HB2_NTERM_EMIT (-1)
 
 HB2_HD long long cidx(const Geom& G, int i, int j, int k)
 {

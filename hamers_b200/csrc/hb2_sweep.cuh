@@ -284,11 +284,11 @@ HB2_HD long long update_index(const DirArgs& A, const PencilCtx& c, int cc)
     return c.ibase + (long long)cc * c.ist;
 }
 
-template <class Tr, int DIR>
+template <class Tr, int DIR, bool FUSED>
 HB2_HD void update_fetch(const DirArgs& A, const PencilCtx& c, int cc, UpdateIn<Tr>& in)
 {
     const long long ix = update_index<Tr, DIR>(A, c, cc);
-    if (DIR > 0 && A.mode == MODE_FUSED) {
+    if (DIR > 0 && FUSED) {
 #pragma unroll
         for (int e = 0; e < Tr::NEQ; e++) in.R[e] = load_stream(A.R[e] + ix);
     }
@@ -311,7 +311,7 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
     /* the same cells in the primitive-variable ring (primary copies) */
     const int v_m1 = Sh::slotv(c.pp, (cc - 1) & (Sh::RING - 1)), v_0 = Sh::slotv(c.pp, cc & (Sh::RING - 1)),
               v_p1 = Sh::slotv(c.pp, (cc + 1) & (Sh::RING - 1));
-    const bool fused = (A.mode == MODE_FUSED);
+    constexpr bool fused = (NTERM != HB2_NTERM_EMIT);
     const double dxd = G.dx[DIR];
     const int ci = (DIR == 0) ? cc : c.i, cj = (DIR == 1) ? cc : c.j, ck = (DIR == 2) ? cc : c.k;
     const long long ix = c.ibase + (long long)cc * c.ist;
@@ -470,7 +470,8 @@ HB2_HD void pipeline_iteration(const DirArgs& A, double* smem, const PencilCtx& 
     int cc;
     const bool do_update = update_wanted<Tr, DIR, MATH>(c, t - 1, cc);
     UpdateIn<Tr> uin;
-    if (HB2_PREFETCH_R && do_update) update_fetch<Tr, DIR>(A, c, cc, uin);
+    constexpr bool FUSED = (NTERM != HB2_NTERM_EMIT);
+    if (HB2_PREFETCH_R && do_update) update_fetch<Tr, DIR, FUSED>(A, c, cc, uin);
     unsigned int flag;
     if (HB2_PREFETCH_FLAG) {
         flag = pr.flag;
@@ -479,7 +480,7 @@ HB2_HD void pipeline_iteration(const DirArgs& A, double* smem, const PencilCtx& 
         flag = (t < nsteps) ? face_flag_fetch<Tr, DIR, MATH>(A, c, t) : 0u;
     }
     if (t < nsteps) phase_face<Tr, DIR, MATH>(A, smem, c, t, flag);
-    if (!HB2_PREFETCH_R && do_update) update_fetch<Tr, DIR>(A, c, cc, uin);
+    if (!HB2_PREFETCH_R && do_update) update_fetch<Tr, DIR, FUSED>(A, c, cc, uin);
     if (do_update) phase_update<Tr, DIR, MATH, NTERM>(A, smem, c, cc, uin);
 }
 

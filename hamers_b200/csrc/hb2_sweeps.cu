@@ -201,8 +201,9 @@ int launch_dir_n(const DirArgs& A, cudaStream_t st)
 template <class Tr, int DIR>
 int launch_dir(const DirArgs& A, cudaStream_t st)
 {
+    if (A.mode == MODE_EMIT) return launch_dir_n<Tr, DIR, HB2_NTERM_EMIT>(A, st);
     /* the RK linear combination exists only in the last direction of a fused stage */
-    if (DIR == Tr::DIM - 1 && A.mode == MODE_FUSED) {
+    if (DIR == Tr::DIM - 1) {
         if (A.nterm == 1) return launch_dir_n<Tr, DIR, 1>(A, st);
         if (A.nterm == 2) return launch_dir_n<Tr, DIR, 2>(A, st);
         if (A.nterm == 3) return launch_dir_n<Tr, DIR, 3>(A, st);

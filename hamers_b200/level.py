@@ -372,6 +372,18 @@ class UniformLevel:
         self.ghosts_valid = True
         self.time += dt
 
+    def stable_dt(self, cfl: float = 1.0) -> float:
+        """Level-wide stable time step: Euler::computeSpectralRadiusesAndStableDtOnPatch per box, then the MAX
+        all-reduce of RungeKuttaLevelIntegrator::getLevelDt (RungeKuttaLevelIntegrator.cpp:1786-1928) over ranks."""
+        torch = self.torch
+        if not hasattr(self, "_sr"):
+            self._sr = torch.zeros(4, dtype=torch.float64, device="cuda")
+        self.plan.max_wave_speed(self.S[self.cur], self._sr)
+        if self.dist is not None:
+            self.dist.all_reduce(self._sr, op=self.dist.ReduceOp.MAX)
+        self.spectral_radii = self._sr.cpu().numpy().copy()
+        return cfl / float(self.spectral_radii[3])
+
     def advance(self, dt: float, nsteps: int):
         for _ in range(nsteps):
             self.rk_step(dt)

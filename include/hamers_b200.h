@@ -178,8 +178,13 @@ int hb2_pack_boxes_dev(hb2_plan_t plan, const double* const* U, int32_t nbox, co
 int hb2_unpack_boxes_dev(hb2_plan_t plan, double* const* U, int32_t nbox, const int32_t* lo,
                          const int32_t* hi, const int64_t* offsets, const double* buffer);
 
-/* Euler::computeSpectralRadiusesAndStableDtOnPatch building block:
- * max over the interior of (|u_d| + c)/dx_d per direction, result in out_dev[0..dim-1]. */
+/* Euler::computeSpectralRadiusesAndStableDtOnPatch (Euler.cpp:489-900) without source terms, with
+ * MAX_WAVE_SPEED_d = |u_d| + c (FlowModelSingleSpecies.cpp:3884-4388) evaluated on the fly:
+ *   out_dev[a]   = max over the interior of (|u_a| + c)/dx_a, a < dim   (the reference also visits the ghost cells,
+ *                  which hold neighbour interiors: the level-wide maximum is the same)
+ *   out_dev[3]   = max over the interior of sum_a (|u_a| + c)/dx_a     (stable dt of the patch = CFL / out_dev[3])
+ * out_dev: 4 doubles of DEVICE memory; non-negative doubles, so a MAX all-reduce over ranks
+ * (RungeKuttaLevelIntegrator.cpp:1864, 1911) can be applied to them directly. */
 int hb2_max_wave_speed_dev(hb2_plan_t plan, const double* const* Q, double* out_dev);
 
 /* ---- the hot path, HOST buffers (H2D + kernels + D2H inside the call) ------------------- */

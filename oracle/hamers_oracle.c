@@ -371,6 +371,40 @@ static void cell_stage(const geom_t* q, const double* gam, const double* const* 
     }
 }
 
+/* Euler.cpp:760-893 (3D; 2D :627-745): spectral radii and stable dt of one patch, see hamers_oracle.h */
+int orc_spectral_radii_and_dt(const orc_desc* d, const double* const* Q, int include_ghosts, double* out)
+{
+    geom_t q;
+    make_geom(d, &q);
+    const int dim = q.dim;
+    double* vel[3] = {dalloc(q.ncell_g), dalloc(q.ncell_g), dalloc(q.ncell_g)};
+    double *p = dalloc(q.ncell_g), *c = dalloc(q.ncell_g), *rho_m = dalloc(q.ncell_g);
+    cell_stage(&q, d->gamma, Q, vel, p, c, rho_m);
+    double sr[4] = {0.0, 0.0, 0.0, 0.0};
+    const int g = include_ghosts ? G : 0;
+    const int gz = (dim == 3) ? g : 0;
+    for (int k = -gz; k < nz_of(d) + gz; k++)
+        for (int j = -g; j < d->n[1] + g; j++)
+            for (int i = -g; i < d->n[0] + g; i++) {
+                const long x = cidx(&q, i, j, k);
+                double sum = 0.0;
+                for (int a = 0; a < dim; a++) {
+                    const double lambda_max = fabs(vel[a][x]) + c[x];
+                    const double spectral_radius = lambda_max / d->dx[a];
+                    sr[a] = fmax(sr[a], spectral_radius);
+                    sum = (a == 0) ? spectral_radius : sum + spectral_radius;
+                }
+                sr[3] = fmax(sr[3], sum);
+            }
+    for (int a = 0; a < dim; a++) out[a] = sr[a];
+    out[dim] = 1.0 / sr[3];
+    for (int a = 0; a < 3; a++) free(vel[a]);
+    free(p);
+    free(c);
+    free(rho_m);
+    return 0;
+}
+
 /* node flux in direction dir at ghost-box cell x, equation e.
  * single-species: FlowModelSingleSpecies.cpp:3388-3391, 3470-3474, 3611-3614, 3693-3697, 3856-3860;
  * five-eqn: FlowModelFiveEqnAllaire.cpp:5206-5275, 5434-5482, 5559-5628, 5806-5875. */

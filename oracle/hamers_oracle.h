@@ -77,6 +77,17 @@ int orc_advance_stage(const orc_desc* d, int ncoef,
                       const double* const* const* S_int,
                       double* const* U_out);
 
+/*
+ * Euler::computeSpectralRadiusesAndStableDtOnPatch (Euler.cpp:489-900; 3D body :760-893) with the derived data
+ * MAX_WAVE_SPEED_d = |u_d| + c (FlowModelSingleSpecies.cpp:3959, 4003, 4064; five-eqn FlowModelFiveEqnAllaire.cpp
+ * computeCellDataOfMaxWaveSpeedWithVelocityAndSoundSpeed) for one patch, WITHOUT source terms:
+ *   out[a]   = max over the cells of (|u_a| + c)/dx_a,  a < dim
+ *   out[dim] = 1 / max over the cells of sum_a (|u_a| + c)/dx_a          (the patch's stable dt for CFL = 1)
+ * include_ghosts != 0 loops over the ghost box like the reference (its ghost cells hold neighbour data by then),
+ * 0 over the interior only.
+ */
+int orc_spectral_radii_and_dt(const orc_desc* d, const double* const* Q, int include_ghosts, double* out);
+
 /* Point kernels exported for pinning against oracle/_ref (the reference's own functions). */
 void orc_weno5js_point(const double U[6], int p, double* U_minus, double* U_plus);
 /* V layout: single-species [rho, vel(d), p]; five-eqn [Zrho(ns), vel(d), p, Z(ns-1)] */

@@ -200,6 +200,15 @@ def level_advance(level: PatchDesc, patch, U: np.ndarray, dt: float, nsteps: int
     return U
 
 
+def spectral_radii_and_dt(desc: PatchDesc, Q: np.ndarray, include_ghosts: bool = True):
+    """Euler::computeSpectralRadiusesAndStableDtOnPatch: (spectral radii per direction, stable dt for CFL = 1)."""
+    out = (C.c_double * 4)()
+    d = desc.c()
+    rc = lib().orc_spectral_radii_and_dt(C.byref(d), _pp([Q[c] for c in range(desc.ncomp)]), 1 if include_ghosts else 0, out)
+    assert rc == 0
+    return np.array(out[:desc.dim]), float(out[desc.dim])
+
+
 def weno5js_point(U, p=2):
     Ua = (C.c_double * 6)(*[float(x) for x in U])
     m, pl = C.c_double(), C.c_double()

@@ -83,7 +83,8 @@ static void run_dir_n(const DirArgs& A)
 template <class Tr, int DIR, int MATH>
 static void run_dir(const DirArgs& A)
 {
-    if (DIR == Tr::DIM - 1 && A.mode == MODE_FUSED) {
+    if (A.mode == MODE_EMIT) return run_dir_n<Tr, DIR, MATH, HB2_NTERM_EMIT>(A);
+    if (DIR == Tr::DIM - 1) {
         if (A.nterm == 1) return run_dir_n<Tr, DIR, MATH, 1>(A);
         if (A.nterm == 2) return run_dir_n<Tr, DIR, MATH, 2>(A);
         if (MATH == 1 && A.nterm >= HB2_NTERM_QREC) {

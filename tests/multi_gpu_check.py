@@ -45,6 +45,7 @@ def main():
         d = lvl.decomp
         box = (slice(None),) + tuple(slice(d.lo[a], d.lo[a] + d.n[a]) for a in reversed(range(3)))
         lvl.set_interior(U[box])
+        dt_level = lvl.stable_dt(0.5)      # spectral radii per box + MAX all-reduce over the ranks (row f1)
         lvl.advance(dt, args.steps)
         mine = lvl.interior().contiguous()
         gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
@@ -59,6 +60,11 @@ def main():
             # reference: the whole level as ONE box on this GPU (no torch.distributed inside)
             plan = abi.Plan(3, N, flow_model=model, species_gamma=gam, dx=lvl.dx, math=math).use_torch_stream()
             S = torch.from_numpy(pb.pad_periodic(U)).cuda()
+            sr = torch.zeros(4, dtype=torch.float64, device="cuda")
+            plan.max_wave_speed(S, sr)
+            dt_one = 0.5 / float(sr[3])
+            print(f"[multi_gpu_check] world {world} stable dt: level {dt_level:.17g}, single box {dt_one:.17g}")
+            ok &= dt_level == dt_one
             for _ in range(args.steps):
                 plan.advance_level(S, dt)
             torch.cuda.synchronize()

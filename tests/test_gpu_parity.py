@@ -184,6 +184,27 @@ def test_periodic_fill_and_pack_unpack(name, product_lib):
     plan.close()
 
 
+@pytest.mark.parametrize("name", list(CASES))
+def test_spectral_radii_and_stable_dt(name, oracle_lib, product_lib):
+    """SURVEY row f1: Euler::computeSpectralRadiusesAndStableDtOnPatch -- bit-identical to the oracle."""
+    import torch
+    from hamers_b200 import problems as pb
+
+    desc, U = make_case(name, "random")
+    Q = pb.pad_periodic(U)
+    sr_o, dt_o = oracle_lib.spectral_radii_and_dt(desc, Q, include_ghosts=False)
+    sr_g, dt_g = oracle_lib.spectral_radii_and_dt(desc, Q, include_ghosts=True)
+    assert np.array_equal(sr_o, sr_g) and dt_o == dt_g      # periodic ghosts add nothing
+    plan = _plan(desc, 0)
+    out = torch.full((4,), -1.0, dtype=torch.float64, device="cuda")
+    plan.max_wave_speed(_to_dev(Q), out)
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    assert np.array_equal(o[:desc.dim], sr_o)
+    assert 1.0 / o[3] == dt_o
+    plan.close()
+
+
 def test_pack_unpack_many_boxes(product_lib):
     """hb2_pack_boxes_dev / hb2_unpack_boxes_dev: several boxes (interior slabs, ghost regions, an edge bar) in one
     launch, at arbitrary positions of one buffer."""
