@@ -277,6 +277,17 @@ def run_ours(args):
             "kernels": kern,
         }
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
+        # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of this workload
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_n_traffic.json")) as fh:
+                tr = json.load(fh)
+            if tr["size"] == args.size and tr["model"] == args.model and tr["math"] == args.math and world == 1:
+                roofline["traffic"] = tr["dram_bytes_per_launch"][dom]
+                roofline["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)"
+                roofline["traffic_source"] = tr["source"]
+                roofline["algorithmic_bytes_per_launch"] = {"xsweep": 80.0, "ysweep": 120.0, "zsweep": 160.0}[dom] * ncell_local
+        except Exception:
+            pass
         line = {
             "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
