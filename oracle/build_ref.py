@@ -7,7 +7,7 @@ SAMRAI-free.  This recipe reads them where they lie under /root/reference, wraps
 namespaces inside a generated translation unit under oracle/_ref/ (git-ignored, never
 committed), compiles it with the reference's own flags (g++ -std=c++11 -O3, CMakeLists.txt:80;
 HAMERS_EPSILON = 1.0e-15, include/HAMeRS_config.hpp.in:16) and deletes the generated source.
-The resulting library pins the oracle's WCNS5-JS interpolation and HLLC / HLLC-HLL kernels
+The resulting library pins the oracle's WCNS5-JS / WCNS5-Z / WCNS6-LD interpolations and HLLC / HLLC-HLL kernels
 (tests/test_oracle_pinned.py).
 
 Nothing here is copied into the repository; if /root/reference is absent (the GPU box) the
@@ -27,6 +27,8 @@ OUT = os.path.join(HERE, "_ref")
 SOURCES = {
     # namespace -> reference file holding `static inline` point kernels
     "ref_weno": "src/flow/convective_flux_reconstructors/WCNS56/ConvectiveFluxReconstructorWCNS5-JS-HLLC-HLL.cpp",
+    "ref_weno_z": "src/flow/convective_flux_reconstructors/WCNS56/ConvectiveFluxReconstructorWCNS5-Z-HLLC-HLL.cpp",
+    "ref_weno_ld": "src/flow/convective_flux_reconstructors/WCNS56/ConvectiveFluxReconstructorWCNS6-LD-HLLC-HLL.cpp",
     "ref_ss_hllc": "src/flow/flow_models/single-species/Riemann_solvers/FlowModelRiemannSolverSingleSpeciesHLLC.cpp",
     "ref_ss_hyb": "src/flow/flow_models/single-species/Riemann_solvers/FlowModelRiemannSolverSingleSpeciesHLLC-HLL.cpp",
     "ref_fe_hllc": "src/flow/flow_models/five-eqn_Allaire/Riemann_solvers/FlowModelRiemannSolverFiveEqnAllaireHLLC.cpp",
@@ -64,6 +66,23 @@ void ref_weno5js_point(const double U[6], int p, double* U_minus, double* U_plus
     for (int m = 0; m < 6; m++) { vals[m] = U[m]; Ua[m] = &vals[m]; }
     ref_weno::performLocalWENOInterpolationMinus(U_minus, Ua, 0, p);
     ref_weno::performLocalWENOInterpolationPlus(U_plus, Ua, 0, p);
+}
+
+/* WCNS5-Z and WCNS6-LD point interpolation (SURVEY row f2) */
+void ref_weno5z_point(const double U[6], int p, double* U_minus, double* U_plus)
+{
+    double vals[6]; double* Ua[6];
+    for (int m = 0; m < 6; m++) { vals[m] = U[m]; Ua[m] = &vals[m]; }
+    ref_weno_z::performLocalWENOInterpolationMinus(U_minus, Ua, 0, p);
+    ref_weno_z::performLocalWENOInterpolationPlus(U_plus, Ua, 0, p);
+}
+
+void ref_weno6ld_point(const double U[6], int p, int q, double C, double alpha_tau, double* U_minus, double* U_plus)
+{
+    double vals[6]; double* Ua[6];
+    for (int m = 0; m < 6; m++) { vals[m] = U[m]; Ua[m] = &vals[m]; }
+    ref_weno_ld::performLocalWENOInterpolationMinus(U_minus, Ua, 0, p, q, C, alpha_tau);
+    ref_weno_ld::performLocalWENOInterpolationPlus(U_plus, Ua, 0, p, q, C, alpha_tau);
 }
 
 /* HLLC and HLLC-HLL point kernels on one face (idx = idx_flux = 0).  The midpoint normal velocity is

@@ -83,6 +83,116 @@ void orc_weno5js_point(const double U[6], int p, double* U_minus, double* U_plus
     *U_plus = weno5js_side(U[5], U[4], U[3], U[2], U[1], p);
 }
 
+/* The three smoothness indicators shared by WCNS5-JS / WCNS5-Z / WCNS6-LD (same polynomials in all three files:
+ * WCNS5-Z-HLLC-HLL.cpp:31-44, WCNS6-LD-HLLC-HLL.cpp:51-63). */
+static inline void beta_012(double a, double b, double c, double d, double e, double* b0, double* b1, double* b2)
+{
+    *b0 = 1.0 / 3.0 * (a * (4.0 * a - 19.0 * b + 11.0 * c) + b * (25.0 * b - 31.0 * c) + 10.0 * c * c);
+    *b1 = 1.0 / 3.0 * (b * (4.0 * b - 13.0 * c + 5.0 * d) + 13.0 * c * (c - d) + 4.0 * d * d);
+    *b2 = 1.0 / 3.0 * (c * (10.0 * c - 31.0 * d + 11.0 * e) + d * (25.0 * d - 19.0 * e) + 4.0 * e * e);
+}
+
+/* WCNS5-Z one-sided interpolation: weights WCNS5-Z-HLLC-HLL.cpp:96-107 (tau_5 = |beta_0 - beta_2|,
+ * omega_k = d_k (1 + (tau_5/(beta_k + eps))^p)), value :113-118; plus side mirrored (:124-165). */
+static inline double weno5z_side(double a, double b, double c, double d, double e, int p)
+{
+    double beta_0, beta_1, beta_2;
+    beta_012(a, b, c, d, e, &beta_0, &beta_1, &beta_2);
+    const double tau_5 = fabs(beta_0 - beta_2);
+    double omega_0 = 1.0 / 16.0 * (1.0 + ipow_(tau_5 / (beta_0 + EPSILON), p));
+    double omega_1 = 5.0 / 8.0 * (1.0 + ipow_(tau_5 / (beta_1 + EPSILON), p));
+    double omega_2 = 5.0 / 16.0 * (1.0 + ipow_(tau_5 / (beta_2 + EPSILON), p));
+    const double omega_sum = omega_0 + omega_1 + omega_2;
+    omega_0 = omega_0 / omega_sum;
+    omega_1 = omega_1 / omega_sum;
+    omega_2 = omega_2 / omega_sum;
+    return 3.0 / 8.0 * omega_0 * a +
+           (-10.0 / 8.0 * omega_0 - 1.0 / 8.0 * omega_1) * b +
+           (15.0 / 8.0 * omega_0 + 6.0 / 8.0 * omega_1 + 3.0 / 8.0 * omega_2) * c +
+           (3.0 / 8.0 * omega_1 + 6.0 / 8.0 * omega_2) * d -
+           1.0 / 8.0 * omega_2 * e;
+}
+
+void orc_weno5z_point(const double U[6], int p, double* U_minus, double* U_plus)
+{
+    *U_minus = weno5z_side(U[0], U[1], U[2], U[3], U[4], p);
+    *U_plus = weno5z_side(U[5], U[4], U[3], U[2], U[1], p);
+}
+
+/* WCNS6-LD one-sided interpolation from the six cells (a..f), upwind cell c, face between c and d.
+ * sigma: WCNS6-LD-HLLC-HLL.cpp:23-39 (computed from cells 1..4 = b..e of the UNMIRRORED stencil: the plus side calls
+ * the same computeLocalSigma, :275); beta_0..2 :51-63, beta_3 :64-83; upwind weights :167-177; central weights
+ * :183-197; blend where R_tau > alpha_tau :203-211; value :217-226.  `sigma` is passed in because it does not mirror. */
+static inline double weno6ld_side(double a, double b, double c, double d, double e, double f, double sigma,
+                                  int p, int q, double C, double alpha_tau)
+{
+    double beta_0, beta_1, beta_2;
+    beta_012(a, b, c, d, e, &beta_0, &beta_1, &beta_2);
+    const double beta_3 = 1.0 / 232243200.0 * (a * (525910327.0 * a - 4562164630.0 * b + 7799501420.0 * c -
+        6610694540.0 * d + 2794296070.0 * e - 472758974.0 * f) + 5.0 * b *
+        (2146987907.0 * b - 7722406988.0 * c + 6763559276.0 * d - 2926461814.0 * e + 503766638.0 * f) + 20.0 * c *
+        (1833221603.0 * c - 3358664662.0 * d + 1495974539.0 * e - 263126407.0 * f) +
+        20.0 * d * (1607794163.0 * d - 1486026707.0 * e + 268747951.0 * f) +
+        5.0 * e * (1432381427.0 * e - 536951582.0 * f) +
+        263126407.0 * f * f);
+
+    double omega_upwind_0, omega_upwind_1, omega_upwind_2;
+    const double tau_5 = fabs(beta_0 - beta_2);
+    omega_upwind_0 = 1.0 / 16.0 * (1.0 + ipow_(tau_5 / (beta_0 + EPSILON), p));
+    omega_upwind_1 = 5.0 / 8.0 * (1.0 + ipow_(tau_5 / (beta_1 + EPSILON), p));
+    omega_upwind_2 = 5.0 / 16.0 * (1.0 + ipow_(tau_5 / (beta_2 + EPSILON), p));
+    const double omega_upwind_sum = omega_upwind_0 + omega_upwind_1 + omega_upwind_2;
+    omega_upwind_0 = omega_upwind_0 / omega_upwind_sum;
+    omega_upwind_1 = omega_upwind_1 / omega_upwind_sum;
+    omega_upwind_2 = omega_upwind_2 / omega_upwind_sum;
+
+    double omega_0, omega_1, omega_2, omega_3;
+    const double beta_avg = 1.0 / 8.0 * (beta_0 + beta_2 + 6.0 * beta_1);
+    const double tau_6 = fabs(beta_3 - beta_avg);
+    omega_0 = 1.0 / 32.0 * (C + ipow_(tau_6 / (beta_0 + EPSILON), q));
+    omega_1 = 15.0 / 32.0 * (C + ipow_(tau_6 / (beta_1 + EPSILON), q));
+    omega_2 = 15.0 / 32.0 * (C + ipow_(tau_6 / (beta_2 + EPSILON), q));
+    omega_3 = 1.0 / 32.0 * (C + ipow_(tau_6 / (beta_3 + EPSILON), q));
+    const double omega_sum = omega_0 + omega_1 + omega_2 + omega_3;
+    omega_0 = omega_0 / omega_sum;
+    omega_1 = omega_1 / omega_sum;
+    omega_2 = omega_2 / omega_sum;
+    omega_3 = omega_3 / omega_sum;
+
+    const double R_tau = tau_6 / (beta_avg + EPSILON);
+    if (R_tau > alpha_tau) {
+        omega_0 = sigma * omega_upwind_0 + (1.0 - sigma) * omega_0;
+        omega_1 = sigma * omega_upwind_1 + (1.0 - sigma) * omega_1;
+        omega_2 = sigma * omega_upwind_2 + (1.0 - sigma) * omega_2;
+        omega_3 = (1.0 - sigma) * omega_3;
+    }
+
+    return 3.0 / 8.0 * omega_0 * a +
+           (-10.0 / 8.0 * omega_0 - 1.0 / 8.0 * omega_1) * b +
+           (15.0 / 8.0 * omega_0 + 6.0 / 8.0 * omega_1 + 3.0 / 8.0 * omega_2) * c +
+           (3.0 / 8.0 * omega_1 + 6.0 / 8.0 * omega_2 + 15.0 / 8.0 * omega_3) * d +
+           (-1.0 / 8.0 * omega_2 - 10.0 / 8.0 * omega_3) * e +
+           3.0 / 8.0 * omega_3 * f;
+}
+
+/* WCNS6-LD-HLLC-HLL.cpp:23-39 */
+static inline double weno6ld_sigma(const double U[6])
+{
+    const double alpha_1 = U[2] - U[1];
+    const double alpha_2 = U[3] - U[2];
+    const double alpha_3 = U[4] - U[3];
+    const double theta_1 = fabs(alpha_1 - alpha_2) / (fabs(alpha_1) + fabs(alpha_2) + EPSILON);
+    const double theta_2 = fabs(alpha_2 - alpha_3) / (fabs(alpha_2) + fabs(alpha_3) + EPSILON);
+    return fmax(theta_1, theta_2);
+}
+
+void orc_weno6ld_point(const double U[6], int p, int q, double C, double alpha_tau, double* U_minus, double* U_plus)
+{
+    const double sigma = weno6ld_sigma(U);
+    *U_minus = weno6ld_side(U[0], U[1], U[2], U[3], U[4], U[5], sigma, p, q, C, alpha_tau);
+    *U_plus = weno6ld_side(U[5], U[4], U[3], U[2], U[1], U[0], sigma, p, q, C, alpha_tau);
+}
+
 /* Side thermodynamics fed to the Riemann point kernels.
  * single-species: EquationOfStateIdealGas.cpp:5909 (c), :6238 (epsilon), called from
  *   FlowModelRiemannSolverSingleSpeciesHLLC.cpp:2991-3025.
@@ -575,7 +685,13 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
                 const long s = SIDX(i, j, k);
                 double U[6];
                 for (int m = 0; m < 6; m++) U[m] = W[m][e][s];
-                orc_weno5js_point(U, p_exp, &W_minus[e][s], &W_plus[e][s]);
+                if (d->scheme == ORC_WCNS5_Z)
+                    orc_weno5z_point(U, p_exp, &W_minus[e][s], &W_plus[e][s]);
+                else if (d->scheme == ORC_WCNS6_LD)
+                    orc_weno6ld_point(U, p_exp, d->weno_q > 0 ? d->weno_q : 4, d->weno_C > 0.0 ? d->weno_C : 1.0e9,
+                                      d->weno_alpha_tau > 0.0 ? d->weno_alpha_tau : 35.0, &W_minus[e][s], &W_plus[e][s]);
+                else
+                    orc_weno5js_point(U, p_exp, &W_minus[e][s], &W_plus[e][s]);
             }
         }
 

@@ -38,7 +38,18 @@ typedef struct {
     double gamma[ORC_MAX_SPECIES];   /* species ratio of specific heats */
     double dx[3];
     int weno_p;                      /* constant_p, default 2 (WCNS5-JS-HLLC-HLL.cpp:188-191) */
+    /* the other nonlinear interpolators of the same base class.  0 = WCNS5-JS, 1 = WCNS5-Z
+     * (ConvectiveFluxReconstructorWCNS5-Z-HLLC-HLL.cpp), 2 = WCNS6-LD (ConvectiveFluxReconstructorWCNS6-LD-HLLC-HLL.cpp)
+     * with constant_q (default 4), constant_C (1.0e9), constant_alpha_tau (35): :343-361. */
+    int scheme;
+    int weno_q;
+    double weno_C;
+    double weno_alpha_tau;
 } orc_desc;
+
+#define ORC_WCNS5_JS 0
+#define ORC_WCNS5_Z 1
+#define ORC_WCNS6_LD 2
 
 /* d + 2 (single-species) or d + 2*ns (five-eqn): FlowModelFiveEqnAllaire.cpp:29 */
 int orc_num_eqn(const orc_desc* d);
@@ -90,6 +101,8 @@ int orc_spectral_radii_and_dt(const orc_desc* d, const double* const* Q, int inc
 
 /* Point kernels exported for pinning against oracle/_ref (the reference's own functions). */
 void orc_weno5js_point(const double U[6], int p, double* U_minus, double* U_plus);
+void orc_weno5z_point(const double U[6], int p, double* U_minus, double* U_plus);
+void orc_weno6ld_point(const double U[6], int p, int q, double C, double alpha_tau, double* U_minus, double* U_plus);
 /* V layout: single-species [rho, vel(d), p]; five-eqn [Zrho(ns), vel(d), p, Z(ns-1)] */
 void orc_riemann_point(int model, int dim, int ns, const double* gamma, int dir,
                        const double* V_L, const double* V_R,

@@ -37,6 +37,10 @@ class _Desc(C.Structure):
         ("gamma", C.c_double * MAX_SPECIES),
         ("dx", C.c_double * 3),
         ("weno_p", C.c_int),
+        ("scheme", C.c_int),
+        ("weno_q", C.c_int),
+        ("weno_C", C.c_double),
+        ("weno_alpha_tau", C.c_double),
     ]
 
 
@@ -74,6 +78,10 @@ class PatchDesc:
     gamma: tuple = (1.4,)
     dx: tuple = (1.0, 1.0, 1.0)
     weno_p: int = 2
+    scheme: int = 0            # 0 WCNS5-JS, 1 WCNS5-Z, 2 WCNS6-LD
+    weno_q: int = 4
+    weno_C: float = 1.0e9
+    weno_alpha_tau: float = 35.0
     _c: _Desc = field(default=None, repr=False)
 
     def c(self) -> _Desc:
@@ -87,6 +95,7 @@ class PatchDesc:
         for i, g in enumerate(self.gamma):
             d.gamma[i] = float(g)
         d.weno_p = self.weno_p
+        d.scheme, d.weno_q, d.weno_C, d.weno_alpha_tau = self.scheme, self.weno_q, self.weno_C, self.weno_alpha_tau
         return d
 
     @property
@@ -213,6 +222,20 @@ def weno5js_point(U, p=2):
     Ua = (C.c_double * 6)(*[float(x) for x in U])
     m, pl = C.c_double(), C.c_double()
     lib().orc_weno5js_point(Ua, int(p), C.byref(m), C.byref(pl))
+    return m.value, pl.value
+
+
+def weno5z_point(U, p=2):
+    Ua = (C.c_double * 6)(*[float(x) for x in U])
+    m, pl = C.c_double(), C.c_double()
+    lib().orc_weno5z_point(Ua, int(p), C.byref(m), C.byref(pl))
+    return m.value, pl.value
+
+
+def weno6ld_point(U, p=2, q=4, Cc=1.0e9, alpha_tau=35.0):
+    Ua = (C.c_double * 6)(*[float(x) for x in U])
+    m, pl = C.c_double(), C.c_double()
+    lib().orc_weno6ld_point(Ua, int(p), int(q), C.c_double(Cc), C.c_double(alpha_tau), C.byref(m), C.byref(pl))
     return m.value, pl.value
 
 

@@ -57,6 +57,18 @@ def ref_weno(lib, U, p=2):
     return m.value, pl.value
 
 
+def ref_weno_z(lib, U, p=2):
+    m, pl = C.c_double(), C.c_double()
+    lib.ref_weno5z_point((C.c_double * 6)(*U), int(p), C.byref(m), C.byref(pl))
+    return m.value, pl.value
+
+
+def ref_weno_ld(lib, U, p=2, q=4, Cc=1.0e9, alpha_tau=35.0):
+    m, pl = C.c_double(), C.c_double()
+    lib.ref_weno6ld_point((C.c_double * 6)(*U), int(p), int(q), C.c_double(Cc), C.c_double(alpha_tau), C.byref(m), C.byref(pl))
+    return m.value, pl.value
+
+
 def riemann_inputs(rng, model, dim, ns, n=120):
     neq = dim + 2 if model == 0 else dim + 2 * ns
     VL, VR = np.zeros((n, neq)), np.zeros((n, neq))
@@ -106,6 +118,15 @@ def main():
     out["weno_U"], out["weno_minus"], out["weno_plus"] = U, res[:, 0], res[:, 1]
     res3 = np.array([ref_weno(lib, u, 3) for u in U])
     out["weno_minus_p3"], out["weno_plus_p3"] = res3[:, 0], res3[:, 1]
+    # WCNS5-Z (ConvectiveFluxReconstructorWCNS5-Z-HLLC-HLL.cpp:78-165) and WCNS6-LD
+    # (ConvectiveFluxReconstructorWCNS6-LD-HLLC-HLL.cpp:143-339) on the same stencils; LD also with a low alpha_tau so
+    # that the R_tau > alpha_tau blend is taken on the smooth stencils too
+    rz = np.array([ref_weno_z(lib, u) for u in U])
+    out["weno_z_minus"], out["weno_z_plus"] = rz[:, 0], rz[:, 1]
+    for tag, args in (("ld", (2, 4, 1.0e9, 35.0)), ("ld_b", (2, 4, 1.0e3, 0.5)), ("ld_c", (3, 2, 10.0, 2.0))):
+        rl = np.array([ref_weno_ld(lib, u, *args) for u in U])
+        out[f"weno_{tag}_minus"], out[f"weno_{tag}_plus"] = rl[:, 0], rl[:, 1]
+        out[f"weno_{tag}_params"] = np.array(args, dtype=np.float64)
     for tag, model, dim, ns, gam in CASES:
         for d in range(dim):
             VL, VR = riemann_inputs(rng, model, dim, ns)
