@@ -35,6 +35,8 @@ SYMBOLS = [
     "hb2_plan_set_profiling", "hb2_plan_get_profile", "hb2_advance_level_dev", "hb2_advance_level_host",
 ]
 
+WCNS5_JS, WCNS5_Z, WCNS6_LD = 0, 1, 2
+
 KERNEL_KINDS = ("sensor", "xsweep", "ysweep", "zsweep", "advance", "fill_periodic", "pack", "unpack")
 
 # SSP-RK3(3,3), the reference's default table (RungeKuttaLevelIntegrator.cpp:3894-3929), row-major [stage][m]
@@ -53,6 +55,10 @@ class PatchDescC(C.Structure):
         ("weno_p", C.c_int32),
         ("math", C.c_int32),
         ("device", C.c_int32),
+        ("scheme", C.c_int32),
+        ("weno_q", C.c_int32),
+        ("weno_C", C.c_double),
+        ("weno_alpha_tau", C.c_double),
     ]
 
 
@@ -133,7 +139,8 @@ class Plan:
 
     def __init__(self, dim: int, n: Sequence[int], flow_model: int = SINGLE_SPECIES,
                  species_gamma: Sequence[float] = (1.4,), dx: Sequence[float] = (1.0, 1.0, 1.0),
-                 weno_p: int = 2, math: int = MATH_EXACT, device: int = -1):
+                 weno_p: int = 2, math: int = MATH_EXACT, device: int = -1, scheme: int = 0, weno_q: int = 4,
+                 weno_C: float = 1.0e9, weno_alpha_tau: float = 35.0):
         self.lib = load_library()
         d = PatchDescC()
         d.dim = dim
@@ -147,6 +154,7 @@ class Plan:
         d.weno_p = weno_p
         d.math = math
         d.device = device
+        d.scheme, d.weno_q, d.weno_C, d.weno_alpha_tau = int(scheme), int(weno_q), float(weno_C), float(weno_alpha_tau)
         self.desc = d
         self.dim = dim
         self.n = tuple(int(n[a]) for a in range(dim))

@@ -2,8 +2,9 @@
 
     python -m hamers_b200.build [--force]
 
-Three translation units: the sweeps are compiled twice (exact: -fmad=false, reference operation
-order; fast: FMA contraction + reciprocal sharing) and linked with the ABI layer.  nvcc
+Five translation units: the sweeps are compiled four times (exact: -fmad=false, reference operation
+order, once per nonlinear interpolator WCNS5-JS / WCNS5-Z / WCNS6-LD; fast: FMA contraction + reciprocal
+sharing, WCNS5-JS) and linked with the ABI layer.  nvcc
 cross-compiles without a GPU.  The .so is git-ignored but travels to the GPU box.
 """
 from __future__ import annotations
@@ -25,6 +26,8 @@ COMMON = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-I", 
 
 UNITS = [
     ("hb2_sweeps_exact.o", "hb2_sweeps.cu", ["-DHB2_MATH=0", "-fmad=false"]),
+    ("hb2_sweeps_exact_z.o", "hb2_sweeps.cu", ["-DHB2_MATH=0", "-DHB2_SCHEME=1", "-fmad=false"]),
+    ("hb2_sweeps_exact_ld.o", "hb2_sweeps.cu", ["-DHB2_MATH=0", "-DHB2_SCHEME=2", "-fmad=false"]),
     ("hb2_sweeps_fast.o", "hb2_sweeps.cu", ["-DHB2_MATH=1", "-fmad=true"] + os.environ.get("HB2_FAST_FLAGS", "").split()),
     ("hb2_abi.o", "hb2_abi.cu", ["-fmad=false"]),
 ]
@@ -55,7 +58,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed for {src} {flags}:\n{r.stdout}\n{r.stderr}")
         return r.stderr
 
-    with ThreadPoolExecutor(max_workers=3) as ex:
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
         logs = list(ex.map(compile_one, UNITS))
     if verbose:
         for lg in logs:

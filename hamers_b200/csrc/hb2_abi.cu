@@ -128,6 +128,8 @@ int validate_desc(const hb2_patch_desc* d)
     for (int s = 0; s < d->num_species; s++)
         if (!(d->species_gamma[s] > 1.0)) return fail(-8, "species_gamma must be > 1");
     if (d->math != HB2_MATH_EXACT && d->math != HB2_MATH_FAST) return fail(-9, "math must be HB2_MATH_EXACT or HB2_MATH_FAST");
+    if (d->scheme != HB2_WCNS5_JS && d->scheme != HB2_WCNS5_Z && d->scheme != HB2_WCNS6_LD)
+        return fail(-24, "scheme must be HB2_WCNS5_JS, HB2_WCNS5_Z or HB2_WCNS6_LD");
     return 0;
 }
 
@@ -496,11 +498,16 @@ int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* out)
         p->K.inv_gm1[s] = 1.0 / (p->K.gamma[s] - 1.0);
     }
     p->K.weno_p = p->d.weno_p;
+    p->K.weno_q = d->weno_q > 0 ? d->weno_q : 4;
+    p->K.weno_C = d->weno_C > 0.0 ? d->weno_C : 1.0e9;
+    p->K.weno_alpha_tau = d->weno_alpha_tau > 0.0 ? d->weno_alpha_tau : 35.0;
     p->cfg.model = d->flow_model;
     p->cfg.dim = d->dim;
     p->cfg.ns = d->num_species;
     /* the fast kernels are written for constant_p = 2 (the reference default); other exponents use the exact build */
     p->ops = (d->math == HB2_MATH_EXACT || p->d.weno_p != 2) ? ops_exact() : ops_fast();
+    if (d->scheme == HB2_WCNS5_Z) p->ops = ops_exact_z();
+    if (d->scheme == HB2_WCNS6_LD) p->ops = ops_exact_ld();
     p->ncell_i = (long long)p->G.n[0] * p->G.n[1] * p->G.n[2];
     for (int a = 0; a < 3; a++) {
         long long ee[3] = {p->G.n[0], p->G.n[1], p->G.n[2]};

@@ -70,7 +70,19 @@ struct Consts {
     double gamma[4];
     double inv_gm1[4]; /* 1/(gamma_i - 1), EquationOfStateMixingRulesIdealGas.cpp:7523 */
     int weno_p;
+    int weno_q;            /* WCNS6-LD: constant_q, constant_C, constant_alpha_tau (WCNS6-LD-HLLC-HLL.cpp:343-361) */
+    double weno_C;
+    double weno_alpha_tau;
 };
+
+/* nonlinear interpolator of the translation unit: the reference's three subclasses of
+ * ConvectiveFluxReconstructorWCNS56 differ only in performWENOInterpolation's point kernels */
+#define HB2_WCNS5_JS 0
+#define HB2_WCNS5_Z 1
+#define HB2_WCNS6_LD 2
+#ifndef HB2_SCHEME
+#define HB2_SCHEME HB2_WCNS5_JS
+#endif
 
 #define HB2_MAXC 13
 #define HB2_MAXE 12
@@ -256,6 +268,109 @@ HB2_HD double weno5js_side(double a, double b, double c, double d, double e, int
         const double P2 = 0.375 * c + 0.75 * d - 0.125 * e;
         return (a0 * P0 + a1 * P1 + a2 * P2) * inv;
     }
+}
+
+/* the three smoothness indicators shared by WCNS5-JS / -Z / WCNS6-LD */
+HB2_HD void beta_012(double a, double b, double c, double d, double e, double& b0, double& b1, double& b2)
+{
+    b0 = 1.0 / 3.0 * (a * (4.0 * a - 19.0 * b + 11.0 * c) + b * (25.0 * b - 31.0 * c) + 10.0 * c * c);
+    b1 = 1.0 / 3.0 * (b * (4.0 * b - 13.0 * c + 5.0 * d) + 13.0 * c * (c - d) + 4.0 * d * d);
+    b2 = 1.0 / 3.0 * (c * (10.0 * c - 31.0 * d + 11.0 * e) + d * (25.0 * d - 19.0 * e) + 4.0 * e * e);
+}
+
+/* WCNS5-Z (ConvectiveFluxReconstructorWCNS5-Z-HLLC-HLL.cpp:78-165), reference operation order */
+HB2_HD double weno5z_side(double a, double b, double c, double d, double e, int p)
+{
+    double beta_0, beta_1, beta_2;
+    beta_012(a, b, c, d, e, beta_0, beta_1, beta_2);
+    const double tau_5 = fabs(beta_0 - beta_2);
+    double omega_0 = 1.0 / 16.0 * (1.0 + ipow_(tau_5 / (beta_0 + HB2_EPS), p));
+    double omega_1 = 5.0 / 8.0 * (1.0 + ipow_(tau_5 / (beta_1 + HB2_EPS), p));
+    double omega_2 = 5.0 / 16.0 * (1.0 + ipow_(tau_5 / (beta_2 + HB2_EPS), p));
+    const double omega_sum = omega_0 + omega_1 + omega_2;
+    omega_0 = omega_0 / omega_sum;
+    omega_1 = omega_1 / omega_sum;
+    omega_2 = omega_2 / omega_sum;
+    return 3.0 / 8.0 * omega_0 * a + (-10.0 / 8.0 * omega_0 - 1.0 / 8.0 * omega_1) * b +
+           (15.0 / 8.0 * omega_0 + 6.0 / 8.0 * omega_1 + 3.0 / 8.0 * omega_2) * c +
+           (3.0 / 8.0 * omega_1 + 6.0 / 8.0 * omega_2) * d - 1.0 / 8.0 * omega_2 * e;
+}
+
+/* WCNS6-LD (ConvectiveFluxReconstructorWCNS6-LD-HLLC-HLL.cpp:23-39 sigma, :51-83 beta, :143-339 interpolation),
+ * reference operation order; sigma comes from the unmirrored stencil for both sides */
+HB2_HD double weno6ld_sigma(double w1, double w2, double w3, double w4)
+{
+    const double alpha_1 = w2 - w1;
+    const double alpha_2 = w3 - w2;
+    const double alpha_3 = w4 - w3;
+    const double theta_1 = fabs(alpha_1 - alpha_2) / (fabs(alpha_1) + fabs(alpha_2) + HB2_EPS);
+    const double theta_2 = fabs(alpha_2 - alpha_3) / (fabs(alpha_2) + fabs(alpha_3) + HB2_EPS);
+    return fmax(theta_1, theta_2);
+}
+
+HB2_HD double weno6ld_side(double a, double b, double c, double d, double e, double f, double sigma, const Consts& K)
+{
+    const int p = K.weno_p, q = K.weno_q;
+    double beta_0, beta_1, beta_2;
+    beta_012(a, b, c, d, e, beta_0, beta_1, beta_2);
+    const double beta_3 = 1.0 / 232243200.0 * (a * (525910327.0 * a - 4562164630.0 * b + 7799501420.0 * c -
+        6610694540.0 * d + 2794296070.0 * e - 472758974.0 * f) + 5.0 * b *
+        (2146987907.0 * b - 7722406988.0 * c + 6763559276.0 * d - 2926461814.0 * e + 503766638.0 * f) + 20.0 * c *
+        (1833221603.0 * c - 3358664662.0 * d + 1495974539.0 * e - 263126407.0 * f) +
+        20.0 * d * (1607794163.0 * d - 1486026707.0 * e + 268747951.0 * f) +
+        5.0 * e * (1432381427.0 * e - 536951582.0 * f) +
+        263126407.0 * f * f);
+    double omega_upwind_0, omega_upwind_1, omega_upwind_2;
+    const double tau_5 = fabs(beta_0 - beta_2);
+    omega_upwind_0 = 1.0 / 16.0 * (1.0 + ipow_(tau_5 / (beta_0 + HB2_EPS), p));
+    omega_upwind_1 = 5.0 / 8.0 * (1.0 + ipow_(tau_5 / (beta_1 + HB2_EPS), p));
+    omega_upwind_2 = 5.0 / 16.0 * (1.0 + ipow_(tau_5 / (beta_2 + HB2_EPS), p));
+    const double omega_upwind_sum = omega_upwind_0 + omega_upwind_1 + omega_upwind_2;
+    omega_upwind_0 = omega_upwind_0 / omega_upwind_sum;
+    omega_upwind_1 = omega_upwind_1 / omega_upwind_sum;
+    omega_upwind_2 = omega_upwind_2 / omega_upwind_sum;
+    double omega_0, omega_1, omega_2, omega_3;
+    const double beta_avg = 1.0 / 8.0 * (beta_0 + beta_2 + 6.0 * beta_1);
+    const double tau_6 = fabs(beta_3 - beta_avg);
+    omega_0 = 1.0 / 32.0 * (K.weno_C + ipow_(tau_6 / (beta_0 + HB2_EPS), q));
+    omega_1 = 15.0 / 32.0 * (K.weno_C + ipow_(tau_6 / (beta_1 + HB2_EPS), q));
+    omega_2 = 15.0 / 32.0 * (K.weno_C + ipow_(tau_6 / (beta_2 + HB2_EPS), q));
+    omega_3 = 1.0 / 32.0 * (K.weno_C + ipow_(tau_6 / (beta_3 + HB2_EPS), q));
+    const double omega_sum = omega_0 + omega_1 + omega_2 + omega_3;
+    omega_0 = omega_0 / omega_sum;
+    omega_1 = omega_1 / omega_sum;
+    omega_2 = omega_2 / omega_sum;
+    omega_3 = omega_3 / omega_sum;
+    const double R_tau = tau_6 / (beta_avg + HB2_EPS);
+    if (R_tau > K.weno_alpha_tau) {
+        omega_0 = sigma * omega_upwind_0 + (1.0 - sigma) * omega_0;
+        omega_1 = sigma * omega_upwind_1 + (1.0 - sigma) * omega_1;
+        omega_2 = sigma * omega_upwind_2 + (1.0 - sigma) * omega_2;
+        omega_3 = (1.0 - sigma) * omega_3;
+    }
+    return 3.0 / 8.0 * omega_0 * a + (-10.0 / 8.0 * omega_0 - 1.0 / 8.0 * omega_1) * b +
+           (15.0 / 8.0 * omega_0 + 6.0 / 8.0 * omega_1 + 3.0 / 8.0 * omega_2) * c +
+           (3.0 / 8.0 * omega_1 + 6.0 / 8.0 * omega_2 + 15.0 / 8.0 * omega_3) * d +
+           (-1.0 / 8.0 * omega_2 - 10.0 / 8.0 * omega_3) * e + 3.0 / 8.0 * omega_3 * f;
+}
+
+/* minus / plus midpoint values of one characteristic field from its six stencil values, interpolator of this
+ * translation unit (HB2_SCHEME) */
+template <int MATH>
+HB2_HD void weno_pair(double w0, double w1, double w2, double w3, double w4, double w5, const Consts& K, double& wm,
+                      double& wp)
+{
+#if HB2_SCHEME == HB2_WCNS5_Z
+    wm = weno5z_side(w0, w1, w2, w3, w4, K.weno_p);
+    wp = weno5z_side(w5, w4, w3, w2, w1, K.weno_p);
+#elif HB2_SCHEME == HB2_WCNS6_LD
+    const double sigma = weno6ld_sigma(w1, w2, w3, w4);
+    wm = weno6ld_side(w0, w1, w2, w3, w4, w5, sigma, K);
+    wp = weno6ld_side(w5, w4, w3, w2, w1, w0, sigma, K);
+#else
+    wm = weno5js_side<MATH>(w0, w1, w2, w3, w4, K.weno_p);
+    wp = weno5js_side<MATH>(w5, w4, w3, w2, w1, K.weno_p);
+#endif
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -473,7 +588,6 @@ HB2_HD void face_midpoint(const double (&V)[6][Tr::NEQ], double c_cellL, double 
                           double (&Fm)[Tr::NEQ], double& vel_mid)
 {
     constexpr int DIM = Tr::DIM, NS = Tr::NS, NEQ = Tr::NEQ, IV = Tr::IV, IP = Tr::IP;
-    const int p = K.weno_p;
 
     double V_minus[NEQ], V_plus[NEQ];
     const double c_avg = 0.5 * (c_cellL + c_cellR);
@@ -488,24 +602,20 @@ HB2_HD void face_midpoint(const double (&V)[6][Tr::NEQ], double c_cellL, double 
         /* field 0 */
 #pragma unroll
         for (int m = 0; m < 6; m++) W[m] = kn * V[m][1 + DIR] + 0.5 * V[m][IP];
-        W0m = weno5js_side<MATH>(W[0], W[1], W[2], W[3], W[4], p);
-        W0p = weno5js_side<MATH>(W[5], W[4], W[3], W[2], W[1], p);
+        weno_pair<MATH>(W[0], W[1], W[2], W[3], W[4], W[5], K, W0m, W0p);
         /* field 1 */
 #pragma unroll
         for (int m = 0; m < 6; m++) W[m] = V[m][0] - r_cc * V[m][IP];
-        W1m = weno5js_side<MATH>(W[0], W[1], W[2], W[3], W[4], p);
-        W1p = weno5js_side<MATH>(W[5], W[4], W[3], W[2], W[1], p);
+        weno_pair<MATH>(W[0], W[1], W[2], W[3], W[4], W[5], K, W1m, W1p);
         /* last field */
 #pragma unroll
         for (int m = 0; m < 6; m++) W[m] = kp * V[m][1 + DIR] + 0.5 * V[m][IP];
-        WLm = weno5js_side<MATH>(W[0], W[1], W[2], W[3], W[4], p);
-        WLp = weno5js_side<MATH>(W[5], W[4], W[3], W[2], W[1], p);
+        weno_pair<MATH>(W[0], W[1], W[2], W[3], W[4], W[5], K, WLm, WLp);
         /* tangential velocities are their own characteristic fields */
 #pragma unroll
         for (int a = 0; a < DIM; a++) {
             if (a == DIR) continue;
-            V_minus[1 + a] = weno5js_side<MATH>(V[0][1 + a], V[1][1 + a], V[2][1 + a], V[3][1 + a], V[4][1 + a], p);
-            V_plus[1 + a] = weno5js_side<MATH>(V[5][1 + a], V[4][1 + a], V[3][1 + a], V[2][1 + a], V[1][1 + a], p);
+            weno_pair<MATH>(V[0][1 + a], V[1][1 + a], V[2][1 + a], V[3][1 + a], V[4][1 + a], V[5][1 + a], K, V_minus[1 + a], V_plus[1 + a]);
         }
         V_minus[0] = r_cc * W0m + W1m + r_cc * WLm;
         V_plus[0] = r_cc * W0p + W1p + r_cc * WLp;
@@ -526,20 +636,18 @@ HB2_HD void face_midpoint(const double (&V)[6][Tr::NEQ], double c_cellL, double 
         double W[6], W0m, W0p, WLm, WLp;
 #pragma unroll
         for (int m = 0; m < 6; m++) W[m] = V[m][IV + DIR] - r_rc * V[m][IP];
-        W0m = weno5js_side<MATH>(W[0], W[1], W[2], W[3], W[4], p);
-        W0p = weno5js_side<MATH>(W[5], W[4], W[3], W[2], W[1], p);
+        weno_pair<MATH>(W[0], W[1], W[2], W[3], W[4], W[5], K, W0m, W0p);
 #pragma unroll
         for (int m = 0; m < 6; m++) W[m] = V[m][IV + DIR] + r_rc * V[m][IP];
-        WLm = weno5js_side<MATH>(W[0], W[1], W[2], W[3], W[4], p);
-        WLp = weno5js_side<MATH>(W[5], W[4], W[3], W[2], W[1], p);
+        weno_pair<MATH>(W[0], W[1], W[2], W[3], W[4], W[5], K, WLm, WLp);
 #pragma unroll
         for (int si = 0; si < NS; si++) {
             const double Zrho_avg = 0.5 * (V[2][si] + V[3][si]);
             const double zc = Zrho_avg / (rc * c_avg);
 #pragma unroll
             for (int m = 0; m < 6; m++) W[m] = V[m][si] - zc * V[m][IP];
-            const double Wm = weno5js_side<MATH>(W[0], W[1], W[2], W[3], W[4], p);
-            const double Wp = weno5js_side<MATH>(W[5], W[4], W[3], W[2], W[1], p);
+            double Wm, Wp;
+            weno_pair<MATH>(W[0], W[1], W[2], W[3], W[4], W[5], K, Wm, Wp);
             const double yn = -0.5 * Zrho_avg / c_avg;
             const double yp = 0.5 * Zrho_avg / c_avg;
             V_minus[si] = yn * W0m + Wm + yp * WLm;
@@ -548,14 +656,12 @@ HB2_HD void face_midpoint(const double (&V)[6][Tr::NEQ], double c_cellL, double 
 #pragma unroll
         for (int a = 0; a < DIM; a++) {
             if (a == DIR) continue;
-            V_minus[IV + a] = weno5js_side<MATH>(V[0][IV + a], V[1][IV + a], V[2][IV + a], V[3][IV + a], V[4][IV + a], p);
-            V_plus[IV + a] = weno5js_side<MATH>(V[5][IV + a], V[4][IV + a], V[3][IV + a], V[2][IV + a], V[1][IV + a], p);
+            weno_pair<MATH>(V[0][IV + a], V[1][IV + a], V[2][IV + a], V[3][IV + a], V[4][IV + a], V[5][IV + a], K, V_minus[IV + a], V_plus[IV + a]);
         }
 #pragma unroll
         for (int si = 0; si < NS - 1; si++) {
             const int e = IP + 1 + si;
-            V_minus[e] = weno5js_side<MATH>(V[0][e], V[1][e], V[2][e], V[3][e], V[4][e], p);
-            V_plus[e] = weno5js_side<MATH>(V[5][e], V[4][e], V[3][e], V[2][e], V[1][e], p);
+            weno_pair<MATH>(V[0][e], V[1][e], V[2][e], V[3][e], V[4][e], V[5][e], K, V_minus[e], V_plus[e]);
         }
         V_minus[IV + DIR] = 0.5 * W0m + 0.5 * WLm;
         V_plus[IV + DIR] = 0.5 * W0p + 0.5 * WLp;

@@ -35,7 +35,9 @@ struct Ops {
     int (*advance)(const AdvanceArgs&, cudaStream_t);
 };
 
-const Ops* ops_exact();
-const Ops* ops_fast();
+const Ops* ops_exact();    /* WCNS5-JS, reference operation order */
+const Ops* ops_exact_z();  /* WCNS5-Z */
+const Ops* ops_exact_ld(); /* WCNS6-LD */
+const Ops* ops_fast();     /* WCNS5-JS, re-associated */
 
 }  // namespace hb2

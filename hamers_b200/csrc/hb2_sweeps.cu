@@ -1,9 +1,10 @@
 /*
  * hb2_sweeps.cu -- sm_100a kernels of the WCNS5-JS / HLLC-HLL path.
  *
- * Compiled TWICE into the product library:
- *   -DHB2_MATH=0 -fmad=false : reference operation order, bit-identical to the oracle
- *   -DHB2_MATH=1 -fmad=true  : FP64-instruction-minimal re-association (hb2_fast.cuh), <= 1e-12 relative
+ * Compiled FOUR times into the product library:
+ *   -DHB2_MATH=0 -fmad=false : reference operation order, bit-identical to the oracle (WCNS5-JS), and again with
+ *                              -DHB2_SCHEME=1 (WCNS5-Z) and -DHB2_SCHEME=2 (WCNS6-LD), SURVEY row f2
+ *   -DHB2_MATH=1 -fmad=true  : FP64-instruction-minimal re-association (hb2_fast.cuh), <= 1e-12 relative, WCNS5-JS
  * The arithmetic lives in hb2_core.cuh / hb2_fast.cuh, the thread mapping in hb2_sweep.cuh; this file holds the
  * __global__ entry points and their launchers.
  *
@@ -259,8 +260,17 @@ const Ops g_ops = {op_sensor, op_sweep, op_advance};
 }  // namespace
 
 #if HB2_MATH == 0
-const Ops* ops_exact() { return &g_ops; }
+#if HB2_SCHEME == HB2_WCNS5_Z
+const Ops* ops_exact_z() { return &g_ops; }
+#elif HB2_SCHEME == HB2_WCNS6_LD
+const Ops* ops_exact_ld() { return &g_ops; }
 #else
+const Ops* ops_exact() { return &g_ops; }
+#endif
+#else
+#if HB2_SCHEME != HB2_WCNS5_JS
+#error "the fast arithmetic is written for WCNS5-JS; the other interpolators are compiled with -DHB2_MATH=0"
+#endif
 const Ops* ops_fast() { return &g_ops; }
 #endif
 

@@ -44,7 +44,7 @@ ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::ConvectiveFluxReconstructorWC
     const int& num_eqn, const FLOW_MODEL::TYPE& flow_model_type, const HAMERS_SHARED_PTR<FlowModel>& flow_model,
     const HAMERS_SHARED_PTR<tbox::Database>& convective_flux_reconstructor_db)
     : ConvectiveFluxReconstructor(object_name, dim, grid_geometry, num_eqn, flow_model_type, flow_model, convective_flux_reconstructor_db),
-      d_math(HB2_MATH_EXACT)
+      d_scheme(HB2_WCNS5_JS), d_constant_q(4), d_constant_C(1.0e9), d_constant_alpha_tau(35.0), d_math(HB2_MATH_EXACT)
 {
     /* ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:22: four ghost cells in every direction */
     d_num_conv_ghosts = hier::IntVector::getOne(d_dim) * HB2_GHOSTS;
@@ -77,6 +77,40 @@ void ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::putToRestart(const HAMER
     restart_db->putInteger("d_constant_p", d_constant_p);
 }
 
+ConvectiveFluxReconstructorWCNS6_LD_HLLC_HLL_B200::ConvectiveFluxReconstructorWCNS6_LD_HLLC_HLL_B200(
+    const std::string& object_name, const tbox::Dimension& dim, const HAMERS_SHARED_PTR<geom::CartesianGridGeometry>& grid_geometry,
+    const int& num_eqn, const FLOW_MODEL::TYPE& flow_model_type, const HAMERS_SHARED_PTR<FlowModel>& flow_model,
+    const HAMERS_SHARED_PTR<tbox::Database>& convective_flux_reconstructor_db)
+    : ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200(object_name, dim, grid_geometry, num_eqn, flow_model_type, flow_model,
+                                                        convective_flux_reconstructor_db)
+{
+    d_scheme = HB2_WCNS6_LD;
+    /* ConvectiveFluxReconstructorWCNS6-LD-HLLC-HLL.cpp:343-361 */
+    d_constant_q = d_convective_flux_reconstructor_db->getIntegerWithDefault("constant_q", 4);
+    d_constant_q = d_convective_flux_reconstructor_db->getIntegerWithDefault("d_constant_q", d_constant_q);
+    d_constant_C = d_convective_flux_reconstructor_db->getDoubleWithDefault("constant_C", 1.0e9);
+    d_constant_C = d_convective_flux_reconstructor_db->getDoubleWithDefault("d_constant_C", d_constant_C);
+    d_constant_alpha_tau = d_convective_flux_reconstructor_db->getDoubleWithDefault("constant_alpha_tau", 35.0);
+    d_constant_alpha_tau = d_convective_flux_reconstructor_db->getDoubleWithDefault("d_constant_alpha_tau", d_constant_alpha_tau);
+}
+
+void ConvectiveFluxReconstructorWCNS6_LD_HLLC_HLL_B200::printClassData(std::ostream& os) const
+{
+    ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::printClassData(os);
+    os << "d_constant_q = " << d_constant_q << std::endl;
+    os << "d_constant_C = " << d_constant_C << std::endl;
+    os << "d_constant_alpha_tau = " << d_constant_alpha_tau << std::endl;
+}
+
+void ConvectiveFluxReconstructorWCNS6_LD_HLLC_HLL_B200::putToRestart(const HAMERS_SHARED_PTR<tbox::Database>& restart_db) const
+{
+    /* ConvectiveFluxReconstructorWCNS6-LD-HLLC-HLL.cpp:406-409 */
+    restart_db->putInteger("d_constant_p", d_constant_p);
+    restart_db->putInteger("d_constant_q", d_constant_q);
+    restart_db->putDouble("d_constant_C", d_constant_C);
+    restart_db->putDouble("d_constant_alpha_tau", d_constant_alpha_tau);
+}
+
 hb2_plan_t ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::getPlan(const hier::Patch& patch)
 {
     const int dim = d_dim.getValue();
@@ -91,6 +125,7 @@ hb2_plan_t ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::getPlan(const hier
         key.push_back(dx[a]);
     }
     key.push_back(d_math);
+    key.push_back(d_scheme);
     std::map<std::vector<double>, hb2_plan_t>::iterator it = d_plans.find(key);
     if (it != d_plans.end()) return it->second;
 
@@ -105,6 +140,10 @@ hb2_plan_t ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::getPlan(const hier
     desc.num_species = d_flow_model->getNumberOfSpecies();
     for (int s = 0; s < desc.num_species && s < HB2_MAX_SPECIES; s++) desc.species_gamma[s] = d_flow_model->getSpeciesGamma()[s];
     desc.weno_p = d_constant_p;
+    desc.scheme = d_scheme;
+    desc.weno_q = d_constant_q;
+    desc.weno_C = d_constant_C;
+    desc.weno_alpha_tau = d_constant_alpha_tau;
     desc.math = d_math;
     desc.device = -1;
     hb2_plan_t plan = 0;

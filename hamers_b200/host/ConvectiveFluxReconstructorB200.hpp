@@ -101,8 +101,8 @@ public:
                                                       const HAMERS_SHARED_PTR<tbox::Database>& convective_flux_reconstructor_db);
     ~ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200();
 
-    void printClassData(std::ostream& os) const;
-    void putToRestart(const HAMERS_SHARED_PTR<tbox::Database>& restart_db) const;
+    virtual void printClassData(std::ostream& os) const;
+    virtual void putToRestart(const HAMERS_SHARED_PTR<tbox::Database>& restart_db) const;
 
     /* Fully overwrites convective_flux (ghost 0, already multiplied by dt) on faces 0..N of every direction and "+="s
      * the advective-equation entries of source (ghost 0); the conservative variables (ghost 4, filled by the caller)
@@ -126,13 +126,47 @@ public:
      * operation order) or HB2_MATH_FAST */
     void setMathMode(int math) { d_math = math; }
 
+protected:
+    /* which nonlinear interpolator the plans use (HB2_WCNS5_JS here; the subclasses below set the others) */
+    int d_scheme;
+    int d_constant_p;
+    int d_constant_q;
+    double d_constant_C;
+    double d_constant_alpha_tau;
+
 private:
     hb2_plan_t getPlan(const hier::Patch& patch);
     void gatherConservative(hier::Patch& patch, const HAMERS_SHARED_PTR<hier::VariableContext>& ctx, std::vector<double*>& ptrs) const;
 
-    int d_constant_p;
     int d_math;
     std::map<std::vector<double>, hb2_plan_t> d_plans; /* keyed by (n, dx) */
+};
+
+/* "WCNS5_Z_HLLC_HLL" (ConvectiveFluxReconstructorWCNS5-Z-HLLC-HLL.cpp): same data flow, WCNS5-Z weights. */
+class ConvectiveFluxReconstructorWCNS5_Z_HLLC_HLL_B200 : public ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200 {
+public:
+    ConvectiveFluxReconstructorWCNS5_Z_HLLC_HLL_B200(const std::string& object_name, const tbox::Dimension& dim,
+                                                     const HAMERS_SHARED_PTR<geom::CartesianGridGeometry>& grid_geometry,
+                                                     const int& num_eqn, const FLOW_MODEL::TYPE& flow_model_type,
+                                                     const HAMERS_SHARED_PTR<FlowModel>& flow_model,
+                                                     const HAMERS_SHARED_PTR<tbox::Database>& convective_flux_reconstructor_db)
+        : ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200(object_name, dim, grid_geometry, num_eqn, flow_model_type, flow_model,
+                                                            convective_flux_reconstructor_db)
+    {
+        d_scheme = HB2_WCNS5_Z; /* constant_p: ConvectiveFluxReconstructorWCNS5-Z-HLLC-HLL.cpp:192-195, read by the base */
+    }
+};
+
+/* "WCNS6_LD_HLLC_HLL" (ConvectiveFluxReconstructorWCNS6-LD-HLLC-HLL.cpp): localized-dissipation six-point weights. */
+class ConvectiveFluxReconstructorWCNS6_LD_HLLC_HLL_B200 : public ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200 {
+public:
+    ConvectiveFluxReconstructorWCNS6_LD_HLLC_HLL_B200(const std::string& object_name, const tbox::Dimension& dim,
+                                                      const HAMERS_SHARED_PTR<geom::CartesianGridGeometry>& grid_geometry,
+                                                      const int& num_eqn, const FLOW_MODEL::TYPE& flow_model_type,
+                                                      const HAMERS_SHARED_PTR<FlowModel>& flow_model,
+                                                      const HAMERS_SHARED_PTR<tbox::Database>& convective_flux_reconstructor_db);
+    void printClassData(std::ostream& os) const;
+    void putToRestart(const HAMERS_SHARED_PTR<tbox::Database>& restart_db) const;
 };
 
 #endif

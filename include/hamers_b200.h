@@ -65,7 +65,20 @@ typedef struct hb2_patch_desc {
     int32_t weno_p;                           /* Convective_flux_reconstructor{constant_p}, default 2 */
     int32_t math;                             /* HB2_MATH_EXACT | HB2_MATH_FAST */
     int32_t device;                           /* CUDA device ordinal, -1 = current */
+    /* Which subclass of ConvectiveFluxReconstructorWCNS56 the plan stands for (ConvectiveFluxReconstructorManager.cpp:
+     * "WCNS5_JS_HLLC_HLL" / "WCNS5_Z_HLLC_HLL" / "WCNS6_LD_HLLC_HLL") and the WCNS6-LD constants
+     * Convective_flux_reconstructor{constant_q, constant_C, constant_alpha_tau} (defaults 4, 1.0e9, 35:
+     * ConvectiveFluxReconstructorWCNS6-LD-HLLC-HLL.cpp:343-361; 0 selects the default).  HB2_MATH_FAST exists for
+     * WCNS5-JS with constant_p = 2; every other combination runs the reference-order kernels. */
+    int32_t scheme;                           /* HB2_WCNS5_JS | HB2_WCNS5_Z | HB2_WCNS6_LD */
+    int32_t weno_q;
+    double weno_C;
+    double weno_alpha_tau;
 } hb2_patch_desc;
+
+#define HB2_WCNS5_JS 0
+#define HB2_WCNS5_Z 1
+#define HB2_WCNS6_LD 2
 
 typedef struct hb2_plan_s* hb2_plan_t;
 

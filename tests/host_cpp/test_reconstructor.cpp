@@ -31,7 +31,7 @@ int main(int argc, char** argv)
     int32_t hdr[7];
     double gam[4], dx[3], dt;
     must(std::fread(hdr, 4, 7, fi) == 7 && std::fread(gam, 8, 4, fi) == 4 && std::fread(dx, 8, 3, fi) == 3 && std::fread(&dt, 8, 1, fi) == 1, "short header");
-    const int d = hdr[0], model = hdr[4], ns = hdr[5], math = hdr[6];
+    const int d = hdr[0], model = hdr[4], ns = hdr[5], math = hdr[6] % 10, scheme = hdr[6] / 10;
     const tbox::Dimension dim((unsigned short)d);
 
     try {
@@ -44,9 +44,20 @@ int main(int argc, char** argv)
         const FLOW_MODEL::TYPE type = model == 0 ? FLOW_MODEL::SINGLE_SPECIES : FLOW_MODEL::FIVE_EQN_ALLAIRE;
         HAMERS_SHARED_PTR<FlowModel> flow_model(new FlowModel("flow model", dim, type, ns, flow_model_db));
         HAMERS_SHARED_PTR<geom::CartesianGridGeometry> grid_geometry(new geom::CartesianGridGeometry(dim));
-        ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200 reconstructor("WCNS5_JS_HLLC_HLL", dim, grid_geometry,
-                                                                        flow_model->getNumberOfEquations(), type, flow_model,
-                                                                        reconstructor_db);
+        /* what ConvectiveFluxReconstructorManager does with the input string (ConvectiveFluxReconstructorManager.cpp:37-48) */
+        const char* names[3] = {"WCNS5_JS_HLLC_HLL", "WCNS5_Z_HLLC_HLL", "WCNS6_LD_HLLC_HLL"};
+        must(scheme >= 0 && scheme < 3, "unknown scheme");
+        HAMERS_SHARED_PTR<ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200> holder;
+        if (scheme == 0)
+            holder.reset(new ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200(names[0], dim, grid_geometry, flow_model->getNumberOfEquations(),
+                                                                               type, flow_model, reconstructor_db));
+        else if (scheme == 1)
+            holder.reset(new ConvectiveFluxReconstructorWCNS5_Z_HLLC_HLL_B200(names[1], dim, grid_geometry, flow_model->getNumberOfEquations(),
+                                                                              type, flow_model, reconstructor_db));
+        else
+            holder.reset(new ConvectiveFluxReconstructorWCNS6_LD_HLLC_HLL_B200(names[2], dim, grid_geometry, flow_model->getNumberOfEquations(),
+                                                                               type, flow_model, reconstructor_db));
+        ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200& reconstructor = *holder;
         reconstructor.setMathMode(math);
         reconstructor.printClassData(std::cout);
         HAMERS_SHARED_PTR<tbox::Database> restart_db(new tbox::Database("restart"));

@@ -12,7 +12,8 @@ def _plan(desc, math):
     from hamers_b200 import abi
 
     return abi.Plan(desc.dim, desc.n, flow_model=desc.model, species_gamma=desc.gamma, dx=desc.dx,
-                    weno_p=desc.weno_p, math=math).use_torch_stream()
+                    weno_p=desc.weno_p, math=math, scheme=desc.scheme, weno_q=desc.weno_q, weno_C=desc.weno_C,
+                    weno_alpha_tau=desc.weno_alpha_tau).use_torch_stream()
 
 
 def _to_dev(a):
@@ -52,6 +53,43 @@ def test_flux_and_source_device(name, math, kind, oracle_lib, product_lib):
         assert np.array_equal(Sg, So)
     else:
         assert_fast_parity(Sg, So)
+    plan.close()
+
+
+@pytest.mark.parametrize("params", [dict(scheme=1), dict(scheme=1, weno_p=3), dict(scheme=2),
+                                    dict(scheme=2, weno_q=2, weno_C=10.0, weno_alpha_tau=2.0)])
+@pytest.mark.parametrize("name", list(CASES))
+def test_other_interpolators_flux_and_stage(name, params, oracle_lib, product_lib):
+    """WCNS5-Z and WCNS6-LD (reference-order kernels): side fluxes, sources and one fused SSP-RK3 stage
+    bit-identical to the oracle, on the shock-slab state (all branches) and with non-default constants."""
+    import dataclasses
+
+    import torch
+    from hamers_b200 import problems as pb
+
+    desc, U = make_case(name, "random")
+    desc = dataclasses.replace(desc, **params)
+    Q = pb.pad_periodic(U)
+    dt = 1.0e-3
+    S0 = np.random.default_rng(7).standard_normal((desc.neq,) + desc.cell_shape)
+    Fo, So = oracle_lib.compute_flux_and_source(desc, Q, dt, source=S0.copy())
+    base = dataclasses.replace(desc, scheme=0)
+    Fjs, _ = oracle_lib.compute_flux_and_source(base, Q, dt)
+    assert any((Fo[a] != Fjs[a]).mean() > 0.5 for a in range(desc.dim))   # really another interpolator
+    plan = _plan(desc, 1)      # HB2_MATH_FAST requested: falls back to the reference-order kernels of the scheme
+    Qd = _to_dev(Q)
+    Fd = [torch.full((desc.neq,) + desc.side_shape(a), float("nan"), dtype=torch.float64, device="cuda") for a in range(desc.dim)]
+    Sd = _to_dev(S0)
+    plan.compute_flux_and_source(Qd, dt, Fd, Sd)
+    out = torch.zeros_like(Qd)
+    plan.fused_stage([1.0], [1.0], [Qd], dt, out)
+    torch.cuda.synchronize()
+    for a in range(desc.dim):
+        assert np.array_equal(Fd[a].cpu().numpy(), Fo[a]), f"dir {a}"
+    assert np.array_equal(Sd.cpu().numpy(), So)
+    Fo2, So2 = oracle_lib.compute_flux_and_source(desc, Q, dt)
+    Uo = oracle_lib.advance_stage(desc, [1.0], [1.0], [Q], [Fo2], [So2])
+    assert np.array_equal(interior(desc, out.cpu().numpy()), interior(desc, Uo))
     plan.close()
 
 

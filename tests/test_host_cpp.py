@@ -35,11 +35,15 @@ def test_host_classes_compile_and_link(product_lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("math", [0, 1])
+@pytest.mark.parametrize("math", [0, 1, 10, 20])
 @pytest.mark.parametrize("name", list(CASES))
 def test_reconstructor_class_matches_oracle(name, math, oracle_lib, tmp_path):
+    """math: 0 exact / 1 fast WCNS5_JS_HLLC_HLL; 10 = WCNS5_Z_HLLC_HLL, 20 = WCNS6_LD_HLLC_HLL (reference-order kernels)."""
+    import dataclasses
+
     exe = build_driver()
     desc, U = make_case(name, "random")
+    desc = dataclasses.replace(desc, scheme=math // 10)
     Q = pb.pad_periodic(U)
     dt = 7.5e-4
     fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
@@ -53,6 +57,9 @@ def test_reconstructor_class_matches_oracle(name, math, oracle_lib, tmp_path):
     r = subprocess.run([exe, fin, fout], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "d_constant_p = 2" in r.stdout
+    if math == 20:
+        assert "d_constant_alpha_tau = 35" in r.stdout
+    math = math % 10
     out = np.fromfile(fout)
     Fo, So = oracle_lib.compute_flux_and_source(desc, Q, dt)
     Uo = oracle_lib.advance_stage(desc, [1.0], [1.0], [Q], [Fo], [So])

@@ -10,7 +10,7 @@ from hamers_b200 import problems as pb
 EXPECTED_RATE = 4.8
 
 
-def _run(orc, dim, model, levels, steps_base):
+def _run(orc, dim, model, levels, steps_base, scheme=0):
     errs = []
     for L in range(levels):
         N = 8 * 2 ** L
@@ -18,7 +18,7 @@ def _run(orc, dim, model, levels, steps_base):
             U, dx, gam = pb.convergence_single_species(dim, N)
         else:
             U, dx, gam = pb.convergence_five_eqn(dim, N)
-        lvl = orc.PatchDesc(dim=dim, n=(N,) * dim, model=model, ns=len(gam), gamma=gam, dx=dx)
+        lvl = orc.PatchDesc(dim=dim, n=(N,) * dim, model=model, ns=len(gam), gamma=gam, dx=dx, scheme=scheme)
         dt = 0.001 * (2.0 / 8) / 2 ** L
         nsteps = steps_base * 2 ** L
         orc.level_advance(lvl, (8,) * dim, U, dt, nsteps, nthreads=0)
@@ -49,6 +49,14 @@ def test_3d_five_eqn_order(oracle_lib):
 def test_2d_five_eqn_order(oracle_lib):
     errs, rates = _run(oracle_lib, 2, 1, 4, 8)
     assert rates[-1] > EXPECTED_RATE, (errs, rates)
+
+
+@pytest.mark.parametrize("scheme,rate", [(1, 4.8), (2, 5.8)])
+def test_2d_single_species_order_of_the_other_interpolators(scheme, rate, oracle_lib):
+    """WCNS5_Z_HLLC_HLL must exceed 4.8 and WCNS6_LD_HLLC_HLL 5.8
+    (tests/2D_convergence_test_single_species/convergence_test.py:8-16)."""
+    errs, rates = _run(oracle_lib, 2, 0, 4, 8, scheme=scheme)
+    assert rates[-1] > rate, (errs, rates)
 
 
 def test_level_advance_is_patch_size_independent(oracle_lib):
