@@ -71,8 +71,9 @@ _LIB = None
 
 def load_library():
     """Load libhamers_b200.so; raises (never falls back) when it is missing."""
-    global _LIB
+    global _LIB, SO
     if _LIB is None:
+        SO = os.environ.get("HAMERS_B200_LIB", SO)   # tuning variants (tools/build_variant.py)
         if not os.path.exists(SO):
             raise HamersB200Error(
                 f"{SO} not found: build it with `python -m hamers_b200.build` (there is no CPU fallback)")

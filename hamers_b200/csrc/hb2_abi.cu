@@ -530,10 +530,10 @@ int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* out)
         p->seg_len[a] = sl;
     }
     {
-        /* sensor pass: 61 x 8 tiles marching along z; enough segments for ~4 waves of 3 resident blocks per SM, at
+        /* sensor pass: 61 x 8 tiles marching along z; enough segments for ~4 waves of 2 resident blocks per SM, at
          * least 16 planes each (every segment re-reads 3 planes) */
         const long long tiles = (long long)((p->G.n[0] + 3 + 60) / 61) * ((p->G.n[1] + 3 + 7) / 8);
-        long long nseg = (148LL * 3 * 4 + tiles - 1) / tiles;
+        long long nseg = (148LL * 2 * 4 + tiles - 1) / tiles;
         const long long planes = p->G.n[2] + 3;
         const long long maxseg = planes / 16 > 0 ? planes / 16 : 1;
         if (nseg > maxseg) nseg = maxseg;

@@ -6,11 +6,13 @@
  * re-read per direction by the face loops that form s = -theta_avg/(|theta_avg| + Omega_avg + eps) and select HLLC-HLL
  * where s > 0.65 (:2072-2134).  Here a 256-thread block owns a TX x TY tile of cells and MARCHES along z:
  *
- *     A(t)  velocities of plane t      on the tile + halo (2 low, 1 high)  -> 3-plane shared-memory ring
- *           (density and momentum of plane t+1 are fetched into registers before B(t), so the HBM latency hides behind
- *           the work on plane t)
- *     B(t)  theta, Omega of plane t-1  on the tile + 1 low halo            -> 2-plane shared-memory ring
- *     C(t)  decisions of plane t-1     bit d = face between cells (c - e_d) and c, one byte per cell  -> HBM
+ *     A(t)  velocities of plane t      on the tile + halo (2 low, 1 high)  -> 4-plane shared-memory ring
+ *           (density and momentum of plane t+1 are fetched into registers right behind, so the HBM latency hides
+ *           behind the work on plane t)
+ *     ---- the ONE barrier of the iteration ----
+ *     B(t)  theta, Omega of plane t-1  on the tile + 1 low halo            -> 3-plane shared-memory ring
+ *     C(t)  decisions of plane t-2     bit d = face between cells (c - e_d) and c, one byte per cell  -> HBM
+ *           (from the theta/Omega planes t-2 and t-3 of earlier iterations: B and C share a phase)
  *
  * so the only HBM traffic is one read of density and momentum (L2 absorbs the halo overlap of neighbouring tiles) and
  * one byte written per cell: 33 B/cell instead of the 17 patch-sized double arrays the reference streams.
@@ -32,19 +34,21 @@ struct SensorArgs {
 
 template <class Tr>
 struct SensorShape {
-    static constexpr int NT = 256;
-    static constexpr int NX = 64, NY = NT / NX;    /* thread layout: tx = tid % 64 along x, ty = tid / 64 */
+    static constexpr int NT = 384;
+    static constexpr int NX = 64, NY = NT / NX;    /* thread layout: tx = tid % 64 along x, ty = tid / 64 (6 rows) */
     static constexpr int VX = NX, VY = 11;         /* velocity tile: cells i0-2 .. i0+TX, one row of threads wide */
     static constexpr int TX = VX - 3, TY = VY - 3; /* cells whose decisions the block produces per plane (61 x 8) */
     static constexpr int SX = TX + 1, SY = TY + 1; /* theta/Omega tile: cells i0-1 .. i0+TX-1 */
     static constexpr int VP = VX * VY, SP = SX * SY;
     static constexpr int KY = (VY + NY - 1) / NY;  /* rows per thread */
-    static constexpr int NVP = (Tr::DIM == 3) ? 3 : 1;
-    static constexpr int NSP = (Tr::DIM == 3) ? 2 : 1;
+    /* ring depths for ONE barrier per plane: a velocity plane is overwritten two barriers after its last reader, a
+     * theta/Omega plane is read (decisions of planes t-2) while plane t-1 is being written */
+    static constexpr int NVP = (Tr::DIM == 3) ? 4 : 1;
+    static constexpr int NSP = (Tr::DIM == 3) ? 3 : 1;
     static constexpr int OFF_S = Tr::DIM * NVP * VP;
     static constexpr int SMEM_DOUBLES = OFF_S + 2 * NSP * SP;
-    HB2_HD static int vslot(int t) { return (Tr::DIM == 3) ? (t + 6) % 3 : 0; } /* t >= -3 */
-    HB2_HD static int sslot(int t) { return (Tr::DIM == 3) ? ((t + 4) & 1) : 0; }
+    HB2_HD static int vslot(int t) { return (Tr::DIM == 3) ? ((t + 8) & 3) : 0; } /* t >= -3 */
+    HB2_HD static int sslot(int t) { return (Tr::DIM == 3) ? (t + 6) % 3 : 0; }  /* t >= -3 */
     /* decisions are produced on cells -1..N+1 */
     HB2_HD static int tiles_x(const Geom& G) { return (G.n[0] + 3 + TX - 1) / TX; }
     HB2_HD static int tiles_y(const Geom& G) { return (G.n[1] + 3 + TY - 1) / TY; }

@@ -30,7 +30,7 @@ constexpr int MATH = HB2_MATH;
 
 /* the shock-sensor decisions of the whole patch in one pass (hb2_sensor.cuh) */
 template <class Tr>
-__global__ void __launch_bounds__(256, 3) k_sensor(const __grid_constant__ SensorArgs A)
+__global__ void __launch_bounds__(384, 2) k_sensor(const __grid_constant__ SensorArgs A)
 {
     extern __shared__ double smem[];
     const int tid = (int)threadIdx.x;
@@ -42,13 +42,12 @@ __global__ void __launch_bounds__(256, 3) k_sensor(const __grid_constant__ Senso
             sensor_phase_velocity<Tr, MATH>(smem, tid, t, R);
         }
         sensor_phase_fetch<Tr>(A, T, tid, T.kb, R);
-        for (int t = T.kb; t <= T.ke; t++) {
-            sensor_phase_velocity<Tr, MATH>(smem, tid, t, R);
+        for (int t = T.kb; t <= T.ke + 1; t++) {
+            if (t <= T.ke) sensor_phase_velocity<Tr, MATH>(smem, tid, t, R);
             if (t < T.ke) sensor_phase_fetch<Tr>(A, T, tid, t + 1, R);
             __syncthreads();
-            sensor_phase_gradient<Tr, MATH>(A, smem, T, tid, t - 1);
-            __syncthreads();
-            if (t >= T.kb + 1) sensor_phase_decision<Tr, MATH>(A, smem, T, tid, t - 1);
+            if (t <= T.ke) sensor_phase_gradient<Tr, MATH>(A, smem, T, tid, t - 1);
+            if (t >= T.kb + 2) sensor_phase_decision<Tr, MATH>(A, smem, T, tid, t - 2);
         }
     } else {
         sensor_phase_fetch<Tr>(A, T, tid, 0, R);

@@ -132,13 +132,16 @@ static void run_sweeps(DirArgs A0, int sensor_seg_len, int seg_len, double* cons
                                 sensor_phase_velocity<Tr, MATH>(sm.data(), tid, t, R[tid]);
                             });
                         each([&](int tid) { sensor_phase_fetch<Tr>(S, T, tid, T.kb, R[tid]); });
-                        for (int t = T.kb; t <= T.ke; t++) {
+                        for (int t = T.kb; t <= T.ke + 1; t++) {
                             each([&](int tid) {
-                                sensor_phase_velocity<Tr, MATH>(sm.data(), tid, t, R[tid]);
+                                if (t <= T.ke) sensor_phase_velocity<Tr, MATH>(sm.data(), tid, t, R[tid]);
                                 if (t < T.ke) sensor_phase_fetch<Tr>(S, T, tid, t + 1, R[tid]);
                             });
-                            each([&](int tid) { sensor_phase_gradient<Tr, MATH>(S, sm.data(), T, tid, t - 1); });
-                            if (t >= T.kb + 1) each([&](int tid) { sensor_phase_decision<Tr, MATH>(S, sm.data(), T, tid, t - 1); });
+                            /* the one barrier */
+                            each([&](int tid) {
+                                if (t <= T.ke) sensor_phase_gradient<Tr, MATH>(S, sm.data(), T, tid, t - 1);
+                                if (t >= T.kb + 2) sensor_phase_decision<Tr, MATH>(S, sm.data(), T, tid, t - 2);
+                            });
                         }
                     } else {
                         each([&](int tid) {
