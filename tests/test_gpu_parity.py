@@ -243,6 +243,29 @@ def test_spectral_radii_and_stable_dt(name, oracle_lib, product_lib):
     plan.close()
 
 
+@pytest.mark.parametrize("name", ["ss3d", "fe2d"])
+def test_advance_level_on_host_buffers(name, oracle_lib, product_lib):
+    """hb2_advance_level_host (the end-to-end call of bench.py): U^n on the host in, three stages on the device,
+    U^{n+1} out -- bit-identical to the oracle's level advance in the exact build (the incoming ghost cells of a
+    periodic level are ignored: the device fills them)."""
+    from hamers_b200 import problems as pb
+
+    desc, U = make_case(name, "random")
+    dt = 3.0e-4
+    Uo = U.copy()
+    oracle_lib.level_advance(desc, desc.n, Uo, dt, 2)
+    plan = _plan(desc, 0)
+    host = pb.pad_periodic(U)
+    sl = (slice(None),) + tuple(slice(4, -4) for _ in range(desc.dim))
+    ghost_mask = np.ones(host.shape, dtype=bool)
+    ghost_mask[sl] = False
+    host[ghost_mask] = -777.0          # ghosts are the device's business on a periodic level
+    for _ in range(2):
+        plan.advance_level_host(host, dt)
+    assert np.array_equal(host[sl], Uo)
+    plan.close()
+
+
 def test_pack_unpack_many_boxes(product_lib):
     """hb2_pack_boxes_dev / hb2_unpack_boxes_dev: several boxes (interior slabs, ghost regions, an edge bar) in one
     launch, at arbitrary positions of one buffer."""
