@@ -285,6 +285,7 @@ class UniformLevel:
                     per_buffer[b][o] = bases[peer][b]
             self.push_tables = [self.plan.push_table(t) for t in per_buffer]
             self._flag = torch.zeros(1, dtype=torch.float32, device="cuda")
+        self._force_fill = os.environ.get("HB2_LEVEL_FORCE_FILL", "0") == "1"
         self.ghosts_valid = False
         self.cur = 0
         self.phases = self.decomp.halo_schedule()
@@ -351,6 +352,8 @@ class UniformLevel:
             if self.dist is not None:
                 # orders "every rank's pushes into my ghosts are complete" before the next stage (stream-ordered)
                 self.dist.all_reduce(self._flag)
+            if self._force_fill:      # diagnostic (HB2_LEVEL_FORCE_FILL=1): time the push with the ghosts kept valid regardless
+                self.fill_ghosts(S[out])
         else:
             self.plan.fused_stage(alpha, beta, [S[i] for i in states], dt, S[out])
             self.fill_ghosts(S[out])
