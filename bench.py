@@ -158,8 +158,9 @@ def run_reference(args):
 
 
 def workload_config(args, sample_override=None):
+    sch = {"js": "WCNS5_JS_HLLC_HLL", "z": "WCNS5_Z_HLLC_HLL", "ld": "WCNS6_LD_HLLC_HLL"}[getattr(args, "scheme", "js")]
     name = ("3D single-species Euler" if args.model == "ss" else "3D five-equation Allaire") + \
-           f", WCNS5_JS_HLLC_HLL, SSP-RK3, periodic uniform level {args.size}^3 (convergence-test IC scaled up)"
+           f", {sch}, SSP-RK3, periodic uniform level {args.size}^3 (convergence-test IC scaled up)"
     cfg = {"workload": name, "size": args.size, "math": args.math, "dt": "0.001*dx", "ghosts": 4,
            "l2_policy": "inputs (>= 5 GB per state) exceed the 126 MB L2; no flush needed",
            "step": "one SSP-RK3 time step = 3 hot-path passes (ghost fill + sensor + x/y/z sweeps with fused RK update)"}
@@ -192,7 +193,8 @@ def run_ours(args):
     else:
         Nglob = tuple(args.size * g for g in grid)
     domain_len = 2.0
-    level = UniformLevel(3, Nglob, flow_model=flow_model, species_gamma=gam, math=math)
+    scheme = {"js": abi.WCNS5_JS, "z": abi.WCNS5_Z, "ld": abi.WCNS6_LD}[args.scheme]
+    level = UniformLevel(3, Nglob, flow_model=flow_model, species_gamma=gam, math=math, scheme=scheme)
     # keep dx = 2/size in weak scaling too (same physics per cell)
     make_ic_device(level, args.model)
     dx = level.dx[0]
@@ -301,7 +303,7 @@ def run_ours(args):
     # ---- end-to-end: host buffers through the C ABI (N = 1: advanceLevel on host memory) ----------
     if world == 1 and not args.no_e2e:
         n = args.e2e_size
-        plan = abi.Plan(3, (n,) * 3, flow_model=flow_model, species_gamma=gam, dx=(domain_len / n,) * 3, math=math)
+        plan = abi.Plan(3, (n,) * 3, flow_model=flow_model, species_gamma=gam, dx=(domain_len / n,) * 3, math=math, scheme=scheme)
         ncomp = plan.ncomp
         host = torch.empty((ncomp,) + plan.ghost_shape, dtype=torch.float64).pin_memory()
         lvl2 = level if n == args.size else None
@@ -375,6 +377,8 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--model", default="ss", choices=["ss", "fe"])
     ap.add_argument("--math", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--scheme", default="js", choices=["js", "z", "ld"],
+                    help="nonlinear interpolator: WCNS5_JS (headline), WCNS5_Z, WCNS6_LD (reference-order kernels only)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--ref-size", type=int, default=128)
     ap.add_argument("--e2e-size", type=int, default=0)

@@ -260,6 +260,66 @@ HB2_HD void weno5js_pair_fast(double w0, double w1, double w2, double w3, double
     }
 }
 
+/* WCNS5-Z (ConvectiveFluxReconstructorWCNS5-Z-HLLC-HLL.cpp:78-165) in the same shared form: with b_k = 4(beta_k + eps),
+ * B_k = b_k^2 and T = (b_0 - b_2)^2 = (4 tau_5)^2 the un-normalised weights d_k (1 + (tau_5/(beta_k + eps))^2) become
+ * d_k (B_k + T) prod_{j != k} B_j over the common denominator prod_j B_j: one reciprocal per side, 82 FP64 instructions
+ * per minus/plus pair.  constant_p = 2 only (other exponents run the reference-order kernels). */
+HB2_HD void weno5z_pair_fast(double w0, double w1, double w2, double w3, double w4, double w5, double eps4,
+                             double& wm, double& wp)
+{
+    const double e01 = w1 - w0, e12 = w2 - w1, e23 = w3 - w2, e34 = w4 - w3, e45 = w5 - w4;
+    const double s012 = e12 - e01, s123 = e23 - e12, s234 = e34 - e23, s345 = e45 - e34;
+    const double q012 = fma((13.0 / 3.0) * s012, s012, eps4);
+    const double q123 = fma((13.0 / 3.0) * s123, s123, eps4);
+    const double q234 = fma((13.0 / 3.0) * s234, s234, eps4);
+    const double q345 = fma((13.0 / 3.0) * s345, s345, eps4);
+    const double f0 = fma(2.0, e12, s012);
+    const double f1 = e12 + e23;
+    const double f2 = fma(-2.0, e23, s234);
+    const double b0 = fma(f0, f0, q012);
+    const double b1 = fma(f1, f1, q123);
+    const double b2 = fma(f2, f2, q234);
+    const double g0 = fma(-2.0, e34, s345);
+    const double g1 = e23 + e34;
+    const double g2 = fma(2.0, e23, s123);
+    const double c0 = fma(g0, g0, q345);
+    const double c1 = fma(g1, g1, q234);
+    const double c2 = fma(g2, g2, q123);
+    const double d1 = s012 - s123, d2 = s123 - s234, d3 = s234 - s345;
+    const double h = fma(0.5, e23, w2);
+    {
+        const double tb = b0 - b2;
+        const double T = tb * tb;
+        const double B0 = b0 * b0, B1 = b1 * b1, B2 = b2 * b2;
+        const double a0 = (B0 + T) * (B1 * B2), a1 = (B1 + T) * (B0 * B2), a2 = (B2 + T) * (B0 * B1);
+        const double sum = fma(5.0, a2, fma(10.0, a1, a0));
+        const double P1 = fma(-0.125, s123, h);
+        const double u0 = a0 * d1, u2 = a2 * d2;
+        wm = fma(fma(0.625, u2, 0.375 * u0), rcp_fast(sum), P1);
+    }
+    {
+        const double tb = c0 - c2;
+        const double T = tb * tb;
+        const double B0 = c0 * c0, B1 = c1 * c1, B2 = c2 * c2;
+        const double a0 = (B0 + T) * (B1 * B2), a1 = (B1 + T) * (B0 * B2), a2 = (B2 + T) * (B0 * B1);
+        const double sum = fma(5.0, a2, fma(10.0, a1, a0));
+        const double P1 = fma(-0.125, s234, h);
+        const double u0 = a0 * d3, u2 = a2 * d2;
+        wp = fma(-fma(0.625, u2, 0.375 * u0), rcp_fast(sum), P1);
+    }
+}
+
+/* the fast pair of this translation unit's interpolator (HB2_SCHEME; WCNS6-LD has no fast form) */
+HB2_HD void weno_pair_fast(double w0, double w1, double w2, double w3, double w4, double w5, double eps4, double& wm,
+                           double& wp)
+{
+#if HB2_SCHEME == HB2_WCNS5_Z
+    weno5z_pair_fast(w0, w1, w2, w3, w4, w5, eps4, wm, wp);
+#else
+    weno5js_pair_fast(w0, w1, w2, w3, w4, w5, eps4, wm, wp);
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------
  * HLLC (always) and HLLC-HLL (when `hybrid`) midpoint flux from the two interpolated states
  * ---------------------------------------------------------------------------------------- */
@@ -461,7 +521,7 @@ HB2_HD void face_midpoint_fast(const double* win, bool hybrid, const Consts& K, 
                 for (int m = 0; m < 6; m++) w[m] = fma(b, Y[m * MS], w[m]);
             }
             double wm, wp;
-            weno5js_pair_fast(w[0], w[1], w[2], w[3], w[4], w[5], e4, wm, wp);
+            weno_pair_fast(w[0], w[1], w[2], w[3], w[4], w[5], e4, wm, wp);
             if (f == 0) {
                 rm = h_cc * wm; rp = h_cc * wp;
                 um = -h_rc * wm; up = -h_rc * wp;
@@ -529,7 +589,7 @@ HB2_HD void face_midpoint_fast(const double* win, bool hybrid, const Consts& K, 
                 for (int m = 0; m < 6; m++) w[m] = fma(b, Y[m * MS], w[m]);
             }
             double wm, wp;
-            weno5js_pair_fast(w[0], w[1], w[2], w[3], w[4], w[5], eps4, wm, wp);
+            weno_pair_fast(w[0], w[1], w[2], w[3], w[4], w[5], eps4, wm, wp);
             if (f == 0) {
                 z0m = -yh0 * wm; z0p = -yh0 * wp;
                 z1m = -yh1 * wm; z1p = -yh1 * wp;

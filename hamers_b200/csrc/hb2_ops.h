@@ -39,5 +39,6 @@ const Ops* ops_exact();    /* WCNS5-JS, reference operation order */
 const Ops* ops_exact_z();  /* WCNS5-Z */
 const Ops* ops_exact_ld(); /* WCNS6-LD */
 const Ops* ops_fast();     /* WCNS5-JS, re-associated */
+const Ops* ops_fast_z();   /* WCNS5-Z, re-associated */
 
 }  // namespace hb2

@@ -1,10 +1,11 @@
 /*
  * hb2_sweeps.cu -- sm_100a kernels of the WCNS5-JS / HLLC-HLL path.
  *
- * Compiled FOUR times into the product library:
+ * Compiled FIVE times into the product library:
  *   -DHB2_MATH=0 -fmad=false : reference operation order, bit-identical to the oracle (WCNS5-JS), and again with
  *                              -DHB2_SCHEME=1 (WCNS5-Z) and -DHB2_SCHEME=2 (WCNS6-LD), SURVEY row f2
- *   -DHB2_MATH=1 -fmad=true  : FP64-instruction-minimal re-association (hb2_fast.cuh), <= 1e-12 relative, WCNS5-JS
+ *   -DHB2_MATH=1 -fmad=true  : FP64-instruction-minimal re-association (hb2_fast.cuh), <= 1e-12 relative, WCNS5-JS and
+ *                              (-DHB2_SCHEME=1) WCNS5-Z
  * The arithmetic lives in hb2_core.cuh / hb2_fast.cuh, the thread mapping in hb2_sweep.cuh; this file holds the
  * __global__ entry points and their launchers.
  *
@@ -267,10 +268,13 @@ const Ops* ops_exact_ld() { return &g_ops; }
 const Ops* ops_exact() { return &g_ops; }
 #endif
 #else
-#if HB2_SCHEME != HB2_WCNS5_JS
-#error "the fast arithmetic is written for WCNS5-JS; the other interpolators are compiled with -DHB2_MATH=0"
-#endif
+#if HB2_SCHEME == HB2_WCNS5_Z
+const Ops* ops_fast_z() { return &g_ops; }
+#elif HB2_SCHEME == HB2_WCNS5_JS
 const Ops* ops_fast() { return &g_ops; }
+#else
+#error "WCNS6-LD has no fast arithmetic: compile it with -DHB2_MATH=0"
+#endif
 #endif
 
 }  // namespace hb2
