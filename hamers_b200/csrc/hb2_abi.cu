@@ -507,7 +507,8 @@ int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* out)
     /* the fast kernels are written for constant_p = 2 (the reference default); other exponents use the exact build */
     p->ops = (d->math == HB2_MATH_EXACT || p->d.weno_p != 2) ? ops_exact() : ops_fast();
     if (d->scheme == HB2_WCNS5_Z) p->ops = (d->math == HB2_MATH_FAST && p->d.weno_p == 2) ? ops_fast_z() : ops_exact_z();
-    if (d->scheme == HB2_WCNS6_LD) p->ops = ops_exact_ld();
+    if (d->scheme == HB2_WCNS6_LD)
+        p->ops = (d->math == HB2_MATH_FAST && p->d.weno_p == 2 && p->K.weno_q == 4) ? ops_fast_ld() : ops_exact_ld();
     p->ncell_i = (long long)p->G.n[0] * p->G.n[1] * p->G.n[2];
     for (int a = 0; a < 3; a++) {
         long long ee[3] = {p->G.n[0], p->G.n[1], p->G.n[2]};
@@ -704,7 +705,7 @@ int hb2_fused_stage_push_dev(hb2_plan_t p, int32_t ncoef, const double* alpha, c
             A.beta = beta[ncoef - 1];
             A.nterm = 0;
             /* fast build: the flux state (m = ncoef-1) is rebuilt from the primitive ring instead of being loaded */
-            const bool qrec = (p->ops == ops_fast() || p->ops == ops_fast_z());
+            const bool qrec = (p->ops == ops_fast() || p->ops == ops_fast_z() || p->ops == ops_fast_ld());
             A.alpha_q = alpha[ncoef - 1];
             for (int m = 0; m < (qrec ? ncoef - 1 : ncoef); m++)
                 if (alpha[m] != 0.0) {

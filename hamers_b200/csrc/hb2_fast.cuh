@@ -309,12 +309,83 @@ HB2_HD void weno5z_pair_fast(double w0, double w1, double w2, double w3, double 
     }
 }
 
-/* the fast pair of this translation unit's interpolator (HB2_SCHEME; WCNS6-LD has no fast form) */
-HB2_HD void weno_pair_fast(double w0, double w1, double w2, double w3, double w4, double w5, double eps4, double& wm,
-                           double& wp)
+/* WCNS6-LD (ConvectiveFluxReconstructorWCNS6-LD-HLLC-HLL.cpp:23-339), one side, from the six values (a..f, upwind
+ * cell c), the three shared smoothness indicators b_k = beta_k + eps and sigma.  constant_p = 2, constant_q = 4.
+ * The reference's 3 + 4 + 1 divisions by (beta_k + eps) and (beta_avg + eps) become five reciprocals shared by the
+ * upwind and the central weights, the two normalisations one reciprocal each; the R_tau > alpha_tau switch is a select.
+ * beta_3 is the reference's polynomial as written (FMA-contracted). */
+HB2_HD double weno6ld_side_fast(double a, double b, double c, double d, double e, double f, double b0, double b1,
+                                double b2, double sigma, double eps_b, const Consts& K)
+{
+    const double beta_3 = (1.0 / 232243200.0) *
+        fma(a, fma(525910327.0, a, fma(-4562164630.0, b, fma(7799501420.0, c, fma(-6610694540.0, d, fma(2794296070.0, e, -472758974.0 * f))))),
+        fma(5.0 * b, fma(2146987907.0, b, fma(-7722406988.0, c, fma(6763559276.0, d, fma(-2926461814.0, e, 503766638.0 * f)))),
+        fma(20.0 * c, fma(1833221603.0, c, fma(-3358664662.0, d, fma(1495974539.0, e, -263126407.0 * f))),
+        fma(20.0 * d, fma(1607794163.0, d, fma(-1486026707.0, e, 268747951.0 * f)),
+        fma(5.0 * e, fma(1432381427.0, e, -536951582.0 * f), 263126407.0 * f * f)))));
+    const double b3 = beta_3 + eps_b;
+    const double r0 = rcp_fast(b0), r1 = rcp_fast(b1), r2 = rcp_fast(b2), r3 = rcp_fast(b3);
+    /* upwind (WCNS5-Z) weights */
+    const double tau_5 = fabs(b0 - b2);
+    const double y0 = tau_5 * r0, y1 = tau_5 * r1, y2 = tau_5 * r2;
+    const double u0 = (1.0 / 16.0) * fma(y0, y0, 1.0), u1 = (5.0 / 8.0) * fma(y1, y1, 1.0), u2 = (5.0 / 16.0) * fma(y2, y2, 1.0);
+    const double ur = rcp_fast(u0 + u1 + u2);
+    /* central weights: (beta_0 + beta_2 + 6 beta_1)/8 + eps = (b0 + b2 + 6 b1)/8 */
+    const double bavg = 0.125 * fma(6.0, b1, b0 + b2);
+    const double tau_6 = fabs(b3 - bavg);
+    const double x0 = tau_6 * r0, x1 = tau_6 * r1, x2 = tau_6 * r2, x3 = tau_6 * r3;
+    const double x0s = x0 * x0, x1s = x1 * x1, x2s = x2 * x2, x3s = x3 * x3;
+    const double c0 = (1.0 / 32.0) * fma(x0s, x0s, K.weno_C), c1 = (15.0 / 32.0) * fma(x1s, x1s, K.weno_C);
+    const double c2 = (15.0 / 32.0) * fma(x2s, x2s, K.weno_C), c3 = (1.0 / 32.0) * fma(x3s, x3s, K.weno_C);
+    const double cr = rcp_fast((c0 + c1) + (c2 + c3));
+    double o0 = c0 * cr, o1 = c1 * cr, o2 = c2 * cr, o3 = c3 * cr;
+    const double R_tau = tau_6 * rcp_fast(bavg);
+    const bool blend = R_tau > K.weno_alpha_tau;
+    const double sg = blend ? sigma : 0.0;      /* omega = sigma omega_upwind + (1 - sigma) omega_central where blended */
+    const double su = sg * ur, om = 1.0 - sg;
+    o0 = fma(su, u0, om * o0);
+    o1 = fma(su, u1, om * o1);
+    o2 = fma(su, u2, om * o2);
+    o3 = om * o3;
+    return fma(0.375 * o0, a, fma(fma(-1.25, o0, -0.125 * o1), b, fma(fma(1.875, o0, fma(0.75, o1, 0.375 * o2)), c,
+           fma(fma(0.375, o1, fma(0.75, o2, 1.875 * o3)), d, fma(fma(-0.125, o2, -1.25 * o3), e, 0.375 * o3 * f)))));
+}
+
+HB2_HD void weno6ld_pair_fast(double w0, double w1, double w2, double w3, double w4, double w5, double eps4,
+                              const Consts& K, double& wm, double& wp)
+{
+    /* eps4 = 4 eps scale^2 (the caller hands in characteristic variables scaled by 1 or 2) */
+    const double eps_b = 0.25 * eps4;
+    const double eps_s = (eps4 > 6.0 * HB2_EPS) ? 2.0 * HB2_EPS : HB2_EPS;
+    const double e01 = w1 - w0, e12 = w2 - w1, e23 = w3 - w2, e34 = w4 - w3, e45 = w5 - w4;
+    const double s012 = e12 - e01, s123 = e23 - e12, s234 = e34 - e23, s345 = e45 - e34;
+    /* sigma of the unmirrored stencil, both sides (:23-39): alpha_1..3 = e12, e23, e34 */
+    const double a23 = fabs(e23);
+    const double theta_1 = fabs(s123) * rcp_fast(fabs(e12) + a23 + eps_s);
+    const double theta_2 = fabs(s234) * rcp_fast(a23 + fabs(e34) + eps_s);
+    const double sigma = max_fast(theta_1, theta_2);
+    /* beta_k + eps = 13/12 s^2 + (f/2)^2 + eps */
+    const double q012 = fma((13.0 / 12.0) * s012, s012, eps_b);
+    const double q123 = fma((13.0 / 12.0) * s123, s123, eps_b);
+    const double q234 = fma((13.0 / 12.0) * s234, s234, eps_b);
+    const double q345 = fma((13.0 / 12.0) * s345, s345, eps_b);
+    const double hm = 0.5 * (e12 + e23), hp = 0.5 * (e23 + e34);
+    const double f0 = fma(0.5, s012, e12), f2 = fma(0.5, s234, -e23);
+    const double g0 = fma(0.5, s345, -e34), g2 = fma(0.5, s123, e23);
+    const double b0 = fma(f0, f0, q012), b1 = fma(hm, hm, q123), b2 = fma(f2, f2, q234);
+    const double c0 = fma(g0, g0, q345), c1 = fma(hp, hp, q234), c2 = fma(g2, g2, q123);
+    wm = weno6ld_side_fast(w0, w1, w2, w3, w4, w5, b0, b1, b2, sigma, eps_b, K);
+    wp = weno6ld_side_fast(w5, w4, w3, w2, w1, w0, c0, c1, c2, sigma, eps_b, K);
+}
+
+/* the fast pair of this translation unit's interpolator (HB2_SCHEME) */
+HB2_HD void weno_pair_fast(double w0, double w1, double w2, double w3, double w4, double w5, double eps4, const Consts& K,
+                           double& wm, double& wp)
 {
 #if HB2_SCHEME == HB2_WCNS5_Z
     weno5z_pair_fast(w0, w1, w2, w3, w4, w5, eps4, wm, wp);
+#elif HB2_SCHEME == HB2_WCNS6_LD
+    weno6ld_pair_fast(w0, w1, w2, w3, w4, w5, eps4, K, wm, wp);
 #else
     weno5js_pair_fast(w0, w1, w2, w3, w4, w5, eps4, wm, wp);
 #endif
@@ -521,7 +592,7 @@ HB2_HD void face_midpoint_fast(const double* win, bool hybrid, const Consts& K, 
                 for (int m = 0; m < 6; m++) w[m] = fma(b, Y[m * MS], w[m]);
             }
             double wm, wp;
-            weno_pair_fast(w[0], w[1], w[2], w[3], w[4], w[5], e4, wm, wp);
+            weno_pair_fast(w[0], w[1], w[2], w[3], w[4], w[5], e4, K, wm, wp);
             if (f == 0) {
                 rm = h_cc * wm; rp = h_cc * wp;
                 um = -h_rc * wm; up = -h_rc * wp;
@@ -589,7 +660,7 @@ HB2_HD void face_midpoint_fast(const double* win, bool hybrid, const Consts& K, 
                 for (int m = 0; m < 6; m++) w[m] = fma(b, Y[m * MS], w[m]);
             }
             double wm, wp;
-            weno_pair_fast(w[0], w[1], w[2], w[3], w[4], w[5], eps4, wm, wp);
+            weno_pair_fast(w[0], w[1], w[2], w[3], w[4], w[5], eps4, K, wm, wp);
             if (f == 0) {
                 z0m = -yh0 * wm; z0p = -yh0 * wp;
                 z1m = -yh1 * wm; z1p = -yh1 * wp;

@@ -40,5 +40,6 @@ const Ops* ops_exact_z();  /* WCNS5-Z */
 const Ops* ops_exact_ld(); /* WCNS6-LD */
 const Ops* ops_fast();     /* WCNS5-JS, re-associated */
 const Ops* ops_fast_z();   /* WCNS5-Z, re-associated */
+const Ops* ops_fast_ld();  /* WCNS6-LD, re-associated (constant_p = 2, constant_q = 4) */
 
 }  // namespace hb2

@@ -1,11 +1,11 @@
 /*
  * hb2_sweeps.cu -- sm_100a kernels of the WCNS5-JS / HLLC-HLL path.
  *
- * Compiled FIVE times into the product library:
+ * Compiled SIX times into the product library:
  *   -DHB2_MATH=0 -fmad=false : reference operation order, bit-identical to the oracle (WCNS5-JS), and again with
  *                              -DHB2_SCHEME=1 (WCNS5-Z) and -DHB2_SCHEME=2 (WCNS6-LD), SURVEY row f2
  *   -DHB2_MATH=1 -fmad=true  : FP64-instruction-minimal re-association (hb2_fast.cuh), <= 1e-12 relative, WCNS5-JS and
- *                              (-DHB2_SCHEME=1) WCNS5-Z
+ *                              (-DHB2_SCHEME=1, 2) WCNS5-Z, WCNS6-LD
  * The arithmetic lives in hb2_core.cuh / hb2_fast.cuh, the thread mapping in hb2_sweep.cuh; this file holds the
  * __global__ entry points and their launchers.
  *
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(384, 2) k_sensor(const __grid_constant__ Senso
 #endif
 
 template <class Tr, int DIR, int NTERM>
-__global__ void __launch_bounds__(256, (MATH == 1 && Tr::MODEL == SS) ? HB2_MINB : 1) k_sweep(const __grid_constant__ DirArgs A)
+__global__ void __launch_bounds__(256, (MATH == 1 && Tr::MODEL == SS && HB2_SCHEME != HB2_WCNS6_LD) ? HB2_MINB : 1) k_sweep(const __grid_constant__ DirArgs A)
 {
     using Sh = SweepShape<Tr, DIR, MATH>;
     extern __shared__ double smem[];
@@ -270,10 +270,10 @@ const Ops* ops_exact() { return &g_ops; }
 #else
 #if HB2_SCHEME == HB2_WCNS5_Z
 const Ops* ops_fast_z() { return &g_ops; }
-#elif HB2_SCHEME == HB2_WCNS5_JS
-const Ops* ops_fast() { return &g_ops; }
+#elif HB2_SCHEME == HB2_WCNS6_LD
+const Ops* ops_fast_ld() { return &g_ops; }
 #else
-#error "WCNS6-LD has no fast arithmetic: compile it with -DHB2_MATH=0"
+const Ops* ops_fast() { return &g_ops; }
 #endif
 #endif
 

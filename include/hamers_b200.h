@@ -69,7 +69,7 @@ typedef struct hb2_patch_desc {
      * "WCNS5_JS_HLLC_HLL" / "WCNS5_Z_HLLC_HLL" / "WCNS6_LD_HLLC_HLL") and the WCNS6-LD constants
      * Convective_flux_reconstructor{constant_q, constant_C, constant_alpha_tau} (defaults 4, 1.0e9, 35:
      * ConvectiveFluxReconstructorWCNS6-LD-HLLC-HLL.cpp:343-361; 0 selects the default).  HB2_MATH_FAST exists for
-     * WCNS5-JS and WCNS5-Z with constant_p = 2; every other combination runs the reference-order kernels. */
+     * constant_p = 2 (and constant_q = 4 for WCNS6-LD); every other combination runs the reference-order kernels. */
     int32_t scheme;                           /* HB2_WCNS5_JS | HB2_WCNS5_Z | HB2_WCNS6_LD */
     int32_t weno_q;
     double weno_C;

@@ -68,10 +68,10 @@ def rel_err_field(a, b):
     return np.abs(a - b) / (np.abs(b) + scale)
 
 
-def assert_fast_parity(a, b, what=""):
+def assert_fast_parity(a, b, what="", outlier_fraction=OUTLIER_FRACTION):
     r = rel_err_field(a, b)
     assert np.isfinite(r).all(), f"{what}: non-finite entries"
     n_out = int((r > RTOL).sum())
-    assert n_out <= max(8, int(OUTLIER_FRACTION * r.size)), f"{what}: {n_out} of {r.size} entries exceed {RTOL}, max {r.max():.3e}"
+    assert n_out <= max(8, int(outlier_fraction * r.size)), f"{what}: {n_out} of {r.size} entries exceed {RTOL}, max {r.max():.3e}"
     assert r.max() <= OUTLIER_RTOL, f"{what}: max relative error {r.max():.3e}"
     return float(r.max()), n_out

@@ -76,7 +76,7 @@ def test_other_interpolators_flux_and_stage(name, params, oracle_lib, product_li
     base = dataclasses.replace(desc, scheme=0)
     Fjs, _ = oracle_lib.compute_flux_and_source(base, Q, dt)
     assert any((Fo[a] != Fjs[a]).mean() > 0.5 for a in range(desc.dim))   # really another interpolator
-    plan = _plan(desc, 0 if desc.scheme == 1 else 1)   # WCNS6-LD has no fast build: HB2_MATH_FAST falls back to these kernels
+    plan = _plan(desc, 0)
     Qd = _to_dev(Q)
     Fd = [torch.full((desc.neq,) + desc.side_shape(a), float("nan"), dtype=torch.float64, device="cuda") for a in range(desc.dim)]
     Sd = _to_dev(S0)
@@ -93,18 +93,19 @@ def test_other_interpolators_flux_and_stage(name, params, oracle_lib, product_li
     plan.close()
 
 
+@pytest.mark.parametrize("scheme", [1, 2])
 @pytest.mark.parametrize("kind", ["random", "smooth"])
 @pytest.mark.parametrize("name", list(CASES))
-def test_fast_wcns5z_within_tolerance(name, kind, oracle_lib, product_lib):
-    """The re-associated WCNS5-Z kernels (HB2_MATH_FAST, constant_p = 2): <= 1e-12 relative of the oracle, like the
-    fast WCNS5-JS build (fluxes, sources, one fused stage)."""
+def test_fast_wcns5z_and_wcns6ld_within_tolerance(name, kind, scheme, oracle_lib, product_lib):
+    """The re-associated WCNS5-Z / WCNS6-LD kernels (HB2_MATH_FAST; constant_p = 2, constant_q = 4): <= 1e-12 relative of
+    the oracle, like the fast WCNS5-JS build (fluxes, sources, one fused stage)."""
     import dataclasses
 
     import torch
     from hamers_b200 import problems as pb
 
     desc, U = make_case(name, kind)
-    desc = dataclasses.replace(desc, scheme=1)
+    desc = dataclasses.replace(desc, scheme=scheme)
     Q = pb.pad_periodic(U)
     dt = 1.0e-3
     # the source is "+="-ed into whatever the caller holds (O(1) here: on the smooth field the advective source itself is
@@ -121,14 +122,18 @@ def test_fast_wcns5z_within_tolerance(name, kind, oracle_lib, product_lib):
     out = torch.zeros_like(Qd)
     plan.fused_stage([1.0], [1.0], [Qd], dt, out)
     torch.cuda.synchronize()
+    # WCNS6-LD: beta_3 is an expanded polynomial with ~1e9-sized cancelling coefficients and the weights carry
+    # (tau_6/(beta + eps))^4: more faces of the white-noise state are ill-conditioned in the reference's own formula
+    # (tests/test_oracle_conditioning.py); none may exceed 1e-9 all the same
+    frac = 5.0e-3 if scheme == 2 else 1.0e-3
     exact_hits = 0
     for a in range(desc.dim):
         Fg = Fd[a].cpu().numpy()
-        assert_fast_parity(Fg, Fo[a], f"dir {a}")
+        assert_fast_parity(Fg, Fo[a], f"dir {a}", frac)
         exact_hits += int(np.array_equal(Fg, Fo[a]))
     assert exact_hits < desc.dim or kind == "smooth"      # it really is the re-associated build, not the exact one
-    assert_fast_parity(Sd.cpu().numpy(), So, "source")
-    assert_fast_parity(interior(desc, out.cpu().numpy()), interior(desc, Uo), "fused stage")
+    assert_fast_parity(Sd.cpu().numpy(), So, "source", frac)
+    assert_fast_parity(interior(desc, out.cpu().numpy()), interior(desc, Uo), "fused stage", frac)
     plan.close()
 
 
