@@ -78,12 +78,17 @@ def test_convergence_order_and_l1_errors(dim, model, steps_base, math, oracle_li
             assert abs(l1g - l1o) <= 0.01 * l1o and abs(l2g - l2o) <= 0.03 * l2o and abs(lig - lio) <= 0.3 * lio
 
 
+@pytest.mark.parametrize("math", [0, 1])
 @pytest.mark.parametrize("scheme,expected", [(1, 4.8), (2, 5.8)])
-def test_convergence_order_of_the_other_interpolators(scheme, expected, oracle_lib, product_lib):
-    eg = _gpu_errors(2, 0, 4, 8, 0, scheme=scheme)
+def test_convergence_order_of_the_other_interpolators(scheme, expected, math, oracle_lib, product_lib):
+    eg = _gpu_errors(2, 0, 4, 8, math, scheme=scheme)
     eo = _oracle_errors(oracle_lib, 2, 0, 4, 8, scheme=scheme)
     assert np.log2(eg[-2][1] / eg[-1][1]) > expected
-    assert eg == eo
+    if math == 0:
+        assert eg == eo
+    else:
+        for (l1g, l2g, _), (l1o, l2o, _) in zip(eg, eo):
+            assert abs(l1g - l1o) <= 0.01 * l1o and abs(l2g - l2o) <= 0.03 * l2o
 
 
 @pytest.mark.parametrize("push", [False, True])
