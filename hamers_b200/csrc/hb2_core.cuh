@@ -779,50 +779,6 @@ HB2_HD void rk_update_cell(const DirArgs& A, double* const* push_table, long lon
     if (A.push && near_face<Tr>(A.G, ci, cj, ck)) push_cell<Tr>(A.G, push_table, ci, cj, ck, Unew);
 }
 
-/* ------------------------------------------------------------------------------------------
- * sensor inputs: dilatation and vorticity magnitude of cell (i,j,k), i,j,k in -2..N+1
- * (ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:1523-1659, 2D :663-731;
- *  DerivativeFirstOrder.cpp:382, 601).  Velocities are exact quotients so that the hard
- *  s > 0.65 switch sees the reference's bits.
- * ---------------------------------------------------------------------------------------- */
-template <class Tr>
-HB2_HD void sensor_cell(const Geom& G, const double* const* Q, long long x, double& theta, double& Omega)
-{
-    constexpr int DIM = Tr::DIM, NM = Tr::NM;
-    double grad[DIM][DIM]; /* grad[a][b] = d u_a / d x_b */
-#pragma unroll
-    for (int b = 0; b < DIM; b++) {
-        const long long xp = x + G.cs[b], xm = x - G.cs[b];
-        double rp = 0.0, rm = 0.0;
-        if (Tr::MODEL == SS) {
-            rp = Q[0][xp];
-            rm = Q[0][xm];
-        } else {
-#pragma unroll
-            for (int si = 0; si < NM; si++) {
-                rp += Q[si][xp];
-                rm += Q[si][xm];
-            }
-        }
-#pragma unroll
-        for (int a = 0; a < DIM; a++) {
-            const double up = Q[NM + a][xp] / rp;
-            const double um = Q[NM + a][xm] / rm;
-            grad[a][b] = (0.5 * (up - um)) / G.dx[b];
-        }
-    }
-    if (DIM == 2) {
-        theta = grad[0][0] + grad[1][1];
-        Omega = fabs(grad[1][0] - grad[0][1]);
-    } else {
-        theta = grad[0][0] + grad[1][1] + grad[2 % DIM][2 % DIM];
-        const double omega_x = grad[2 % DIM][1] - grad[1][2 % DIM];
-        const double omega_y = grad[0][2 % DIM] - grad[2 % DIM][0];
-        const double omega_z = grad[1][0] - grad[0][1];
-        Omega = sqrt(omega_x * omega_x + omega_y * omega_y + omega_z * omega_z);
-    }
-}
-
 /* Shock-sensor decision of the face between cells L and R (ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:2088-2123):
  * s = -theta_avg/(|theta_avg| + Omega_avg + eps); HLLC-HLL iff s > 0.65. */
 HB2_HD bool face_sensor(double th_L, double th_R, double Om_L, double Om_R)

@@ -711,37 +711,4 @@ HB2_HD void face_midpoint_fast(const double* win, bool hybrid, const Consts& K, 
     riemann_fast<Tr, DIR>(V_minus, V_plus, K, hybrid, Fm, vel_mid);
 }
 
-/* sensor inputs with reciprocal multiplications (same quantities as sensor_cell) */
-template <class Tr>
-HB2_HD void sensor_cell_fast(const Geom& G, const double* const* Q, long long x, const double (&hidx)[3], double& theta,
-                             double& Omega)
-{
-    constexpr int DIM = Tr::DIM, NM = Tr::NM;
-    double grad[DIM][DIM];
-#pragma unroll
-    for (int b = 0; b < DIM; b++) {
-        const long long xp = x + G.cs[b], xm = x - G.cs[b];
-        double rp = Q[0][xp], rm = Q[0][xm];
-#pragma unroll
-        for (int si = 1; si < NM; si++) {
-            rp += Q[si][xp];
-            rm += Q[si][xm];
-        }
-        const double rr = rcp_fast(rp * rm);
-        const double ip = rr * rm * hidx[b], im = rr * rp * hidx[b]; /* (1/rho_+-) * 0.5/dx_b */
-#pragma unroll
-        for (int a = 0; a < DIM; a++) grad[a][b] = fma(Q[NM + a][xp], ip, -Q[NM + a][xm] * im);
-    }
-    if (DIM == 2) {
-        theta = grad[0][0] + grad[1][1];
-        Omega = fabs(grad[1][0] - grad[0][1]);
-    } else {
-        theta = grad[0][0] + grad[1][1] + grad[2 % DIM][2 % DIM];
-        const double omega_x = grad[2 % DIM][1] - grad[1][2 % DIM];
-        const double omega_y = grad[0][2 % DIM] - grad[2 % DIM][0];
-        const double omega_z = grad[1][0] - grad[0][1];
-        Omega = sqrt_fast<true>(fma(omega_x, omega_x, fma(omega_y, omega_y, omega_z * omega_z)));
-    }
-}
-
 }  // namespace hb2

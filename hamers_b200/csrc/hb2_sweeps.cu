@@ -158,11 +158,14 @@ int launch_sensor_t(const SensorArgs& A, cudaStream_t st)
 {
     using Sh = SensorShape<Tr>;
     const size_t smem = (size_t)Sh::SMEM_DOUBLES * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
+    /* function attributes are per device: one process may hold plans on several GPUs */
+    static unsigned long long attr_set = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((attr_set >> (dev & 63)) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(k_sensor<Tr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        attr_set |= 1ull << (dev & 63);
     }
     dim3 grid(Sh::tiles_x(A.G), Sh::tiles_y(A.G), Sh::segments(A.G, A.seg_len));
     k_sensor<Tr><<<grid, Sh::NT, smem, st>>>(A);
@@ -175,13 +178,15 @@ int launch_dir_n(const DirArgs& A, cudaStream_t st)
     using Sh = SweepShape<Tr, DIR, MATH>;
     const Geom& G = A.G;
     const size_t smem = (size_t)Sh::SMEM_DOUBLES * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0; /* per device, see launch_sensor_t */
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((attr_set >> (dev & 63)) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(k_sweep<Tr, DIR, NTERM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         e = cudaFuncSetAttribute(k_sweep<Tr, DIR, NTERM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        attr_set |= 1ull << (dev & 63);
     }
     const int nseg = (G.n[DIR] + A.seg_len - 1) / A.seg_len;
     dim3 grid(1, 1, nseg);
