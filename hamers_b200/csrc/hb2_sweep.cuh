@@ -4,7 +4,7 @@
  * One block owns P pencils (lines of cells along the sweep axis) and advances along them in chunks of C cells;
  * P*C = 256 threads, one thread per (pencil, position in the chunk):
  *     y / z sweep : P = 32 pencils = 32 consecutive x (lanes -> 256-byte coalesced rows), C = 8 (one row per warp)
- *     x sweep     : P = 8 pencils = 8 consecutive y rows (one per warp), C = 32 consecutive x (lanes)
+ *     x sweep     : P = 16 pencils = 16 consecutive y rows (two per warp), C = 16 consecutive x (half a warp), HB2_XC
  * The work of a pencil is a three-stage software pipeline whose hand-over goes through shared-memory RINGS indexed
  * by the position along the sweep axis (slot = position mod RING):
  *     L(t)  load    cells  c0-4+tC+o  : conservative -> primitive variables, sound speed              -> sV (, sN)
@@ -45,16 +45,23 @@
 #define HB2_PREFETCH_R 0
 #endif
 
+/* x sweep: cells of a row one iteration advances (lanes along x).  A pencil of n cells takes ceil((n + 8)/XC)
+ * iterations: with 32 a 512-cell row needs 17 for 16.25 (4 % of the lanes idle) and a 256-cell row 9 for 8.25 (8 %);
+ * with 16 (two rows per warp) it is 33 for 32.5 and 17 for 16.5. */
+#ifndef HB2_XC
+#define HB2_XC 16
+#endif
+
 namespace hb2 {
 
 template <class Tr, int DIR, int MATH>
 struct SweepShape {
     static constexpr int NT = 256;
     static constexpr int NW = NT / 32;
-    static constexpr int P = (DIR == 0) ? NW : 32;     /* pencils per block */
-    static constexpr int C = (DIR == 0) ? 32 : NW;     /* cells per chunk along the sweep axis */
+    static constexpr int P = (DIR == 0) ? NT / HB2_XC : 32;   /* pencils per block */
+    static constexpr int C = (DIR == 0) ? HB2_XC : NW;        /* cells per chunk along the sweep axis */
     /* ring slots along the sweep axis: one iteration touches 3C+5 consecutive cells and 2C+3 consecutive faces */
-    static constexpr int RING = (DIR == 0) ? 128 : 32;
+    static constexpr int RING = (DIR == 0) ? 4 * HB2_XC : 32;
     static constexpr int CS = RING * P;                /* doubles per ring component (midpoint flux, node flux) */
     /* The primitive-variable ring is MIRRORED: its first DUP slots are stored a second time behind the last slot, so
      * that the six stencil cells of a face are always at base + m*MS (no wrap inside a stencil window). */
@@ -114,8 +121,8 @@ HB2_HD PencilCtx pencil_ctx(const DirArgs& A, const BlockId& b, int tid)
     const int lane = tid & 31, w = tid >> 5;
     c.tid = tid;
     c.sq = 0;
-    c.pp = (DIR == 0) ? w : lane;
-    c.o = (DIR == 0) ? lane : w;
+    c.pp = (DIR == 0) ? tid / Sh::C : lane;
+    c.o = (DIR == 0) ? tid % Sh::C : w;
     c.i = c.j = c.k = 0;
     if (DIR == 0) {
         c.j = b.x * Sh::P + c.pp;
