@@ -208,19 +208,22 @@ template <class Tr, int DIR>
 int launch_dir(const DirArgs& A, cudaStream_t st)
 {
     if (A.mode == MODE_EMIT) return launch_dir_n<Tr, DIR, HB2_NTERM_EMIT>(A, st);
-    /* the RK linear combination exists only in the last direction of a fused stage */
-    if (DIR == Tr::DIM - 1) {
-        if (A.nterm == 1) return launch_dir_n<Tr, DIR, 1>(A, st);
-        if (A.nterm == 2) return launch_dir_n<Tr, DIR, 2>(A, st);
-        if (A.nterm == 3) return launch_dir_n<Tr, DIR, 3>(A, st);
+    /* the RK linear combination exists only in the last direction of a fused stage: only the variants the ABI asks
+     * for are instantiated (fast build: the flux state rebuilt + 0..2 loaded states; exact build: 1..3 loaded states) */
+    if constexpr (DIR == Tr::DIM - 1) {
         if constexpr (MATH == 1) {
             if (A.nterm == HB2_NTERM_QREC) return launch_dir_n<Tr, DIR, HB2_NTERM_QREC>(A, st);
             if (A.nterm == HB2_NTERM_QREC + 1) return launch_dir_n<Tr, DIR, HB2_NTERM_QREC + 1>(A, st);
             if (A.nterm == HB2_NTERM_QREC + 2) return launch_dir_n<Tr, DIR, HB2_NTERM_QREC + 2>(A, st);
+        } else {
+            if (A.nterm == 1) return launch_dir_n<Tr, DIR, 1>(A, st);
+            if (A.nterm == 2) return launch_dir_n<Tr, DIR, 2>(A, st);
+            if (A.nterm == 3) return launch_dir_n<Tr, DIR, 3>(A, st);
         }
         return (int)cudaErrorInvalidValue;
+    } else {
+        return launch_dir_n<Tr, DIR, 0>(A, st);
     }
-    return launch_dir_n<Tr, DIR, 0>(A, st);
 }
 
 template <class Tr>
