@@ -129,3 +129,46 @@ def test_large_box_conservation_and_translation_equivariance(push, product_lib):
     assert np.isfinite(A).all()
     B, _, _ = run(np.ascontiguousarray(np.roll(U, shift, axis=(1, 2, 3))))
     assert np.array_equal(B, np.roll(A, shift, axis=(1, 2, 3)))
+
+
+def test_full_size_512_conservation_and_translation_equivariance(product_lib):
+    """BASELINE.json's full size (512^3, the bench workload's box), everything on the device: totals of the conserved
+    variables are preserved to round-off over a step, and a periodic shift of the initial state shifts the result bit
+    for bit (exercises 17-chunk x pencils, 65-chunk y/z pencils, multi-segment sensor marches, 30+ waves of blocks)."""
+    import torch
+    from hamers_b200.level import UniformLevel
+
+    if torch.cuda.get_device_properties(0).total_memory < 80e9:
+        pytest.skip("needs ~60 GB of device memory")
+    N = 512
+    g = torch.Generator(device="cuda").manual_seed(5)
+    ax = (torch.arange(N, device="cuda", dtype=torch.float64) + 0.5) / N
+    x, y, z = ax[None, None, :], ax[None, :, None], ax[:, None, None]
+    two_pi = 2.0 * np.pi
+    rho = 1.0 + 0.3 * torch.sin(two_pi * (x + 2 * y)) * torch.cos(two_pi * z) + 0.01 * torch.randn((N, N, N), generator=g, device="cuda", dtype=torch.float64)
+    u = 0.5 * torch.sin(two_pi * (y + z)) - 1.5 * torch.tanh(40.0 * (x - 0.5)) + 0 * z
+    v = -0.7 * torch.cos(two_pi * x) + 0 * y + 0 * z
+    w = 0.3 + 0.2 * torch.sin(two_pi * (x - z)) + 0 * y
+    p = 1.0 + 0.2 * torch.cos(two_pi * (x + y + z))
+    E = p / 0.4 + 0.5 * rho * (u * u + v * v + w * w)
+    U = torch.stack([rho, rho * u, rho * v, rho * w, E]).contiguous()
+    del rho, u, v, w, p, E
+    shift = (101, 5, 37)
+    dt = 0.25 * 0.001 * 2.0 / N
+
+    def run(U0):
+        lvl = UniformLevel(3, (N, N, N), species_gamma=(1.4,), math=1)
+        lvl.interior().copy_(U0)
+        lvl.advance(dt, 1)
+        torch.cuda.synchronize()
+        out = lvl.interior().clone()
+        lvl.close()
+        return out
+
+    A = run(U)
+    assert bool(torch.isfinite(A).all())
+    t0, t1 = U.sum(dim=(1, 2, 3)), A.sum(dim=(1, 2, 3))
+    scale = U.abs().sum(dim=(1, 2, 3))
+    assert bool(((t1 - t0).abs() <= 1e-12 * scale).all()), (t0, t1)
+    B = run(torch.roll(U, shift, dims=(1, 2, 3)).contiguous())
+    assert torch.equal(B, torch.roll(A, shift, dims=(1, 2, 3)))
