@@ -290,13 +290,19 @@ def run_ours(args):
                 roofline["algorithmic_bytes_per_launch"] = {"xsweep": 80.0, "ysweep": 120.0, "zsweep": 160.0}[dom] * ncell_local
         except Exception:
             pass
+        # the same dominant kernel against the HBM roof (the secondary roof of this FP64-bound path): algorithmic bytes
+        # of the launch (x 80, y 120, z 160 B/cell with the R round trips of the three-sweep design) / its time
+        dom_bytes = {"xsweep": 80.0, "ysweep": 120.0, "zsweep": 160.0}[dom] * ncell_local
+        roofline_hbm = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                        "unit": "GB/s", "peak_source": hbm_src, "traffic": roofline.get("traffic")}
+        roofline_hbm["frac"] = roofline_hbm["achieved"] / roofline_hbm["peak"]
         line = {
             "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(args), global_cells=list(Nglob), process_grid=list(grid),
                            cells_per_gpu=ncell_local, parallelism=f"box{world}"),
-            "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
+            "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "roofline_hbm": roofline_hbm,
             "sanity": {"finite": finite, "rho_min": rho_min, "rho_max": rho_max},
         }
 
