@@ -44,6 +44,10 @@
 #ifndef HB2_PREFETCH_R
 #define HB2_PREFETCH_R 0
 #endif
+/* L2 prefetch distance (iterations) of the update phase's HBM inputs; 0 = off */
+#ifndef HB2_PREFETCH_L2
+#define HB2_PREFETCH_L2 1
+#endif
 
 /* x sweep: cells of a row one iteration advances (lanes along x).  A pencil of n cells takes ceil((n + 8)/XC)
  * iterations: with 32 a 512-cell row needs 17 for 16.25 (4 % of the lanes idle) and a 256-cell row 9 for 8.25 (8 %);
@@ -302,6 +306,38 @@ HB2_HD void update_fetch(const DirArgs& A, const PencilCtx& c, int cc, UpdateIn<
     in.T = (Tr::ADV && DIR > 0) ? A.T[ix] : 0.0;
 }
 
+HB2_HD void prefetch_l2(const void* p)
+{
+#if defined(__CUDA_ARCH__)
+#if defined(HB2_PREFETCH_TO_L1)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+#else
+    (void)p;
+#endif
+}
+
+template <class Tr, int DIR, int NTERM>
+HB2_HD void update_prefetch(const DirArgs& A, const PencilCtx& c, int cc)
+{
+    constexpr bool QREC = (NTERM >= HB2_NTERM_QREC);
+    constexpr int NLOAD = QREC ? NTERM - HB2_NTERM_QREC : (NTERM > 0 ? NTERM : 0);
+    if (DIR > 0) {
+        const long long ix = c.ibase + (long long)cc * c.ist;
+#pragma unroll
+        for (int e = 0; e < Tr::NEQ; e++) prefetch_l2(A.R[e] + ix);
+    }
+    if (NLOAD > 0) {
+        const long long x = c.base + (long long)cc * c.st;
+#pragma unroll
+        for (int k = 0; k < NLOAD; k++)
+#pragma unroll
+            for (int e = 0; e < Tr::NEQ; e++) prefetch_l2(A.Ut[k][e] + x);
+    }
+}
+
 /* NTERM: number of states in the RK linear combination (compile-time, so that their loads are unconditional and are
  * all issued up front); 0 for the directions / modes without the RK update */
 template <class Tr, int DIR, int MATH, int NTERM>
@@ -478,6 +514,13 @@ HB2_HD void pipeline_iteration(const DirArgs& A, double* smem, const PencilCtx& 
     const bool do_update = update_wanted<Tr, DIR, MATH>(c, t - 1, cc);
     UpdateIn<Tr> uin;
     constexpr bool FUSED = (NTERM != HB2_NTERM_EMIT);
+    /* The HBM inputs of the update phase (running right-hand side, RK states) are loaded where they are consumed: held
+     * in registers across the face phase they spill, staged with cp.async they load the shared-memory pipe.  Their DRAM
+     * latency is taken out one iteration ahead with L2 prefetches instead (no register, no shared memory): HB2_PREFETCH_L2. */
+    if (HB2_PREFETCH_L2 && FUSED) {
+        int cn;
+        if (update_wanted<Tr, DIR, MATH>(c, t + HB2_PREFETCH_L2 - 1, cn)) update_prefetch<Tr, DIR, NTERM>(A, c, cn);
+    }
     if (HB2_PREFETCH_R && do_update) update_fetch<Tr, DIR, FUSED>(A, c, cc, uin);
     unsigned int flag;
     if (HB2_PREFETCH_FLAG) {
