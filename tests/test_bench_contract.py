@@ -1,6 +1,6 @@
 """bench.py's output contract, checked where no GPU exists: the reference arm (`--impl reference`, the CPU oracle on a
 bounded sample) must print ONE JSON line with the keys the driver reads, and under a multi-rank launch only rank 0
-works.  The GPU arm's line is produced on the GPU box (profiles/r01_p_bench_512.json is a committed sample, checked
+works.  The GPU arm's line is produced on the GPU box (profiles/r01_q_bench_512.json is a committed sample, checked
 here for the same keys plus `roofline`, `cpu_baseline`, `e2e`, `clocks` and `gpu_launches`)."""
 import json
 import os
@@ -40,7 +40,7 @@ def test_reference_arm_other_ranks_do_nothing():
 
 
 def test_committed_gpu_line_has_the_contract_keys():
-    with open(os.path.join(ROOT, "profiles", "r01_p_bench_512.json")) as fh:
+    with open(os.path.join(ROOT, "profiles", "r01_q_bench_512.json")) as fh:
         d = json.loads(fh.read())
     assert BASE_KEYS <= set(d) and d["n_gpus"] == 1 and d["config"]["size"] == 512
     rf = d["roofline"]
