@@ -8,28 +8,30 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "host_emu", "libhb2_emu.so")
+_SO = os.path.join(_HERE, "host_emu", "libhb2_emu.so")          # scheme 0; libhb2_emu_s<k>.so for WCNS5-Z / WCNS6-LD
 _SRC = os.path.join(_HERE, "host_emu", "emu.cpp")
 _CORE = [os.path.join(_HERE, "..", "hamers_b200", "csrc", f) for f in ("hb2_core.cuh", "hb2_fast.cuh", "hb2_sweep.cuh", "hb2_sensor.cuh")]
-_LIB = None
+_LIB = {}
 
 
 class EmuDesc(C.Structure):
     _fields_ = [("dim", C.c_int), ("n", C.c_int * 3), ("model", C.c_int), ("ns", C.c_int),
                 ("gamma", C.c_double * 4), ("dx", C.c_double * 3), ("weno_p", C.c_int),
-                ("math", C.c_int), ("bx", C.c_int), ("seg_len", C.c_int)]
+                ("math", C.c_int), ("bx", C.c_int), ("seg_len", C.c_int),
+                ("weno_q", C.c_int), ("weno_C", C.c_double), ("weno_alpha_tau", C.c_double)]
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        stale = (not os.path.exists(_SO)) or any(
-            os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_SO) for s in [_SRC] + _CORE)
+def lib(scheme: int = 0):
+    """The emulation library of one nonlinear interpolator (HB2_SCHEME is a compile-time property of the kernels)."""
+    if scheme not in _LIB:
+        so = _SO if scheme == 0 else _SO.replace(".so", f"_s{scheme}.so")
+        stale = (not os.path.exists(so)) or any(
+            os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(so) for s in [_SRC] + _CORE)
         if stale:
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
-                                   "-Wno-unknown-pragmas", "-o", _SO, _SRC])
-        _LIB = C.CDLL(_SO)
-    return _LIB
+                                   "-Wno-unknown-pragmas", f"-DHB2_SCHEME={scheme}", "-o", so, _SRC])
+        _LIB[scheme] = C.CDLL(so)
+    return _LIB[scheme]
 
 
 def _pp(arrs):
@@ -51,6 +53,7 @@ def _desc(desc, math, bx, seg_len):
     for i, g in enumerate(desc.gamma):
         d.gamma[i] = g
     d.weno_p, d.math, d.bx, d.seg_len = desc.weno_p, math, bx, seg_len
+    d.weno_q, d.weno_C, d.weno_alpha_tau = desc.weno_q, desc.weno_C, desc.weno_alpha_tau
     return d
 
 
@@ -60,7 +63,7 @@ def flux_and_source(desc, Q, dt, math=0, bx=0, seg_len=0, source=None):
     S = np.zeros((neq,) + desc.cell_shape) if source is None else source
     d = _desc(desc, math, bx, seg_len)
     Q = np.ascontiguousarray(Q)
-    rc = lib().emu_flux_and_source(C.byref(d), _pp([Q[c] for c in range(desc.ncomp)]), C.c_double(dt),
+    rc = lib(desc.scheme).emu_flux_and_source(C.byref(d), _pp([Q[c] for c in range(desc.ncomp)]), C.c_double(dt),
                                    _pp([F[a][e] for a in range(dim) for e in range(neq)]),
                                    _pp([S[e] for e in range(neq)]))
     assert rc == 0
@@ -75,7 +78,7 @@ def fused_stage(desc, alpha, beta, U_int, dt, math=0, bx=0, seg_len=0, push=Fals
     tab = _pp([Us[m][c] for m in range(ncoef) for c in range(desc.ncomp)])
     a = (C.c_double * ncoef)(*[float(x) for x in alpha])
     b = (C.c_double * ncoef)(*[float(x) for x in beta])
-    rc = lib().emu_fused_stage_push(C.byref(d), ncoef, a, b, tab, C.c_double(dt), _pp([U_out[c] for c in range(desc.ncomp)]),
+    rc = lib(desc.scheme).emu_fused_stage_push(C.byref(d), ncoef, a, b, tab, C.c_double(dt), _pp([U_out[c] for c in range(desc.ncomp)]),
                                     1 if push else 0)
     assert rc == 0
     return U_out

@@ -19,6 +19,8 @@ struct EmuDesc {
     int dim, n[3], model, ns;
     double gamma[4], dx[3];
     int weno_p, math, bx, seg_len;
+    int weno_q;            /* WCNS6-LD constants (the interpolator itself is compiled in: -DHB2_SCHEME) */
+    double weno_C, weno_alpha_tau;
 };
 
 static void make_geom(const EmuDesc* d, Geom* G)
@@ -188,6 +190,9 @@ static void fill_common(const EmuDesc* d, DirArgs* A, const double* const* Q, do
         A->K.inv_gm1[s] = 1.0 / (A->K.gamma[s] - 1.0);
     }
     A->K.weno_p = d->weno_p > 0 ? d->weno_p : 2;
+    A->K.weno_q = d->weno_q > 0 ? d->weno_q : 4;
+    A->K.weno_C = d->weno_C > 0.0 ? d->weno_C : 1.0e9;
+    A->K.weno_alpha_tau = d->weno_alpha_tau > 0.0 ? d->weno_alpha_tau : 35.0;
     const int ncomp = d->model == SS ? d->dim + 2 : d->dim + 2 * d->ns + 1;
     for (int c = 0; c < ncomp; c++) A->Q[c] = Q[c];
     A->dt = dt;

@@ -99,3 +99,35 @@ def test_emulated_push_fills_the_ghosts(name, oracle_lib):
     pushed = emu_host.fused_stage(desc, [1.0], [1.0], [Q], 5.0e-4, math=0, push=True)
     assert np.array_equal(interior(desc, pushed), interior(desc, plain))
     assert np.array_equal(pushed, pb.pad_periodic(np.ascontiguousarray(interior(desc, pushed))))
+
+
+@pytest.mark.parametrize("scheme", [1, 2])
+@pytest.mark.parametrize("math", [0, 1])
+@pytest.mark.parametrize("name", ["ss2d", "fe3d"])
+def test_emulated_other_interpolators(name, math, scheme, oracle_lib):
+    """WCNS5-Z / WCNS6-LD through the emulated kernels (compiled with -DHB2_SCHEME): reference-order arithmetic
+    bit-identical to the oracle, re-associated arithmetic within the fast-build criterion (WCNS6-LD with its larger
+    share of ill-conditioned faces, tests/test_oracle_conditioning.py)."""
+    import dataclasses
+
+    desc, U = make_case(name, "random")
+    desc = dataclasses.replace(desc, scheme=scheme)
+    Q = pb.pad_periodic(U)
+    dt = 1.0e-3
+    S0 = np.random.default_rng(7).standard_normal((desc.neq,) + desc.cell_shape)
+    Fo, So = oracle_lib.compute_flux_and_source(desc, Q, dt, source=S0.copy())
+    Fe, Se = emu_host.flux_and_source(desc, Q, dt, math=math, source=S0.copy())
+    F1, S1 = oracle_lib.compute_flux_and_source(desc, Q, dt)
+    Uo = oracle_lib.advance_stage(desc, [1.0], [1.0], [Q], [F1], [S1])
+    Ue = emu_host.fused_stage(desc, [1.0], [1.0], [Q], dt, math=math)
+    frac = 5.0e-3 if scheme == 2 else 1.0e-3
+    for a in range(desc.dim):
+        if math == 0:
+            assert np.array_equal(Fe[a], Fo[a]), f"dir {a}"
+        else:
+            assert_fast_parity(Fe[a], Fo[a], f"dir {a}", frac)
+    if math == 0:
+        assert np.array_equal(Se, So) and np.array_equal(interior(desc, Ue), interior(desc, Uo))
+    else:
+        assert_fast_parity(Se, So, "source", frac)
+        assert_fast_parity(interior(desc, Ue), interior(desc, Uo), "fused stage", frac)
