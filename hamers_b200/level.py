@@ -119,6 +119,15 @@ def _code(o):
     return sum((o[a] + 1) * 3 ** a for a in range(len(o)))
 
 
+def neighbour_ranks(dec: "BoxDecomposition"):
+    """{offset: rank} of the (up to 26, 8 in 2-D) boxes around this rank's box on the periodic process grid; a rank
+    is its own neighbour in the directions it owns alone."""
+    import itertools
+
+    return {o: dec.rank_of([dec.coords[a] + o[a] for a in range(dec.dim)])
+            for o in itertools.product((-1, 0, 1), repeat=dec.dim) if any(o)}
+
+
 def oneshot_schedule(dec: "BoxDecomposition", ncomp: int):
     """Single-phase ghost fill: every rank sends each of its (up to 26) neighbours the face / edge / corner region
     that neighbour's ghost box needs, all neighbours at once, ONE message per peer.  Directions owned by a single rank
@@ -273,10 +282,7 @@ class UniformLevel:
         self.push_tables = None
         if self.push:
             per_buffer = [dict() for _ in range(3)]
-            for o in itertools.product((-1, 0, 1), repeat=dim):
-                if not any(o):
-                    continue
-                peer = self.decomp.rank_of([self.decomp.coords[a] + o[a] for a in range(dim)])
+            for o, peer in neighbour_ranks(self.decomp).items():
                 if peer not in bases:
                     ptrs = [abi.ipc_open(h) for h in handles[peer]]
                     self._opened += ptrs

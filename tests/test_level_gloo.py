@@ -8,7 +8,7 @@ import socket
 import numpy as np
 import pytest
 
-from hamers_b200.level import BoxDecomposition, exchange_halos, exchange_halos_oneshot, oneshot_schedule
+from hamers_b200.level import BoxDecomposition, exchange_halos, exchange_halos_oneshot, neighbour_ranks, oneshot_schedule
 
 G = 4
 
@@ -118,6 +118,27 @@ def test_oneshot_schedule_matches_between_ranks():
                 assert len(back) == 1 and back[0].numel == t.numel
                 assert [tuple(h - l for l, h in zip(lo, hi)) for lo, hi in t.boxes] == \
                        [tuple(h - l for l, h in zip(lo, hi)) for lo, hi in back[0].boxes]
+
+
+def test_push_neighbour_table_is_consistent():
+    """The fused ghost push stores a cell of rank r near its face in direction o into the ghost box of
+    neighbour_ranks(r)[o] at coordinate c - o*n: that cell must be exactly what the periodic level holds there, i.e.
+    the neighbour's ghost cell c - o*n maps back to r's interior cell c."""
+    for dim, N, world in ((3, (16, 16, 16), 8), (3, (16, 16, 8), 4), (3, (16, 8, 8), 2), (2, (16, 24), 2), (2, (32, 16), 8)):
+        decs = [BoxDecomposition(dim, N, world, r) for r in range(world)]
+        for d in decs:
+            nb = neighbour_ranks(d)
+            assert len(nb) == 3 ** dim - 1
+            for o, peer in nb.items():
+                back = neighbour_ranks(decs[peer])[tuple(-x for x in o)]
+                assert back == d.rank
+                # a cell at the low corner region of r in direction o, in global periodic coordinates
+                c = tuple(0 if o[a] < 0 else (d.n[a] - 1 if o[a] > 0 else 1) for a in range(dim))
+                glob = tuple((d.lo[a] + c[a]) % N[a] for a in range(dim))
+                ghost = tuple(c[a] - o[a] * d.n[a] for a in range(dim))          # coordinate in the peer's frame
+                p = decs[peer]
+                assert tuple((p.lo[a] + ghost[a]) % N[a] for a in range(dim)) == glob
+                assert any(ghost[a] < 0 or ghost[a] >= p.n[a] for a in range(dim))   # it is a ghost cell there
 
 
 def test_decomposition_covers_level_once():
