@@ -131,3 +131,24 @@ def test_emulated_other_interpolators(name, math, scheme, oracle_lib):
     else:
         assert_fast_parity(Se, So, "source", frac)
         assert_fast_parity(interior(desc, Ue), interior(desc, Uo), "fused stage", frac)
+
+
+@pytest.mark.parametrize("model,ns", [(0, 1), (1, 2)])
+@pytest.mark.parametrize("N", [(4, 4, 4), (5, 4, 6), (4, 33, 5), (65, 4, 4)])
+def test_emulated_tiny_and_ragged_patches(N, model, ns, oracle_lib):
+    """Patches as narrow as the ghost width (every cell is near BOTH faces of a direction: the fused ghost push then
+    stores it into both neighbours), pencils shorter than one chunk, odd extents: fluxes, the fused stage and the pushed
+    ghosts against the oracle."""
+    U, dx, gam = pb.random_state(3, N, model=model, seed=3, shock=True)
+    desc = oracle_lib.PatchDesc(dim=3, n=N, model=model, ns=ns, gamma=gam, dx=dx)
+    Q = pb.pad_periodic(U)
+    Fo, So = oracle_lib.compute_flux_and_source(desc, Q, 1.0e-3)
+    Uo = oracle_lib.advance_stage(desc, [1.0], [1.0], [Q], [Fo], [So])
+    Fe, _ = emu_host.flux_and_source(desc, Q, 1.0e-3, math=0)
+    Ue = emu_host.fused_stage(desc, [1.0], [1.0], [Q], 1.0e-3, math=0, push=True)
+    for a in range(3):
+        assert np.array_equal(Fe[a], Fo[a]), f"dir {a}"
+    assert np.array_equal(interior(desc, Ue), interior(desc, Uo))
+    assert np.array_equal(Ue, pb.pad_periodic(np.ascontiguousarray(interior(desc, Ue))))
+    Uf = emu_host.fused_stage(desc, [1.0], [1.0], [Q], 1.0e-3, math=1)
+    assert_fast_parity(interior(desc, Uf), interior(desc, Uo))
