@@ -310,6 +310,45 @@ def test_advance_level_on_host_buffers(name, oracle_lib, product_lib):
     plan.close()
 
 
+def test_exact_build_matches_committed_golden_vectors(product_lib):
+    """The CUDA path (reference-order build) against tests/golden/path_vectors.npz -- committed oracle outputs on the
+    seeded branch-coverage states, three interpolators: side fluxes, source, a fused stage and the spectral radii,
+    bit for bit."""
+    import dataclasses
+    import os
+    import sys
+
+    import torch
+    from hamers_b200 import problems as pb
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden_path as mg
+
+    gold = np.load(os.path.join(here, "golden", "path_vectors.npz"))
+    for name, scheme in mg.CASES:
+        desc, U = make_case(name, "random")
+        desc = dataclasses.replace(desc, scheme=scheme)
+        key = f"{name}_s{scheme}"
+        Qd = _to_dev(pb.pad_periodic(U))
+        plan = _plan(desc, 0)
+        Fd = [torch.empty((desc.neq,) + desc.side_shape(a), dtype=torch.float64, device="cuda") for a in range(desc.dim)]
+        Sd = torch.zeros((desc.neq,) + desc.cell_shape, dtype=torch.float64, device="cuda")
+        plan.compute_flux_and_source(Qd, mg.DT, Fd, Sd)
+        out = torch.zeros_like(Qd)
+        plan.fused_stage([1.0], [1.0], [Qd], mg.DT, out)
+        sr = torch.zeros(4, dtype=torch.float64, device="cuda")
+        plan.max_wave_speed(Qd, sr)
+        torch.cuda.synchronize()
+        for a in range(desc.dim):
+            assert np.array_equal(Fd[a].cpu().numpy(), gold[f"{key}_F{a}"]), (key, a)
+        assert np.array_equal(Sd.cpu().numpy(), gold[f"{key}_S"]), key
+        assert np.array_equal(interior(desc, out.cpu().numpy()), gold[f"{key}_U"]), key
+        o = sr.cpu().numpy()
+        assert np.array_equal(np.append(o[:desc.dim], 1.0 / o[3]), gold[f"{key}_sr"]), key
+        plan.close()
+
+
 def test_pack_unpack_many_boxes(product_lib):
     """hb2_pack_boxes_dev / hb2_unpack_boxes_dev: several boxes (interior slabs, ghost regions, an edge bar) in one
     launch, at arbitrary positions of one buffer."""
