@@ -36,6 +36,29 @@ SOURCES = {
 }
 
 
+EOS_SOURCE = "src/util/mixing_rules/equations_of_state/ideal_gas/EquationOfStateIdealGas.cpp"
+EOS_SCALARS = ("getPressure", "getSoundSpeed", "getInternalEnergy")
+
+
+def member_function(text: str, cls: str, name: str) -> str:
+    """The FIRST definition `double\n<cls>::<name>(...) const { ... }` in text (the scalar overload comes first in the
+    reference's file), as text."""
+    m = re.search(r"^double\s*\n" + cls + "::" + name + r"\(", text, flags=re.M)
+    start = m.start()
+    brace = text.index("{", m.end())
+    depth, i = 0, brace
+    while True:
+        ch = text[i]
+        if ch == "{":
+            depth += 1
+        elif ch == "}":
+            depth -= 1
+            if depth == 0:
+                break
+        i += 1
+    return text[start:i + 1]
+
+
 def static_inline_functions(text: str) -> str:
     """Return the concatenation of every `static inline ...` function definition in text."""
     out = []
@@ -133,6 +156,18 @@ int ref_riemann_point(int model, int dim, int ns, int dir,
 """
 
 
+EOS_WRAPPER = r"""
+extern "C" void ref_eos_point(double gamma, double rho, double epsilon, double* p, double* c, double* eps_back)
+{
+    ref_eos::EquationOfStateIdealGas eos;
+    std::vector<const double*> thermo(1, &gamma);
+    *p = eos.getPressure(&rho, &epsilon, thermo);
+    *c = eos.getSoundSpeed(&rho, p, thermo);
+    *eps_back = eos.getInternalEnergy(&rho, p, thermo);
+}
+"""
+
+
 def main() -> int:
     if not os.path.isdir(REF):
         print(f"[build_ref] {REF} not present: keeping any prebuilt oracle/_ref/libhamers_ref.so")
@@ -143,7 +178,15 @@ def main() -> int:
         with open(os.path.join(REF, rel)) as fh:
             body = static_inline_functions(fh.read())
         parts.append(f"namespace {ns} {{\n{body}\n}}\n")
+    # the scalar ideal-gas EOS members (EquationOfStateIdealGas.cpp:29-45, 561-577, 1093-1108) behind a stub class
+    with open(os.path.join(REF, EOS_SOURCE)) as fh:
+        eos_text = fh.read()
+    decls = "\n".join(f"    double {n}(const double* const, const double* const, const std::vector<const double*>&) const;"
+                      for n in EOS_SCALARS)
+    bodies = "\n\n".join(member_function(eos_text, "EquationOfStateIdealGas", n) for n in EOS_SCALARS)
+    parts.append("#include <vector>\nnamespace ref_eos {\nstruct EquationOfStateIdealGas {\n" + decls + "\n};\n" + bodies + "\n}\n")
     parts.append(WRAPPERS)
+    parts.append(EOS_WRAPPER)
     gen = os.path.join(OUT, "_generated_ref_kernels.cpp")
     with open(gen, "w") as fh:
         fh.write("\n".join(parts))

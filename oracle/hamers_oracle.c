@@ -44,6 +44,19 @@ long orc_side_size(const orc_desc* d, int dir)
 /* Point kernels                                                              */
 /* ------------------------------------------------------------------------- */
 
+/* Ideal-gas equation of state, the expressions of EquationOfStateIdealGas.cpp:29-45 (= :5580 on cell data),
+ * :561-577 (= :5909) and :1093-1108 (= :6238); pinned against the reference's scalar members (oracle/_ref). */
+static inline double eos_pressure(double gamma, double rho, double epsilon) { return (gamma - 1.0) * rho * epsilon; }
+static inline double eos_sound_speed(double gamma, double rho, double p) { return sqrt(gamma * p / rho); }
+static inline double eos_internal_energy(double gamma, double rho, double p) { return p / ((gamma - 1.0) * rho); }
+
+void orc_eos_point(double gamma, double rho, double epsilon, double* p, double* c, double* eps_back)
+{
+    *p = eos_pressure(gamma, rho, epsilon);
+    *c = eos_sound_speed(gamma, rho, *p);
+    *eps_back = eos_internal_energy(gamma, rho, *p);
+}
+
 /* ConvectiveFluxReconstructorWCNS5-JS-HLLC-HLL.cpp:9-18 */
 static inline double ipow_(double base, int e)
 {
@@ -208,8 +221,8 @@ static inline void side_thermo(int model, int dim, int ns, const double* gamma, 
         const double rho = V[0];
         const double p = V[dim + 1];
         *rho_o = rho;
-        *c_o = sqrt(gamma[0] * p / rho);
-        *eps_o = p / ((gamma[0] - 1.0) * rho);
+        *c_o = eos_sound_speed(gamma[0], rho, p);
+        *eps_o = eos_internal_energy(gamma[0], rho, p);
     } else {
         double rho = 0.0;
         for (int si = 0; si < ns; si++) rho += V[si];
@@ -452,8 +465,8 @@ static void cell_stage(const geom_t* q, const double* gam, const double* const* 
                 ke = (a == 0) ? vel[a][x] * vel[a][x] : ke + vel[a][x] * vel[a][x];
             }
             const double epsilon = Q[dim + 1][x] / rho - 1.0 / 2.0 * ke;
-            p[x] = (gam[0] - 1.0) * rho * epsilon;
-            c[x] = sqrt(gam[0] * p[x] / rho);
+            p[x] = eos_pressure(gam[0], rho, epsilon);
+            c[x] = eos_sound_speed(gam[0], rho, p[x]);
         } else {
             double rho = 0.0;
             for (int si = 0; si < ns; si++) rho += Q[si][x];

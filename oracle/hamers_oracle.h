@@ -6,10 +6,10 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this library; the product (hamers_b200/) never links or calls it.
  *
- * Parity status: the point kernels for the WCNS5-JS interpolation and the HLLC /
- * HLLC-HLL Riemann solvers are PINNED against the reference's own compiled
- * `static inline` functions (oracle/_ref, built by oracle/build_ref.py from
- * /root/reference).  Everything else (derived cell data, characteristic
+ * Parity status: the point kernels for the WCNS5-JS / WCNS5-Z / WCNS6-LD interpolations,
+ * the HLLC / HLLC-HLL Riemann solvers and the ideal-gas equation of state are PINNED
+ * against the reference's own compiled functions (oracle/_ref, built by
+ * oracle/build_ref.py from /root/reference).  Everything else (derived cell data, characteristic
  * projection, bounds check / fallback, sensor, flux differencing, RK update) is a
  * restatement of formulas cited below ("parity unpinned" for those pieces: the
  * reference holds no golden vectors and cannot be built here without SAMRAI).
@@ -100,6 +100,7 @@ int orc_advance_stage(const orc_desc* d, int ncoef,
 int orc_spectral_radii_and_dt(const orc_desc* d, const double* const* Q, int include_ghosts, double* out);
 
 /* Point kernels exported for pinning against oracle/_ref (the reference's own functions). */
+void orc_eos_point(double gamma, double rho, double epsilon, double* p, double* c, double* eps_back);
 void orc_weno5js_point(const double U[6], int p, double* U_minus, double* U_plus);
 void orc_weno5z_point(const double U[6], int p, double* U_minus, double* U_plus);
 void orc_weno6ld_point(const double U[6], int p, int q, double C, double alpha_tau, double* U_minus, double* U_plus);

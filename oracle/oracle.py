@@ -218,6 +218,13 @@ def spectral_radii_and_dt(desc: PatchDesc, Q: np.ndarray, include_ghosts: bool =
     return np.array(out[:desc.dim]), float(out[desc.dim])
 
 
+def eos_point(gamma, rho, epsilon):
+    """(p, c, epsilon recovered from p) of the ideal-gas EOS as the oracle's path evaluates them."""
+    p, c, e = C.c_double(), C.c_double(), C.c_double()
+    lib().orc_eos_point(C.c_double(gamma), C.c_double(rho), C.c_double(epsilon), C.byref(p), C.byref(c), C.byref(e))
+    return p.value, c.value, e.value
+
+
 def weno5js_point(U, p=2):
     Ua = (C.c_double * 6)(*[float(x) for x in U])
     m, pl = C.c_double(), C.c_double()

@@ -9,6 +9,7 @@ Contents (all float64, seeded):
   weno_U      (n, 6)   six-point stencils (smooth, random, shock-like, constant, tiny-variation)
   weno_minus  (n,)     performLocalWENOInterpolationMinus  (ConvectiveFluxReconstructorWCNS5-JS-HLLC-HLL.cpp:78-118)
   weno_plus   (n,)     performLocalWENOInterpolationPlus   (:124-164)
+  eos_in (n, 3) = (gamma, rho, epsilon), eos_out (n, 3) = (p, c, epsilon from p): EquationOfStateIdealGas scalar members
   rp_<case>_{VL,VR,thermo,F_HLLC,F_HYB,vel_mid} for case in ss2d{0,1}, ss3d{0,1,2}, fe2d{0,1}, fe3d{0,1,2}:
                        computeLocal...HLLC{2D,3D} / ...HLLC_HLL{2D,3D} of the reference
                        (FlowModelRiemannSolverSingleSpeciesHLLC.cpp:604-1079, ...HLLC-HLL.cpp:889-1629,
@@ -127,6 +128,16 @@ def main():
         rl = np.array([ref_weno_ld(lib, u, *args) for u in U])
         out[f"weno_{tag}_minus"], out[f"weno_{tag}_plus"] = rl[:, 0], rl[:, 1]
         out[f"weno_{tag}_params"] = np.array(args, dtype=np.float64)
+    # ideal-gas EOS scalars (EquationOfStateIdealGas.cpp:29-45, 561-577, 1093-1108); own generator: the arrays above keep
+    # their values
+    rng_eos = np.random.default_rng(77)
+    eos_in = np.stack([rng_eos.uniform(1.1, 1.7, 300), 10.0 ** rng_eos.uniform(-3, 3, 300), 10.0 ** rng_eos.uniform(-3, 4, 300)], axis=1)
+    eos_out = []
+    for g, r, e in eos_in:
+        p_, c_, b_ = C.c_double(), C.c_double(), C.c_double()
+        lib.ref_eos_point(C.c_double(g), C.c_double(r), C.c_double(e), C.byref(p_), C.byref(c_), C.byref(b_))
+        eos_out.append((p_.value, c_.value, b_.value))
+    out["eos_in"], out["eos_out"] = eos_in, np.array(eos_out)
     for tag, model, dim, ns, gam in CASES:
         for d in range(dim):
             VL, VR = riemann_inputs(rng, model, dim, ns)
