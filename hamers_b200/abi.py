@@ -42,6 +42,8 @@ KERNEL_KINDS = ("sensor", "xsweep", "ysweep", "zsweep", "advance", "fill_periodi
 # SSP-RK3(3,3), the reference's default table (RungeKuttaLevelIntegrator.cpp:3894-3929), row-major [stage][m]
 SSPRK3_ALPHA = np.array([[1.0, 0.0, 0.0], [3.0 / 4.0, 1.0 / 4.0, 0.0], [1.0 / 3.0, 0.0, 2.0 / 3.0]])
 SSPRK3_BETA = np.array([[1.0, 0.0, 0.0], [0.0, 1.0 / 4.0, 0.0], [0.0, 0.0, 2.0 / 3.0]])
+# weights of the flux / source sums kept for the AMR flux synchronisation (hb2_advance_stage_dev's gamma)
+SSPRK3_GAMMA = np.array([[1.0 / 6.0, 0.0, 0.0], [0.0, 1.0 / 6.0, 0.0], [0.0, 0.0, 2.0 / 3.0]])
 
 
 class PatchDescC(C.Structure):

@@ -9,6 +9,7 @@ Contents (all float64, seeded):
   weno_U      (n, 6)   six-point stencils (smooth, random, shock-like, constant, tiny-variation)
   weno_minus  (n,)     performLocalWENOInterpolationMinus  (ConvectiveFluxReconstructorWCNS5-JS-HLLC-HLL.cpp:78-118)
   weno_plus   (n,)     performLocalWENOInterpolationPlus   (:124-164)
+  rk_alpha, rk_beta, rk_gamma (3, 3): the reference's default SSPRK(3,3) table (RungeKuttaLevelIntegrator.cpp:3894-3929)
   eos_in (n, 3) = (gamma, rho, epsilon), eos_out (n, 3) = (p, c, epsilon from p): EquationOfStateIdealGas scalar members
   rp_<case>_{VL,VR,thermo,F_HLLC,F_HYB,vel_mid} for case in ss2d{0,1}, ss3d{0,1,2}, fe2d{0,1}, fe3d{0,1,2}:
                        computeLocal...HLLC{2D,3D} / ...HLLC_HLL{2D,3D} of the reference
@@ -128,6 +129,19 @@ def main():
         rl = np.array([ref_weno_ld(lib, u, *args) for u in U])
         out[f"weno_{tag}_minus"], out[f"weno_{tag}_plus"] = rl[:, 0], rl[:, 1]
         out[f"weno_{tag}_params"] = np.array(args, dtype=np.float64)
+    # the default Runge-Kutta table, SSPRK(3,3), read from the reference's source text (RungeKuttaLevelIntegrator.cpp:3894-3929)
+    import re
+    ref_root = os.environ.get("HAMERS_REFERENCE", "/root/reference")
+    with open(os.path.join(ref_root, "src", "algs", "integrator", "RungeKuttaLevelIntegrator.cpp")) as fh:
+        txt = fh.read()
+    blk = txt[txt.index("Use SSPRK(3, 3) Runge-Kutta scheme as the default scheme"):]
+    blk = blk[:blk.index("else if (input_db)")]
+    for nm in ("alpha", "beta", "gamma"):
+        tab = np.zeros((3, 3))
+        for i, j, expr in re.findall(r"d_" + nm + r"\[(\d)\]\[(\d)\]\s*=\s*([0-9./ ]+);", blk):
+            num = [float(x) for x in expr.split("/")]
+            tab[int(i), int(j)] = num[0] / num[1] if len(num) == 2 else num[0]
+        out["rk_" + nm] = tab
     # ideal-gas EOS scalars (EquationOfStateIdealGas.cpp:29-45, 561-577, 1093-1108); own generator: the arrays above keep
     # their values
     rng_eos = np.random.default_rng(77)
