@@ -24,7 +24,7 @@ MATH_FAST = 1
 
 # every symbol include/hamers_b200.h declares (tests check the library exports them all)
 SYMBOLS = [
-    "hb2_last_error", "hb2_version", "hb2_device_count", "hb2_num_eqn", "hb2_num_comp", "hb2_num_ghosts",
+    "hb2_last_error", "hb2_version", "hb2_constants", "hb2_device_count", "hb2_num_eqn", "hb2_num_comp", "hb2_num_ghosts",
     "hb2_cell_ghost_size", "hb2_cell_size", "hb2_side_size", "hb2_plan_create", "hb2_plan_destroy",
     "hb2_plan_set_stream", "hb2_plan_use_own_stream", "hb2_plan_synchronize", "hb2_plan_launch_count", "hb2_plan_workspace_bytes",
     "hb2_compute_flux_and_source_dev", "hb2_advance_stage_dev", "hb2_fused_stage_dev",
@@ -405,6 +405,13 @@ class DeviceArray:
         if self.ptr:
             device_free(self.ptr)
             self.ptr = 0
+
+
+def constants():
+    """The hard-switch constants compiled into the kernels (hb2_constants); no device needed."""
+    out = (C.c_double * 7)()
+    _check(load_library().hb2_constants(out), "hb2_constants")
+    return list(out)
 
 
 def device_count() -> int:

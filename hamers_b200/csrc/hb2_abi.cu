@@ -415,6 +415,19 @@ extern "C" {
 const char* hb2_last_error(void) { return g_err.c_str(); }
 const char* hb2_version(void) { return "hamers-b200 0.1 (sm_100a, WCNS5_JS_HLLC_HLL)"; }
 
+int hb2_constants(double out[7])
+{
+    if (!out) return fail(-1, "null argument");
+    out[0] = HB2_EPS;
+    out[1] = HB2_SENSOR_THRESHOLD;
+    out[2] = HB2_Y_BOUND_LO;
+    out[3] = HB2_Y_BOUND_UP;
+    out[4] = HB2_Z_BOUND_LO;
+    out[5] = HB2_Z_BOUND_UP;
+    out[6] = HB2_GHOSTS;
+    return 0;
+}
+
 int hb2_device_count(int32_t* count)
 {
     int n = 0;

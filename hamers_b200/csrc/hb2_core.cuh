@@ -37,6 +37,12 @@
 
 #define HB2_G 4
 #define HB2_EPS 1.0e-15 /* HAMERS_EPSILON, include/HAMeRS_config.hpp.in:16 */
+/* hard switches of the path (reported by hb2_constants and compared with the reference's source in the tests) */
+#define HB2_SENSOR_THRESHOLD 0.65 /* ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:2123, 2218, 2313 */
+#define HB2_Y_BOUND_LO (-0.001)   /* FlowModelBasicUtilitiesFiveEqnAllaire.hpp:24-27 */
+#define HB2_Y_BOUND_UP 1.001
+#define HB2_Z_BOUND_LO (-1000.0)
+#define HB2_Z_BOUND_UP 1000.0
 
 namespace hb2 {
 
@@ -418,7 +424,7 @@ HB2_HD int side_bounded(const double (&V)[Tr::NEQ], const Consts& K)
         ok &= (V[0] > 0.0) ? 1 : 0;
         ok &= (V[NEQ - 1] > 0.0) ? 1 : 0;
     } else {
-        const double Z_lo = -1000.0, Z_up = 1000.0, Y_lo = -0.001, Y_up = 1.001;
+        const double Z_lo = HB2_Z_BOUND_LO, Z_up = HB2_Z_BOUND_UP, Y_lo = HB2_Y_BOUND_LO, Y_up = HB2_Y_BOUND_UP;
         double Z[NS];
         Z[NS - 1] = 1.0;
 #pragma unroll
@@ -786,7 +792,7 @@ HB2_HD bool face_sensor(double th_L, double th_R, double Om_L, double Om_R)
     const double theta_avg = 0.5 * (th_L + th_R);
     const double Omega_avg = 0.5 * (Om_L + Om_R);
     const double s = -theta_avg / (fabs(theta_avg) + Omega_avg + HB2_EPS);
-    return s > 0.65;
+    return s > HB2_SENSOR_THRESHOLD;
 }
 
 }  // namespace hb2

@@ -199,7 +199,7 @@ HB2_HD void sensor_phase_gradient(const SensorArgs& A, double* smem, const Senso
 HB2_HD bool face_sensor_fast(double th_L, double th_R, double Om_L, double Om_R)
 {
     const double ts = th_L + th_R;
-    return -ts > 0.65 * (fabs(ts) + (Om_L + Om_R) + 2.0 * HB2_EPS);
+    return -ts > HB2_SENSOR_THRESHOLD * (fabs(ts) + (Om_L + Om_R) + 2.0 * HB2_EPS);
 }
 
 /* C: decisions of plane tc from theta/Omega of planes tc-1, tc */

@@ -86,6 +86,10 @@ typedef struct hb2_plan_s* hb2_plan_t;
 const char* hb2_last_error(void);
 const char* hb2_version(void);
 int hb2_device_count(int32_t* count);
+/* The constants of the path's hard switches as compiled into the kernels: out = { HAMERS_EPSILON
+ * (include/HAMeRS_config.hpp.in:16), the sensor threshold 0.65 (ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:2123),
+ * Y / Z bounds lo, up (FlowModelBasicUtilitiesFiveEqnAllaire.hpp:24-27), ghost width (…WCNS56-HLLC-HLL.cpp:22) }. */
+int hb2_constants(double out[7]);
 int hb2_num_eqn(const hb2_patch_desc* d, int32_t* num_eqn);      /* FlowModel::getNumberOfEquations() */
 int hb2_num_comp(const hb2_patch_desc* d, int32_t* num_comp);
 /* ConvectiveFluxReconstructor::getConvectiveFluxNumberOfGhostCells(): 4 in every direction */

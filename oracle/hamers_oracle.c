@@ -50,6 +50,25 @@ static inline double eos_pressure(double gamma, double rho, double epsilon) { re
 static inline double eos_sound_speed(double gamma, double rho, double p) { return sqrt(gamma * p / rho); }
 static inline double eos_internal_energy(double gamma, double rho, double p) { return p / ((gamma - 1.0) * rho); }
 
+/* hard-switch constants: ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:2123 (0.65);
+ * FlowModelBasicUtilitiesFiveEqnAllaire.hpp:24-27 (bounds); include/HAMeRS_config.hpp.in:16 (epsilon) */
+#define ORC_SENSOR_THRESHOLD 0.65
+#define ORC_Y_BOUND_LO (-0.001)
+#define ORC_Y_BOUND_UP 1.001
+#define ORC_Z_BOUND_LO (-1000.0)
+#define ORC_Z_BOUND_UP 1000.0
+
+void orc_constants(double out[7])
+{
+    out[0] = EPSILON;
+    out[1] = ORC_SENSOR_THRESHOLD;
+    out[2] = ORC_Y_BOUND_LO;
+    out[3] = ORC_Y_BOUND_UP;
+    out[4] = ORC_Z_BOUND_LO;
+    out[5] = ORC_Z_BOUND_UP;
+    out[6] = G;
+}
+
 void orc_eos_point(double gamma, double rho, double epsilon, double* p, double* c, double* eps_back)
 {
     *p = eos_pressure(gamma, rho, epsilon);
@@ -757,7 +776,7 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
                     ok &= (Vs[0][s] > 0.0) ? 1 : 0;
                     ok &= (Vs[neq - 1][s] > 0.0) ? 1 : 0;
                 } else {
-                    const double Z_lo = -1000.0, Z_up = 1000.0, Y_lo = -0.001, Y_up = 1.001;
+                    const double Z_lo = ORC_Z_BOUND_LO, Z_up = ORC_Z_BOUND_UP, Y_lo = ORC_Y_BOUND_LO, Y_up = ORC_Y_BOUND_UP;
                     double Z[ORC_MAX_SPECIES];
                     Z[ns - 1] = 1.0;
                     for (int si = 0; si < ns - 1; si++) {
@@ -845,7 +864,7 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
             FOR_FACES
             {
                 const long s = SIDX(i, j, k);
-                if (sensor[s] > 0.65)
+                if (sensor[s] > ORC_SENSOR_THRESHOLD)
                     F_midpoint[e][s] = F_HYB[e][s];
                 else
                     F_midpoint[e][s] = F_HLLC[e][s];

@@ -100,6 +100,7 @@ int orc_advance_stage(const orc_desc* d, int ncoef,
 int orc_spectral_radii_and_dt(const orc_desc* d, const double* const* Q, int include_ghosts, double* out);
 
 /* Point kernels exported for pinning against oracle/_ref (the reference's own functions). */
+void orc_constants(double out[7]); /* eps, sensor threshold, Y lo/up, Z lo/up, ghost width */
 void orc_eos_point(double gamma, double rho, double epsilon, double* p, double* c, double* eps_back);
 void orc_weno5js_point(const double U[6], int p, double* U_minus, double* U_plus);
 void orc_weno5z_point(const double U[6], int p, double* U_minus, double* U_plus);

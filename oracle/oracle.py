@@ -218,6 +218,12 @@ def spectral_radii_and_dt(desc: PatchDesc, Q: np.ndarray, include_ghosts: bool =
     return np.array(out[:desc.dim]), float(out[desc.dim])
 
 
+def constants():
+    out = (C.c_double * 7)()
+    lib().orc_constants(out)
+    return list(out)
+
+
 def eos_point(gamma, rho, epsilon):
     """(p, c, epsilon recovered from p) of the ideal-gas EOS as the oracle's path evaluates them."""
     p, c, e = C.c_double(), C.c_double(), C.c_double()

@@ -9,6 +9,7 @@ Contents (all float64, seeded):
   weno_U      (n, 6)   six-point stencils (smooth, random, shock-like, constant, tiny-variation)
   weno_minus  (n,)     performLocalWENOInterpolationMinus  (ConvectiveFluxReconstructorWCNS5-JS-HLLC-HLL.cpp:78-118)
   weno_plus   (n,)     performLocalWENOInterpolationPlus   (:124-164)
+  ref_constants (7,): HAMERS_EPSILON, sensor threshold, Y bounds lo/up, Z bounds lo/up, ghost width, parsed from the source
   rk_alpha, rk_beta, rk_gamma (3, 3): the reference's default SSPRK(3,3) table (RungeKuttaLevelIntegrator.cpp:3894-3929)
   eos_in (n, 3) = (gamma, rho, epsilon), eos_out (n, 3) = (p, c, epsilon from p): EquationOfStateIdealGas scalar members
   rp_<case>_{VL,VR,thermo,F_HLLC,F_HYB,vel_mid} for case in ss2d{0,1}, ss3d{0,1,2}, fe2d{0,1}, fe3d{0,1,2}:
@@ -142,6 +143,18 @@ def main():
             num = [float(x) for x in expr.split("/")]
             tab[int(i), int(j)] = num[0] / num[1] if len(num) == 2 else num[0]
         out["rk_" + nm] = tab
+    # constants of the hard switches, read from the reference's source text
+    def grab(rel, pattern):
+        with open(os.path.join(ref_root, rel)) as fh2:
+            return float(re.search(pattern, fh2.read()).group(1))
+    wcns56 = "src/flow/convective_flux_reconstructors/WCNS56/ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp"
+    fe_hpp = "include/flow/flow_models/five-eqn_Allaire/FlowModelBasicUtilitiesFiveEqnAllaire.hpp"
+    out["ref_constants"] = np.array([
+        grab("include/HAMeRS_config.hpp.in", r"#define HAMERS_EPSILON\s+([0-9.eE+-]+)"),
+        grab(wcns56, r"s_z\[idx_midpoint_z\] > ([0-9.]+)"),
+        grab(fe_hpp, r"d_Y_bound_lo = double\(([-0-9.]+)\)"), grab(fe_hpp, r"d_Y_bound_up = double\(([-0-9.]+)\)"),
+        grab(fe_hpp, r"d_Z_bound_lo = double\(([-0-9.]+)\)"), grab(fe_hpp, r"d_Z_bound_up = double\(([-0-9.]+)\)"),
+        grab(wcns56, r"d_num_conv_ghosts = hier::IntVector::getOne\(d_dim\)\*([0-9]+)")])
     # ideal-gas EOS scalars (EquationOfStateIdealGas.cpp:29-45, 561-577, 1093-1108); own generator: the arrays above keep
     # their values
     rng_eos = np.random.default_rng(77)
