@@ -59,6 +59,80 @@ def member_function(text: str, cls: str, name: str) -> str:
     return text[start:i + 1]
 
 
+def statement(text: str, pattern: str, occurrence: int = -1) -> str:
+    """The C statement of `text` that starts at the given occurrence of regex `pattern` and runs to the next ';'."""
+    ms = list(re.finditer(pattern, text))
+    m = ms[occurrence]
+    return text[m.start():text.index(";", m.end()) + 1]
+
+
+def path_statements() -> str:
+    """A function built around the reference's OWN statements for the first derivative (DerivativeFirstOrder.cpp:601),
+    dilatation and vorticity magnitude (ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:1631, 1653-1657), the sensor
+    value (:2098-2101) and the face flux (:2370-2375): the statements are read from /root/reference and compiled
+    verbatim; only the scaffolding around them (arrays of length 1-3, index constants) is ours."""
+    with open(os.path.join(REF, "src/util/derivatives/DerivativeFirstOrder.cpp")) as fh:
+        der = fh.read()
+    with open(os.path.join(REF, SOURCES["ref_weno"].replace("WCNS5-JS-HLLC-HLL", "WCNS56-HLLC-HLL"))) as fh:
+        w56 = fh.read()
+    s_der = statement(der, r"dudx\[idx_derivative\] = \(double\(1\)/double\(2\)")
+    s_theta = statement(w56, r"theta\[idx\] = dudx\[idx\] \+ dvdy\[idx\] \+ dwdz\[idx\]")
+    s_ox = statement(w56, r"const double omega_x = dwdy\[idx\]")
+    s_oy = statement(w56, r"const double omega_y = dudz\[idx\]")
+    s_oz = statement(w56, r"const double omega_z = dvdx\[idx\] - dudy\[idx\]")
+    s_Om = statement(w56, r"Omega\[idx\] = sqrt\(omega_x")
+    s_ta = statement(w56, r"double theta_avg = 0\.5\*\(theta\[idx_L\]")
+    s_Oa = statement(w56, r"double Omega_avg = 0\.5\*\(Omega\[idx_L\]")
+    s_s = statement(w56, r"s_x\[idx_midpoint_x\] = -theta_avg")
+    s_F = statement(w56, r"F_face_x\[idx_face_x\] = dt\*\(")
+    return f"""
+extern "C" void ref_path_points(const double in[16], double out[5])
+{{
+    {{
+        const double u[2] = {{in[1], in[0]}};
+        const int idx_x_L = 0, idx_x_R = 1, idx_derivative = 0;
+        const double dx = in[2];
+        double dudx[1];
+        {s_der}
+        out[0] = dudx[0];
+    }}
+    double theta[2], Omega[2];
+    {{
+        const int idx = 0;
+        const double dudx[1] = {{in[3]}}, dudy[1] = {{in[4]}}, dudz[1] = {{in[5]}}, dvdx[1] = {{in[6]}}, dvdy[1] = {{in[7]}},
+                     dvdz[1] = {{in[8]}}, dwdx[1] = {{in[9]}}, dwdy[1] = {{in[10]}}, dwdz[1] = {{in[11]}};
+        {s_theta}
+        {s_ox}
+        {s_oy}
+        {s_oz}
+        {s_Om}
+        out[1] = theta[0];
+        out[2] = Omega[0];
+    }}
+    {{
+        theta[1] = 0.75*out[1] - in[3];
+        Omega[1] = 1.25*out[2];
+        const int idx_L = 0, idx_R = 1, idx_midpoint_x = 0;
+        double s_x[1];
+        {s_ta}
+        {s_Oa}
+        {s_s}
+        out[3] = s_x[0];
+    }}
+    {{
+        const double dt = in[12];
+        double mid[3] = {{in[13], in[14], in[15]}}, node[2] = {{in[1], in[0]}};
+        double* F_midpoint_x[1] = {{mid}};
+        double* F_node_x[1] = {{node}};
+        const int ei = 0, idx_midpoint_x_L = 0, idx_midpoint_x = 1, idx_midpoint_x_R = 2, idx_node_L = 0, idx_node_R = 1, idx_face_x = 0;
+        double F_face_x[1];
+        {s_F}
+        out[4] = F_face_x[0];
+    }}
+}}
+"""
+
+
 def static_inline_functions(text: str) -> str:
     """Return the concatenation of every `static inline ...` function definition in text."""
     out = []
@@ -187,6 +261,7 @@ def main() -> int:
     parts.append("#include <vector>\nnamespace ref_eos {\nstruct EquationOfStateIdealGas {\n" + decls + "\n};\n" + bodies + "\n}\n")
     parts.append(WRAPPERS)
     parts.append(EOS_WRAPPER)
+    parts.append(path_statements())
     gen = os.path.join(OUT, "_generated_ref_kernels.cpp")
     with open(gen, "w") as fh:
         fh.write("\n".join(parts))

@@ -50,6 +50,43 @@ static inline double eos_pressure(double gamma, double rho, double epsilon) { re
 static inline double eos_sound_speed(double gamma, double rho, double p) { return sqrt(gamma * p / rho); }
 static inline double eos_internal_energy(double gamma, double rho, double p) { return p / ((gamma - 1.0) * rho); }
 
+/* Point formulas of the sensor chain and of the flux reconstruction, used by the loops below and exported so that they
+ * can be pinned against the reference's own statements (oracle/_ref compiles those verbatim):
+ *   first derivative, order 2: DerivativeFirstOrder.cpp:229, 382, 601
+ *   dilatation / vorticity magnitude: ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:1631, 1653-1657 (2D :713, :729)
+ *   sensor value: :2098-2101
+ *   6th-order midpoint-and-node flux: :2370-2375 */
+static inline double derivative_2nd(double u_R, double u_L, double dx) { return (1.0 / 2.0 * (u_R - u_L)) / dx; }
+static inline double dilatation_3d(double dudx, double dvdy, double dwdz) { return dudx + dvdy + dwdz; }
+static inline double vorticity_mag_3d(double dudy, double dudz, double dvdx, double dvdz, double dwdx, double dwdy)
+{
+    const double omega_x = dwdy - dvdz;
+    const double omega_y = dudz - dwdx;
+    const double omega_z = dvdx - dudy;
+    return sqrt(omega_x * omega_x + omega_y * omega_y + omega_z * omega_z);
+}
+static inline double sensor_value(double theta_L, double theta_R, double Omega_L, double Omega_R)
+{
+    const double theta_avg = 0.5 * (theta_L + theta_R);
+    const double Omega_avg = 0.5 * (Omega_L + Omega_R);
+    return -theta_avg / (fabs(theta_avg) + Omega_avg + EPSILON);
+}
+static inline double face_flux(double dt, double Fm_L, double Fm_0, double Fm_R, double Fn_L, double Fn_R)
+{
+    return dt * (1.0 / 30.0 * (Fm_R + Fm_L) - 3.0 / 10.0 * (Fn_R + Fn_L) + 23.0 / 15.0 * Fm_0);
+}
+
+void orc_path_points(const double in[16], double out[5])
+{
+    /* in: u_R, u_L, dx | dudx dudy dudz dvdx dvdy dvdz dwdx dwdy dwdz | (theta, Omega as computed here and scaled copies) |
+     *     dt, Fm_L, Fm_0, Fm_R  (Fn_L = in[1], Fn_R = in[0]) */
+    out[0] = derivative_2nd(in[0], in[1], in[2]);
+    out[1] = dilatation_3d(in[3], in[7], in[11]);
+    out[2] = vorticity_mag_3d(in[4], in[5], in[6], in[8], in[9], in[10]);
+    out[3] = sensor_value(out[1], 0.75 * out[1] - in[3], out[2], 1.25 * out[2]);
+    out[4] = face_flux(in[12], in[13], in[14], in[15], in[1], in[0]);
+}
+
 /* hard-switch constants: ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:2123 (0.65);
  * FlowModelBasicUtilitiesFiveEqnAllaire.hpp:24-27 (bounds); include/HAMeRS_config.hpp.in:16 (epsilon) */
 #define ORC_SENSOR_THRESHOLD 0.65
@@ -621,7 +658,7 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
                 for (int j = -g2[1]; j < q->n[1] + g2[1]; j++)
                     for (int i = -g2[0]; i < q->n[0] + g2[0]; i++) {
                         const long x = cidx(q, i, j, k);
-                        out[IDX2(i, j, k)] = (1.0 / 2.0 * (vel[a][x + q->cs[b]] - vel[a][x - q->cs[b]])) / d->dx[b];
+                        out[IDX2(i, j, k)] = derivative_2nd(vel[a][x + q->cs[b]], vel[a][x - q->cs[b]], d->dx[b]);
                     }
         }
     }
@@ -630,11 +667,9 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
             theta[x] = grad[0][x] + grad[3][x];
             Omega[x] = fabs(grad[2][x] - grad[1][x]);
         } else {
-            theta[x] = grad[0][x] + grad[4][x] + grad[8][x];
-            const double omega_x = grad[7][x] - grad[5][x];
-            const double omega_y = grad[2][x] - grad[6][x];
-            const double omega_z = grad[3][x] - grad[1][x];
-            Omega[x] = sqrt(omega_x * omega_x + omega_y * omega_y + omega_z * omega_z);
+            /* grad[3a + b] = d u_a / d x_b */
+            theta[x] = dilatation_3d(grad[0][x], grad[4][x], grad[8][x]);
+            Omega[x] = vorticity_mag_3d(grad[1][x], grad[2][x], grad[3][x], grad[5][x], grad[6][x], grad[7][x]);
         }
     }
 
@@ -856,9 +891,7 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
             const long xR2 = IDX2(i, j, k);
             const long st2 = dir == 0 ? 1 : (dir == 1 ? d2[0] : (long)d2[0] * d2[1]);
             const long xL2 = xR2 - st2;
-            const double theta_avg = 0.5 * (theta[xL2] + theta[xR2]);
-            const double Omega_avg = 0.5 * (Omega[xL2] + Omega[xR2]);
-            sensor[s] = -theta_avg / (fabs(theta_avg) + Omega_avg + EPSILON);
+            sensor[s] = sensor_value(theta[xL2], theta[xR2], Omega[xL2], Omega[xR2]);
         }
         for (int e = 0; e < neq; e++) {
             FOR_FACES
@@ -889,9 +922,8 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
                             const long f = i + fd[0] * ((long)j + fd[1] * (long)k);
                             const long s = SIDX(i, j, k);
                             const long xR = cidx(q, i, j, k), xL = xR - st;
-                            F_face[f] = dt * (1.0 / 30.0 * (F_midpoint[e][s + sst] + F_midpoint[e][s - sst]) -
-                                              3.0 / 10.0 * (node_flux(q, Q, vel, p, dir, e, xR) + node_flux(q, Q, vel, p, dir, e, xL)) +
-                                              23.0 / 15.0 * F_midpoint[e][s]);
+                            F_face[f] = face_flux(dt, F_midpoint[e][s - sst], F_midpoint[e][s], F_midpoint[e][s + sst],
+                                                  node_flux(q, Q, vel, p, dir, e, xL), node_flux(q, Q, vel, p, dir, e, xR));
                         }
             }
         }

@@ -7,8 +7,8 @@
  * legs may load this library; the product (hamers_b200/) never links or calls it.
  *
  * Parity status: the point kernels for the WCNS5-JS / WCNS5-Z / WCNS6-LD interpolations,
- * the HLLC / HLLC-HLL Riemann solvers and the ideal-gas equation of state are PINNED
- * against the reference's own compiled functions (oracle/_ref, built by
+ * the HLLC / HLLC-HLL Riemann solvers, the ideal-gas equation of state, the sensor chain
+ * and the face-flux formula are PINNED against the reference's own compiled code (oracle/_ref, built by
  * oracle/build_ref.py from /root/reference).  Everything else (derived cell data, characteristic
  * projection, bounds check / fallback, sensor, flux differencing, RK update) is a
  * restatement of formulas cited below ("parity unpinned" for those pieces: the
@@ -100,6 +100,9 @@ int orc_advance_stage(const orc_desc* d, int ncoef,
 int orc_spectral_radii_and_dt(const orc_desc* d, const double* const* Q, int include_ghosts, double* out);
 
 /* Point kernels exported for pinning against oracle/_ref (the reference's own functions). */
+/* first derivative, dilatation, vorticity magnitude, sensor value and the face-flux formula as the loops evaluate them
+ * (layout of in/out: hamers_oracle.c) */
+void orc_path_points(const double in[16], double out[5]);
 void orc_constants(double out[7]); /* eps, sensor threshold, Y lo/up, Z lo/up, ghost width */
 void orc_eos_point(double gamma, double rho, double epsilon, double* p, double* c, double* eps_back);
 void orc_weno5js_point(const double U[6], int p, double* U_minus, double* U_plus);

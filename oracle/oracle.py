@@ -218,6 +218,14 @@ def spectral_radii_and_dt(desc: PatchDesc, Q: np.ndarray, include_ghosts: bool =
     return np.array(out[:desc.dim]), float(out[desc.dim])
 
 
+def path_points(vals):
+    """orc_path_points: (derivative, theta, Omega, sensor value, face flux) from 16 inputs."""
+    a = (C.c_double * 16)(*[float(x) for x in vals])
+    out = (C.c_double * 5)()
+    lib().orc_path_points(a, out)
+    return list(out)
+
+
 def constants():
     out = (C.c_double * 7)()
     lib().orc_constants(out)

@@ -9,6 +9,9 @@ Contents (all float64, seeded):
   weno_U      (n, 6)   six-point stencils (smooth, random, shock-like, constant, tiny-variation)
   weno_minus  (n,)     performLocalWENOInterpolationMinus  (ConvectiveFluxReconstructorWCNS5-JS-HLLC-HLL.cpp:78-118)
   weno_plus   (n,)     performLocalWENOInterpolationPlus   (:124-164)
+  path_points_in (n, 16), path_points_out (n, 5): first derivative (DerivativeFirstOrder.cpp:601), dilatation, vorticity
+                       magnitude, sensor value and face flux (ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:1631,
+                       1653-1657, 2098-2101, 2370-2375) from the reference's own statements, compiled verbatim
   ref_constants (7,): HAMERS_EPSILON, sensor threshold, Y bounds lo/up, Z bounds lo/up, ghost width, parsed from the source
   rk_alpha, rk_beta, rk_gamma (3, 3): the reference's default SSPRK(3,3) table (RungeKuttaLevelIntegrator.cpp:3894-3929)
   eos_in (n, 3) = (gamma, rho, epsilon), eos_out (n, 3) = (p, c, epsilon from p): EquationOfStateIdealGas scalar members
@@ -155,6 +158,17 @@ def main():
         grab(fe_hpp, r"d_Y_bound_lo = double\(([-0-9.]+)\)"), grab(fe_hpp, r"d_Y_bound_up = double\(([-0-9.]+)\)"),
         grab(fe_hpp, r"d_Z_bound_lo = double\(([-0-9.]+)\)"), grab(fe_hpp, r"d_Z_bound_up = double\(([-0-9.]+)\)"),
         grab(wcns56, r"d_num_conv_ghosts = hier::IntVector::getOne\(d_dim\)\*([0-9]+)")])
+    # the reference's own statements of the sensor chain and of the face-flux formula (oracle/build_ref.py: path_statements)
+    rng_pp = np.random.default_rng(123)
+    pp_in = rng_pp.standard_normal((400, 16)) * 10.0 ** rng_pp.uniform(-3, 3, (400, 1))
+    pp_in[:, 2] = np.abs(pp_in[:, 2]) + 1.0e-3       # dx
+    pp_in[:, 12] = np.abs(pp_in[:, 12])              # dt
+    pp_out = []
+    for v in pp_in:
+        o = (C.c_double * 5)()
+        lib.ref_path_points((C.c_double * 16)(*v), o)
+        pp_out.append(list(o))
+    out["path_points_in"], out["path_points_out"] = pp_in, np.array(pp_out)
     # ideal-gas EOS scalars (EquationOfStateIdealGas.cpp:29-45, 561-577, 1093-1108); own generator: the arrays above keep
     # their values
     rng_eos = np.random.default_rng(77)
