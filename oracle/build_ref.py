@@ -133,6 +133,95 @@ extern "C" void ref_path_points(const double in[16], double out[5])
 """
 
 
+def path_statements2() -> str:
+    """Second group, same technique: velocity and specific internal energy (FlowModelSingleSpecies.cpp:2824-2826,
+    3049-3051), face averages, characteristic projection and its inverse of the single-species 3-D x direction
+    (FlowModelBasicUtilitiesSingleSpecies.cpp:5000-5001, 6324-6329, 7373-7379), RK update (Euler.cpp:1479, 1544-1548)."""
+    with open(os.path.join(REF, "src/flow/flow_models/single-species/FlowModelSingleSpecies.cpp")) as fh:
+        fm = fh.read()
+    with open(os.path.join(REF, "src/flow/flow_models/single-species/FlowModelBasicUtilitiesSingleSpecies.cpp")) as fh:
+        bu = fh.read()
+    with open(os.path.join(REF, "src/apps/Euler/Euler.cpp")) as fh:
+        eu = fh.read()
+    s_u = statement(fm, r"u\[idx_velocity\] = rho_u\[idx\]/rho\[idx\]")
+    s_v = statement(fm, r"v\[idx_velocity\] = rho_v\[idx\]/rho\[idx\]")
+    s_w = statement(fm, r"w\[idx_velocity\] = rho_w\[idx\]/rho\[idx\]")
+    s_e = statement(fm, r"epsilon\[idx_internal_energy\] = E\[idx\]/rho\[idx\] -\s*double\(1\)/double\(2\)\*\(u\[idx_velocity\]\*u\[idx_velocity\] \+ v\[idx_velocity\]\*v\[idx_velocity\] \+")
+    s_ra = statement(bu, r"rho_average\[idx_face_x\] = double\(1\)/double\(2\)\*\(rho\[idx_L\] \+ rho\[idx_R\]\)")
+    s_ca = statement(bu, r"c_average\[idx_face_x\] = double\(1\)/double\(2\)\*\(c\[idx_sound_speed_L\] \+ c\[idx_sound_speed_R\]\)")
+    proj = [statement(bu, r"W\[0\]\[idx_face\] = -double\(1\)/double\(2\)\*rho_average\[idx_face\]\*c_average\[idx_face\]\*V\[1\]\[idx_vel\]"),
+            statement(bu, r"W\[1\]\[idx_face\] = V\[0\]\[idx_rho\] - double\(1\)/\(c_average"),
+            statement(bu, r"W\[2\]\[idx_face\] = V\[2\]\[idx_vel\]"),
+            statement(bu, r"W\[3\]\[idx_face\] = V\[3\]\[idx_vel\]"),
+            statement(bu, r"W\[4\]\[idx_face\] = double\(1\)/double\(2\)\*rho_average\[idx_face\]\*c_average\[idx_face\]\*V\[1\]\[idx_vel\]")]
+    back = [statement(bu, r"V\[0\]\[idx_face\] = double\(1\)/\(c_average\[idx_face\]\*c_average\[idx_face\]\)\*W\[0\]\[idx_face\]"),
+            statement(bu, r"V\[1\]\[idx_face\] = -double\(1\)/\(rho_average\[idx_face\]\*c_average\[idx_face\]\)\*W\[0\]\[idx_face\]"),
+            statement(bu, r"V\[2\]\[idx_face\] = W\[2\]\[idx_face\]"),
+            statement(bu, r"V\[3\]\[idx_face\] = W\[3\]\[idx_face\]"),
+            statement(bu, r"V\[4\]\[idx_face\] = W\[0\]\[idx_face\] \+ W\[4\]\[idx_face\]")]
+    s_al = statement(eu, r"Q\[ei\]\[idx\] \+= alpha\[n\]\*Q_intermediate\[ei\]\[idx_intermediate\]")
+    s_be = statement(eu, r"Q\[ei\]\[idx\] \+= beta\[n\]\*\s*\(-\(F_x_intermediate\[idx_flux_x_R\] - F_x_intermediate\[idx_flux_x_L\]\)/dx_0 -\s*\(F_y_intermediate\[idx_flux_y_T\] - F_y_intermediate\[idx_flux_y_B\]\)/dx_1 -\s*\(F_z")
+    nl = "\n        "
+    return f"""
+extern "C" void ref_path_points2(const double in[32], double out[20])
+{{
+    {{
+        const int idx = 0, idx_velocity = 0, idx_internal_energy = 0;
+        const double rho[1] = {{in[0]}}, rho_u[1] = {{in[1]}}, rho_v[1] = {{in[2]}}, rho_w[1] = {{in[3]}}, E[1] = {{in[4]}};
+        double u[1], v[1], w[1], epsilon[1];
+        {s_u}
+        {s_v}
+        {s_w}
+        {s_e}
+        out[0] = u[0]; out[1] = v[0]; out[2] = w[0]; out[3] = epsilon[0];
+    }}
+    double rho_average[1], c_average[1];
+    {{
+        const int idx_face_x = 0, idx_L = 0, idx_R = 1, idx_sound_speed_L = 0, idx_sound_speed_R = 1;
+        const double rho[2] = {{in[5], in[6]}}, c[2] = {{in[7], in[8]}};
+        {s_ra}
+        {s_ca}
+        out[4] = rho_average[0]; out[5] = c_average[0];
+    }}
+    {{
+        const int idx_face = 0, idx_rho = 0, idx_vel = 0, idx_p = 0;
+        double v0[1] = {{in[9]}}, v1[1] = {{in[10]}}, v2[1] = {{in[11]}}, v3[1] = {{in[12]}}, v4[1] = {{in[13]}};
+        double* V[5] = {{v0, v1, v2, v3, v4}};
+        double w0[1], w1[1], w2[1], w3[1], w4[1];
+        double* W[5] = {{w0, w1, w2, w3, w4}};
+        {nl.join(proj)}
+        for (int e = 0; e < 5; e++) out[6 + e] = W[e][0];
+    }}
+    {{
+        const int idx_face = 0;
+        double w0[1] = {{in[14]}}, w1[1] = {{in[15]}}, w2[1] = {{in[16]}}, w3[1] = {{in[17]}}, w4[1] = {{in[18]}};
+        double* W[5] = {{w0, w1, w2, w3, w4}};
+        double v0[1], v1[1], v2[1], v3[1], v4[1];
+        double* V[5] = {{v0, v1, v2, v3, v4}};
+        {nl.join(back)}
+        for (int e = 0; e < 5; e++) out[11 + e] = V[e][0];
+    }}
+    {{
+        const int ei = 0, n = 0, idx = 0, idx_intermediate = 0, idx_source = 0;
+        const int idx_flux_x_R = 0, idx_flux_x_L = 1, idx_flux_y_T = 0, idx_flux_y_B = 1, idx_flux_z_F = 0, idx_flux_z_B = 1;
+        double q0[1] = {{in[19]}};
+        double* Q[1] = {{q0}};
+        const double alpha[1] = {{in[20]}}, beta[1] = {{in[22]}};
+        double qi[1] = {{in[21]}};
+        double* Q_intermediate[1] = {{qi}};
+        const double F_x_intermediate[2] = {{in[23], in[24]}}, F_y_intermediate[2] = {{in[25], in[26]}}, F_z_intermediate[2] = {{in[27], in[28]}};
+        const double dx_0 = in[29], dx_1 = in[30], dx_2 = in[31];
+        const double S_intermediate[1] = {{in[18]}};
+        {s_al}
+        out[16] = Q[0][0];
+        {s_be}
+        out[17] = Q[0][0];
+        out[18] = 0.0; out[19] = 0.0;
+    }}
+}}
+"""
+
+
 def static_inline_functions(text: str) -> str:
     """Return the concatenation of every `static inline ...` function definition in text."""
     out = []
@@ -262,6 +351,7 @@ def main() -> int:
     parts.append(WRAPPERS)
     parts.append(EOS_WRAPPER)
     parts.append(path_statements())
+    parts.append(path_statements2())
     gen = os.path.join(OUT, "_generated_ref_kernels.cpp")
     with open(gen, "w") as fh:
         fh.write("\n".join(parts))

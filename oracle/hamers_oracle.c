@@ -76,6 +76,73 @@ static inline double face_flux(double dt, double Fm_L, double Fm_0, double Fm_R,
     return dt * (1.0 / 30.0 * (Fm_R + Fm_L) - 3.0 / 10.0 * (Fn_R + Fn_L) + 23.0 / 15.0 * Fm_0);
 }
 
+/* More point formulas of the single-species 3-D x-direction path, used by the loops below and pinned the same way:
+ *   velocity, specific internal energy: FlowModelSingleSpecies.cpp:2824-2826, 3049-3051
+ *   face averages, characteristic projection and its inverse: FlowModelBasicUtilitiesSingleSpecies.cpp:5000-5001,
+ *     6324-6329, 7373-7379
+ *   RK update: Euler.cpp:1479 (alpha term), 1544-1548 (beta term) */
+static inline double quotient(double a, double rho) { return a / rho; }
+static inline double internal_energy_3d(double E, double rho, double u, double v, double w)
+{
+    return E / rho - 1.0 / 2.0 * (u * u + v * v + w * w);
+}
+static inline double face_average(double a_L, double a_R) { return 1.0 / 2.0 * (a_L + a_R); }
+static inline double char_acoustic_minus(double rho_avg, double c_avg, double un, double p)
+{
+    return -1.0 / 2.0 * rho_avg * c_avg * un + 1.0 / 2.0 * p;
+}
+static inline double char_acoustic_plus(double rho_avg, double c_avg, double un, double p)
+{
+    return 1.0 / 2.0 * rho_avg * c_avg * un + 1.0 / 2.0 * p;
+}
+static inline double char_entropy(double c_avg, double rho, double p) { return rho - 1.0 / (c_avg * c_avg) * p; }
+static inline double back_density(double c_avg, double W0, double W1, double WL)
+{
+    return 1.0 / (c_avg * c_avg) * W0 + W1 + 1.0 / (c_avg * c_avg) * WL;
+}
+static inline double back_normal_velocity(double rho_avg, double c_avg, double W0, double WL)
+{
+    return -1.0 / (rho_avg * c_avg) * W0 + 1.0 / (rho_avg * c_avg) * WL;
+}
+static inline double back_pressure(double W0, double WL) { return W0 + WL; }
+static inline double rk_beta_term_3d(double beta, double FxR, double FxL, double FyT, double FyB, double FzF, double FzB,
+                                     double dx0, double dx1, double dx2, double S)
+{
+    return beta * (-(FxR - FxL) / dx0 - (FyT - FyB) / dx1 - (FzF - FzB) / dx2 + S);
+}
+
+void orc_path_points2(const double in[32], double out[20])
+{
+    /* in: rho, rho_u, rho_v, rho_w, E | rho_L, rho_R, c_L, c_R | V0..V4 of a stencil cell | Wc0..Wc4 |
+     *     Q0, alpha, Qint, beta, FxR, FxL, FyT, FyB, FzF, FzB, dx0, dx1, dx2, S */
+    out[0] = quotient(in[1], in[0]);
+    out[1] = quotient(in[2], in[0]);
+    out[2] = quotient(in[3], in[0]);
+    out[3] = internal_energy_3d(in[4], in[0], out[0], out[1], out[2]);
+    const double rho_avg = face_average(in[5], in[6]), c_avg = face_average(in[7], in[8]);
+    out[4] = rho_avg;
+    out[5] = c_avg;
+    const double* V = in + 9;
+    out[6] = char_acoustic_minus(rho_avg, c_avg, V[1], V[4]);
+    out[7] = char_entropy(c_avg, V[0], V[4]);
+    out[8] = V[2];
+    out[9] = V[3];
+    out[10] = char_acoustic_plus(rho_avg, c_avg, V[1], V[4]);
+    const double* Wc = in + 14;
+    out[11] = back_density(c_avg, Wc[0], Wc[1], Wc[4]);
+    out[12] = back_normal_velocity(rho_avg, c_avg, Wc[0], Wc[4]);
+    out[13] = Wc[2];
+    out[14] = Wc[3];
+    out[15] = back_pressure(Wc[0], Wc[4]);
+    double Q = in[19];
+    Q += in[20] * in[21];
+    out[16] = Q;
+    Q += rk_beta_term_3d(in[22], in[23], in[24], in[25], in[26], in[27], in[28], in[29], in[30], in[31], in[18]);
+    out[17] = Q;
+    out[18] = 0.0;
+    out[19] = 0.0;
+}
+
 void orc_path_points(const double in[16], double out[5])
 {
     /* in: u_R, u_L, dx | dudx dudy dudz dvdx dvdy dvdz dwdx dwdy dwdz | (theta, Omega as computed here and scaled copies) |
@@ -517,9 +584,10 @@ static void cell_stage(const geom_t* q, const double* gam, const double* const* 
             const double rho = Q[0][x];
             double ke = 0.0;
             for (int a = 0; a < dim; a++) {
-                vel[a][x] = Q[1 + a][x] / rho;
+                vel[a][x] = quotient(Q[1 + a][x], rho);
                 ke = (a == 0) ? vel[a][x] * vel[a][x] : ke + vel[a][x] * vel[a][x];
             }
+            /* = internal_energy_3d for dim == 3 (same operation order: E/rho - 1/2 ((u u + v v) + w w)) */
             const double epsilon = Q[dim + 1][x] / rho - 1.0 / 2.0 * ke;
             p[x] = eos_pressure(gam[0], rho, epsilon);
             c[x] = eos_sound_speed(gam[0], rho, p[x]);
@@ -703,8 +771,8 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
             const long xR = cidx(q, i, j, k), xL = xR - st, s = SIDX(i, j, k);
             if (has_adv)
                 for (int si = 0; si < ns; si++) Zrho_avg[si][s] = 1.0 / 2.0 * (Q[si][xL] + Q[si][xR]);
-            rho_avg[s] = 1.0 / 2.0 * (rho_cell[xL] + rho_cell[xR]);
-            c_avg[s] = 1.0 / 2.0 * (c[xL] + c[xR]);
+            rho_avg[s] = face_average(rho_cell[xL], rho_cell[xR]);
+            c_avg[s] = face_average(c[xL], c[xR]);
         }
 
         /* ---- step 4: characteristic variables of the six stencil cells (:1814-1822) ----
@@ -719,12 +787,12 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
             {
                 const long x = cidx(q, i, j, k) + off, s = SIDX(i, j, k);
                 if (q->model == ORC_SINGLE_SPECIES) {
-                    W[m][0][s] = -1.0 / 2.0 * rho_avg[s] * c_avg[s] * V[1 + dir][x] + 1.0 / 2.0 * V[dim + 1][x];
-                    W[m][1][s] = V[0][x] - 1.0 / (c_avg[s] * c_avg[s]) * V[dim + 1][x];
+                    W[m][0][s] = char_acoustic_minus(rho_avg[s], c_avg[s], V[1 + dir][x], V[dim + 1][x]);
+                    W[m][1][s] = char_entropy(c_avg[s], V[0][x], V[dim + 1][x]);
                     int w = 2;
                     for (int a = 0; a < dim; a++)
                         if (a != dir) W[m][w++][s] = V[1 + a][x];
-                    W[m][dim + 1][s] = 1.0 / 2.0 * rho_avg[s] * c_avg[s] * V[1 + dir][x] + 1.0 / 2.0 * V[dim + 1][x];
+                    W[m][dim + 1][s] = char_acoustic_plus(rho_avg[s], c_avg[s], V[1 + dir][x], V[dim + 1][x]);
                 } else {
                     W[m][0][s] = V[iv + dir][x] - 1.0 / (rho_avg[s] * c_avg[s]) * V[ip][x];
                     for (int si = 0; si < ns; si++)
@@ -771,15 +839,15 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
             {
                 const long s = SIDX(i, j, k);
                 if (q->model == ORC_SINGLE_SPECIES) {
-                    Vs[0][s] = 1.0 / (c_avg[s] * c_avg[s]) * Wc[0][s] + Wc[1][s] + 1.0 / (c_avg[s] * c_avg[s]) * Wc[dim + 1][s];
+                    Vs[0][s] = back_density(c_avg[s], Wc[0][s], Wc[1][s], Wc[dim + 1][s]);
                     int w = 2;
                     for (int a = 0; a < dim; a++) {
                         if (a == dir)
-                            Vs[1 + a][s] = -1.0 / (rho_avg[s] * c_avg[s]) * Wc[0][s] + 1.0 / (rho_avg[s] * c_avg[s]) * Wc[dim + 1][s];
+                            Vs[1 + a][s] = back_normal_velocity(rho_avg[s], c_avg[s], Wc[0][s], Wc[dim + 1][s]);
                         else
                             Vs[1 + a][s] = Wc[w++][s];
                     }
-                    Vs[dim + 1][s] = Wc[0][s] + Wc[dim + 1][s];
+                    Vs[dim + 1][s] = back_pressure(Wc[0][s], Wc[dim + 1][s]);
                 } else {
                     for (int si = 0; si < ns; si++)
                         Vs[si][s] = -1.0 / 2.0 * Zrho_avg[si][s] / c_avg[s] * Wc[0][s] + Wc[si + 1][s] +
@@ -1037,9 +1105,8 @@ int orc_advance_stage(const orc_desc* d, int ncoef,
                                                           (Fy[fyB + nx] - Fy[fyB]) / d->dx[1] + Sn[xs]);
                             } else {
                                 const long fzB = xs;
-                                U_out[e][x] += beta[n] * (-(Fx[fxL + 1] - Fx[fxL]) / d->dx[0] -
-                                                          (Fy[fyB + nx] - Fy[fyB]) / d->dx[1] -
-                                                          (Fz[fzB + nx * ny] - Fz[fzB]) / d->dx[2] + Sn[xs]);
+                                U_out[e][x] += rk_beta_term_3d(beta[n], Fx[fxL + 1], Fx[fxL], Fy[fyB + nx], Fy[fyB],
+                                                               Fz[fzB + nx * ny], Fz[fzB], d->dx[0], d->dx[1], d->dx[2], Sn[xs]);
                             }
                         }
             }

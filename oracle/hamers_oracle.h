@@ -103,6 +103,8 @@ int orc_spectral_radii_and_dt(const orc_desc* d, const double* const* Q, int inc
 /* first derivative, dilatation, vorticity magnitude, sensor value and the face-flux formula as the loops evaluate them
  * (layout of in/out: hamers_oracle.c) */
 void orc_path_points(const double in[16], double out[5]);
+/* velocity, internal energy, face averages, characteristic projection and its inverse (single-species, 3-D, x), RK update */
+void orc_path_points2(const double in[32], double out[20]);
 void orc_constants(double out[7]); /* eps, sensor threshold, Y lo/up, Z lo/up, ghost width */
 void orc_eos_point(double gamma, double rho, double epsilon, double* p, double* c, double* eps_back);
 void orc_weno5js_point(const double U[6], int p, double* U_minus, double* U_plus);

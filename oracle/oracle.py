@@ -226,6 +226,14 @@ def path_points(vals):
     return list(out)
 
 
+def path_points2(vals):
+    """orc_path_points2: derived data, characteristic projection / back-projection, RK update from 32 inputs."""
+    a = (C.c_double * 32)(*[float(x) for x in vals])
+    out = (C.c_double * 20)()
+    lib().orc_path_points2(a, out)
+    return list(out)
+
+
 def constants():
     out = (C.c_double * 7)()
     lib().orc_constants(out)

@@ -12,6 +12,10 @@ Contents (all float64, seeded):
   path_points_in (n, 16), path_points_out (n, 5): first derivative (DerivativeFirstOrder.cpp:601), dilatation, vorticity
                        magnitude, sensor value and face flux (ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:1631,
                        1653-1657, 2098-2101, 2370-2375) from the reference's own statements, compiled verbatim
+  path_points2_in (n, 32), path_points2_out (n, 20): velocity and specific internal energy (FlowModelSingleSpecies.cpp:
+                       2824-2826, 3049-3051), face averages, characteristic projection and back-projection
+                       (FlowModelBasicUtilitiesSingleSpecies.cpp:5000-5001, 6324-6329, 7373-7379), RK alpha/beta update
+                       (Euler.cpp:1479, 1544-1548), again the reference's own statements compiled verbatim
   ref_constants (7,): HAMERS_EPSILON, sensor threshold, Y bounds lo/up, Z bounds lo/up, ghost width, parsed from the source
   rk_alpha, rk_beta, rk_gamma (3, 3): the reference's default SSPRK(3,3) table (RungeKuttaLevelIntegrator.cpp:3894-3929)
   eos_in (n, 3) = (gamma, rho, epsilon), eos_out (n, 3) = (p, c, epsilon from p): EquationOfStateIdealGas scalar members
@@ -169,6 +173,17 @@ def main():
         lib.ref_path_points((C.c_double * 16)(*v), o)
         pp_out.append(list(o))
     out["path_points_in"], out["path_points_out"] = pp_in, np.array(pp_out)
+    # second group (oracle/build_ref.py: path_statements2); own generator again
+    rng_p2 = np.random.default_rng(321)
+    p2_in = rng_p2.standard_normal((400, 32)) * 10.0 ** rng_p2.uniform(-2, 2, (400, 1))
+    pos = [0, 5, 6, 7, 8, 29, 30, 31]               # densities, sound speeds, mesh widths
+    p2_in[:, pos] = np.abs(p2_in[:, pos]) + 1.0e-3
+    p2_out = []
+    for v in p2_in:
+        o = (C.c_double * 20)()
+        lib.ref_path_points2((C.c_double * 32)(*v), o)
+        p2_out.append(list(o))
+    out["path_points2_in"], out["path_points2_out"] = p2_in, np.array(p2_out)
     # ideal-gas EOS scalars (EquationOfStateIdealGas.cpp:29-45, 561-577, 1093-1108); own generator: the arrays above keep
     # their values
     rng_eos = np.random.default_rng(77)
