@@ -222,6 +222,166 @@ extern "C" void ref_path_points2(const double in[32], double out[20])
 """
 
 
+def line_range(text: str, first: int, last: int) -> str:
+    """Lines first..last (1-based, inclusive) of text: restricts statement() to one branch of a dimension switch."""
+    return "\n".join(text.split("\n")[first - 1:last])
+
+
+def path_statements3() -> str:
+    """Third group, five-eqn Allaire with two species, 3-D, x direction: mixture density
+    (EquationOfStateMixingRules.cpp:871), mass fractions, velocity, internal energy (FlowModelFiveEqnAllaire.cpp:3965,
+    4188-4190, 4428-4430), mixture gamma from all stored volume fractions (EquationOfStateMixingRulesIdealGas.cpp:7544,
+    7565, 7586), pressure, Gruneisen parameter, Psi (EquationOfStateIdealGas.cpp:5756, 8157, 8308), sound speed
+    (FlowModelFiveEqnAllaire.cpp:4700-4853), face averages, projection and back-projection
+    (FlowModelBasicUtilitiesFiveEqnAllaire.cpp:7952-7996, 8848-8921, 9700-9760), advective source
+    (ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:2623-2641)."""
+    def rd(rel):
+        with open(os.path.join(REF, rel)) as fh:
+            return fh.read()
+    fm = rd("src/flow/flow_models/five-eqn_Allaire/FlowModelFiveEqnAllaire.cpp")
+    bu = rd("src/flow/flow_models/five-eqn_Allaire/FlowModelBasicUtilitiesFiveEqnAllaire.cpp")
+    mr = rd("src/util/mixing_rules/equations_of_state/EquationOfStateMixingRules.cpp")
+    mi = line_range(rd("src/util/mixing_rules/equations_of_state/ideal_gas/EquationOfStateMixingRulesIdealGas.cpp"), 7515, 7590)
+    ig = rd("src/util/mixing_rules/equations_of_state/ideal_gas/EquationOfStateIdealGas.cpp")
+    w56 = rd(SOURCES["ref_weno"].replace("WCNS5-JS-HLLC-HLL", "WCNS56-HLLC-HLL"))
+    s_rho = statement(mr, r"rho\[idx_mixture_density\] \+= Z_rho\[si\]\[idx_partial_densities\]")
+    s_Y = statement(fm, r"Y\[si\]\[idx_mass_fractions\] = Z_rho\[si\]\[idx\]/rho\[idx_density\]")
+    s_u = statement(fm, r"u\[idx_velocity\] = rho_u\[idx\]/rho\[idx_density\]")
+    s_v = statement(fm, r"v\[idx_velocity\] = rho_v\[idx\]/rho\[idx_density\]")
+    s_w = statement(fm, r"w\[idx_velocity\] = rho_w\[idx\]/rho\[idx_density\]")
+    s_e = statement(fm, r"epsilon\[idx_internal_energy\] = E\[idx\]/rho\[idx_density\] -\s*double\(1\)/double\(2\)\*\(u\[idx_velocity\]\*u\[idx_velocity\] \+ v\[idx_velocity\]\*v\[idx_velocity\] \+")
+    s_ood = statement(mi, r"const double one_over_denominator = double\(1\)/\(d_species_gamma\[si\] - double\(1\)\)")
+    s_xi = statement(mi, r"gamma\[idx_mixture_thermo_properties\] \+= Z\[si\]\[idx_volume_fractions\]\*one_over_denominator")
+    s_gm = statement(mi, r"gamma\[idx_mixture_thermo_properties\] = double\(1\)/gamma\[idx_mixture_thermo_properties\] \+ double\(1\)")
+    s_p = statement(ig, r"p\[idx_pressure\] = \(gamma\[idx_thermo_properties\] - double\(1\)\)\*rho\[idx_density\]\*\s*epsilon\[idx_internal_energy\]")
+    s_Gr = statement(ig, r"Gamma\[idx_gruneisen_parameter\] = gamma\[idx_thermo_properties\] - double\(1\)")
+    s_Psi = statement(ig, r"Psi\[idx_partial_pressure_partial_density\] = p\[idx_pressure\]/rho\[idx_density\]")
+    s_c0 = statement(fm, r"c\[idx_sound_speed\] = Gamma\[idx_sound_speed\]\*p\[idx_pressure\]/rho\[idx_density\]")
+    s_c1 = statement(fm, r"c\[idx_sound_speed\] \+= Y\[si\]\[idx_mass_fractions\]\*Psi\[si\]\[idx_sound_speed\]")
+    s_c2 = statement(fm, r"c\[idx_sound_speed\] = sqrt\(c\[idx_sound_speed\]\)")
+    s_za = statement(bu, r"Z_rho_average\[si\]\[idx_face_x\] = double\(1\)/double\(2\)\*\(Z_rho\[si\]\[idx_L\] \+ Z_rho\[si\]\[idx_R\]\)")
+    s_ra = statement(bu, r"rho_average\[idx_face_x\] = double\(1\)/double\(2\)\*\(rho\[idx_density_L\] \+ rho\[idx_density_R\]\)")
+    s_ca = statement(bu, r"c_average\[idx_face_x\] = double\(1\)/double\(2\)\*\(c\[idx_sound_speed_L\] \+ c\[idx_sound_speed_R\]\)")
+    px = line_range(bu, 8800, 8925)       # 3-D, x direction of the projection
+    s_w0 = statement(px, r"W\[0\]\[idx_face\] = V\[d_num_species\]\[idx_vel\] -")
+    s_wsi = statement(px, r"W\[1 \+ si\]\[idx_face\] = V\[si\]\[idx_Z_rho\] - Z_rho_average")
+    s_wv = statement(px, r"W\[d_num_species \+ 1\]\[idx_face\] = V\[d_num_species \+ 1\]\[idx_vel\]")
+    s_ww = statement(px, r"W\[d_num_species \+ 2\]\[idx_face\] = V\[d_num_species \+ 2\]\[idx_vel\]")
+    s_wz = statement(px, r"W\[d_num_species \+ 3 \+ si\]\[idx_face\] = V\[d_num_species \+ 4 \+ si\]\[idx_Z\]")
+    s_wl = statement(px, r"W\[2\*d_num_species \+ 2\]\[idx_face\] = V\[d_num_species\]\[idx_vel\] \+")
+    bx = line_range(bu, 9660, 9765)       # 3-D, x direction of the back-projection
+    s_vsi = statement(bx, r"V\[si\]\[idx_face\] = -double\(1\)/double\(2\)\*Z_rho_average")
+    s_vz = statement(bx, r"V\[d_num_species \+ 4 \+ si\]\[idx_face\] = W\[d_num_species \+ 3 \+ si\]\[idx_face\]")
+    s_vu = statement(bx, r"V\[d_num_species\]\[idx_face\] = double\(1\)/double\(2\)\*W\[0\]\[idx_face\] \+")
+    s_vv = statement(bx, r"V\[d_num_species \+ 1\]\[idx_face\] = W\[d_num_species \+ 1\]\[idx_face\]")
+    s_vw = statement(bx, r"V\[d_num_species \+ 2\]\[idx_face\] = W\[d_num_species \+ 2\]\[idx_face\]")
+    s_vp = statement(bx, r"V\[d_num_species \+ 3\]\[idx_face\] = -double\(1\)/double\(2\)\*rho_average")
+    s_S = statement(w56, r"S\[idx_cell_nghost\] \+= dt\*Q\[ei\]\[idx_cell_wghost\]\*\(")
+    return f"""
+extern "C" void ref_path_points3(const double in[56], double out[32])
+{{
+    const int d_num_species = 2, d_num_eqn = 7;
+    {{
+        const int idx = 0, idx_density = 0, idx_mixture_density = 0, idx_partial_densities = 0, idx_mass_fractions = 0;
+        const int idx_velocity = 0, idx_internal_energy = 0, idx_mixture_thermo_properties = 0, idx_volume_fractions = 0;
+        const int idx_thermo_properties = 0, idx_pressure = 0, idx_gruneisen_parameter = 0, idx_sound_speed = 0;
+        const int idx_partial_pressure_partial_density = 0;
+        double zr0[1] = {{in[0]}}, zr1[1] = {{in[1]}}, z0[1] = {{in[6]}}, z1[1] = {{in[7]}};
+        double* Z_rho[2] = {{zr0, zr1}};
+        double* Z[2] = {{z0, z1}};
+        const double rho_u[1] = {{in[2]}}, rho_v[1] = {{in[3]}}, rho_w[1] = {{in[4]}}, E[1] = {{in[5]}};
+        const double d_species_gamma[2] = {{in[8], in[9]}};
+        double rho[1] = {{0.0}}, y0[1], y1[1], u[1], v[1], w[1], epsilon[1], gamma[1] = {{0.0}}, p[1], Gamma[1], c[1];
+        double psi0[1], psi1[1];
+        double* Y[2] = {{y0, y1}};
+        double* Psi[2] = {{psi0, psi1}};
+        for (int si = 0; si < d_num_species; si++) {{ {s_rho} }}
+        for (int si = 0; si < d_num_species; si++) {{ {s_Y} }}
+        {s_u}
+        {s_v}
+        {s_w}
+        {s_e}
+        for (int si = 0; si < d_num_species; si++) {{
+            {s_ood}
+            {s_xi}
+        }}
+        {s_gm}
+        {s_p}
+        {s_Gr}
+        for (int si = 0; si < d_num_species; si++) {{
+            double* Psi_si = Psi[si];
+            double* Psi = Psi_si;      /* the reference fills one species' array per call of the single-species EOS */
+            {s_Psi}
+        }}
+        {s_c0}
+        for (int si = 0; si < d_num_species; si++) {{ {s_c1} }}
+        {s_c2}
+        out[0] = rho[0]; out[1] = y0[0]; out[2] = y1[0]; out[3] = u[0]; out[4] = v[0]; out[5] = w[0]; out[6] = epsilon[0];
+        out[7] = gamma[0]; out[8] = p[0]; out[9] = c[0];
+    }}
+    double zra0[1], zra1[1], rho_average[1], c_average[1];
+    double* Z_rho_average[2] = {{zra0, zra1}};
+    {{
+        const int idx_face_x = 0, idx_L = 0, idx_R = 1, idx_density_L = 0, idx_density_R = 1;
+        const int idx_sound_speed_L = 0, idx_sound_speed_R = 1;
+        const double zr0[2] = {{in[10], in[11]}}, zr1[2] = {{in[12], in[13]}}, rho[2] = {{in[14], in[15]}}, c[2] = {{in[16], in[17]}};
+        const double* Z_rho[2] = {{zr0, zr1}};
+        for (int si = 0; si < d_num_species; si++) {{ {s_za} }}
+        {s_ra}
+        {s_ca}
+        out[10] = zra0[0]; out[11] = zra1[0]; out[12] = rho_average[0]; out[13] = c_average[0];
+    }}
+    {{
+        const int idx_face = 0, idx_Z_rho = 0, idx_vel = 0, idx_p = 0, idx_Z = 0;
+        double v_[7][1], w_[7][1];
+        double *V[7], *W[7];
+        for (int e = 0; e < 7; e++) {{ v_[e][0] = in[18 + e]; V[e] = v_[e]; W[e] = w_[e]; }}
+        for (int si = 0; si < d_num_species; si++) {{ {s_wsi} }}
+        for (int si = 0; si < d_num_species - 1; si++) {{ {s_wz} }}
+        {s_w0}
+        {s_wv}
+        {s_ww}
+        {s_wl}
+        /* reference order of the characteristic variables: u-c/(rho c), partial densities, tangential velocities,
+           volume fractions, u+c/(rho c); ours swaps nothing: out[14..20] = W[0..6] */
+        for (int e = 0; e < 7; e++) out[14 + e] = W[e][0];
+    }}
+    {{
+        const int idx_face = 0;
+        double v_[7][1], w_[7][1];
+        double *V[7], *W[7];
+        for (int e = 0; e < 7; e++) {{ w_[e][0] = in[25 + e]; V[e] = v_[e]; W[e] = w_[e]; }}
+        for (int si = 0; si < d_num_species; si++) {{ {s_vsi} }}
+        for (int si = 0; si < d_num_species - 1; si++) {{ {s_vz} }}
+        {s_vu}
+        {s_vv}
+        {s_vw}
+        {s_vp}
+        for (int e = 0; e < 7; e++) out[21 + e] = V[e][0];
+    }}
+    {{
+        const int ei = 0, idx_cell_nghost = 0, idx_cell_wghost = 0;
+        const int idx_midpoint_x_R = 0, idx_midpoint_x_L = 1, idx_midpoint_x_RR = 2, idx_midpoint_x_LL = 3;
+        const int idx_cell_wghost_x_R = 0, idx_cell_wghost_x_L = 1;
+        const int idx_midpoint_y_T = 0, idx_midpoint_y_B = 1, idx_midpoint_y_TT = 2, idx_midpoint_y_BB = 3;
+        const int idx_cell_wghost_y_T = 0, idx_cell_wghost_y_B = 1;
+        const int idx_midpoint_z_F = 0, idx_midpoint_z_B = 1, idx_midpoint_z_FF = 2, idx_midpoint_z_BB = 3;
+        const int idx_cell_wghost_z_F = 0, idx_cell_wghost_z_B = 1;
+        double S[1] = {{in[32]}};
+        const double dt = in[33];
+        double q0[1] = {{in[34]}};
+        double* Q[1] = {{q0}};
+        const double u_midpoint_x[4] = {{in[35], in[36], in[37], in[38]}}, u[2] = {{in[39], in[40]}};
+        const double v_midpoint_y[4] = {{in[41], in[42], in[43], in[44]}}, v[2] = {{in[45], in[46]}};
+        const double w_midpoint_z[4] = {{in[47], in[48], in[49], in[50]}}, w[2] = {{in[51], in[52]}};
+        const double dx[3] = {{in[53], in[54], in[55]}};
+        {s_S}
+        out[28] = S[0]; out[29] = 0.0; out[30] = 0.0; out[31] = 0.0;
+    }}
+}}
+"""
+
+
 def static_inline_functions(text: str) -> str:
     """Return the concatenation of every `static inline ...` function definition in text."""
     out = []
@@ -352,6 +512,7 @@ def main() -> int:
     parts.append(EOS_WRAPPER)
     parts.append(path_statements())
     parts.append(path_statements2())
+    parts.append(path_statements3())
     gen = os.path.join(OUT, "_generated_ref_kernels.cpp")
     with open(gen, "w") as fh:
         fh.write("\n".join(parts))

@@ -111,6 +111,110 @@ static inline double rk_beta_term_3d(double beta, double FxR, double FxL, double
     return beta * (-(FxR - FxL) / dx0 - (FyT - FyB) / dx1 - (FzF - FzB) / dx2 + S);
 }
 
+/* five-eqn helpers (each is the point formula of one reference statement; pinned through orc_path_points3).
+ * EquationOfStateMixingRulesIdealGas.cpp:7544, 7565, 7586 (xi accumulation, gamma_m) */
+static inline double fe_xi_accumulate(double xi, double Z, double gamma_species)
+{
+    const double one_over_denominator = 1.0 / (gamma_species - 1.0);
+    return xi + Z * one_over_denominator;
+}
+static inline double fe_gamma_from_xi(double xi) { return 1.0 / xi + 1.0; }
+/* EquationOfStateIdealGas.cpp:5756 */
+static inline double fe_pressure(double gamma_m, double rho, double epsilon) { return (gamma_m - 1.0) * rho * epsilon; }
+/* EquationOfStateIdealGas.cpp:8157 (Gruneisen), :8308 (Psi), FlowModelFiveEqnAllaire.cpp:4789, 4818 (c^2 terms) */
+static inline double fe_gruneisen(double gamma_m) { return gamma_m - 1.0; }
+static inline double fe_psi(double p, double rho) { return p / rho; }
+static inline double fe_c2_first(double Gamma, double p, double rho) { return Gamma * p / rho; }
+static inline double fe_c2_accumulate(double cc, double Y, double Psi) { return cc + Y * Psi; }
+/* FlowModelBasicUtilitiesFiveEqnAllaire.cpp:8848-8850, 8913-8914, 8920-8921 (projection, x; y/z are permutations) */
+static inline double fe_char_minus(double rho_avg, double c_avg, double un, double p)
+{
+    return un - 1.0 / (rho_avg * c_avg) * p;
+}
+static inline double fe_char_plus(double rho_avg, double c_avg, double un, double p)
+{
+    return un + 1.0 / (rho_avg * c_avg) * p;
+}
+static inline double fe_char_partial_density(double Zrho_avg, double rho_avg, double c_avg, double Zrho, double p)
+{
+    return Zrho - Zrho_avg / (rho_avg * c_avg * c_avg) * p;
+}
+/* :9700-9703, 9751-9752, 9758-9760 (back-projection) */
+static inline double fe_back_partial_density(double Zrho_avg, double c_avg, double W0, double Wsi, double Wlast)
+{
+    return -1.0 / 2.0 * Zrho_avg / c_avg * W0 + Wsi + 1.0 / 2.0 * Zrho_avg / c_avg * Wlast;
+}
+static inline double fe_back_normal_velocity(double W0, double Wlast) { return 1.0 / 2.0 * W0 + 1.0 / 2.0 * Wlast; }
+static inline double fe_back_pressure(double rho_avg, double c_avg, double W0, double Wlast)
+{
+    return -1.0 / 2.0 * rho_avg * c_avg * W0 + 1.0 / 2.0 * rho_avg * c_avg * Wlast;
+}
+/* ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:2623-2641: one direction's term of the advective source */
+static inline double adv_source_term(double um_R, double um_L, double u_R, double u_L, double um_RR, double um_LL, double dx)
+{
+    return (3.0 / 2.0 * (um_R - um_L) - 3.0 / 10.0 * (u_R - u_L) + 1.0 / 30.0 * (um_RR - um_LL)) / dx;
+}
+
+void orc_path_points3(const double in[56], double out[32])
+{
+    /* two species, 3-D, x direction.
+     * in: Zrho0 Zrho1 rho_u rho_v rho_w E Z0 Z1 gamma0 gamma1 | Zrho0_L Zrho0_R Zrho1_L Zrho1_R rho_L rho_R c_L c_R |
+     *     V0..V6 = (Zrho0, Zrho1, u, v, w, p, Z0) of a stencil cell | Wc0..Wc6 |
+     *     S dt Q | um_R um_L um_RR um_LL u_R u_L (x) | same (y) | same (z) | dx0 dx1 dx2 */
+    double rho = 0.0;
+    rho += in[0];
+    rho += in[1];
+    out[0] = rho;
+    out[1] = in[0] / rho;
+    out[2] = in[1] / rho;
+    out[3] = in[2] / rho;
+    out[4] = in[3] / rho;
+    out[5] = in[4] / rho;
+    out[6] = internal_energy_3d(in[5], rho, out[3], out[4], out[5]);
+    double xi = 0.0;
+    xi = fe_xi_accumulate(xi, in[6], in[8]);
+    xi = fe_xi_accumulate(xi, in[7], in[9]);
+    const double gamma_m = fe_gamma_from_xi(xi);
+    out[7] = gamma_m;
+    const double p = fe_pressure(gamma_m, rho, out[6]);
+    out[8] = p;
+    double cc = fe_c2_first(fe_gruneisen(gamma_m), p, rho);
+    cc = fe_c2_accumulate(cc, out[1], fe_psi(p, rho));
+    cc = fe_c2_accumulate(cc, out[2], fe_psi(p, rho));
+    out[9] = sqrt(cc);
+    const double Zrho_avg[2] = {face_average(in[10], in[11]), face_average(in[12], in[13])};
+    const double rho_avg = face_average(in[14], in[15]), c_avg = face_average(in[16], in[17]);
+    out[10] = Zrho_avg[0];
+    out[11] = Zrho_avg[1];
+    out[12] = rho_avg;
+    out[13] = c_avg;
+    const double* V = in + 18;
+    out[14] = fe_char_minus(rho_avg, c_avg, V[2], V[5]);
+    out[15] = fe_char_partial_density(Zrho_avg[0], rho_avg, c_avg, V[0], V[5]);
+    out[16] = fe_char_partial_density(Zrho_avg[1], rho_avg, c_avg, V[1], V[5]);
+    out[17] = V[3];
+    out[18] = V[4];
+    out[19] = V[6];
+    out[20] = fe_char_plus(rho_avg, c_avg, V[2], V[5]);
+    const double* Wc = in + 25;
+    out[21] = fe_back_partial_density(Zrho_avg[0], c_avg, Wc[0], Wc[1], Wc[6]);
+    out[22] = fe_back_partial_density(Zrho_avg[1], c_avg, Wc[0], Wc[2], Wc[6]);
+    out[23] = fe_back_normal_velocity(Wc[0], Wc[6]);
+    out[24] = Wc[3];
+    out[25] = Wc[4];
+    out[26] = fe_back_pressure(rho_avg, c_avg, Wc[0], Wc[6]);
+    out[27] = Wc[5];
+    double S = in[32];
+    double acc = adv_source_term(in[35], in[36], in[39], in[40], in[37], in[38], in[53]);
+    acc = acc + adv_source_term(in[41], in[42], in[45], in[46], in[43], in[44], in[54]);
+    acc = acc + adv_source_term(in[47], in[48], in[51], in[52], in[49], in[50], in[55]);
+    S += in[33] * in[34] * acc;
+    out[28] = S;
+    out[29] = 0.0;
+    out[30] = 0.0;
+    out[31] = 0.0;
+}
+
 void orc_path_points2(const double in[32], double out[20])
 {
     /* in: rho, rho_u, rho_v, rho_w, E | rho_L, rho_R, c_L, c_R | V0..V4 of a stencil cell | Wc0..Wc4 |
@@ -604,15 +708,11 @@ static void cell_stage(const geom_t* q, const double* gam, const double* const* 
             }
             const double epsilon = Q[ns + dim][x] / rho - 1.0 / 2.0 * ke;
             double xi = 0.0;
-            for (int si = 0; si < ns; si++) {
-                const double one_over_denominator = 1.0 / (gam[si] - 1.0);
-                xi += Q[ns + dim + 1 + si][x] * one_over_denominator;
-            }
-            const double gamma_m = 1.0 / xi + 1.0;
-            p[x] = (gamma_m - 1.0) * rho * epsilon;
-            const double Gamma = gamma_m - 1.0;
-            double cc = Gamma * p[x] / rho;
-            for (int si = 0; si < ns; si++) cc += Y[si] * (p[x] / rho);
+            for (int si = 0; si < ns; si++) xi = fe_xi_accumulate(xi, Q[ns + dim + 1 + si][x], gam[si]);
+            const double gamma_m = fe_gamma_from_xi(xi);
+            p[x] = fe_pressure(gamma_m, rho, epsilon);
+            double cc = fe_c2_first(fe_gruneisen(gamma_m), p[x], rho);
+            for (int si = 0; si < ns; si++) cc = fe_c2_accumulate(cc, Y[si], fe_psi(p[x], rho));
             c[x] = sqrt(cc);
         }
     }
@@ -770,7 +870,7 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
         {
             const long xR = cidx(q, i, j, k), xL = xR - st, s = SIDX(i, j, k);
             if (has_adv)
-                for (int si = 0; si < ns; si++) Zrho_avg[si][s] = 1.0 / 2.0 * (Q[si][xL] + Q[si][xR]);
+                for (int si = 0; si < ns; si++) Zrho_avg[si][s] = face_average(Q[si][xL], Q[si][xR]);
             rho_avg[s] = face_average(rho_cell[xL], rho_cell[xR]);
             c_avg[s] = face_average(c[xL], c[xR]);
         }
@@ -794,14 +894,14 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
                         if (a != dir) W[m][w++][s] = V[1 + a][x];
                     W[m][dim + 1][s] = char_acoustic_plus(rho_avg[s], c_avg[s], V[1 + dir][x], V[dim + 1][x]);
                 } else {
-                    W[m][0][s] = V[iv + dir][x] - 1.0 / (rho_avg[s] * c_avg[s]) * V[ip][x];
+                    W[m][0][s] = fe_char_minus(rho_avg[s], c_avg[s], V[iv + dir][x], V[ip][x]);
                     for (int si = 0; si < ns; si++)
-                        W[m][1 + si][s] = V[si][x] - Zrho_avg[si][s] / (rho_avg[s] * c_avg[s] * c_avg[s]) * V[ip][x];
+                        W[m][1 + si][s] = fe_char_partial_density(Zrho_avg[si][s], rho_avg[s], c_avg[s], V[si][x], V[ip][x]);
                     int w = ns + 1;
                     for (int a = 0; a < dim; a++)
                         if (a != dir) W[m][w++][s] = V[iv + a][x];
                     for (int si = 0; si < ns - 1; si++) W[m][ns + dim + si][s] = V[ip + 1 + si][x];
-                    W[m][neq - 1][s] = V[iv + dir][x] + 1.0 / (rho_avg[s] * c_avg[s]) * V[ip][x];
+                    W[m][neq - 1][s] = fe_char_plus(rho_avg[s], c_avg[s], V[iv + dir][x], V[ip][x]);
                 }
             }
         }
@@ -850,16 +950,15 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
                     Vs[dim + 1][s] = back_pressure(Wc[0][s], Wc[dim + 1][s]);
                 } else {
                     for (int si = 0; si < ns; si++)
-                        Vs[si][s] = -1.0 / 2.0 * Zrho_avg[si][s] / c_avg[s] * Wc[0][s] + Wc[si + 1][s] +
-                                    1.0 / 2.0 * Zrho_avg[si][s] / c_avg[s] * Wc[neq - 1][s];
+                        Vs[si][s] = fe_back_partial_density(Zrho_avg[si][s], c_avg[s], Wc[0][s], Wc[si + 1][s], Wc[neq - 1][s]);
                     int w = ns + 1;
                     for (int a = 0; a < dim; a++) {
                         if (a == dir)
-                            Vs[iv + a][s] = 1.0 / 2.0 * Wc[0][s] + 1.0 / 2.0 * Wc[neq - 1][s];
+                            Vs[iv + a][s] = fe_back_normal_velocity(Wc[0][s], Wc[neq - 1][s]);
                         else
                             Vs[iv + a][s] = Wc[w++][s];
                     }
-                    Vs[ip][s] = -1.0 / 2.0 * rho_avg[s] * c_avg[s] * Wc[0][s] + 1.0 / 2.0 * rho_avg[s] * c_avg[s] * Wc[neq - 1][s];
+                    Vs[ip][s] = fe_back_pressure(rho_avg[s], c_avg[s], Wc[0][s], Wc[neq - 1][s]);
                     for (int si = 0; si < ns - 1; si++) Vs[ip + 1 + si][s] = Wc[ns + dim + si][s];
                 }
             }
@@ -1034,9 +1133,8 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
                             const long sst = dir == 0 ? 1 : (dir == 1 ? sd[0] : sd[0] * sd[1]);
                             const double* um = vel_midpoint[dir];
                             /* faces: s = face at the low side of the cell ("L"), s+sst = "R" */
-                            const double term = (3.0 / 2.0 * (um[s + sst] - um[s]) -
-                                                 3.0 / 10.0 * (vel[dir][x + q->cs[dir]] - vel[dir][x - q->cs[dir]]) +
-                                                 1.0 / 30.0 * (um[s + 2 * sst] - um[s - sst])) / d->dx[dir];
+                            const double term = adv_source_term(um[s + sst], um[s], vel[dir][x + q->cs[dir]], vel[dir][x - q->cs[dir]],
+                                                                um[s + 2 * sst], um[s - sst], d->dx[dir]);
                             acc = (dir == 0) ? term : acc + term;
                         }
                         Se[xs] += dt * Q[e][x] * acc;

@@ -105,6 +105,9 @@ int orc_spectral_radii_and_dt(const orc_desc* d, const double* const* Q, int inc
 void orc_path_points(const double in[16], double out[5]);
 /* velocity, internal energy, face averages, characteristic projection and its inverse (single-species, 3-D, x), RK update */
 void orc_path_points2(const double in[32], double out[20]);
+/* five-eqn (two species, 3-D, x): mixture density, mass fractions, velocity, internal energy, mixture gamma, pressure,
+ * sound speed, face averages, characteristic projection and its inverse, advective source */
+void orc_path_points3(const double in[56], double out[32]);
 void orc_constants(double out[7]); /* eps, sensor threshold, Y lo/up, Z lo/up, ghost width */
 void orc_eos_point(double gamma, double rho, double epsilon, double* p, double* c, double* eps_back);
 void orc_weno5js_point(const double U[6], int p, double* U_minus, double* U_plus);

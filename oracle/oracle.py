@@ -234,6 +234,14 @@ def path_points2(vals):
     return list(out)
 
 
+def path_points3(vals):
+    """orc_path_points3: five-eqn derived data, projection / back-projection, advective source from 56 inputs."""
+    a = (C.c_double * 56)(*[float(x) for x in vals])
+    out = (C.c_double * 32)()
+    lib().orc_path_points3(a, out)
+    return list(out)
+
+
 def constants():
     out = (C.c_double * 7)()
     lib().orc_constants(out)

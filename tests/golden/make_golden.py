@@ -16,6 +16,13 @@ Contents (all float64, seeded):
                        2824-2826, 3049-3051), face averages, characteristic projection and back-projection
                        (FlowModelBasicUtilitiesSingleSpecies.cpp:5000-5001, 6324-6329, 7373-7379), RK alpha/beta update
                        (Euler.cpp:1479, 1544-1548), again the reference's own statements compiled verbatim
+  path_points3_in (n, 56), path_points3_out (n, 32): five-eqn Allaire, two species, 3-D, x: mixture density, mass
+                       fractions, velocity, internal energy, mixture gamma, pressure, sound speed, face averages,
+                       projection / back-projection, advective source (EquationOfStateMixingRules.cpp:871,
+                       FlowModelFiveEqnAllaire.cpp:3965, 4188-4190, 4428-4430, 4700-4853,
+                       EquationOfStateMixingRulesIdealGas.cpp:7544-7586, EquationOfStateIdealGas.cpp:5756, 8157, 8308,
+                       FlowModelBasicUtilitiesFiveEqnAllaire.cpp:7952-7996, 8848-8921, 9700-9760,
+                       ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:2623-2641), statements compiled verbatim
   ref_constants (7,): HAMERS_EPSILON, sensor threshold, Y bounds lo/up, Z bounds lo/up, ghost width, parsed from the source
   rk_alpha, rk_beta, rk_gamma (3, 3): the reference's default SSPRK(3,3) table (RungeKuttaLevelIntegrator.cpp:3894-3929)
   eos_in (n, 3) = (gamma, rho, epsilon), eos_out (n, 3) = (p, c, epsilon from p): EquationOfStateIdealGas scalar members
@@ -184,6 +191,20 @@ def main():
         lib.ref_path_points2((C.c_double * 32)(*v), o)
         p2_out.append(list(o))
     out["path_points2_in"], out["path_points2_out"] = p2_in, np.array(p2_out)
+    # third group, five-eqn with two species (oracle/build_ref.py: path_statements3); own generator
+    rng_p3 = np.random.default_rng(654)
+    p3_in = rng_p3.standard_normal((400, 56)) * 10.0 ** rng_p3.uniform(-1, 1, (400, 1))
+    pos3 = [0, 1, 5, 6, 7, 10, 11, 12, 13, 14, 15, 16, 17, 33, 53, 54, 55]     # partial densities, E, Z, averages' inputs, dt, dx
+    p3_in[:, pos3] = np.abs(p3_in[:, pos3]) + 1.0e-3
+    p3_in[:, 8:10] = rng_p3.uniform(1.1, 1.7, (400, 2))                      # species gammas
+    p3_in[:, 5] += 0.5 * (p3_in[:, 2:5] ** 2).sum(axis=1) / p3_in[:, 0:2].sum(axis=1)   # positive internal energy
+    p3_out = []
+    for v in p3_in:
+        o = (C.c_double * 32)()
+        lib.ref_path_points3((C.c_double * 56)(*v), o)
+        p3_out.append(list(o))
+    out["path_points3_in"], out["path_points3_out"] = p3_in, np.array(p3_out)
+    assert np.isfinite(out["path_points3_out"]).all()
     # ideal-gas EOS scalars (EquationOfStateIdealGas.cpp:29-45, 561-577, 1093-1108); own generator: the arrays above keep
     # their values
     rng_eos = np.random.default_rng(77)
