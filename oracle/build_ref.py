@@ -382,6 +382,80 @@ extern "C" void ref_path_points3(const double in[56], double out[32])
 """
 
 
+def path_statements4() -> str:
+    """Fourth group: the thermodynamic state the five-eqn Riemann solver rebuilds from one interpolated side
+    (FlowModelRiemannSolverFiveEqnAllaireHLLC.cpp:5709-5941: rho, Y, c) with the mixture gamma from the ns-1 interpolated
+    volume fractions (EquationOfStateMixingRulesIdealGas.cpp:7770-7829, 3-D), Gruneisen parameter, Psi and
+    epsilon(p) (EquationOfStateIdealGas.cpp:8157, 8308, 6414)."""
+    def rd(rel):
+        with open(os.path.join(REF, rel)) as fh:
+            return fh.read()
+    rs = line_range(rd("src/flow/flow_models/five-eqn_Allaire/Riemann_solvers/FlowModelRiemannSolverFiveEqnAllaireHLLC.cpp"), 5640, 5990)
+    mi = line_range(rd("src/util/mixing_rules/equations_of_state/ideal_gas/EquationOfStateMixingRulesIdealGas.cpp"), 7736, 7835)
+    ig = rd("src/util/mixing_rules/equations_of_state/ideal_gas/EquationOfStateIdealGas.cpp")
+    s_r0 = statement(rs, r"rho_x_L\[idx\] = double\(0\)")
+    s_r1 = statement(rs, r"rho_x_L\[idx\] \+= V_x_L\[si\]\[idx\]")
+    s_Y = statement(rs, r"Y_x_L\[si\]\[idx\] = V_x_L\[si\]\[idx\]/rho_x_L\[idx\]")
+    s_Z = statement(rs, r"Z_x_L\[si\]\[idx\] = V_x_L\[d_num_species \+ 4 \+ si\]\[idx\]")
+    s_ood = statement(mi, r"const double one_over_denominator = double\(1\)/\(d_species_gamma\[si\] - double\(1\)\)")
+    s_xi = statement(mi, r"gamma\[idx_mixture_thermo_properties\] \+= Z\[si\]\[idx_volume_fractions\]\*one_over_denominator")
+    s_zl = statement(mi, r"Z_last\[idx_volume_fractions_last\] -= Z\[si\]\[idx_volume_fractions\]")
+    s_xl = statement(mi, r"gamma\[idx_mixture_thermo_properties\] \+= Z_last\[idx_volume_fractions_last\]/")
+    s_gm = statement(mi, r"gamma\[idx_mixture_thermo_properties\] = double\(1\)/gamma\[idx_mixture_thermo_properties\] \+ double\(1\)")
+    s_Gr = statement(ig, r"Gamma\[idx_gruneisen_parameter\] = gamma\[idx_thermo_properties\] - double\(1\)")
+    s_Psi = statement(ig, r"Psi\[idx_partial_pressure_partial_density\] = p\[idx_pressure\]/rho\[idx_density\]")
+    s_eps = statement(ig, r"epsilon\[idx_internal_energy\] = p\[idx_pressure\]/\(\(gamma\[idx_thermo_properties\] - double\(1\)\)\*")
+    s_c0 = statement(rs, r"c_x_L\[idx\] = Gamma_x_L\[idx\]\*V_x_L\[d_num_species \+ 3\]\[idx\]/rho_x_L\[idx\]")
+    s_c1 = statement(rs, r"c_x_L\[idx\] \+= Y_x_L\[si\]\[idx\]\*Psi_x_L\[si\]\[idx\]")
+    s_c2 = statement(rs, r"c_x_L\[idx\] = sqrt\(c_x_L\[idx\]\)")
+    return f"""
+extern "C" void ref_path_points4(const double in[12], double out[4])
+{{
+    const int d_num_species = 2;
+    const int idx = 0, idx_mixture_thermo_properties = 0, idx_volume_fractions = 0, idx_volume_fractions_last = 0;
+    const int idx_thermo_properties = 0, idx_gruneisen_parameter = 0, idx_partial_pressure_partial_density = 0;
+    const int idx_pressure = 0, idx_density = 0, idx_internal_energy = 0;
+    double v_[7][1];
+    double* V_x_L[7];
+    for (int e = 0; e < 7; e++) {{ v_[e][0] = in[e]; V_x_L[e] = v_[e]; }}
+    const std::vector<double> d_species_gamma = {{in[7], in[8]}};
+    double rho_x_L[1], y0[1], y1[1], z0[1], c_x_L[1], Gamma_x_L[1], psi0[1], psi1[1], epsilon[1];
+    double* Y_x_L[2] = {{y0, y1}};
+    double* Z_x_L[1] = {{z0}};
+    double* Psi_x_L[2] = {{psi0, psi1}};
+    {s_r0}
+    for (int si = 0; si < d_num_species; si++) {{ {s_r1} }}
+    for (int si = 0; si < d_num_species; si++) {{ {s_Y} }}
+    for (int si = 0; si < d_num_species - 1; si++) {{ {s_Z} }}
+    {{
+        /* EquationOfStateMixingRulesIdealGas: gamma starts at 0 and Z_last at 1 (fillAll), then */
+        double gamma[1] = {{0.0}}, Z_last[1] = {{1.0}};
+        double** Z = Z_x_L;
+        for (int si = 0; si < d_num_species - 1; si++) {{
+            {s_ood}
+            {s_xi}
+            {s_zl}
+        }}
+        {s_xl}
+        {s_gm}
+        double* Gamma = Gamma_x_L;
+        {s_Gr}
+        const double* p = V_x_L[d_num_species + 3];
+        const double* rho = rho_x_L;
+        for (int si = 0; si < d_num_species; si++) {{
+            double* Psi = Psi_x_L[si];
+            {s_Psi}
+        }}
+        {s_eps}
+    }}
+    {s_c0}
+    for (int si = 0; si < d_num_species; si++) {{ {s_c1} }}
+    {s_c2}
+    out[0] = rho_x_L[0]; out[1] = c_x_L[0]; out[2] = epsilon[0]; out[3] = 0.0;
+}}
+"""
+
+
 def static_inline_functions(text: str) -> str:
     """Return the concatenation of every `static inline ...` function definition in text."""
     out = []
@@ -513,6 +587,7 @@ def main() -> int:
     parts.append(path_statements())
     parts.append(path_statements2())
     parts.append(path_statements3())
+    parts.append(path_statements4())
     gen = os.path.join(OUT, "_generated_ref_kernels.cpp")
     with open(gen, "w") as fh:
         fh.write("\n".join(parts))

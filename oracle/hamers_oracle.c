@@ -119,6 +119,9 @@ static inline double fe_xi_accumulate(double xi, double Z, double gamma_species)
     return xi + Z * one_over_denominator;
 }
 static inline double fe_gamma_from_xi(double xi) { return 1.0 / xi + 1.0; }
+/* EquationOfStateMixingRulesIdealGas.cpp:7827-7828 (last species from Z_last = 1 - sum Z_i), EquationOfStateIdealGas.cpp:6414 */
+static inline double fe_xi_last(double xi, double Z_last, double gamma_last) { return xi + Z_last / (gamma_last - 1.0); }
+static inline double fe_internal_energy_from_p(double gamma_m, double rho, double p) { return p / ((gamma_m - 1.0) * rho); }
 /* EquationOfStateIdealGas.cpp:5756 */
 static inline double fe_pressure(double gamma_m, double rho, double epsilon) { return (gamma_m - 1.0) * rho * epsilon; }
 /* EquationOfStateIdealGas.cpp:8157 (Gruneisen), :8308 (Psi), FlowModelFiveEqnAllaire.cpp:4789, 4818 (c^2 terms) */
@@ -213,6 +216,17 @@ void orc_path_points3(const double in[56], double out[32])
     out[29] = 0.0;
     out[30] = 0.0;
     out[31] = 0.0;
+}
+
+static inline void side_thermo(int model, int dim, int ns, const double* gamma, const double* V,
+                               double* rho_o, double* c_o, double* eps_o);
+
+void orc_path_points4(const double in[12], double out[4])
+{
+    /* five-eqn, two species, 3-D: in = V (Zrho0, Zrho1, u, v, w, p, Z0) of one interpolated side, gamma0, gamma1;
+     * out = rho, c, epsilon as fed to the Riemann point kernels */
+    side_thermo(ORC_FIVE_EQN_ALLAIRE, 3, 2, in + 7, in, &out[0], &out[1], &out[2]);
+    out[3] = 0.0;
 }
 
 void orc_path_points2(const double in[32], double out[20])
@@ -440,7 +454,8 @@ void orc_weno6ld_point(const double U[6], int p, int q, double C, double alpha_t
  *   mixture gamma from the ns-1 interpolated volume fractions
  *   (EquationOfStateMixingRulesIdealGas.cpp:7599-7832, Z_last = 1 - sum Z_i, fill :5377-5576),
  *   Gamma = gamma-1 (EquationOfStateIdealGas.cpp:8157), Psi_i = p/rho
- *   (EquationOfStateMixingRulesIdealGas.cpp:6736), epsilon = p/((gamma-1)*rho) (:6414). */
+ *   (EquationOfStateMixingRulesIdealGas.cpp:6736), epsilon = p/((gamma-1)*rho) (EquationOfStateIdealGas.cpp:6414).
+ *   Pinned through orc_path_points4. */
 static inline void side_thermo(int model, int dim, int ns, const double* gamma, const double* V,
                                double* rho_o, double* c_o, double* eps_o)
 {
@@ -458,18 +473,16 @@ static inline void side_thermo(int model, int dim, int ns, const double* gamma, 
         for (int si = 0; si < ns; si++) Y[si] = V[si] / rho;
         double xi = 0.0, Z_last = 1.0;
         for (int si = 0; si < ns - 1; si++) {
-            const double one_over_denominator = 1.0 / (gamma[si] - 1.0);
-            xi += V[ns + dim + 1 + si] * one_over_denominator;
+            xi = fe_xi_accumulate(xi, V[ns + dim + 1 + si], gamma[si]);
             Z_last -= V[ns + dim + 1 + si];
         }
-        xi += Z_last / (gamma[ns - 1] - 1.0);
-        const double gamma_m = 1.0 / xi + 1.0;
-        const double Gamma = gamma_m - 1.0;
-        double c = Gamma * p / rho;
-        for (int si = 0; si < ns; si++) c += Y[si] * (p / rho);
+        xi = fe_xi_last(xi, Z_last, gamma[ns - 1]);
+        const double gamma_m = fe_gamma_from_xi(xi);
+        double c = fe_c2_first(fe_gruneisen(gamma_m), p, rho);
+        for (int si = 0; si < ns; si++) c = fe_c2_accumulate(c, Y[si], fe_psi(p, rho));
         *rho_o = rho;
         *c_o = sqrt(c);
-        *eps_o = p / ((gamma_m - 1.0) * rho);
+        *eps_o = fe_internal_energy_from_p(gamma_m, rho, p);
     }
 }
 

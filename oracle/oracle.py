@@ -242,6 +242,14 @@ def path_points3(vals):
     return list(out)
 
 
+def path_points4(vals):
+    """orc_path_points4: five-eqn (rho, c, epsilon, 0) of one interpolated side from V[7] and two species gammas."""
+    a = (C.c_double * 12)(*([float(x) for x in vals] + [0.0] * (12 - len(vals))))
+    out = (C.c_double * 4)()
+    lib().orc_path_points4(a, out)
+    return list(out)
+
+
 def constants():
     out = (C.c_double * 7)()
     lib().orc_constants(out)

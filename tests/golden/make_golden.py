@@ -23,6 +23,10 @@ Contents (all float64, seeded):
                        EquationOfStateMixingRulesIdealGas.cpp:7544-7586, EquationOfStateIdealGas.cpp:5756, 8157, 8308,
                        FlowModelBasicUtilitiesFiveEqnAllaire.cpp:7952-7996, 8848-8921, 9700-9760,
                        ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:2623-2641), statements compiled verbatim
+  path_points4_in (n, 12), path_points4_out (n, 4): (rho, c, epsilon) the five-eqn Riemann solver rebuilds from one
+                       interpolated side (FlowModelRiemannSolverFiveEqnAllaireHLLC.cpp:5709-5941, mixture gamma from the
+                       ns-1 volume fractions EquationOfStateMixingRulesIdealGas.cpp:7770-7829, EquationOfStateIdealGas.cpp:
+                       8157, 8308, 6414), statements compiled verbatim
   ref_constants (7,): HAMERS_EPSILON, sensor threshold, Y bounds lo/up, Z bounds lo/up, ghost width, parsed from the source
   rk_alpha, rk_beta, rk_gamma (3, 3): the reference's default SSPRK(3,3) table (RungeKuttaLevelIntegrator.cpp:3894-3929)
   eos_in (n, 3) = (gamma, rho, epsilon), eos_out (n, 3) = (p, c, epsilon from p): EquationOfStateIdealGas scalar members
@@ -205,6 +209,21 @@ def main():
         p3_out.append(list(o))
     out["path_points3_in"], out["path_points3_out"] = p3_in, np.array(p3_out)
     assert np.isfinite(out["path_points3_out"]).all()
+    # fourth group: five-eqn thermodynamic state of one interpolated side (oracle/build_ref.py: path_statements4)
+    rng_p4 = np.random.default_rng(987)
+    p4_in = np.zeros((400, 12))
+    p4_in[:, 0:2] = 10.0 ** rng_p4.uniform(-3, 1, (400, 2))            # partial densities
+    p4_in[:, 2:5] = rng_p4.standard_normal((400, 3))                   # velocity
+    p4_in[:, 5] = 10.0 ** rng_p4.uniform(-2, 2, 400)                   # pressure
+    p4_in[:, 6] = rng_p4.uniform(-0.001, 1.001, 400)                   # interpolated volume fraction, within the bounds
+    p4_in[:, 7:9] = rng_p4.uniform(1.1, 1.7, (400, 2))                 # species gammas
+    p4_out = []
+    for v in p4_in:
+        o = (C.c_double * 4)()
+        lib.ref_path_points4((C.c_double * 12)(*v), o)
+        p4_out.append(list(o))
+    out["path_points4_in"], out["path_points4_out"] = p4_in, np.array(p4_out)
+    assert np.isfinite(out["path_points4_out"]).all()
     # ideal-gas EOS scalars (EquationOfStateIdealGas.cpp:29-45, 561-577, 1093-1108); own generator: the arrays above keep
     # their values
     rng_eos = np.random.default_rng(77)
