@@ -414,8 +414,10 @@ HB2_HD void side_thermo(const double (&V)[Tr::NEQ], const Consts& K, double& rho
     }
 }
 
-/* bounded flag of one interpolated side */
-template <class Tr>
+/* bounded flag of one interpolated side.  Five-eqn c^2 check: the reference accumulates Y_i Psi_i onto Gamma p / rho only in
+ * its x-direction block (FlowModelBasicUtilitiesFiveEqnAllaire.cpp:6654-6678); its y and z blocks re-assign
+ * c_sq = Gamma p / rho inside the species loop (:6968-6992, 7281-7305), so the test there is Gamma p / rho > 0.  Mirrored. */
+template <class Tr, int DIR>
 HB2_HD int side_bounded(const double (&V)[Tr::NEQ], const Consts& K)
 {
     constexpr int DIM = Tr::DIM, NS = Tr::NS, NEQ = Tr::NEQ;
@@ -452,8 +454,10 @@ HB2_HD int side_bounded(const double (&V)[Tr::NEQ], const Consts& K)
         const double gamma_m = 1.0 / xi + 1.0;
         const double Gamma = gamma_m - 1.0;
         double c_sq = Gamma * p / rho;
+        if (DIR == 0) {
 #pragma unroll
-        for (int si = 0; si < NS; si++) c_sq += Y[si] * (p / rho);
+            for (int si = 0; si < NS; si++) c_sq += Y[si] * (p / rho);
+        }
         ok &= (c_sq > 0.0) ? 1 : 0;
     }
     return ok;
@@ -678,7 +682,7 @@ HB2_HD void face_midpoint(const double (&V)[6][Tr::NEQ], double c_cellL, double 
     }
 
     /* bounds check and first-order fallback */
-    const int ok = side_bounded<Tr>(V_minus, K) & side_bounded<Tr>(V_plus, K);
+    const int ok = side_bounded<Tr, DIR>(V_minus, K) & side_bounded<Tr, DIR>(V_plus, K);
     if (!ok) {
 #pragma unroll
         for (int e = 0; e < NEQ; e++) {

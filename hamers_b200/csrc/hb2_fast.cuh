@@ -697,7 +697,7 @@ HB2_HD void face_midpoint_fast(const double* win, bool hybrid, const Consts& K, 
     }
 
     /* bounds check and first-order fallback (rare) */
-    const int ok = side_bounded<Tr>(V_minus, K) & side_bounded<Tr>(V_plus, K);
+    const int ok = side_bounded<Tr, DIR>(V_minus, K) & side_bounded<Tr, DIR>(V_plus, K);
     if (warp_any(!ok)) {
         uniform_branch_fence();
         if (!ok) {

@@ -66,6 +66,27 @@ def statement(text: str, pattern: str, occurrence: int = -1) -> str:
     return text[m.start():text.index(";", m.end()) + 1]
 
 
+def if_else_block(text: str, pattern: str, occurrence: int = -1) -> str:
+    """The `if (...) {...} else {...}` of `text` whose `if` starts at the given occurrence of regex `pattern`."""
+    m = list(re.finditer(pattern, text))[occurrence]
+
+    def close_of(open_at: int) -> int:
+        depth = 0
+        for i in range(open_at, len(text)):
+            if text[i] == "{":
+                depth += 1
+            elif text[i] == "}":
+                depth -= 1
+                if depth == 0:
+                    return i
+        raise ValueError("unbalanced braces")
+    end_if = close_of(text.index("{", m.end()))
+    rest = text[end_if + 1:]
+    assert rest.lstrip().startswith("else"), rest[:40]
+    end_else = close_of(text.index("{", end_if + 1))
+    return text[m.start():end_else + 1]
+
+
 def path_statements() -> str:
     """A function built around the reference's OWN statements for the first derivative (DerivativeFirstOrder.cpp:601),
     dilatation and vorticity magnitude (ConvectiveFluxReconstructorWCNS56-HLLC-HLL.cpp:1631, 1653-1657), the sensor
@@ -456,6 +477,117 @@ extern "C" void ref_path_points4(const double in[12], double out[4])
 """
 
 
+def path_statements5() -> str:
+    """Fifth group: the bounds flag of one interpolated side.  Five-eqn, 3-D: the x block
+    (FlowModelBasicUtilitiesFiveEqnAllaire.cpp:6400-6712) and the y block (:6713-7026; the z block :7027-7340 repeats
+    the y block's statements) -- they differ in the species loop of the c^2 check, see side_bounded in hamers_oracle.c.
+    Single-species, 3-D x (FlowModelBasicUtilitiesSingleSpecies.cpp:3311-3326).  The Gruneisen parameter and Psi come from
+    the statements of the third group (all ns volume fractions)."""
+    def rd(rel):
+        with open(os.path.join(REF, rel)) as fh:
+            return fh.read()
+    bu = rd("src/flow/flow_models/five-eqn_Allaire/FlowModelBasicUtilitiesFiveEqnAllaire.cpp")
+    ss = line_range(rd("src/flow/flow_models/single-species/FlowModelBasicUtilitiesSingleSpecies.cpp"), 3270, 3330)
+    mi = line_range(rd("src/util/mixing_rules/equations_of_state/ideal_gas/EquationOfStateMixingRulesIdealGas.cpp"), 7515, 7590)
+    ig = rd("src/util/mixing_rules/equations_of_state/ideal_gas/EquationOfStateIdealGas.cpp")
+    s_ood = statement(mi, r"const double one_over_denominator = double\(1\)/\(d_species_gamma\[si\] - double\(1\)\)")
+    s_xi = statement(mi, r"gamma\[idx_mixture_thermo_properties\] \+= Z\[si\]\[idx_volume_fractions\]\*one_over_denominator")
+    s_gm = statement(mi, r"gamma\[idx_mixture_thermo_properties\] = double\(1\)/gamma\[idx_mixture_thermo_properties\] \+ double\(1\)")
+    s_Gr = statement(ig, r"Gamma\[idx_gruneisen_parameter\] = gamma\[idx_thermo_properties\] - double\(1\)")
+    s_Psi = statement(ig, r"Psi\[idx_partial_pressure_partial_density\] = p\[idx_pressure\]/rho\[idx_density\]")
+
+    def fe_block(first: int, last: int, name: str) -> str:
+        t = line_range(bu, first, last)
+        s_z = statement(t, r"Z\[si\]\[idx_face\] = V\[d_num_species \+ d_dim\.getValue\(\) \+ 1 \+ si\]\[idx_face\]")
+        s_zl = statement(t, r"Z\[d_num_species - 1\]\[idx_face\] -= Z\[si\]\[idx_face\]")
+        b_z = if_else_block(t, r"if \(Z\[si\]\[idx_face\] > d_Z_bound_lo")
+        b_zl = if_else_block(t, r"if \(Z\[d_num_species - 1\]\[idx_face\] > d_Z_bound_lo")
+        s_rho = statement(t, r"rho\[idx_face\] \+= V\[si\]\[idx_face\]")
+        s_Y = statement(t, r"Y\[si\]\[idx_face\] = V\[si\]\[idx_face\]/rho\[idx_face\]")
+        b_Y = if_else_block(t, r"if \(Y\[si\]\[idx_face\] > d_Y_bound_lo")
+        b_V = if_else_block(t, r"if \(V\[si\]\[idx_face\] > double\(0\)\)")
+        s_p = statement(t, r"p\[idx_face\] = V\[d_num_species \+ d_dim\.getValue\(\)\]\[idx_face\]")
+        s_c0 = statement(t, r"c_sq\[idx_face\] = Gamma\[idx_face\]\*p\[idx_face\]/rho\[idx_face\]", 0)
+        # the statement inside the species loop: `+= Y Psi` in the x block, a second `= Gamma p / rho` in the y / z blocks
+        s_c1 = statement(t, r"c_sq\[idx_face\] (\+= Y\[si\]\[idx_face\]\*Psi\[si\]\[idx_face\]|= Gamma\[idx_face\]\*p\[idx_face\]/rho\[idx_face\])", -1)
+        b_c = if_else_block(t, r"if \(c_sq\[idx_face\] > double\(0\)\)")
+        return f"""
+static int {name}(const double* Vin, const double* gam)
+{{
+    const int d_num_species = 2, idx_face = 0;
+    struct {{ int getValue() const {{ return 3; }} }} d_dim;
+    const int idx_mixture_thermo_properties = 0, idx_volume_fractions = 0, idx_thermo_properties = 0;
+    const int idx_gruneisen_parameter = 0, idx_partial_pressure_partial_density = 0, idx_pressure = 0, idx_density = 0;
+    const double d_Z_bound_lo = REF_Z_BOUND_LO, d_Z_bound_up = REF_Z_BOUND_UP;
+    const double d_Y_bound_lo = REF_Y_BOUND_LO, d_Y_bound_up = REF_Y_BOUND_UP;
+    const std::vector<double> d_species_gamma = {{gam[0], gam[1]}};
+    int are_bounded[1] = {{1}};                              /* bounded_flag->fillAll(1) */
+    double v_[7][1], z_[2][1] = {{{{0.0}}, {{1.0}}}}, y_[2][1], psi_[2][1];     /* last volume fraction filled with 1 */
+    double *V[7], *Z[2] = {{z_[0], z_[1]}}, *Y[2] = {{y_[0], y_[1]}}, *Psi[2] = {{psi_[0], psi_[1]}};
+    for (int e = 0; e < 7; e++) {{ v_[e][0] = Vin[e]; V[e] = v_[e]; }}
+    double rho[1] = {{0.0}}, p[1], Gamma[1], c_sq[1], gamma[1] = {{0.0}};
+    for (int si = 0; si < d_num_species - 1; si++) {{
+        {s_z}
+        {s_zl}
+        {b_z}
+    }}
+    {b_zl}
+    for (int si = 0; si < d_num_species; si++) {{ {s_rho} }}
+    for (int si = 0; si < d_num_species; si++) {{
+        {s_Y}
+        {b_Y}
+    }}
+    for (int si = 0; si < d_num_species; si++) {{ {b_V} }}
+    {s_p}
+    for (int si = 0; si < d_num_species; si++) {{
+        {s_ood}
+        {s_xi}
+    }}
+    {s_gm}
+    {s_Gr}
+    for (int si = 0; si < d_num_species; si++) {{
+        double* Psi_si = Psi[si];
+        double* Psi = Psi_si;
+        {s_Psi}
+    }}
+    {s_c0}
+    for (int si = 0; si < d_num_species; si++) {{ {s_c1} }}
+    {b_c}
+    return are_bounded[0];
+}}
+"""
+    b_r = if_else_block(ss, r"if \(V\[0\]\[idx_face\] > double\(0\)\)", 0)
+    b_pp = if_else_block(ss, r"if \(V\[d_num_eqn - 1\]\[idx_face\] > double\(0\)\)", 0)
+    fe_hpp = rd("include/flow/flow_models/five-eqn_Allaire/FlowModelBasicUtilitiesFiveEqnAllaire.hpp")
+
+    def bound(nm):
+        return re.search(nm + r" = double\(([-0-9.]+)\)", fe_hpp).group(1)
+    return f"""
+#define REF_Y_BOUND_LO ({bound("d_Y_bound_lo")})
+#define REF_Y_BOUND_UP ({bound("d_Y_bound_up")})
+#define REF_Z_BOUND_LO ({bound("d_Z_bound_lo")})
+#define REF_Z_BOUND_UP ({bound("d_Z_bound_up")})
+{fe_block(6400, 6712, "ref_fe_bounded_x")}
+{fe_block(6713, 7026, "ref_fe_bounded_y")}
+{fe_block(7027, 7340, "ref_fe_bounded_z")}
+extern "C" void ref_path_points5(const double in[16], double out[2])
+{{
+    const int dir = (int)in[9];
+    out[0] = (double)(dir == 0 ? ref_fe_bounded_x(in, in + 7) : (dir == 1 ? ref_fe_bounded_y(in, in + 7) : ref_fe_bounded_z(in, in + 7)));
+    {{
+        const int d_num_eqn = 5, idx_face = 0;
+        int are_bounded[1] = {{1}};
+        double v_[5][1];
+        double* V[5];
+        for (int e = 0; e < 5; e++) {{ v_[e][0] = in[10 + e]; V[e] = v_[e]; }}
+        {b_r}
+        {b_pp}
+        out[1] = (double)are_bounded[0];
+    }}
+}}
+"""
+
+
 def static_inline_functions(text: str) -> str:
     """Return the concatenation of every `static inline ...` function definition in text."""
     out = []
@@ -588,6 +720,7 @@ def main() -> int:
     parts.append(path_statements2())
     parts.append(path_statements3())
     parts.append(path_statements4())
+    parts.append(path_statements5())
     gen = os.path.join(OUT, "_generated_ref_kernels.cpp")
     with open(gen, "w") as fh:
         fh.write("\n".join(parts))

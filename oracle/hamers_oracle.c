@@ -280,6 +280,58 @@ void orc_path_points(const double in[16], double out[5])
 #define ORC_Z_BOUND_LO (-1000.0)
 #define ORC_Z_BOUND_UP 1000.0
 
+/* Bounds flag of one interpolated side (1 = bounded).
+ * single-species: FlowModelBasicUtilitiesSingleSpecies.cpp:3311-3326 (rho > 0 && p > 0).
+ * five-eqn: FlowModelBasicUtilitiesFiveEqnAllaire.cpp:6440-6710 (3-D x), 6750-7025 (y), 7060-7340 (z): volume fractions
+ *   (the last one from 1 - sum) and mass fractions strictly inside their bounds, partial densities > 0, c^2 > 0 with the
+ *   Gruneisen parameter from ALL ns volume fractions.  REFERENCE QUIRK, mirrored here: the species loop of the c^2 check
+ *   accumulates Y_i Psi_i only in the x direction (:5819, 6091, 6678); in the y and z directions it re-assigns
+ *   c_sq = Gamma p / rho (:6359, 6992, 7305), so the check there is Gamma p / rho > 0.  The two forms give the same flag
+ *   whenever Gamma = 1/xi > 0, i.e. for every physical set of species gammas.  Pinned through orc_path_points5. */
+static inline int side_bounded(int model, int dim, int ns, int dir, const double* gamma, const double* Vs)
+{
+    int ok = 1;
+    if (model == ORC_SINGLE_SPECIES) {
+        ok &= (Vs[0] > 0.0) ? 1 : 0;
+        ok &= (Vs[dim + 1] > 0.0) ? 1 : 0;
+        return ok;
+    }
+    const double Z_lo = ORC_Z_BOUND_LO, Z_up = ORC_Z_BOUND_UP, Y_lo = ORC_Y_BOUND_LO, Y_up = ORC_Y_BOUND_UP;
+    double Z[ORC_MAX_SPECIES];
+    Z[ns - 1] = 1.0;
+    for (int si = 0; si < ns - 1; si++) {
+        Z[si] = Vs[ns + dim + 1 + si];
+        Z[ns - 1] -= Z[si];
+        ok &= (Z[si] > Z_lo && Z[si] < Z_up) ? 1 : 0;
+    }
+    ok &= (Z[ns - 1] > Z_lo && Z[ns - 1] < Z_up) ? 1 : 0;
+    double rho = 0.0;
+    for (int si = 0; si < ns; si++) rho += Vs[si];
+    double Y[ORC_MAX_SPECIES];
+    for (int si = 0; si < ns; si++) {
+        Y[si] = Vs[si] / rho;
+        ok &= (Y[si] > Y_lo && Y[si] < Y_up) ? 1 : 0;
+    }
+    for (int si = 0; si < ns; si++) ok &= (Vs[si] > 0.0) ? 1 : 0;
+    const double pp = Vs[ns + dim];
+    double xi = 0.0;
+    for (int si = 0; si < ns; si++) xi = fe_xi_accumulate(xi, Z[si], gamma[si]);
+    const double gamma_m = fe_gamma_from_xi(xi);
+    double c_sq = fe_c2_first(fe_gruneisen(gamma_m), pp, rho);
+    for (int si = 0; si < ns; si++)
+        c_sq = (dir == 0) ? fe_c2_accumulate(c_sq, Y[si], fe_psi(pp, rho)) : fe_c2_first(fe_gruneisen(gamma_m), pp, rho);
+    ok &= (c_sq > 0.0) ? 1 : 0;
+    return ok;
+}
+
+void orc_path_points5(const double in[16], double out[2])
+{
+    /* in: five-eqn side V[7] (two species, 3-D), gamma0, gamma1, direction (0 / 1 / 2) | single-species side V[5];
+     * out: the two bounds flags */
+    out[0] = (double)side_bounded(ORC_FIVE_EQN_ALLAIRE, 3, 2, (int)in[9], in + 7, in);
+    out[1] = (double)side_bounded(ORC_SINGLE_SPECIES, 3, 1, 0, in + 7, in + 10);
+}
+
 void orc_constants(double out[7])
 {
     out[0] = EPSILON;
@@ -986,42 +1038,9 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
             FOR_FACES
             {
                 const long s = SIDX(i, j, k);
-                int ok = 1;
-                if (q->model == ORC_SINGLE_SPECIES) {
-                    ok &= (Vs[0][s] > 0.0) ? 1 : 0;
-                    ok &= (Vs[neq - 1][s] > 0.0) ? 1 : 0;
-                } else {
-                    const double Z_lo = ORC_Z_BOUND_LO, Z_up = ORC_Z_BOUND_UP, Y_lo = ORC_Y_BOUND_LO, Y_up = ORC_Y_BOUND_UP;
-                    double Z[ORC_MAX_SPECIES];
-                    Z[ns - 1] = 1.0;
-                    for (int si = 0; si < ns - 1; si++) {
-                        Z[si] = Vs[ns + dim + 1 + si][s];
-                        Z[ns - 1] -= Z[si];
-                        ok &= (Z[si] > Z_lo && Z[si] < Z_up) ? 1 : 0;
-                    }
-                    ok &= (Z[ns - 1] > Z_lo && Z[ns - 1] < Z_up) ? 1 : 0;
-                    double rho = 0.0;
-                    for (int si = 0; si < ns; si++) rho += Vs[si][s];
-                    double Y[ORC_MAX_SPECIES];
-                    for (int si = 0; si < ns; si++) {
-                        Y[si] = Vs[si][s] / rho;
-                        ok &= (Y[si] > Y_lo && Y[si] < Y_up) ? 1 : 0;
-                    }
-                    for (int si = 0; si < ns; si++) ok &= (Vs[si][s] > 0.0) ? 1 : 0;
-                    const double pp = Vs[ns + dim][s];
-                    /* Gruneisen parameter from the FULL set of ns volume fractions
-                     * (data_volume_fractions has depth ns here, :5560-5573) */
-                    double xi = 0.0;
-                    for (int si = 0; si < ns; si++) {
-                        const double one_over_denominator = 1.0 / (d->gamma[si] - 1.0);
-                        xi += Z[si] * one_over_denominator;
-                    }
-                    const double gamma_m = 1.0 / xi + 1.0;
-                    const double Gamma = gamma_m - 1.0;
-                    double c_sq = Gamma * pp / rho;
-                    for (int si = 0; si < ns; si++) c_sq += Y[si] * (pp / rho);
-                    ok &= (c_sq > 0.0) ? 1 : 0;
-                }
+                double Vside[ORC_MAX_EQ];
+                for (int e = 0; e < neq; e++) Vside[e] = Vs[e][s];
+                const int ok = side_bounded(q->model, dim, ns, dir, d->gamma, Vside);
                 flag[side][s] = ok;
             }
         }

@@ -110,6 +110,8 @@ void orc_path_points2(const double in[32], double out[20]);
 void orc_path_points3(const double in[56], double out[32]);
 /* five-eqn: (rho, c, epsilon) rebuilt from one interpolated side in front of the Riemann point kernels */
 void orc_path_points4(const double in[12], double out[4]);
+/* bounds flags of one interpolated side: five-eqn (direction-dependent, see side_bounded) and single-species */
+void orc_path_points5(const double in[16], double out[2]);
 void orc_constants(double out[7]); /* eps, sensor threshold, Y lo/up, Z lo/up, ghost width */
 void orc_eos_point(double gamma, double rho, double epsilon, double* p, double* c, double* eps_back);
 void orc_weno5js_point(const double U[6], int p, double* U_minus, double* U_plus);

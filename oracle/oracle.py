@@ -250,6 +250,14 @@ def path_points4(vals):
     return list(out)
 
 
+def path_points5(vals):
+    """orc_path_points5: bounds flags (five-eqn side V[7], gammas, direction | single-species side V[5])."""
+    a = (C.c_double * 16)(*([float(x) for x in vals] + [0.0] * (16 - len(vals))))
+    out = (C.c_double * 2)()
+    lib().orc_path_points5(a, out)
+    return list(out)
+
+
 def constants():
     out = (C.c_double * 7)()
     lib().orc_constants(out)

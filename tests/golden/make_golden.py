@@ -27,6 +27,9 @@ Contents (all float64, seeded):
                        interpolated side (FlowModelRiemannSolverFiveEqnAllaireHLLC.cpp:5709-5941, mixture gamma from the
                        ns-1 volume fractions EquationOfStateMixingRulesIdealGas.cpp:7770-7829, EquationOfStateIdealGas.cpp:
                        8157, 8308, 6414), statements compiled verbatim
+  path_points5_in (n, 16), path_points5_out (n, 2): bounds flags of one interpolated side, five-eqn (3-D x / y / z blocks,
+                       FlowModelBasicUtilitiesFiveEqnAllaire.cpp:6400-7340) and single-species
+                       (FlowModelBasicUtilitiesSingleSpecies.cpp:3311-3326): the reference's if / else blocks verbatim
   ref_constants (7,): HAMERS_EPSILON, sensor threshold, Y bounds lo/up, Z bounds lo/up, ghost width, parsed from the source
   rk_alpha, rk_beta, rk_gamma (3, 3): the reference's default SSPRK(3,3) table (RungeKuttaLevelIntegrator.cpp:3894-3929)
   eos_in (n, 3) = (gamma, rho, epsilon), eos_out (n, 3) = (p, c, epsilon from p): EquationOfStateIdealGas scalar members
@@ -224,6 +227,30 @@ def main():
         p4_out.append(list(o))
     out["path_points4_in"], out["path_points4_out"] = p4_in, np.array(p4_out)
     assert np.isfinite(out["path_points4_out"]).all()
+    # fifth group: bounds flags of one interpolated side (oracle/build_ref.py: path_statements5), all outcomes and the
+    # directions in which the reference's five-eqn c^2 check differs
+    rng_p5 = np.random.default_rng(555)
+    p5_in = np.zeros((1200, 16))
+    for v in p5_in:
+        v[0:2] = rng_p5.uniform(-0.05, 1.0, 2)
+        v[2:5] = rng_p5.standard_normal(3)
+        v[5] = rng_p5.uniform(-0.1, 2.0)
+        v[6] = [rng_p5.uniform(-0.3, 1.3), rng_p5.uniform(-8.0, 8.0), rng_p5.uniform(-1500.0, 1500.0)][rng_p5.integers(0, 3)]
+        v[7:9] = [rng_p5.uniform(1.1, 1.7, 2), np.array([1.4, 1.09]), np.array([1.0005, 3.0])][rng_p5.integers(0, 3)]
+        v[9] = rng_p5.integers(0, 3)
+        v[10] = rng_p5.uniform(-0.1, 1.0)
+        v[11:14] = rng_p5.standard_normal(3)
+        v[14] = rng_p5.uniform(-0.1, 1.0)
+    p5_in[::50, 0] = 0.0                                  # the comparisons are strict
+    p5_in[::77, 14] = 0.0
+    p5_in[::91, 5] = 0.0
+    p5_in[::97, 6] = [-1000.0, 1000.0, -0.0, 1.0][0]
+    p5_out = []
+    for v in p5_in:
+        o = (C.c_double * 2)()
+        lib.ref_path_points5((C.c_double * 16)(*v), o)
+        p5_out.append(list(o))
+    out["path_points5_in"], out["path_points5_out"] = p5_in, np.array(p5_out)
     # ideal-gas EOS scalars (EquationOfStateIdealGas.cpp:29-45, 561-577, 1093-1108); own generator: the arrays above keep
     # their values
     rng_eos = np.random.default_rng(77)

@@ -152,3 +152,30 @@ def test_emulated_tiny_and_ragged_patches(N, model, ns, oracle_lib):
     assert np.array_equal(Ue, pb.pad_periodic(np.ascontiguousarray(interior(desc, Ue))))
     Uf = emu_host.fused_stage(desc, [1.0], [1.0], [Q], 1.0e-3, math=1)
     assert_fast_parity(interior(desc, Uf), interior(desc, Uo))
+
+
+@pytest.mark.parametrize("name", ["fe2d", "fe3d"])
+def test_emulated_bounds_check_follows_the_reference_per_direction(name, oracle_lib):
+    """The reference's five-eqn c^2 check accumulates Y_i Psi_i only in its x-direction block; its y / z blocks test
+    Gamma p / rho > 0 (FlowModelBasicUtilitiesFiveEqnAllaire.cpp:6654-6678 vs 6968-6992, 7281-7305; pinned in
+    tests/test_oracle_pinned.py).  With species gammas (1.0005, 3) an interpolated volume fraction just below zero gives
+    -1 < Gamma < 0, where the two forms disagree, so the first-order fallback is taken on different faces per
+    direction: the emulated kernels must follow the oracle bit for bit there too."""
+    import dataclasses
+
+    desc, U = make_case(name, "random")
+    desc = dataclasses.replace(desc, gamma=(1.0005, 3.0))
+    # the state exercises the disagreement: an interpolated side as it occurs here, flagged differently by direction
+    side = [0.3, 0.4, 0.1, -0.2, 0.3, 1.0, -0.002, 1.0005, 3.0]
+    assert oracle_lib.path_points5(side + [0.0])[0] == 1.0 and oracle_lib.path_points5(side + [1.0])[0] == 0.0
+    Q = pb.pad_periodic(U)
+    dt = 1.0e-3
+    Fo, So = oracle_lib.compute_flux_and_source(desc, Q, dt)
+    Fe, Se = emu_host.flux_and_source(desc, Q, dt, math=0)
+    for a in range(desc.dim):
+        assert np.array_equal(Fe[a], Fo[a]), f"dir {a}"
+    assert np.array_equal(Se, So)
+    # re-associated arithmetic: same faces fall back (a wrong flag shows as an O(1) flux difference)
+    Ff, Sf = emu_host.flux_and_source(desc, Q, dt, math=1)
+    for a in range(desc.dim):
+        assert_fast_parity(Ff[a], Fo[a], f"dir {a}", 5.0e-3)
