@@ -588,6 +588,51 @@ extern "C" void ref_path_points5(const double in[16], double out[2])
 """
 
 
+def path_statements6() -> str:
+    """Sixth group: max wave speeds (FlowModelSingleSpecies.cpp:4064, 4237, 4365) and the spectral radii / stable dt of
+    Euler::computeSpectralRadiusesAndStableDtOnPatch (Euler.cpp:846-861, 3-D)."""
+    def rd(rel):
+        with open(os.path.join(REF, rel)) as fh:
+            return fh.read()
+    fm = rd("src/flow/flow_models/single-species/FlowModelSingleSpecies.cpp")
+    eu = line_range(rd("src/apps/Euler/Euler.cpp"), 760, 893)
+    s_lx = statement(fm, r"lambda_max_x\[idx_max_wave_speed_x\] = fabs\(u\[idx_velocity\]\) \+ c\[idx_sound_speed\]")
+    s_ly = statement(fm, r"lambda_max_y\[idx_max_wave_speed_y\] = fabs\(v\[idx_velocity\]\) \+ c\[idx_sound_speed\]")
+    s_lz = statement(fm, r"lambda_max_z\[idx_max_wave_speed_z\] = fabs\(w\[idx_velocity\]\) \+ c\[idx_sound_speed\]")
+    s_rx = statement(eu, r"const double spectral_radius_x = max_lambda_x\[idx\]/dx_0")
+    s_ry = statement(eu, r"const double spectral_radius_y = max_lambda_y\[idx\]/dx_1")
+    s_rz = statement(eu, r"const double spectral_radius_z = max_lambda_z\[idx\]/dx_2")
+    s_m3 = statement(eu, r"spectral_radiuses_and_dt_3 = fmax\(spectral_radiuses_and_dt_3,")
+    s_dt = statement(eu, r"spectral_radiuses_and_dt\[3\] = double\(1\)/spectral_radiuses_and_dt\[3\]")
+    return f"""
+extern "C" void ref_path_points6(const double in[8], double out[6])
+{{
+    const int idx = 0, idx_velocity = 0, idx_sound_speed = 0;
+    const int idx_max_wave_speed_x = 0, idx_max_wave_speed_y = 0, idx_max_wave_speed_z = 0;
+    const double u[1] = {{in[0]}}, v[1] = {{in[1]}}, w[1] = {{in[2]}}, c[1] = {{in[3]}};
+    const double dx_0 = in[4], dx_1 = in[5], dx_2 = in[6];
+    double lambda_max_x[1], lambda_max_y[1], lambda_max_z[1];
+    {s_lx}
+    {s_ly}
+    {s_lz}
+    const double *max_lambda_x = lambda_max_x, *max_lambda_y = lambda_max_y, *max_lambda_z = lambda_max_z;
+    {s_rx}
+    {s_ry}
+    {s_rz}
+    out[0] = spectral_radius_x; out[1] = spectral_radius_y; out[2] = spectral_radius_z;
+    double spectral_radiuses_and_dt_3 = -1.0;
+    {s_m3}
+    out[3] = spectral_radiuses_and_dt_3;            /* the sum as the reference associates it */
+    spectral_radiuses_and_dt_3 = in[7];
+    {s_m3}
+    double spectral_radiuses_and_dt[4] = {{0.0, 0.0, 0.0, spectral_radiuses_and_dt_3}};
+    out[4] = spectral_radiuses_and_dt[3];
+    {s_dt}
+    out[5] = spectral_radiuses_and_dt[3];
+}}
+"""
+
+
 def static_inline_functions(text: str) -> str:
     """Return the concatenation of every `static inline ...` function definition in text."""
     out = []
@@ -721,6 +766,7 @@ def main() -> int:
     parts.append(path_statements3())
     parts.append(path_statements4())
     parts.append(path_statements5())
+    parts.append(path_statements6())
     gen = os.path.join(OUT, "_generated_ref_kernels.cpp")
     with open(gen, "w") as fh:
         fh.write("\n".join(parts))

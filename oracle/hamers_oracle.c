@@ -783,6 +783,25 @@ static void cell_stage(const geom_t* q, const double* gam, const double* const* 
     }
 }
 
+/* FlowModelSingleSpecies.cpp:4064, 4237, 4365 (max wave speed), Euler.cpp:846-848 (spectral radius); pinned through
+ * orc_path_points6 */
+static inline double max_wave_speed(double un, double c) { return fabs(un) + c; }
+static inline double spectral_radius_of(double lambda_max, double dx) { return lambda_max / dx; }
+
+void orc_path_points6(const double in[8], double out[6])
+{
+    /* in: u, v, w, c, dx0, dx1, dx2, running maximum of the sum; out: three spectral radii, their sum as accumulated,
+     * the updated running maximum and the stable dt from it (Euler.cpp:846-861) */
+    double sum = 0.0;
+    for (int a = 0; a < 3; a++) {
+        out[a] = spectral_radius_of(max_wave_speed(in[a], in[3]), in[4 + a]);
+        sum = (a == 0) ? out[a] : sum + out[a];
+    }
+    out[3] = sum;
+    out[4] = fmax(in[7], sum);
+    out[5] = 1.0 / out[4];
+}
+
 /* Euler.cpp:760-893 (3D; 2D :627-745): spectral radii and stable dt of one patch, see hamers_oracle.h */
 int orc_spectral_radii_and_dt(const orc_desc* d, const double* const* Q, int include_ghosts, double* out)
 {
@@ -801,8 +820,8 @@ int orc_spectral_radii_and_dt(const orc_desc* d, const double* const* Q, int inc
                 const long x = cidx(&q, i, j, k);
                 double sum = 0.0;
                 for (int a = 0; a < dim; a++) {
-                    const double lambda_max = fabs(vel[a][x]) + c[x];
-                    const double spectral_radius = lambda_max / d->dx[a];
+                    const double lambda_max = max_wave_speed(vel[a][x], c[x]);
+                    const double spectral_radius = spectral_radius_of(lambda_max, d->dx[a]);
                     sr[a] = fmax(sr[a], spectral_radius);
                     sum = (a == 0) ? spectral_radius : sum + spectral_radius;
                 }

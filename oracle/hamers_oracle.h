@@ -112,6 +112,8 @@ void orc_path_points3(const double in[56], double out[32]);
 void orc_path_points4(const double in[12], double out[4]);
 /* bounds flags of one interpolated side: five-eqn (direction-dependent, see side_bounded) and single-species */
 void orc_path_points5(const double in[16], double out[2]);
+/* max wave speeds, spectral radii, their sum, running maximum and stable dt of one cell */
+void orc_path_points6(const double in[8], double out[6]);
 void orc_constants(double out[7]); /* eps, sensor threshold, Y lo/up, Z lo/up, ghost width */
 void orc_eos_point(double gamma, double rho, double epsilon, double* p, double* c, double* eps_back);
 void orc_weno5js_point(const double U[6], int p, double* U_minus, double* U_plus);

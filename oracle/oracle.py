@@ -258,6 +258,14 @@ def path_points5(vals):
     return list(out)
 
 
+def path_points6(vals):
+    """orc_path_points6: spectral radii of one cell, their sum, running maximum, stable dt."""
+    a = (C.c_double * 8)(*[float(x) for x in vals])
+    out = (C.c_double * 6)()
+    lib().orc_path_points6(a, out)
+    return list(out)
+
+
 def constants():
     out = (C.c_double * 7)()
     lib().orc_constants(out)

@@ -30,6 +30,8 @@ Contents (all float64, seeded):
   path_points5_in (n, 16), path_points5_out (n, 2): bounds flags of one interpolated side, five-eqn (3-D x / y / z blocks,
                        FlowModelBasicUtilitiesFiveEqnAllaire.cpp:6400-7340) and single-species
                        (FlowModelBasicUtilitiesSingleSpecies.cpp:3311-3326): the reference's if / else blocks verbatim
+  path_points6_in (n, 8), path_points6_out (n, 6): max wave speeds, spectral radii, their sum, running maximum and stable
+                       dt of one cell (FlowModelSingleSpecies.cpp:4064, 4237, 4365; Euler.cpp:846-861), statements verbatim
   ref_constants (7,): HAMERS_EPSILON, sensor threshold, Y bounds lo/up, Z bounds lo/up, ghost width, parsed from the source
   rk_alpha, rk_beta, rk_gamma (3, 3): the reference's default SSPRK(3,3) table (RungeKuttaLevelIntegrator.cpp:3894-3929)
   eos_in (n, 3) = (gamma, rho, epsilon), eos_out (n, 3) = (p, c, epsilon from p): EquationOfStateIdealGas scalar members
@@ -251,6 +253,16 @@ def main():
         lib.ref_path_points5((C.c_double * 16)(*v), o)
         p5_out.append(list(o))
     out["path_points5_in"], out["path_points5_out"] = p5_in, np.array(p5_out)
+    # sixth group: spectral radii and stable dt of one cell (oracle/build_ref.py: path_statements6)
+    rng_p6 = np.random.default_rng(666)
+    p6_in = np.abs(rng_p6.standard_normal((300, 8))) * 10.0 ** rng_p6.uniform(-2, 2, (300, 1)) + 1.0e-3
+    p6_in[:, 0:3] *= rng_p6.choice([-1.0, 1.0], (300, 3))
+    p6_out = []
+    for v in p6_in:
+        o = (C.c_double * 6)()
+        lib.ref_path_points6((C.c_double * 8)(*v), o)
+        p6_out.append(list(o))
+    out["path_points6_in"], out["path_points6_out"] = p6_in, np.array(p6_out)
     # ideal-gas EOS scalars (EquationOfStateIdealGas.cpp:29-45, 561-577, 1093-1108); own generator: the arrays above keep
     # their values
     rng_eos = np.random.default_rng(77)
