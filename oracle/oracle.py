@@ -47,7 +47,8 @@ class _Desc(C.Structure):
 def build(force: bool = False) -> str:
     """Compile liboracle.so with the reference's CI flags (gcc -O3, no SIMD pragmas, no FMA)."""
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("hamers_oracle.c", "oracle_level.c", "hamers_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("hamers_oracle.c", "oracle_level.c", "hamers_oracle.h", "oracle_diffusive.c",
+                                                   "oracle_diffusive.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs if os.path.exists(s)):
         subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
     return so
@@ -319,3 +320,107 @@ def side_thermo(model, dim, ns, gamma, V):
     r, c, e = C.c_double(), C.c_double(), C.c_double()
     lib().orc_side_thermo(int(model), int(dim), int(ns), g, Va, C.byref(r), C.byref(c), C.byref(e))
     return r.value, c.value, e.value
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# node-based sixth-order diffusive flux of the single-species Navier-Stokes application
+# (oracle_diffusive.c)
+# ---------------------------------------------------------------------------------------------------------------------
+GD = 6   # DiffusiveFluxReconstructorNodeSixthOrder.cpp:24
+
+
+class _Transport(C.Structure):
+    _fields_ = [("mu", C.c_double), ("mu_v", C.c_double), ("c_p", C.c_double), ("c_v", C.c_double), ("Pr", C.c_double)]
+
+
+@dataclass
+class Transport:
+    """CONSTANT shear / bulk viscosity and PRANDTL conductivity of an ideal gas (orc_transport)."""
+    mu: float
+    mu_v: float = 0.0
+    c_p: float = 1004.5
+    c_v: float = 717.5
+    Pr: float = 0.72
+
+    def c(self) -> _Transport:
+        return _Transport(self.mu, self.mu_v, self.c_p, self.c_v, self.Pr)
+
+
+def diff_ghost_shape(desc: PatchDesc):
+    return tuple(int(desc.n[a]) + 2 * GD for a in reversed(range(desc.dim)))
+
+
+def compute_diffusive_flux(desc: PatchDesc, tr: Transport, Q: np.ndarray, dt: float):
+    """Q: (neq, *diff_ghost_shape) with all 6 ghost layers filled.  Returns the list per direction of (neq, *side_shape)."""
+    Q = np.ascontiguousarray(Q, dtype=np.float64)
+    assert Q.shape == (desc.neq,) + diff_ghost_shape(desc), (Q.shape, diff_ghost_shape(desc))
+    neq, dim = desc.neq, desc.dim
+    F = [np.full((neq,) + desc.side_shape(a), np.nan) for a in range(dim)]
+    d, t = desc.c(), tr.c()
+    Fp = _pp([F[a][e] for a in range(dim) for e in range(neq)])
+    Qp = _pp([Q[c] for c in range(neq)])
+    L = lib()
+    L.orc_compute_diffusive_flux.restype = C.c_int
+    rc = L.orc_compute_diffusive_flux(C.byref(d), C.byref(t), Qp, C.c_double(dt), Fp)
+    assert rc == 0
+    return F
+
+
+def advance_stage_ns(desc: PatchDesc, g: int, alpha, beta, U_int, Fc_int, Fd_int, S_int):
+    """One NavierStokes::advanceSingleStepOnPatch (conservative diffusive flux).  U_int[m]: (neq, *shape with ghost g)."""
+    ncoef, neq, dim = len(alpha), desc.neq, desc.dim
+    U_out = np.zeros_like(np.ascontiguousarray(U_int[0]))
+    d = desc.c()
+    keep = []
+    PP = C.POINTER(C.POINTER(C.c_double))
+    tabs = [(PP * ncoef)() for _ in range(4)]
+    for m in range(ncoef):
+        Um = np.ascontiguousarray(U_int[m])
+        ptrs = [_pp([Um[c] for c in range(neq)])]
+        for src in (Fc_int, Fd_int):
+            ptrs.append(_pp([src[m][a][e] for a in range(dim) for e in range(neq)] if src[m] is not None
+                            else [None] * (dim * neq)))
+        ptrs.append(_pp([S_int[m][e] for e in range(neq)] if S_int[m] is not None else [None] * neq))
+        keep += [Um] + ptrs
+        for t, p_ in zip(tabs, ptrs):
+            t[m] = C.cast(p_, PP)
+    a = (C.c_double * ncoef)(*[float(x) for x in alpha])
+    b = (C.c_double * ncoef)(*[float(x) for x in beta])
+    L = lib()
+    L.orc_advance_stage_ns.restype = C.c_int
+    rc = L.orc_advance_stage_ns(C.byref(d), C.c_int(g), C.c_int(ncoef), a, b, tabs[0], tabs[1], tabs[2], tabs[3],
+                                _pp([U_out[c] for c in range(neq)]))
+    assert rc == 0
+    return U_out
+
+
+def diff_first_derivative(u7, dx_inv):
+    L = lib()
+    L.orc_diff_first_derivative.restype = C.c_double
+    return L.orc_diff_first_derivative((C.c_double * 7)(*[float(x) for x in u7]), C.c_double(dx_inv))
+
+
+def diff_reconstruct(F6, dt):
+    L = lib()
+    L.orc_diff_reconstruct.restype = C.c_double
+    return L.orc_diff_reconstruct((C.c_double * 6)(*[float(x) for x in F6]), C.c_double(dt))
+
+
+def diff_point(dim, gamma, rho, p, vel, tr: Transport):
+    """(T, kappa, D[...]) of one cell."""
+    L = lib()
+    L.orc_diff_temperature.restype = C.c_double
+    L.orc_diff_conductivity.restype = C.c_double
+    T = L.orc_diff_temperature(C.c_double(gamma), C.c_double(tr.c_v), C.c_double(rho), C.c_double(p))
+    kappa = L.orc_diff_conductivity(C.c_double(tr.c_p), C.c_double(tr.mu), C.c_double(tr.Pr))
+    D = (C.c_double * 13)()
+    L.orc_diff_diffusivities(C.c_int(dim), C.c_double(tr.mu), C.c_double(tr.mu_v), C.c_double(kappa),
+                             (C.c_double * 3)(*[float(x) for x in list(vel) + [0.0] * (3 - len(vel))]), D)
+    return T, kappa, list(D)[:13 if dim == 3 else 10]
+
+
+def diff_terms(dim, fdir, ddir, e):
+    n = C.c_int()
+    var, dif = (C.c_int * 4)(), (C.c_int * 4)()
+    lib().orc_diff_terms(C.c_int(dim), C.c_int(fdir), C.c_int(ddir), C.c_int(e), C.byref(n), var, dif)
+    return [(var[i], dif[i]) for i in range(n.value)]

@@ -1,0 +1,278 @@
+/*
+ * oracle_diffusive.c -- CPU ORACLE of SURVEY.md row f4 (test infrastructure, NOT a product path).
+ *
+ * Restates, in the reference's operation order, the conservative-form viscous flux of the single-species
+ * Navier-Stokes application with the node-based sixth-order reconstructor (the one all ten shipped viscous decks use,
+ * diffusive_flux_reconstructor = "SIXTH_ORDER"):
+ *
+ *   DiffusiveFluxReconstructorNode::computeDiffusiveFluxOnPatch
+ *       src/flow/diffusive_flux_reconstructors/node/DiffusiveFluxReconstructorNode.cpp:31-1736
+ *   DiffusiveFluxReconstructorNodeSixthOrder::computeFirstDerivativesIn{X,Y,Z}, reconstructFlux{X,Y,Z}
+ *       .../node/DiffusiveFluxReconstructorNodeSixthOrder.cpp:65-939   (6 ghost cells, :24-27)
+ *   FlowModelDiffusiveFluxUtilitiesSingleSpecies: variables to differentiate (:654-1503), diffusivity of each term
+ *       (:1505-2363), the diffusivities D_00..D_12 (:4031-4296)
+ *       src/flow/flow_models/single-species/FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp
+ *   temperature  EquationOfStateIdealGas.cpp:6897   T = p/((gamma - 1) c_v rho)
+ *   viscosities  EquationOfShearViscosityConstant.cpp:273, EquationOfBulkViscosityConstant (same form)
+ *   conductivity EquationOfThermalConductivityPrandtl.cpp:309   kappa = c_p mu / Pr
+ *   RK update    NavierStokes.cpp:2085-2092   (conservative form of the diffusive flux)
+ *
+ * Parity status: the derivative and reconstruction kernels and the point formulas are pinned against the reference's
+ * own code (oracle/build_ref.py: diffusive_*; tests/test_oracle_diffusive.py); which term goes into which equation is
+ * restated from the tables cited above.
+ */
+#include "oracle_diffusive.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define GD ORC_DIFF_GHOSTS
+
+/* DiffusiveFluxReconstructorNodeSixthOrder.cpp:76-78 */
+static const double a_n = 3.0 / 4.0;
+static const double b_n = -(3.0 / 20.0);
+static const double c_n = 1.0 / 60.0;
+
+/* :236-239 (x), :391-394 (y), :488-491 (z): note the multiplication by the inverse mesh width */
+double orc_diff_first_derivative(const double u[7], double dx_inv)
+{
+    return (a_n * (u[4] - u[2]) + b_n * (u[5] - u[1]) + c_n * (u[6] - u[0])) * dx_inv;
+}
+
+/* :679-683: face value from the six nodes around the face (LLL, LL, L, R, RR, RRR), already times dt */
+double orc_diff_reconstruct(const double F[6], double dt)
+{
+    const double a_r = a_n + b_n + c_n;
+    const double b_r = b_n + c_n;
+    const double c_r = c_n;
+    return dt * (a_r * (F[2] + F[3]) + b_r * (F[1] + F[4]) + c_r * (F[0] + F[5]));
+}
+
+/* EquationOfStateIdealGas.cpp:6897; EquationOfThermalConductivityPrandtl.cpp:309 */
+double orc_diff_temperature(double gamma, double c_v, double rho, double p) { return p / ((gamma - 1.0) * c_v * rho); }
+double orc_diff_conductivity(double c_p, double mu, double Pr) { return c_p * mu / Pr; }
+
+/* FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp:4227-4245 (3-D: D_00..D_12), :4153-4166 (2-D: D_00..D_09) */
+void orc_diff_diffusivities(int dim, double mu, double mu_v, double kappa, const double* vel, double* D)
+{
+    const double u = vel[0], v = vel[1];
+    if (dim == 2) {
+        D[0] = -(4.0 / 3.0 * mu + mu_v);
+        D[1] = 2.0 / 3.0 * mu - mu_v;
+        D[2] = -mu;
+        D[3] = -u * (4.0 / 3.0 * mu + mu_v);
+        D[4] = -v * (4.0 / 3.0 * mu + mu_v);
+        D[5] = u * (2.0 / 3.0 * mu - mu_v);
+        D[6] = v * (2.0 / 3.0 * mu - mu_v);
+        D[7] = -u * mu;
+        D[8] = -v * mu;
+        D[9] = -kappa;
+    } else {
+        const double w = vel[2];
+        D[0] = -(4.0 / 3.0 * mu + mu_v);
+        D[1] = 2.0 / 3.0 * mu - mu_v;
+        D[2] = -mu;
+        D[3] = -u * (4.0 / 3.0 * mu + mu_v);
+        D[4] = -v * (4.0 / 3.0 * mu + mu_v);
+        D[5] = -w * (4.0 / 3.0 * mu + mu_v);
+        D[6] = u * (2.0 / 3.0 * mu - mu_v);
+        D[7] = v * (2.0 / 3.0 * mu - mu_v);
+        D[8] = w * (2.0 / 3.0 * mu - mu_v);
+        D[9] = -u * mu;
+        D[10] = -v * mu;
+        D[11] = -w * mu;
+        D[12] = -kappa;
+    }
+}
+
+/* One term of a node flux: derivative of variable `var` (0..dim-1 velocity component, dim = temperature) times
+ * diffusivity D[diff].  terms[flux dir][derivative dir][equation] lists them in the reference's order
+ * (FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp:978-1503 variables, :1838-2363 diffusivities for 3-D;
+ * :760-976, :1640-1836 for 2-D).  The continuity equation has no term. */
+typedef struct {
+    int n;
+    struct {
+        int var, diff;
+    } t[4];
+} term_list;
+
+#define T3 3 /* temperature slot, 3-D */
+static const term_list terms3[3][3][5] = {
+    /* flux x */
+    {{{0, {{0, 0}}}, {1, {{0, 0}}}, {1, {{1, 2}}}, {1, {{2, 2}}}, {4, {{0, 3}, {1, 10}, {2, 11}, {T3, 12}}}},      /* d/dx */
+     {{0, {{0, 0}}}, {1, {{1, 1}}}, {1, {{0, 2}}}, {0, {{0, 0}}}, {2, {{0, 10}, {1, 6}}}},                         /* d/dy */
+     {{0, {{0, 0}}}, {1, {{2, 1}}}, {0, {{0, 0}}}, {1, {{0, 2}}}, {2, {{0, 11}, {2, 6}}}}},                        /* d/dz */
+    /* flux y */
+    {{{0, {{0, 0}}}, {1, {{1, 2}}}, {1, {{0, 1}}}, {0, {{0, 0}}}, {2, {{0, 7}, {1, 9}}}},
+     {{0, {{0, 0}}}, {1, {{0, 2}}}, {1, {{1, 0}}}, {1, {{2, 2}}}, {4, {{0, 9}, {1, 4}, {2, 11}, {T3, 12}}}},
+     {{0, {{0, 0}}}, {0, {{0, 0}}}, {1, {{2, 1}}}, {1, {{1, 2}}}, {2, {{1, 11}, {2, 7}}}}},
+    /* flux z */
+    {{{0, {{0, 0}}}, {1, {{2, 2}}}, {0, {{0, 0}}}, {1, {{0, 1}}}, {2, {{0, 8}, {2, 9}}}},
+     {{0, {{0, 0}}}, {0, {{0, 0}}}, {1, {{2, 2}}}, {1, {{1, 1}}}, {2, {{1, 8}, {2, 10}}}},
+     {{0, {{0, 0}}}, {1, {{0, 2}}}, {1, {{1, 2}}}, {1, {{2, 0}}}, {4, {{0, 9}, {1, 10}, {2, 5}, {T3, 12}}}}},
+};
+#define T2 2 /* temperature slot, 2-D */
+static const term_list terms2[2][2][4] = {
+    {{{0, {{0, 0}}}, {1, {{0, 0}}}, {1, {{1, 2}}}, {3, {{0, 3}, {1, 8}, {T2, 9}}}},
+     {{0, {{0, 0}}}, {1, {{1, 1}}}, {1, {{0, 2}}}, {2, {{0, 8}, {1, 5}}}}},
+    {{{0, {{0, 0}}}, {1, {{1, 2}}}, {1, {{0, 1}}}, {2, {{0, 6}, {1, 7}}}},
+     {{0, {{0, 0}}}, {1, {{0, 2}}}, {1, {{1, 0}}}, {3, {{0, 7}, {1, 4}, {T2, 9}}}}},
+};
+
+static const term_list* terms_of(int dim, int fdir, int ddir, int e)
+{
+    return dim == 3 ? &terms3[fdir][ddir][e] : &terms2[fdir][ddir][e];
+}
+
+void orc_diff_terms(int dim, int fdir, int ddir, int e, int* n, int var[4], int diff[4])
+{
+    const term_list* tl = terms_of(dim, fdir, ddir, e);
+    *n = tl->n;
+    for (int i = 0; i < tl->n; i++) {
+        var[i] = tl->t[i].var;
+        diff[i] = tl->t[i].diff;
+    }
+}
+
+long orc_diff_ghost_size(const orc_desc* d)
+{
+    long s = 1;
+    for (int a = 0; a < d->dim; a++) s *= d->n[a] + 2 * GD;
+    return s;
+}
+
+int orc_compute_diffusive_flux(const orc_desc* d, const orc_transport* tr, const double* const* Q, double dt,
+                               double* const* F)
+{
+    if (d->model != ORC_SINGLE_SPECIES || (d->dim != 2 && d->dim != 3)) return 1;
+    const int dim = d->dim, neq = dim + 2;
+    const int n0 = d->n[0], n1 = d->n[1], n2 = dim == 3 ? d->n[2] : 1;
+    const int g2 = dim == 3 ? GD : 0;
+    const long e0 = n0 + 2 * GD, e1 = n1 + 2 * GD;
+    const long cs[3] = {1, e0, e0 * e1};
+    const long ncell = orc_diff_ghost_size(d);
+#define CIDX(i, j, k) ((long)((i) + GD) + e0 * ((long)((j) + GD) + e1 * (long)((k) + g2)))
+
+    /* derived cell data on the whole ghost box: velocity, pressure, temperature, diffusivities
+     * (FlowModelDiffusiveFluxUtilitiesSingleSpecies::computeDerivedCellData, :490-567) */
+    const int nD = dim == 3 ? 13 : 10;
+    double* var[4];      /* velocity components, then temperature */
+    for (int a = 0; a <= dim; a++) var[a] = (double*)malloc(sizeof(double) * (size_t)ncell);
+    double* D[13];
+    for (int m = 0; m < nD; m++) D[m] = (double*)malloc(sizeof(double) * (size_t)ncell);
+    const double kappa = orc_diff_conductivity(tr->c_p, tr->mu, tr->Pr);
+    for (long x = 0; x < ncell; x++) {
+        const double rho = Q[0][x];
+        double vel[3] = {0.0, 0.0, 0.0}, ke = 0.0, Dx[13];
+        for (int a = 0; a < dim; a++) {
+            vel[a] = Q[1 + a][x] / rho;                                   /* FlowModelSingleSpecies.cpp:2824-2826 */
+            ke = (a == 0) ? vel[a] * vel[a] : ke + vel[a] * vel[a];
+            var[a][x] = vel[a];
+        }
+        const double epsilon = Q[dim + 1][x] / rho - 1.0 / 2.0 * ke;       /* :3049-3051 */
+        const double p = (d->gamma[0] - 1.0) * rho * epsilon;              /* EquationOfStateIdealGas.cpp:5580 */
+        var[dim][x] = orc_diff_temperature(d->gamma[0], tr->c_v, rho, p);
+        orc_diff_diffusivities(dim, tr->mu, tr->mu_v, kappa, vel, Dx);
+        for (int m = 0; m < nD; m++) D[m][x] = Dx[m];
+    }
+
+    double* Fn[5];
+    for (int e = 0; e < neq; e++) Fn[e] = (double*)malloc(sizeof(double) * (size_t)ncell);
+    for (int fdir = 0; fdir < dim; fdir++) {
+        const double dx_inv[3] = {1.0 / d->dx[0], 1.0 / d->dx[1], dim == 3 ? 1.0 / d->dx[2] : 0.0};
+        /* node flux on interior cells extended by 3 in the flux direction (DiffusiveFluxReconstructorNode.cpp:
+         * 3-D x :888-1055, y :1161-1328, z :1434-1601; fillAll(0) first, then "+=" per term: x, y, z derivatives) */
+        const int lo[3] = {fdir == 0 ? -3 : 0, fdir == 1 ? -3 : 0, fdir == 2 ? -3 : 0};
+        const int hi[3] = {n0 + (fdir == 0 ? 3 : 0), n1 + (fdir == 1 ? 3 : 0), n2 + (fdir == 2 ? 3 : 0)};
+        for (int e = 0; e < neq; e++) {
+            for (int k = lo[2]; k < hi[2]; k++)
+                for (int j = lo[1]; j < hi[1]; j++)
+                    for (int i = lo[0]; i < hi[0]; i++) {
+                        const long x = CIDX(i, j, k);
+                        double acc = 0.0;
+                        for (int ddir = 0; ddir < dim; ddir++) {
+                            const term_list* tl = terms_of(dim, fdir, ddir, e);
+                            for (int ti = 0; ti < tl->n; ti++) {
+                                const double* u = var[tl->t[ti].var];
+                                double s[7];
+                                for (int m = 0; m < 7; m++) s[m] = u[x + (m - 3) * cs[ddir]];
+                                const double dudx = orc_diff_first_derivative(s, dx_inv[ddir]);
+                                acc += D[tl->t[ti].diff][x] * dudx;
+                            }
+                        }
+                        Fn[e][x] = acc;
+                    }
+        }
+        /* face flux (reconstructFlux{X,Y,Z}, DiffusiveFluxReconstructorNodeSixthOrder.cpp:507-939): the side data is
+         * zero-filled first (DiffusiveFluxReconstructorNode.cpp:84) and the kernels "+=" */
+        const int fn[3] = {n0 + (fdir == 0), n1 + (fdir == 1), n2 + (fdir == 2)};
+        for (int e = 0; e < neq; e++) {
+            double* Fs = F[fdir * neq + e];
+            for (int k = 0; k < fn[2]; k++)
+                for (int j = 0; j < fn[1]; j++)
+                    for (int i = 0; i < fn[0]; i++) {
+                        const long x = CIDX(i, j, k);          /* the cell on the high side of the face ("R") */
+                        double s[6];
+                        for (int m = 0; m < 6; m++) s[m] = Fn[e][x + (m - 3) * cs[fdir]];
+                        const long sidx = i + (long)fn[0] * ((long)j + (long)fn[1] * (long)k);
+                        Fs[sidx] = 0.0;
+                        Fs[sidx] += orc_diff_reconstruct(s, dt);
+                    }
+        }
+    }
+    for (int e = 0; e < neq; e++) free(Fn[e]);
+    for (int m = 0; m < nD; m++) free(D[m]);
+    for (int a = 0; a <= dim; a++) free(var[a]);
+#undef CIDX
+    return 0;
+}
+
+/* NavierStokes::advanceSingleStepOnPatch, conservative diffusive form (NavierStokes.cpp:1947-2097, 3-D :2085-2092;
+ * 2-D :1715-1751).  U on ghost boxes of width g (same for U_int and U_out), fluxes and sources on ghost 0. */
+int orc_advance_stage_ns(const orc_desc* d, int g, int ncoef, const double* alpha, const double* beta,
+                         const double* const* const* U_int, const double* const* const* Fc_int,
+                         const double* const* const* Fd_int, const double* const* const* S_int, double* const* U_out)
+{
+    const int dim = d->dim, neq = orc_num_eqn(d);
+    const int n0 = d->n[0], n1 = d->n[1], n2 = dim == 3 ? d->n[2] : 1;
+    const int g2 = dim == 3 ? g : 0;
+    const long e0 = n0 + 2 * g, e1 = n1 + 2 * g, e2 = n2 + 2 * g2;
+    const long ncell = e0 * e1 * e2;
+    for (int e = 0; e < neq; e++) memset(U_out[e], 0, sizeof(double) * (size_t)ncell);
+    for (int n = 0; n < ncoef; n++) {
+        if (alpha[n] != 0.0)
+            for (int e = 0; e < neq; e++)
+                for (int k = 0; k < n2; k++)
+                    for (int j = 0; j < n1; j++)
+                        for (int i = 0; i < n0; i++) {
+                            const long x = (i + g) + e0 * ((long)(j + g) + e1 * (long)(k + g2));
+                            U_out[e][x] += alpha[n] * U_int[n][e][x];
+                        }
+        if (beta[n] != 0.0)
+            for (int e = 0; e < neq; e++) {
+                const double *Fcx = Fc_int[n][0 * neq + e], *Fcy = Fc_int[n][1 * neq + e];
+                const double *Fdx = Fd_int[n][0 * neq + e], *Fdy = Fd_int[n][1 * neq + e];
+                const double* Fcz = dim == 3 ? Fc_int[n][2 * neq + e] : NULL;
+                const double* Fdz = dim == 3 ? Fd_int[n][2 * neq + e] : NULL;
+                const double* S = S_int[n][e];
+                for (int k = 0; k < n2; k++)
+                    for (int j = 0; j < n1; j++)
+                        for (int i = 0; i < n0; i++) {
+                            const long x = (i + g) + e0 * ((long)(j + g) + e1 * (long)(k + g2));
+                            const long xs = i + (long)n0 * ((long)j + (long)n1 * (long)k);
+                            const long fxL = i + (long)(n0 + 1) * ((long)j + (long)n1 * (long)k), fxR = fxL + 1;
+                            const long fyB = i + (long)n0 * ((long)j + (long)(n1 + 1) * (long)k), fyT = fyB + n0;
+                            if (dim == 2) {
+                                U_out[e][x] += beta[n] * (-(Fcx[fxR] - Fcx[fxL] + Fdx[fxR] - Fdx[fxL]) / d->dx[0] -
+                                                          (Fcy[fyT] - Fcy[fyB] + Fdy[fyT] - Fdy[fyB]) / d->dx[1] + S[xs]);
+                            } else {
+                                const long fzB = xs, fzF = fzB + (long)n0 * n1;
+                                U_out[e][x] += beta[n] * (-(Fcx[fxR] - Fcx[fxL] + Fdx[fxR] - Fdx[fxL]) / d->dx[0] -
+                                                          (Fcy[fyT] - Fcy[fyB] + Fdy[fyT] - Fdy[fyB]) / d->dx[1] -
+                                                          (Fcz[fzF] - Fcz[fzB] + Fdz[fzF] - Fdz[fzB]) / d->dx[2] + S[xs]);
+                            }
+                        }
+            }
+    }
+    return 0;
+}
