@@ -633,6 +633,115 @@ extern "C" void ref_path_points6(const double in[8], double out[6])
 """
 
 
+def void_member_function(text: str, cls: str, name: str) -> str:
+    """The definition `void\n<cls>::<name>(...) const { ... }` in text, as text."""
+    m = re.search(r"^void\s*\n" + cls + "::" + name + r"\(", text, flags=re.M)
+    brace = text.index("{", m.end())
+    depth, i = 0, brace
+    while True:
+        if text[i] == "{":
+            depth += 1
+        elif text[i] == "}":
+            depth -= 1
+            if depth == 0:
+                break
+        i += 1
+    return text[m.start():i + 1]
+
+
+def diffusive_kernels() -> str:
+    """the six kernels of DiffusiveFluxReconstructorNodeSixthOrder (computeFirstDerivativesIn{X,Y,Z},
+    reconstructFlux{X,Y,Z}, DiffusiveFluxReconstructorNodeSixthOrder.cpp:65-939) compiled verbatim as members of a stub
+    class (hier::IntVector / tbox::Dimension reduced to what the kernels use), driven over the same index ranges as the
+    base class does (DiffusiveFluxReconstructorNode.cpp:1795-1812, 2276-2297); and the reference's statements for the
+    temperature, the Prandtl conductivity and the diffusivities D_00..D_12 / D_00..D_09."""
+    def rd(rel):
+        with open(os.path.join(REF, rel)) as fh:
+            return fh.read()
+    cls = "DiffusiveFluxReconstructorNodeSixthOrder"
+    src = rd("src/flow/diffusive_flux_reconstructors/node/DiffusiveFluxReconstructorNodeSixthOrder.cpp")
+    names = ["computeFirstDerivativesInX", "computeFirstDerivativesInY", "computeFirstDerivativesInZ",
+             "reconstructFluxX", "reconstructFluxY", "reconstructFluxZ"]
+    bodies = "\n\n".join(void_member_function(src, cls, n) for n in names)
+    iv = "const hier::IntVector&"
+    der = f"(double*, const double* const, {iv}, {iv}, {iv}, {iv}, {iv}, {iv}, const double&) const;"
+    rec = f"(double*, const double* const, {iv}, {iv}, {iv}, {iv}, {iv}, const double&) const;"
+    decls = "\n".join(f"    void {n}{der if 'Derivatives' in n else rec}" for n in names)
+    ig = rd("src/util/mixing_rules/equations_of_state/ideal_gas/EquationOfStateIdealGas.cpp")
+    pr = rd("src/util/mixing_rules/equations_of_thermal_conductivity/Prandtl/EquationOfThermalConductivityPrandtl.cpp")
+    du = rd("src/flow/flow_models/single-species/FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp")
+    s_T = statement(ig, r"T\[idx_temperature\] = p\[idx_pressure\]/\(\(gamma - double\(1\)\)\*c_v\*rho\[idx_density\]\)")
+    s_k = statement(pr, r"kappa\[idx_thermal_conductivity\] = c_p\*mu\[idx_min\]/Pr")
+    du3 = line_range(du, 4255, 4285)
+    du2 = line_range(du, 4175, 4198)
+    D3 = "\n        ".join(statement(du3, r"D_%02d\[idx_diffusivities\] = " % m) for m in range(13))
+    D2 = "\n        ".join(statement(du2, r"D_%02d\[idx_diffusivities\] = " % m) for m in range(10))
+    return f"""
+namespace ref_diff {{
+namespace hier {{ struct IntVector {{ int v[3]; int operator[](int i) const {{ return v[i]; }} }}; }}
+namespace tbox {{ struct Dimension {{ int d; explicit Dimension(int d_) : d(d_) {{}}
+                  bool operator==(const Dimension& o) const {{ return d == o.d; }} }}; }}
+struct {cls} {{
+    tbox::Dimension d_dim;
+    explicit {cls}(int dim) : d_dim(dim) {{}}
+{decls}
+}};
+{bodies}
+}}
+
+extern "C" void ref_diff_derivative(int dim, int dir, const double* u, const int* n, double dx_inv, double* out)
+{{
+    using namespace ref_diff;
+    const int g = 6;
+    {cls} k(dim);
+    hier::IntVector ng = {{{{g, g, dim == 3 ? g : 0}}}}, dims = {{{{n[0] + 2 * g, n[1] + 2 * g, dim == 3 ? n[2] + 2 * g : 1}}}};
+    hier::IntVector lo = {{{{-g, -g, dim == 3 ? -g : 0}}}}, dd = dims;
+    lo.v[dir] += 3;
+    dd.v[dir] -= 6;
+    if (dir == 0) k.computeFirstDerivativesInX(out, u, ng, ng, dims, dims, lo, dd, dx_inv);
+    if (dir == 1) k.computeFirstDerivativesInY(out, u, ng, ng, dims, dims, lo, dd, dx_inv);
+    if (dir == 2) k.computeFirstDerivativesInZ(out, u, ng, ng, dims, dims, lo, dd, dx_inv);
+}}
+
+extern "C" void ref_diff_reconstruct(int dim, int dir, const double* F_node, const int* n, double dt, double* F_face)
+{{
+    using namespace ref_diff;
+    const int g = 6;
+    {cls} k(dim);
+    hier::IntVector ng = {{{{g, g, dim == 3 ? g : 0}}}}, dims = {{{{n[0] + 2 * g, n[1] + 2 * g, dim == 3 ? n[2] + 2 * g : 1}}}};
+    hier::IntVector lo = {{{{0, 0, 0}}}}, interior = {{{{n[0], n[1], dim == 3 ? n[2] : 1}}}}, dd = interior;
+    dd.v[dir]++;
+    if (dir == 0) k.reconstructFluxX(F_face, F_node, ng, dims, lo, dd, interior, dt);
+    if (dir == 1) k.reconstructFluxY(F_face, F_node, ng, dims, lo, dd, interior, dt);
+    if (dir == 2) k.reconstructFluxZ(F_face, F_node, ng, dims, lo, dd, interior, dt);
+}}
+
+extern "C" void ref_diff_point(int dim, const double in[10], double out[15])
+{{
+    /* in: gamma, c_v, rho, p, c_p, mu, Pr, mu_v | u, v, w(in[10] is not read in 2-D);  out: T, kappa, D[...] */
+    const int idx_temperature = 0, idx_pressure = 0, idx_density = 0, idx_thermal_conductivity = 0, idx_min = 0;
+    const int idx_diffusivities = 0, idx_shear_viscosity = 0, idx_bulk_viscosity = 0, idx_velocity = 0;
+    const double gamma = in[0], c_v = in[1], rho[1] = {{in[2]}}, p[1] = {{in[3]}}, c_p = in[4], mu[1] = {{in[5]}}, Pr = in[6];
+    const double mu_v[1] = {{in[7]}}, u[1] = {{in[8]}}, v[1] = {{in[9]}}, w[1] = {{dim == 3 ? in[10] : 0.0}};
+    double T[1], kappa[1];
+    {s_T}
+    {s_k}
+    out[0] = T[0]; out[1] = kappa[0];
+    double D_00[1], D_01[1], D_02[1], D_03[1], D_04[1], D_05[1], D_06[1], D_07[1], D_08[1], D_09[1], D_10[1], D_11[1], D_12[1];
+    if (dim == 3) {{
+        {D3}
+        const double* D[13] = {{D_00, D_01, D_02, D_03, D_04, D_05, D_06, D_07, D_08, D_09, D_10, D_11, D_12}};
+        for (int m = 0; m < 13; m++) out[2 + m] = D[m][0];
+    }} else {{
+        {D2}
+        const double* D[10] = {{D_00, D_01, D_02, D_03, D_04, D_05, D_06, D_07, D_08, D_09}};
+        for (int m = 0; m < 10; m++) out[2 + m] = D[m][0];
+        (void)w; (void)D_10; (void)D_11; (void)D_12;
+    }}
+}}
+"""
+
+
 def static_inline_functions(text: str) -> str:
     """Return the concatenation of every `static inline ...` function definition in text."""
     out = []
@@ -767,6 +876,7 @@ def main() -> int:
     parts.append(path_statements4())
     parts.append(path_statements5())
     parts.append(path_statements6())
+    parts.append(diffusive_kernels())
     gen = os.path.join(OUT, "_generated_ref_kernels.cpp")
     with open(gen, "w") as fh:
         fh.write("\n".join(parts))

@@ -424,3 +424,25 @@ def diff_terms(dim, fdir, ddir, e):
     var, dif = (C.c_int * 4)(), (C.c_int * 4)()
     lib().orc_diff_terms(C.c_int(dim), C.c_int(fdir), C.c_int(ddir), C.c_int(e), C.byref(n), var, dif)
     return [(var[i], dif[i]) for i in range(n.value)]
+
+
+def diff_derivative_array(dim, ddir, u, n, dx_inv):
+    """computeFirstDerivativesIn{X,Y,Z} over the reference's range; u on the ghost box (6); untouched entries are NaN."""
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.full_like(u, np.nan)
+    lib().orc_diff_derivative_array(C.c_int(dim), C.c_int(ddir), u.ctypes.data_as(C.POINTER(C.c_double)),
+                                    (C.c_int * 3)(*[int(x) for x in list(n) + [1] * (3 - len(n))]), C.c_double(dx_inv),
+                                    out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out
+
+
+def diff_reconstruct_array(dim, fdir, F_node, n, dt):
+    """reconstructFlux{X,Y,Z} into a zero-filled side array of direction fdir."""
+    F_node = np.ascontiguousarray(F_node, dtype=np.float64)
+    shape = [int(x) for x in n][:dim]
+    shape[fdir] += 1
+    out = np.zeros(tuple(reversed(shape)))
+    lib().orc_diff_reconstruct_array(C.c_int(dim), C.c_int(fdir), F_node.ctypes.data_as(C.POINTER(C.c_double)),
+                                     (C.c_int * 3)(*[int(x) for x in list(n) + [1] * (3 - len(n))]), C.c_double(dt),
+                                     out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out

@@ -52,7 +52,7 @@ double orc_diff_reconstruct(const double F[6], double dt)
 double orc_diff_temperature(double gamma, double c_v, double rho, double p) { return p / ((gamma - 1.0) * c_v * rho); }
 double orc_diff_conductivity(double c_p, double mu, double Pr) { return c_p * mu / Pr; }
 
-/* FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp:4227-4245 (3-D: D_00..D_12), :4153-4166 (2-D: D_00..D_09) */
+/* FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp:4262-4280 (3-D: D_00..D_12), :4180-4193 (2-D: D_00..D_09) */
 void orc_diff_diffusivities(int dim, double mu, double mu_v, double kappa, const double* vel, double* D)
 {
     const double u = vel[0], v = vel[1];
@@ -141,6 +141,46 @@ long orc_diff_ghost_size(const orc_desc* d)
     return s;
 }
 
+/* computeFirstDerivativesIn{X,Y,Z} over the range the base class passes (DiffusiveFluxReconstructorNode.cpp:1795-1812):
+ * the whole ghost box, shrunk by 3 cells on both sides of the derivative direction.  u, out: ghost-box layout. */
+void orc_diff_derivative_array(int dim, int ddir, const double* u, const int* n, double dx_inv, double* out)
+{
+    const int g2 = dim == 3 ? GD : 0;
+    const int n2 = dim == 3 ? n[2] : 1;
+    const long e0 = n[0] + 2 * GD, e1 = n[1] + 2 * GD;
+    const long cs[3] = {1, e0, e0 * e1};
+    int lo[3] = {-GD, -GD, -g2}, hi[3] = {n[0] + GD, n[1] + GD, n2 + g2};
+    lo[ddir] += 3;
+    hi[ddir] -= 3;
+    for (int k = lo[2]; k < hi[2]; k++)
+        for (int j = lo[1]; j < hi[1]; j++)
+            for (int i = lo[0]; i < hi[0]; i++) {
+                const long x = (long)(i + GD) + e0 * ((long)(j + GD) + e1 * (long)(k + g2));
+                double s[7];
+                for (int m = 0; m < 7; m++) s[m] = u[x + (m - 3) * cs[ddir]];
+                out[x] = orc_diff_first_derivative(s, dx_inv);
+            }
+}
+
+/* reconstructFlux{X,Y,Z} over the faces of the interior (DiffusiveFluxReconstructorNode.cpp:2276-2297): "+=" into the
+ * side data.  F_node: ghost-box layout; F_face: side layout of direction fdir, ghost 0. */
+void orc_diff_reconstruct_array(int dim, int fdir, const double* F_node, const int* n, double dt, double* F_face)
+{
+    const int g2 = dim == 3 ? GD : 0;
+    const int n2 = dim == 3 ? n[2] : 1;
+    const long e0 = n[0] + 2 * GD, e1 = n[1] + 2 * GD;
+    const long cs[3] = {1, e0, e0 * e1};
+    const int fn[3] = {n[0] + (fdir == 0), n[1] + (fdir == 1), n2 + (fdir == 2)};
+    for (int k = 0; k < fn[2]; k++)
+        for (int j = 0; j < fn[1]; j++)
+            for (int i = 0; i < fn[0]; i++) {
+                const long x = (long)(i + GD) + e0 * ((long)(j + GD) + e1 * (long)(k + g2));   /* cell on the high side */
+                double s[6];
+                for (int m = 0; m < 6; m++) s[m] = F_node[x + (m - 3) * cs[fdir]];
+                F_face[i + (long)fn[0] * ((long)j + (long)fn[1] * (long)k)] += orc_diff_reconstruct(s, dt);
+            }
+}
+
 int orc_compute_diffusive_flux(const orc_desc* d, const orc_transport* tr, const double* const* Q, double dt,
                                double* const* F)
 {
@@ -149,7 +189,6 @@ int orc_compute_diffusive_flux(const orc_desc* d, const orc_transport* tr, const
     const int n0 = d->n[0], n1 = d->n[1], n2 = dim == 3 ? d->n[2] : 1;
     const int g2 = dim == 3 ? GD : 0;
     const long e0 = n0 + 2 * GD, e1 = n1 + 2 * GD;
-    const long cs[3] = {1, e0, e0 * e1};
     const long ncell = orc_diff_ghost_size(d);
 #define CIDX(i, j, k) ((long)((i) + GD) + e0 * ((long)((j) + GD) + e1 * (long)((k) + g2)))
 
@@ -176,51 +215,46 @@ int orc_compute_diffusive_flux(const orc_desc* d, const orc_transport* tr, const
         for (int m = 0; m < nD; m++) D[m][x] = Dx[m];
     }
 
-    double* Fn[5];
-    for (int e = 0; e < neq; e++) Fn[e] = (double*)malloc(sizeof(double) * (size_t)ncell);
+    /* first derivatives of every variable in every direction, each computed once like the reference's
+     * derivatives_{x,y,z}_computed maps do (DiffusiveFluxReconstructorNode.cpp:1764-1838) */
+    double* der[4][3];
+    for (int a = 0; a <= dim; a++)
+        for (int ddir = 0; ddir < dim; ddir++) {
+            der[a][ddir] = (double*)malloc(sizeof(double) * (size_t)ncell);
+            orc_diff_derivative_array(dim, ddir, var[a], d->n, 1.0 / d->dx[ddir], der[a][ddir]);
+        }
+
+    double* Fn = (double*)malloc(sizeof(double) * (size_t)ncell);
     for (int fdir = 0; fdir < dim; fdir++) {
-        const double dx_inv[3] = {1.0 / d->dx[0], 1.0 / d->dx[1], dim == 3 ? 1.0 / d->dx[2] : 0.0};
-        /* node flux on interior cells extended by 3 in the flux direction (DiffusiveFluxReconstructorNode.cpp:
-         * 3-D x :888-1055, y :1161-1328, z :1434-1601; fillAll(0) first, then "+=" per term: x, y, z derivatives) */
+        /* node flux on the interior cells extended by 3 in the flux direction (DiffusiveFluxReconstructorNode.cpp:
+         * 3-D x :888-1055, y :1161-1328, z :1434-1601): fillAll(0), then "+=" term by term, x- then y- then
+         * z-derivatives */
         const int lo[3] = {fdir == 0 ? -3 : 0, fdir == 1 ? -3 : 0, fdir == 2 ? -3 : 0};
         const int hi[3] = {n0 + (fdir == 0 ? 3 : 0), n1 + (fdir == 1 ? 3 : 0), n2 + (fdir == 2 ? 3 : 0)};
         for (int e = 0; e < neq; e++) {
-            for (int k = lo[2]; k < hi[2]; k++)
-                for (int j = lo[1]; j < hi[1]; j++)
-                    for (int i = lo[0]; i < hi[0]; i++) {
-                        const long x = CIDX(i, j, k);
-                        double acc = 0.0;
-                        for (int ddir = 0; ddir < dim; ddir++) {
-                            const term_list* tl = terms_of(dim, fdir, ddir, e);
-                            for (int ti = 0; ti < tl->n; ti++) {
-                                const double* u = var[tl->t[ti].var];
-                                double s[7];
-                                for (int m = 0; m < 7; m++) s[m] = u[x + (m - 3) * cs[ddir]];
-                                const double dudx = orc_diff_first_derivative(s, dx_inv[ddir]);
-                                acc += D[tl->t[ti].diff][x] * dudx;
+            memset(Fn, 0, sizeof(double) * (size_t)ncell);
+            for (int ddir = 0; ddir < dim; ddir++) {
+                const term_list* tl = terms_of(dim, fdir, ddir, e);
+                for (int ti = 0; ti < tl->n; ti++) {
+                    const double* mu = D[tl->t[ti].diff];
+                    const double* dudx = der[tl->t[ti].var][ddir];
+                    for (int k = lo[2]; k < hi[2]; k++)
+                        for (int j = lo[1]; j < hi[1]; j++)
+                            for (int i = lo[0]; i < hi[0]; i++) {
+                                const long x = CIDX(i, j, k);
+                                Fn[x] += mu[x] * dudx[x];
                             }
-                        }
-                        Fn[e][x] = acc;
-                    }
-        }
-        /* face flux (reconstructFlux{X,Y,Z}, DiffusiveFluxReconstructorNodeSixthOrder.cpp:507-939): the side data is
-         * zero-filled first (DiffusiveFluxReconstructorNode.cpp:84) and the kernels "+=" */
-        const int fn[3] = {n0 + (fdir == 0), n1 + (fdir == 1), n2 + (fdir == 2)};
-        for (int e = 0; e < neq; e++) {
+                }
+            }
+            /* face flux: the side data is zero-filled first (DiffusiveFluxReconstructorNode.cpp:84) */
             double* Fs = F[fdir * neq + e];
-            for (int k = 0; k < fn[2]; k++)
-                for (int j = 0; j < fn[1]; j++)
-                    for (int i = 0; i < fn[0]; i++) {
-                        const long x = CIDX(i, j, k);          /* the cell on the high side of the face ("R") */
-                        double s[6];
-                        for (int m = 0; m < 6; m++) s[m] = Fn[e][x + (m - 3) * cs[fdir]];
-                        const long sidx = i + (long)fn[0] * ((long)j + (long)fn[1] * (long)k);
-                        Fs[sidx] = 0.0;
-                        Fs[sidx] += orc_diff_reconstruct(s, dt);
-                    }
+            memset(Fs, 0, sizeof(double) * (size_t)orc_side_size(d, fdir));
+            orc_diff_reconstruct_array(dim, fdir, Fn, d->n, dt, Fs);
         }
     }
-    for (int e = 0; e < neq; e++) free(Fn[e]);
+    free(Fn);
+    for (int a = 0; a <= dim; a++)
+        for (int ddir = 0; ddir < dim; ddir++) free(der[a][ddir]);
     for (int m = 0; m < nD; m++) free(D[m]);
     for (int a = 0; a <= dim; a++) free(var[a]);
 #undef CIDX

@@ -40,6 +40,8 @@ int orc_advance_stage_ns(const orc_desc* d, int g, int ncoef, const double* alph
 /* point formulas exported for pinning against oracle/_ref */
 double orc_diff_first_derivative(const double u[7], double dx_inv);
 double orc_diff_reconstruct(const double F[6], double dt);
+void orc_diff_derivative_array(int dim, int ddir, const double* u, const int* n, double dx_inv, double* out);
+void orc_diff_reconstruct_array(int dim, int fdir, const double* F_node, const int* n, double dt, double* F_face);
 double orc_diff_temperature(double gamma, double c_v, double rho, double p);
 double orc_diff_conductivity(double c_p, double mu, double Pr);
 void orc_diff_diffusivities(int dim, double mu, double mu_v, double kappa, const double* vel, double* D);
