@@ -33,6 +33,9 @@ SYMBOLS = [
     "hb2_ipc_open", "hb2_ipc_close",
     "hb2_compute_flux_and_source_host", "hb2_fused_stage_host", "hb2_probe_fp64_peak", "hb2_probe_hbm_bandwidth",
     "hb2_plan_set_profiling", "hb2_plan_get_profile", "hb2_advance_level_dev", "hb2_advance_level_host",
+    # diffusive flux of the single-species Navier-Stokes application
+    "hb2_diffusive_plan_create", "hb2_diffusive_plan_destroy", "hb2_diffusive_plan_set_stream", "hb2_diffusive_plan_launches",
+    "hb2_compute_diffusive_flux_dev", "hb2_compute_diffusive_flux_host", "hb2_advance_stage_ns_dev",
 ]
 
 WCNS5_JS, WCNS5_Z, WCNS6_LD = 0, 1, 2
@@ -362,6 +365,94 @@ class Plan:
         _check(self.lib.hb2_fused_stage_host(self._h, ncoef, a, b, tab, C.c_double(dt),
                                              _ptr_table(_host_ptrs(U_out, self.ncomp))), "hb2_fused_stage_host")
         return U_out
+
+
+DIFF_GHOSTS = 6   # DiffusiveFluxReconstructorNodeSixthOrder.cpp:24
+
+
+class DiffusiveDescC(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("n", C.c_int32 * 3), ("dx", C.c_double * 3), ("species_gamma", C.c_double),
+                ("species_c_v", C.c_double), ("species_mu", C.c_double), ("species_mu_v", C.c_double),
+                ("species_c_p", C.c_double), ("species_Pr", C.c_double), ("device", C.c_int32)]
+
+
+class DiffusivePlan:
+    """SURVEY row f4 (mirrors hb2_diff_plan_t): DiffusiveFluxReconstructorNodeSixthOrder ("SIXTH_ORDER") of the
+    single-species Navier-Stokes application with CONSTANT viscosities and PRANDTL conductivity, and the stage update
+    that consumes its flux.  State arrays here carry SIX ghost cells: (dim + 2, [nz+12,] ny+12, nx+12)."""
+
+    def __init__(self, dim: int, n: Sequence[int], dx: Sequence[float], species_gamma: float, species_c_v: float,
+                 species_mu: float, species_mu_v: float, species_c_p: float, species_Pr: float, device: int = 0):
+        self.lib = load_library()
+        d = DiffusiveDescC()
+        d.dim = dim
+        for a in range(3):
+            d.n[a] = int(n[a]) if a < dim else 1
+            d.dx[a] = float(dx[a]) if a < dim else 1.0
+        d.species_gamma, d.species_c_v, d.species_mu, d.species_mu_v = species_gamma, species_c_v, species_mu, species_mu_v
+        d.species_c_p, d.species_Pr, d.device = species_c_p, species_Pr, device
+        self.dim, self.n, self.neq = dim, tuple(int(x) for x in n[:dim]), dim + 2
+        self._h = C.c_void_p()
+        _check(self.lib.hb2_diffusive_plan_create(C.byref(d), C.byref(self._h)), "hb2_diffusive_plan_create")
+
+    def close(self):
+        if self._h:
+            self.lib.hb2_diffusive_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def use_torch_stream(self):
+        import torch
+
+        _check(self.lib.hb2_diffusive_plan_set_stream(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               "hb2_diffusive_plan_set_stream")
+        return self
+
+    @property
+    def launch_count(self) -> int:
+        v = C.c_int64()
+        _check(self.lib.hb2_diffusive_plan_launches(self._h, C.byref(v)), "hb2_diffusive_plan_launches")
+        return v.value
+
+    @property
+    def ghost_shape(self):
+        return tuple(x + 2 * DIFF_GHOSTS for x in reversed(self.n))
+
+    def side_shape(self, d: int):
+        s = list(self.n)
+        s[d] += 1
+        return tuple(reversed(s))
+
+    def compute_diffusive_flux(self, Q, dt: float, flux):
+        """DiffusiveFluxReconstructor::computeDiffusiveFluxOnPatch on device tensors (Q: ghost 6, all ghosts filled)."""
+        qp = _ptr_table(_dev_ptrs(Q, self.neq))
+        fp = _ptr_table([p for d in range(self.dim) for p in _dev_ptrs(flux[d], self.neq)])
+        _check(self.lib.hb2_compute_diffusive_flux_dev(self._h, qp, C.c_double(dt), fp), "hb2_compute_diffusive_flux_dev")
+
+    def compute_diffusive_flux_host(self, Q: np.ndarray, dt: float, flux=None):
+        if flux is None:
+            flux = [np.empty((self.neq,) + self.side_shape(d)) for d in range(self.dim)]
+        qp = _ptr_table(_host_ptrs(Q, self.neq))
+        fp = _ptr_table([p for d in range(self.dim) for p in _host_ptrs(flux[d], self.neq)])
+        _check(self.lib.hb2_compute_diffusive_flux_host(self._h, qp, C.c_double(dt), fp), "hb2_compute_diffusive_flux_host")
+        return flux
+
+    def advance_stage_ns(self, num_ghosts: int, alpha, beta, U_int, Fc_int, Fd_int, S_int, U_out):
+        """NavierStokes::advanceSingleStepOnPatch (conservative diffusive flux) on device tensors; rows with a zero
+        coefficient may be None."""
+        ncoef, neq, dim = len(alpha), self.neq, self.dim
+
+        def rows(src, per_row, width):
+            out = []
+            for m in range(ncoef):
+                out += per_row(src[m]) if src[m] is not None else [None] * width
+            return _ptr_table(out)
+        a = (C.c_double * ncoef)(*[float(x) for x in alpha])
+        b = (C.c_double * ncoef)(*[float(x) for x in beta])
+        _check(self.lib.hb2_advance_stage_ns_dev(
+            self._h, int(num_ghosts), ncoef, a, b, rows(U_int, lambda u: _dev_ptrs(u, neq), neq),
+            rows(Fc_int, lambda f: [p for d in range(dim) for p in _dev_ptrs(f[d], neq)], dim * neq),
+            rows(Fd_int, lambda f: [p for d in range(dim) for p in _dev_ptrs(f[d], neq)], dim * neq),
+            rows(S_int, lambda s_: _dev_ptrs(s_, neq), neq), _ptr_table(_dev_ptrs(U_out, neq))), "hb2_advance_stage_ns_dev")
 
 
 def device_malloc(nbytes: int) -> int:

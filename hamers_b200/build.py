@@ -2,9 +2,10 @@
 
     python -m hamers_b200.build [--force]
 
-Seven translation units: the sweeps are compiled six times (exact: -fmad=false, reference operation
+Eight translation units: the sweeps are compiled six times (exact: -fmad=false, reference operation
 order, once per nonlinear interpolator WCNS5-JS / WCNS5-Z / WCNS6-LD; fast: FMA contraction + reciprocal
-sharing, one per interpolator) and linked with the ABI layer.  nvcc
+sharing, one per interpolator) and linked with the ABI layer and the
+diffusive-flux unit (-fmad=false).  nvcc
 cross-compiles without a GPU.  The .so is git-ignored but travels to the GPU box.
 """
 from __future__ import annotations
@@ -32,8 +33,9 @@ UNITS = [
     ("hb2_sweeps_fast_z.o", "hb2_sweeps.cu", ["-DHB2_MATH=1", "-DHB2_SCHEME=1", "-fmad=true"]),
     ("hb2_sweeps_fast_ld.o", "hb2_sweeps.cu", ["-DHB2_MATH=1", "-DHB2_SCHEME=2", "-fmad=true"]),
     ("hb2_abi.o", "hb2_abi.cu", ["-fmad=false"]),
+    ("hb2_diffusive.o", "hb2_diffusive.cu", ["-fmad=false"]),
 ]
-DEPS = ["hb2_core.cuh", "hb2_fast.cuh", "hb2_sweep.cuh", "hb2_sensor.cuh", "hb2_ops.h", "hb2_sweeps.cu", "hb2_abi.cu", os.path.join(ROOT, "include", "hamers_b200.h")]
+DEPS = ["hb2_core.cuh", "hb2_fast.cuh", "hb2_sweep.cuh", "hb2_sensor.cuh", "hb2_ops.h", "hb2_sweeps.cu", "hb2_abi.cu", "hb2_diffusive.cu", "hb2_diffusive.cuh", os.path.join(ROOT, "include", "hamers_b200.h")]
 
 
 def _mtime(p):

@@ -41,6 +41,11 @@ int env_int(const char* name, int dflt)
 
 }  // namespace
 
+namespace hb2 {
+/* error channel shared with the other translation units of the library (hb2_diffusive.cu) */
+int set_error(int code, const std::string& msg) { return fail(code, msg); }
+}  // namespace hb2
+
 struct hb2_plan_s {
     hb2_patch_desc d;
     Geom G;

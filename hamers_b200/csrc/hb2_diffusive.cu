@@ -1,0 +1,273 @@
+/*
+ * hb2_diffusive.cu -- SURVEY.md row f4: kernels and C ABI of the node-based sixth-order diffusive flux
+ * (DiffusiveFluxReconstructorNodeSixthOrder of the reference, "SIXTH_ORDER" in its input decks) and of the
+ * Navier-Stokes stage update that consumes it.  Entry points are declared in include/hamers_b200.h.
+ *
+ * Three kernels per call, all HBM-bound streaming kernels with x-contiguous (coalesced) accesses and grid-stride loops
+ * over a grid sized as a multiple of the SM count:
+ *   k_diff_primitives   ghost box: 5 (4) conservative doubles in, velocity + temperature out
+ *   k_diff_node<FDIR>   cells extended by 3 along FDIR: sixth-order derivatives of the primitives (stencil reads served
+ *                       by L1/L2: each primitive value is used by 18 neighbouring nodes), diffusivities on the fly,
+ *                       node flux of the momentum and energy equations out
+ *   k_diff_face<FDIR>   faces: six-node reconstruction, times dt, all equations out (the continuity flux is +0.0 like
+ *                       the reference's fillAll(0))
+ * No CPU fallback: every entry point needs a CUDA device.  Built with -fmad=false: reference operation order.
+ */
+#include "../../include/hamers_b200.h"
+#include "hb2_diffusive.cuh"
+
+#include <cuda_runtime.h>
+#include <string>
+
+namespace hb2 {
+int set_error(int code, const std::string& msg);   /* hb2_abi.cu: what hb2_last_error() returns */
+}
+using namespace hb2;
+
+#define HB2D_CUDA(call)                                                                             \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return set_error(-100 - (int)e_, std::string(#call) + ": " + cudaGetErrorString(e_));   \
+    } while (0)
+
+struct hb2_diff_plan_s {
+    hb2_diffusive_desc d;
+    DiffGeom G;
+    DiffConsts K;
+    int device, neq, sm_count;
+    cudaStream_t stream;
+    double* P[4];                 /* primitive scratch on the ghost box */
+    double* Fn[5];                /* node-flux scratch (equation 0 unused) */
+    double* stQ[5];               /* staging of the host-buffer entry point */
+    double* stF[15];
+    long long nside[3];
+    long long launches;
+};
+
+namespace {
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_diff_primitives(const __grid_constant__ DiffGeom G, const __grid_constant__ DiffConsts K,
+                                                         const __grid_constant__ DiffPtrs A)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < G.ncell_g; x += stride)
+        diff_primitives_thread<DIM>(K, A, x);
+}
+
+template <int DIM, int FDIR>
+__global__ void __launch_bounds__(256) k_diff_node(const __grid_constant__ DiffGeom G, const __grid_constant__ DiffConsts K,
+                                                   const __grid_constant__ DiffPtrs A)
+{
+    const long long total = diff_node_count<DIM, FDIR>(G);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride)
+        diff_node_thread<DIM, FDIR>(G, K, A, t);
+}
+
+template <int DIM, int FDIR>
+__global__ void __launch_bounds__(256) k_diff_face(const __grid_constant__ DiffGeom G, const __grid_constant__ DiffPtrs A, double dt)
+{
+    const long long total = diff_face_count<DIM, FDIR>(G);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride)
+        diff_face_thread<DIM, FDIR>(G, A, dt, t);
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_advance_ns(const __grid_constant__ NsArgs A)
+{
+    const long long total = (long long)A.G.n[0] * A.G.n[1] * A.G.n[2];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) advance_ns_thread<DIM>(A, t);
+}
+
+int grid_for(long long work, int sm_count)
+{
+    const long long blocks = (work + 255) / 256;
+    const long long cap = (long long)sm_count * 8;       /* 8 resident 256-thread CTAs per SM, grid-stride beyond */
+    return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+template <int DIM, int FDIR>
+int launch_dir(hb2_diff_plan_t p, const DiffPtrs& A, double dt)
+{
+    const DiffGeom& G = p->G;
+    k_diff_node<DIM, FDIR><<<grid_for(diff_node_count<DIM, FDIR>(G), p->sm_count), 256, 0, p->stream>>>(G, p->K, A);
+    k_diff_face<DIM, FDIR><<<grid_for(p->nside[FDIR], p->sm_count), 256, 0, p->stream>>>(G, A, dt);
+    p->launches += 2;
+    HB2D_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int DIM>
+int run_flux(hb2_diff_plan_t p, const double* const* Q, double dt, double* const* flux)
+{
+    DiffPtrs A{};
+    for (int c = 0; c < DIM + 2; c++) A.Q[c] = Q[c];
+    for (int v = 0; v < DIM + 1; v++) A.P[v] = p->P[v];
+    for (int e = 0; e < DIM + 2; e++) A.Fn[e] = p->Fn[e];
+    k_diff_primitives<DIM><<<grid_for(p->G.ncell_g, p->sm_count), 256, 0, p->stream>>>(p->G, p->K, A);
+    p->launches++;
+    HB2D_CUDA(cudaGetLastError());
+    for (int f = 0; f < DIM; f++) {
+        for (int e = 0; e < DIM + 2; e++) A.F[e] = flux[f * (DIM + 2) + e];
+        int rc = f == 0 ? launch_dir<DIM, 0>(p, A, dt) : f == 1 ? launch_dir<DIM, 1>(p, A, dt) : launch_dir<DIM, (DIM == 3 ? 2 : 1)>(p, A, dt);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hb2_diffusive_plan_create(const hb2_diffusive_desc* d, hb2_diff_plan_t* out)
+{
+    if (!d || !out) return set_error(-1, "null argument");
+    if (d->dim != 2 && d->dim != 3) return set_error(-2, "dim must be 2 or 3");
+    for (int a = 0; a < d->dim; a++) {
+        if (d->n[a] < 1) return set_error(-3, "patch dims must be positive");
+        if (!(d->dx[a] > 0.0)) return set_error(-4, "grid spacing must be positive");
+    }
+    if (!(d->species_gamma > 1.0)) return set_error(-8, "species_gamma must be > 1");
+    if (!(d->species_c_v > 0.0) || !(d->species_c_p > 0.0) || !(d->species_Pr > 0.0))
+        return set_error(-30, "species_c_v, species_c_p and species_Pr must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return set_error(-20, "no CUDA device: hamers_b200 has no CPU fallback (the CPU oracle lives under oracle/ and is test infrastructure)");
+    hb2_diff_plan_t p = new hb2_diff_plan_s();
+    p->d = *d;
+    p->device = d->device;
+    HB2D_CUDA(cudaSetDevice(p->device));
+    cudaDeviceProp prop;
+    HB2D_CUDA(cudaGetDeviceProperties(&prop, p->device));
+    p->sm_count = prop.multiProcessorCount;
+    make_diff_geom(d->dim, d->n, d->dx, HB2_DIFF_G, &p->G);
+    p->K.gamma = d->species_gamma;
+    p->K.c_v = d->species_c_v;
+    p->K.mu = d->species_mu;
+    p->K.mu_v = d->species_mu_v;
+    p->K.kappa = d->species_c_p * d->species_mu / d->species_Pr;      /* EquationOfThermalConductivityPrandtl.cpp:309 */
+    p->neq = d->dim + 2;
+    p->stream = nullptr;
+    for (int a = 0; a < 3; a++) {
+        long long s = 1;
+        for (int b = 0; b < 3; b++) s *= p->G.n[b] + ((a == b && a < d->dim) ? 1 : 0);
+        p->nside[a] = s;
+    }
+    const size_t bytes = sizeof(double) * (size_t)p->G.ncell_g;
+    for (int v = 0; v < d->dim + 1; v++) HB2D_CUDA(cudaMalloc(&p->P[v], bytes));
+    for (int e = 1; e < p->neq; e++) {
+        HB2D_CUDA(cudaMalloc(&p->Fn[e], bytes));
+        HB2D_CUDA(cudaMemset(p->Fn[e], 0, bytes));
+    }
+    *out = p;
+    return 0;
+}
+
+int hb2_diffusive_plan_destroy(hb2_diff_plan_t p)
+{
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    for (int v = 0; v < 4; v++) cudaFree(p->P[v]);
+    for (int e = 0; e < 5; e++) {
+        cudaFree(p->Fn[e]);
+        cudaFree(p->stQ[e]);
+    }
+    for (int e = 0; e < 15; e++) cudaFree(p->stF[e]);
+    delete p;
+    return 0;
+}
+
+int hb2_diffusive_plan_set_stream(hb2_diff_plan_t p, void* stream)
+{
+    if (!p) return set_error(-1, "null plan");
+    p->stream = (cudaStream_t)stream;
+    return 0;
+}
+
+int hb2_diffusive_plan_launches(hb2_diff_plan_t p, int64_t* launches)
+{
+    if (!p || !launches) return set_error(-1, "null argument");
+    *launches = p->launches;
+    return 0;
+}
+
+int hb2_compute_diffusive_flux_dev(hb2_diff_plan_t p, const double* const* Q, double dt, double* const* flux)
+{
+    if (!p || !Q || !flux) return set_error(-1, "null argument");
+    HB2D_CUDA(cudaSetDevice(p->device));
+    return p->d.dim == 2 ? run_flux<2>(p, Q, dt, flux) : run_flux<3>(p, Q, dt, flux);
+}
+
+int hb2_compute_diffusive_flux_host(hb2_diff_plan_t p, const double* const* Q_host, double dt, double* const* flux_host)
+{
+    if (!p || !Q_host || !flux_host) return set_error(-1, "null argument");
+    HB2D_CUDA(cudaSetDevice(p->device));
+    const size_t cbytes = sizeof(double) * (size_t)p->G.ncell_g;
+    const int dim = p->d.dim, neq = p->neq;
+    const double* Qd[5];
+    double* Fd[15];
+    for (int c = 0; c < neq; c++) {
+        if (!p->stQ[c]) HB2D_CUDA(cudaMalloc(&p->stQ[c], cbytes));
+        HB2D_CUDA(cudaMemcpyAsync(p->stQ[c], Q_host[c], cbytes, cudaMemcpyHostToDevice, p->stream));
+        Qd[c] = p->stQ[c];
+    }
+    for (int f = 0; f < dim; f++)
+        for (int e = 0; e < neq; e++) {
+            double*& slot = p->stF[f * neq + e];
+            if (!slot) HB2D_CUDA(cudaMalloc(&slot, sizeof(double) * (size_t)p->nside[f]));
+            Fd[f * neq + e] = slot;
+        }
+    int rc = hb2_compute_diffusive_flux_dev(p, Qd, dt, Fd);
+    if (rc) return rc;
+    for (int f = 0; f < dim; f++)
+        for (int e = 0; e < neq; e++)
+            HB2D_CUDA(cudaMemcpyAsync(flux_host[f * neq + e], Fd[f * neq + e], sizeof(double) * (size_t)p->nside[f],
+                                      cudaMemcpyDeviceToHost, p->stream));
+    HB2D_CUDA(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int hb2_advance_stage_ns_dev(hb2_diff_plan_t p, int32_t num_ghosts, int32_t ncoef, const double* alpha, const double* beta,
+                             const double* const* U_int, const double* const* Fc_int, const double* const* Fd_int,
+                             const double* const* S_int, double* const* U_out)
+{
+    if (!p || !alpha || !beta || !U_int || !Fc_int || !Fd_int || !S_int || !U_out) return set_error(-1, "null argument");
+    if (ncoef < 1 || ncoef > HB2_MAXS) return set_error(-10, "ncoef out of range");
+    if (num_ghosts < 0) return set_error(-31, "num_ghosts must be >= 0");
+    HB2D_CUDA(cudaSetDevice(p->device));
+    const int dim = p->d.dim, neq = p->neq;
+    NsArgs A{};
+    make_diff_geom(dim, p->d.n, p->d.dx, num_ghosts, &A.G);
+    A.neq = neq;
+    A.ncoef = ncoef;
+    for (int m = 0; m < ncoef; m++) {
+        A.alpha[m] = alpha[m];
+        A.beta[m] = beta[m];
+        for (int e = 0; e < neq; e++) {
+            A.U[m][e] = U_int[m * neq + e];
+            A.S[m][e] = S_int[m * neq + e];
+            if (alpha[m] != 0.0 && !A.U[m][e]) return set_error(-11, "U_int row with alpha != 0 is NULL");
+            if (beta[m] != 0.0 && !A.S[m][e]) return set_error(-12, "S_int row with beta != 0 is NULL");
+        }
+        for (int f = 0; f < dim * neq; f++) {
+            A.Fc[m][f] = Fc_int[m * dim * neq + f];
+            A.Fd[m][f] = Fd_int[m * dim * neq + f];
+            if (beta[m] != 0.0 && (!A.Fc[m][f] || !A.Fd[m][f])) return set_error(-12, "flux row with beta != 0 is NULL");
+        }
+    }
+    for (int e = 0; e < neq; e++) A.Uout[e] = U_out[e];
+    const long long total = (long long)A.G.n[0] * A.G.n[1] * A.G.n[2];
+    if (dim == 2)
+        k_advance_ns<2><<<grid_for(total, p->sm_count), 256, 0, p->stream>>>(A);
+    else
+        k_advance_ns<3><<<grid_for(total, p->sm_count), 256, 0, p->stream>>>(A);
+    p->launches++;
+    HB2D_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  /* extern "C" */

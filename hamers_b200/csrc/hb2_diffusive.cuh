@@ -1,0 +1,351 @@
+/*
+ * hb2_diffusive.cuh -- SURVEY.md row f4: node-based sixth-order diffusive (viscous) flux of the single-species
+ * Navier-Stokes application, per-thread arithmetic.
+ *
+ * `__host__ __device__` like hb2_core.cuh: inlined into the sm_100a kernels of hb2_diffusive.cu and compiled by g++
+ * into the test-only host emulation (tests/host_emu/emu_diffusive.cpp).  Reference operation order throughout (the
+ * translation unit is built with -fmad=false): results are bit-identical to oracle/oracle_diffusive.c.
+ *
+ * Reference behaviour restated here (path:line under the reference tree):
+ *   driver            src/flow/diffusive_flux_reconstructors/node/DiffusiveFluxReconstructorNode.cpp:31-1736
+ *   derivative        .../node/DiffusiveFluxReconstructorNodeSixthOrder.cpp:65-505   (a_n, b_n, c_n; times 1/dx)
+ *   reconstruction    .../node/DiffusiveFluxReconstructorNodeSixthOrder.cpp:507-939  (a_r, b_r, c_r; times dt, "+=" on 0)
+ *   terms             src/flow/flow_models/single-species/FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp:654-2363
+ *   diffusivities     ...FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp:4180-4193 (2-D), 4262-4280 (3-D)
+ *   T, kappa          EquationOfStateIdealGas.cpp:6897; EquationOfThermalConductivityPrandtl.cpp:309
+ *   RK update         src/apps/Navier-Stokes/NavierStokes.cpp:1715-1751 (2-D), 2085-2092 (3-D)
+ *
+ * Data layout: cell data on the ghost box of width 6 (d_num_diff_ghosts), x fastest; the primitive scratch (velocity
+ * components, temperature) and the node-flux scratch use the same box; side fluxes on ghost 0 like the convective ones.
+ */
+#pragma once
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define HB2D_HD __host__ __device__ __forceinline__
+#else
+#define HB2D_HD inline
+#endif
+
+#define HB2_DIFF_G 6 /* DiffusiveFluxReconstructorNodeSixthOrder.cpp:24 */
+#ifndef HB2_MAXS
+#define HB2_MAXS 4   /* RK coefficients per stage row, as in hb2_core.cuh */
+#endif
+
+namespace hb2 {
+
+struct DiffGeom {
+    int dim;
+    int n[3];          /* interior cells (n[2] = 1 in 2-D) */
+    int g[3];          /* 6, 6, 6 (0 in the unused direction of 2-D) */
+    int gd[3];         /* ghost-box dims */
+    long long cs[3];   /* cell strides in the ghost box */
+    long long ncell_g;
+    double dx_inv[3];  /* double(1)/dx[d], DiffusiveFluxReconstructorNode.cpp:1762 */
+    double dx[3];
+};
+
+struct DiffConsts {
+    double gamma, c_v;     /* ideal gas */
+    double mu, mu_v;       /* CONSTANT shear / bulk viscosity */
+    double kappa;          /* c_p*mu/Pr */
+};
+
+/* one term of a node flux: derivative of variable `var` (velocity component, or DIM for the temperature) in one
+ * direction times the diffusivity D[diff] */
+struct DiffTerm {
+    signed char var, diff;
+};
+struct DiffTermList {
+    int n;
+    DiffTerm t[4];
+};
+
+/* terms[flux direction][derivative direction][equation], in the reference's order of accumulation
+ * (FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp:978-1503 and 1838-2363) */
+template <int DIM>
+struct DiffTerms;
+
+template <>
+struct DiffTerms<3> {
+    static constexpr int NEQ = 5, ND = 13, T = 3;
+    HB2D_HD static constexpr DiffTermList get(int f, int d, int e)
+    {
+        constexpr DiffTermList none = {0, {{0, 0}, {0, 0}, {0, 0}, {0, 0}}};
+        if (e == 0) return none;
+        if (f == 0) {
+            if (d == 0) return e == 1 ? DiffTermList{1, {{0, 0}}} : e == 2 ? DiffTermList{1, {{1, 2}}} : e == 3 ? DiffTermList{1, {{2, 2}}}
+                                                                  : DiffTermList{4, {{0, 3}, {1, 10}, {2, 11}, {T, 12}}};
+            if (d == 1) return e == 1 ? DiffTermList{1, {{1, 1}}} : e == 2 ? DiffTermList{1, {{0, 2}}} : e == 3 ? none
+                                                                  : DiffTermList{2, {{0, 10}, {1, 6}}};
+            return e == 1 ? DiffTermList{1, {{2, 1}}} : e == 2 ? none : e == 3 ? DiffTermList{1, {{0, 2}}}
+                                                                  : DiffTermList{2, {{0, 11}, {2, 6}}};
+        }
+        if (f == 1) {
+            if (d == 0) return e == 1 ? DiffTermList{1, {{1, 2}}} : e == 2 ? DiffTermList{1, {{0, 1}}} : e == 3 ? none
+                                                                  : DiffTermList{2, {{0, 7}, {1, 9}}};
+            if (d == 1) return e == 1 ? DiffTermList{1, {{0, 2}}} : e == 2 ? DiffTermList{1, {{1, 0}}} : e == 3 ? DiffTermList{1, {{2, 2}}}
+                                                                  : DiffTermList{4, {{0, 9}, {1, 4}, {2, 11}, {T, 12}}};
+            return e == 1 ? none : e == 2 ? DiffTermList{1, {{2, 1}}} : e == 3 ? DiffTermList{1, {{1, 2}}}
+                                                                  : DiffTermList{2, {{1, 11}, {2, 7}}};
+        }
+        if (d == 0) return e == 1 ? DiffTermList{1, {{2, 2}}} : e == 2 ? none : e == 3 ? DiffTermList{1, {{0, 1}}}
+                                                              : DiffTermList{2, {{0, 8}, {2, 9}}};
+        if (d == 1) return e == 1 ? none : e == 2 ? DiffTermList{1, {{2, 2}}} : e == 3 ? DiffTermList{1, {{1, 1}}}
+                                                              : DiffTermList{2, {{1, 8}, {2, 10}}};
+        return e == 1 ? DiffTermList{1, {{0, 2}}} : e == 2 ? DiffTermList{1, {{1, 2}}} : e == 3 ? DiffTermList{1, {{2, 0}}}
+                                                              : DiffTermList{4, {{0, 9}, {1, 10}, {2, 5}, {T, 12}}};
+    }
+};
+
+template <>
+struct DiffTerms<2> {
+    static constexpr int NEQ = 4, ND = 10, T = 2;
+    HB2D_HD static constexpr DiffTermList get(int f, int d, int e)
+    {
+        constexpr DiffTermList none = {0, {{0, 0}, {0, 0}, {0, 0}, {0, 0}}};
+        if (e == 0) return none;
+        if (f == 0) {
+            if (d == 0) return e == 1 ? DiffTermList{1, {{0, 0}}} : e == 2 ? DiffTermList{1, {{1, 2}}}
+                                                                  : DiffTermList{3, {{0, 3}, {1, 8}, {T, 9}}};
+            return e == 1 ? DiffTermList{1, {{1, 1}}} : e == 2 ? DiffTermList{1, {{0, 2}}} : DiffTermList{2, {{0, 8}, {1, 5}}};
+        }
+        if (d == 0) return e == 1 ? DiffTermList{1, {{1, 2}}} : e == 2 ? DiffTermList{1, {{0, 1}}} : DiffTermList{2, {{0, 6}, {1, 7}}};
+        return e == 1 ? DiffTermList{1, {{0, 2}}} : e == 2 ? DiffTermList{1, {{1, 0}}} : DiffTermList{3, {{0, 7}, {1, 4}, {T, 9}}};
+    }
+};
+
+/* velocity and temperature of one cell from its conservative variables (FlowModelSingleSpecies.cpp:2824-2826, 3049-3051;
+ * EquationOfStateIdealGas.cpp:5580, 6897) */
+template <int DIM>
+HB2D_HD void diff_primitives(const double (&Q)[DIM + 2], const DiffConsts& K, double (&P)[DIM + 1])
+{
+    const double rho = Q[0];
+    double ke = 0.0;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) {
+        P[a] = Q[1 + a] / rho;
+        ke = (a == 0) ? P[a] * P[a] : ke + P[a] * P[a];
+    }
+    const double epsilon = Q[DIM + 1] / rho - 1.0 / 2.0 * ke;
+    const double p = (K.gamma - 1.0) * rho * epsilon;
+    P[DIM] = p / ((K.gamma - 1.0) * K.c_v * rho);
+}
+
+/* the diffusivities of one cell (FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp:4180-4193, 4262-4280) */
+template <int DIM>
+HB2D_HD void diff_diffusivities(const double* vel, const DiffConsts& K, double (&D)[DiffTerms<DIM>::ND])
+{
+    const double mu = K.mu, mu_v = K.mu_v;
+    const double u = vel[0], v = vel[1];
+    D[0] = -(4.0 / 3.0 * mu + mu_v);
+    D[1] = 2.0 / 3.0 * mu - mu_v;
+    D[2] = -mu;
+    if constexpr (DIM == 2) {
+        D[3] = -u * (4.0 / 3.0 * mu + mu_v);
+        D[4] = -v * (4.0 / 3.0 * mu + mu_v);
+        D[5] = u * (2.0 / 3.0 * mu - mu_v);
+        D[6] = v * (2.0 / 3.0 * mu - mu_v);
+        D[7] = -u * mu;
+        D[8] = -v * mu;
+        D[9] = -K.kappa;
+    } else {
+        const double w = vel[DIM - 1];
+        D[3] = -u * (4.0 / 3.0 * mu + mu_v);
+        D[4] = -v * (4.0 / 3.0 * mu + mu_v);
+        D[5] = -w * (4.0 / 3.0 * mu + mu_v);
+        D[6] = u * (2.0 / 3.0 * mu - mu_v);
+        D[7] = v * (2.0 / 3.0 * mu - mu_v);
+        D[8] = w * (2.0 / 3.0 * mu - mu_v);
+        D[9] = -u * mu;
+        D[10] = -v * mu;
+        D[11] = -w * mu;
+        D[12] = -K.kappa;
+    }
+}
+
+/* DiffusiveFluxReconstructorNodeSixthOrder.cpp:236-239: sixth-order first derivative at a node, p points at the node */
+HB2D_HD double diff_first_derivative(const double* p, long long stride, double dx_inv)
+{
+    const double a_n = 3.0 / 4.0;
+    const double b_n = -(3.0 / 20.0);
+    const double c_n = 1.0 / 60.0;
+    return (a_n * (p[stride] - p[-stride]) + b_n * (p[2 * stride] - p[-2 * stride]) + c_n * (p[3 * stride] - p[-3 * stride])) *
+           dx_inv;
+}
+
+/* :679-683: face flux from the six nodes LLL..RRR around the face; p points at node R (the cell on the high side) */
+HB2D_HD double diff_reconstruct(const double* p, long long stride, double dt)
+{
+    const double a_n = 3.0 / 4.0;
+    const double b_n = -(3.0 / 20.0);
+    const double c_n = 1.0 / 60.0;
+    const double a_r = a_n + b_n + c_n;
+    const double b_r = b_n + c_n;
+    const double c_r = c_n;
+    double F = 0.0;                              /* diffusive_flux->fillAll(0), then "+=" */
+    F += dt * (a_r * (p[-stride] + p[0]) + b_r * (p[-2 * stride] + p[stride]) + c_r * (p[-3 * stride] + p[2 * stride]));
+    return F;
+}
+
+/* The node flux of all equations at ghost-box cell x for flux direction FDIR
+ * (DiffusiveFluxReconstructorNode.cpp:888-1055 and the y / z copies): zero, then "+=" term by term.
+ * P[v] are the primitive scratch arrays (velocity components, temperature) on the ghost box. */
+template <int DIM, int FDIR>
+HB2D_HD void diff_node_flux(const DiffGeom& G, const DiffConsts& K, const double* const* P, long long x,
+                            double (&Fn)[DIM + 2])
+{
+    using TT = DiffTerms<DIM>;
+    double vel[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int a = 0; a < DIM; a++) vel[a] = P[a][x];
+    double D[TT::ND];
+    diff_diffusivities<DIM>(vel, K, D);
+    /* every derivative is evaluated at most once (the reference's derivatives_*_computed maps) */
+    double der[DIM + 1][DIM];
+    bool have[DIM + 1][DIM] = {};
+#pragma unroll
+    for (int e = 0; e < DIM + 2; e++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            const DiffTermList tl = TT::get(FDIR, d, e);
+#pragma unroll
+            for (int ti = 0; ti < 4; ti++) {
+                if (ti < tl.n) {
+                    const int v = tl.t[ti].var;
+                    if (!have[v][d]) {
+                        der[v][d] = diff_first_derivative(P[v] + x, G.cs[d], G.dx_inv[d]);
+                        have[v][d] = true;
+                    }
+                    acc += D[tl.t[ti].diff] * der[v][d];
+                }
+            }
+        }
+        Fn[e] = acc;
+    }
+}
+
+/* ---- one thread of each kernel (the kernels of hb2_diffusive.cu are grid-stride loops over these; the host emulation
+ * calls them from plain loops) ---- */
+struct DiffPtrs {
+    const double* Q[5];
+    double* P[4];
+    double* Fn[5];
+    double* F[5];
+};
+
+template <int DIM>
+HB2D_HD void diff_primitives_thread(const DiffConsts& K, const DiffPtrs& A, long long x)
+{
+    double Q[DIM + 2], P[DIM + 1];
+#pragma unroll
+    for (int c = 0; c < DIM + 2; c++) Q[c] = A.Q[c][x];
+    diff_primitives<DIM>(Q, K, P);
+#pragma unroll
+    for (int v = 0; v < DIM + 1; v++) A.P[v][x] = P[v];
+}
+
+template <int DIM, int FDIR>
+HB2D_HD long long diff_node_count(const DiffGeom& G)
+{
+    return (long long)(G.n[0] + (FDIR == 0 ? 6 : 0)) * (G.n[1] + (FDIR == 1 ? 6 : 0)) * (G.n[2] + (FDIR == 2 ? 6 : 0));
+}
+
+/* node t of the interior extended by 3 cells on both sides of FDIR, x fastest */
+template <int DIM, int FDIR>
+HB2D_HD void diff_node_thread(const DiffGeom& G, const DiffConsts& K, const DiffPtrs& A, long long t)
+{
+    const int e0 = G.n[0] + (FDIR == 0 ? 6 : 0), e1 = G.n[1] + (FDIR == 1 ? 6 : 0);
+    const int i = (int)(t % e0) - (FDIR == 0 ? 3 : 0);
+    const int j = (int)((t / e0) % e1) - (FDIR == 1 ? 3 : 0);
+    const int k = (int)(t / ((long long)e0 * e1)) - (FDIR == 2 ? 3 : 0);
+    const long long x = (i + G.g[0]) + G.cs[1] * (j + G.g[1]) + G.cs[2] * (k + G.g[2]);
+    const double* P[DIM + 1];
+#pragma unroll
+    for (int v = 0; v < DIM + 1; v++) P[v] = A.P[v];
+    double Fn[DIM + 2];
+    diff_node_flux<DIM, FDIR>(G, K, P, x, Fn);
+#pragma unroll
+    for (int e = 1; e < DIM + 2; e++) A.Fn[e][x] = Fn[e];
+}
+
+template <int DIM, int FDIR>
+HB2D_HD long long diff_face_count(const DiffGeom& G)
+{
+    return (long long)(G.n[0] + (FDIR == 0)) * (G.n[1] + (FDIR == 1)) * (G.n[2] + (FDIR == 2));
+}
+
+/* face t of direction FDIR (side-data order) */
+template <int DIM, int FDIR>
+HB2D_HD void diff_face_thread(const DiffGeom& G, const DiffPtrs& A, double dt, long long t)
+{
+    const int f0 = G.n[0] + (FDIR == 0), f1 = G.n[1] + (FDIR == 1);
+    const int i = (int)(t % f0), j = (int)((t / f0) % f1), k = (int)(t / ((long long)f0 * f1));
+    const long long x = (i + G.g[0]) + G.cs[1] * (j + G.g[1]) + G.cs[2] * (k + G.g[2]);
+    A.F[0][t] = 0.0;                             /* no diffusive mass flux: the fillAll(0) of the reference */
+#pragma unroll
+    for (int e = 1; e < DIM + 2; e++) A.F[e][t] = diff_reconstruct(A.Fn[e] + x, G.cs[FDIR], dt);
+}
+
+struct NsArgs {
+    DiffGeom G;       /* geometry of the STATE arrays: their ghost width need not be 6 */
+    int neq, ncoef;
+    double alpha[HB2_MAXS], beta[HB2_MAXS];
+    const double* U[HB2_MAXS][5];
+    const double* Fc[HB2_MAXS][15];
+    const double* Fd[HB2_MAXS][15];
+    const double* S[HB2_MAXS][5];
+    double* Uout[5];
+};
+
+/* NavierStokes::advanceSingleStepOnPatch, conservative diffusive form (NavierStokes.cpp:1715-1751, 2085-2092), interior
+ * cell t */
+template <int DIM>
+HB2D_HD void advance_ns_thread(const NsArgs& A, long long t)
+{
+    const DiffGeom& G = A.G;
+    const int i = (int)(t % G.n[0]), j = (int)((t / G.n[0]) % G.n[1]), k = (int)(t / ((long long)G.n[0] * G.n[1]));
+    const long long x = (i + G.g[0]) + G.cs[1] * (j + G.g[1]) + G.cs[2] * (k + G.g[2]);
+    const long long fxL = i + (long long)(G.n[0] + 1) * (j + (long long)G.n[1] * k), fxR = fxL + 1;
+    const long long fyB = i + (long long)G.n[0] * (j + (long long)(G.n[1] + 1) * k), fyT = fyB + G.n[0];
+    const long long fzB = t, fzF = t + (long long)G.n[0] * G.n[1];
+    for (int e = 0; e < A.neq; e++) {
+        double Q = 0.0;
+        for (int n = 0; n < A.ncoef; n++) {
+            if (A.alpha[n] != 0.0) Q += A.alpha[n] * A.U[n][e][x];
+            if (A.beta[n] != 0.0) {
+                const double *Fcx = A.Fc[n][e], *Fcy = A.Fc[n][A.neq + e], *Fdx = A.Fd[n][e], *Fdy = A.Fd[n][A.neq + e];
+                if (DIM == 2) {
+                    Q += A.beta[n] * (-(Fcx[fxR] - Fcx[fxL] + Fdx[fxR] - Fdx[fxL]) / G.dx[0] -
+                                      (Fcy[fyT] - Fcy[fyB] + Fdy[fyT] - Fdy[fyB]) / G.dx[1] + A.S[n][e][t]);
+                } else {
+                    const double *Fcz = A.Fc[n][2 * A.neq + e], *Fdz = A.Fd[n][2 * A.neq + e];
+                    Q += A.beta[n] * (-(Fcx[fxR] - Fcx[fxL] + Fdx[fxR] - Fdx[fxL]) / G.dx[0] -
+                                      (Fcy[fyT] - Fcy[fyB] + Fdy[fyT] - Fdy[fyB]) / G.dx[1] -
+                                      (Fcz[fzF] - Fcz[fzB] + Fdz[fzF] - Fdz[fzB]) / G.dx[2] + A.S[n][e][t]);
+                }
+            }
+        }
+        A.Uout[e][x] = Q;
+    }
+}
+
+inline void make_diff_geom(int dim, const int* n, const double* dx, int g, DiffGeom* G)
+{
+    G->dim = dim;
+    for (int a = 0; a < 3; a++) {
+        G->n[a] = (a < dim) ? n[a] : 1;
+        G->g[a] = (a < dim) ? g : 0;
+        G->gd[a] = G->n[a] + 2 * G->g[a];
+        G->dx[a] = (a < dim) ? dx[a] : 1.0;
+        G->dx_inv[a] = (a < dim) ? 1.0 / dx[a] : 0.0;
+    }
+    G->cs[0] = 1;
+    G->cs[1] = G->gd[0];
+    G->cs[2] = (long long)G->gd[0] * G->gd[1];
+    G->ncell_g = (long long)G->gd[0] * G->gd[1] * G->gd[2];
+}
+
+}  // namespace hb2

@@ -222,6 +222,50 @@ int hb2_probe_fp64_peak(int32_t device, double seconds_hint, double* flops_per_s
 /* device-to-device copy bandwidth, bytes read + written per second */
 int hb2_probe_hbm_bandwidth(int32_t device, int64_t bytes, double* bytes_per_s);
 
+/* ---- diffusive (viscous) flux of the single-species Navier-Stokes application -------------------
+ * Replaces DiffusiveFluxReconstructorNodeSixthOrder ("SIXTH_ORDER", the reconstructor of every shipped viscous deck):
+ *   src/flow/diffusive_flux_reconstructors/node/DiffusiveFluxReconstructorNode.cpp:31-1736 (computeDiffusiveFluxOnPatch)
+ *   src/flow/diffusive_flux_reconstructors/node/DiffusiveFluxReconstructorNodeSixthOrder.cpp:65-939 (kernels)
+ *   src/flow/flow_models/single-species/FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp:654-2363, 4031-4296
+ * with equation_of_shear_viscosity / equation_of_bulk_viscosity = "CONSTANT", equation_of_thermal_conductivity =
+ * "PRANDTL" and the ideal-gas temperature (what those decks select).  Cell data carries SIX ghost cells here
+ * (d_num_diff_ghosts, DiffusiveFluxReconstructorNodeSixthOrder.cpp:24), all of them filled by the caller. */
+#define HB2_DIFF_GHOSTS 6
+typedef struct {
+    int32_t dim;            /* 2 or 3 */
+    int32_t n[3];           /* interior cells of the patch */
+    double dx[3];
+    double species_gamma;   /* Equation_of_state_mixing_rules { species_gamma } */
+    double species_c_v;     /* R/(gamma - 1) with species_R of the same block */
+    double species_mu;      /* Equation_of_shear_viscosity_mixing_rules { species_mu } */
+    double species_mu_v;    /* Equation_of_bulk_viscosity_mixing_rules { species_mu_v } */
+    double species_c_p;     /* Equation_of_thermal_conductivity_mixing_rules { species_c_p, species_Pr } */
+    double species_Pr;
+    int32_t device;
+} hb2_diffusive_desc;
+typedef struct hb2_diff_plan_s* hb2_diff_plan_t;
+
+int hb2_diffusive_plan_create(const hb2_diffusive_desc* desc, hb2_diff_plan_t* plan);
+int hb2_diffusive_plan_destroy(hb2_diff_plan_t plan);
+int hb2_diffusive_plan_set_stream(hb2_diff_plan_t plan, void* cuda_stream);
+int hb2_diffusive_plan_launches(hb2_diff_plan_t plan, int64_t* launches);
+
+/* DiffusiveFluxReconstructor::computeDiffusiveFluxOnPatch
+ * (include/flow/diffusive_flux_reconstructors/DiffusiveFluxReconstructor.hpp; called from NavierStokes.cpp:1153-1160).
+ * Q: dim+2 conservative components on the ghost box of width 6 (device pointers).  flux[dir*num_eqn + e]: ghost-0 side
+ * arrays, fully overwritten, ALREADY multiplied by dt (the continuity rows are +0.0). */
+int hb2_compute_diffusive_flux_dev(hb2_diff_plan_t plan, const double* const* Q, double dt, double* const* flux);
+/* same with host pointers (H2D, kernels and D2H inside the call): the API-preserving seam */
+int hb2_compute_diffusive_flux_host(hb2_diff_plan_t plan, const double* const* Q_host, double dt, double* const* flux_host);
+
+/* NavierStokes::advanceSingleStepOnPatch with the conservative diffusive flux (NavierStokes.cpp:1715-1751, 2085-2092):
+ *   U_out = sum_m alpha[m] U_int[m] + beta[m] ( -(Fc_R - Fc_L + Fd_R - Fd_L)/dx_0 - ... + S[m] )
+ * U_int[m*num_eqn + e], U_out[e]: cell data with num_ghosts ghost cells; Fc_int / Fd_int[m*dim*num_eqn + dir*num_eqn + e],
+ * S_int[m*num_eqn + e]: ghost 0.  Rows with a zero coefficient may be NULL.  The ghosts of U_out are left untouched. */
+int hb2_advance_stage_ns_dev(hb2_diff_plan_t plan, int32_t num_ghosts, int32_t ncoef, const double* alpha, const double* beta,
+                             const double* const* U_int, const double* const* Fc_int, const double* const* Fd_int,
+                             const double* const* S_int, double* const* U_out);
+
 #ifdef __cplusplus
 }
 #endif

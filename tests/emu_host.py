@@ -82,3 +82,63 @@ def fused_stage(desc, alpha, beta, U_int, dt, math=0, bx=0, seg_len=0, push=Fals
                                     1 if push else 0)
     assert rc == 0
     return U_out
+
+
+# ---- diffusive-flux kernels (tests/host_emu/emu_diffusive.cpp) ----------------------------------------
+_DSO = os.path.join(_HERE, "host_emu", "libhb2_emu_diffusive.so")
+_DSRC = os.path.join(_HERE, "host_emu", "emu_diffusive.cpp")
+_DCORE = os.path.join(_HERE, "..", "hamers_b200", "csrc", "hb2_diffusive.cuh")
+_DLIB = None
+
+
+class EmuDiffDesc(C.Structure):
+    _fields_ = [("dim", C.c_int), ("n", C.c_int * 3), ("dx", C.c_double * 3), ("gamma", C.c_double), ("c_v", C.c_double),
+                ("mu", C.c_double), ("mu_v", C.c_double), ("c_p", C.c_double), ("Pr", C.c_double)]
+
+
+def dlib():
+    global _DLIB
+    if _DLIB is None:
+        stale = (not os.path.exists(_DSO)) or any(os.path.getmtime(s) > os.path.getmtime(_DSO) for s in (_DSRC, _DCORE))
+        if stale:
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                                   "-o", _DSO, _DSRC])
+        _DLIB = C.CDLL(_DSO)
+    return _DLIB
+
+
+def _ddesc(desc, tr):
+    d = EmuDiffDesc()
+    d.dim = desc.dim
+    for a in range(3):
+        d.n[a] = int(desc.n[a]) if a < desc.dim else 1
+        d.dx[a] = float(desc.dx[a]) if a < desc.dim else 1.0
+    d.gamma, d.c_v, d.mu, d.mu_v, d.c_p, d.Pr = desc.gamma[0], tr.c_v, tr.mu, tr.mu_v, tr.c_p, tr.Pr
+    return d
+
+
+def diffusive_flux(desc, tr, Q, dt):
+    neq, dim = desc.neq, desc.dim
+    F = [np.full((neq,) + desc.side_shape(a), np.nan) for a in range(dim)]
+    Q = np.ascontiguousarray(Q)
+    d = _ddesc(desc, tr)
+    rc = dlib().emu_diffusive_flux(C.byref(d), _pp([Q[c] for c in range(neq)]), C.c_double(dt),
+                                   _pp([F[a][e] for a in range(dim) for e in range(neq)]))
+    assert rc == 0
+    return F
+
+
+def advance_stage_ns(desc, tr, g, alpha, beta, U_int, Fc_int, Fd_int, S_int):
+    ncoef, neq, dim = len(alpha), desc.neq, desc.dim
+    U_out = np.full_like(np.ascontiguousarray(U_int[0]), np.nan)
+    U_int = [np.ascontiguousarray(u) for u in U_int]
+    d = _ddesc(desc, tr)
+    rc = dlib().emu_advance_stage_ns(
+        C.byref(d), C.c_int(g), C.c_int(ncoef), (C.c_double * ncoef)(*alpha), (C.c_double * ncoef)(*beta),
+        _pp([U_int[m][e] for m in range(ncoef) for e in range(neq)]),
+        _pp([Fc_int[m][a][e] if Fc_int[m] is not None else None for m in range(ncoef) for a in range(dim) for e in range(neq)]),
+        _pp([Fd_int[m][a][e] if Fd_int[m] is not None else None for m in range(ncoef) for a in range(dim) for e in range(neq)]),
+        _pp([S_int[m][e] if S_int[m] is not None else None for m in range(ncoef) for e in range(neq)]),
+        _pp([U_out[e] for e in range(neq)]))
+    assert rc == 0
+    return U_out

@@ -1,0 +1,86 @@
+/*
+ * emu_diffusive.cpp -- TEST-ONLY host emulation of the diffusive-flux kernels (never part of the product library).
+ *
+ * Compiles hamers_b200/csrc/hb2_diffusive.cuh with g++ and calls the very per-thread functions the kernels of
+ * hb2_diffusive.cu call (diff_primitives_thread, diff_node_thread, diff_face_thread, advance_ns_thread) from plain loops
+ * that stand in for the grid-stride loops.  Lets the CPU test suite check indexing and arithmetic against the oracle in a
+ * container without a GPU; the GPU parity tests (pytest -m gpu) remain the parity tests proper.
+ */
+#include "../../hamers_b200/csrc/hb2_diffusive.cuh"
+#include <cmath>
+#include <limits>
+#include <vector>
+
+using namespace hb2;
+
+struct EmuDiffDesc {
+    int dim, n[3];
+    double dx[3];
+    double gamma, c_v, mu, mu_v, c_p, Pr;
+};
+
+template <int DIM, int FDIR>
+static void run_dir(const DiffGeom& G, const DiffConsts& K, DiffPtrs& A, double dt, double* const* F)
+{
+    for (int e = 0; e < DIM + 2; e++) A.F[e] = F[FDIR * (DIM + 2) + e];
+    for (long long t = 0; t < diff_node_count<DIM, FDIR>(G); t++) diff_node_thread<DIM, FDIR>(G, K, A, t);
+    for (long long t = 0; t < diff_face_count<DIM, FDIR>(G); t++) diff_face_thread<DIM, FDIR>(G, A, dt, t);
+}
+
+template <int DIM>
+static int run(const EmuDiffDesc* d, const double* const* Q, double dt, double* const* F)
+{
+    DiffGeom G;
+    make_diff_geom(d->dim, d->n, d->dx, HB2_DIFF_G, &G);
+    DiffConsts K{d->gamma, d->c_v, d->mu, d->mu_v, d->c_p * d->mu / d->Pr};
+    /* scratch starts as NaN: a node or primitive the kernels read without having written it shows up in the output */
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    std::vector<std::vector<double>> P(DIM + 1, std::vector<double>((size_t)G.ncell_g, nan));
+    std::vector<std::vector<double>> Fn(DIM + 2, std::vector<double>((size_t)G.ncell_g, nan));
+    DiffPtrs A{};
+    for (int c = 0; c < DIM + 2; c++) A.Q[c] = Q[c];
+    for (int v = 0; v < DIM + 1; v++) A.P[v] = P[v].data();
+    for (int e = 0; e < DIM + 2; e++) A.Fn[e] = Fn[e].data();
+    for (long long x = 0; x < G.ncell_g; x++) diff_primitives_thread<DIM>(K, A, x);
+    run_dir<DIM, 0>(G, K, A, dt, F);
+    run_dir<DIM, 1>(G, K, A, dt, F);
+    if (DIM == 3) run_dir<DIM, (DIM == 3 ? 2 : 1)>(G, K, A, dt, F);
+    return 0;
+}
+
+extern "C" int emu_diffusive_flux(const EmuDiffDesc* d, const double* const* Q, double dt, double* const* F)
+{
+    return d->dim == 2 ? run<2>(d, Q, dt, F) : run<3>(d, Q, dt, F);
+}
+
+extern "C" int emu_advance_stage_ns(const EmuDiffDesc* d, int g, int ncoef, const double* alpha, const double* beta,
+                                    const double* const* U_int, const double* const* Fc_int, const double* const* Fd_int,
+                                    const double* const* S_int, double* const* U_out)
+{
+    const int dim = d->dim, neq = dim + 2;
+    NsArgs A{};
+    make_diff_geom(dim, d->n, d->dx, g, &A.G);
+    A.neq = neq;
+    A.ncoef = ncoef;
+    for (int m = 0; m < ncoef; m++) {
+        A.alpha[m] = alpha[m];
+        A.beta[m] = beta[m];
+        for (int e = 0; e < neq; e++) {
+            A.U[m][e] = U_int[m * neq + e];
+            A.S[m][e] = S_int[m * neq + e];
+        }
+        for (int f = 0; f < dim * neq; f++) {
+            A.Fc[m][f] = Fc_int[m * dim * neq + f];
+            A.Fd[m][f] = Fd_int[m * dim * neq + f];
+        }
+    }
+    for (int e = 0; e < neq; e++) A.Uout[e] = U_out[e];
+    const long long total = (long long)A.G.n[0] * A.G.n[1] * A.G.n[2];
+    for (long long t = 0; t < total; t++) {
+        if (dim == 2)
+            advance_ns_thread<2>(A, t);
+        else
+            advance_ns_thread<3>(A, t);
+    }
+    return 0;
+}

@@ -79,6 +79,9 @@ def test_no_cpu_fallback_without_a_device(product_lib):
     with pytest.raises(abi.HamersB200Error) as ei:
         abi.Plan(3, (8, 8, 8))
     assert "no CPU fallback" in str(ei.value)
+    with pytest.raises(abi.HamersB200Error) as ei:
+        abi.DiffusivePlan(3, (8, 8, 8), (0.1, 0.1, 0.1), 1.4, 2.5, 0.05, 0.0, 3.5, 0.72)
+    assert "no CPU fallback" in str(ei.value)
 
 
 def test_product_never_imports_the_oracle():

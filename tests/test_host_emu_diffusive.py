@@ -1,0 +1,74 @@
+"""Host emulation of the diffusive-flux kernels against the oracle: the per-thread functions of
+hamers_b200/csrc/hb2_diffusive.cuh, compiled with g++ and driven by plain loops, must be bit-identical to
+oracle/oracle_diffusive.c (reference operation order, no FMA contraction on either side)."""
+import numpy as np
+import pytest
+
+import emu_host
+from hamers_b200 import problems as pb
+from oracle import oracle as orc
+
+TR = orc.Transport(mu=0.05, mu_v=0.02, c_p=3.5, c_v=2.5, Pr=0.72)
+
+
+def state(dim, N, seed=5):
+    U, dx, gam = pb.random_state(dim, N, seed=seed, shock=True)
+    return orc.PatchDesc(dim=dim, n=N, gamma=gam, dx=dx), U
+
+
+@pytest.mark.parametrize("dim,N", [(2, (24, 17)), (3, (13, 10, 12)), (2, (1, 1)), (3, (1, 2, 1)), (3, (7, 1, 3)), (2, (6, 40))])
+def test_emulated_diffusive_flux_is_bit_identical(dim, N):
+    desc, U = state(dim, N)
+    Q = pb.pad_periodic(U, orc.GD)
+    dt = 1.0e-3
+    Fo = orc.compute_diffusive_flux(desc, TR, Q, dt)
+    Fe = emu_host.diffusive_flux(desc, TR, Q, dt)
+    for a in range(dim):
+        assert not np.isnan(Fe[a]).any()
+        assert np.array_equal(Fe[a], Fo[a]), f"dir {a}"
+        assert not Fo[a][0].any() and not np.signbit(Fe[a][0]).any()        # +0.0 mass flux
+        assert min(N) < 3 or np.abs(Fo[a][1:]).max() > 0.0
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_emulated_kernels_read_only_what_they_were_given(dim):
+    """Ghost cells outside the stencil footprint (the corners beyond 3 cells in two directions at once are still needed:
+    d/dy at x-ghost nodes) -- poisoning the layers the reference never reads must not change the result, poisoning one it
+    reads must."""
+    N = (9, 8, 7)[:dim]
+    desc, U = state(dim, N)
+    Q = pb.pad_periodic(U, orc.GD)
+    F0 = emu_host.diffusive_flux(desc, TR, Q, 1.0e-3)
+    Qp = Q.copy()
+    g = orc.GD
+    # a cell 4 deep in the x-ghosts AND 4 deep in the y-ghosts is outside every stencil (footprint: <= 3 in the second direction)
+    idx = (slice(None),) + (slice(None),) * (dim - 2) + (g - 4, g - 4)
+    Qp[idx] = 1.0e30
+    F1 = emu_host.diffusive_flux(desc, TR, Qp, 1.0e-3)
+    assert all(np.array_equal(a, b) for a, b in zip(F0, F1))
+    Qp = Q.copy()
+    idx = (1,) + (slice(None),) * (dim - 2) + (g - 3, g - 3)        # x momentum only: scaling every component keeps u and T
+    Qp[idx] *= 1.5
+    F2 = emu_host.diffusive_flux(desc, TR, Qp, 1.0e-3)
+    assert any(not np.array_equal(a, b) for a, b in zip(F0, F2))
+
+
+@pytest.mark.parametrize("dim,g", [(2, 6), (3, 6), (3, 4)])
+def test_emulated_ns_stage_is_bit_identical(dim, g):
+    rng = np.random.default_rng(11)
+    N = (6, 5, 4)[:dim]
+    desc = orc.PatchDesc(dim=dim, n=N, gamma=(1.4,), dx=(0.1, 0.2, 0.3)[:dim])
+    neq = desc.neq
+    shape = tuple(n + 2 * g for n in reversed(N))
+    for alpha, beta in (([1.0], [1.0]), ([0.75, 0.25], [0.0, 0.25]), ([1.0 / 3.0, 0.0, 2.0 / 3.0], [0.0, 0.0, 2.0 / 3.0])):
+        nc = len(alpha)
+        U = [rng.standard_normal((neq,) + shape) for _ in range(nc)]
+        Fc = [[rng.standard_normal((neq,) + desc.side_shape(a)) for a in range(dim)] for _ in range(nc)]
+        Fd = [[rng.standard_normal((neq,) + desc.side_shape(a)) for a in range(dim)] for _ in range(nc)]
+        S = [rng.standard_normal((neq,) + desc.cell_shape) for _ in range(nc)]
+        Uo = orc.advance_stage_ns(desc, g, alpha, beta, U, Fc, Fd, S)
+        Ue = emu_host.advance_stage_ns(desc, TR, g, alpha, beta, U, Fc, Fd, S)
+        inner = (slice(None),) + (slice(g, -g),) * dim
+        assert np.array_equal(Ue[inner], Uo[inner])
+        Ue[inner] = np.nan
+        assert np.isnan(Ue).all()                    # the kernel leaves the ghosts alone

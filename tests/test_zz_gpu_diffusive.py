@@ -1,0 +1,107 @@
+"""SURVEY row f4, GPU parity through the C ABI: the node-based sixth-order diffusive flux and the Navier-Stokes stage
+update against the CPU oracle (oracle/oracle_diffusive.c) -- bit-identical (the diffusive unit is built with
+-fmad=false and keeps the reference's operation order).  Written after the last GPU run of round 1: the same per-thread
+functions pass tests/test_host_emu_diffusive.py on the CPU; this file is the parity test proper."""
+import numpy as np
+import pytest
+
+from hamers_b200 import problems as pb
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TR = orc.Transport(mu=0.05, mu_v=0.02, c_p=3.5, c_v=2.5, Pr=0.72)
+
+
+def _plan(desc):
+    from hamers_b200 import abi
+
+    return abi.DiffusivePlan(desc.dim, desc.n, desc.dx, desc.gamma[0], TR.c_v, TR.mu, TR.mu_v, TR.c_p, TR.Pr).use_torch_stream()
+
+
+def _state(dim, N, seed=5):
+    U, dx, gam = pb.random_state(dim, N, seed=seed, shock=True)
+    return orc.PatchDesc(dim=dim, n=N, gamma=gam, dx=dx), U
+
+
+@pytest.mark.parametrize("dim,N", [(2, (24, 17)), (3, (13, 10, 12)), (2, (1, 1)), (3, (7, 1, 3)), (3, (64, 48, 40)), (2, (300, 200))])
+def test_diffusive_flux_device_and_host_entry_points(dim, N, product_lib):
+    import torch
+
+    desc, U = _state(dim, N)
+    Q = pb.pad_periodic(U, orc.GD)
+    dt = 1.0e-3
+    Fo = orc.compute_diffusive_flux(desc, TR, Q, dt)
+    plan = _plan(desc)
+    Qd = torch.from_numpy(Q).cuda()
+    Fd = [torch.full((desc.neq,) + desc.side_shape(a), float("nan"), dtype=torch.float64, device="cuda") for a in range(dim)]
+    plan.compute_diffusive_flux(Qd, dt, Fd)
+    torch.cuda.synchronize()
+    for a in range(dim):
+        assert np.array_equal(Fd[a].cpu().numpy(), Fo[a]), f"dir {a}"
+    assert plan.launch_count == 1 + 2 * dim
+    Fh = plan.compute_diffusive_flux_host(Q, dt)
+    for a in range(dim):
+        assert np.array_equal(Fh[a], Fo[a]), f"host entry point, dir {a}"
+    plan.close()
+
+
+@pytest.mark.parametrize("dim,g", [(2, 6), (3, 6), (3, 4)])
+def test_ns_stage_update(dim, g, product_lib):
+    import torch
+
+    rng = np.random.default_rng(11)
+    N = (33, 20, 9)[:dim]
+    desc = orc.PatchDesc(dim=dim, n=N, gamma=(1.4,), dx=(0.1, 0.2, 0.3)[:dim])
+    neq = desc.neq
+    shape = tuple(n + 2 * g for n in reversed(N))
+    plan = _plan(desc)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()        # noqa: E731
+    for alpha, beta in (([1.0], [1.0]), ([0.75, 0.25], [0.0, 0.25]), ([1.0 / 3.0, 0.0, 2.0 / 3.0], [0.0, 0.0, 2.0 / 3.0])):
+        nc = len(alpha)
+        U = [rng.standard_normal((neq,) + shape) for _ in range(nc)]
+        Fc = [[rng.standard_normal((neq,) + desc.side_shape(a)) for a in range(dim)] for _ in range(nc)]
+        Fd = [[rng.standard_normal((neq,) + desc.side_shape(a)) for a in range(dim)] for _ in range(nc)]
+        S = [rng.standard_normal((neq,) + desc.cell_shape) for _ in range(nc)]
+        Uo = orc.advance_stage_ns(desc, g, alpha, beta, U, Fc, Fd, S)
+        out = torch.full((neq,) + shape, float("nan"), dtype=torch.float64, device="cuda")
+        plan.advance_stage_ns(g, alpha, beta, [dev(u) for u in U], [[dev(f) for f in Fm] for Fm in Fc],
+                              [[dev(f) for f in Fm] for Fm in Fd], [dev(s) for s in S], out)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        inner = (slice(None),) + (slice(g, -g),) * dim
+        assert np.array_equal(got[inner], Uo[inner])
+        got[inner] = np.nan
+        assert np.isnan(got).all()
+    plan.close()
+
+
+def test_viscous_stage_from_both_reconstructors(product_lib):
+    """One forward-Euler Navier-Stokes stage assembled like NavierStokes::computeFluxesAndSourcesOnPatch +
+    advanceSingleStepOnPatch: convective flux from the WCNS5-JS / HLLC-HLL plan (ghost 4 view of the state), diffusive
+    flux from the sixth-order plan (ghost 6), combined by hb2_advance_stage_ns_dev; against the oracle's same assembly."""
+    import torch
+    from hamers_b200 import abi
+
+    N = (20, 16, 12)
+    desc, U = _state(3, N)
+    dt = 2.0e-4
+    Q6, Q4 = pb.pad_periodic(U, 6), pb.pad_periodic(U, 4)
+    Fc_o, S_o = orc.compute_flux_and_source(desc, Q4, dt)
+    Fd_o = orc.compute_diffusive_flux(desc, TR, Q6, dt)
+    Uo = orc.advance_stage_ns(desc, 6, [1.0], [1.0], [Q6], [Fc_o], [Fd_o], [S_o])
+    cplan = abi.Plan(3, N, species_gamma=desc.gamma, dx=desc.dx, math=abi.MATH_EXACT).use_torch_stream()
+    dplan = _plan(desc)
+    Q6d, Q4d = torch.from_numpy(Q6).cuda(), torch.from_numpy(Q4).cuda()
+    Fc = [torch.zeros((5,) + desc.side_shape(a), dtype=torch.float64, device="cuda") for a in range(3)]
+    Fd = [torch.zeros((5,) + desc.side_shape(a), dtype=torch.float64, device="cuda") for a in range(3)]
+    S = torch.zeros((5,) + desc.cell_shape, dtype=torch.float64, device="cuda")
+    cplan.compute_flux_and_source(Q4d, dt, Fc, S)
+    dplan.compute_diffusive_flux(Q6d, dt, Fd)
+    out = torch.zeros_like(Q6d)
+    dplan.advance_stage_ns(6, [1.0], [1.0], [Q6d], [Fc], [Fd], [S], out)
+    torch.cuda.synchronize()
+    inner = (slice(None),) + (slice(6, -6),) * 3
+    assert np.array_equal(out.cpu().numpy()[inner], Uo[inner])
+    cplan.close()
+    dplan.close()
