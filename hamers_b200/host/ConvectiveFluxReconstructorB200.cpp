@@ -8,7 +8,7 @@
 
 FlowModel::FlowModel(const std::string& object_name, const tbox::Dimension& dim, const FLOW_MODEL::TYPE& type, int num_species,
                      const HAMERS_SHARED_PTR<tbox::Database>& flow_model_db)
-    : d_object_name(object_name), d_dim(dim), d_type(type), d_num_species(num_species), d_num_eqn(0)
+    : d_object_name(object_name), d_dim(dim), d_type(type), d_num_species(num_species), d_num_eqn(0), d_flow_model_db(flow_model_db)
 {
     const int d = dim.getValue();
     /* Flow_model { Equation_of_state_mixing_rules { species_gamma = ... } } */

@@ -50,6 +50,8 @@ public:
     const std::vector<HAMERS_SHARED_PTR<pdat::CellVariable<double> > >& getConservativeVariables() const { return d_cons; }
     /* number of stored components (the five-eqn model stores all ns volume fractions) */
     int getNumberOfStoredComponents() const;
+    /* the Flow_model input block (equation of state and transport mixing-rule keys) */
+    const HAMERS_SHARED_PTR<tbox::Database>& getFlowModelDatabase() const { return d_flow_model_db; }
 
 private:
     std::string d_object_name;
@@ -58,6 +60,7 @@ private:
     int d_num_species, d_num_eqn;
     std::vector<double> d_species_gamma;
     std::vector<HAMERS_SHARED_PTR<pdat::CellVariable<double> > > d_cons;
+    HAMERS_SHARED_PTR<tbox::Database> d_flow_model_db;
 };
 
 class ConvectiveFluxReconstructor {

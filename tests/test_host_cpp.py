@@ -34,6 +34,73 @@ def test_host_classes_compile_and_link(product_lib):
     assert os.path.exists(build_driver())
 
 
+# ---- DiffusiveFluxReconstructorNodeSixthOrder_B200 ----------------------------------------------------
+DEXE = os.path.join(ROOT, "tests", "host_cpp", "test_diffusive")
+TRANSPORT = dict(R=1.0, mu=0.05, mu_v=0.02, c_p=3.5, Pr=0.72)
+
+
+def build_diffusive_driver():
+    srcs = [os.path.join(ROOT, "tests", "host_cpp", "test_diffusive.cpp"), os.path.join(HOST, "DiffusiveFluxReconstructorB200.cpp"),
+            os.path.join(HOST, "ConvectiveFluxReconstructorB200.cpp")]
+    deps = srcs + [os.path.join(HOST, "DiffusiveFluxReconstructorB200.hpp"), os.path.join(HOST, "ConvectiveFluxReconstructorB200.hpp"),
+                   os.path.join(HOST, "samrai_shim.hpp"), os.path.join(ROOT, "include", "hamers_b200.h")]
+    if os.path.exists(DEXE) and all(os.path.getmtime(d) <= os.path.getmtime(DEXE) for d in deps):
+        return DEXE
+    libdir = os.path.join(ROOT, "hamers_b200")
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-Wall", "-Wextra", "-Werror", "-o", DEXE] + srcs +
+                          ["-L", libdir, "-lhamers_b200", "-Wl,-rpath," + libdir])
+    return DEXE
+
+
+def run_diffusive_driver(tmp_path, dim, N, U6, dx, gamma, dt):
+    fin, fout = str(tmp_path / "din.bin"), str(tmp_path / "dout.bin")
+    with open(fin, "wb") as fh:
+        fh.write(struct.pack("4i", dim, *(list(N) + [1] * (3 - dim))))
+        t = TRANSPORT
+        fh.write(struct.pack("10d", gamma, t["R"], t["mu"], t["mu_v"], t["c_p"], t["Pr"], *(list(dx) + [1.0] * (3 - dim)), dt))
+        fh.write(np.ascontiguousarray(U6).tobytes())
+    return subprocess.run([build_diffusive_driver(), fin, fout], capture_output=True, text=True), fout
+
+
+def test_diffusive_host_class_compiles_links_and_refuses_to_run_without_a_device(product_lib, tmp_path):
+    """-std=c++11 -Werror against the SAMRAI shim; without a CUDA device the class surfaces the library's message through
+    TBOX_ERROR (no CPU fallback)."""
+    import ctypes
+
+    n = ctypes.c_int32()
+    product_lib.hb2_device_count(ctypes.byref(n))
+    U, dx, gam = pb.random_state(3, (6, 5, 4), seed=1, shock=False)
+    r, _ = run_diffusive_driver(tmp_path, 3, (6, 5, 4), pb.pad_periodic(U, 6), dx, gam[0], 1.0e-3)
+    assert "Print DiffusiveFluxReconstructorNodeSixthOrder_B200 object" in r.stdout
+    if n.value == 0:
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr, r.stdout + r.stderr
+    else:
+        assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,N", [(2, (24, 17)), (3, (13, 10, 12))])
+def test_diffusive_reconstructor_class_matches_oracle(dim, N, tmp_path):
+    from oracle import oracle as orc
+
+    U, dx, gam = pb.random_state(dim, N, seed=5, shock=True)
+    Q = pb.pad_periodic(U, 6)
+    dt = 7.5e-4
+    r, fout = run_diffusive_driver(tmp_path, dim, N, Q, dx, gam[0], dt)
+    assert r.returncode == 0, r.stdout + r.stderr
+    desc = orc.PatchDesc(dim=dim, n=N, gamma=gam, dx=dx)
+    t = TRANSPORT
+    tr = orc.Transport(mu=t["mu"], mu_v=t["mu_v"], c_p=t["c_p"], c_v=1.0 / (gam[0] - 1.0) * t["R"], Pr=t["Pr"])
+    Fo = orc.compute_diffusive_flux(desc, tr, Q, dt)
+    out = np.fromfile(fout)
+    pos = 0
+    for a in range(dim):
+        k = Fo[a].size
+        assert np.array_equal(out[pos:pos + k].reshape(Fo[a].shape), Fo[a]), f"dir {a}"
+        pos += k
+    assert pos == out.size
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("math", [0, 1, 10, 20])
 @pytest.mark.parametrize("name", list(CASES))
