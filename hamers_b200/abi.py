@@ -382,7 +382,7 @@ class DiffusivePlan:
     that consumes its flux.  State arrays here carry SIX ghost cells: (dim + 2, [nz+12,] ny+12, nx+12)."""
 
     def __init__(self, dim: int, n: Sequence[int], dx: Sequence[float], species_gamma: float, species_c_v: float,
-                 species_mu: float, species_mu_v: float, species_c_p: float, species_Pr: float, device: int = 0):
+                 species_mu: float, species_mu_v: float, species_c_p: float, species_Pr: float, device: int = -1):
         self.lib = load_library()
         d = DiffusiveDescC()
         d.dim = dim

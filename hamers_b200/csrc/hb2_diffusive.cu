@@ -140,6 +140,11 @@ int hb2_diffusive_plan_create(const hb2_diffusive_desc* d, hb2_diff_plan_t* out)
     hb2_diff_plan_t p = new hb2_diff_plan_s();
     p->d = *d;
     p->device = d->device;
+    if (p->device < 0) HB2D_CUDA(cudaGetDevice(&p->device));      /* -1: the calling thread's current device */
+    if (p->device >= ndev) {
+        delete p;
+        return set_error(-21, "device index out of range");
+    }
     HB2D_CUDA(cudaSetDevice(p->device));
     cudaDeviceProp prop;
     HB2D_CUDA(cudaGetDeviceProperties(&prop, p->device));

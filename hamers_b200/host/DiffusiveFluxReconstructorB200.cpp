@@ -85,7 +85,7 @@ hb2_diff_plan_t DiffusiveFluxReconstructorNodeSixthOrder_B200::getPlan(const hie
     desc.species_mu_v = d_species_mu_v;
     desc.species_c_p = d_species_c_p;
     desc.species_Pr = d_species_Pr;
-    desc.device = 0;
+    desc.device = -1;
     hb2_diff_plan_t plan = 0;
     if (hb2_diffusive_plan_create(&desc, &plan) != 0) TBOX_ERROR(d_object_name << ": " << hb2_last_error() << std::endl);
     d_plans[key] = plan;

@@ -241,7 +241,7 @@ typedef struct {
     double species_mu_v;    /* Equation_of_bulk_viscosity_mixing_rules { species_mu_v } */
     double species_c_p;     /* Equation_of_thermal_conductivity_mixing_rules { species_c_p, species_Pr } */
     double species_Pr;
-    int32_t device;
+    int32_t device;         /* CUDA device index; -1 = the calling thread's current device */
 } hb2_diffusive_desc;
 typedef struct hb2_diff_plan_s* hb2_diff_plan_t;
 
