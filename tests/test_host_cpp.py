@@ -79,29 +79,6 @@ def test_diffusive_host_class_compiles_links_and_refuses_to_run_without_a_device
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dim,N", [(2, (24, 17)), (3, (13, 10, 12))])
-def test_diffusive_reconstructor_class_matches_oracle(dim, N, tmp_path):
-    from oracle import oracle as orc
-
-    U, dx, gam = pb.random_state(dim, N, seed=5, shock=True)
-    Q = pb.pad_periodic(U, 6)
-    dt = 7.5e-4
-    r, fout = run_diffusive_driver(tmp_path, dim, N, Q, dx, gam[0], dt)
-    assert r.returncode == 0, r.stdout + r.stderr
-    desc = orc.PatchDesc(dim=dim, n=N, gamma=gam, dx=dx)
-    t = TRANSPORT
-    tr = orc.Transport(mu=t["mu"], mu_v=t["mu_v"], c_p=t["c_p"], c_v=1.0 / (gam[0] - 1.0) * t["R"], Pr=t["Pr"])
-    Fo = orc.compute_diffusive_flux(desc, tr, Q, dt)
-    out = np.fromfile(fout)
-    pos = 0
-    for a in range(dim):
-        k = Fo[a].size
-        assert np.array_equal(out[pos:pos + k].reshape(Fo[a].shape), Fo[a]), f"dir {a}"
-        pos += k
-    assert pos == out.size
-
-
-@pytest.mark.gpu
 @pytest.mark.parametrize("math", [0, 1, 10, 20])
 @pytest.mark.parametrize("name", list(CASES))
 def test_reconstructor_class_matches_oracle(name, math, oracle_lib, tmp_path):

@@ -105,3 +105,27 @@ def test_viscous_stage_from_both_reconstructors(product_lib):
     assert np.array_equal(out.cpu().numpy()[inner], Uo[inner])
     cplan.close()
     dplan.close()
+
+
+@pytest.mark.parametrize("dim,N", [(2, (24, 17)), (3, (13, 10, 12))])
+def test_diffusive_reconstructor_class_matches_oracle(dim, N, tmp_path, product_lib):
+    """DiffusiveFluxReconstructorNodeSixthOrder_B200 driven like NavierStokes::computeFluxesAndSourcesOnPatch does
+    (tests/host_cpp/test_diffusive.cpp), host buffers, against the oracle."""
+    from test_host_cpp import TRANSPORT, run_diffusive_driver
+
+    U, dx, gam = pb.random_state(dim, N, seed=5, shock=True)
+    Q = pb.pad_periodic(U, 6)
+    dt = 7.5e-4
+    r, fout = run_diffusive_driver(tmp_path, dim, N, Q, dx, gam[0], dt)
+    assert r.returncode == 0, r.stdout + r.stderr
+    desc = orc.PatchDesc(dim=dim, n=N, gamma=gam, dx=dx)
+    t = TRANSPORT
+    tr = orc.Transport(mu=t["mu"], mu_v=t["mu_v"], c_p=t["c_p"], c_v=1.0 / (gam[0] - 1.0) * t["R"], Pr=t["Pr"])
+    Fo = orc.compute_diffusive_flux(desc, tr, Q, dt)
+    out = np.fromfile(fout)
+    pos = 0
+    for a in range(dim):
+        k = Fo[a].size
+        assert np.array_equal(out[pos:pos + k].reshape(Fo[a].shape), Fo[a]), f"dir {a}"
+        pos += k
+    assert pos == out.size
