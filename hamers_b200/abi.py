@@ -36,6 +36,7 @@ SYMBOLS = [
     # diffusive flux of the single-species Navier-Stokes application
     "hb2_diffusive_plan_create", "hb2_diffusive_plan_destroy", "hb2_diffusive_plan_set_stream", "hb2_diffusive_plan_launches",
     "hb2_compute_diffusive_flux_dev", "hb2_compute_diffusive_flux_host", "hb2_advance_stage_ns_dev",
+    "hb2_diffusive_fill_ghosts_periodic_dev", "hb2_diffusive_extract_view_dev",
 ]
 
 WCNS5_JS, WCNS5_Z, WCNS6_LD = 0, 1, 2
@@ -435,6 +436,17 @@ class DiffusivePlan:
         fp = _ptr_table([p for d in range(self.dim) for p in _host_ptrs(flux[d], self.neq)])
         _check(self.lib.hb2_compute_diffusive_flux_host(self._h, qp, C.c_double(dt), fp), "hb2_compute_diffusive_flux_host")
         return flux
+
+    def fill_ghosts_periodic(self, U, mask: int = 7):
+        """Periodic same-level ghost fill of a six-ghost state tensor (neq, *ghost_shape), in place."""
+        _check(self.lib.hb2_diffusive_fill_ghosts_periodic_dev(self._h, _ptr_table(_dev_ptrs(U, self.neq)), int(mask)),
+               "hb2_diffusive_fill_ghosts_periodic_dev")
+
+    def extract_view(self, U, num_ghosts: int, U_view):
+        """Copy the num_ghosts-wide ghost box of the six-ghost state U into U_view (neq, n + 2 num_ghosts ...)."""
+        _check(self.lib.hb2_diffusive_extract_view_dev(self._h, _ptr_table(_dev_ptrs(U, self.neq)), int(num_ghosts),
+                                                       _ptr_table(_dev_ptrs(U_view, self.neq))),
+               "hb2_diffusive_extract_view_dev")
 
     def advance_stage_ns(self, num_ghosts: int, alpha, beta, U_int, Fc_int, Fd_int, S_int, U_out):
         """NavierStokes::advanceSingleStepOnPatch (conservative diffusive flux) on device tensors; rows with a zero

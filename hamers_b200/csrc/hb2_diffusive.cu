@@ -83,6 +83,22 @@ __global__ void __launch_bounds__(256) k_advance_ns(const __grid_constant__ NsAr
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) advance_ns_thread<DIM>(A, t);
 }
 
+__global__ void __launch_bounds__(256) k_diff_fill_periodic(const __grid_constant__ DiffGeom G, const __grid_constant__ DiffStatePtrs A,
+                                                            int ncomp, int mask)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < G.ncell_g; t += stride)
+        diff_fill_periodic_thread(G, A, ncomp, mask, t);
+}
+
+__global__ void __launch_bounds__(256) k_diff_extract_view(const __grid_constant__ DiffGeom Gs, const __grid_constant__ DiffGeom Gd,
+                                                           const __grid_constant__ DiffStatePtrs A, int ncomp)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < Gd.ncell_g; t += stride)
+        diff_extract_view_thread(Gs, Gd, A, ncomp, t);
+}
+
 int grid_for(long long work, int sm_count)
 {
     const long long blocks = (work + 255) / 256;
@@ -233,6 +249,36 @@ int hb2_compute_diffusive_flux_host(hb2_diff_plan_t p, const double* const* Q_ho
             HB2D_CUDA(cudaMemcpyAsync(flux_host[f * neq + e], Fd[f * neq + e], sizeof(double) * (size_t)p->nside[f],
                                       cudaMemcpyDeviceToHost, p->stream));
     HB2D_CUDA(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int hb2_diffusive_fill_ghosts_periodic_dev(hb2_diff_plan_t p, double* const* U, int32_t periodic_mask)
+{
+    if (!p || !U) return set_error(-1, "null argument");
+    HB2D_CUDA(cudaSetDevice(p->device));
+    DiffStatePtrs A{};
+    for (int c = 0; c < p->neq; c++) A.U[c] = U[c];
+    k_diff_fill_periodic<<<grid_for(p->G.ncell_g, p->sm_count), 256, 0, p->stream>>>(p->G, A, p->neq, periodic_mask);
+    p->launches++;
+    HB2D_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int hb2_diffusive_extract_view_dev(hb2_diff_plan_t p, const double* const* U, int32_t num_ghosts, double* const* U_view)
+{
+    if (!p || !U || !U_view) return set_error(-1, "null argument");
+    if (num_ghosts < 0 || num_ghosts > HB2_DIFF_G) return set_error(-31, "num_ghosts must be in 0..6");
+    HB2D_CUDA(cudaSetDevice(p->device));
+    DiffGeom Gd;
+    make_diff_geom(p->d.dim, p->d.n, p->d.dx, num_ghosts, &Gd);
+    DiffStatePtrs A{};
+    for (int c = 0; c < p->neq; c++) {
+        A.src[c] = U[c];
+        A.U[c] = U_view[c];
+    }
+    k_diff_extract_view<<<grid_for(Gd.ncell_g, p->sm_count), 256, 0, p->stream>>>(p->G, Gd, A, p->neq);
+    p->launches++;
+    HB2D_CUDA(cudaGetLastError());
     return 0;
 }
 

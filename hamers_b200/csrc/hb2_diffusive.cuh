@@ -332,6 +332,44 @@ HB2D_HD void advance_ns_thread(const NsArgs& A, long long t)
     }
 }
 
+/* ---- state management of a six-ghost level (what xfer::RefineSchedule::fillData does for a periodic single-patch level,
+ * and the four-ghost view the convective reconstructor reads) ---- */
+struct DiffStatePtrs {
+    double* U[5];
+    const double* src[5];
+};
+
+HB2D_HD int diff_wrap(int i, int n)
+{
+    int r = i % n;
+    return r < 0 ? r + n : r;
+}
+
+/* ghost-box cell t of G: ghost cells take the value of their periodic image in the interior; interior cells are left
+ * alone.  Directions whose bit is not set in `mask` are left alone too. */
+HB2D_HD void diff_fill_periodic_thread(const DiffGeom& G, const DiffStatePtrs& A, int ncomp, int mask, long long t)
+{
+    const int i = (int)(t % G.gd[0]) - G.g[0];
+    const int j = (int)((t / G.gd[0]) % G.gd[1]) - G.g[1];
+    const int k = (int)(t / ((long long)G.gd[0] * G.gd[1])) - G.g[2];
+    const bool in0 = i >= 0 && i < G.n[0], in1 = j >= 0 && j < G.n[1], in2 = k >= 0 && k < G.n[2];
+    if (in0 && in1 && in2) return;
+    if ((!in0 && !(mask & 1)) || (!in1 && !(mask & 2)) || (!in2 && !(mask & 4))) return;
+    const long long s = (diff_wrap(i, G.n[0]) + G.g[0]) + G.cs[1] * (diff_wrap(j, G.n[1]) + G.g[1]) +
+                        G.cs[2] * (diff_wrap(k, G.n[2]) + G.g[2]);
+    for (int c = 0; c < ncomp; c++) A.U[c][t] = A.U[c][s];
+}
+
+/* cell t of the ghost box of Gd (fewer ghosts) copied from the same cell of the ghost box of Gs */
+HB2D_HD void diff_extract_view_thread(const DiffGeom& Gs, const DiffGeom& Gd, const DiffStatePtrs& A, int ncomp, long long t)
+{
+    const int i = (int)(t % Gd.gd[0]) - Gd.g[0];
+    const int j = (int)((t / Gd.gd[0]) % Gd.gd[1]) - Gd.g[1];
+    const int k = (int)(t / ((long long)Gd.gd[0] * Gd.gd[1])) - Gd.g[2];
+    const long long s = (i + Gs.g[0]) + Gs.cs[1] * (j + Gs.g[1]) + Gs.cs[2] * (k + Gs.g[2]);
+    for (int c = 0; c < ncomp; c++) A.U[c][t] = A.src[c][s];
+}
+
 inline void make_diff_geom(int dim, const int* n, const double* dx, int g, DiffGeom* G)
 {
     G->dim = dim;

@@ -1,0 +1,98 @@
+"""GPU-resident periodic uniform level of the single-species Navier-Stokes application.
+
+One SSP-RK3 step is three passes of `RungeKuttaLevelIntegrator::advanceLevel`'s stage body
+(src/algs/integrator/RungeKuttaLevelIntegrator.cpp:1672-1745) with the patch strategy of
+src/apps/Navier-Stokes/NavierStokes.cpp: per stage
+
+    computeFluxesAndSourcesOnPatch   (:1108-1245)  zero source, convective flux + source (WCNS5-JS / HLLC-HLL or the other
+                                                   interpolators), diffusive flux ("SIXTH_ORDER")
+    advanceSingleStepOnPatch         (:2085-2092)  conservative update with both side fluxes
+    same-level ghost fill            (RungeKuttaLevelIntegrator.cpp:1701)
+
+The state carries six ghost cells (max of the convective 4 and the diffusive 6, NavierStokes.cpp ctor); the convective
+reconstructor reads its four-ghost view.  Single GPU, one patch covering the periodic level; the side fluxes are
+materialised (the fused, flux-free stage of the Euler path does not carry the diffusive term yet).  The arithmetic of
+every piece is the reference's: with math = MATH_EXACT a step is bit-identical to the oracle's composition of the same
+calls (tests/test_zz_gpu_diffusive.py)."""
+from __future__ import annotations
+
+from typing import Sequence, Tuple
+
+import numpy as np
+
+from . import abi
+
+
+class NavierStokesLevel:
+    def __init__(self, dim: int, N: Sequence[int], species_gamma: float = 1.4, species_R: float = 1.0,
+                 species_mu: float = 1.0e-3, species_mu_v: float = 0.0, species_c_p: float = 3.5, species_Pr: float = 0.72,
+                 domain: Tuple[float, float] = (0.0, 1.0), math: int = abi.MATH_EXACT, scheme: int = 0):
+        import torch
+
+        self.torch = torch
+        self.dim, self.n = dim, tuple(int(x) for x in N[:dim])
+        self.neq = dim + 2
+        L = domain[1] - domain[0]
+        self.domain_lo = domain[0]
+        self.dx = tuple(L / n for n in self.n)
+        c_v = 1.0 / (species_gamma - 1.0) * species_R           # EquationOfStateMixingRulesIdealGas.cpp:119
+        self.cplan = abi.Plan(dim, self.n, species_gamma=(species_gamma,), dx=self.dx, math=math, scheme=scheme).use_torch_stream()
+        self.dplan = abi.DiffusivePlan(dim, self.n, self.dx, species_gamma, c_v, species_mu, species_mu_v, species_c_p,
+                                       species_Pr).use_torch_stream()
+        f64 = dict(dtype=torch.float64, device="cuda")
+        g6 = tuple(x + 12 for x in reversed(self.n))
+        g4 = tuple(x + 8 for x in reversed(self.n))
+        self.S = [torch.zeros((self.neq,) + g6, **f64) for _ in range(3)]           # U0 and the two intermediate states
+        self.Q4 = torch.zeros((self.neq,) + g4, **f64)                              # four-ghost view of the newest state
+        self.Fc = [torch.zeros((self.neq,) + self.dplan.side_shape(a), **f64) for a in range(dim)]
+        self.Fd = [torch.zeros((self.neq,) + self.dplan.side_shape(a), **f64) for a in range(dim)]
+        self.src = torch.zeros((self.neq,) + tuple(reversed(self.n)), **f64)
+        self.cur = 0
+        self.ghosts_valid = False
+        self.alpha, self.beta = abi.SSPRK3_ALPHA, abi.SSPRK3_BETA
+
+    def close(self):
+        self.cplan.close()
+        self.dplan.close()
+
+    def _interior_slices(self):
+        return (slice(None),) + (slice(6, -6),) * self.dim
+
+    def interior(self):
+        """View of the interior cells of the current state (writing through it invalidates the ghosts)."""
+        self.ghosts_valid = False
+        return self.S[self.cur][self._interior_slices()]
+
+    def coordinates(self):
+        return [self.domain_lo + (np.arange(n) + 0.5) * d for n, d in zip(self.n, self.dx)]
+
+    @property
+    def launch_count(self) -> int:
+        return self.cplan.launch_count + self.dplan.launch_count
+
+    def _stage(self, alpha, beta, states, dt, out):
+        S = self.S
+        newest = S[states[-1]]
+        # NavierStokes::computeFluxesAndSourcesOnPatch on the newest state (the RK table only uses its flux)
+        self.src.zero_()
+        self.dplan.extract_view(newest, 4, self.Q4)
+        self.cplan.compute_flux_and_source(self.Q4, dt, self.Fc, self.src)
+        self.dplan.compute_diffusive_flux(newest, dt, self.Fd)
+        m = len(states)
+        none = [None] * (m - 1)
+        self.dplan.advance_stage_ns(6, alpha, beta, [S[i] for i in states], none + [self.Fc], none + [self.Fd],
+                                    none + [self.src], S[out])
+        self.dplan.fill_ghosts_periodic(S[out])
+
+    def rk_step(self, dt: float):
+        """One SSP-RK3 step (RungeKuttaLevelIntegrator.cpp:3894-3929): three stages, the result becomes the current state."""
+        a, b = self.alpha, self.beta
+        i0 = self.cur
+        i1, i2 = (i0 + 1) % 3, (i0 + 2) % 3
+        if not self.ghosts_valid:
+            self.dplan.fill_ghosts_periodic(self.S[i0])
+        self._stage(a[0][:1], b[0][:1], [i0], dt, i1)
+        self._stage(a[1][:2], b[1][:2], [i0, i1], dt, i2)
+        self._stage(a[2][:3], b[2][:3], [i0, i1, i2], dt, i1)      # alpha[2][1] == 0: U1 is free to be overwritten
+        self.cur = i1
+        self.ghosts_valid = True

@@ -258,6 +258,13 @@ int hb2_compute_diffusive_flux_dev(hb2_diff_plan_t plan, const double* const* Q,
 /* same with host pointers (H2D, kernels and D2H inside the call): the API-preserving seam */
 int hb2_compute_diffusive_flux_host(hb2_diff_plan_t plan, const double* const* Q_host, double dt, double* const* flux_host);
 
+/* Same-level periodic ghost fill of a six-ghost state (what xfer::RefineSchedule::fillData does for one patch covering a
+ * periodic level, RungeKuttaLevelIntegrator.cpp:1568, 1701); periodic_mask bit d = direction d is periodic. */
+int hb2_diffusive_fill_ghosts_periodic_dev(hb2_diff_plan_t plan, double* const* U, int32_t periodic_mask);
+/* The num_ghosts-wide view of a six-ghost state, as a separate array: the convective reconstructor reads four ghost
+ * cells (hb2_compute_flux_and_source_dev), SAMRAI hands it the same allocation with a larger ghost box instead. */
+int hb2_diffusive_extract_view_dev(hb2_diff_plan_t plan, const double* const* U, int32_t num_ghosts, double* const* U_view);
+
 /* NavierStokes::advanceSingleStepOnPatch with the conservative diffusive flux (NavierStokes.cpp:1715-1751, 2085-2092):
  *   U_out = sum_m alpha[m] U_int[m] + beta[m] ( -(Fc_R - Fc_L + Fd_R - Fd_L)/dx_0 - ... + S[m] )
  * U_int[m*num_eqn + e], U_out[e]: cell data with num_ghosts ghost cells; Fc_int / Fd_int[m*dim*num_eqn + dir*num_eqn + e],

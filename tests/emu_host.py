@@ -142,3 +142,22 @@ def advance_stage_ns(desc, tr, g, alpha, beta, U_int, Fc_int, Fd_int, S_int):
         _pp([U_out[e] for e in range(neq)]))
     assert rc == 0
     return U_out
+
+
+def diff_fill_periodic(desc, tr, U, mask=7):
+    """in place on U (neq, *six-ghost shape)"""
+    d = _ddesc(desc, tr)
+    assert U.flags["C_CONTIGUOUS"]
+    rc = dlib().emu_diff_fill_periodic(C.byref(d), _pp([U[c] for c in range(desc.neq)]), C.c_int(mask))
+    assert rc == 0
+    return U
+
+
+def diff_extract_view(desc, tr, U, g):
+    d = _ddesc(desc, tr)
+    U = np.ascontiguousarray(U)
+    V = np.full((desc.neq,) + tuple(int(desc.n[a]) + 2 * g for a in reversed(range(desc.dim))), np.nan)
+    rc = dlib().emu_diff_extract_view(C.byref(d), _pp([U[c] for c in range(desc.neq)]), C.c_int(g),
+                                      _pp([V[c] for c in range(desc.neq)]))
+    assert rc == 0
+    return V

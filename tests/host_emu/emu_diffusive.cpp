@@ -84,3 +84,27 @@ extern "C" int emu_advance_stage_ns(const EmuDiffDesc* d, int g, int ncoef, cons
     }
     return 0;
 }
+
+extern "C" int emu_diff_fill_periodic(const EmuDiffDesc* d, double* const* U, int mask)
+{
+    DiffGeom G;
+    make_diff_geom(d->dim, d->n, d->dx, HB2_DIFF_G, &G);
+    DiffStatePtrs A{};
+    for (int c = 0; c < d->dim + 2; c++) A.U[c] = U[c];
+    for (long long t = 0; t < G.ncell_g; t++) diff_fill_periodic_thread(G, A, d->dim + 2, mask, t);
+    return 0;
+}
+
+extern "C" int emu_diff_extract_view(const EmuDiffDesc* d, const double* const* U, int g, double* const* V)
+{
+    DiffGeom Gs, Gd;
+    make_diff_geom(d->dim, d->n, d->dx, HB2_DIFF_G, &Gs);
+    make_diff_geom(d->dim, d->n, d->dx, g, &Gd);
+    DiffStatePtrs A{};
+    for (int c = 0; c < d->dim + 2; c++) {
+        A.src[c] = U[c];
+        A.U[c] = V[c];
+    }
+    for (long long t = 0; t < Gd.ncell_g; t++) diff_extract_view_thread(Gs, Gd, A, d->dim + 2, t);
+    return 0;
+}

@@ -72,3 +72,26 @@ def test_emulated_ns_stage_is_bit_identical(dim, g):
         assert np.array_equal(Ue[inner], Uo[inner])
         Ue[inner] = np.nan
         assert np.isnan(Ue).all()                    # the kernel leaves the ghosts alone
+
+
+@pytest.mark.parametrize("dim,N", [(2, (7, 5)), (3, (6, 4, 9)), (3, (2, 1, 3)), (2, (1, 1))])
+def test_emulated_periodic_fill_and_ghost_view(dim, N):
+    """Six-ghost periodic fill (also where the patch is narrower than the ghost width: images wrap several times) and the
+    four-ghost view handed to the convective reconstructor, against numpy's wrap padding."""
+    desc, U = state(dim, N)
+    want6 = pb.pad_periodic(U, 6)
+    got = np.full_like(want6, np.nan)
+    got[(slice(None),) + (slice(6, -6),) * dim] = U
+    emu_host.diff_fill_periodic(desc, TR, got)
+    assert np.array_equal(got, want6)
+    for g in (4, 0, 6):
+        assert np.array_equal(emu_host.diff_extract_view(desc, TR, want6, g), pb.pad_periodic(U, g) if g else U)
+    # mask: only x periodic -> y (and z) ghost layers keep their NaN, x ghosts of interior rows are filled
+    part = np.full_like(want6, np.nan)
+    inner = (slice(None),) + (slice(6, -6),) * dim
+    part[inner] = U
+    emu_host.diff_fill_periodic(desc, TR, part, mask=1)
+    rows = (slice(None),) + (slice(6, -6),) * (dim - 1) + (slice(None),)
+    assert np.array_equal(part[rows], want6[rows])
+    part[rows] = 0.0
+    assert np.isnan(part[:, 0]).all() and np.isnan(part[:, -1]).all()
