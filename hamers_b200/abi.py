@@ -36,7 +36,7 @@ SYMBOLS = [
     # diffusive flux of the single-species Navier-Stokes application
     "hb2_diffusive_plan_create", "hb2_diffusive_plan_destroy", "hb2_diffusive_plan_set_stream", "hb2_diffusive_plan_launches",
     "hb2_compute_diffusive_flux_dev", "hb2_compute_diffusive_flux_host", "hb2_advance_stage_ns_dev",
-    "hb2_diffusive_fill_ghosts_periodic_dev", "hb2_diffusive_extract_view_dev",
+    "hb2_diffusive_fill_ghosts_periodic_dev", "hb2_diffusive_extract_view_dev", "hb2_diffusive_accumulate_dev",
 ]
 
 WCNS5_JS, WCNS5_Z, WCNS6_LD = 0, 1, 2
@@ -65,6 +65,7 @@ class PatchDescC(C.Structure):
         ("weno_q", C.c_int32),
         ("weno_C", C.c_double),
         ("weno_alpha_tau", C.c_double),
+        ("num_ghosts", C.c_int32),
     ]
 
 
@@ -147,9 +148,11 @@ class Plan:
     def __init__(self, dim: int, n: Sequence[int], flow_model: int = SINGLE_SPECIES,
                  species_gamma: Sequence[float] = (1.4,), dx: Sequence[float] = (1.0, 1.0, 1.0),
                  weno_p: int = 2, math: int = MATH_EXACT, device: int = -1, scheme: int = 0, weno_q: int = 4,
-                 weno_C: float = 1.0e9, weno_alpha_tau: float = 35.0):
+                 weno_C: float = 1.0e9, weno_alpha_tau: float = 35.0, num_ghosts: int = GHOSTS):
         self.lib = load_library()
         d = PatchDescC()
+        d.num_ghosts = int(num_ghosts)
+        self.num_ghosts = int(num_ghosts)
         d.dim = dim
         for a in range(3):
             d.n[a] = int(n[a]) if a < dim else 1
@@ -175,7 +178,7 @@ class Plan:
     # -- shapes ---------------------------------------------------------------------------
     @property
     def ghost_shape(self):
-        return tuple(self.n[a] + 2 * GHOSTS for a in reversed(range(self.dim)))
+        return tuple(self.n[a] + 2 * self.num_ghosts for a in reversed(range(self.dim)))
 
     @property
     def cell_shape(self):
@@ -447,6 +450,12 @@ class DiffusivePlan:
         _check(self.lib.hb2_diffusive_extract_view_dev(self._h, _ptr_table(_dev_ptrs(U, self.neq)), int(num_ghosts),
                                                        _ptr_table(_dev_ptrs(U_view, self.neq))),
                "hb2_diffusive_extract_view_dev")
+
+    def accumulate(self, num_ghosts: int, beta: float, Fd, U):
+        """U += beta (-div F_d) on the interior of U (neq, ... with num_ghosts ghosts); Fd: list per direction."""
+        fp = _ptr_table([p for d in range(self.dim) for p in _dev_ptrs(Fd[d], self.neq)])
+        _check(self.lib.hb2_diffusive_accumulate_dev(self._h, int(num_ghosts), C.c_double(beta), fp,
+                                                     _ptr_table(_dev_ptrs(U, self.neq))), "hb2_diffusive_accumulate_dev")
 
     def advance_stage_ns(self, num_ghosts: int, alpha, beta, U_int, Fc_int, Fd_int, S_int, U_out):
         """NavierStokes::advanceSingleStepOnPatch (conservative diffusive flux) on device tensors; rows with a zero

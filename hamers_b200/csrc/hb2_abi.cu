@@ -135,6 +135,8 @@ int validate_desc(const hb2_patch_desc* d)
     if (d->math != HB2_MATH_EXACT && d->math != HB2_MATH_FAST) return fail(-9, "math must be HB2_MATH_EXACT or HB2_MATH_FAST");
     if (d->scheme != HB2_WCNS5_JS && d->scheme != HB2_WCNS5_Z && d->scheme != HB2_WCNS6_LD)
         return fail(-24, "scheme must be HB2_WCNS5_JS, HB2_WCNS5_Z or HB2_WCNS6_LD");
+    if (d->num_ghosts != 0 && (d->num_ghosts < HB2_GHOSTS || d->num_ghosts > 8))
+        return fail(-25, "num_ghosts must be 0 (= 4) or between 4 and 8");
     return 0;
 }
 
@@ -143,7 +145,7 @@ void make_geom(const hb2_patch_desc* d, Geom* G)
     G->dim = d->dim;
     for (int a = 0; a < 3; a++) {
         G->n[a] = (a < d->dim) ? d->n[a] : 1;
-        G->g[a] = (a < d->dim) ? HB2_GHOSTS : 0;
+        G->g[a] = (a < d->dim) ? (d->num_ghosts > 0 ? d->num_ghosts : HB2_GHOSTS) : 0;
         G->gd[a] = G->n[a] + 2 * G->g[a];
         G->dx[a] = (a < d->dim) ? d->dx[a] : 1.0;
     }
@@ -460,7 +462,7 @@ int hb2_num_comp(const hb2_patch_desc* d, int32_t* v)
 int hb2_num_ghosts(const hb2_patch_desc* d, int32_t ghosts[3])
 {
     if (!d) return fail(-1, "null argument");
-    for (int a = 0; a < 3; a++) ghosts[a] = (a < d->dim) ? HB2_GHOSTS : 0;
+    for (int a = 0; a < 3; a++) ghosts[a] = (a < d->dim) ? (d->num_ghosts > 0 ? d->num_ghosts : HB2_GHOSTS) : 0;
     return 0;
 }
 int64_t hb2_cell_ghost_size(const hb2_patch_desc* d)
@@ -692,6 +694,9 @@ int hb2_fused_stage_push_dev(hb2_plan_t p, int32_t ncoef, const double* alpha, c
     for (int m = 0; m < ncoef - 1; m++)
         if (beta[m] != 0.0)
             return fail(-16, "fused stage needs beta[m] == 0 for m < ncoef-1; use hb2_compute_flux_and_source_dev + hb2_advance_stage_dev");
+    if (push && p->G.g[0] != HB2_GHOSTS)
+        return fail(-26, "the fused ghost push fills the four layers of the convective layout; plans with num_ghosts != 4 "
+                         "fill their ghosts separately");
     HB2_CUDA(cudaSetDevice(p->device));
     int rc = ensure_ws(p, true);
     if (rc) return rc;

@@ -99,6 +99,14 @@ __global__ void __launch_bounds__(256) k_diff_extract_view(const __grid_constant
         diff_extract_view_thread(Gs, Gd, A, ncomp, t);
 }
 
+template <int DIM>
+__global__ void __launch_bounds__(256) k_diff_accumulate(const __grid_constant__ NsAccArgs A)
+{
+    const long long total = (long long)A.G.n[0] * A.G.n[1] * A.G.n[2];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) diff_accumulate_thread<DIM>(A, t);
+}
+
 int grid_for(long long work, int sm_count)
 {
     const long long blocks = (work + 255) / 256;
@@ -249,6 +257,31 @@ int hb2_compute_diffusive_flux_host(hb2_diff_plan_t p, const double* const* Q_ho
             HB2D_CUDA(cudaMemcpyAsync(flux_host[f * neq + e], Fd[f * neq + e], sizeof(double) * (size_t)p->nside[f],
                                       cudaMemcpyDeviceToHost, p->stream));
     HB2D_CUDA(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int hb2_diffusive_accumulate_dev(hb2_diff_plan_t p, int32_t num_ghosts, double beta, const double* const* Fd, double* const* U)
+{
+    if (!p || !Fd || !U) return set_error(-1, "null argument");
+    if (num_ghosts < 0) return set_error(-31, "num_ghosts must be >= 0");
+    HB2D_CUDA(cudaSetDevice(p->device));
+    const int dim = p->d.dim, neq = p->neq;
+    NsAccArgs A{};
+    make_diff_geom(dim, p->d.n, p->d.dx, num_ghosts, &A.G);
+    A.neq = neq;
+    A.beta = beta;
+    for (int f = 0; f < dim * neq; f++) {
+        A.Fd[f] = Fd[f];
+        if (!A.Fd[f]) return set_error(-12, "diffusive flux row is NULL");
+    }
+    for (int e = 0; e < neq; e++) A.U[e] = U[e];
+    const long long total = (long long)A.G.n[0] * A.G.n[1] * A.G.n[2];
+    if (dim == 2)
+        k_diff_accumulate<2><<<grid_for(total, p->sm_count), 256, 0, p->stream>>>(A);
+    else
+        k_diff_accumulate<3><<<grid_for(total, p->sm_count), 256, 0, p->stream>>>(A);
+    p->launches++;
+    HB2D_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -332,6 +332,38 @@ HB2D_HD void advance_ns_thread(const NsArgs& A, long long t)
     }
 }
 
+/* Diffusive part of the stage update on top of a state that already holds sum alpha U + beta (-div F_c + S) (the fused
+ * convective stage): U += beta (-(Fd_R - Fd_L)/dx_0 - ...).  Same terms as NavierStokes.cpp:2085-2092, associated
+ * differently (the reference adds the two flux differences before dividing): <= a few ulp, used by the
+ * re-associated (HB2_MATH_FAST) path only. */
+struct NsAccArgs {
+    DiffGeom G;       /* geometry of U */
+    int neq;
+    double beta;
+    const double* Fd[15];
+    double* U[5];
+};
+
+template <int DIM>
+HB2D_HD void diff_accumulate_thread(const NsAccArgs& A, long long t)
+{
+    const DiffGeom& G = A.G;
+    const int i = (int)(t % G.n[0]), j = (int)((t / G.n[0]) % G.n[1]), k = (int)(t / ((long long)G.n[0] * G.n[1]));
+    const long long x = (i + G.g[0]) + G.cs[1] * (j + G.g[1]) + G.cs[2] * (k + G.g[2]);
+    const long long fxL = i + (long long)(G.n[0] + 1) * (j + (long long)G.n[1] * k), fxR = fxL + 1;
+    const long long fyB = i + (long long)G.n[0] * (j + (long long)(G.n[1] + 1) * k), fyT = fyB + G.n[0];
+    const long long fzB = t, fzF = t + (long long)G.n[0] * G.n[1];
+    for (int e = 1; e < A.neq; e++) {            /* the continuity equation has no diffusive flux */
+        const double *Fdx = A.Fd[e], *Fdy = A.Fd[A.neq + e];
+        double div = -(Fdx[fxR] - Fdx[fxL]) / G.dx[0] - (Fdy[fyT] - Fdy[fyB]) / G.dx[1];
+        if (DIM == 3) {
+            const double* Fdz = A.Fd[2 * A.neq + e];
+            div -= (Fdz[fzF] - Fdz[fzB]) / G.dx[2];
+        }
+        A.U[e][x] += A.beta * div;
+    }
+}
+
 /* ---- state management of a six-ghost level (what xfer::RefineSchedule::fillData does for a periodic single-patch level,
  * and the four-ghost view the convective reconstructor reads) ---- */
 struct DiffStatePtrs {

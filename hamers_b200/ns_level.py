@@ -9,11 +9,16 @@ src/apps/Navier-Stokes/NavierStokes.cpp: per stage
     advanceSingleStepOnPatch         (:2085-2092)  conservative update with both side fluxes
     same-level ghost fill            (RungeKuttaLevelIntegrator.cpp:1701)
 
-The state carries six ghost cells (max of the convective 4 and the diffusive 6, NavierStokes.cpp ctor); the convective
-reconstructor reads its four-ghost view.  Single GPU, one patch covering the periodic level; the side fluxes are
-materialised (the fused, flux-free stage of the Euler path does not carry the diffusive term yet).  The arithmetic of
-every piece is the reference's: with math = MATH_EXACT a step is bit-identical to the oracle's composition of the same
-calls (tests/test_zz_gpu_diffusive.py)."""
+The state carries six ghost cells (max of the convective 4 and the diffusive 6, NavierStokes.cpp ctor) and both
+reconstructors read the same arrays (the convective plan is created with num_ghosts = 6), like SAMRAI hands them the
+same allocation.  Single GPU, one patch covering the periodic level.  Two routes per stage:
+
+  math = MATH_EXACT  both side fluxes materialised and combined by hb2_advance_stage_ns_dev in the reference's
+                     association: a step is bit-identical to the oracle's composition of the same calls;
+  math = MATH_FAST   the fused convective stage (no convective flux or source array is ever written), then the diffusive
+                     divergence accumulated on top (hb2_diffusive_accumulate_dev): same terms, re-associated, <= 1e-12.
+
+(tests/test_zz_gpu_diffusive.py; CPU emulation of both routes in tests/test_host_emu_diffusive.py.)"""
 from __future__ import annotations
 
 from typing import Sequence, Tuple
@@ -36,17 +41,18 @@ class NavierStokesLevel:
         self.domain_lo = domain[0]
         self.dx = tuple(L / n for n in self.n)
         c_v = 1.0 / (species_gamma - 1.0) * species_R           # EquationOfStateMixingRulesIdealGas.cpp:119
-        self.cplan = abi.Plan(dim, self.n, species_gamma=(species_gamma,), dx=self.dx, math=math, scheme=scheme).use_torch_stream()
+        self.math = math
+        self.cplan = abi.Plan(dim, self.n, species_gamma=(species_gamma,), dx=self.dx, math=math, scheme=scheme,
+                              num_ghosts=abi.DIFF_GHOSTS).use_torch_stream()
         self.dplan = abi.DiffusivePlan(dim, self.n, self.dx, species_gamma, c_v, species_mu, species_mu_v, species_c_p,
                                        species_Pr).use_torch_stream()
         f64 = dict(dtype=torch.float64, device="cuda")
         g6 = tuple(x + 12 for x in reversed(self.n))
-        g4 = tuple(x + 8 for x in reversed(self.n))
         self.S = [torch.zeros((self.neq,) + g6, **f64) for _ in range(3)]           # U0 and the two intermediate states
-        self.Q4 = torch.zeros((self.neq,) + g4, **f64)                              # four-ghost view of the newest state
-        self.Fc = [torch.zeros((self.neq,) + self.dplan.side_shape(a), **f64) for a in range(dim)]
         self.Fd = [torch.zeros((self.neq,) + self.dplan.side_shape(a), **f64) for a in range(dim)]
-        self.src = torch.zeros((self.neq,) + tuple(reversed(self.n)), **f64)
+        if math == abi.MATH_EXACT:
+            self.Fc = [torch.zeros((self.neq,) + self.dplan.side_shape(a), **f64) for a in range(dim)]
+            self.src = torch.zeros((self.neq,) + tuple(reversed(self.n)), **f64)
         self.cur = 0
         self.ghosts_valid = False
         self.alpha, self.beta = abi.SSPRK3_ALPHA, abi.SSPRK3_BETA
@@ -74,14 +80,17 @@ class NavierStokesLevel:
         S = self.S
         newest = S[states[-1]]
         # NavierStokes::computeFluxesAndSourcesOnPatch on the newest state (the RK table only uses its flux)
-        self.src.zero_()
-        self.dplan.extract_view(newest, 4, self.Q4)
-        self.cplan.compute_flux_and_source(self.Q4, dt, self.Fc, self.src)
         self.dplan.compute_diffusive_flux(newest, dt, self.Fd)
-        m = len(states)
-        none = [None] * (m - 1)
-        self.dplan.advance_stage_ns(6, alpha, beta, [S[i] for i in states], none + [self.Fc], none + [self.Fd],
-                                    none + [self.src], S[out])
+        if self.math == abi.MATH_EXACT:
+            self.src.zero_()
+            self.cplan.compute_flux_and_source(newest, dt, self.Fc, self.src)
+            m = len(states)
+            none = [None] * (m - 1)
+            self.dplan.advance_stage_ns(6, alpha, beta, [S[i] for i in states], none + [self.Fc], none + [self.Fd],
+                                        none + [self.src], S[out])
+        else:
+            self.cplan.fused_stage(alpha, beta, [S[i] for i in states], dt, S[out])
+            self.dplan.accumulate(6, float(beta[-1]), self.Fd, S[out])
         self.dplan.fill_ghosts_periodic(S[out])
 
     def rk_step(self, dt: float):

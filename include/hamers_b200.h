@@ -74,6 +74,10 @@ typedef struct hb2_patch_desc {
     int32_t weno_q;
     double weno_C;
     double weno_alpha_tau;
+    /* Ghost width of the cell-data LAYOUT the plan's state arrays use: 0 = HB2_GHOSTS.  The kernels read four layers
+     * whatever it is; a Navier-Stokes application allocates the state with six (the diffusive reconstructor's width,
+     * HB2_DIFF_GHOSTS) and hands the same arrays to both reconstructors, like SAMRAI does.  4 <= num_ghosts <= 8. */
+    int32_t num_ghosts;
 } hb2_patch_desc;
 
 #define HB2_WCNS5_JS 0
@@ -272,6 +276,13 @@ int hb2_diffusive_extract_view_dev(hb2_diff_plan_t plan, const double* const* U,
 int hb2_advance_stage_ns_dev(hb2_diff_plan_t plan, int32_t num_ghosts, int32_t ncoef, const double* alpha, const double* beta,
                              const double* const* U_int, const double* const* Fc_int, const double* const* Fd_int,
                              const double* const* S_int, double* const* U_out);
+
+/* The diffusive part of that update on top of a state that already holds sum_m alpha[m] U_int[m] + beta (-div F_c + S),
+ * i.e. the output of hb2_fused_stage_dev on the same arrays (plan created with num_ghosts = 6):
+ *   U += beta ( -(Fd_R - Fd_L)/dx_0 - ... ).
+ * Same terms as NavierStokes.cpp:2085-2092 associated differently (a few ulp): the HB2_MATH_FAST route of the stage,
+ * which never materialises the convective flux.  U[e]: cell data with num_ghosts ghost cells. */
+int hb2_diffusive_accumulate_dev(hb2_diff_plan_t plan, int32_t num_ghosts, double beta, const double* const* Fd, double* const* U);
 
 #ifdef __cplusplus
 }

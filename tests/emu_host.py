@@ -18,7 +18,7 @@ class EmuDesc(C.Structure):
     _fields_ = [("dim", C.c_int), ("n", C.c_int * 3), ("model", C.c_int), ("ns", C.c_int),
                 ("gamma", C.c_double * 4), ("dx", C.c_double * 3), ("weno_p", C.c_int),
                 ("math", C.c_int), ("bx", C.c_int), ("seg_len", C.c_int),
-                ("weno_q", C.c_int), ("weno_C", C.c_double), ("weno_alpha_tau", C.c_double)]
+                ("weno_q", C.c_int), ("weno_C", C.c_double), ("weno_alpha_tau", C.c_double), ("ghosts", C.c_int)]
 
 
 def lib(scheme: int = 0):
@@ -43,8 +43,9 @@ def _pp(arrs):
     return P
 
 
-def _desc(desc, math, bx, seg_len):
+def _desc(desc, math, bx, seg_len, ghosts=0):
     d = EmuDesc()
+    d.ghosts = ghosts
     d.dim = desc.dim
     for a in range(3):
         d.n[a] = int(desc.n[a]) if a < desc.dim else 1
@@ -57,11 +58,12 @@ def _desc(desc, math, bx, seg_len):
     return d
 
 
-def flux_and_source(desc, Q, dt, math=0, bx=0, seg_len=0, source=None):
+def flux_and_source(desc, Q, dt, math=0, bx=0, seg_len=0, source=None, ghosts=0):
+    """ghosts: ghost width of the layout of Q (0 = the convective 4)."""
     neq, dim = desc.neq, desc.dim
     F = [np.full((neq,) + desc.side_shape(a), np.nan) for a in range(dim)]
     S = np.zeros((neq,) + desc.cell_shape) if source is None else source
-    d = _desc(desc, math, bx, seg_len)
+    d = _desc(desc, math, bx, seg_len, ghosts)
     Q = np.ascontiguousarray(Q)
     rc = lib(desc.scheme).emu_flux_and_source(C.byref(d), _pp([Q[c] for c in range(desc.ncomp)]), C.c_double(dt),
                                    _pp([F[a][e] for a in range(dim) for e in range(neq)]),
@@ -70,10 +72,10 @@ def flux_and_source(desc, Q, dt, math=0, bx=0, seg_len=0, source=None):
     return F, S
 
 
-def fused_stage(desc, alpha, beta, U_int, dt, math=0, bx=0, seg_len=0, push=False):
+def fused_stage(desc, alpha, beta, U_int, dt, math=0, bx=0, seg_len=0, push=False, ghosts=0):
     ncoef = len(alpha)
-    U_out = np.zeros((desc.ncomp,) + desc.ghost_shape)
-    d = _desc(desc, math, bx, seg_len)
+    U_out = np.zeros_like(np.ascontiguousarray(U_int[0]))
+    d = _desc(desc, math, bx, seg_len, ghosts)
     Us = [np.ascontiguousarray(u) for u in U_int]
     tab = _pp([Us[m][c] for m in range(ncoef) for c in range(desc.ncomp)])
     a = (C.c_double * ncoef)(*[float(x) for x in alpha])
@@ -161,3 +163,14 @@ def diff_extract_view(desc, tr, U, g):
                                       _pp([V[c] for c in range(desc.neq)]))
     assert rc == 0
     return V
+
+
+def diff_accumulate(desc, tr, g, beta, Fd, U):
+    """in place on U (neq, *shape with g ghosts)"""
+    d = _ddesc(desc, tr)
+    assert U.flags["C_CONTIGUOUS"]
+    rc = dlib().emu_diff_accumulate(C.byref(d), C.c_int(g), C.c_double(beta),
+                                    _pp([Fd[a][e] for a in range(desc.dim) for e in range(desc.neq)]),
+                                    _pp([U[e] for e in range(desc.neq)]))
+    assert rc == 0
+    return U

@@ -21,6 +21,7 @@ struct EmuDesc {
     int weno_p, math, bx, seg_len;
     int weno_q;            /* WCNS6-LD constants (the interpolator itself is compiled in: -DHB2_SCHEME) */
     double weno_C, weno_alpha_tau;
+    int ghosts;            /* ghost width of the cell-data layout (0 = 4); the kernels read 4 layers whatever it is */
 };
 
 static void make_geom(const EmuDesc* d, Geom* G)
@@ -28,7 +29,7 @@ static void make_geom(const EmuDesc* d, Geom* G)
     G->dim = d->dim;
     for (int a = 0; a < 3; a++) {
         G->n[a] = (a < d->dim) ? d->n[a] : 1;
-        G->g[a] = (a < d->dim) ? HB2_G : 0;
+        G->g[a] = (a < d->dim) ? (d->ghosts > 0 ? d->ghosts : HB2_G) : 0;
         G->gd[a] = G->n[a] + 2 * G->g[a];
         G->dx[a] = (a < d->dim) ? d->dx[a] : 1.0;
     }

@@ -108,3 +108,22 @@ extern "C" int emu_diff_extract_view(const EmuDiffDesc* d, const double* const* 
     for (long long t = 0; t < Gd.ncell_g; t++) diff_extract_view_thread(Gs, Gd, A, d->dim + 2, t);
     return 0;
 }
+
+extern "C" int emu_diff_accumulate(const EmuDiffDesc* d, int g, double beta, const double* const* Fd, double* const* U)
+{
+    const int dim = d->dim, neq = dim + 2;
+    NsAccArgs A{};
+    make_diff_geom(dim, d->n, d->dx, g, &A.G);
+    A.neq = neq;
+    A.beta = beta;
+    for (int f = 0; f < dim * neq; f++) A.Fd[f] = Fd[f];
+    for (int e = 0; e < neq; e++) A.U[e] = U[e];
+    const long long total = (long long)A.G.n[0] * A.G.n[1] * A.G.n[2];
+    for (long long t = 0; t < total; t++) {
+        if (dim == 2)
+            diff_accumulate_thread<2>(A, t);
+        else
+            diff_accumulate_thread<3>(A, t);
+    }
+    return 0;
+}

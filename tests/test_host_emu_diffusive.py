@@ -95,3 +95,30 @@ def test_emulated_periodic_fill_and_ghost_view(dim, N):
     assert np.array_equal(part[rows], want6[rows])
     part[rows] = 0.0
     assert np.isnan(part[:, 0]).all() and np.isnan(part[:, -1]).all()
+
+
+@pytest.mark.parametrize("math", [0, 1])
+@pytest.mark.parametrize("dim,N", [(2, (24, 17)), (3, (13, 10, 12))])
+def test_emulated_fused_navier_stokes_stage(dim, N, math, oracle_lib):
+    """The flux-free route of a Navier-Stokes stage: fused convective stage on the six-ghost arrays, then the diffusive
+    divergence accumulated on top.  Against the oracle's materialised composition (NavierStokes.cpp:2085-2092): the terms
+    are the same, their association is not -- within the fast-build criterion, and ~1e-16 with reference-order kernels."""
+    from common import assert_fast_parity
+
+    desc, U = state(dim, N)
+    dt = 2.0e-4
+    Q6, Q4 = pb.pad_periodic(U, 6), pb.pad_periodic(U, 4)
+    Fc, S = oracle_lib.compute_flux_and_source(desc, Q4, dt)
+    Fd = orc.compute_diffusive_flux(desc, TR, Q6, dt)
+    inner = (slice(None),) + (slice(6, -6),) * dim
+    for alpha, beta in (([1.0], [1.0]), ([0.75, 0.25], [0.0, 0.25])):
+        m = len(alpha)
+        states = [Q6] * m if m == 1 else [pb.pad_periodic(U * 1.01, 6), Q6]
+        none = [None] * (m - 1)
+        want = orc.advance_stage_ns(desc, 6, alpha, beta, states, none + [Fc], none + [Fd], none + [S])[inner]
+        got = emu_host.fused_stage(desc, alpha, beta, states, dt, math=math, ghosts=6)
+        emu_host.diff_accumulate(desc, TR, 6, beta[-1], emu_host.diffusive_flux(desc, TR, Q6, dt), got)
+        if math == 0:
+            assert np.abs(got[inner] - want).max() <= 1.0e-14 * np.abs(want).max()
+        else:
+            assert_fast_parity(got[inner], want, "fused NS stage")
