@@ -4,6 +4,7 @@ fallback) when asked to compute without a CUDA device."""
 import ctypes as C
 import os
 import re
+import subprocess
 
 import pytest
 
@@ -93,3 +94,17 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "liboracle" not in text and "hamers_oracle" not in text, f
+
+
+def test_descriptor_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of hb2_patch_desc / hb2_diffusive_desc have the C structs' size and the offsets of their last
+    members (a C probe compiled against include/hamers_b200.h)."""
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hamers_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu\\n", sizeof(hb2_patch_desc), offsetof(hb2_patch_desc, num_ghosts),'
+                   ' sizeof(hb2_diffusive_desc), offsetof(hb2_diffusive_desc, device)); return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert got == [C.sizeof(abi.PatchDescC), abi.PatchDescC.num_ghosts.offset, C.sizeof(abi.DiffusiveDescC),
+                   abi.DiffusiveDescC.device.offset]
