@@ -742,6 +742,82 @@ extern "C" void ref_diff_point(int dim, const double in[10], double out[15])
 """
 
 
+def diffusive_term_tables() -> str:
+    """SURVEY row f4: FlowModelDiffusiveFluxUtilitiesSingleSpecies::getCellDataOfDiffusiveFluxVariablesForDerivative (:654-1503)
+    and ::getCellDataOfDiffusiveFluxDiffusivities (:1505-2363) -- which derivative carries which diffusivity in which
+    equation -- compiled verbatim as members of a stub class (FlowModel, pdat::CellData, tbox::Dimension, TBOX_ERROR reduced
+    to what the two functions use)."""
+    with open(os.path.join(REF, "src/flow/flow_models/single-species/FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp")) as fh:
+        src = fh.read()
+    cls = "FlowModelDiffusiveFluxUtilitiesSingleSpecies"
+    f1 = void_member_function(src, cls, "getCellDataOfDiffusiveFluxVariablesForDerivative")
+    f2 = void_member_function(src, cls, "getCellDataOfDiffusiveFluxDiffusivities")
+    return f"""
+#include <memory>
+#include <string>
+#include <sstream>
+#include <vector>
+#include <cstdlib>
+namespace ref_diff_tables {{
+#define TBOX_ERROR(X) do {{ std::ostringstream os_; os_ << X; std::abort(); }} while (0)
+#define HAMERS_SHARED_PTR std::shared_ptr
+namespace tbox {{ struct Dimension {{ int d; explicit Dimension(int d_) : d(d_) {{}}
+                  bool operator==(const Dimension& o) const {{ return d == o.d; }} }}; }}
+namespace pdat {{ template <class T> struct CellData {{ int tag; }}; }}
+namespace DIRECTION {{ enum TYPE {{ X_DIRECTION = 0, Y_DIRECTION = 1, Z_DIRECTION = 2 }}; }}
+struct FlowModel {{
+    std::shared_ptr<pdat::CellData<double> > velocity, temperature;
+    bool hasRegisteredPatch() const {{ return true; }}
+    std::shared_ptr<pdat::CellData<double> > getCellData(const std::string& key) const
+    {{
+        return key == "VELOCITY" ? velocity : (key == "TEMPERATURE" ? temperature : std::shared_ptr<pdat::CellData<double> >());
+    }}
+}};
+struct {cls} {{
+    std::weak_ptr<FlowModel> d_flow_model;
+    std::string d_object_name;
+    tbox::Dimension d_dim;
+    int d_num_eqn;
+    bool d_cell_data_computed_diffusivities;
+    std::shared_ptr<pdat::CellData<double> > d_data_diffusivities;
+    explicit {cls}(int dim) : d_object_name("ref"), d_dim(dim), d_num_eqn(dim + 2), d_cell_data_computed_diffusivities(true) {{}}
+    void getCellDataOfDiffusiveFluxVariablesForDerivative(std::vector<std::vector<std::shared_ptr<pdat::CellData<double> > > >&,
+                                                          std::vector<std::vector<int> >&, const DIRECTION::TYPE&, const DIRECTION::TYPE&);
+    void getCellDataOfDiffusiveFluxDiffusivities(std::vector<std::vector<std::shared_ptr<pdat::CellData<double> > > >&,
+                                                 std::vector<std::vector<int> >&, const DIRECTION::TYPE&, const DIRECTION::TYPE&);
+}};
+{f1}
+
+{f2}
+}}
+
+/* the terms of equation e of the node flux in direction fdir that carry a derivative in direction ddir: variable
+ * (velocity component, or dim for the temperature) and index of the diffusivity; returns -1 if the two tables disagree */
+extern "C" int ref_diff_terms(int dim, int fdir, int ddir, int e, int var[4], int diff[4])
+{{
+    using namespace ref_diff_tables;
+    std::shared_ptr<FlowModel> fm(new FlowModel());
+    fm->velocity.reset(new pdat::CellData<double>());
+    fm->temperature.reset(new pdat::CellData<double>());
+    {cls} u(dim);
+    u.d_flow_model = fm;
+    u.d_data_diffusivities.reset(new pdat::CellData<double>());
+    std::vector<std::vector<std::shared_ptr<pdat::CellData<double> > > > vdata, ddata;
+    std::vector<std::vector<int> > vidx, didx;
+    u.getCellDataOfDiffusiveFluxVariablesForDerivative(vdata, vidx, (DIRECTION::TYPE)fdir, (DIRECTION::TYPE)ddir);
+    u.getCellDataOfDiffusiveFluxDiffusivities(ddata, didx, (DIRECTION::TYPE)fdir, (DIRECTION::TYPE)ddir);
+    if (vdata[e].size() != ddata[e].size() || vidx[e].size() != vdata[e].size() || didx[e].size() != ddata[e].size()) return -1;
+    const int n = (int)vdata[e].size();
+    for (int i = 0; i < n && i < 4; i++) {{
+        if (ddata[e][i] != u.d_data_diffusivities) return -1;
+        var[i] = vdata[e][i] == fm->velocity ? vidx[e][i] : (vdata[e][i] == fm->temperature && vidx[e][i] == 0 ? dim : -1);
+        diff[i] = didx[e][i];
+    }}
+    return n;
+}}
+"""
+
+
 def static_inline_functions(text: str) -> str:
     """Return the concatenation of every `static inline ...` function definition in text."""
     out = []
@@ -877,6 +953,7 @@ def main() -> int:
     parts.append(path_statements5())
     parts.append(path_statements6())
     parts.append(diffusive_kernels())
+    parts.append(diffusive_term_tables())
     gen = os.path.join(OUT, "_generated_ref_kernels.cpp")
     with open(gen, "w") as fh:
         fh.write("\n".join(parts))

@@ -174,3 +174,9 @@ def diff_accumulate(desc, tr, g, beta, Fd, U):
                                     _pp([U[e] for e in range(desc.neq)]))
     assert rc == 0
     return U
+
+
+def diff_terms(dim, f, d, e):
+    var, dif = (C.c_int * 4)(), (C.c_int * 4)()
+    n = dlib().emu_diff_terms(dim, f, d, e, var, dif)
+    return [(var[i], dif[i]) for i in range(n)]

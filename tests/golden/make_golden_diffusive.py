@@ -5,6 +5,9 @@ Run in the build container (needs /root/reference); the fixture is committed, th
   u{dim}d            (ghost box, 6 ghosts) random cell data, n = (5, 4, 3)[:dim]
   der{dim}d{dir}     computeFirstDerivativesIn{X,Y,Z}(u) over the base class's range (NaN where not written)
   rec{dim}d{dir}     reconstructFlux{X,Y,Z}(u as node flux) into a zero-filled side array, dt = 0.37
+  terms{dim}d        (flux dir, derivative dir, equation, term, 2) = (variable, diffusivity index) in the reference's order of
+                     accumulation, -1 padded: FlowModelDiffusiveFluxUtilitiesSingleSpecies::getCellDataOfDiffusiveFluxVariables
+                     ForDerivative / getCellDataOfDiffusiveFluxDiffusivities compiled verbatim (variable dim = temperature)
   point{dim}d_in (n, 11) = gamma, c_v, rho, p, c_p, mu, Pr, mu_v, u, v, w;  point{dim}d_out (n, 2 + 13 | 10) = T, kappa, D_xx
 """
 import ctypes as C
@@ -39,6 +42,17 @@ def main():
             rec = np.zeros(tuple(reversed(fs)))
             lib.ref_diff_reconstruct(dim, d, u.ctypes.data_as(P), nn, C.c_double(DT), rec.ctypes.data_as(P))
             out[f"rec{dim}d{d}"] = rec
+        # the term tables, from the reference's own getCellDataOfDiffusiveFluxVariablesForDerivative / ...Diffusivities
+        terms = np.full((dim, dim, dim + 2, 4, 2), -1, dtype=np.int64)
+        for f in range(dim):
+            for d in range(dim):
+                for e in range(dim + 2):
+                    v, k = (C.c_int * 4)(), (C.c_int * 4)()
+                    cnt = lib.ref_diff_terms(dim, f, d, e, v, k)
+                    assert 0 <= cnt <= 4
+                    for i in range(cnt):
+                        terms[f, d, e, i] = (v[i], k[i])
+        out[f"terms{dim}d"] = terms
         pin = np.abs(rng.standard_normal((200, 11))) * 10.0 ** rng.uniform(-2, 2, (200, 11)) + 1.0e-3
         pin[:, 0] = rng.uniform(1.1, 1.7, 200)
         pin[:, 8:11] *= rng.choice([-1.0, 1.0], (200, 3))

@@ -127,3 +127,14 @@ extern "C" int emu_diff_accumulate(const EmuDiffDesc* d, int g, double beta, con
     }
     return 0;
 }
+
+/* the compile-time term tables the kernels are unrolled from */
+extern "C" int emu_diff_terms(int dim, int f, int d, int e, int var[4], int diff[4])
+{
+    const DiffTermList tl = dim == 2 ? DiffTerms<2>::get(f, d, e) : DiffTerms<3>::get(f, d, e);
+    for (int i = 0; i < tl.n; i++) {
+        var[i] = tl.t[i].var;
+        diff[i] = tl.t[i].diff;
+    }
+    return tl.n;
+}

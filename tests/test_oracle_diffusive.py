@@ -174,10 +174,28 @@ def test_temperature_conductivity_and_diffusivities_match_reference_golden(dim):
         assert [T, kappa] + D == ref.tolist()
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_term_tables_match_reference_golden(dim):
+    """Which derivative carries which diffusivity in which equation, in the order of accumulation: the oracle's tables and
+    the compile-time tables of the product kernels (hb2_diffusive.cuh: DiffTerms) against the reference's own
+    getCellDataOfDiffusiveFluxVariablesForDerivative / getCellDataOfDiffusiveFluxDiffusivities, compiled verbatim as members
+    of a stub class (oracle/build_ref.py: diffusive_term_tables; outputs in the golden fixture)."""
+    import emu_host
+
+    ref = DGOLD[f"terms{dim}d"]
+    nterms = 0
+    for f in range(dim):
+        for d in range(dim):
+            for e in range(dim + 2):
+                want = [tuple(int(x) for x in t) for t in ref[f, d, e] if t[0] >= 0]
+                assert orc.diff_terms(dim, f, d, e) == want, (f, d, e)
+                assert emu_host.diff_terms(dim, f, d, e) == want, (f, d, e)
+                nterms += len(want)
+    assert nterms == (45 if dim == 3 else 18)       # 3 x (7 + 4 + 4) and 2 x (5 + 4)
+
+
 def test_term_tables_are_the_stress_tensor():
-    """Which derivative carries which diffusivity in which equation is restated from the reference's tables
-    (FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp:654-2363), not extracted.  Cross-check: assembled symbolically the
-    tables give F_d = -(0, tau . e_f, u . tau . e_f + kappa dT/dx_f) with the Newtonian tau, for every direction."""
+    """Independent cross-check of the term tables (pinned in the test above): assembled symbolically they give F_d = -(0, tau . e_f, u . tau . e_f + kappa dT/dx_f) with the Newtonian tau, for every direction."""
     for dim in (2, 3):
         rng = np.random.default_rng(dim)
         mu, mu_v, kappa = 0.3, 0.07, 1.9
