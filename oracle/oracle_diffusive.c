@@ -17,9 +17,10 @@
  *   conductivity EquationOfThermalConductivityPrandtl.cpp:309   kappa = c_p mu / Pr
  *   RK update    NavierStokes.cpp:2085-2092   (conservative form of the diffusive flux)
  *
- * Parity status: the derivative and reconstruction kernels and the point formulas are pinned against the reference's
- * own code (oracle/build_ref.py: diffusive_*; tests/test_oracle_diffusive.py); which term goes into which equation is
- * restated from the tables cited above.
+ * Parity status: the derivative and reconstruction kernels, the point formulas and the term tables (which derivative
+ * carries which diffusivity in which equation, in the order of accumulation) are pinned against the reference's own code,
+ * compiled verbatim (oracle/build_ref.py: diffusive_kernels, diffusive_term_tables; tests/test_oracle_diffusive.py); the
+ * loop ranges and the order of the x / y / z derivative groups are restated from the driver cited above.
  */
 #include "oracle_diffusive.h"
 #include <math.h>
