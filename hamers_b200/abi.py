@@ -37,6 +37,7 @@ SYMBOLS = [
     "hb2_diffusive_plan_create", "hb2_diffusive_plan_destroy", "hb2_diffusive_plan_set_stream", "hb2_diffusive_plan_launches",
     "hb2_compute_diffusive_flux_dev", "hb2_compute_diffusive_flux_host", "hb2_advance_stage_ns_dev",
     "hb2_diffusive_fill_ghosts_periodic_dev", "hb2_diffusive_extract_view_dev", "hb2_diffusive_accumulate_dev",
+    "hb2_diffusive_divergence_accumulate_dev",
 ]
 
 WCNS5_JS, WCNS5_Z, WCNS6_LD = 0, 1, 2
@@ -456,6 +457,14 @@ class DiffusivePlan:
         fp = _ptr_table([p for d in range(self.dim) for p in _dev_ptrs(Fd[d], self.neq)])
         _check(self.lib.hb2_diffusive_accumulate_dev(self._h, int(num_ghosts), C.c_double(beta), fp,
                                                      _ptr_table(_dev_ptrs(U, self.neq))), "hb2_diffusive_accumulate_dev")
+
+    def divergence_accumulate(self, Q, dt: float, num_ghosts: int, beta: float, U):
+        """U += beta (-div F_d(Q)) without writing the diffusive side flux (bit-identical to compute_diffusive_flux +
+        accumulate).  Q: six-ghost state; U: (neq, ... with num_ghosts ghosts), not Q."""
+        _check(self.lib.hb2_diffusive_divergence_accumulate_dev(self._h, _ptr_table(_dev_ptrs(Q, self.neq)), C.c_double(dt),
+                                                                int(num_ghosts), C.c_double(beta),
+                                                                _ptr_table(_dev_ptrs(U, self.neq))),
+               "hb2_diffusive_divergence_accumulate_dev")
 
     def advance_stage_ns(self, num_ghosts: int, alpha, beta, U_int, Fc_int, Fd_int, S_int, U_out):
         """NavierStokes::advanceSingleStepOnPatch (conservative diffusive flux) on device tensors; rows with a zero

@@ -39,6 +39,8 @@ struct hb2_diff_plan_s {
     cudaStream_t stream;
     double* P[4];                 /* primitive scratch on the ghost box */
     double* Fn[5];                /* node-flux scratch (equation 0 unused) */
+    double* FnDir[3][5];          /* one node-flux set per direction, for the flux-free update (allocated on first use;
+                                     FnDir[0] aliases Fn) */
     double* stQ[5];               /* staging of the host-buffer entry point */
     double* stF[15];
     long long nside[3];
@@ -107,6 +109,15 @@ __global__ void __launch_bounds__(256) k_diff_accumulate(const __grid_constant__
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) diff_accumulate_thread<DIM>(A, t);
 }
 
+template <int DIM>
+__global__ void __launch_bounds__(256) k_diff_divergence_accumulate(const __grid_constant__ NsDivArgs A)
+{
+    const long long total = (long long)A.G6.n[0] * A.G6.n[1] * A.G6.n[2];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride)
+        diff_divergence_accumulate_thread<DIM>(A, t);
+}
+
 int grid_for(long long work, int sm_count)
 {
     const long long blocks = (work + 255) / 256;
@@ -143,6 +154,49 @@ int run_flux(hb2_diff_plan_t p, const double* const* Q, double dt, double* const
     return 0;
 }
 
+}  // namespace
+
+namespace {
+template <int DIM>
+int run_divergence(hb2_diff_plan_t p, const double* const* Q, double dt, int num_ghosts, double beta, double* const* U)
+{
+    const size_t bytes = sizeof(double) * (size_t)p->G.ncell_g;
+    for (int f = 0; f < DIM; f++)
+        for (int e = 1; e < DIM + 2; e++) {
+            if (f == 0) p->FnDir[0][e] = p->Fn[e];
+            if (!p->FnDir[f][e]) {
+                HB2D_CUDA(cudaMalloc(&p->FnDir[f][e], bytes));
+                HB2D_CUDA(cudaMemsetAsync(p->FnDir[f][e], 0, bytes, p->stream));
+            }
+        }
+    DiffPtrs A{};
+    for (int c = 0; c < DIM + 2; c++) A.Q[c] = Q[c];
+    for (int v = 0; v < DIM + 1; v++) A.P[v] = p->P[v];
+    k_diff_primitives<DIM><<<grid_for(p->G.ncell_g, p->sm_count), 256, 0, p->stream>>>(p->G, p->K, A);
+    for (int e = 0; e < DIM + 2; e++) A.Fn[e] = p->FnDir[0][e];
+    k_diff_node<DIM, 0><<<grid_for(diff_node_count<DIM, 0>(p->G), p->sm_count), 256, 0, p->stream>>>(p->G, p->K, A);
+    for (int e = 0; e < DIM + 2; e++) A.Fn[e] = p->FnDir[1][e];
+    k_diff_node<DIM, 1><<<grid_for(diff_node_count<DIM, 1>(p->G), p->sm_count), 256, 0, p->stream>>>(p->G, p->K, A);
+    if (DIM == 3) {
+        for (int e = 0; e < DIM + 2; e++) A.Fn[e] = p->FnDir[2][e];
+        k_diff_node<DIM, (DIM == 3 ? 2 : 1)><<<grid_for(diff_node_count<DIM, (DIM == 3 ? 2 : 1)>(p->G), p->sm_count), 256, 0, p->stream>>>(
+            p->G, p->K, A);
+    }
+    NsDivArgs D{};
+    D.G6 = p->G;
+    make_diff_geom(DIM, p->d.n, p->d.dx, num_ghosts, &D.GU);
+    D.neq = DIM + 2;
+    D.beta = beta;
+    D.dt = dt;
+    for (int f = 0; f < DIM; f++)
+        for (int e = 0; e < DIM + 2; e++) D.Fn[f][e] = p->FnDir[f][e];
+    for (int e = 0; e < DIM + 2; e++) D.U[e] = U[e];
+    const long long total = (long long)p->G.n[0] * p->G.n[1] * p->G.n[2];
+    k_diff_divergence_accumulate<DIM><<<grid_for(total, p->sm_count), 256, 0, p->stream>>>(D);
+    p->launches += 2 + DIM;
+    HB2D_CUDA(cudaGetLastError());
+    return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -204,6 +258,7 @@ int hb2_diffusive_plan_destroy(hb2_diff_plan_t p)
     for (int e = 0; e < 5; e++) {
         cudaFree(p->Fn[e]);
         cudaFree(p->stQ[e]);
+        for (int f = 1; f < 3; f++) cudaFree(p->FnDir[f][e]);     /* FnDir[0] aliases Fn */
     }
     for (int e = 0; e < 15; e++) cudaFree(p->stF[e]);
     delete p;
@@ -283,6 +338,15 @@ int hb2_diffusive_accumulate_dev(hb2_diff_plan_t p, int32_t num_ghosts, double b
     p->launches++;
     HB2D_CUDA(cudaGetLastError());
     return 0;
+}
+
+int hb2_diffusive_divergence_accumulate_dev(hb2_diff_plan_t p, const double* const* Q, double dt, int32_t num_ghosts, double beta,
+                                            double* const* U)
+{
+    if (!p || !Q || !U) return set_error(-1, "null argument");
+    if (num_ghosts < 0) return set_error(-31, "num_ghosts must be >= 0");
+    HB2D_CUDA(cudaSetDevice(p->device));
+    return p->d.dim == 2 ? run_divergence<2>(p, Q, dt, num_ghosts, beta, U) : run_divergence<3>(p, Q, dt, num_ghosts, beta, U);
 }
 
 int hb2_diffusive_fill_ghosts_periodic_dev(hb2_diff_plan_t p, double* const* U, int32_t periodic_mask)

@@ -364,6 +364,38 @@ HB2D_HD void diff_accumulate_thread(const NsAccArgs& A, long long t)
     }
 }
 
+/* The same update without materialising the diffusive side flux: both faces of the cell are reconstructed from the node
+ * fluxes of every direction (kept in three scratch sets) and differenced on the spot.  Every operation and its order are
+ * those of diff_face_thread followed by diff_accumulate_thread: bit-identical to that route. */
+struct NsDivArgs {
+    DiffGeom G6;      /* geometry of the node-flux scratch (six ghosts) */
+    DiffGeom GU;      /* geometry of U */
+    int neq;
+    double beta, dt;
+    const double* Fn[3][5];
+    double* U[5];
+};
+
+template <int DIM>
+HB2D_HD void diff_divergence_accumulate_thread(const NsDivArgs& A, long long t)
+{
+    const DiffGeom &G = A.G6, &GU = A.GU;
+    const int i = (int)(t % G.n[0]), j = (int)((t / G.n[0]) % G.n[1]), k = (int)(t / ((long long)G.n[0] * G.n[1]));
+    const long long x6 = (i + G.g[0]) + G.cs[1] * (j + G.g[1]) + G.cs[2] * (k + G.g[2]);
+    const long long xu = (i + GU.g[0]) + GU.cs[1] * (j + GU.g[1]) + GU.cs[2] * (k + GU.g[2]);
+    for (int e = 1; e < A.neq; e++) {
+        /* face "L" of the cell is the face whose high-side cell is the cell itself, face "R" the next one */
+        const double FxL = diff_reconstruct(A.Fn[0][e] + x6, G.cs[0], A.dt), FxR = diff_reconstruct(A.Fn[0][e] + x6 + G.cs[0], G.cs[0], A.dt);
+        const double FyB = diff_reconstruct(A.Fn[1][e] + x6, G.cs[1], A.dt), FyT = diff_reconstruct(A.Fn[1][e] + x6 + G.cs[1], G.cs[1], A.dt);
+        double div = -(FxR - FxL) / G.dx[0] - (FyT - FyB) / G.dx[1];
+        if (DIM == 3) {
+            const double FzB = diff_reconstruct(A.Fn[2][e] + x6, G.cs[2], A.dt), FzF = diff_reconstruct(A.Fn[2][e] + x6 + G.cs[2], G.cs[2], A.dt);
+            div -= (FzF - FzB) / G.dx[2];
+        }
+        A.U[e][xu] += A.beta * div;
+    }
+}
+
 /* ---- state management of a six-ghost level (what xfer::RefineSchedule::fillData does for a periodic single-patch level,
  * and the four-ghost view the convective reconstructor reads) ---- */
 struct DiffStatePtrs {

@@ -15,8 +15,9 @@ same allocation.  Single GPU, one patch covering the periodic level.  Two routes
 
   math = MATH_EXACT  both side fluxes materialised and combined by hb2_advance_stage_ns_dev in the reference's
                      association: a step is bit-identical to the oracle's composition of the same calls;
-  math = MATH_FAST   the fused convective stage (no convective flux or source array is ever written), then the diffusive
-                     divergence accumulated on top (hb2_diffusive_accumulate_dev): same terms, re-associated, <= 1e-12.
+  math = MATH_FAST   the fused convective stage, then the diffusive divergence accumulated on top
+                     (hb2_diffusive_divergence_accumulate_dev): no side flux or source array of either kind is ever
+                     written; same terms, re-associated, <= 1e-12.
 
 (tests/test_zz_gpu_diffusive.py; CPU emulation of both routes in tests/test_host_emu_diffusive.py.)"""
 from __future__ import annotations
@@ -49,8 +50,8 @@ class NavierStokesLevel:
         f64 = dict(dtype=torch.float64, device="cuda")
         g6 = tuple(x + 12 for x in reversed(self.n))
         self.S = [torch.zeros((self.neq,) + g6, **f64) for _ in range(3)]           # U0 and the two intermediate states
-        self.Fd = [torch.zeros((self.neq,) + self.dplan.side_shape(a), **f64) for a in range(dim)]
         if math == abi.MATH_EXACT:
+            self.Fd = [torch.zeros((self.neq,) + self.dplan.side_shape(a), **f64) for a in range(dim)]
             self.Fc = [torch.zeros((self.neq,) + self.dplan.side_shape(a), **f64) for a in range(dim)]
             self.src = torch.zeros((self.neq,) + tuple(reversed(self.n)), **f64)
         self.cur = 0
@@ -80,8 +81,8 @@ class NavierStokesLevel:
         S = self.S
         newest = S[states[-1]]
         # NavierStokes::computeFluxesAndSourcesOnPatch on the newest state (the RK table only uses its flux)
-        self.dplan.compute_diffusive_flux(newest, dt, self.Fd)
         if self.math == abi.MATH_EXACT:
+            self.dplan.compute_diffusive_flux(newest, dt, self.Fd)
             self.src.zero_()
             self.cplan.compute_flux_and_source(newest, dt, self.Fc, self.src)
             m = len(states)
@@ -90,7 +91,7 @@ class NavierStokesLevel:
                                         none + [self.src], S[out])
         else:
             self.cplan.fused_stage(alpha, beta, [S[i] for i in states], dt, S[out])
-            self.dplan.accumulate(6, float(beta[-1]), self.Fd, S[out])
+            self.dplan.divergence_accumulate(newest, dt, 6, float(beta[-1]), S[out])
         self.dplan.fill_ghosts_periodic(S[out])
 
     def rk_step(self, dt: float):

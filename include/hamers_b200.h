@@ -283,6 +283,12 @@ int hb2_advance_stage_ns_dev(hb2_diff_plan_t plan, int32_t num_ghosts, int32_t n
  * Same terms as NavierStokes.cpp:2085-2092 associated differently (a few ulp): the HB2_MATH_FAST route of the stage,
  * which never materialises the convective flux.  U[e]: cell data with num_ghosts ghost cells. */
 int hb2_diffusive_accumulate_dev(hb2_diff_plan_t plan, int32_t num_ghosts, double beta, const double* const* Fd, double* const* U);
+/* hb2_compute_diffusive_flux_dev(Q) + hb2_diffusive_accumulate_dev in one call that never writes the diffusive side flux
+ * either: the node fluxes of all directions stay in the plan's scratch and both faces of a cell are reconstructed where
+ * they are differenced.  Bit-identical to the two-call route.  Q: six-ghost state the flux is taken of; U: the state to
+ * update (num_ghosts ghost cells; may not alias Q). */
+int hb2_diffusive_divergence_accumulate_dev(hb2_diff_plan_t plan, const double* const* Q, double dt, int32_t num_ghosts,
+                                            double beta, double* const* U);
 
 #ifdef __cplusplus
 }

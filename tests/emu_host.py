@@ -180,3 +180,14 @@ def diff_terms(dim, f, d, e):
     var, dif = (C.c_int * 4)(), (C.c_int * 4)()
     n = dlib().emu_diff_terms(dim, f, d, e, var, dif)
     return [(var[i], dif[i]) for i in range(n)]
+
+
+def diff_divergence_accumulate(desc, tr, Q, dt, g, beta, U):
+    """in place on U: U += beta (-div F_d(Q)), no side flux written"""
+    d = _ddesc(desc, tr)
+    Q = np.ascontiguousarray(Q)
+    assert U.flags["C_CONTIGUOUS"]
+    rc = dlib().emu_diff_divergence_accumulate(C.byref(d), _pp([Q[c] for c in range(desc.neq)]), C.c_double(dt), C.c_int(g),
+                                               C.c_double(beta), _pp([U[e] for e in range(desc.neq)]))
+    assert rc == 0
+    return U

@@ -138,3 +138,46 @@ extern "C" int emu_diff_terms(int dim, int f, int d, int e, int var[4], int diff
     }
     return tl.n;
 }
+
+template <int DIM>
+static int run_div(const EmuDiffDesc* d, const double* const* Q, double dt, int g, double beta, double* const* U)
+{
+    DiffGeom G;
+    make_diff_geom(d->dim, d->n, d->dx, HB2_DIFF_G, &G);
+    DiffConsts K{d->gamma, d->c_v, d->mu, d->mu_v, d->c_p * d->mu / d->Pr};
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    std::vector<std::vector<double>> P(DIM + 1, std::vector<double>((size_t)G.ncell_g, nan));
+    std::vector<std::vector<double>> Fn(3 * (DIM + 2), std::vector<double>((size_t)G.ncell_g, nan));
+    DiffPtrs A{};
+    for (int c = 0; c < DIM + 2; c++) A.Q[c] = Q[c];
+    for (int v = 0; v < DIM + 1; v++) A.P[v] = P[v].data();
+    for (long long x = 0; x < G.ncell_g; x++) diff_primitives_thread<DIM>(K, A, x);
+    NsDivArgs D{};
+    D.G6 = G;
+    make_diff_geom(d->dim, d->n, d->dx, g, &D.GU);
+    D.neq = DIM + 2;
+    D.beta = beta;
+    D.dt = dt;
+    for (int f = 0; f < DIM; f++) {
+        for (int e = 0; e < DIM + 2; e++) {
+            A.Fn[e] = Fn[f * (DIM + 2) + e].data();
+            D.Fn[f][e] = A.Fn[e];
+        }
+        if (f == 0)
+            for (long long t = 0; t < diff_node_count<DIM, 0>(G); t++) diff_node_thread<DIM, 0>(G, K, A, t);
+        else if (f == 1)
+            for (long long t = 0; t < diff_node_count<DIM, 1>(G); t++) diff_node_thread<DIM, 1>(G, K, A, t);
+        else
+            for (long long t = 0; t < diff_node_count<DIM, (DIM == 3 ? 2 : 1)>(G); t++) diff_node_thread<DIM, (DIM == 3 ? 2 : 1)>(G, K, A, t);
+    }
+    for (int e = 0; e < DIM + 2; e++) D.U[e] = U[e];
+    const long long total = (long long)G.n[0] * G.n[1] * G.n[2];
+    for (long long t = 0; t < total; t++) diff_divergence_accumulate_thread<DIM>(D, t);
+    return 0;
+}
+
+extern "C" int emu_diff_divergence_accumulate(const EmuDiffDesc* d, const double* const* Q, double dt, int g, double beta,
+                                              double* const* U)
+{
+    return d->dim == 2 ? run_div<2>(d, Q, dt, g, beta, U) : run_div<3>(d, Q, dt, g, beta, U);
+}

@@ -202,3 +202,36 @@ def test_navier_stokes_level_steps_match_the_oracle_composition(dim, N, math, pr
     # viscosity acts: the result differs from the inviscid step, and mass is conserved to round-off
     assert abs(got[inner][0].sum() - U[0].sum()) < 1.0e-12 * U[0].size
     lvl.close()
+
+
+@pytest.mark.parametrize("dim,N,g", [(2, (24, 17), 6), (3, (13, 10, 12), 6), (3, (40, 33, 20), 4)])
+def test_flux_free_divergence_update(dim, N, g, product_lib):
+    """hb2_diffusive_divergence_accumulate_dev == hb2_compute_diffusive_flux_dev + hb2_diffusive_accumulate_dev bit for bit,
+    and both equal U + beta (-div F_d) formed from the oracle's side fluxes to round-off."""
+    import torch
+
+    desc, U = _state(dim, N)
+    Q6 = pb.pad_periodic(U, orc.GD)
+    rng = np.random.default_rng(2)
+    base = rng.standard_normal((desc.neq,) + tuple(n + 2 * g for n in reversed(N)))
+    dt, beta = 3.0e-4, 2.0 / 3.0
+    plan = _plan(desc)
+    Qd = torch.from_numpy(Q6).cuda()
+    Fd = [torch.zeros((desc.neq,) + desc.side_shape(a), dtype=torch.float64, device="cuda") for a in range(dim)]
+    two, one = torch.from_numpy(base).cuda(), torch.from_numpy(base).cuda()
+    plan.compute_diffusive_flux(Qd, dt, Fd)
+    plan.accumulate(g, beta, Fd, two)
+    plan.divergence_accumulate(Qd, dt, g, beta, one)
+    torch.cuda.synchronize()
+    assert torch.equal(one, two)
+    Fo = orc.compute_diffusive_flux(desc, TR, Q6, dt)
+    inner = (slice(None),) + ((slice(g, -g),) * dim if g else ())
+    want = base[inner].copy()
+    for a in range(dim):
+        want += beta * (-np.diff(Fo[a], axis=dim - a) / desc.dx[a])
+    got = one.cpu().numpy()
+    assert np.abs(got[inner] - want).max() <= 1.0e-13 * max(1.0, np.abs(want).max())
+    outside = got.copy()
+    outside[inner] = base[inner]
+    assert np.array_equal(outside, base)                     # ghosts untouched
+    plan.close()
