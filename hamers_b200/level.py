@@ -128,11 +128,12 @@ def neighbour_ranks(dec: "BoxDecomposition"):
             for o in itertools.product((-1, 0, 1), repeat=dec.dim) if any(o)}
 
 
-def oneshot_schedule(dec: "BoxDecomposition", ncomp: int):
+def oneshot_schedule(dec: "BoxDecomposition", ncomp: int, ghosts: int = G):
     """Single-phase ghost fill: every rank sends each of its (up to 26) neighbours the face / edge / corner region
     that neighbour's ghost box needs, all neighbours at once, ONE message per peer.  Directions owned by a single rank
     are periodic images of the rank's own box and are filled locally afterwards (`local_mask`), ghost-inclusive in the
-    exchanged directions.  Returns (sends, recvs, local_mask) with sends / recvs lists of PeerTraffic."""
+    exchanged directions.  `ghosts` is the halo width (4 for the convective path, 6 for a Navier-Stokes state).
+    Returns (sends, recvs, local_mask) with sends / recvs lists of PeerTraffic."""
     import itertools
 
     dim, n, grid = dec.dim, dec.n, dec.grid
@@ -143,12 +144,12 @@ def oneshot_schedule(dec: "BoxDecomposition", ncomp: int):
             continue
         peer = dec.rank_of([dec.coords[a] + o[a] for a in range(dim)])
         # my interior cells next to the face / edge / corner in direction o
-        slo = tuple(n[a] - G if o[a] > 0 else 0 for a in range(dim))
-        shi = tuple(G if o[a] < 0 else n[a] for a in range(dim))
+        slo = tuple(n[a] - ghosts if o[a] > 0 else 0 for a in range(dim))
+        shi = tuple(ghosts if o[a] < 0 else n[a] for a in range(dim))
         sends.setdefault(peer, []).append((_code(o), slo, shi))
         # my ghost cells in direction o, sent by the neighbour there towards -o
-        rlo = tuple(-G if o[a] < 0 else (n[a] if o[a] > 0 else 0) for a in range(dim))
-        rhi = tuple(0 if o[a] < 0 else (n[a] + G if o[a] > 0 else n[a]) for a in range(dim))
+        rlo = tuple(-ghosts if o[a] < 0 else (n[a] if o[a] > 0 else 0) for a in range(dim))
+        rhi = tuple(0 if o[a] < 0 else (n[a] + ghosts if o[a] > 0 else n[a]) for a in range(dim))
         recvs.setdefault(peer, []).append((_code(tuple(-x for x in o)), rlo, rhi))
 
     def finish(table):

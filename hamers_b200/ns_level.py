@@ -11,7 +11,9 @@ src/apps/Navier-Stokes/NavierStokes.cpp: per stage
 
 The state carries six ghost cells (max of the convective 4 and the diffusive 6, NavierStokes.cpp ctor) and both
 reconstructors read the same arrays (the convective plan is created with num_ghosts = 6), like SAMRAI hands them the
-same allocation.  Single GPU, one patch covering the periodic level.  Two routes per stage:
+same allocation.  One patch per rank: with torch.distributed initialised the periodic level is split into boxes like the
+Euler level (hamers_b200/level.py: BoxDecomposition) and the six-wide halos travel in the single-phase schedule (one NCCL
+message per neighbour, multi-box pack / unpack kernels); no other collective.  Two routes per stage:
 
   math = MATH_EXACT  both side fluxes materialised and combined by hb2_advance_stage_ns_dev in the reference's
                      association: a step is bit-identical to the oracle's composition of the same calls;
@@ -27,20 +29,27 @@ from typing import Sequence, Tuple
 import numpy as np
 
 from . import abi
+from .level import BoxDecomposition, exchange_halos_oneshot, oneshot_schedule
 
 
 class NavierStokesLevel:
     def __init__(self, dim: int, N: Sequence[int], species_gamma: float = 1.4, species_R: float = 1.0,
                  species_mu: float = 1.0e-3, species_mu_v: float = 0.0, species_c_p: float = 3.5, species_Pr: float = 0.72,
-                 domain: Tuple[float, float] = (0.0, 1.0), math: int = abi.MATH_EXACT, scheme: int = 0):
+                 domain: Tuple[float, float] = (0.0, 1.0), math: int = abi.MATH_EXACT, scheme: int = 0, grid=None,
+                 distributed: bool = True):
         import torch
+        import torch.distributed as dist
 
         self.torch = torch
-        self.dim, self.n = dim, tuple(int(x) for x in N[:dim])
+        self.dist = dist if (distributed and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+        nranks = self.dist.get_world_size() if self.dist else 1
+        rank = self.dist.get_rank() if self.dist else 0
+        self.decomp = BoxDecomposition(dim, tuple(int(x) for x in N[:dim]), nranks, rank, grid)
+        self.dim, self.n = dim, self.decomp.n                  # this rank's box
         self.neq = dim + 2
         L = domain[1] - domain[0]
         self.domain_lo = domain[0]
-        self.dx = tuple(L / n for n in self.n)
+        self.dx = tuple(L / n for n in self.decomp.N)
         c_v = 1.0 / (species_gamma - 1.0) * species_R           # EquationOfStateMixingRulesIdealGas.cpp:119
         self.math = math
         self.cplan = abi.Plan(dim, self.n, species_gamma=(species_gamma,), dx=self.dx, math=math, scheme=scheme,
@@ -57,6 +66,11 @@ class NavierStokesLevel:
         self.cur = 0
         self.ghosts_valid = False
         self.alpha, self.beta = abi.SSPRK3_ALPHA, abi.SSPRK3_BETA
+        self.oneshot = oneshot_schedule(self.decomp, self.neq, abi.DIFF_GHOSTS)
+        self._tables, self._bufs = {}, {}
+        if self.dist is not None:
+            assert all(n >= abi.DIFF_GHOSTS for n in self.n), "boxes must be at least one halo width wide"
+            self.dist.barrier()
 
     def close(self):
         self.cplan.close()
@@ -71,7 +85,33 @@ class NavierStokesLevel:
         return self.S[self.cur][self._interior_slices()]
 
     def coordinates(self):
-        return [self.domain_lo + (np.arange(n) + 0.5) * d for n, d in zip(self.n, self.dx)]
+        """cell-centre coordinates of this rank's box per axis (numpy)."""
+        return [self.domain_lo + (lo + np.arange(n) + 0.5) * d for lo, n, d in zip(self.decomp.lo, self.n, self.dx)]
+
+    # -- ghost fill: same-level, periodic; across ranks the single-phase schedule of the Euler level, six cells wide ------
+    def _buffer(self, key, numel):
+        b = self._bufs.get(key)
+        if b is None or b.numel() != numel:
+            b = self.torch.empty(numel, dtype=self.torch.float64, device="cuda")
+            self._bufs[key] = b
+        return b
+
+    def _table(self, key, boxes, offsets):
+        t = self._tables.get(key)
+        if t is None:
+            t = self.cplan.box_table(boxes, offsets)
+            self._tables[key] = t
+        return t
+
+    def fill_ghosts(self, U):
+        if self.dist is None:
+            self.dplan.fill_ghosts_periodic(U)
+            return
+        exchange_halos_oneshot(self.oneshot, self.neq,
+                               pack_many=lambda boxes, off, b: self.cplan.pack_boxes(U, self._table("s", boxes, off), b),
+                               unpack_many=lambda boxes, off, b: self.cplan.unpack_boxes(U, self._table("r", boxes, off), b),
+                               fill_local=lambda mask: self.dplan.fill_ghosts_periodic(U, mask),
+                               new_buffer=self._buffer, dist=self.dist)
 
     @property
     def launch_count(self) -> int:
@@ -92,7 +132,7 @@ class NavierStokesLevel:
         else:
             self.cplan.fused_stage(alpha, beta, [S[i] for i in states], dt, S[out])
             self.dplan.divergence_accumulate(newest, dt, 6, float(beta[-1]), S[out])
-        self.dplan.fill_ghosts_periodic(S[out])
+        self.fill_ghosts(S[out])
 
     def rk_step(self, dt: float):
         """One SSP-RK3 step (RungeKuttaLevelIntegrator.cpp:3894-3929): three stages, the result becomes the current state."""
@@ -100,7 +140,7 @@ class NavierStokesLevel:
         i0 = self.cur
         i1, i2 = (i0 + 1) % 3, (i0 + 2) % 3
         if not self.ghosts_valid:
-            self.dplan.fill_ghosts_periodic(self.S[i0])
+            self.fill_ghosts(self.S[i0])
         self._stage(a[0][:1], b[0][:1], [i0], dt, i1)
         self._stage(a[1][:2], b[1][:2], [i0, i1], dt, i2)
         self._stage(a[2][:3], b[2][:3], [i0, i1, i2], dt, i1)      # alpha[2][1] == 0: U1 is free to be overwritten

@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, dim, N, ncomp, q, oneshot=False):
+def _worker(rank, world, port, dim, N, ncomp, q, oneshot=False, G=G):
     import torch
     import torch.distributed as dist
 
@@ -78,7 +78,7 @@ def _worker(rank, world, port, dim, N, ncomp, q, oneshot=False):
                     shp = U[region(lo, hi)].shape
                     U[region(lo, hi)] = buf[off:off + int(np.prod(shp))].numpy().reshape(shp)
 
-            exchange_halos_oneshot(oneshot_schedule(dec, ncomp), ncomp, pack_many, unpack_many, fill_local, new_buffer, dist)
+            exchange_halos_oneshot(oneshot_schedule(dec, ncomp, G), ncomp, pack_many, unpack_many, fill_local, new_buffer, dist)
         else:
             exchange_halos(dec.halo_schedule(), ncomp, pack, unpack, fill_local, new_buffer, dist)
         # expected: periodic image of the global array
@@ -99,6 +99,24 @@ def test_halo_exchange_gloo(dim, N, world, oneshot):
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, dim, N, 3, q, oneshot)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, nans in res:
+        assert ok, f"rank {rank}: ghost box differs from the periodic image ({nans} cells never filled)"
+
+
+@pytest.mark.parametrize("dim,N,world", [(3, (16, 12, 8), 2), (2, (24, 12), 4)])
+def test_six_wide_halo_exchange_gloo(dim, N, world):
+    """The single-phase schedule with the Navier-Stokes halo width (six ghost cells)."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, dim, N, 2, q, True, 6)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(world)]

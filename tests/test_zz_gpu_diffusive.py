@@ -235,3 +235,22 @@ def test_flux_free_divergence_update(dim, N, g, product_lib):
     outside[inner] = base[inner]
     assert np.array_equal(outside, base)                     # ghosts untouched
     plan.close()
+
+
+def test_two_gpu_navier_stokes_level_matches_single_box():
+    """Box boundaries are invisible: two ranks with six-wide halos over NCCL against the one-box run (skipped on one GPU;
+    the schedule is covered on CPU by tests/test_level_gloo.py::test_six_wide_halo_exchange_gloo)."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29537", os.path.join(root, "tests", "multi_gpu_ns_check.py"), "--size", "40"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "bit-identical = True" in r.stdout
