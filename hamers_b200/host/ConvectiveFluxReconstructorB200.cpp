@@ -111,7 +111,7 @@ void ConvectiveFluxReconstructorWCNS6_LD_HLLC_HLL_B200::putToRestart(const HAMER
     restart_db->putDouble("d_constant_alpha_tau", d_constant_alpha_tau);
 }
 
-hb2_plan_t ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::getPlan(const hier::Patch& patch)
+hb2_plan_t ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::getPlan(const hier::Patch& patch, int num_ghosts)
 {
     const int dim = d_dim.getValue();
     const hier::IntVector interior_dims = patch.getBox().numberCells();
@@ -126,6 +126,7 @@ hb2_plan_t ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::getPlan(const hier
     }
     key.push_back(d_math);
     key.push_back(d_scheme);
+    key.push_back(num_ghosts);
     std::map<std::vector<double>, hb2_plan_t>::iterator it = d_plans.find(key);
     if (it != d_plans.end()) return it->second;
 
@@ -146,25 +147,35 @@ hb2_plan_t ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::getPlan(const hier
     desc.weno_alpha_tau = d_constant_alpha_tau;
     desc.math = d_math;
     desc.device = -1;
+    desc.num_ghosts = num_ghosts;
     hb2_plan_t plan = 0;
     if (hb2_plan_create(&desc, &plan) != 0) TBOX_ERROR(d_object_name << ": " << hb2_last_error() << std::endl);
     d_plans[key] = plan;
     return plan;
 }
 
-void ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::gatherConservative(hier::Patch& patch,
-                                                                         const HAMERS_SHARED_PTR<hier::VariableContext>& ctx,
-                                                                         std::vector<double*>& ptrs) const
+int ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::gatherConservative(hier::Patch& patch,
+                                                                        const HAMERS_SHARED_PTR<hier::VariableContext>& ctx,
+                                                                        std::vector<double*>& ptrs) const
 {
     const std::vector<HAMERS_SHARED_PTR<pdat::CellVariable<double> > >& vars = d_flow_model->getConservativeVariables();
+    int ghosts = -1;
     for (size_t v = 0; v < vars.size(); v++) {
         HAMERS_SHARED_PTR<pdat::CellData<double> > data(
             HAMERS_SHARED_PTR_CAST<pdat::CellData<double>, hier::PatchData>(patch.getPatchData(vars[v], ctx)));
         if (!data) TBOX_ERROR(d_object_name << ": conservative variable '" << vars[v]->getName() << "' is not cell data." << std::endl);
-        if (!(data->getGhostCellWidth() == d_num_conv_ghosts))
-            TBOX_ERROR(d_object_name << ": conservative variables need " << HB2_GHOSTS << " ghost cells." << std::endl);
+        /* at least the four layers this reconstructor reads, the same width in every direction and variable */
+        const hier::IntVector gw = data->getGhostCellWidth();
+        const int g = gw[0];
+        bool uniform = true;
+        for (int a = 0; a < d_dim.getValue(); a++) uniform = uniform && gw[a] == g;
+        if (!uniform || g < HB2_GHOSTS || g > 8 || (ghosts >= 0 && g != ghosts))
+            TBOX_ERROR(d_object_name << ": conservative variables need the same ghost width, at least " << HB2_GHOSTS
+                                     << " (at most 8), in every direction." << std::endl);
+        ghosts = g;
         for (int d = 0; d < data->getDepth(); d++) ptrs.push_back(data->getPointer(d));
     }
+    return ghosts;
 }
 
 void ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::computeConvectiveFluxAndSourceOnPatch(
@@ -175,7 +186,6 @@ void ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::computeConvectiveFluxAnd
     NULL_USE(time);
     NULL_USE(RK_step_number);
     const int dim = d_dim.getValue();
-    hb2_plan_t plan = getPlan(patch);
 
     HAMERS_SHARED_PTR<pdat::SideData<double> > convective_flux(
         HAMERS_SHARED_PTR_CAST<pdat::SideData<double>, hier::PatchData>(patch.getPatchData(variable_convective_flux, data_context)));
@@ -189,7 +199,7 @@ void ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::computeConvectiveFluxAnd
     TBOX_ASSERT(source->getDepth() == d_num_eqn);
 
     std::vector<double*> Q;
-    gatherConservative(patch, data_context, Q);
+    hb2_plan_t plan = getPlan(patch, gatherConservative(patch, data_context, Q));
     std::vector<double*> F, S;
     for (int n = 0; n < dim; n++)
         for (int e = 0; e < d_num_eqn; e++) F.push_back(convective_flux->getPointer(n, e));
@@ -207,10 +217,16 @@ void ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::advanceFusedStageOnPatch
     const size_t ncoef = alpha.size();
     if (beta.size() != ncoef || intermediate_contexts.size() != ncoef || ncoef == 0)
         TBOX_ERROR(d_object_name << ": alpha, beta and the intermediate contexts must have the same, non-zero length." << std::endl);
-    hb2_plan_t plan = getPlan(patch);
     std::vector<double*> U_int, U_out;
-    for (size_t m = 0; m < ncoef; m++) gatherConservative(patch, intermediate_contexts[m], U_int);
-    gatherConservative(patch, output_context, U_out);
+    int ghosts = -1;
+    for (size_t m = 0; m < ncoef; m++) {
+        const int g = gatherConservative(patch, intermediate_contexts[m], U_int);
+        if (ghosts >= 0 && g != ghosts) TBOX_ERROR(d_object_name << ": the intermediate states differ in ghost width." << std::endl);
+        ghosts = g;
+    }
+    if (gatherConservative(patch, output_context, U_out) != ghosts)
+        TBOX_ERROR(d_object_name << ": the output state differs in ghost width from the intermediate states." << std::endl);
+    hb2_plan_t plan = getPlan(patch, ghosts);
     if (hb2_fused_stage_host(plan, (int32_t)ncoef, alpha.data(), beta.data(), (const double* const*)U_int.data(), dt, U_out.data()) != 0)
         TBOX_ERROR(d_object_name << ": " << hb2_last_error() << std::endl);
 }

@@ -138,8 +138,11 @@ protected:
     double d_constant_alpha_tau;
 
 private:
-    hb2_plan_t getPlan(const hier::Patch& patch);
-    void gatherConservative(hier::Patch& patch, const HAMERS_SHARED_PTR<hier::VariableContext>& ctx, std::vector<double*>& ptrs) const;
+    /* one plan per (patch shape, ghost width of the state arrays): an application that allocates the state with more
+     * ghost cells than the four this reconstructor reads -- Navier-Stokes: six -- passes the same arrays */
+    hb2_plan_t getPlan(const hier::Patch& patch, int num_ghosts);
+    /* appends the component pointers; returns the ghost width of the data (uniform over variables and directions) */
+    int gatherConservative(hier::Patch& patch, const HAMERS_SHARED_PTR<hier::VariableContext>& ctx, std::vector<double*>& ptrs) const;
 
     int d_math;
     std::map<std::vector<double>, hb2_plan_t> d_plans; /* keyed by (n, dx) */

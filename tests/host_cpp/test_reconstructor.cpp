@@ -5,7 +5,8 @@
  * fused RK stage, dump the results.  tests/test_host_cpp.py writes the input, runs this program on the GPU box and
  * compares the dump with the oracle.
  *
- *   input  (binary): int32 dim, n[3], model, ns, math; double gamma[4], dx[3], dt; then ncomp ghost-box components
+ *   input  (binary): int32 dim, n[3], model, ns, math (+ 10 x scheme, + 100: the state is allocated with SIX ghost cells,
+ *                    like the Navier-Stokes application does); double gamma[4], dx[3], dt; then ncomp ghost-box components
  *   output (binary): per direction num_eqn side components, num_eqn source components, ncomp ghost-box components of
  *                    the fused first RK stage
  */
@@ -31,7 +32,8 @@ int main(int argc, char** argv)
     int32_t hdr[7];
     double gam[4], dx[3], dt;
     must(std::fread(hdr, 4, 7, fi) == 7 && std::fread(gam, 8, 4, fi) == 4 && std::fread(dx, 8, 3, fi) == 3 && std::fread(&dt, 8, 1, fi) == 1, "short header");
-    const int d = hdr[0], model = hdr[4], ns = hdr[5], math = hdr[6] % 10, scheme = hdr[6] / 10;
+    const int d = hdr[0], model = hdr[4], ns = hdr[5], math = hdr[6] % 10, scheme = (hdr[6] % 100) / 10;
+    const int state_ghosts = hdr[6] >= 100 ? 6 : 4;
     const tbox::Dimension dim((unsigned short)d);
 
     try {
@@ -63,8 +65,10 @@ int main(int argc, char** argv)
         HAMERS_SHARED_PTR<tbox::Database> restart_db(new tbox::Database("restart"));
         reconstructor.putToRestart(restart_db);
         must(restart_db->getInteger("d_constant_p") == 2, "putToRestart");
-        const hier::IntVector ghosts = reconstructor.getConvectiveFluxNumberOfGhostCells();
-        for (int a = 0; a < d; a++) must(ghosts[a] == 4, "ghost width");
+        const hier::IntVector conv_ghosts = reconstructor.getConvectiveFluxNumberOfGhostCells();
+        for (int a = 0; a < d; a++) must(conv_ghosts[a] == 4, "ghost width");
+        /* the application allocates max(convective, diffusive) ghost cells: 4 for Euler, 6 for Navier-Stokes */
+        const hier::IntVector ghosts = hier::IntVector::getOne(dim) * state_ghosts;
 
         /* one patch, interior box [0, n-1] */
         hier::IntVector lo(dim, 0), hi(dim, 0);
@@ -115,7 +119,7 @@ int main(int argc, char** argv)
         size_t ncell = 1, nghost = 1;
         for (int a = 0; a < d; a++) {
             ncell *= (size_t)nc[a];
-            nghost *= (size_t)(nc[a] + 8);
+            nghost *= (size_t)(nc[a] + 2 * state_ghosts);
         }
         for (int e = 0; e < neq; e++) std::fwrite(source->getPointer(e), 8, ncell, fo);
         for (size_t v = 0; v < cons.size(); v++) {

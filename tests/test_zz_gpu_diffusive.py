@@ -254,3 +254,46 @@ def test_two_gpu_navier_stokes_level_matches_single_box():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "bit-identical = True" in r.stdout
+
+
+@pytest.mark.parametrize("math", [100, 101])
+def test_convective_class_on_a_six_ghost_state(math, oracle_lib, tmp_path):
+    """ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200 handed patch data with six ghost cells (what the Navier-Stokes
+    application allocates): same fluxes, source and fused stage as on the four-ghost state (tests/host_cpp/
+    test_reconstructor.cpp with the +100 flag)."""
+    import struct
+    import subprocess
+
+    from common import assert_fast_parity, make_case
+    from test_host_cpp import build_driver
+
+    exe = build_driver()
+    desc, U = make_case("ss3d", "random")
+    Q4, Q6 = pb.pad_periodic(U, 4), pb.pad_periodic(U, 6)
+    dt = 7.5e-4
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as fh:
+        fh.write(struct.pack("7i", desc.dim, *desc.n, desc.model, desc.ns, math))
+        fh.write(struct.pack("8d", *(list(desc.gamma) + [0.0] * 3 + list(desc.dx) + [dt])))
+        fh.write(np.ascontiguousarray(Q6).tobytes())
+    r = subprocess.run([exe, fin, fout], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = np.fromfile(fout)
+    Fo, So = oracle_lib.compute_flux_and_source(desc, Q4, dt)
+    Uo = oracle_lib.advance_stage(desc, [1.0], [1.0], [Q4], [Fo], [So])
+    pos = 0
+    for a in range(3):
+        k = Fo[a].size
+        Fg = out[pos:pos + k].reshape(Fo[a].shape)
+        pos += k
+        if math % 10 == 0:
+            assert np.array_equal(Fg, Fo[a]), f"dir {a}"
+        else:
+            assert_fast_parity(Fg, Fo[a], f"dir {a}")
+    pos += So.size
+    Ug = out[pos:].reshape(Q6.shape)
+    in4, in6 = (slice(None),) + (slice(4, -4),) * 3, (slice(None),) + (slice(6, -6),) * 3
+    if math % 10 == 0:
+        assert np.array_equal(Ug[in6], Uo[in4])
+    else:
+        assert_fast_parity(Ug[in6], Uo[in4], "fused stage")
