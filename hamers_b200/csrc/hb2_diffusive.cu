@@ -68,6 +68,16 @@ __global__ void __launch_bounds__(256) k_diff_node(const __grid_constant__ DiffG
         diff_node_thread<DIM, FDIR>(G, K, A, t);
 }
 
+template <int DIM>
+__global__ void __launch_bounds__(256) k_diff_node_all(const __grid_constant__ DiffGeom G, const __grid_constant__ DiffConsts K,
+                                                       const __grid_constant__ DiffAllPtrs A)
+{
+    const long long total = diff_node_all_count<DIM>(G);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride)
+        diff_node_all_thread<DIM>(G, K, A, t);
+}
+
 template <int DIM, int FDIR>
 __global__ void __launch_bounds__(256) k_diff_face(const __grid_constant__ DiffGeom G, const __grid_constant__ DiffPtrs A, double dt)
 {
@@ -173,15 +183,12 @@ int run_divergence(hb2_diff_plan_t p, const double* const* Q, double dt, int num
     for (int c = 0; c < DIM + 2; c++) A.Q[c] = Q[c];
     for (int v = 0; v < DIM + 1; v++) A.P[v] = p->P[v];
     k_diff_primitives<DIM><<<grid_for(p->G.ncell_g, p->sm_count), 256, 0, p->stream>>>(p->G, p->K, A);
-    for (int e = 0; e < DIM + 2; e++) A.Fn[e] = p->FnDir[0][e];
-    k_diff_node<DIM, 0><<<grid_for(diff_node_count<DIM, 0>(p->G), p->sm_count), 256, 0, p->stream>>>(p->G, p->K, A);
-    for (int e = 0; e < DIM + 2; e++) A.Fn[e] = p->FnDir[1][e];
-    k_diff_node<DIM, 1><<<grid_for(diff_node_count<DIM, 1>(p->G), p->sm_count), 256, 0, p->stream>>>(p->G, p->K, A);
-    if (DIM == 3) {
-        for (int e = 0; e < DIM + 2; e++) A.Fn[e] = p->FnDir[2][e];
-        k_diff_node<DIM, (DIM == 3 ? 2 : 1)><<<grid_for(diff_node_count<DIM, (DIM == 3 ? 2 : 1)>(p->G), p->sm_count), 256, 0, p->stream>>>(
-            p->G, p->K, A);
-    }
+    /* the node fluxes of all directions in one pass: every derivative is evaluated once */
+    DiffAllPtrs N{};
+    for (int v = 0; v < DIM + 1; v++) N.P[v] = p->P[v];
+    for (int f = 0; f < DIM; f++)
+        for (int e = 0; e < DIM + 2; e++) N.Fn[f][e] = p->FnDir[f][e];
+    k_diff_node_all<DIM><<<grid_for(diff_node_all_count<DIM>(p->G), p->sm_count), 256, 0, p->stream>>>(p->G, p->K, N);
     NsDivArgs D{};
     D.G6 = p->G;
     make_diff_geom(DIM, p->d.n, p->d.dx, num_ghosts, &D.GU);
@@ -193,7 +200,7 @@ int run_divergence(hb2_diff_plan_t p, const double* const* Q, double dt, int num
     for (int e = 0; e < DIM + 2; e++) D.U[e] = U[e];
     const long long total = (long long)p->G.n[0] * p->G.n[1] * p->G.n[2];
     k_diff_divergence_accumulate<DIM><<<grid_for(total, p->sm_count), 256, 0, p->stream>>>(D);
-    p->launches += 2 + DIM;
+    p->launches += 3;
     HB2D_CUDA(cudaGetLastError());
     return 0;
 }

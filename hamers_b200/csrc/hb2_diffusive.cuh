@@ -227,6 +227,45 @@ HB2D_HD void diff_node_flux(const DiffGeom& G, const DiffConsts& K, const double
     }
 }
 
+/* The node fluxes of ALL flux directions at ghost-box cell x in one pass: the three directions draw on the same twelve
+ * (2-D: six) first derivatives, so each is evaluated once and used up to three times.  Term by term the arithmetic is that
+ * of diff_node_flux<DIM, FDIR>: the values are bit-identical. */
+template <int DIM>
+HB2D_HD void diff_node_flux_all(const DiffGeom& G, const DiffConsts& K, const double* const* P, long long x,
+                                double (&Fn)[DIM][DIM + 2])
+{
+    using TT = DiffTerms<DIM>;
+    double vel[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int a = 0; a < DIM; a++) vel[a] = P[a][x];
+    double D[TT::ND];
+    diff_diffusivities<DIM>(vel, K, D);
+    double der[DIM + 1][DIM];
+#pragma unroll
+    for (int v = 0; v < DIM + 1; v++) {
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            /* dT/dx_d enters the energy flux of direction d only; every velocity derivative is used by some direction */
+            der[v][d] = diff_first_derivative(P[v] + x, G.cs[d], G.dx_inv[d]);
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < DIM; f++) {
+#pragma unroll
+        for (int e = 0; e < DIM + 2; e++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) {
+                const DiffTermList tl = TT::get(f, d, e);
+#pragma unroll
+                for (int ti = 0; ti < 4; ti++)
+                    if (ti < tl.n) acc += D[tl.t[ti].diff] * der[tl.t[ti].var][d];
+            }
+            Fn[f][e] = acc;
+        }
+    }
+}
+
 /* ---- one thread of each kernel (the kernels of hb2_diffusive.cu are grid-stride loops over these; the host emulation
  * calls them from plain loops) ---- */
 struct DiffPtrs {
@@ -269,6 +308,38 @@ HB2D_HD void diff_node_thread(const DiffGeom& G, const DiffConsts& K, const Diff
     diff_node_flux<DIM, FDIR>(G, K, P, x, Fn);
 #pragma unroll
     for (int e = 1; e < DIM + 2; e++) A.Fn[e][x] = Fn[e];
+}
+
+struct DiffAllPtrs {
+    const double* P[4];
+    double* Fn[3][5];
+};
+
+template <int DIM>
+HB2D_HD long long diff_node_all_count(const DiffGeom& G)
+{
+    return (long long)(G.n[0] + 6) * (G.n[1] + 6) * (G.n[2] + (DIM == 3 ? 6 : 0));
+}
+
+/* node t of the interior extended by 3 cells in EVERY direction (the union of the three per-direction node sets plus
+ * the edge / corner nodes between them, which no face reads: (n + 6)^3 nodes instead of 3 n^2 (n + 6)) */
+template <int DIM>
+HB2D_HD void diff_node_all_thread(const DiffGeom& G, const DiffConsts& K, const DiffAllPtrs& A, long long t)
+{
+    const int e0 = G.n[0] + 6, e1 = G.n[1] + 6;
+    const int i = (int)(t % e0) - 3, j = (int)((t / e0) % e1) - 3;
+    const int k = (int)(t / ((long long)e0 * e1)) - (DIM == 3 ? 3 : 0);
+    const long long x = (i + G.g[0]) + G.cs[1] * (j + G.g[1]) + G.cs[2] * (k + G.g[2]);
+    const double* P[DIM + 1];
+#pragma unroll
+    for (int v = 0; v < DIM + 1; v++) P[v] = A.P[v];
+    double Fn[DIM][DIM + 2];
+    diff_node_flux_all<DIM>(G, K, P, x, Fn);
+#pragma unroll
+    for (int f = 0; f < DIM; f++) {
+#pragma unroll
+        for (int e = 1; e < DIM + 2; e++) A.Fn[f][e][x] = Fn[f][e];
+    }
 }
 
 template <int DIM, int FDIR>

@@ -158,18 +158,14 @@ static int run_div(const EmuDiffDesc* d, const double* const* Q, double dt, int 
     D.neq = DIM + 2;
     D.beta = beta;
     D.dt = dt;
-    for (int f = 0; f < DIM; f++) {
+    DiffAllPtrs N{};
+    for (int v = 0; v < DIM + 1; v++) N.P[v] = P[v].data();
+    for (int f = 0; f < DIM; f++)
         for (int e = 0; e < DIM + 2; e++) {
-            A.Fn[e] = Fn[f * (DIM + 2) + e].data();
-            D.Fn[f][e] = A.Fn[e];
+            N.Fn[f][e] = Fn[f * (DIM + 2) + e].data();
+            D.Fn[f][e] = N.Fn[f][e];
         }
-        if (f == 0)
-            for (long long t = 0; t < diff_node_count<DIM, 0>(G); t++) diff_node_thread<DIM, 0>(G, K, A, t);
-        else if (f == 1)
-            for (long long t = 0; t < diff_node_count<DIM, 1>(G); t++) diff_node_thread<DIM, 1>(G, K, A, t);
-        else
-            for (long long t = 0; t < diff_node_count<DIM, (DIM == 3 ? 2 : 1)>(G); t++) diff_node_thread<DIM, (DIM == 3 ? 2 : 1)>(G, K, A, t);
-    }
+    for (long long t = 0; t < diff_node_all_count<DIM>(G); t++) diff_node_all_thread<DIM>(G, K, N, t);
     for (int e = 0; e < DIM + 2; e++) D.U[e] = U[e];
     const long long total = (long long)G.n[0] * G.n[1] * G.n[2];
     for (long long t = 0; t < total; t++) diff_divergence_accumulate_thread<DIM>(D, t);
