@@ -3,14 +3,17 @@
  * (DiffusiveFluxReconstructorNodeSixthOrder of the reference, "SIXTH_ORDER" in its input decks) and of the
  * Navier-Stokes stage update that consumes it.  Entry points are declared in include/hamers_b200.h.
  *
- * Three kernels per call, all HBM-bound streaming kernels with x-contiguous (coalesced) accesses and grid-stride loops
- * over a grid sized as a multiple of the SM count:
+ * HBM-bound streaming kernels with x-contiguous (coalesced) accesses and grid-stride loops over a grid sized as a multiple
+ * of the SM count:
  *   k_diff_primitives   ghost box: 5 (4) conservative doubles in, velocity + temperature out
- *   k_diff_node<FDIR>   cells extended by 3 along FDIR: sixth-order derivatives of the primitives (stencil reads served
- *                       by L1/L2: each primitive value is used by 18 neighbouring nodes), diffusivities on the fly,
- *                       node flux of the momentum and energy equations out
+ *   k_diff_node_all     cells extended by 3 in every direction: the twelve sixth-order derivatives of the primitives, each
+ *                       evaluated once (stencil reads served by L1/L2: a primitive value is used by 18 neighbouring
+ *                       nodes), diffusivities on the fly, node fluxes of the momentum and energy equations of ALL flux
+ *                       directions out
  *   k_diff_face<FDIR>   faces: six-node reconstruction, times dt, all equations out (the continuity flux is +0.0 like
- *                       the reference's fillAll(0))
+ *                       the reference's fillAll(0))                                  -- the materialised route
+ *   k_diff_divergence_accumulate   both faces of a cell in every direction, differenced on the spot: U += beta (-div F_d)
+ *                                                                                    -- the flux-free route
  * No CPU fallback: every entry point needs a CUDA device.  Built with -fmad=false: reference operation order.
  */
 #include "../../include/hamers_b200.h"
@@ -56,16 +59,6 @@ __global__ void __launch_bounds__(256) k_diff_primitives(const __grid_constant__
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < G.ncell_g; x += stride)
         diff_primitives_thread<DIM>(K, A, x);
-}
-
-template <int DIM, int FDIR>
-__global__ void __launch_bounds__(256) k_diff_node(const __grid_constant__ DiffGeom G, const __grid_constant__ DiffConsts K,
-                                                   const __grid_constant__ DiffPtrs A)
-{
-    const long long total = diff_node_count<DIM, FDIR>(G);
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride)
-        diff_node_thread<DIM, FDIR>(G, K, A, t);
 }
 
 template <int DIM>
@@ -139,36 +132,16 @@ template <int DIM, int FDIR>
 int launch_dir(hb2_diff_plan_t p, const DiffPtrs& A, double dt)
 {
     const DiffGeom& G = p->G;
-    k_diff_node<DIM, FDIR><<<grid_for(diff_node_count<DIM, FDIR>(G), p->sm_count), 256, 0, p->stream>>>(G, p->K, A);
     k_diff_face<DIM, FDIR><<<grid_for(p->nside[FDIR], p->sm_count), 256, 0, p->stream>>>(G, A, dt);
-    p->launches += 2;
+    p->launches += 1;
     HB2D_CUDA(cudaGetLastError());
     return 0;
 }
 
+/* primitives, then the node fluxes of all directions in one pass (every derivative evaluated once) into the plan's
+ * per-direction scratch sets */
 template <int DIM>
-int run_flux(hb2_diff_plan_t p, const double* const* Q, double dt, double* const* flux)
-{
-    DiffPtrs A{};
-    for (int c = 0; c < DIM + 2; c++) A.Q[c] = Q[c];
-    for (int v = 0; v < DIM + 1; v++) A.P[v] = p->P[v];
-    for (int e = 0; e < DIM + 2; e++) A.Fn[e] = p->Fn[e];
-    k_diff_primitives<DIM><<<grid_for(p->G.ncell_g, p->sm_count), 256, 0, p->stream>>>(p->G, p->K, A);
-    p->launches++;
-    HB2D_CUDA(cudaGetLastError());
-    for (int f = 0; f < DIM; f++) {
-        for (int e = 0; e < DIM + 2; e++) A.F[e] = flux[f * (DIM + 2) + e];
-        int rc = f == 0 ? launch_dir<DIM, 0>(p, A, dt) : f == 1 ? launch_dir<DIM, 1>(p, A, dt) : launch_dir<DIM, (DIM == 3 ? 2 : 1)>(p, A, dt);
-        if (rc) return rc;
-    }
-    return 0;
-}
-
-}  // namespace
-
-namespace {
-template <int DIM>
-int run_divergence(hb2_diff_plan_t p, const double* const* Q, double dt, int num_ghosts, double beta, double* const* U)
+int node_stage(hb2_diff_plan_t p, const double* const* Q)
 {
     const size_t bytes = sizeof(double) * (size_t)p->G.ncell_g;
     for (int f = 0; f < DIM; f++)
@@ -183,12 +156,41 @@ int run_divergence(hb2_diff_plan_t p, const double* const* Q, double dt, int num
     for (int c = 0; c < DIM + 2; c++) A.Q[c] = Q[c];
     for (int v = 0; v < DIM + 1; v++) A.P[v] = p->P[v];
     k_diff_primitives<DIM><<<grid_for(p->G.ncell_g, p->sm_count), 256, 0, p->stream>>>(p->G, p->K, A);
-    /* the node fluxes of all directions in one pass: every derivative is evaluated once */
     DiffAllPtrs N{};
     for (int v = 0; v < DIM + 1; v++) N.P[v] = p->P[v];
     for (int f = 0; f < DIM; f++)
         for (int e = 0; e < DIM + 2; e++) N.Fn[f][e] = p->FnDir[f][e];
     k_diff_node_all<DIM><<<grid_for(diff_node_all_count<DIM>(p->G), p->sm_count), 256, 0, p->stream>>>(p->G, p->K, N);
+    p->launches += 2;
+    HB2D_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int DIM>
+int run_flux(hb2_diff_plan_t p, const double* const* Q, double dt, double* const* flux)
+{
+    int rc = node_stage<DIM>(p, Q);
+    if (rc) return rc;
+    for (int f = 0; f < DIM; f++) {
+        DiffPtrs A{};
+        for (int e = 0; e < DIM + 2; e++) {
+            A.Fn[e] = p->FnDir[f][e];
+            A.F[e] = flux[f * (DIM + 2) + e];
+        }
+        rc = f == 0 ? launch_dir<DIM, 0>(p, A, dt) : f == 1 ? launch_dir<DIM, 1>(p, A, dt) : launch_dir<DIM, (DIM == 3 ? 2 : 1)>(p, A, dt);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace
+
+namespace {
+template <int DIM>
+int run_divergence(hb2_diff_plan_t p, const double* const* Q, double dt, int num_ghosts, double beta, double* const* U)
+{
+    int rc = node_stage<DIM>(p, Q);
+    if (rc) return rc;
     NsDivArgs D{};
     D.G6 = p->G;
     make_diff_geom(DIM, p->d.n, p->d.dx, num_ghosts, &D.GU);
@@ -200,7 +202,7 @@ int run_divergence(hb2_diff_plan_t p, const double* const* Q, double dt, int num
     for (int e = 0; e < DIM + 2; e++) D.U[e] = U[e];
     const long long total = (long long)p->G.n[0] * p->G.n[1] * p->G.n[2];
     k_diff_divergence_accumulate<DIM><<<grid_for(total, p->sm_count), 256, 0, p->stream>>>(D);
-    p->launches += 3;
+    p->launches += 1;
     HB2D_CUDA(cudaGetLastError());
     return 0;
 }

@@ -189,47 +189,10 @@ HB2D_HD double diff_reconstruct(const double* p, long long stride, double dt)
     return F;
 }
 
-/* The node flux of all equations at ghost-box cell x for flux direction FDIR
- * (DiffusiveFluxReconstructorNode.cpp:888-1055 and the y / z copies): zero, then "+=" term by term.
- * P[v] are the primitive scratch arrays (velocity components, temperature) on the ghost box. */
-template <int DIM, int FDIR>
-HB2D_HD void diff_node_flux(const DiffGeom& G, const DiffConsts& K, const double* const* P, long long x,
-                            double (&Fn)[DIM + 2])
-{
-    using TT = DiffTerms<DIM>;
-    double vel[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-    for (int a = 0; a < DIM; a++) vel[a] = P[a][x];
-    double D[TT::ND];
-    diff_diffusivities<DIM>(vel, K, D);
-    /* every derivative is evaluated at most once (the reference's derivatives_*_computed maps) */
-    double der[DIM + 1][DIM];
-    bool have[DIM + 1][DIM] = {};
-#pragma unroll
-    for (int e = 0; e < DIM + 2; e++) {
-        double acc = 0.0;
-#pragma unroll
-        for (int d = 0; d < DIM; d++) {
-            const DiffTermList tl = TT::get(FDIR, d, e);
-#pragma unroll
-            for (int ti = 0; ti < 4; ti++) {
-                if (ti < tl.n) {
-                    const int v = tl.t[ti].var;
-                    if (!have[v][d]) {
-                        der[v][d] = diff_first_derivative(P[v] + x, G.cs[d], G.dx_inv[d]);
-                        have[v][d] = true;
-                    }
-                    acc += D[tl.t[ti].diff] * der[v][d];
-                }
-            }
-        }
-        Fn[e] = acc;
-    }
-}
-
-/* The node fluxes of ALL flux directions at ghost-box cell x in one pass: the three directions draw on the same twelve
- * (2-D: six) first derivatives, so each is evaluated once and used up to three times.  Term by term the arithmetic is that
- * of diff_node_flux<DIM, FDIR>: the values are bit-identical. */
+/* The node fluxes of ALL flux directions at ghost-box cell x in one pass (DiffusiveFluxReconstructorNode.cpp:888-1055 and
+ * the y / z copies: per direction and equation zero, then "+=" term by term, x-, y-, then z-derivative terms).  The three
+ * directions draw on the same twelve (2-D: six) first derivatives, so each is evaluated once -- like the reference's
+ * derivatives_*_computed maps do -- and used up to three times.  P[v]: primitive scratch arrays on the ghost box. */
 template <int DIM>
 HB2D_HD void diff_node_flux_all(const DiffGeom& G, const DiffConsts& K, const double* const* P, long long x,
                                 double (&Fn)[DIM][DIM + 2])
@@ -284,30 +247,6 @@ HB2D_HD void diff_primitives_thread(const DiffConsts& K, const DiffPtrs& A, long
     diff_primitives<DIM>(Q, K, P);
 #pragma unroll
     for (int v = 0; v < DIM + 1; v++) A.P[v][x] = P[v];
-}
-
-template <int DIM, int FDIR>
-HB2D_HD long long diff_node_count(const DiffGeom& G)
-{
-    return (long long)(G.n[0] + (FDIR == 0 ? 6 : 0)) * (G.n[1] + (FDIR == 1 ? 6 : 0)) * (G.n[2] + (FDIR == 2 ? 6 : 0));
-}
-
-/* node t of the interior extended by 3 cells on both sides of FDIR, x fastest */
-template <int DIM, int FDIR>
-HB2D_HD void diff_node_thread(const DiffGeom& G, const DiffConsts& K, const DiffPtrs& A, long long t)
-{
-    const int e0 = G.n[0] + (FDIR == 0 ? 6 : 0), e1 = G.n[1] + (FDIR == 1 ? 6 : 0);
-    const int i = (int)(t % e0) - (FDIR == 0 ? 3 : 0);
-    const int j = (int)((t / e0) % e1) - (FDIR == 1 ? 3 : 0);
-    const int k = (int)(t / ((long long)e0 * e1)) - (FDIR == 2 ? 3 : 0);
-    const long long x = (i + G.g[0]) + G.cs[1] * (j + G.g[1]) + G.cs[2] * (k + G.g[2]);
-    const double* P[DIM + 1];
-#pragma unroll
-    for (int v = 0; v < DIM + 1; v++) P[v] = A.P[v];
-    double Fn[DIM + 2];
-    diff_node_flux<DIM, FDIR>(G, K, P, x, Fn);
-#pragma unroll
-    for (int e = 1; e < DIM + 2; e++) A.Fn[e][x] = Fn[e];
 }
 
 struct DiffAllPtrs {

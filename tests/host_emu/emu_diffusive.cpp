@@ -2,7 +2,7 @@
  * emu_diffusive.cpp -- TEST-ONLY host emulation of the diffusive-flux kernels (never part of the product library).
  *
  * Compiles hamers_b200/csrc/hb2_diffusive.cuh with g++ and calls the very per-thread functions the kernels of
- * hb2_diffusive.cu call (diff_primitives_thread, diff_node_thread, diff_face_thread, advance_ns_thread) from plain loops
+ * hb2_diffusive.cu call (diff_primitives_thread, diff_node_all_thread, diff_face_thread, advance_ns_thread, ...) from plain loops
  * that stand in for the grid-stride loops.  Lets the CPU test suite check indexing and arithmetic against the oracle in a
  * container without a GPU; the GPU parity tests (pytest -m gpu) remain the parity tests proper.
  */
@@ -19,32 +19,49 @@ struct EmuDiffDesc {
     double gamma, c_v, mu, mu_v, c_p, Pr;
 };
 
+template <int DIM>
+struct NodeStage {
+    DiffGeom G;
+    DiffConsts K;
+    std::vector<std::vector<double>> P, Fn;
+    /* scratch starts as NaN: a node or primitive the kernels read without having written it shows up in the output */
+    NodeStage(const EmuDiffDesc* d, const double* const* Q)
+    {
+        make_diff_geom(d->dim, d->n, d->dx, HB2_DIFF_G, &G);
+        K = DiffConsts{d->gamma, d->c_v, d->mu, d->mu_v, d->c_p * d->mu / d->Pr};
+        const double nan = std::numeric_limits<double>::quiet_NaN();
+        P.assign(DIM + 1, std::vector<double>((size_t)G.ncell_g, nan));
+        Fn.assign(3 * (DIM + 2), std::vector<double>((size_t)G.ncell_g, nan));
+        DiffPtrs A{};
+        for (int c = 0; c < DIM + 2; c++) A.Q[c] = Q[c];
+        for (int v = 0; v < DIM + 1; v++) A.P[v] = P[v].data();
+        for (long long x = 0; x < G.ncell_g; x++) diff_primitives_thread<DIM>(K, A, x);
+        DiffAllPtrs N{};
+        for (int v = 0; v < DIM + 1; v++) N.P[v] = P[v].data();
+        for (int f = 0; f < DIM; f++)
+            for (int e = 0; e < DIM + 2; e++) N.Fn[f][e] = Fn[f * (DIM + 2) + e].data();
+        for (long long t = 0; t < diff_node_all_count<DIM>(G); t++) diff_node_all_thread<DIM>(G, K, N, t);
+    }
+};
+
 template <int DIM, int FDIR>
-static void run_dir(const DiffGeom& G, const DiffConsts& K, DiffPtrs& A, double dt, double* const* F)
+static void run_faces(NodeStage<DIM>& S, double dt, double* const* F)
 {
-    for (int e = 0; e < DIM + 2; e++) A.F[e] = F[FDIR * (DIM + 2) + e];
-    for (long long t = 0; t < diff_node_count<DIM, FDIR>(G); t++) diff_node_thread<DIM, FDIR>(G, K, A, t);
-    for (long long t = 0; t < diff_face_count<DIM, FDIR>(G); t++) diff_face_thread<DIM, FDIR>(G, A, dt, t);
+    DiffPtrs A{};
+    for (int e = 0; e < DIM + 2; e++) {
+        A.Fn[e] = S.Fn[FDIR * (DIM + 2) + e].data();
+        A.F[e] = F[FDIR * (DIM + 2) + e];
+    }
+    for (long long t = 0; t < diff_face_count<DIM, FDIR>(S.G); t++) diff_face_thread<DIM, FDIR>(S.G, A, dt, t);
 }
 
 template <int DIM>
 static int run(const EmuDiffDesc* d, const double* const* Q, double dt, double* const* F)
 {
-    DiffGeom G;
-    make_diff_geom(d->dim, d->n, d->dx, HB2_DIFF_G, &G);
-    DiffConsts K{d->gamma, d->c_v, d->mu, d->mu_v, d->c_p * d->mu / d->Pr};
-    /* scratch starts as NaN: a node or primitive the kernels read without having written it shows up in the output */
-    const double nan = std::numeric_limits<double>::quiet_NaN();
-    std::vector<std::vector<double>> P(DIM + 1, std::vector<double>((size_t)G.ncell_g, nan));
-    std::vector<std::vector<double>> Fn(DIM + 2, std::vector<double>((size_t)G.ncell_g, nan));
-    DiffPtrs A{};
-    for (int c = 0; c < DIM + 2; c++) A.Q[c] = Q[c];
-    for (int v = 0; v < DIM + 1; v++) A.P[v] = P[v].data();
-    for (int e = 0; e < DIM + 2; e++) A.Fn[e] = Fn[e].data();
-    for (long long x = 0; x < G.ncell_g; x++) diff_primitives_thread<DIM>(K, A, x);
-    run_dir<DIM, 0>(G, K, A, dt, F);
-    run_dir<DIM, 1>(G, K, A, dt, F);
-    if (DIM == 3) run_dir<DIM, (DIM == 3 ? 2 : 1)>(G, K, A, dt, F);
+    NodeStage<DIM> S(d, Q);
+    run_faces<DIM, 0>(S, dt, F);
+    run_faces<DIM, 1>(S, dt, F);
+    if (DIM == 3) run_faces<DIM, (DIM == 3 ? 2 : 1)>(S, dt, F);
     return 0;
 }
 
@@ -142,32 +159,17 @@ extern "C" int emu_diff_terms(int dim, int f, int d, int e, int var[4], int diff
 template <int DIM>
 static int run_div(const EmuDiffDesc* d, const double* const* Q, double dt, int g, double beta, double* const* U)
 {
-    DiffGeom G;
-    make_diff_geom(d->dim, d->n, d->dx, HB2_DIFF_G, &G);
-    DiffConsts K{d->gamma, d->c_v, d->mu, d->mu_v, d->c_p * d->mu / d->Pr};
-    const double nan = std::numeric_limits<double>::quiet_NaN();
-    std::vector<std::vector<double>> P(DIM + 1, std::vector<double>((size_t)G.ncell_g, nan));
-    std::vector<std::vector<double>> Fn(3 * (DIM + 2), std::vector<double>((size_t)G.ncell_g, nan));
-    DiffPtrs A{};
-    for (int c = 0; c < DIM + 2; c++) A.Q[c] = Q[c];
-    for (int v = 0; v < DIM + 1; v++) A.P[v] = P[v].data();
-    for (long long x = 0; x < G.ncell_g; x++) diff_primitives_thread<DIM>(K, A, x);
+    NodeStage<DIM> S(d, Q);
     NsDivArgs D{};
-    D.G6 = G;
+    D.G6 = S.G;
     make_diff_geom(d->dim, d->n, d->dx, g, &D.GU);
     D.neq = DIM + 2;
     D.beta = beta;
     D.dt = dt;
-    DiffAllPtrs N{};
-    for (int v = 0; v < DIM + 1; v++) N.P[v] = P[v].data();
     for (int f = 0; f < DIM; f++)
-        for (int e = 0; e < DIM + 2; e++) {
-            N.Fn[f][e] = Fn[f * (DIM + 2) + e].data();
-            D.Fn[f][e] = N.Fn[f][e];
-        }
-    for (long long t = 0; t < diff_node_all_count<DIM>(G); t++) diff_node_all_thread<DIM>(G, K, N, t);
+        for (int e = 0; e < DIM + 2; e++) D.Fn[f][e] = S.Fn[f * (DIM + 2) + e].data();
     for (int e = 0; e < DIM + 2; e++) D.U[e] = U[e];
-    const long long total = (long long)G.n[0] * G.n[1] * G.n[2];
+    const long long total = (long long)S.G.n[0] * S.G.n[1] * S.G.n[2];
     for (long long t = 0; t < total; t++) diff_divergence_accumulate_thread<DIM>(D, t);
     return 0;
 }
