@@ -36,7 +36,7 @@ class NavierStokesLevel:
     def __init__(self, dim: int, N: Sequence[int], species_gamma: float = 1.4, species_R: float = 1.0,
                  species_mu: float = 1.0e-3, species_mu_v: float = 0.0, species_c_p: float = 3.5, species_Pr: float = 0.72,
                  domain: Tuple[float, float] = (0.0, 1.0), math: int = abi.MATH_EXACT, scheme: int = 0, grid=None,
-                 distributed: bool = True):
+                 distributed: bool = True, device: str = "cuda"):
         import torch
         import torch.distributed as dist
 
@@ -56,7 +56,8 @@ class NavierStokesLevel:
                               num_ghosts=abi.DIFF_GHOSTS).use_torch_stream()
         self.dplan = abi.DiffusivePlan(dim, self.n, self.dx, species_gamma, c_v, species_mu, species_mu_v, species_c_p,
                                        species_Pr).use_torch_stream()
-        f64 = dict(dtype=torch.float64, device="cuda")
+        self.device = device            # "cuda"; the CPU test suite drives the same loop over emulation-backed plans
+        f64 = dict(dtype=torch.float64, device=device)
         g6 = tuple(x + 12 for x in reversed(self.n))
         self.S = [torch.zeros((self.neq,) + g6, **f64) for _ in range(3)]           # U0 and the two intermediate states
         if math == abi.MATH_EXACT:
@@ -92,7 +93,7 @@ class NavierStokesLevel:
     def _buffer(self, key, numel):
         b = self._bufs.get(key)
         if b is None or b.numel() != numel:
-            b = self.torch.empty(numel, dtype=self.torch.float64, device="cuda")
+            b = self.torch.empty(numel, dtype=self.torch.float64, device=self.device)
             self._bufs[key] = b
         return b
 
