@@ -37,7 +37,7 @@ SYMBOLS = [
     "hb2_diffusive_plan_create", "hb2_diffusive_plan_destroy", "hb2_diffusive_plan_set_stream", "hb2_diffusive_plan_launches",
     "hb2_compute_diffusive_flux_dev", "hb2_compute_diffusive_flux_host", "hb2_advance_stage_ns_dev",
     "hb2_diffusive_fill_ghosts_periodic_dev", "hb2_diffusive_extract_view_dev", "hb2_diffusive_accumulate_dev",
-    "hb2_diffusive_divergence_accumulate_dev",
+    "hb2_diffusive_divergence_accumulate_dev", "hb2_diffusive_max_spectral_radius_dev",
 ]
 
 WCNS5_JS, WCNS5_Z, WCNS6_LD = 0, 1, 2
@@ -465,6 +465,12 @@ class DiffusivePlan:
                                                                 int(num_ghosts), C.c_double(beta),
                                                                 _ptr_table(_dev_ptrs(U, self.neq))),
                "hb2_diffusive_divergence_accumulate_dev")
+
+    def max_spectral_radius(self, Q, species_c_p_eos: float, out):
+        """out[0] (1-element float64 CUDA tensor) = max diffusive spectral radius of the six-ghost state Q."""
+        _check(self.lib.hb2_diffusive_max_spectral_radius_dev(self._h, _ptr_table(_dev_ptrs(Q, self.neq)),
+                                                              C.c_double(species_c_p_eos), C.c_void_p(out.data_ptr())),
+               "hb2_diffusive_max_spectral_radius_dev")
 
     def advance_stage_ns(self, num_ghosts: int, alpha, beta, U_int, Fc_int, Fd_int, S_int, U_out):
         """NavierStokes::advanceSingleStepOnPatch (conservative diffusive flux) on device tensors; rows with a zero

@@ -121,6 +121,19 @@ __global__ void __launch_bounds__(256) k_diff_divergence_accumulate(const __grid
         diff_divergence_accumulate_thread<DIM>(A, t);
 }
 
+/* max over the ghost box of the diffusive spectral radius.  Non-negative doubles order like their bit patterns. */
+template <int DIM>
+__global__ void __launch_bounds__(256) k_diff_spectral_radius(const __grid_constant__ DiffGeom G, const __grid_constant__ DiffConsts K,
+                                                              double c_p_eos, const double* __restrict__ rho, unsigned long long* out)
+{
+    double m = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < G.ncell_g; x += stride)
+        m = fmax(m, diff_spectral_radius_cell<DIM>(G, K, c_p_eos, rho[x]));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
 int grid_for(long long work, int sm_count)
 {
     const long long blocks = (work + 255) / 256;
@@ -356,6 +369,22 @@ int hb2_diffusive_divergence_accumulate_dev(hb2_diff_plan_t p, const double* con
     if (num_ghosts < 0) return set_error(-31, "num_ghosts must be >= 0");
     HB2D_CUDA(cudaSetDevice(p->device));
     return p->d.dim == 2 ? run_divergence<2>(p, Q, dt, num_ghosts, beta, U) : run_divergence<3>(p, Q, dt, num_ghosts, beta, U);
+}
+
+int hb2_diffusive_max_spectral_radius_dev(hb2_diff_plan_t p, const double* const* Q, double species_c_p_eos, double* out_dev)
+{
+    if (!p || !Q || !out_dev) return set_error(-1, "null argument");
+    if (!(species_c_p_eos > 0.0)) return set_error(-30, "species_c_p_eos must be positive");
+    HB2D_CUDA(cudaSetDevice(p->device));
+    HB2D_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), p->stream));
+    unsigned long long* o = (unsigned long long*)out_dev;
+    if (p->d.dim == 2)
+        k_diff_spectral_radius<2><<<grid_for(p->G.ncell_g, p->sm_count), 256, 0, p->stream>>>(p->G, p->K, species_c_p_eos, Q[0], o);
+    else
+        k_diff_spectral_radius<3><<<grid_for(p->G.ncell_g, p->sm_count), 256, 0, p->stream>>>(p->G, p->K, species_c_p_eos, Q[0], o);
+    p->launches++;
+    HB2D_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int hb2_diffusive_fill_ghosts_periodic_dev(hb2_diff_plan_t p, double* const* U, int32_t periodic_mask)

@@ -406,6 +406,17 @@ HB2D_HD void diff_divergence_accumulate_thread(const NsDivArgs& A, long long t)
     }
 }
 
+/* Diffusive spectral radius of one cell (FlowModelSingleSpecies.cpp:4661-4665 MAX_DIFFUSIVITY; NavierStokes.cpp:884-886,
+ * 1083-1086): 2 max_d D_max / dx_d^2 with D_max = max(mu/rho, mu_v/rho, kappa/(rho c_p)) */
+template <int DIM>
+HB2D_HD double diff_spectral_radius_cell(const DiffGeom& G, const DiffConsts& K, double c_p_eos, double rho)
+{
+    double D_max = fmax(K.mu / rho, K.mu_v / rho);
+    D_max = fmax(D_max, K.kappa / (rho * c_p_eos));
+    if (DIM == 2) return 2.0 * fmax(D_max / (G.dx[0] * G.dx[0]), D_max / (G.dx[1] * G.dx[1]));
+    return 2.0 * fmax(D_max / (G.dx[0] * G.dx[0]), fmax(D_max / (G.dx[1] * G.dx[1]), D_max / (G.dx[2] * G.dx[2])));
+}
+
 /* ---- state management of a six-ghost level (what xfer::RefineSchedule::fillData does for a periodic single-patch level,
  * and the four-ghost view the convective reconstructor reads) ---- */
 struct DiffStatePtrs {

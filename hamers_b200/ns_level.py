@@ -51,6 +51,7 @@ class NavierStokesLevel:
         self.domain_lo = domain[0]
         self.dx = tuple(L / n for n in self.decomp.N)
         c_v = 1.0 / (species_gamma - 1.0) * species_R           # EquationOfStateMixingRulesIdealGas.cpp:119
+        self.c_p_eos = species_gamma / (species_gamma - 1.0) * species_R        # :113, the c_p of MAX_DIFFUSIVITY
         self.math = math
         self.cplan = abi.Plan(dim, self.n, species_gamma=(species_gamma,), dx=self.dx, math=math, scheme=scheme,
                               num_ghosts=abi.DIFF_GHOSTS).use_torch_stream()
@@ -134,6 +135,21 @@ class NavierStokesLevel:
             self.cplan.fused_stage(alpha, beta, [S[i] for i in states], dt, S[out])
             self.dplan.divergence_accumulate(newest, dt, 6, float(beta[-1]), S[out])
         self.fill_ghosts(S[out])
+
+    def stable_dt(self, cfl: float = 1.0) -> float:
+        """Level-wide stable time step: NavierStokes::computeSpectralRadiusesAndStableDtOnPatch per box (acoustic radii of
+        the convective plan, diffusive radius of the diffusive plan; NavierStokes.cpp:1006-1091), then the MAX all-reduce of
+        RungeKuttaLevelIntegrator::getLevelDt over ranks."""
+        torch = self.torch
+        if not hasattr(self, "_sr"):
+            self._sr = torch.zeros(5, dtype=torch.float64, device=self.device)
+        self.cplan.max_wave_speed(self.S[self.cur], self._sr[:4])
+        self.dplan.max_spectral_radius(self.S[self.cur], self.c_p_eos, self._sr[4:])
+        if self.dist is not None:
+            self.dist.all_reduce(self._sr, op=self.dist.ReduceOp.MAX)
+        sr = self._sr.cpu().numpy().copy()
+        self.spectral_radii = sr
+        return cfl / (max(float(sr[4]), float(sr[3])) + 1.0e-15)
 
     def rk_step(self, dt: float):
         """One SSP-RK3 step (RungeKuttaLevelIntegrator.cpp:3894-3929): three stages, the result becomes the current state."""

@@ -262,6 +262,13 @@ int hb2_compute_diffusive_flux_dev(hb2_diff_plan_t plan, const double* const* Q,
 /* same with host pointers (H2D, kernels and D2H inside the call): the API-preserving seam */
 int hb2_compute_diffusive_flux_host(hb2_diff_plan_t plan, const double* const* Q_host, double dt, double* const* flux_host);
 
+/* The diffusive part of NavierStokes::computeSpectralRadiusesAndStableDtOnPatch (NavierStokes.cpp:1064-1089; 2-D :868-891):
+ * out_dev[0] = max over the six-ghost box of 2 max_d MAX_DIFFUSIVITY / dx_d^2, MAX_DIFFUSIVITY = max(mu/rho, mu_v/rho,
+ * kappa/(rho c_p)) (FlowModelSingleSpecies.cpp:4661-4665) with c_p = species_c_p_eos, the isobaric specific heat of the
+ * equation of state (gamma/(gamma - 1) R).  The patch's stable dt is then
+ *   1 / (max(out_dev[0], <max sum of the acoustic radii: hb2_max_wave_speed_dev's 4th output>) + HAMERS_EPSILON). */
+int hb2_diffusive_max_spectral_radius_dev(hb2_diff_plan_t plan, const double* const* Q, double species_c_p_eos, double* out_dev);
+
 /* Same-level periodic ghost fill of a six-ghost state (what xfer::RefineSchedule::fillData does for one patch covering a
  * periodic level, RungeKuttaLevelIntegrator.cpp:1568, 1701); periodic_mask bit d = direction d is periodic. */
 int hb2_diffusive_fill_ghosts_periodic_dev(hb2_diff_plan_t plan, double* const* U, int32_t periodic_mask);

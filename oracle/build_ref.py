@@ -818,6 +818,53 @@ extern "C" int ref_diff_terms(int dim, int fdir, int ddir, int e, int var[4], in
 """
 
 
+def diffusive_dt_statements() -> str:
+    """MAX_DIFFUSIVITY (FlowModelSingleSpecies.cpp:4661-4665) and the diffusive spectral radius / stable
+    dt of NavierStokes::computeSpectralRadiusesAndStableDtOnPatch (NavierStokes.cpp:884-886 and 893 in 2-D, 1083-1086 and
+    1089-1091 in 3-D): the reference's statements compiled verbatim."""
+    def rd(rel):
+        with open(os.path.join(REF, rel)) as fh:
+            return fh.read()
+    fm = rd("src/flow/flow_models/single-species/FlowModelSingleSpecies.cpp")
+    ns = rd("src/apps/Navier-Stokes/NavierStokes.cpp")
+    s_d1 = statement(fm, r"D_max\[idx_max_diffusivity\] = fmax\(mu\[idx_max_diffusivity\]/rho\[idx\],")
+    s_d2 = statement(fm, r"D_max\[idx_max_diffusivity\] = fmax\(D_max\[idx_max_diffusivity\],")
+    ns3, ns2 = line_range(ns, 1000, 1095), line_range(ns, 830, 900)
+    s_r3 = statement(ns3, r"const double spectral_radius_diffusive = double\(2\)\*fmax\(")
+    s_r2 = statement(ns2, r"const double spectral_radius_diffusive = double\(2\)\*fmax\(")
+    s_m3 = statement(ns3, r"spectral_radiuses_and_dt\[3\] = fmax\(spectral_radius_tmp, spectral_radiuses_and_dt\[3\]\)")
+    s_t3 = statement(ns3, r"spectral_radiuses_and_dt\[3\] = double\(1\)/\(spectral_radiuses_and_dt\[3\] \+ HAMERS_EPSILON\)")
+    return f"""
+extern "C" void ref_diff_dt_point(int dim, const double in[9], double out[3])
+{{
+    /* in: mu, mu_v, kappa, c_p, rho, dx_0, dx_1, dx_2, max sum of the acoustic radii;  out: D_max, diffusive radius, dt */
+    const int idx = 0, idx_max_diffusivity = 0;
+    const double mu[1] = {{in[0]}}, mu_v[1] = {{in[1]}}, kappa[1] = {{in[2]}}, c_p[1] = {{in[3]}}, rho[1] = {{in[4]}};
+    const double dx_0 = in[5], dx_1 = in[6], dx_2 = in[7];
+    double D_max[1];
+    {s_d1}
+    {s_d2}
+    out[0] = D_max[0];
+    const double* max_D = D_max;
+    double radius;
+    if (dim == 3) {{
+        {s_r3}
+        radius = spectral_radius_diffusive;
+    }} else {{
+        {s_r2}
+        radius = spectral_radius_diffusive;
+        (void)dx_2;
+    }}
+    out[1] = radius;
+    double spectral_radius_tmp = radius;
+    double spectral_radiuses_and_dt[4] = {{0.0, 0.0, 0.0, in[8]}};
+    {s_m3}
+    {s_t3}
+    out[2] = spectral_radiuses_and_dt[3];
+}}
+"""
+
+
 def static_inline_functions(text: str) -> str:
     """Return the concatenation of every `static inline ...` function definition in text."""
     out = []
@@ -954,6 +1001,7 @@ def main() -> int:
     parts.append(path_statements6())
     parts.append(diffusive_kernels())
     parts.append(diffusive_term_tables())
+    parts.append(diffusive_dt_statements())
     gen = os.path.join(OUT, "_generated_ref_kernels.cpp")
     with open(gen, "w") as fh:
         fh.write("\n".join(parts))

@@ -446,3 +446,25 @@ def diff_reconstruct_array(dim, fdir, F_node, n, dt):
                                      (C.c_int * 3)(*[int(x) for x in list(n) + [1] * (3 - len(n))]), C.c_double(dt),
                                      out.ctypes.data_as(C.POINTER(C.c_double)))
     return out
+
+
+def ns_spectral_radii_and_dt(desc: PatchDesc, tr: Transport, c_p_eos: float, Q: np.ndarray):
+    """NavierStokes::computeSpectralRadiusesAndStableDtOnPatch on a six-ghost state: (acoustic radii per direction, stable
+    dt, maximum diffusive spectral radius)."""
+    Q = np.ascontiguousarray(Q, dtype=np.float64)
+    assert Q.shape == (desc.neq,) + diff_ghost_shape(desc)
+    out = (C.c_double * 5)()
+    d, t = desc.c(), tr.c()
+    L = lib()
+    L.orc_ns_spectral_radii_and_dt.restype = C.c_int
+    rc = L.orc_ns_spectral_radii_and_dt(C.byref(d), C.byref(t), C.c_double(c_p_eos), _pp([Q[c] for c in range(desc.neq)]), out)
+    assert rc == 0
+    return list(out)[:desc.dim], out[desc.dim], out[desc.dim + 1]
+
+
+def diff_max_diffusivity_point(dim, mu, mu_v, kappa, c_p_eos, rho, dx):
+    L = lib()
+    L.orc_diff_max_diffusivity.restype = C.c_double
+    L.orc_diff_spectral_radius.restype = C.c_double
+    D = L.orc_diff_max_diffusivity(C.c_double(mu), C.c_double(mu_v), C.c_double(kappa), C.c_double(c_p_eos), C.c_double(rho))
+    return D, L.orc_diff_spectral_radius(C.c_int(dim), C.c_double(D), (C.c_double * 3)(*[float(x) for x in list(dx) + [1.0] * (3 - len(dx))]))

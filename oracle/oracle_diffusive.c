@@ -262,6 +262,59 @@ int orc_compute_diffusive_flux(const orc_desc* d, const orc_transport* tr, const
     return 0;
 }
 
+/* FlowModelSingleSpecies.cpp:4661-4665: MAX_DIFFUSIVITY = max(mu/rho, mu_v/rho, kappa/(rho c_p)), c_p the isobaric specific
+ * heat of the equation of state (gamma/(gamma - 1) R, EquationOfStateMixingRulesIdealGas.cpp:113) */
+double orc_diff_max_diffusivity(double mu, double mu_v, double kappa, double c_p_eos, double rho)
+{
+    double D_max = fmax(mu / rho, mu_v / rho);
+    D_max = fmax(D_max, kappa / (rho * c_p_eos));
+    return D_max;
+}
+
+/* NavierStokes.cpp:1083-1086 (3-D), 884-886 (2-D): diffusive spectral radius of one cell */
+double orc_diff_spectral_radius(int dim, double D_max, const double* dx)
+{
+    if (dim == 2) return 2.0 * fmax(D_max / (dx[0] * dx[0]), D_max / (dx[1] * dx[1]));
+    return 2.0 * fmax(D_max / (dx[0] * dx[0]), fmax(D_max / (dx[1] * dx[1]), D_max / (dx[2] * dx[2])));
+}
+
+/* NavierStokes::computeSpectralRadiusesAndStableDtOnPatch (NavierStokes.cpp:585-1102; 3-D :1006-1089), no source terms:
+ * over the whole ghost box (six ghosts)
+ *   out[a]   = max (|u_a| + c)/dx_a,  a < dim
+ *   out[dim] = 1 / (max(max sum_a (|u_a| + c)/dx_a, max diffusive spectral radius) + HAMERS_EPSILON)
+ *   out[dim + 1] = max diffusive spectral radius (not an output of the reference; exported for the tests) */
+int orc_ns_spectral_radii_and_dt(const orc_desc* d, const orc_transport* tr, double c_p_eos, const double* const* Q, double* out)
+{
+    if (d->model != ORC_SINGLE_SPECIES || (d->dim != 2 && d->dim != 3)) return 1;
+    const int dim = d->dim;
+    const long ncell = orc_diff_ghost_size(d);
+    const double kappa = orc_diff_conductivity(tr->c_p, tr->mu, tr->Pr);
+    double sr[3] = {0.0, 0.0, 0.0}, sr_sum = 0.0, sr_diff = 0.0;
+    for (long x = 0; x < ncell; x++) {
+        const double rho = Q[0][x];
+        double vel[3], ke = 0.0;
+        for (int a = 0; a < dim; a++) {
+            vel[a] = Q[1 + a][x] / rho;
+            ke = (a == 0) ? vel[a] * vel[a] : ke + vel[a] * vel[a];
+        }
+        const double epsilon = Q[dim + 1][x] / rho - 1.0 / 2.0 * ke;
+        double p, c, eb;
+        orc_eos_point(d->gamma[0], rho, epsilon, &p, &c, &eb);
+        double sum = 0.0;
+        for (int a = 0; a < dim; a++) {
+            const double s = (fabs(vel[a]) + c) / d->dx[a];
+            sr[a] = fmax(sr[a], s);
+            sum = (a == 0) ? s : sum + s;
+        }
+        sr_sum = fmax(sr_sum, sum);
+        sr_diff = fmax(sr_diff, orc_diff_spectral_radius(dim, orc_diff_max_diffusivity(tr->mu, tr->mu_v, kappa, c_p_eos, rho), d->dx));
+    }
+    for (int a = 0; a < dim; a++) out[a] = sr[a];
+    out[dim] = 1.0 / (fmax(sr_diff, sr_sum) + 1.0e-15);
+    out[dim + 1] = sr_diff;
+    return 0;
+}
+
 /* NavierStokes::advanceSingleStepOnPatch, conservative diffusive form (NavierStokes.cpp:1947-2097, 3-D :2085-2092;
  * 2-D :1715-1751).  U on ghost boxes of width g (same for U_int and U_out), fluxes and sources on ghost 0. */
 int orc_advance_stage_ns(const orc_desc* d, int g, int ncoef, const double* alpha, const double* beta,

@@ -37,6 +37,13 @@ int orc_advance_stage_ns(const orc_desc* d, int g, int ncoef, const double* alph
                          const double* const* const* U_int, const double* const* const* Fc_int,
                          const double* const* const* Fd_int, const double* const* const* S_int, double* const* U_out);
 
+/* NavierStokes::computeSpectralRadiusesAndStableDtOnPatch without source terms, over the six-ghost box: out[0..dim-1] the
+ * acoustic spectral radii, out[dim] the stable dt, out[dim+1] the maximum diffusive spectral radius.  c_p_eos: isobaric
+ * specific heat of the equation of state, gamma/(gamma - 1) R. */
+int orc_ns_spectral_radii_and_dt(const orc_desc* d, const orc_transport* tr, double c_p_eos, const double* const* Q, double* out);
+double orc_diff_max_diffusivity(double mu, double mu_v, double kappa, double c_p_eos, double rho);
+double orc_diff_spectral_radius(int dim, double D_max, const double* dx);
+
 /* point formulas exported for pinning against oracle/_ref */
 double orc_diff_first_derivative(const double u[7], double dx_inv);
 double orc_diff_reconstruct(const double F[6], double dt);

@@ -191,3 +191,11 @@ def diff_divergence_accumulate(desc, tr, Q, dt, g, beta, U):
                                                C.c_double(beta), _pp([U[e] for e in range(desc.neq)]))
     assert rc == 0
     return U
+
+
+def diff_max_spectral_radius(desc, tr, c_p_eos, Q):
+    d = _ddesc(desc, tr)
+    f = dlib().emu_diff_max_spectral_radius
+    f.restype = C.c_double
+    rho = np.ascontiguousarray(Q[0])
+    return f(C.byref(d), C.c_double(c_p_eos), rho.ctypes.data_as(C.POINTER(C.c_double)))

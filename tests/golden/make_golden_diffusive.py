@@ -8,6 +8,8 @@ Run in the build container (needs /root/reference); the fixture is committed, th
   terms{dim}d        (flux dir, derivative dir, equation, term, 2) = (variable, diffusivity index) in the reference's order of
                      accumulation, -1 padded: FlowModelDiffusiveFluxUtilitiesSingleSpecies::getCellDataOfDiffusiveFluxVariables
                      ForDerivative / getCellDataOfDiffusiveFluxDiffusivities compiled verbatim (variable dim = temperature)
+  dt{dim}d_in (n, 9) = mu, mu_v, kappa, c_p, rho, dx[3], max acoustic sum;  dt{dim}d_out (n, 3) = MAX_DIFFUSIVITY, diffusive
+                     spectral radius, stable dt (FlowModelSingleSpecies.cpp:4661-4665; NavierStokes.cpp:884-893, 1083-1091)
   point{dim}d_in (n, 11) = gamma, c_v, rho, p, c_p, mu, Pr, mu_v, u, v, w;  point{dim}d_out (n, 2 + 13 | 10) = T, kappa, D_xx
 """
 import ctypes as C
@@ -62,6 +64,14 @@ def main():
             lib.ref_diff_point(dim, (C.c_double * 11)(*v), o)
             pout.append(list(o)[:2 + (13 if dim == 3 else 10)])
         out[f"point{dim}d_in"], out[f"point{dim}d_out"] = pin, np.array(pout)
+        # MAX_DIFFUSIVITY, diffusive spectral radius and stable dt (oracle/build_ref.py: diffusive_dt_statements)
+        din = np.abs(rng.standard_normal((200, 9))) * 10.0 ** rng.uniform(-3, 2, (200, 9)) + 1.0e-6
+        dout = []
+        for v in din:
+            o = (C.c_double * 3)()
+            lib.ref_diff_dt_point(dim, (C.c_double * 9)(*v), o)
+            dout.append(list(o))
+        out[f"dt{dim}d_in"], out[f"dt{dim}d_out"] = din, np.array(dout)
     np.savez_compressed(os.path.join(HERE, "diffusive_kernels.npz"), **out)
     print("wrote diffusive_kernels.npz", {k: v.shape for k, v in out.items()})
 

@@ -179,3 +179,14 @@ extern "C" int emu_diff_divergence_accumulate(const EmuDiffDesc* d, const double
 {
     return d->dim == 2 ? run_div<2>(d, Q, dt, g, beta, U) : run_div<3>(d, Q, dt, g, beta, U);
 }
+
+extern "C" double emu_diff_max_spectral_radius(const EmuDiffDesc* d, double c_p_eos, const double* rho)
+{
+    DiffGeom G;
+    make_diff_geom(d->dim, d->n, d->dx, HB2_DIFF_G, &G);
+    DiffConsts K{d->gamma, d->c_v, d->mu, d->mu_v, d->c_p * d->mu / d->Pr};
+    double m = 0.0;
+    for (long long x = 0; x < G.ncell_g; x++)
+        m = std::fmax(m, d->dim == 2 ? diff_spectral_radius_cell<2>(G, K, c_p_eos, rho[x]) : diff_spectral_radius_cell<3>(G, K, c_p_eos, rho[x]));
+    return m;
+}

@@ -138,3 +138,25 @@ def test_emulated_flux_free_divergence_is_the_two_call_route_bit_for_bit(dim, N,
     assert np.array_equal(one, two)
     assert np.array_equal(one[0], base[0])                                  # no diffusive mass flux
     assert min(N) < 3 or not np.array_equal(one[1:], base[1:])
+
+
+@pytest.mark.parametrize("dim,N", [(2, (24, 17)), (3, (13, 10, 12))])
+def test_emulated_diffusive_spectral_radius_and_stable_dt(dim, N):
+    """NavierStokes::computeSpectralRadiusesAndStableDtOnPatch: the diffusive spectral radius (emulated kernel arithmetic)
+    equals the oracle's, and combined with the acoustic part (the Euler path's hb2_max_wave_speed_dev quantity, oracle:
+    orc_spectral_radii_and_dt) it gives the oracle's stable dt."""
+    desc, U = state(dim, N)
+    Q6 = pb.pad_periodic(U, 6)
+    c_p_eos = desc.gamma[0] / (desc.gamma[0] - 1.0) * 1.0
+    for tr in (TR, orc.Transport(mu=1.0e-3, mu_v=0.4, c_p=3.5, c_v=2.5, Pr=0.05)):
+        radii, dt, sr_diff = orc.ns_spectral_radii_and_dt(desc, tr, c_p_eos, Q6)
+        assert emu_host.diff_max_spectral_radius(desc, tr, c_p_eos, Q6) == sr_diff > 0.0
+        euler = orc.lib()
+        out = (orc.C.c_double * 4)()
+        euler.orc_spectral_radii_and_dt(orc.C.byref(desc.c()), orc._pp([c for c in np.ascontiguousarray(pb.pad_periodic(U, 4))]), 1, out)
+        assert list(out)[:dim] == radii
+        assert dt == 1.0 / (max(sr_diff, 1.0 / out[dim]) + 1.0e-15) or abs(dt - 1.0 / (max(sr_diff, 1.0 / out[dim]) + 1.0e-15)) < 1e-15 * dt
+    # viscosity-limited on a fine mesh: the diffusive radius takes over
+    fine = orc.PatchDesc(dim=dim, n=N, gamma=desc.gamma, dx=tuple(1.0e-4 for _ in range(dim)))
+    _, dt_f, sr_f = orc.ns_spectral_radii_and_dt(fine, TR, c_p_eos, Q6)
+    assert abs(dt_f * (sr_f + 1.0e-15) - 1.0) < 1.0e-14

@@ -175,6 +175,17 @@ def test_temperature_conductivity_and_diffusivities_match_reference_golden(dim):
 
 
 @pytest.mark.parametrize("dim", [2, 3])
+def test_max_diffusivity_spectral_radius_and_dt_match_reference_golden(dim):
+    """MAX_DIFFUSIVITY (FlowModelSingleSpecies.cpp:4661-4665), the diffusive spectral radius and the stable dt of
+    NavierStokes::computeSpectralRadiusesAndStableDtOnPatch (NavierStokes.cpp:884-893, 1083-1091): the reference's statements
+    compiled verbatim; outputs in the golden fixture."""
+    for v, ref in zip(DGOLD[f"dt{dim}d_in"], DGOLD[f"dt{dim}d_out"]):
+        D, radius = orc.diff_max_diffusivity_point(dim, v[0], v[1], v[2], v[3], v[4], v[5:5 + dim])
+        dt = 1.0 / (max(radius, v[8]) + 1.0e-15)
+        assert [D, radius, dt] == ref.tolist()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
 def test_term_tables_match_reference_golden(dim):
     """Which derivative carries which diffusivity in which equation, in the order of accumulation: the oracle's tables and
     the compile-time tables of the product kernels (hb2_diffusive.cuh: DiffTerms) against the reference's own

@@ -297,3 +297,27 @@ def test_convective_class_on_a_six_ghost_state(math, oracle_lib, tmp_path):
         assert np.array_equal(Ug[in6], Uo[in4])
     else:
         assert_fast_parity(Ug[in6], Uo[in4], "fused stage")
+
+
+@pytest.mark.parametrize("dim,N", [(3, (16, 12, 10)), (2, (20, 14))])
+def test_navier_stokes_stable_dt(dim, N, product_lib):
+    """NavierStokes::computeSpectralRadiusesAndStableDtOnPatch: acoustic radii from the convective plan (on the six-ghost
+    state), diffusive radius from the diffusive plan, against the oracle; also where viscosity limits the step."""
+    import torch
+    from hamers_b200.ns_level import NavierStokesLevel
+
+    U, _, _ = pb.random_state(dim, N, seed=5, shock=True)
+    for mu, length in ((0.05, 1.0), (0.05, 1.0e-3)):
+        lvl = NavierStokesLevel(dim, N, species_gamma=1.4, species_R=1.0, species_mu=mu, species_mu_v=0.02, species_c_p=3.5,
+                                species_Pr=0.72, domain=(0.0, length))
+        lvl.interior().copy_(torch.from_numpy(U))
+        lvl.fill_ghosts(lvl.S[lvl.cur])
+        dt = lvl.stable_dt(1.0)
+        desc = orc.PatchDesc(dim=dim, n=N, gamma=(1.4,), dx=lvl.dx)
+        tr = orc.Transport(mu=mu, mu_v=0.02, c_p=3.5, c_v=1.0 / (1.4 - 1.0) * 1.0, Pr=0.72)
+        radii, dt_o, sr_diff = orc.ns_spectral_radii_and_dt(desc, tr, lvl.c_p_eos, pb.pad_periodic(U, 6))
+        assert lvl.spectral_radii[:dim].tolist() == radii and lvl.spectral_radii[4] == sr_diff
+        assert abs(dt - dt_o) <= 1.0e-15 * dt_o
+        if length < 1.0:
+            assert sr_diff > lvl.spectral_radii[3]            # viscosity-limited
+        lvl.close()
