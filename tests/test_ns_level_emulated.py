@@ -90,9 +90,9 @@ def oracle_ns_step(desc, tr, U, dt):
     return states[-1][inner]
 
 
-@pytest.mark.parametrize("math", [0, 1])
-@pytest.mark.parametrize("dim,N", [(3, (10, 8, 7)), (2, (14, 9))])
-def test_navier_stokes_level_loop_on_emulated_kernels(dim, N, math, monkeypatch):
+@pytest.mark.parametrize("dim,N,math,scheme", [(3, (10, 8, 7), 0, 0), (3, (10, 8, 7), 1, 0), (2, (14, 9), 0, 0), (2, (14, 9), 1, 0),
+                                                (3, (9, 8, 7), 0, 2)])          # last: WCNS6_LD, what the shipped TGV deck selects
+def test_navier_stokes_level_loop_on_emulated_kernels(dim, N, math, scheme, monkeypatch):
     import torch
     from hamers_b200 import ns_level
 
@@ -106,8 +106,9 @@ def test_navier_stokes_level_loop_on_emulated_kernels(dim, N, math, monkeypatch)
     p = 1.0 + 0.1 * np.cos(2 * np.pi * X[0])
     U = np.stack([rho] + [rho * v for v in vel] + [p / 0.4 + 0.5 * rho * sum(v * v for v in vel)])
     lvl = ns_level.NavierStokesLevel(dim, N, species_gamma=1.4, species_R=1.0, species_mu=0.05, species_mu_v=0.02,
-                                     species_c_p=3.5, species_Pr=0.72, domain=(0.0, 1.0), math=math, device="cpu")
-    desc = orc.PatchDesc(dim=dim, n=N, gamma=(1.4,), dx=lvl.dx)
+                                     species_c_p=3.5, species_Pr=0.72, domain=(0.0, 1.0), math=math, device="cpu",
+                                     scheme=scheme)
+    desc = orc.PatchDesc(dim=dim, n=N, gamma=(1.4,), dx=lvl.dx, scheme=scheme)
     tr = orc.Transport(mu=0.05, mu_v=0.02, c_p=3.5, c_v=1.0 / (1.4 - 1.0) * 1.0, Pr=0.72)
     lvl.interior().copy_(torch.from_numpy(U))
     dt = 2.0e-4
