@@ -151,11 +151,11 @@ def test_emulated_diffusive_spectral_radius_and_stable_dt(dim, N):
     for tr in (TR, orc.Transport(mu=1.0e-3, mu_v=0.4, c_p=3.5, c_v=2.5, Pr=0.05)):
         radii, dt, sr_diff = orc.ns_spectral_radii_and_dt(desc, tr, c_p_eos, Q6)
         assert emu_host.diff_max_spectral_radius(desc, tr, c_p_eos, Q6) == sr_diff > 0.0
-        euler = orc.lib()
-        out = (orc.C.c_double * 4)()
-        euler.orc_spectral_radii_and_dt(orc.C.byref(desc.c()), orc._pp([c for c in np.ascontiguousarray(pb.pad_periodic(U, 4))]), 1, out)
-        assert list(out)[:dim] == radii
-        assert dt == 1.0 / (max(sr_diff, 1.0 / out[dim]) + 1.0e-15) or abs(dt - 1.0 / (max(sr_diff, 1.0 / out[dim]) + 1.0e-15)) < 1e-15 * dt
+        Q4 = pb.pad_periodic(U, 4)
+        radii_euler, dt_euler = orc.spectral_radii_and_dt(desc, Q4)
+        assert radii_euler.tolist() == radii
+        want = 1.0 / (max(sr_diff, 1.0 / dt_euler) + 1.0e-15)
+        assert abs(dt - want) <= 1.0e-15 * dt
     # viscosity-limited on a fine mesh: the diffusive radius takes over
     fine = orc.PatchDesc(dim=dim, n=N, gamma=desc.gamma, dx=tuple(1.0e-4 for _ in range(dim)))
     _, dt_f, sr_f = orc.ns_spectral_radii_and_dt(fine, TR, c_p_eos, Q6)
