@@ -761,8 +761,9 @@ HB2_HD void push_cell(const Geom& G, double* const* table, int ci, int cj, int c
 template <class Tr>
 HB2_HD bool near_face(const Geom& G, int ci, int cj, int ck)
 {
-    bool near = (unsigned)(ci - HB2_G) >= (unsigned)(G.n[0] - 2 * HB2_G) || (unsigned)(cj - HB2_G) >= (unsigned)(G.n[1] - 2 * HB2_G);
-    if (Tr::DIM == 3) near = near || (unsigned)(ck - HB2_G) >= (unsigned)(G.n[2] - 2 * HB2_G);
+    /* signed comparisons: boxes narrower than two ghost widths (4 < n < 8) have cells near both faces */
+    bool near = ci < HB2_G || ci >= G.n[0] - HB2_G || cj < HB2_G || cj >= G.n[1] - HB2_G;
+    if (Tr::DIM == 3) near = near || ck < HB2_G || ck >= G.n[2] - HB2_G;
     return near;
 }
 

@@ -430,18 +430,20 @@ HB2D_HD int diff_wrap(int i, int n)
     return r < 0 ? r + n : r;
 }
 
-/* ghost-box cell t of G: ghost cells take the value of their periodic image in the interior; interior cells are left
- * alone.  Directions whose bit is not set in `mask` are left alone too. */
+/* ghost-box cell t of G: ghost cells of the directions in `mask` take the value of their periodic image. */
 HB2D_HD void diff_fill_periodic_thread(const DiffGeom& G, const DiffStatePtrs& A, int ncomp, int mask, long long t)
 {
     const int i = (int)(t % G.gd[0]) - G.g[0];
     const int j = (int)((t / G.gd[0]) % G.gd[1]) - G.g[1];
     const int k = (int)(t / ((long long)G.gd[0] * G.gd[1])) - G.g[2];
     const bool in0 = i >= 0 && i < G.n[0], in1 = j >= 0 && j < G.n[1], in2 = k >= 0 && k < G.n[2];
-    if (in0 && in1 && in2) return;
-    if ((!in0 && !(mask & 1)) || (!in1 && !(mask & 2)) || (!in2 && !(mask & 4))) return;
-    const long long s = (diff_wrap(i, G.n[0]) + G.g[0]) + G.cs[1] * (diff_wrap(j, G.n[1]) + G.g[1]) +
-                        G.cs[2] * (diff_wrap(k, G.n[2]) + G.g[2]);
+    /* a cell is filled when it is a ghost in at least one MASKED direction; only the masked coordinates are wrapped, so
+     * the fill is ghost-inclusive in the other directions (after an exchange across ranks in those directions the edge
+     * and corner ghosts come from the already exchanged slabs, like k_fill_periodic of the convective plan) */
+    if (!((!in0 && (mask & 1)) || (!in1 && (mask & 2)) || (!in2 && (mask & 4)))) return;
+    const int si = (mask & 1) ? diff_wrap(i, G.n[0]) : i, sj = (mask & 2) ? diff_wrap(j, G.n[1]) : j,
+              sk = (mask & 4) ? diff_wrap(k, G.n[2]) : k;
+    const long long s = (si + G.g[0]) + G.cs[1] * (sj + G.g[1]) + G.cs[2] * (sk + G.g[2]);
     for (int c = 0; c < ncomp; c++) A.U[c][t] = A.U[c][s];
 }
 

@@ -392,7 +392,8 @@ class UniformLevel:
         if self.dist is not None:
             self.dist.all_reduce(self._sr, op=self.dist.ReduceOp.MAX)
         self.spectral_radii = self._sr.cpu().numpy().copy()
-        return cfl / float(self.spectral_radii[3])
+        # Euler.cpp:846-861: dt = 1 / (spectral radius + HAMERS_EPSILON)
+        return cfl / (float(self.spectral_radii[3]) + 1.0e-15)
 
     def advance(self, dt: float, nsteps: int):
         for _ in range(nsteps):

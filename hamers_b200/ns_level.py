@@ -143,6 +143,11 @@ class NavierStokesLevel:
         torch = self.torch
         if not hasattr(self, "_sr"):
             self._sr = torch.zeros(5, dtype=torch.float64, device=self.device)
+        if not self.ghosts_valid:
+            # the diffusive radius is reduced over the whole six-ghost box like the reference's loop: stale or zero
+            # ghosts (rho = 0 -> mu/rho = inf) must not enter it
+            self.fill_ghosts(self.S[self.cur])
+            self.ghosts_valid = True
         self.cplan.max_wave_speed(self.S[self.cur], self._sr[:4])
         self.dplan.max_spectral_radius(self.S[self.cur], self.c_p_eos, self._sr[4:])
         if self.dist is not None:

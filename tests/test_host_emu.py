@@ -134,7 +134,7 @@ def test_emulated_other_interpolators(name, math, scheme, oracle_lib):
 
 
 @pytest.mark.parametrize("model,ns", [(0, 1), (1, 2)])
-@pytest.mark.parametrize("N", [(4, 4, 4), (5, 4, 6), (4, 33, 5), (65, 4, 4)])
+@pytest.mark.parametrize("N", [(4, 4, 4), (5, 4, 6), (4, 33, 5), (65, 4, 4), (5, 5, 6), (7, 7, 7)])
 def test_emulated_tiny_and_ragged_patches(N, model, ns, oracle_lib):
     """Patches as narrow as the ghost width (every cell is near BOTH faces of a direction: the fused ghost push then
     stores it into both neighbours), pencils shorter than one chunk, odd extents: fluxes, the fused stage and the pushed

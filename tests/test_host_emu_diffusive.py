@@ -95,6 +95,13 @@ def test_emulated_periodic_fill_and_ghost_view(dim, N):
     assert np.array_equal(part[rows], want6[rows])
     part[rows] = 0.0
     assert np.isnan(part[:, 0]).all() and np.isnan(part[:, -1]).all()
+    # across ranks (process grid (2,1,1)): the x ghosts of the interior rows arrive by the exchange, the rank-local
+    # directions are filled afterwards and must be ghost-inclusive in x, so that edge and corner ghosts are filled too
+    # (NavierStokesLevel.fill_ghosts: exchange, then fill_local(local_mask))
+    exch = np.full_like(want6, np.nan)
+    exch[rows] = want6[rows]
+    emu_host.diff_fill_periodic(desc, TR, exch, mask=(1 << dim) - 2)
+    assert np.array_equal(exch, want6)
 
 
 @pytest.mark.parametrize("math", [0, 1])
