@@ -117,6 +117,68 @@ def make_ic_device(level, model):
     del sin, s
 
 
+def bit_checksum(t):
+    """Order-independent checksum of a float64 tensor: the sum of the 64-bit patterns modulo 2^64.  Two runs whose cells
+    hold the same bits give the same number whatever the decomposition into boxes."""
+    import torch
+
+    return int(t.contiguous().view(torch.int64).sum().item())
+
+
+def level_parity(level, model, dist, n_total_steps, dt):
+    """What xfer::RefineSchedule::fillData guarantees (RungeKuttaLevelIntegrator.cpp:1568, 1701): a box boundary is
+    invisible.  (i) the error norms of the reference's own acceptance statistic
+    (problems/Euler/error_statistics/ConvergenceSingleSpecies.cpp:199-249: L1, L2, Linf of rho against the advected
+    exact solution; five-eqn: of Z_1, ConvergenceFiveEqnAllaire.cpp) after all steps run so far, reduced over ranks like
+    the reference's MPI_SUM / MPI_MAX; (ii) a bit checksum of the whole state (sum of the 64-bit patterns mod 2^64, summed
+    over ranks)."""
+    import torch
+
+    t = n_total_steps * dt
+    xs = [torch.as_tensor(c, dtype=torch.float64, device="cuda") for c in level.local_coordinates()]
+    s = (xs[0][None, None, :] + xs[1][None, :, None]) + xs[2][:, None, None]
+    inter = level.S[level.cur][level._interior_slices()]
+    if model == "ss":
+        exact = 1.0 + 0.5 * torch.sin(np.pi * (s - 3.0 * t))
+        num = inter[0]
+    else:
+        exact = 0.5 + 0.25 * torch.sin(np.pi * (s - 3.0 * t))
+        num = inter[-2]
+    err = (exact - num).abs()
+    dvol = float(np.prod(level.dx))
+    acc = torch.stack([err.sum() * dvol, (err * err).sum() * dvol, torch.tensor(dvol * err.numel(), dtype=torch.float64, device="cuda")])
+    emax = err.max().reshape(1)
+    del err, exact, s
+    cks = torch.tensor([bit_checksum(inter)], dtype=torch.int64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        dist.all_reduce(emax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cks, op=dist.ReduceOp.SUM)          # int64 addition wraps: still the sum modulo 2^64
+    return {"time": t, "steps_total": n_total_steps, "L1_error": float(acc[0] / acc[2]), "L2_error": float(torch.sqrt(acc[1] / acc[2])),
+            "Linf_error": float(emax[0]), "checksum": int(cks[0]) & 0xFFFFFFFFFFFFFFFF,
+            "statistic": "rho vs exact advected solution (ConvergenceSingleSpecies.cpp:199-249)" if model == "ss"
+            else "Z_1 vs exact advected solution (ConvergenceFiveEqnAllaire.cpp)"}
+
+
+def single_box_replica(args, Nglob, flow_model, gam, math, scheme, n_total_steps, dt, model):
+    """The same level as ONE box on this GPU (the N = 1 configuration: periodic-fill kernel, no exchange), advanced by the
+    same number of steps: its checksum and error norms are what a multi-GPU run must reproduce."""
+    import torch
+
+    from hamers_b200.level import UniformLevel
+
+    one = UniformLevel(3, Nglob, flow_model=flow_model, species_gamma=gam, math=math, scheme=scheme, distributed=False)
+    make_ic_device(one, model)
+    for _ in range(n_total_steps):
+        one.rk_step(dt)
+    torch.cuda.synchronize()
+    out = level_parity(one, model, None, n_total_steps, dt)
+    one.close()
+    del one
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     """CPU arm: the oracle (reference-structured restatement, gcc -O3, one OpenMP thread per core standing in
     for one MPI rank, 32^3 patches) on a bounded sample of the same workload."""
@@ -240,6 +302,29 @@ def run_ours(args):
     sec = ms * 1e-3
     value = ncell_global * 3 * args.steps / sec
 
+    # parity of the run itself: error norms against the exact solution + bit checksum; for N > 1 rank 0 then repeats the run
+    # as one box (N = 1 configuration) and the two must agree bit for bit
+    n_total = max(args.warmup, 0) + args.steps
+    parity = level_parity(level, args.model, dist, n_total, dt)
+    if world > 1 and not args.no_replica:
+        if ncell_global <= 640 ** 3:
+            rep = None
+            if rank == 0:
+                rep = single_box_replica(args, Nglob, flow_model, gam, math, scheme, n_total, dt, args.model)
+            if rank == 0:
+                parity["n1_checksum"] = rep["checksum"]
+                parity["n1_L1_error"] = rep["L1_error"]
+                parity["n1_L2_error"] = rep["L2_error"]
+                parity["matches_n1"] = bool(rep["checksum"] == parity["checksum"])
+                parity["n1_source"] = "same level advanced as ONE box on rank 0's GPU in this run (outside the timed region)"
+            dist.barrier()
+        else:
+            parity["matches_n1"] = None
+            parity["n1_source"] = "level too large for one GPU next to this rank's box: not replicated"
+    elif world == 1:
+        parity["matches_n1"] = True
+        parity["n1_source"] = "this is the N = 1 run"
+
     # sanity of the run itself: the solution must stay finite and close to the advected wave
     rho_min = float(level.interior()[0].min())
     rho_max = float(level.interior()[0].max())
@@ -303,7 +388,7 @@ def run_ours(args):
             "config": dict(workload_config(args), global_cells=list(Nglob), process_grid=list(grid),
                            cells_per_gpu=ncell_local, parallelism=f"box{world}"),
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "roofline_hbm": roofline_hbm,
-            "sanity": {"finite": finite, "rho_min": rho_min, "rho_max": rho_max},
+            "sanity": {"finite": finite, "rho_min": rho_min, "rho_max": rho_max}, "parity": parity,
         }
 
     # ---- end-to-end: host buffers through the C ABI (N = 1: advanceLevel on host memory) ----------
@@ -338,6 +423,29 @@ def run_ours(args):
                        "size": n, "ms_per_step": 1e3 * el / args.e2e_steps, "launches": plan.launch_count - k0,
                        "api": "hb2_advance_level_host (advanceLevel on pinned host memory: H2D U^n, 3 stages on device, D2H U^{n+1})"}
         plan.close()
+    elif not args.no_e2e:
+        # N > 1: one host box per rank (what each MPI rank of the reference owns); per step H2D of the box, ghost exchange
+        # over NVLink, three stages, D2H of the new box.  Wall clock between barriers, max over ranks.
+        inter = level.S[level.cur][level._interior_slices()]
+        host = torch.empty(inter.shape, dtype=torch.float64).pin_memory()
+        host.copy_(inter)
+        torch.cuda.synchronize()
+        level.rk_step_host(host, dt)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            level.rk_step_host(host, dt)
+        barrier()
+        el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        nbytes = host.numel() * 8 * world
+        if rank == 0:
+            el = float(el[0])
+            line["e2e"] = {"value": ncell_global * 3 * args.e2e_steps / el, "unit": "cell-updates/s",
+                           "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": args.e2e_steps,
+                           "size": list(Nglob), "ms_per_step": 1e3 * el / args.e2e_steps,
+                           "api": "UniformLevel.rk_step_host: one pinned host box per rank (interior cells); per step H2D, NVLink "
+                                  "ghost exchange, 3 fused stages, D2H; bytes summed over ranks"}
     elif rank == 0:
         line["e2e"] = None
 
@@ -392,6 +500,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-replica", action="store_true", help="N > 1: skip the one-box replica behind parity.matches_n1")
     args = ap.parse_args()
     if args.e2e_size <= 0:
         args.e2e_size = args.size

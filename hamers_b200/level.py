@@ -239,7 +239,8 @@ class UniformLevel:
 
     def __init__(self, dim: int, N: Sequence[int], flow_model: int = 0, species_gamma: Sequence[float] = (1.4,),
                  domain: Tuple[float, float] = (-1.0, 1.0), math: int = 1, weno_p: int = 2,
-                 grid: Optional[Sequence[int]] = None, push: Optional[bool] = None, scheme: int = 0):
+                 grid: Optional[Sequence[int]] = None, push: Optional[bool] = None, scheme: int = 0,
+                 distributed: bool = True):
         import itertools
         import os
 
@@ -249,7 +250,9 @@ class UniformLevel:
         from . import abi
 
         self.torch = torch
-        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        # distributed=False: the whole level as one box on this GPU even inside a torchrun job (the N = 1 replica that
+        # multi-GPU runs are compared with)
+        self.dist = dist if (distributed and dist.is_available() and dist.is_initialized()) else None
         nranks = self.dist.get_world_size() if self.dist else 1
         rank = self.dist.get_rank() if self.dist else 0
         self.decomp = BoxDecomposition(dim, N, nranks, rank, grid)
@@ -381,6 +384,17 @@ class UniformLevel:
         self.cur = i1
         self.ghosts_valid = True
         self.time += dt
+
+    def rk_step_host(self, host, dt: float):
+        """One SSP-RK3 step on HOST memory: `host` is this rank's box, interior cells only, (ncomp, *cell_shape), pinned
+        torch tensor.  H2D of the box, same-level ghost fill across ranks, three fused stages, D2H of the new interior
+        (the per-rank form of hb2_advance_level_host when the level is spread over several GPUs)."""
+        torch = self.torch
+        self.S[self.cur][self._interior_slices()].copy_(host, non_blocking=True)
+        self.ghosts_valid = False
+        self.rk_step(dt)
+        host.copy_(self.S[self.cur][self._interior_slices()], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
 
     def stable_dt(self, cfl: float = 1.0) -> float:
         """Level-wide stable time step: Euler::computeSpectralRadiusesAndStableDtOnPatch per box, then the MAX
