@@ -20,10 +20,12 @@
 
 int orc_num_eqn(const orc_desc* d)
 {
+    if (d->model == ORC_FOUR_EQN_CONSERVATIVE) return d->dim + 1 + d->ns;
     return d->model == ORC_SINGLE_SPECIES ? d->dim + 2 : d->dim + 2 * d->ns;
 }
 int orc_num_comp(const orc_desc* d)
 {
+    if (d->model == ORC_FOUR_EQN_CONSERVATIVE) return d->dim + 1 + d->ns;
     return d->model == ORC_SINGLE_SPECIES ? d->dim + 2 : d->dim + 2 * d->ns + 1;
 }
 static int nz_of(const orc_desc* d) { return d->dim == 3 ? d->n[2] : 1; }
@@ -156,6 +158,46 @@ static inline double fe_back_pressure(double rho_avg, double c_avg, double W0, d
 static inline double adv_source_term(double um_R, double um_L, double u_R, double u_L, double um_RR, double um_LL, double dx)
 {
     return (3.0 / 2.0 * (um_R - um_L) - 3.0 / 10.0 * (u_R - u_L) + 1.0 / 30.0 * (um_RR - um_LL)) / dx;
+}
+
+/* ---- four-eqn conservative model: mixture of ideal gases closed by MASS fractions ----
+ * EquationOfStateMixingRulesIdealGas.cpp:108-119 (species c_p, c_v), :7000-7120 (array form of
+ * computeMixtureThermodynamicPropertiesWithMassFractions: c_p += Y_i c_p_i, c_v += Y_i c_v_i, gamma = c_p/c_v),
+ * EquationOfStateIdealGas.cpp:5756 (p), :6414 (epsilon from p), :8157 (Gamma = gamma - 1),
+ * EquationOfStateMixingRulesIdealGas.cpp:6406-6409 (Psi_i = ((c_p_i - gamma c_v_i)/c_v + gamma - 1) epsilon),
+ * FlowModelFourEqnConservative.cpp:5180-5430 (c = sqrt(Gamma p/rho + sum Y_i Psi_i)).  Pinned through orc_path_points7. */
+static inline double fc_species_c_p(double gamma, double R) { return gamma / (gamma - 1.0) * R; }
+static inline double fc_species_c_v(double gamma, double R) { return 1.0 / (gamma - 1.0) * R; }
+static inline double fc_accumulate(double acc, double Y, double c_species) { return acc + Y * c_species; }
+static inline double fc_gamma(double c_p, double c_v) { return c_p / c_v; }
+static inline double fc_psi(double c_p_i, double c_v_i, double gamma, double c_v, double epsilon)
+{
+    return ((c_p_i - gamma * c_v_i) / c_v + gamma - 1.0) * epsilon;
+}
+/* gamma[0..ns) species gammas, gamma[ns..2ns) species R (see orc_riemann_point) */
+static inline void fc_mixture(int ns, const double* gamma, const double* R, const double* Y, double* c_p_o, double* c_v_o)
+{
+    double c_p = 0.0, c_v = 0.0;
+    for (int si = 0; si < ns; si++) {
+        c_p = fc_accumulate(c_p, Y[si], fc_species_c_p(gamma[si], R[si]));
+        c_v = fc_accumulate(c_v, Y[si], fc_species_c_v(gamma[si], R[si]));
+    }
+    *c_p_o = c_p;
+    *c_v_o = c_v;
+}
+/* sound speed of a state (rho, Y, p): the reference recomputes epsilon from p for Psi */
+static inline double fc_sound_speed(int ns, const double* gamma, const double* R, double rho, const double* Y, double p,
+                                    double* eps_o)
+{
+    double c_p, c_v;
+    fc_mixture(ns, gamma, R, Y, &c_p, &c_v);
+    const double gamma_m = fc_gamma(c_p, c_v);
+    const double eps = fe_internal_energy_from_p(gamma_m, rho, p);
+    double cc = fe_c2_first(fe_gruneisen(gamma_m), p, rho);
+    for (int si = 0; si < ns; si++)
+        cc = fe_c2_accumulate(cc, Y[si], fc_psi(fc_species_c_p(gamma[si], R[si]), fc_species_c_v(gamma[si], R[si]), gamma_m, c_v, eps));
+    if (eps_o) *eps_o = eps;
+    return sqrt(cc);
 }
 
 void orc_path_points3(const double in[56], double out[32])
@@ -296,6 +338,19 @@ static inline int side_bounded(int model, int dim, int ns, int dir, const double
         ok &= (Vs[dim + 1] > 0.0) ? 1 : 0;
         return ok;
     }
+    if (model == ORC_FOUR_EQN_CONSERVATIVE) {
+        /* FlowModelBasicUtilitiesFourEqnConservative.cpp:3737-4510: rho = sum rho Y_i; every Y_i strictly inside its
+         * bounds (FlowModelBasicUtilitiesFourEqnConservative.hpp:24-25, the same numbers as the five-eqn model's); rho > 0; p > 0 */
+        double rho = 0.0;
+        for (int si = 0; si < ns; si++) rho += Vs[si];
+        for (int si = 0; si < ns; si++) {
+            const double Y = Vs[si] / rho;
+            ok &= (Y > ORC_Y_BOUND_LO && Y < ORC_Y_BOUND_UP) ? 1 : 0;
+        }
+        ok &= (rho > 0.0) ? 1 : 0;
+        ok &= (Vs[ns + dim] > 0.0) ? 1 : 0;
+        return ok;
+    }
     const double Z_lo = ORC_Z_BOUND_LO, Z_up = ORC_Z_BOUND_UP, Y_lo = ORC_Y_BOUND_LO, Y_up = ORC_Y_BOUND_UP;
     double Z[ORC_MAX_SPECIES];
     Z[ns - 1] = 1.0;
@@ -322,6 +377,41 @@ static inline int side_bounded(int model, int dim, int ns, int dir, const double
         c_sq = (dir == 0) ? fe_c2_accumulate(c_sq, Y[si], fe_psi(pp, rho)) : fe_c2_first(fe_gruneisen(gamma_m), pp, rho);
     ok &= (c_sq > 0.0) ? 1 : 0;
     return ok;
+}
+
+void orc_path_points7(const double in[16], double out[15])
+{
+    /* four-eqn conservative, two species, 3-D (layout: hamers_oracle.h) */
+    const int ns = 2, dim = 3;
+    const double* gam = in + 6;     /* gamma0, gamma1, R0, R1 */
+    double rho = 0.0;
+    for (int si = 0; si < ns; si++) rho += in[si];
+    double Y[2];
+    for (int si = 0; si < ns; si++) Y[si] = in[si] / rho;
+    double vel[3], ke = 0.0;
+    for (int a = 0; a < dim; a++) {
+        vel[a] = in[ns + a] / rho;
+        ke = (a == 0) ? vel[a] * vel[a] : ke + vel[a] * vel[a];
+    }
+    const double epsilon = in[ns + dim] / rho - 1.0 / 2.0 * ke;
+    double c_p, c_v;
+    fc_mixture(ns, gam, gam + ns, Y, &c_p, &c_v);
+    const double gamma_m = fc_gamma(c_p, c_v);
+    const double p = fe_pressure(gamma_m, rho, epsilon);
+    const double eps_p = fe_internal_energy_from_p(gamma_m, rho, p);
+    out[0] = rho;
+    out[1] = Y[0];
+    out[2] = Y[1];
+    out[3] = epsilon;
+    out[4] = c_p;
+    out[5] = c_v;
+    out[6] = gamma_m;
+    out[7] = p;
+    for (int si = 0; si < ns; si++)
+        out[8 + si] = fc_psi(fc_species_c_p(gam[si], gam[ns + si]), fc_species_c_v(gam[si], gam[ns + si]), gamma_m, c_v, eps_p);
+    out[10] = fc_sound_speed(ns, gam, gam + ns, rho, Y, p, 0);
+    side_thermo(ORC_FOUR_EQN_CONSERVATIVE, dim, ns, gam, in + 10, &out[11], &out[12], &out[13]);
+    out[14] = (double)side_bounded(ORC_FOUR_EQN_CONSERVATIVE, dim, ns, 0, gam, in + 10);
 }
 
 void orc_path_points5(const double in[16], double out[2])
@@ -517,6 +607,15 @@ static inline void side_thermo(int model, int dim, int ns, const double* gamma, 
         *rho_o = rho;
         *c_o = eos_sound_speed(gamma[0], rho, p);
         *eps_o = eos_internal_energy(gamma[0], rho, p);
+    } else if (model == ORC_FOUR_EQN_CONSERVATIVE) {
+        /* FlowModelRiemannSolverFourEqnConservativeHLLC-HLL.cpp:5150-5290: rho = sum rho Y_i, Y_i, Gamma, Psi_i, c, epsilon */
+        double rho = 0.0;
+        for (int si = 0; si < ns; si++) rho += V[si];
+        const double p = V[ns + dim];
+        double Y[ORC_MAX_SPECIES];
+        for (int si = 0; si < ns; si++) Y[si] = V[si] / rho;
+        *rho_o = rho;
+        *c_o = fc_sound_speed(ns, gamma, gamma + ns, rho, Y, p, eps_o);
     } else {
         double rho = 0.0;
         for (int si = 0; si < ns; si++) rho += V[si];
@@ -551,8 +650,9 @@ static inline void riemann_kernel(int model, int dim, int ns, int dir,
                                   double eps_L, double eps_R,
                                   double* F_HLLC, double* F_HLLC_HLL, double* vel_mid)
 {
-    const int neq = (model == ORC_SINGLE_SPECIES) ? dim + 2 : dim + 2 * ns;
+    const int neq = (model == ORC_SINGLE_SPECIES) ? dim + 2 : (model == ORC_FOUR_EQN_CONSERVATIVE ? dim + 1 + ns : dim + 2 * ns);
     const int nm = (model == ORC_SINGLE_SPECIES) ? 1 : ns;     /* number of mass equations */
+    const int nz = (model == ORC_FIVE_EQN_ALLAIRE) ? ns - 1 : 0; /* advected volume fractions */
     const int iv = nm;                                         /* first velocity index in V */
     const int ip = nm + dim;                                   /* pressure index in V / energy in Q */
 
@@ -601,13 +701,13 @@ static inline void riemann_kernel(int model, int dim, int ns, int dir,
             for (int si = 0; si < ns; si++) Q[si] = V[si];
             for (int a = 0; a < dim; a++) Q[iv + a] = rho * V[iv + a];
             Q[ip] = rho * (eps + 1.0 / 2.0 * ke);
-            for (int si = 0; si < ns - 1; si++) Q[ip + 1 + si] = V[ip + 1 + si];
+            for (int si = 0; si < nz; si++) Q[ip + 1 + si] = V[ip + 1 + si];
 
             for (int si = 0; si < ns; si++) F[si] = un * V[si];
             for (int a = 0; a < dim; a++)
                 F[iv + a] = (a == dir) ? un * Q[iv + a] + p : un * Q[iv + a];
             F[ip] = un * (Q[ip] + p);
-            for (int si = 0; si < ns - 1; si++) F[ip + 1 + si] = un * V[ip + 1 + si];
+            for (int si = 0; si < nz; si++) F[ip + 1 + si] = un * V[ip + 1 + si];
         }
     }
 
@@ -744,6 +844,20 @@ static double* dalloc(long n)
  * five-eqn: EquationOfStateMixingRules.cpp:735-900 (rho), FlowModelFiveEqnAllaire.cpp:3965 (Y),
  *   :4428-4430 (epsilon), EquationOfStateMixingRulesIdealGas.cpp:7520-7587 (gamma_m from ALL ns
  *   stored volume fractions), EquationOfStateIdealGas.cpp:5756 (p), FlowModelFiveEqnAllaire.cpp:4779-4853 (c). */
+/* species gammas followed by the species gas constants (used by the four-eqn conservative model only) */
+static void model_constants(const orc_desc* d, double* gam)
+{
+    for (int si = 0; si < ORC_MAX_SPECIES; si++) {
+        gam[si] = 0.0;
+        gam[ORC_MAX_SPECIES + si] = 0.0;
+    }
+    const int ns = d->model == ORC_SINGLE_SPECIES ? 1 : d->ns;
+    for (int si = 0; si < ns; si++) {
+        gam[si] = d->gamma[si];
+        gam[ns + si] = (d->model == ORC_FOUR_EQN_CONSERVATIVE) ? d->R[si] : 0.0;
+    }
+}
+
 static void cell_stage(const geom_t* q, const double* gam, const double* const* Q,
                        double** vel, double* p, double* c, double* rho_m)
 {
@@ -760,6 +874,23 @@ static void cell_stage(const geom_t* q, const double* gam, const double* const* 
             const double epsilon = Q[dim + 1][x] / rho - 1.0 / 2.0 * ke;
             p[x] = eos_pressure(gam[0], rho, epsilon);
             c[x] = eos_sound_speed(gam[0], rho, p[x]);
+        } else if (q->model == ORC_FOUR_EQN_CONSERVATIVE) {
+            /* FlowModelFourEqnConservative.cpp:3877 (rho), :3914 (Y), :4569 (velocity), :4793 (epsilon), :5034 (p), :5087 (c) */
+            double rho = 0.0;
+            for (int si = 0; si < ns; si++) rho += Q[si][x];
+            rho_m[x] = rho;
+            double Y[ORC_MAX_SPECIES];
+            for (int si = 0; si < ns; si++) Y[si] = Q[si][x] / rho;
+            double ke = 0.0;
+            for (int a = 0; a < dim; a++) {
+                vel[a][x] = Q[ns + a][x] / rho;
+                ke = (a == 0) ? vel[a][x] * vel[a][x] : ke + vel[a][x] * vel[a][x];
+            }
+            const double epsilon = Q[ns + dim][x] / rho - 1.0 / 2.0 * ke;
+            double c_p, c_v;
+            fc_mixture(ns, gam, gam + ns, Y, &c_p, &c_v);
+            p[x] = fe_pressure(fc_gamma(c_p, c_v), rho, epsilon);
+            c[x] = fc_sound_speed(ns, gam, gam + ns, rho, Y, p[x], 0);
         } else {
             double rho = 0.0;
             for (int si = 0; si < ns; si++) rho += Q[si][x];
@@ -810,7 +941,9 @@ int orc_spectral_radii_and_dt(const orc_desc* d, const double* const* Q, int inc
     const int dim = q.dim;
     double* vel[3] = {dalloc(q.ncell_g), dalloc(q.ncell_g), dalloc(q.ncell_g)};
     double *p = dalloc(q.ncell_g), *c = dalloc(q.ncell_g), *rho_m = dalloc(q.ncell_g);
-    cell_stage(&q, d->gamma, Q, vel, p, c, rho_m);
+    double gam[2 * ORC_MAX_SPECIES];
+    model_constants(d, gam);
+    cell_stage(&q, gam, Q, vel, p, c, rho_m);
     double sr[4] = {0.0, 0.0, 0.0, 0.0};
     const int g = include_ghosts ? G : 0;
     const int gz = (dim == 3) ? g : 0;
@@ -867,14 +1000,18 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
     const int iv = nm, ip = nm + dim;
     const int p_exp = d->weno_p > 0 ? d->weno_p : 2;
     const int has_adv = (q->model == ORC_FIVE_EQN_ALLAIRE);
+    const int multi = (q->model != ORC_SINGLE_SPECIES);       /* partial densities instead of one density */
+    const int nz = has_adv ? ns - 1 : 0;                      /* advected volume fractions */
+    double gam[2 * ORC_MAX_SPECIES];
+    model_constants(d, gam);
 
     /* ---- step 1: derived cell data (WCNS56-HLLC-HLL.cpp:1392-1410) ---- */
     double* vel[3] = {0, 0, 0};
     for (int a = 0; a < dim; a++) vel[a] = dalloc(q->ncell_g);
     double* p = dalloc(q->ncell_g);
     double* c = dalloc(q->ncell_g);
-    double* rho_m = has_adv ? dalloc(q->ncell_g) : 0;
-    cell_stage(q, d->gamma, Q, vel, p, c, rho_m);
+    double* rho_m = multi ? dalloc(q->ncell_g) : 0;
+    cell_stage(q, gam, Q, vel, p, c, rho_m);
 
     /* primitive variable pointers (FlowModelSingleSpecies / FiveEqnAllaire getCellDataOfPrimitiveVariables) */
     const double* V[ORC_MAX_EQ];
@@ -886,9 +1023,9 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
         for (int si = 0; si < ns; si++) V[si] = Q[si];
         for (int a = 0; a < dim; a++) V[ns + a] = vel[a];
         V[ns + dim] = p;
-        for (int si = 0; si < ns - 1; si++) V[ns + dim + 1 + si] = Q[ns + dim + 1 + si];
+        for (int si = 0; si < nz; si++) V[ns + dim + 1 + si] = Q[ns + dim + 1 + si];
     }
-    const double* rho_cell = has_adv ? rho_m : Q[0];
+    const double* rho_cell = multi ? rho_m : Q[0];
 
     /* ---- step 2: velocity gradient, dilatation, vorticity (:1523-1659; 2D :663-731) ----
      * arrays with 2 ghosts; derivative (1/2*(uR-uL))/dx, DerivativeFirstOrder.cpp:382,601 */
@@ -947,13 +1084,13 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
 
         /* ---- step 3: projection variables (SS :5000-5001; 5eq :7952,7995-7996) ---- */
         double* Zrho_avg[ORC_MAX_SPECIES];
-        for (int si = 0; si < ns; si++) Zrho_avg[si] = has_adv ? dalloc(nside) : 0;
+        for (int si = 0; si < ns; si++) Zrho_avg[si] = multi ? dalloc(nside) : 0;
         double* rho_avg = dalloc(nside);
         double* c_avg = dalloc(nside);
         FOR_FACES
         {
             const long xR = cidx(q, i, j, k), xL = xR - st, s = SIDX(i, j, k);
-            if (has_adv)
+            if (multi)   /* five-eqn :7952; four-eqn FlowModelBasicUtilitiesFourEqnConservative.cpp:4638-5370 (same statements on rho Y_i) */
                 for (int si = 0; si < ns; si++) Zrho_avg[si][s] = face_average(Q[si][xL], Q[si][xR]);
             rho_avg[s] = face_average(rho_cell[xL], rho_cell[xR]);
             c_avg[s] = face_average(c[xL], c[xR]);
@@ -984,7 +1121,7 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
                     int w = ns + 1;
                     for (int a = 0; a < dim; a++)
                         if (a != dir) W[m][w++][s] = V[iv + a][x];
-                    for (int si = 0; si < ns - 1; si++) W[m][ns + dim + si][s] = V[ip + 1 + si][x];
+                    for (int si = 0; si < nz; si++) W[m][ns + dim + si][s] = V[ip + 1 + si][x];
                     W[m][neq - 1][s] = fe_char_plus(rho_avg[s], c_avg[s], V[iv + dir][x], V[ip][x]);
                 }
             }
@@ -1043,7 +1180,7 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
                             Vs[iv + a][s] = Wc[w++][s];
                     }
                     Vs[ip][s] = fe_back_pressure(rho_avg[s], c_avg[s], Wc[0][s], Wc[neq - 1][s]);
-                    for (int si = 0; si < ns - 1; si++) Vs[ip + 1 + si][s] = Wc[ns + dim + si][s];
+                    for (int si = 0; si < nz; si++) Vs[ip + 1 + si][s] = Wc[ns + dim + si][s];
                 }
             }
         }
@@ -1059,7 +1196,7 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
                 const long s = SIDX(i, j, k);
                 double Vside[ORC_MAX_EQ];
                 for (int e = 0; e < neq; e++) Vside[e] = Vs[e][s];
-                const int ok = side_bounded(q->model, dim, ns, dir, d->gamma, Vside);
+                const int ok = side_bounded(q->model, dim, ns, dir, gam, Vside);
                 flag[side][s] = ok;
             }
         }
@@ -1094,7 +1231,7 @@ int orc_compute_flux_and_source(const orc_desc* d, const double* const* Q, doubl
                 VL[e] = V_minus[e][s];
                 VR[e] = V_plus[e][s];
             }
-            orc_riemann_point(q->model, dim, ns, d->gamma, dir, VL, VR, FH, FB, &vm);
+            orc_riemann_point(q->model, dim, ns, gam, dir, VL, VR, FH, FB, &vm);
             for (int e = 0; e < neq; e++) {
                 F_HLLC[e][s] = FH[e];
                 F_HYB[e][s] = FB[e];

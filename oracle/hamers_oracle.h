@@ -29,6 +29,9 @@ extern "C" {
 
 #define ORC_SINGLE_SPECIES 0
 #define ORC_FIVE_EQN_ALLAIRE 1
+/* FlowModelFourEqnConservative (FlowModelManager.cpp "FOUR_EQN_CONSERVATIVE"): partial densities rho Y_i,
+ * momentum, total energy; all equations conservative; mixture of ideal gases closed by mass fractions */
+#define ORC_FOUR_EQN_CONSERVATIVE 2
 
 typedef struct {
     int dim;                         /* 2 or 3 */
@@ -45,13 +48,17 @@ typedef struct {
     int weno_q;
     double weno_C;
     double weno_alpha_tau;
+    /* four-eqn conservative: species gas constants, Equation_of_state_mixing_rules { species_R }
+     * (EquationOfStateMixingRulesIdealGas.cpp:60-125: c_p_i = gamma_i/(gamma_i - 1) R_i, c_v_i = 1/(gamma_i - 1) R_i) */
+    double R[ORC_MAX_SPECIES];
 } orc_desc;
 
 #define ORC_WCNS5_JS 0
 #define ORC_WCNS5_Z 1
 #define ORC_WCNS6_LD 2
 
-/* d + 2 (single-species) or d + 2*ns (five-eqn): FlowModelFiveEqnAllaire.cpp:29 */
+/* d + 2 (single-species), d + 2*ns (five-eqn: FlowModelFiveEqnAllaire.cpp:29) or d + 1 + ns (four-eqn conservative:
+ * FlowModelFourEqnConservative.cpp:29) */
 int orc_num_eqn(const orc_desc* d);
 /* number of stored conservative components: num_eqn (+1 for the five-eqn Z_last) */
 int orc_num_comp(const orc_desc* d);
@@ -114,12 +121,17 @@ void orc_path_points4(const double in[12], double out[4]);
 void orc_path_points5(const double in[16], double out[2]);
 /* max wave speeds, spectral radii, their sum, running maximum and stable dt of one cell */
 void orc_path_points6(const double in[8], double out[6]);
+/* four-eqn conservative (two species, 3-D): mixture properties from mass fractions, pressure, sound speed of a cell; the
+ * (rho, c, epsilon) of an interpolated side; its bounds flag.  in: rhoY0, rhoY1, mx, my, mz, E, gamma0, gamma1, R0, R1 |
+ * side V[6]; out: rho, Y0, Y1, epsilon, c_p, c_v, gamma, p, Psi0, Psi1, c | rho, c, eps | flag */
+void orc_path_points7(const double in[16], double out[15]);
 void orc_constants(double out[7]); /* eps, sensor threshold, Y lo/up, Z lo/up, ghost width */
 void orc_eos_point(double gamma, double rho, double epsilon, double* p, double* c, double* eps_back);
 void orc_weno5js_point(const double U[6], int p, double* U_minus, double* U_plus);
 void orc_weno5z_point(const double U[6], int p, double* U_minus, double* U_plus);
 void orc_weno6ld_point(const double U[6], int p, int q, double C, double alpha_tau, double* U_minus, double* U_plus);
-/* V layout: single-species [rho, vel(d), p]; five-eqn [Zrho(ns), vel(d), p, Z(ns-1)] */
+/* V layout: single-species [rho, vel(d), p]; five-eqn [Zrho(ns), vel(d), p, Z(ns-1)]; four-eqn [rhoY(ns), vel(d), p].
+ * gamma: ns species gammas, followed by the ns species gas constants R for the four-eqn model */
 void orc_riemann_point(int model, int dim, int ns, const double* gamma, int dir,
                        const double* V_L, const double* V_R,
                        double* F_HLLC, double* F_HLLC_HLL, double* vel_mid);

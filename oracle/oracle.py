@@ -41,6 +41,7 @@ class _Desc(C.Structure):
         ("weno_q", C.c_int),
         ("weno_C", C.c_double),
         ("weno_alpha_tau", C.c_double),
+        ("R", C.c_double * MAX_SPECIES),
     ]
 
 
@@ -83,6 +84,7 @@ class PatchDesc:
     weno_q: int = 4
     weno_C: float = 1.0e9
     weno_alpha_tau: float = 35.0
+    R: tuple = ()              # four-eqn conservative: species gas constants (species_R)
     _c: _Desc = field(default=None, repr=False)
 
     def c(self) -> _Desc:
@@ -97,15 +99,19 @@ class PatchDesc:
             d.gamma[i] = float(g)
         d.weno_p = self.weno_p
         d.scheme, d.weno_q, d.weno_C, d.weno_alpha_tau = self.scheme, self.weno_q, self.weno_C, self.weno_alpha_tau
+        for i, r in enumerate(self.R):
+            d.R[i] = float(r)
         return d
 
     @property
     def neq(self) -> int:
+        if self.model == FOUR_EQN_CONSERVATIVE:
+            return self.dim + 1 + self.ns
         return self.dim + 2 if self.model == SINGLE_SPECIES else self.dim + 2 * self.ns
 
     @property
     def ncomp(self) -> int:
-        return self.neq if self.model == SINGLE_SPECIES else self.neq + 1
+        return self.neq + 1 if self.model == FIVE_EQN_ALLAIRE else self.neq
 
     @property
     def ghost_shape(self):

@@ -19,6 +19,14 @@ KEYS = [
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum",
 ]
 STALL = "smsp__average_warps_issue_stalled_"
+OPS = ("dfma", "dmul", "dadd")
+
+
+def num(x):
+    try:
+        return float(x.replace(",", ""))
+    except ValueError:
+        return None
 
 
 def main():
@@ -32,15 +40,25 @@ def main():
         for k in KEYS:
             if k in col:
                 print(f"  {k}: {r[col[k]]} {units[col[k]]}")
+        # FP64 thread-instruction counts: this ncu version exports them per elapsed cycle (summed over the SM
+        # sub-partitions); times the elapsed cycles of one sub-partition = instructions of the launch
+        cyc = num(r[col["smsp__cycles_elapsed.max"]]) if "smsp__cycles_elapsed.max" in col else None
+        for op in OPS:
+            k = f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed"
+            if k in col and cyc:
+                v = num(r[col[k]])
+                if v is not None:
+                    print(f"  thread instructions {op}: {v * cyc:.4g}  ({v:.1f} per cycle)")
+        # stall reasons: warps stalled per issue-active cycle; printed as the share of all stalled-warp samples
         st = []
         for h, i in col.items():
-            if h.startswith(STALL) and h.endswith("_per_warp_active.pct"):
-                try:
-                    st.append((float(r[i].replace(',', '')), h[len(STALL):-len("_per_warp_active.pct")]))
-                except ValueError:
-                    pass
+            if h.startswith(STALL) and h.endswith("_per_issue_active.ratio"):
+                v = num(r[i])
+                if v is not None:
+                    st.append((v, h[len(STALL):-len("_per_issue_active.ratio")]))
+        tot = sum(v for v, _ in st) or 1.0
         st.sort(reverse=True)
-        print("  top stalls (% of warp-active cycles): " + ", ".join(f"{n}={v:.1f}" for v, n in st[:8]))
+        print("  stall reasons (share of warp-cycles, all reasons = 100 %): " + ", ".join(f"{n}={100.0 * v / tot:.1f}" for v, n in st[:9]))
         print()
 
 
