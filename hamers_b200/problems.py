@@ -138,3 +138,95 @@ def random_state(dim: int, N, model=SINGLE_SPECIES, seed=20261017, shock=True):
         E = p / (gamma_m - 1.0) + 0.5 * rho_m * ke
         U = np.stack([Zr1, Zr2] + [rho_m * v for v in vel] + [E, Z1, Z2])
     return np.ascontiguousarray(U.astype(np.float64)), dx, gam
+
+
+# ---- FOUR_EQN_CONSERVATIVE flow model (partial densities rho Y_i, momentum, total energy) ------------------
+FOUR_EQN_CONSERVATIVE = 2
+
+
+def mixture_gamma_mass_fractions(Y, gam, R):
+    """gamma = sum Y_i c_p_i / sum Y_i c_v_i (EquationOfStateMixingRulesIdealGas.cpp:4677-4738)."""
+    c_p = sum(y * g / (g - 1.0) * r for y, g, r in zip(Y, gam, R))
+    c_v = sum(y * 1.0 / (g - 1.0) * r for y, g, r in zip(Y, gam, R))
+    return c_p / c_v
+
+
+def convergence_four_eqn(dim: int, N):
+    """Two-species analogue of the reference's convergence problems for the four-eqn conservative model (the reference
+    ships none for this model): partial-density waves advected with u = v = (w =) 1 at uniform pressure 1.
+    Returns (U, dx, gammas, Rs) with U = [rhoY_1, rhoY_2, rho*u, rho*v, (rho*w), E]."""
+    xs, dx = cell_centres(dim, N)
+    s = _sum_coords(dim, xs)
+    gam, R = (8.0 / 5.0, 7.0 / 5.0), (1.0, 2.0)
+    rY1 = 1.0 + 0.5 * np.sin(np.pi * s)
+    rY2 = 1.0 - 0.25 * np.sin(np.pi * s)
+    rho = rY1 + rY2
+    g = mixture_gamma_mass_fractions((rY1 / rho, rY2 / rho), gam, R)
+    E = 1.0 / (g - 1.0) + 0.5 * rho * float(dim)
+    U = np.stack([rY1, rY2] + [rho * 1.0] * dim + [E]).astype(np.float64)
+    return np.ascontiguousarray(U), dx, gam, R
+
+
+def exact_rhoY1_four_eqn(dim: int, N, time: float):
+    xs, _ = cell_centres(dim, N)
+    s = _sum_coords(dim, xs)
+    return 1.0 + 0.5 * np.sin(np.pi * (s - float(dim) * time))
+
+
+def random_state_four_eqn(dim: int, N, seed=20261017, shock=True):
+    """The branch-coverage state of random_state with two species of different gamma and R.  Returns (U, dx, gammas, Rs)."""
+    U1, dx, _ = random_state(dim, N, model=SINGLE_SPECIES, seed=seed, shock=shock)
+    rng = np.random.default_rng(seed + 1)
+    gam, R = (1.6, 1.4), (0.7, 1.3)
+    rho = U1[0]
+    Y1 = rng.uniform(0.02, 0.98, rho.shape)
+    vel = [U1[1 + a] / rho for a in range(dim)]
+    p = 0.4 * (U1[dim + 1] - 0.5 * rho * sum(v * v for v in vel))
+    g = mixture_gamma_mass_fractions((Y1, 1.0 - Y1), gam, R)
+    E = p / (g - 1.0) + 0.5 * rho * sum(v * v for v in vel)
+    U = np.stack([rho * Y1, rho * (1.0 - Y1)] + [rho * v for v in vel] + [E])
+    return np.ascontiguousarray(U.astype(np.float64)), dx, gam, R
+
+
+# species 0: SF6, species 1: air (input_2D_Richtmyer_Meshkov_instability.txt:21-22)
+RMI_GAMMA = (1.09312, 1.39909)
+RMI_R = (56.927, 296.803)
+
+
+def richtmyer_meshkov_2d(N, x_up=(0.016, 0.001)):
+    """problems/Euler/initial_conditions/RichtmyerMeshkovInstability2D.cpp:58-160 on N = (Nx, Ny) cells of the deck's domain
+    [0, 0.016] x [0, 0.001] (BASELINE.json config 4).  Returns (U, dx, gammas, Rs), U = [rhoY_SF6, rhoY_air, rho u, rho v, E]."""
+    from math import erf
+
+    Nx, Ny = N
+    dx = (x_up[0] / Nx, x_up[1] / Ny)
+    x = (np.arange(Nx) + 0.5) * dx[0]
+    y = (np.arange(Ny) + 0.5) * dx[1]
+    X, Yc = np.meshgrid(x, y, indexing="xy")          # shape (Ny, Nx), x fastest
+    D = 0.001
+    eps_i = 6.0 / 128.0 * D
+    g1 = 1.39909
+    c_p = (668.286, 1040.50)
+    c_v = (611.359, 743.697)
+    rho_SF6, u_SF6, p_SF6 = 5.972856, 436.201332, 101325.0
+    rho_pre, u_pre, p_pre = 1.145598, 436.201332, 101325.0
+    rho_post, u_post, p_post = 1.616874, 309.060123, 164859.0
+    dR = X - (2.0 / 5.0 - 1.0 / 10.0 * np.sin(2 * np.pi * (Yc / D + 1.0 / 4.0))) * D
+    f_sm = 0.5 * (1.0 + np.vectorize(erf)(dR / eps_i))
+    rY0 = rho_SF6 * (1.0 - f_sm)
+    rY1 = rho_pre * f_sm
+    u_i = u_SF6 * (1.0 - f_sm) + u_pre * f_sm
+    p_i = p_SF6 * (1.0 - f_sm) + p_pre * f_sm
+    rho_i = rY0 + rY1
+    Y0 = rY0 / rho_i
+    Y1 = 1.0 - Y0
+    gamma = (Y0 * c_p[0] + Y1 * c_p[1]) / (Y0 * c_v[0] + Y1 * c_v[1])
+    E = p_i / (gamma - 1.0) + 0.5 * rho_i * (u_i * u_i)
+    ru = rho_i * u_i
+    post = X > 7.0 / 10.0 * D
+    rY0 = np.where(post, 0.0, rY0)
+    rY1 = np.where(post, rho_post, rY1)
+    ru = np.where(post, rho_post * u_post, ru)
+    E = np.where(post, p_post / (g1 - 1.0) + 0.5 * rho_post * u_post * u_post, E)
+    U = np.stack([rY0, rY1, ru, np.zeros_like(ru), E]).astype(np.float64)
+    return np.ascontiguousarray(U), dx, RMI_GAMMA, RMI_R

@@ -33,6 +33,9 @@ SOURCES = {
     "ref_ss_hyb": "src/flow/flow_models/single-species/Riemann_solvers/FlowModelRiemannSolverSingleSpeciesHLLC-HLL.cpp",
     "ref_fe_hllc": "src/flow/flow_models/five-eqn_Allaire/Riemann_solvers/FlowModelRiemannSolverFiveEqnAllaireHLLC.cpp",
     "ref_fe_hyb": "src/flow/flow_models/five-eqn_Allaire/Riemann_solvers/FlowModelRiemannSolverFiveEqnAllaireHLLC-HLL.cpp",
+    # SURVEY row f3
+    "ref_fc_hllc": "src/flow/flow_models/four-eqn_conservative/Riemann_solvers/FlowModelRiemannSolverFourEqnConservativeHLLC.cpp",
+    "ref_fc_hyb": "src/flow/flow_models/four-eqn_conservative/Riemann_solvers/FlowModelRiemannSolverFourEqnConservativeHLLC-HLL.cpp",
 }
 
 
@@ -962,6 +965,238 @@ int ref_riemann_point(int model, int dim, int ns, int dir,
 """
 
 
+FC_WRAPPER = r"""
+extern "C" int ref_riemann_point_fc(int dim, int ns, int dir, const double* V_L, const double* V_R,
+                                    double rho_L, double rho_R, double c_L, double c_R, double eps_L, double eps_R,
+                                    double* F_HLLC, double* F_HYB)
+{
+    /* FlowModelRiemannSolverFourEqnConservativeHLLC.cpp / ...HLLC-HLL.cpp point kernels on one face (idx = idx_flux = 0) */
+    const int neq = dim + 1 + ns;
+    double vl[16], vr[16], f1[16], f2[16];
+    double *VL[16], *VR[16], *F1[16], *F2[16];
+    for (int e = 0; e < neq; e++) { vl[e] = V_L[e]; vr[e] = V_R[e]; VL[e] = &vl[e]; VR[e] = &vr[e]; F1[e] = &f1[e]; F2[e] = &f2[e]; }
+    double s_minus = 0, s_plus = 0, s_star = 0, Chi = 0;
+    const int key = dim*10 + dir;
+#define FC_CALL(D, N) \
+    ref_fc_hllc::computeLocalConvectiveFluxIn##D##DirectionFromPrimitiveVariablesHLLC##N(F1, VL, VR, &rho_L, &rho_R, &c_L, &c_R, &eps_L, &eps_R, s_minus, s_plus, s_star, Chi, 0, 0, ns, neq); \
+    ref_fc_hyb::computeLocalConvectiveFluxIn##D##DirectionFromPrimitiveVariablesHLLC_HLL##N(F2, VL, VR, &rho_L, &rho_R, &c_L, &c_R, &eps_L, &eps_R, s_minus, s_plus, s_star, Chi, 0, 0, ns, neq);
+    switch (key) {
+    case 20: FC_CALL(X, 2D) break;
+    case 21: FC_CALL(Y, 2D) break;
+    case 30: FC_CALL(X, 3D) break;
+    case 31: FC_CALL(Y, 3D) break;
+    case 32: FC_CALL(Z, 3D) break;
+    default: return -1;
+    }
+#undef FC_CALL
+    for (int e = 0; e < neq; e++) { F_HLLC[e] = f1[e]; F_HYB[e] = f2[e]; }
+    return 0;
+}
+"""
+
+
+def path_statements7() -> str:
+    """Seventh group, four-eqn conservative model with two species, 3-D: mixture density
+    (EquationOfStateMixingRules.cpp), mass fractions, velocity, internal energy (FlowModelFourEqnConservative.cpp:4107,
+    4767-4769, 5007), species c_p / c_v (EquationOfStateMixingRulesIdealGas.cpp:108-119), mixture c_p, c_v, gamma from the
+    mass fractions (the array form, :7080-7120), pressure, epsilon from p, Gruneisen parameter (EquationOfStateIdealGas.cpp),
+    Psi_i (EquationOfStateMixingRulesIdealGas.cpp:6540-6545), sound speed (FlowModelFourEqnConservative.cpp:5373-5421);
+    the bounds flag of an interpolated side (FlowModelBasicUtilitiesFourEqnConservative.cpp:4390-4500, 3-D x block);
+    projection / back-projection in x (FlowModelBasicUtilitiesFourEqnConservative.cpp:5896-5975, 6640-6700)."""
+    def rd(rel):
+        with open(os.path.join(REF, rel)) as fh:
+            return fh.read()
+    fm = rd("src/flow/flow_models/four-eqn_conservative/FlowModelFourEqnConservative.cpp")
+    bu = rd("src/flow/flow_models/four-eqn_conservative/FlowModelBasicUtilitiesFourEqnConservative.cpp")
+    mr = rd("src/util/mixing_rules/equations_of_state/EquationOfStateMixingRules.cpp")
+    mi_all = rd("src/util/mixing_rules/equations_of_state/ideal_gas/EquationOfStateMixingRulesIdealGas.cpp")
+    ig = rd("src/util/mixing_rules/equations_of_state/ideal_gas/EquationOfStateIdealGas.cpp")
+    hpp = rd("include/flow/flow_models/four-eqn_conservative/FlowModelBasicUtilitiesFourEqnConservative.hpp")
+    s_rho = statement(mr, r"rho\[idx_mixture_density\] \+= Z_rho\[si\]\[idx_partial_densities\]")
+    s_Y = statement(fm, r"Y\[si\]\[idx_mass_fractions\] = rho_Y\[si\]\[idx\]/rho\[idx_density\]")
+    s_u = statement(fm, r"u\[idx_velocity\] = rho_u\[idx\]/rho\[idx_density\]")
+    s_v = statement(fm, r"v\[idx_velocity\] = rho_v\[idx\]/rho\[idx_density\]")
+    s_w = statement(fm, r"w\[idx_velocity\] = rho_w\[idx\]/rho\[idx_density\]")
+    s_e = statement(fm, r"epsilon\[idx_internal_energy\] = E\[idx\]/rho\[idx_density\] -\s*double\(1\)/double\(2\)\*\(u\[idx_velocity\]\*u\[idx_velocity\] \+ v\[idx_velocity\]\*v\[idx_velocity\] \+")
+    ctor = line_range(mi_all, 100, 125)
+    s_scp = statement(ctor, r"d_species_c_p\.push_back\(d_species_gamma\[si\]/\(d_species_gamma\[si\] - double\(1\)\)\*d_species_R\[si\]\)")
+    s_scv = statement(ctor, r"d_species_c_v\.push_back\(double\(1\)/\(d_species_gamma\[si\] - double\(1\)\)\*d_species_R\[si\]\)")
+    mi = line_range(mi_all, 6946, 7150)      # computeMixtureThermodynamicPropertiesWithMassFractions, all species given
+    s_cp = statement(mi, r"c_p\[idx_mixture_thermo_properties\] \+= Y\[si\]\[idx_mass_fractions\]\*d_species_c_p\[si\]")
+    s_cv = statement(mi, r"c_v\[idx_mixture_thermo_properties\] \+= Y\[si\]\[idx_mass_fractions\]\*d_species_c_v\[si\]")
+    s_gm = statement(mi, r"gamma\[idx_mixture_thermo_properties\] = c_p\[idx_mixture_thermo_properties\]/")
+    s_p = statement(ig, r"p\[idx_pressure\] = \(gamma\[idx_thermo_properties\] - double\(1\)\)\*rho\[idx_density\]\*\s*epsilon\[idx_internal_energy\]")
+    s_ep = statement(ig, r"epsilon\[idx_internal_energy\] = p\[idx_pressure\]/\(\(gamma\[idx_thermo_properties\] - double\(1\)\)\*\s*rho\[idx_density\]\)")
+    s_Gr = statement(ig, r"Gamma\[idx_gruneisen_parameter\] = gamma\[idx_thermo_properties\] - double\(1\)")
+    ps = line_range(mi_all, 6367, 6564)
+    s_Psi = statement(ps, r"Psi_i\[idx_partial_pressure_partial_partial_densities\] =")
+    s_c0 = statement(fm, r"c\[idx_sound_speed\] = Gamma\[idx_sound_speed\]\*p\[idx_pressure\]/rho\[idx_density\]")
+    s_c1 = statement(fm, r"c\[idx_sound_speed\] \+= Y\[si\]\[idx_mass_fractions\]\*Psi\[si\]\[idx_sound_speed\]")
+    s_c2 = statement(fm, r"c\[idx_sound_speed\] = sqrt\(c\[idx_sound_speed\]\)")
+    # bounds flag, 3-D x block of checkSideDataOfPrimitiveVariablesBounded
+    bb = line_range(bu, 4380, 4510)
+    s_brho = statement(bb, r"rho\[idx_face\] \+= V\[si\]\[idx_face\]", 0)
+    s_bY = statement(bb, r"const double Y = V\[si\]\[idx_face\]/rho\[idx_face\]", 0)
+    b_Y = if_else_block(bb, r"if \(Y > d_Y_bound_lo && Y < d_Y_bound_up\)", 0)
+    b_r = if_else_block(bb, r"if \(rho\[idx_face\] > double\(0\)\)", 0)
+    b_p = if_else_block(bb, r"if \(V\[d_num_species \+ d_dim\.getValue\(\)\]\[idx_face\] > double\(0\)\)", 0)
+
+    def bound(nm):
+        return re.search(nm + r" = double\(([-0-9.]+)\)", hpp).group(1)
+    # projection / back-projection, 3-D x direction
+    m = re.search(r"^FlowModelBasicUtilitiesFourEqnConservative::computeSideDataOfCharacteristicVariablesFromPrimitiveVariables\(", bu, flags=re.M)
+    m2 = re.search(r"^FlowModelBasicUtilitiesFourEqnConservative::computeSideDataOfPrimitiveVariablesFromCharacteristicVariables\(", bu, flags=re.M)
+    proj, back = bu[m.start():m2.start()], bu[m2.start():]
+    s_za = statement(bu, r"rho_Y_average\[si\]\[idx_face_x\] = double\(1\)/double\(2\)\*\(rho_Y\[si\]\[idx_L\] \+ rho_Y\[si\]\[idx_R\]\)")
+    s_ra = statement(bu, r"rho_average\[idx_face_x\] = double\(1\)/double\(2\)\*\(rho\[idx_density_L\] \+ rho\[idx_density_R\]\)")
+    s_ca = statement(bu, r"c_average\[idx_face_x\] = double\(1\)/double\(2\)\*\(c\[idx_sound_speed_L\] \+ c\[idx_sound_speed_R\]\)")
+    # the first statements that use V[d_num_species + 3][idx_p] are the 3-D x block's
+    s_w0 = statement(proj, r"W\[0\]\[idx_face\] = V\[d_num_species\]\[idx_vel\] -\s*double\(1\)/\(rho_average\[idx_face\]\*c_average\[idx_face\]\)\*V\[d_num_species \+ 3\]\[idx_p\]", 0)
+    s_wsi = statement(proj, r"W\[1 \+ si\]\[idx_face\] = V\[si\]\[idx_rho_Y\] - rho_Y_average\[si\]\[idx_face\]/\s*\(rho_average\[idx_face\]\*c_average\[idx_face\]\*c_average\[idx_face\]\)\*\s*V\[d_num_species \+ 3\]\[idx_p\]", 0)
+    s_wl = statement(proj, r"W\[d_num_species \+ 3\]\[idx_face\] = V\[d_num_species\]\[idx_vel\] \+", 0)
+    back3 = back[back.index("d_dim == tbox::Dimension(3)"):]
+    s_vsi = statement(back3, r"V\[si\]\[idx_face\] = -double\(1\)/double\(2\)\*rho_Y_average", 0)
+    s_vu = statement(back3, r"V\[d_num_species\]\[idx_face\] = double\(1\)/double\(2\)\*W\[0\]\[idx_face\] \+", 0)
+    s_vp = statement(back3, r"V\[d_num_species \+ 3\]\[idx_face\] = -double\(1\)/double\(2\)\*rho_average", 0)
+    return f"""
+extern "C" void ref_path_points7(const double in[16], double out[15])
+{{
+    const int d_num_species = 2, d_num_eqn = 6;
+    const std::vector<double> d_species_gamma = {{in[6], in[7]}}, d_species_R = {{in[8], in[9]}};
+    std::vector<double> d_species_c_p, d_species_c_v;
+    for (int si = 0; si < d_num_species; si++) {{ {s_scp} }}
+    for (int si = 0; si < d_num_species; si++) {{ {s_scv} }}
+    {{
+        const int idx = 0, idx_density = 0, idx_mixture_density = 0, idx_partial_densities = 0, idx_mass_fractions = 0;
+        const int idx_velocity = 0, idx_internal_energy = 0, idx_mixture_thermo_properties = 0;
+        const int idx_thermo_properties = 0, idx_pressure = 0, idx_gruneisen_parameter = 0, idx_sound_speed = 0;
+        const int idx_partial_pressure_partial_partial_densities = 0;
+        double ry0[1] = {{in[0]}}, ry1[1] = {{in[1]}};
+        double* rho_Y[2] = {{ry0, ry1}};
+        double** Z_rho = rho_Y;            /* the mixing rules' generic name of the partial densities */
+        const double rho_u[1] = {{in[2]}}, rho_v[1] = {{in[3]}}, rho_w[1] = {{in[4]}}, E[1] = {{in[5]}};
+        double rho[1] = {{0.0}}, y0[1], y1[1], u[1], v[1], w[1], epsilon[1], gamma[1], p[1], Gamma[1], c[1];
+        double c_p[1] = {{0.0}}, c_v[1] = {{0.0}}, psi0[1], psi1[1];
+        double* Y[2] = {{y0, y1}};
+        double* Psi[2] = {{psi0, psi1}};
+        for (int si = 0; si < d_num_species; si++) {{ {s_rho} }}
+        for (int si = 0; si < d_num_species; si++) {{ {s_Y} }}
+        {s_u}
+        {s_v}
+        {s_w}
+        {s_e}
+        out[3] = epsilon[0];
+        for (int si = 0; si < d_num_species; si++) {{
+            {s_cp}
+            {s_cv}
+        }}
+        {s_gm}
+        {s_p}
+        {s_ep}
+        {s_Gr}
+        for (int si = 0; si < d_num_species; si++) {{
+            double* Psi_i = Psi[si];
+            {s_Psi}
+        }}
+        {s_c0}
+        for (int si = 0; si < d_num_species; si++) {{ {s_c1} }}
+        {s_c2}
+        out[0] = rho[0]; out[1] = y0[0]; out[2] = y1[0];
+        out[4] = c_p[0]; out[5] = c_v[0]; out[6] = gamma[0]; out[7] = p[0]; out[8] = psi0[0]; out[9] = psi1[0]; out[10] = c[0];
+    }}
+    {{
+        /* (rho, c, epsilon) of an interpolated side: the Riemann driver repeats the cell statements on side data */
+        const int idx_density = 0, idx_mass_fractions = 0, idx_mixture_thermo_properties = 0, idx_thermo_properties = 0;
+        const int idx_pressure = 0, idx_internal_energy = 0, idx_gruneisen_parameter = 0, idx_sound_speed = 0;
+        const int idx_partial_pressure_partial_partial_densities = 0;
+        const double* Vs = in + 10;
+        double rho[1] = {{0.0}};
+        for (int si = 0; si < d_num_species; si++) rho[0] += Vs[si];
+        double y0[1] = {{Vs[0]/rho[0]}}, y1[1] = {{Vs[1]/rho[0]}};
+        double* Y[2] = {{y0, y1}};
+        double p[1] = {{Vs[d_num_species + 3]}}, c_p[1] = {{0.0}}, c_v[1] = {{0.0}}, gamma[1], epsilon[1], Gamma[1], c[1], psi0[1], psi1[1];
+        double* Psi[2] = {{psi0, psi1}};
+        for (int si = 0; si < d_num_species; si++) {{
+            {s_cp}
+            {s_cv}
+        }}
+        {s_gm}
+        {s_ep}
+        {s_Gr}
+        for (int si = 0; si < d_num_species; si++) {{
+            double* Psi_i = Psi[si];
+            {s_Psi}
+        }}
+        {s_c0}
+        for (int si = 0; si < d_num_species; si++) {{ {s_c1} }}
+        {s_c2}
+        out[11] = rho[0]; out[12] = c[0]; out[13] = epsilon[0];
+    }}
+    {{
+        const int idx_face = 0;
+        struct {{ int getValue() const {{ return 3; }} }} d_dim;
+        const double d_Y_bound_lo = ({bound("d_Y_bound_lo")}), d_Y_bound_up = ({bound("d_Y_bound_up")});
+        int are_bounded[1] = {{1}};
+        double v_[6][1];
+        double* V[6];
+        for (int e = 0; e < 6; e++) {{ v_[e][0] = in[10 + e]; V[e] = v_[e]; }}
+        double rho[1] = {{0.0}};
+        for (int si = 0; si < d_num_species; si++) {{ {s_brho} }}
+        for (int si = 0; si < d_num_species; si++) {{
+            {s_bY}
+            {b_Y}
+        }}
+        {b_r}
+        {b_p}
+        out[14] = (double)are_bounded[0];
+    }}
+}}
+
+extern "C" void ref_path_points8(const double in[24], double out[16])
+{{
+    /* four-eqn conservative, 3-D x: face averages (in[0..7]: rhoY0 L/R, rhoY1 L/R, rho L/R, c L/R), projection of V
+     * (in[8..13]) and back-projection of W (in[14..19]) with those averages */
+    const int d_num_species = 2, d_num_eqn = 6;
+    double rya0[1], rya1[1], rho_average[1], c_average[1];
+    double* rho_Y_average[2] = {{rya0, rya1}};
+    {{
+        const int idx_face_x = 0, idx_L = 0, idx_R = 1, idx_density_L = 0, idx_density_R = 1;
+        const int idx_sound_speed_L = 0, idx_sound_speed_R = 1;
+        const double ry0[2] = {{in[0], in[1]}}, ry1[2] = {{in[2], in[3]}}, rho[2] = {{in[4], in[5]}}, c[2] = {{in[6], in[7]}};
+        const double* rho_Y[2] = {{ry0, ry1}};
+        for (int si = 0; si < d_num_species; si++) {{ {s_za} }}
+        {s_ra}
+        {s_ca}
+        out[0] = rya0[0]; out[1] = rya1[0]; out[2] = rho_average[0]; out[3] = c_average[0];
+    }}
+    {{
+        const int idx_face = 0, idx_rho_Y = 0, idx_vel = 0, idx_p = 0;
+        double v_[6][1], w_[6][1];
+        double *V[6], *W[6];
+        for (int e = 0; e < 6; e++) {{ v_[e][0] = in[8 + e]; V[e] = v_[e]; W[e] = w_[e]; }}
+        for (int si = 0; si < d_num_species; si++) {{ {s_wsi} }}
+        {s_w0}
+        W[d_num_species + 1][idx_face] = V[d_num_species + 1][idx_vel];
+        W[d_num_species + 2][idx_face] = V[d_num_species + 2][idx_vel];
+        {s_wl}
+        for (int e = 0; e < 6; e++) out[4 + e] = W[e][0];
+    }}
+    {{
+        const int idx_face = 0;
+        double v_[6][1], w_[6][1];
+        double *V[6], *W[6];
+        for (int e = 0; e < 6; e++) {{ w_[e][0] = in[14 + e]; V[e] = v_[e]; W[e] = w_[e]; }}
+        for (int si = 0; si < d_num_species; si++) {{ {s_vsi} }}
+        {s_vu}
+        V[d_num_species + 1][idx_face] = W[d_num_species + 1][idx_face];
+        V[d_num_species + 2][idx_face] = W[d_num_species + 2][idx_face];
+        {s_vp}
+        for (int e = 0; e < 6; e++) out[10 + e] = V[e][0];
+    }}
+}}
+"""
+
+
 EOS_WRAPPER = r"""
 extern "C" void ref_eos_point(double gamma, double rho, double epsilon, double* p, double* c, double* eps_back)
 {
@@ -999,6 +1234,8 @@ def main() -> int:
     parts.append(path_statements4())
     parts.append(path_statements5())
     parts.append(path_statements6())
+    parts.append(FC_WRAPPER)
+    parts.append(path_statements7())
     parts.append(diffusive_kernels())
     parts.append(diffusive_term_tables())
     parts.append(diffusive_dt_statements())

@@ -414,6 +414,30 @@ void orc_path_points7(const double in[16], double out[15])
     out[14] = (double)side_bounded(ORC_FOUR_EQN_CONSERVATIVE, dim, ns, 0, gam, in + 10);
 }
 
+void orc_path_points8(const double in[24], double out[16])
+{
+    /* four-eqn conservative, 3-D x: face averages, projection and back-projection -- the same helper functions as the
+     * five-eqn model's (the reference's statements are the same on rho Y_i instead of Z_i rho_i); layout: build_ref.py */
+    const double ry_avg[2] = {face_average(in[0], in[1]), face_average(in[2], in[3])};
+    const double rho_avg = face_average(in[4], in[5]), c_avg = face_average(in[6], in[7]);
+    out[0] = ry_avg[0];
+    out[1] = ry_avg[1];
+    out[2] = rho_avg;
+    out[3] = c_avg;
+    const double* V = in + 8;
+    out[4] = fe_char_minus(rho_avg, c_avg, V[2], V[5]);
+    for (int si = 0; si < 2; si++) out[5 + si] = fe_char_partial_density(ry_avg[si], rho_avg, c_avg, V[si], V[5]);
+    out[7] = V[3];
+    out[8] = V[4];
+    out[9] = fe_char_plus(rho_avg, c_avg, V[2], V[5]);
+    const double* W = in + 14;
+    for (int si = 0; si < 2; si++) out[10 + si] = fe_back_partial_density(ry_avg[si], c_avg, W[0], W[1 + si], W[5]);
+    out[12] = fe_back_normal_velocity(W[0], W[5]);
+    out[13] = W[3];
+    out[14] = W[4];
+    out[15] = fe_back_pressure(rho_avg, c_avg, W[0], W[5]);
+}
+
 void orc_path_points5(const double in[16], double out[2])
 {
     /* in: five-eqn side V[7] (two species, 3-D), gamma0, gamma1, direction (0 / 1 / 2) | single-species side V[5];

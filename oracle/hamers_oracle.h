@@ -125,6 +125,8 @@ void orc_path_points6(const double in[8], double out[6]);
  * (rho, c, epsilon) of an interpolated side; its bounds flag.  in: rhoY0, rhoY1, mx, my, mz, E, gamma0, gamma1, R0, R1 |
  * side V[6]; out: rho, Y0, Y1, epsilon, c_p, c_v, gamma, p, Psi0, Psi1, c | rho, c, eps | flag */
 void orc_path_points7(const double in[16], double out[15]);
+/* four-eqn conservative (3-D, x): face averages, characteristic projection and its inverse */
+void orc_path_points8(const double in[24], double out[16]);
 void orc_constants(double out[7]); /* eps, sensor threshold, Y lo/up, Z lo/up, ghost width */
 void orc_eos_point(double gamma, double rho, double epsilon, double* p, double* c, double* eps_back);
 void orc_weno5js_point(const double U[6], int p, double* U_minus, double* U_plus);

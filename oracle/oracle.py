@@ -22,6 +22,7 @@ G = 4
 MAX_SPECIES = 4
 SINGLE_SPECIES = 0
 FIVE_EQN_ALLAIRE = 1
+FOUR_EQN_CONSERVATIVE = 2
 
 # SSP-RK3 default table, RungeKuttaLevelIntegrator.cpp:3894-3929
 SSPRK3_ALPHA = np.array([[1.0, 0.0, 0.0], [3.0 / 4.0, 1.0 / 4.0, 0.0], [1.0 / 3.0, 0.0, 2.0 / 3.0]])
@@ -265,6 +266,28 @@ def path_points5(vals):
     return list(out)
 
 
+def path_points7(vals):
+    """orc_path_points7: four-eqn conservative mixture chain of a cell, side state, bounds flag."""
+    a = (C.c_double * 16)(*[float(x) for x in vals])
+    out = (C.c_double * 15)()
+    lib().orc_path_points7(a, out)
+    return list(out)
+
+
+def path_points8(vals):
+    """orc_path_points8: four-eqn conservative face averages, projection, back-projection (3-D x)."""
+    a = (C.c_double * 24)(*([float(x) for x in vals] + [0.0] * (24 - len(vals))))
+    out = (C.c_double * 16)()
+    lib().orc_path_points8(a, out)
+    return list(out)
+
+
+def _neq_of(model, dim, ns):
+    if model == FOUR_EQN_CONSERVATIVE:
+        return dim + 1 + ns
+    return dim + 2 if model == SINGLE_SPECIES else dim + 2 * ns
+
+
 def path_points6(vals):
     """orc_path_points6: spectral radii of one cell, their sum, running maximum, stable dt."""
     a = (C.c_double * 8)(*[float(x) for x in vals])
@@ -308,8 +331,9 @@ def weno6ld_point(U, p=2, q=4, Cc=1.0e9, alpha_tau=35.0):
 
 
 def riemann_point(model, dim, ns, gamma, direction, V_L, V_R):
-    neq = dim + 2 if model == SINGLE_SPECIES else dim + 2 * ns
-    g = (C.c_double * MAX_SPECIES)(*[float(x) for x in gamma])
+    """gamma: the species gammas; for the four-eqn conservative model followed by the species gas constants R."""
+    neq = _neq_of(model, dim, ns)
+    g = (C.c_double * (2 * MAX_SPECIES))(*[float(x) for x in gamma])
     VL = (C.c_double * neq)(*[float(x) for x in V_L])
     VR = (C.c_double * neq)(*[float(x) for x in V_R])
     F1 = (C.c_double * neq)()
@@ -320,8 +344,8 @@ def riemann_point(model, dim, ns, gamma, direction, V_L, V_R):
 
 
 def side_thermo(model, dim, ns, gamma, V):
-    neq = dim + 2 if model == SINGLE_SPECIES else dim + 2 * ns
-    g = (C.c_double * MAX_SPECIES)(*[float(x) for x in gamma])
+    neq = _neq_of(model, dim, ns)
+    g = (C.c_double * (2 * MAX_SPECIES))(*[float(x) for x in gamma])
     Va = (C.c_double * neq)(*[float(x) for x in V])
     r, c, e = C.c_double(), C.c_double(), C.c_double()
     lib().orc_side_thermo(int(model), int(dim), int(ns), g, Va, C.byref(r), C.byref(c), C.byref(e))
