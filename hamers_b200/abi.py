@@ -19,6 +19,7 @@ MAX_SPECIES = 4
 GHOSTS = 4
 SINGLE_SPECIES = 0
 FIVE_EQN_ALLAIRE = 1
+FOUR_EQN_CONSERVATIVE = 2      # SURVEY row f3 (needs species_R; reference-order kernels only)
 MATH_EXACT = 0
 MATH_FAST = 1
 
@@ -67,6 +68,7 @@ class PatchDescC(C.Structure):
         ("weno_C", C.c_double),
         ("weno_alpha_tau", C.c_double),
         ("num_ghosts", C.c_int32),
+        ("species_R", C.c_double * MAX_SPECIES),
     ]
 
 
@@ -149,7 +151,8 @@ class Plan:
     def __init__(self, dim: int, n: Sequence[int], flow_model: int = SINGLE_SPECIES,
                  species_gamma: Sequence[float] = (1.4,), dx: Sequence[float] = (1.0, 1.0, 1.0),
                  weno_p: int = 2, math: int = MATH_EXACT, device: int = -1, scheme: int = 0, weno_q: int = 4,
-                 weno_C: float = 1.0e9, weno_alpha_tau: float = 35.0, num_ghosts: int = GHOSTS):
+                 weno_C: float = 1.0e9, weno_alpha_tau: float = 35.0, num_ghosts: int = GHOSTS,
+                 species_R: Sequence[float] = ()):
         self.lib = load_library()
         d = PatchDescC()
         d.num_ghosts = int(num_ghosts)
@@ -159,9 +162,11 @@ class Plan:
             d.n[a] = int(n[a]) if a < dim else 1
             d.dx[a] = float(dx[a]) if a < dim else 1.0
         d.flow_model = flow_model
-        d.num_species = len(species_gamma) if flow_model == FIVE_EQN_ALLAIRE else 1
+        d.num_species = len(species_gamma) if flow_model != SINGLE_SPECIES else 1
         for i, g in enumerate(species_gamma):
             d.species_gamma[i] = float(g)
+        for i, r in enumerate(species_R):
+            d.species_R[i] = float(r)
         d.weno_p = weno_p
         d.math = math
         d.device = device
@@ -171,8 +176,11 @@ class Plan:
         self.n = tuple(int(n[a]) for a in range(dim))
         self.flow_model = flow_model
         self.num_species = d.num_species
-        self.neq = dim + 2 if flow_model == SINGLE_SPECIES else dim + 2 * d.num_species
-        self.ncomp = self.neq if flow_model == SINGLE_SPECIES else self.neq + 1
+        if flow_model == FOUR_EQN_CONSERVATIVE:
+            self.neq = dim + 1 + d.num_species
+        else:
+            self.neq = dim + 2 if flow_model == SINGLE_SPECIES else dim + 2 * d.num_species
+        self.ncomp = self.neq + 1 if flow_model == FIVE_EQN_ALLAIRE else self.neq
         self._h = C.c_void_p()
         _check(self.lib.hb2_plan_create(C.byref(d), C.byref(self._h)), "hb2_plan_create")
 

@@ -127,8 +127,12 @@ int validate_desc(const hb2_patch_desc* d)
         if (d->num_species != 1) return fail(-5, "SINGLE_SPECIES requires num_species = 1");
     } else if (d->flow_model == HB2_FIVE_EQN_ALLAIRE) {
         if (d->num_species != 2) return fail(-6, "FIVE_EQN_ALLAIRE is built for num_species = 2");
+    } else if (d->flow_model == HB2_FOUR_EQN_CONSERVATIVE) {
+        if (d->num_species != 2) return fail(-6, "FOUR_EQN_CONSERVATIVE is built for num_species = 2");
+        for (int s = 0; s < d->num_species; s++)
+            if (!(d->species_R[s] > 0.0)) return fail(-26, "FOUR_EQN_CONSERVATIVE needs species_R > 0 for every species");
     } else {
-        return fail(-7, "unknown flow_model (SINGLE_SPECIES = 0, FIVE_EQN_ALLAIRE = 1)");
+        return fail(-7, "unknown flow_model (SINGLE_SPECIES = 0, FIVE_EQN_ALLAIRE = 1, FOUR_EQN_CONSERVATIVE = 2)");
     }
     for (int s = 0; s < d->num_species; s++)
         if (!(d->species_gamma[s] > 1.0)) return fail(-8, "species_gamma must be > 1");
@@ -155,8 +159,12 @@ void make_geom(const hb2_patch_desc* d, Geom* G)
     G->ncell_g = (long long)G->gd[0] * G->gd[1] * G->gd[2];
 }
 
-int neq_of(const hb2_patch_desc* d) { return d->flow_model == HB2_SINGLE_SPECIES ? d->dim + 2 : d->dim + 2 * d->num_species; }
-int ncomp_of(const hb2_patch_desc* d) { return d->flow_model == HB2_SINGLE_SPECIES ? d->dim + 2 : d->dim + 2 * d->num_species + 1; }
+int neq_of(const hb2_patch_desc* d)
+{
+    if (d->flow_model == HB2_FOUR_EQN_CONSERVATIVE) return d->dim + 1 + d->num_species;
+    return d->flow_model == HB2_SINGLE_SPECIES ? d->dim + 2 : d->dim + 2 * d->num_species;
+}
+int ncomp_of(const hb2_patch_desc* d) { return d->flow_model == HB2_FIVE_EQN_ALLAIRE ? neq_of(d) + 1 : neq_of(d); }
 
 struct PtrTab {
     double* p[HB2_MAXC];
@@ -516,6 +524,9 @@ int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* out)
     for (int s = 0; s < HB2_MAX_SPECIES; s++) {
         p->K.gamma[s] = (s < d->num_species) ? d->species_gamma[s] : 1.4;
         p->K.inv_gm1[s] = 1.0 / (p->K.gamma[s] - 1.0);
+        const double R = (d->flow_model == HB2_FOUR_EQN_CONSERVATIVE && s < d->num_species) ? d->species_R[s] : 1.0;
+        p->K.cp[s] = p->K.gamma[s] / (p->K.gamma[s] - 1.0) * R;
+        p->K.cv[s] = 1.0 / (p->K.gamma[s] - 1.0) * R;
     }
     p->K.weno_p = p->d.weno_p;
     p->K.weno_q = d->weno_q > 0 ? d->weno_q : 4;
@@ -529,6 +540,9 @@ int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* out)
     if (d->scheme == HB2_WCNS5_Z) p->ops = (d->math == HB2_MATH_FAST && p->d.weno_p == 2) ? ops_fast_z() : ops_exact_z();
     if (d->scheme == HB2_WCNS6_LD)
         p->ops = (d->math == HB2_MATH_FAST && p->d.weno_p == 2 && p->K.weno_q == 4) ? ops_fast_ld() : ops_exact_ld();
+    /* the four-eqn conservative model has reference-order kernels only */
+    if (d->flow_model == HB2_FOUR_EQN_CONSERVATIVE)
+        p->ops = d->scheme == HB2_WCNS5_Z ? ops_exact_z() : (d->scheme == HB2_WCNS6_LD ? ops_exact_ld() : ops_exact());
     p->ncell_i = (long long)p->G.n[0] * p->G.n[1] * p->G.n[2];
     for (int a = 0; a < 3; a++) {
         long long ee[3] = {p->G.n[0], p->G.n[1], p->G.n[2]};
@@ -976,6 +990,8 @@ int hb2_max_wave_speed_dev(hb2_plan_t p, const double* const* Q, double* out_dev
     if (p->cfg.model == SS && p->cfg.dim == 3) k_wave_speed<Traits<SS, 3, 1>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
     if (p->cfg.model == FE && p->cfg.dim == 2) k_wave_speed<Traits<FE, 2, 2>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
     if (p->cfg.model == FE && p->cfg.dim == 3) k_wave_speed<Traits<FE, 3, 2>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
+    if (p->cfg.model == FC && p->cfg.dim == 2) k_wave_speed<Traits<FC, 2, 2>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
+    if (p->cfg.model == FC && p->cfg.dim == 3) k_wave_speed<Traits<FC, 3, 2>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
     p->launches++;
     HB2_CUDA(cudaGetLastError());
     return 0;

@@ -46,7 +46,7 @@
 
 namespace hb2 {
 
-enum { SS = 0, FE = 1 };
+enum { SS = 0, FE = 1, FC = 2 };   /* single-species, five-eqn Allaire, four-eqn conservative */
 enum { MODE_EMIT = 0, MODE_FUSED = 1 };
 
 template <int MODEL_, int DIM_, int NS_>
@@ -55,8 +55,10 @@ struct Traits {
     static constexpr int DIM = DIM_;
     static constexpr int NS = (MODEL_ == SS) ? 1 : NS_;
     static constexpr int NM = NS;                                  /* mass equations */
-    static constexpr int NEQ = (MODEL_ == SS) ? DIM_ + 2 : DIM_ + 2 * NS_;
-    static constexpr int NCOMP = (MODEL_ == SS) ? NEQ : NEQ + 1;   /* + stored Z_last */
+    /* FlowModelSingleSpecies.cpp:29, FlowModelFiveEqnAllaire.cpp:29, FlowModelFourEqnConservative.cpp:29 */
+    static constexpr int NEQ = (MODEL_ == SS) ? DIM_ + 2 : (MODEL_ == FC ? DIM_ + 1 + NS_ : DIM_ + 2 * NS_);
+    static constexpr int NCOMP = (MODEL_ == FE) ? NEQ + 1 : NEQ;   /* + stored Z_last */
+    static constexpr int NZ = (MODEL_ == FE) ? NS_ - 1 : 0;        /* advected volume fractions */
     static constexpr int IV = NM;                                  /* first velocity index */
     static constexpr int IP = NM + DIM_;                           /* pressure (V) / energy (Q) index */
     static constexpr bool ADV = (MODEL_ == FE);                    /* has advective equations */
@@ -75,6 +77,8 @@ struct Geom {
 struct Consts {
     double gamma[4];
     double inv_gm1[4]; /* 1/(gamma_i - 1), EquationOfStateMixingRulesIdealGas.cpp:7523 */
+    double cp[4];      /* four-eqn conservative: species c_p_i = gamma_i/(gamma_i - 1) R_i, c_v_i = 1/(gamma_i - 1) R_i */
+    double cv[4];      /* (EquationOfStateMixingRulesIdealGas.cpp:108-119) */
     int weno_p;
     int weno_q;            /* WCNS6-LD: constant_q, constant_C, constant_alpha_tau (WCNS6-LD-HLLC-HLL.cpp:343-361) */
     double weno_C;
@@ -153,6 +157,18 @@ HB2_HD long long sidx(const Geom& G, int i, int j, int k)
 /* ------------------------------------------------------------------------------------------
  * cell stage: conservative -> primitive + sound speed
  * ---------------------------------------------------------------------------------------- */
+/* four-eqn conservative: c = sqrt(Gamma p/rho + sum Y_i Psi_i), Psi_i = ((c_p_i - gamma c_v_i)/c_v + gamma - 1) epsilon with
+ * epsilon recomputed from p (FlowModelFourEqnConservative.cpp:5087-5430; EquationOfStateMixingRulesIdealGas.cpp:6406-6409) */
+template <int NS>
+HB2_HD double fc_sound_speed(const Consts& K, double rho, const double (&Y)[NS], double p, double gamma_m, double c_v)
+{
+    const double eps = p / ((gamma_m - 1.0) * rho);
+    double cc = (gamma_m - 1.0) * p / rho;
+#pragma unroll
+    for (int si = 0; si < NS; si++) cc += Y[si] * (((K.cp[si] - gamma_m * K.cv[si]) / c_v + gamma_m - 1.0) * eps);
+    return sqrt(cc);
+}
+
 template <class Tr>
 HB2_HD void cons_to_prim(const double (&q)[Tr::NCOMP], const Consts& K, double (&V)[Tr::NEQ], double& c)
 {
@@ -170,6 +186,35 @@ HB2_HD void cons_to_prim(const double (&q)[Tr::NCOMP], const Consts& K, double (
         const double p = (K.gamma[0] - 1.0) * rho * epsilon;
         V[DIM + 1] = p;
         c = sqrt(K.gamma[0] * p / rho);
+    } else if (Tr::MODEL == FC) {
+        /* FlowModelFourEqnConservative.cpp:3877-5430; mixture rules with MASS fractions
+         * (EquationOfStateMixingRulesIdealGas.cpp:6946-7150, 6367-6564) */
+        double rho = 0.0;
+#pragma unroll
+        for (int si = 0; si < NS; si++) rho += q[si];
+        double Y[NS];
+#pragma unroll
+        for (int si = 0; si < NS; si++) {
+            V[si] = q[si];
+            Y[si] = q[si] / rho;
+        }
+        double ke = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+            V[NS + a] = q[NS + a] / rho;
+            ke = (a == 0) ? V[NS + a] * V[NS + a] : ke + V[NS + a] * V[NS + a];
+        }
+        const double epsilon = q[NS + DIM] / rho - 0.5 * ke;
+        double c_p = 0.0, c_v = 0.0;
+#pragma unroll
+        for (int si = 0; si < NS; si++) {
+            c_p += Y[si] * K.cp[si];
+            c_v += Y[si] * K.cv[si];
+        }
+        const double gamma_m = c_p / c_v;
+        const double p = (gamma_m - 1.0) * rho * epsilon;
+        V[NS + DIM] = p;
+        c = fc_sound_speed<NS>(K, rho, Y, p, gamma_m, c_v);
     } else {
         double rho = 0.0;
 #pragma unroll
@@ -199,7 +244,7 @@ HB2_HD void cons_to_prim(const double (&q)[Tr::NCOMP], const Consts& K, double (
         for (int si = 0; si < NS; si++) cc += Y[si] * (p / rho);
         c = sqrt(cc);
 #pragma unroll
-        for (int si = 0; si < NS - 1; si++) V[NS + DIM + 1 + si] = q[NS + DIM + 1 + si];
+        for (int si = 0; si < Tr::NZ; si++) V[NS + DIM + 1 + si] = q[NS + DIM + 1 + si];
     }
 }
 
@@ -222,7 +267,7 @@ HB2_HD void node_flux(const double (&q)[Tr::NCOMP], const double (&V)[Tr::NEQ], 
         for (int a = 0; a < DIM; a++) Fn[NS + a] = (a == DIR) ? un * q[NS + a] + p : un * q[NS + a];
         Fn[NS + DIM] = un * (q[NS + DIM] + p);
 #pragma unroll
-        for (int si = 0; si < NS - 1; si++) Fn[NS + DIM + 1 + si] = un * q[NS + DIM + 1 + si];
+        for (int si = 0; si < Tr::NZ; si++) Fn[NS + DIM + 1 + si] = un * q[NS + DIM + 1 + si];
     }
 }
 
@@ -391,6 +436,25 @@ HB2_HD void side_thermo(const double (&V)[Tr::NEQ], const Consts& K, double& rho
         const double p = V[DIM + 1];
         c = sqrt(K.gamma[0] * p / rho);
         eps = p / ((K.gamma[0] - 1.0) * rho);
+    } else if (Tr::MODEL == FC) {
+        /* FlowModelRiemannSolverFourEqnConservativeHLLC-HLL.cpp:5150-5290 */
+        double r = 0.0;
+#pragma unroll
+        for (int si = 0; si < NS; si++) r += V[si];
+        const double p = V[NS + DIM];
+        double Y[NS];
+        double c_p = 0.0, c_v = 0.0;
+#pragma unroll
+        for (int si = 0; si < NS; si++) Y[si] = V[si] / r;
+#pragma unroll
+        for (int si = 0; si < NS; si++) {
+            c_p += Y[si] * K.cp[si];
+            c_v += Y[si] * K.cv[si];
+        }
+        const double gamma_m = c_p / c_v;
+        rho = r;
+        eps = p / ((gamma_m - 1.0) * r);
+        c = fc_sound_speed<NS>(K, r, Y, p, gamma_m, c_v);
     } else {
         double r = 0.0;
 #pragma unroll
@@ -425,6 +489,18 @@ HB2_HD int side_bounded(const double (&V)[Tr::NEQ], const Consts& K)
     if (Tr::MODEL == SS) {
         ok &= (V[0] > 0.0) ? 1 : 0;
         ok &= (V[NEQ - 1] > 0.0) ? 1 : 0;
+    } else if (Tr::MODEL == FC) {
+        /* FlowModelBasicUtilitiesFourEqnConservative.cpp:3737-4510 */
+        double rho = 0.0;
+#pragma unroll
+        for (int si = 0; si < NS; si++) rho += V[si];
+#pragma unroll
+        for (int si = 0; si < NS; si++) {
+            const double Y = V[si] / rho;
+            ok &= (Y > HB2_Y_BOUND_LO && Y < HB2_Y_BOUND_UP) ? 1 : 0;
+        }
+        ok &= (rho > 0.0) ? 1 : 0;
+        ok &= (V[NS + DIM] > 0.0) ? 1 : 0;
     } else {
         const double Z_lo = HB2_Z_BOUND_LO, Z_up = HB2_Z_BOUND_UP, Y_lo = HB2_Y_BOUND_LO, Y_up = HB2_Y_BOUND_UP;
         double Z[NS];
@@ -511,14 +587,14 @@ HB2_HD void riemann(const double (&V_L)[Tr::NEQ], const double (&V_R)[Tr::NEQ], 
             for (int a = 0; a < DIM; a++) Q[IV + a] = rho * V[IV + a];
             Q[IP] = rho * (eps + 0.5 * ke);
 #pragma unroll
-            for (int si = 0; si < NS - 1; si++) Q[IP + 1 + si] = V[IP + 1 + si];
+            for (int si = 0; si < Tr::NZ; si++) Q[IP + 1 + si] = V[IP + 1 + si];
 #pragma unroll
             for (int si = 0; si < NS; si++) F[si] = un * V[si];
 #pragma unroll
             for (int a = 0; a < DIM; a++) F[IV + a] = (a == DIR) ? un * Q[IV + a] + p : un * Q[IV + a];
             F[IP] = un * (Q[IP] + p);
 #pragma unroll
-            for (int si = 0; si < NS - 1; si++) F[IP + 1 + si] = un * V[IP + 1 + si];
+            for (int si = 0; si < Tr::NZ; si++) F[IP + 1 + si] = un * V[IP + 1 + si];
         }
     };
 
@@ -669,7 +745,7 @@ HB2_HD void face_midpoint(const double (&V)[6][Tr::NEQ], double c_cellL, double 
             weno_pair<MATH>(V[0][IV + a], V[1][IV + a], V[2][IV + a], V[3][IV + a], V[4][IV + a], V[5][IV + a], K, V_minus[IV + a], V_plus[IV + a]);
         }
 #pragma unroll
-        for (int si = 0; si < NS - 1; si++) {
+        for (int si = 0; si < Tr::NZ; si++) {
             const int e = IP + 1 + si;
             weno_pair<MATH>(V[0][e], V[1][e], V[2][e], V[3][e], V[4][e], V[5][e], K, V_minus[e], V_plus[e]);
         }

@@ -137,7 +137,7 @@ HB2_HD void cons_to_prim_fast(const double (&q)[Tr::NCOMP], const Consts& K, dou
         /* c^2 = Gamma p/rho + sum_i Y_i p/rho with sum_i Y_i = 1 */
         c = sqrt_fast<true>((Gamma + 1.0) * p * r);
 #pragma unroll
-        for (int si = 0; si < NS - 1; si++) V[NS + DIM + 1 + si] = q[NS + DIM + 1 + si];
+        for (int si = 0; si < Tr::NZ; si++) V[NS + DIM + 1 + si] = q[NS + DIM + 1 + si];
     }
 }
 
@@ -170,7 +170,7 @@ HB2_HD void node_flux_prim(const double* cell, double E_stored, const Consts& K,
         }
         E = E_stored;
 #pragma unroll
-        for (int si = 0; si < NS - 1; si++) Fn[IP + 1 + si] = un * cell[(IP + 1 + si) * CS];
+        for (int si = 0; si < Tr::NZ; si++) Fn[IP + 1 + si] = un * cell[(IP + 1 + si) * CS];
     }
     const double ru = rho * un;
 #pragma unroll
@@ -199,7 +199,7 @@ HB2_HD void prim_to_cons(const double* cell, double E_stored, const Consts& K, d
     }
     q[IP] = (Tr::MODEL == SS) ? fma(0.5 * rho, ke, cell[IP * CS] * K.inv_gm1[0]) : E_stored;
 #pragma unroll
-    for (int si = 0; si < NS - 1; si++) q[IP + 1 + si] = cell[(IP + 1 + si) * CS];
+    for (int si = 0; si < Tr::NZ; si++) q[IP + 1 + si] = cell[(IP + 1 + si) * CS];
 }
 
 /* ------------------------------------------------------------------------------------------

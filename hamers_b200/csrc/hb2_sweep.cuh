@@ -201,7 +201,7 @@ HB2_HD void phase_commit(const DirArgs& A, double* smem, const PencilCtx& c, int
     using Sh = SweepShape<Tr, DIR, MATH>;
     constexpr int NEQ = Tr::NEQ;
     double V[NEQ], cs;
-    if (MATH == 0)
+    if constexpr (MATH == 0)
         cons_to_prim<Tr>(q, A.K, V, cs);
     else
         cons_to_prim_fast<Tr>(q, A.K, V, cs);
@@ -258,7 +258,7 @@ HB2_HD void phase_face(const DirArgs& A, double* smem, const PencilCtx& c, int t
     /* stencil window: cells f-3..f+2 at win[comp*CSV + m*MS] */
     const double* win = smem + Sh::slotv(c.pp, (f - 3) & (Sh::RING - 1));
     double Fm[NEQ], um;
-    if (MATH == 0) {
+    if constexpr (MATH == 0) {
         double V[6][NEQ];
 #pragma unroll
         for (int m = 0; m < 6; m++)
@@ -384,7 +384,7 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
     }
 
     double rhs[NEQ];
-    if (MATH == 1) {
+    if constexpr (MATH == 1) {
         /* node fluxes from the primitive ring */
         double Np[NEQ], Nm[NEQ];
         node_flux_prim<Tr, DIR, Sh::CSV>(sV + v_p1, sV[(Sh::NV - 1) * Sh::CSV + v_p1], A.K, Np);
@@ -435,7 +435,7 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
         if (LAST) {
             if (Tr::ADV) {
 #pragma unroll
-                for (int si = 0; si < NS - 1; si++) {
+                for (int si = 0; si < Tr::NZ; si++) {
                     const int e = IP + 1 + si;
                     rhs[e] = rhs[e] + A.dt * sV[e * Sh::CSV + v_0] * Tsum;
                 }
@@ -443,7 +443,7 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
             /* Euler.cpp:1479, 1544-1548: zero; += alpha_n*U_n for alpha_n != 0; += beta*(...) */
             double ua[NEQ];
             double qc[NEQ];
-            if (QREC) prim_to_cons<Tr, Sh::CSV>(sV + v_0, sV[(Sh::NV - 1) * Sh::CSV + v_0], A.K, qc);
+            if constexpr (QREC) prim_to_cons<Tr, Sh::CSV>(sV + v_0, sV[(Sh::NV - 1) * Sh::CSV + v_0], A.K, qc);
 #pragma unroll
             for (int e = 0; e < NEQ; e++) {
                 double u = 0.0;
@@ -461,7 +461,7 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
         }
     } else if (LAST && Tr::ADV) {
 #pragma unroll
-        for (int si = 0; si < NS - 1; si++) {
+        for (int si = 0; si < Tr::NZ; si++) {
             const int e = IP + 1 + si;
             A.S[e][ix] += A.dt * sV[e * Sh::CSV + v_0] * Tsum;
         }

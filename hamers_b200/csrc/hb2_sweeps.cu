@@ -234,12 +234,22 @@ int launch_sweep_t(const LaunchCfg&, int dir, const DirArgs& A, cudaStream_t st)
     return launch_dir<Tr, (Tr::DIM == 3 ? 2 : 1)>(A, st);
 }
 
+/* the four-eqn conservative model exists in the reference-order translation units only */
+#if HB2_MATH == 0
+#define HB2_DISPATCH_FC(cfg, CALL)                                                    \
+    if ((cfg).model == FC && (cfg).dim == 2 && (cfg).ns == 2) { using Tr = Traits<FC, 2, 2>; CALL; } \
+    if ((cfg).model == FC && (cfg).dim == 3 && (cfg).ns == 2) { using Tr = Traits<FC, 3, 2>; CALL; }
+#else
+#define HB2_DISPATCH_FC(cfg, CALL)
+#endif
+
 #define HB2_DISPATCH(cfg, CALL)                                                       \
     do {                                                                              \
         if ((cfg).model == SS && (cfg).dim == 2) { using Tr = Traits<SS, 2, 1>; CALL; } \
         if ((cfg).model == SS && (cfg).dim == 3) { using Tr = Traits<SS, 3, 1>; CALL; } \
         if ((cfg).model == FE && (cfg).dim == 2 && (cfg).ns == 2) { using Tr = Traits<FE, 2, 2>; CALL; } \
         if ((cfg).model == FE && (cfg).dim == 3 && (cfg).ns == 2) { using Tr = Traits<FE, 3, 2>; CALL; } \
+        HB2_DISPATCH_FC(cfg, CALL)                                                    \
     } while (0)
 
 int op_sensor(const LaunchCfg& cfg, const SensorArgs& A, cudaStream_t st)

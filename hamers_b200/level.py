@@ -240,7 +240,7 @@ class UniformLevel:
     def __init__(self, dim: int, N: Sequence[int], flow_model: int = 0, species_gamma: Sequence[float] = (1.4,),
                  domain: Tuple[float, float] = (-1.0, 1.0), math: int = 1, weno_p: int = 2,
                  grid: Optional[Sequence[int]] = None, push: Optional[bool] = None, scheme: int = 0,
-                 distributed: bool = True):
+                 distributed: bool = True, species_R: Sequence[float] = ()):
         import itertools
         import os
 
@@ -259,7 +259,7 @@ class UniformLevel:
         self.dim = dim
         self.dx = tuple((domain[1] - domain[0]) / n for n in self.decomp.N)
         self.plan = abi.Plan(dim, self.decomp.n, flow_model=flow_model, species_gamma=species_gamma, dx=self.dx,
-                             weno_p=weno_p, math=math, scheme=scheme).use_torch_stream()
+                             weno_p=weno_p, math=math, scheme=scheme, species_R=species_R).use_torch_stream()
         self.ncomp, self.neq = self.plan.ncomp, self.plan.neq
         shape = (self.ncomp,) + self.plan.ghost_shape
         if push is None:

@@ -26,6 +26,7 @@
  *       single-species : rho, rho*u, rho*v, (rho*w), E                      (num_comp = dim+2)
  *       five-eqn       : Zrho_1..Zrho_ns, rho*u, rho*v, (rho*w), E, Z_1..Z_ns (num_comp = dim+2ns+1;
  *                        the last volume fraction is stored but is not an equation)
+ *       four-eqn cons. : rhoY_1..rhoY_ns, rho*u, rho*v, (rho*w), E           (num_comp = dim+1+ns)
  *   - pointers in the *_dev calls are DEVICE pointers on the plan's device and must stay valid
  *     until the plan's stream has been synchronised; the *_host calls take HOST pointers and do
  *     the H2D / D2H copies themselves (the reference-facing, host-memory drop-in).
@@ -50,6 +51,11 @@ extern "C" {
 
 #define HB2_SINGLE_SPECIES 0    /* FlowModelManager.cpp:20 "SINGLE_SPECIES" */
 #define HB2_FIVE_EQN_ALLAIRE 1  /* FlowModelManager.cpp:44 "FIVE_EQN_ALLAIRE" */
+/* FlowModelManager.cpp "FOUR_EQN_CONSERVATIVE" (src/flow/flow_models/four-eqn_conservative/): partial densities
+ * rho Y_1..rho Y_ns, momentum, total energy (num_comp = num_eqn = dim + 1 + ns), all equations conservative; mixture of
+ * ideal gases closed by mass fractions (species_gamma AND species_R are needed).  Built for num_species = 2; runs the
+ * reference-order kernels whatever `math` says. */
+#define HB2_FOUR_EQN_CONSERVATIVE 2
 
 /* arithmetic variants */
 #define HB2_MATH_EXACT 0        /* reference operation order, no FMA contraction: bit-identical to the oracle */
@@ -78,6 +84,9 @@ typedef struct hb2_patch_desc {
      * whatever it is; a Navier-Stokes application allocates the state with six (the diffusive reconstructor's width,
      * HB2_DIFF_GHOSTS) and hands the same arrays to both reconstructors, like SAMRAI does.  4 <= num_ghosts <= 8. */
     int32_t num_ghosts;
+    /* Equation_of_state_mixing_rules{species_R}: gas constants of the species, used by HB2_FOUR_EQN_CONSERVATIVE only
+     * (EquationOfStateMixingRulesIdealGas.cpp:60-119) */
+    double species_R[HB2_MAX_SPECIES];
 } hb2_patch_desc;
 
 #define HB2_WCNS5_JS 0

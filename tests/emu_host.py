@@ -18,7 +18,8 @@ class EmuDesc(C.Structure):
     _fields_ = [("dim", C.c_int), ("n", C.c_int * 3), ("model", C.c_int), ("ns", C.c_int),
                 ("gamma", C.c_double * 4), ("dx", C.c_double * 3), ("weno_p", C.c_int),
                 ("math", C.c_int), ("bx", C.c_int), ("seg_len", C.c_int),
-                ("weno_q", C.c_int), ("weno_C", C.c_double), ("weno_alpha_tau", C.c_double), ("ghosts", C.c_int)]
+                ("weno_q", C.c_int), ("weno_C", C.c_double), ("weno_alpha_tau", C.c_double), ("ghosts", C.c_int),
+                ("R", C.c_double * 4)]
 
 
 def lib(scheme: int = 0):
@@ -53,6 +54,8 @@ def _desc(desc, math, bx, seg_len, ghosts=0):
     d.model, d.ns = desc.model, desc.ns
     for i, g in enumerate(desc.gamma):
         d.gamma[i] = g
+    for i, r in enumerate(getattr(desc, "R", ())):
+        d.R[i] = r
     d.weno_p, d.math, d.bx, d.seg_len = desc.weno_p, math, bx, seg_len
     d.weno_q, d.weno_C, d.weno_alpha_tau = desc.weno_q, desc.weno_C, desc.weno_alpha_tau
     return d

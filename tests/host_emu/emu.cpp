@@ -22,7 +22,11 @@ struct EmuDesc {
     int weno_q;            /* WCNS6-LD constants (the interpolator itself is compiled in: -DHB2_SCHEME) */
     double weno_C, weno_alpha_tau;
     int ghosts;            /* ghost width of the cell-data layout (0 = 4); the kernels read 4 layers whatever it is */
+    double R[4];           /* four-eqn conservative model: species gas constants */
 };
+
+static int emu_neq(const EmuDesc* d) { return d->model == SS ? d->dim + 2 : (d->model == FC ? d->dim + 1 + d->ns : d->dim + 2 * d->ns); }
+static int emu_ncomp(const EmuDesc* d) { return d->model == FE ? emu_neq(d) + 1 : emu_neq(d); }
 
 static void make_geom(const EmuDesc* d, Geom* G)
 {
@@ -180,6 +184,9 @@ static void run_sweeps(DirArgs A0, int sensor_seg_len, int seg_len, double* cons
         if ((d)->model == SS && (d)->dim == 3) { using Tr = Traits<SS, 3, 1>; if ((d)->math == 0) { constexpr int MATH = 0; CALL; } else { constexpr int MATH = 1; CALL; } return 0; } \
         if ((d)->model == FE && (d)->dim == 2) { using Tr = Traits<FE, 2, 2>; if ((d)->math == 0) { constexpr int MATH = 0; CALL; } else { constexpr int MATH = 1; CALL; } return 0; } \
         if ((d)->model == FE && (d)->dim == 3) { using Tr = Traits<FE, 3, 2>; if ((d)->math == 0) { constexpr int MATH = 0; CALL; } else { constexpr int MATH = 1; CALL; } return 0; } \
+        /* four-eqn conservative: reference-order kernels only, like the product library */ \
+        if ((d)->model == FC && (d)->dim == 2) { using Tr = Traits<FC, 2, 2>; constexpr int MATH = 0; CALL; return 0; } \
+        if ((d)->model == FC && (d)->dim == 3) { using Tr = Traits<FC, 3, 2>; constexpr int MATH = 0; CALL; return 0; } \
     } while (0)
 
 static void fill_common(const EmuDesc* d, DirArgs* A, const double* const* Q, double dt, std::vector<double>& T)
@@ -189,12 +196,15 @@ static void fill_common(const EmuDesc* d, DirArgs* A, const double* const* Q, do
     for (int s = 0; s < 4; s++) {
         A->K.gamma[s] = (s < d->ns) ? d->gamma[s] : 1.4;
         A->K.inv_gm1[s] = 1.0 / (A->K.gamma[s] - 1.0);
+        const double R = (d->model == FC && s < d->ns) ? d->R[s] : 1.0;
+        A->K.cp[s] = A->K.gamma[s] / (A->K.gamma[s] - 1.0) * R;
+        A->K.cv[s] = 1.0 / (A->K.gamma[s] - 1.0) * R;
     }
     A->K.weno_p = d->weno_p > 0 ? d->weno_p : 2;
     A->K.weno_q = d->weno_q > 0 ? d->weno_q : 4;
     A->K.weno_C = d->weno_C > 0.0 ? d->weno_C : 1.0e9;
     A->K.weno_alpha_tau = d->weno_alpha_tau > 0.0 ? d->weno_alpha_tau : 35.0;
-    const int ncomp = d->model == SS ? d->dim + 2 : d->dim + 2 * d->ns + 1;
+    const int ncomp = emu_ncomp(d);
     for (int c = 0; c < ncomp; c++) A->Q[c] = Q[c];
     A->dt = dt;
     T.assign((size_t)A->G.n[0] * A->G.n[1] * A->G.n[2], 0.0);
@@ -206,7 +216,7 @@ extern "C" int emu_flux_and_source(const EmuDesc* d, const double* const* Q, dou
     DirArgs A;
     std::vector<double> T;
     fill_common(d, &A, Q, dt, T);
-    const int neq = d->model == SS ? d->dim + 2 : d->dim + 2 * d->ns;
+    const int neq = emu_neq(d);
     for (int e = 0; e < neq; e++) A.S[e] = S ? S[e] : nullptr;
     EMU_DISPATCH(d, (run_sweeps<Tr, MATH>(A, d->bx, d->seg_len, F, MODE_EMIT)));
     return -1;
@@ -225,8 +235,8 @@ extern "C" int emu_fused_stage(const EmuDesc* d, int ncoef, const double* alpha,
 extern "C" int emu_fused_stage_push(const EmuDesc* d, int ncoef, const double* alpha, const double* beta,
                                     const double* const* U_int, double dt, double* const* U_out, int push)
 {
-    const int ncomp = d->model == SS ? d->dim + 2 : d->dim + 2 * d->ns + 1;
-    const int neq = d->model == SS ? d->dim + 2 : d->dim + 2 * d->ns;
+    const int ncomp = emu_ncomp(d);
+    const int neq = emu_neq(d);
     DirArgs A;
     std::vector<double> T;
     fill_common(d, &A, U_int + (size_t)(ncoef - 1) * ncomp, dt, T);
