@@ -39,6 +39,9 @@ SYMBOLS = [
     "hb2_compute_diffusive_flux_dev", "hb2_compute_diffusive_flux_host", "hb2_advance_stage_ns_dev",
     "hb2_diffusive_fill_ghosts_periodic_dev", "hb2_diffusive_extract_view_dev", "hb2_diffusive_accumulate_dev",
     "hb2_diffusive_divergence_accumulate_dev", "hb2_diffusive_max_spectral_radius_dev",
+    # two-level AMR operators
+    "hb2_amr_refine_dev", "hb2_amr_coarsen_dev", "hb2_amr_fluxsum_update_dev", "hb2_amr_coarsen_fluxsum_dev",
+    "hb2_fill_ghosts_extrapolate_dev",
 ]
 
 WCNS5_JS, WCNS5_Z, WCNS6_LD = 0, 1, 2
@@ -317,6 +320,11 @@ class Plan:
         _check(self.lib.hb2_fill_ghosts_periodic_dev(self._h, _ptr_table(_dev_ptrs(U, self.ncomp)), int(mask)),
                "hb2_fill_ghosts_periodic_dev")
 
+    def fill_ghosts_extrapolate(self, U, direction: int, side: int):
+        """BDRY_COND::BASIC::FLOW on one face of the patch: ghost cells copy the adjacent interior cell."""
+        _check(self.lib.hb2_fill_ghosts_extrapolate_dev(self._h, _ptr_table(_dev_ptrs(U, self.ncomp)), int(direction), int(side)),
+               "hb2_fill_ghosts_extrapolate_dev")
+
     def pack_box(self, U, lo, hi, buffer):
         l = (C.c_int32 * 3)(*[int(lo[a]) if a < self.dim else 0 for a in range(3)])
         h = (C.c_int32 * 3)(*[int(hi[a]) if a < self.dim else 1 for a in range(3)])
@@ -524,6 +532,64 @@ def ipc_open(handle: bytes) -> int:
 
 def ipc_close(ptr: int):
     _check(load_library().hb2_ipc_close(C.c_void_p(ptr)), "hb2_ipc_close")
+
+
+class AmrPairC(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("nc", C.c_int32 * 3), ("nf", C.c_int32 * 3), ("ratio", C.c_int32 * 3),
+                ("origin", C.c_int32 * 3), ("ghosts_c", C.c_int32), ("ghosts_f", C.c_int32), ("ncomp", C.c_int32),
+                ("neq", C.c_int32), ("dxc", C.c_double * 3), ("dxf", C.c_double * 3)]
+
+
+class AmrPair:
+    """One coarse patch and one fine patch of a two-level hierarchy (mirrors hb2_amr_pair)."""
+
+    def __init__(self, dim, nc, nf, ratio, origin, dxc, dxf, ncomp, neq, ghosts_c=GHOSTS, ghosts_f=GHOSTS):
+        self.lib = load_library()
+        d = AmrPairC()
+        d.dim = dim
+        for a in range(3):
+            on = a < dim
+            d.nc[a] = int(nc[a]) if on else 1
+            d.nf[a] = int(nf[a]) if on else 1
+            d.ratio[a] = int(ratio[a]) if on else 1
+            d.origin[a] = int(origin[a]) if on else 0
+            d.dxc[a] = float(dxc[a]) if on else 1.0
+            d.dxf[a] = float(dxf[a]) if on else 1.0
+        d.ghosts_c, d.ghosts_f, d.ncomp, d.neq = int(ghosts_c), int(ghosts_f), int(ncomp), int(neq)
+        self.desc, self.dim, self.ncomp, self.neq = d, dim, int(ncomp), int(neq)
+
+    @staticmethod
+    def _stream():
+        import torch
+
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _box(self, lo, hi):
+        l = (C.c_int32 * 3)(*[int(lo[a]) if a < self.dim else 0 for a in range(3)])
+        h = (C.c_int32 * 3)(*[int(hi[a]) if a < self.dim else 1 for a in range(3)])
+        return l, h
+
+    def refine(self, Uc_old, Uc_new, tfrac: float, lo, hi, Uf):
+        l, h = self._box(lo, hi)
+        new = _ptr_table(_dev_ptrs(Uc_new, self.ncomp)) if Uc_new is not None else None
+        _check(self.lib.hb2_amr_refine_dev(C.byref(self.desc), _ptr_table(_dev_ptrs(Uc_old, self.ncomp)), new, C.c_double(tfrac),
+                                           l, h, _ptr_table(_dev_ptrs(Uf, self.ncomp)), self._stream()), "hb2_amr_refine_dev")
+
+    def coarsen(self, Uf, lo, hi, Uc):
+        l, h = self._box(lo, hi)
+        _check(self.lib.hb2_amr_coarsen_dev(C.byref(self.desc), _ptr_table(_dev_ptrs(Uf, self.ncomp)), l, h,
+                                            _ptr_table(_dev_ptrs(Uc, self.ncomp)), self._stream()), "hb2_amr_coarsen_dev")
+
+    def fluxsum_update(self, F_fine, fluxsum):
+        """F_fine: list per direction of (neq, ...) side tensors; fluxsum: list [2 dir + side] of (neq, tangential cells)."""
+        _check(self.lib.hb2_amr_fluxsum_update_dev(C.byref(self.desc), _ptr_table(_dev_ptrs(F_fine, self.neq)),
+                                                   _ptr_table(_dev_ptrs(fluxsum, self.neq)), self._stream()),
+               "hb2_amr_fluxsum_update_dev")
+
+    def coarsen_fluxsum(self, fluxsum, F_coarse):
+        _check(self.lib.hb2_amr_coarsen_fluxsum_dev(C.byref(self.desc), _ptr_table(_dev_ptrs(fluxsum, self.neq)),
+                                                    _ptr_table(_dev_ptrs(F_coarse, self.neq)), self._stream()),
+               "hb2_amr_coarsen_fluxsum_dev")
 
 
 class DeviceArray:

@@ -45,6 +45,12 @@ namespace hb2 {
 /* error channel shared with the other translation units of the library (hb2_diffusive.cu) */
 int set_error(int code, const std::string& msg) { return fail(code, msg); }
 }  // namespace hb2
+namespace hb2 {
+/* what hb2_amr.cu needs to know about a plan */
+void* plan_stream(hb2_plan_t plan);
+int plan_layout(hb2_plan_t plan, int* dim, int n[3], int* ghosts, int* ncomp);
+void plan_count_launch(hb2_plan_t plan);
+}  // namespace hb2
 
 struct hb2_plan_s {
     hb2_patch_desc d;
@@ -639,6 +645,20 @@ int hb2_plan_synchronize(hb2_plan_t p)
 }
 
 int64_t hb2_plan_launch_count(hb2_plan_t p) { return p ? p->launches : -1; }
+}  // extern "C" (reopened below)
+namespace hb2 {
+void* plan_stream(hb2_plan_t p) { return (void*)p->stream; }
+int plan_layout(hb2_plan_t p, int* dim, int n[3], int* ghosts, int* ncomp)
+{
+    *dim = p->G.dim;
+    for (int a = 0; a < 3; a++) n[a] = p->G.n[a];
+    *ghosts = p->G.g[0];
+    *ncomp = p->ncomp;
+    return 0;
+}
+void plan_count_launch(hb2_plan_t p) { p->launches++; }
+}  // namespace hb2
+extern "C" {
 int64_t hb2_plan_workspace_bytes(hb2_plan_t p) { return p ? p->ws_bytes : -1; }
 
 int hb2_compute_flux_and_source_dev(hb2_plan_t p, const double* const* Q, double dt, double* const* flux,

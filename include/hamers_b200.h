@@ -306,6 +306,48 @@ int hb2_diffusive_accumulate_dev(hb2_diff_plan_t plan, int32_t num_ghosts, doubl
 int hb2_diffusive_divergence_accumulate_dev(hb2_diff_plan_t plan, const double* const* Q, double dt, int32_t num_ghosts,
                                             double beta, double* const* U);
 
+/* ---- patch-data operators of a two-level AMR step (Berger-Colella flux correction) -----------------------
+ * What RungeKuttaLevelIntegrator does around the hot path when a finer level exists (src/algs/integrator/
+ * RungeKuttaLevelIntegrator.cpp): coarse-fine ghost fill with time interpolation (:1568, xfer::RefineSchedule), flux
+ * integrals on the outer sides of fine patches (:2968-3230, src/algs/integrator/fortran/algs_upfluxsum{2,3}d.f), their
+ * coarsening onto the coarse flux (:2147-2158), the repeated conservative difference Euler::synchronizeFluxes
+ * (Euler.cpp:1682-1949 = hb2_advance_stage_dev with alpha = beta = 1 on the accumulated flux) and the conservative
+ * coarsening of the solution (:2189-2203).  One coarse patch and one fine patch per call; all pointers are DEVICE
+ * pointers; cell data in the SAMRAI ghost-box layout, side data ghost 0.  The three SAMRAI geom operators are restated
+ * from SAMRAI 4.1.0's published algorithm (parity unpinned: SAMRAI is not part of the reference tree). */
+typedef struct hb2_amr_pair {
+    int32_t dim;            /* 2 or 3 */
+    int32_t nc[3];          /* interior cells of the coarse patch */
+    int32_t nf[3];          /* interior cells of the fine patch = ratio * (coarse cells it covers) */
+    int32_t ratio[3];       /* PatchHierarchy{ratio_to_coarser} */
+    int32_t origin[3];      /* index, in the coarse patch, of the coarse cell that holds fine cell 0 */
+    int32_t ghosts_c;       /* ghost width of the coarse / fine cell-data layouts (HB2_GHOSTS for the convective state) */
+    int32_t ghosts_f;
+    int32_t ncomp;          /* conservative components moved (hb2_num_comp) */
+    int32_t neq;            /* equations with a flux (hb2_num_eqn) */
+    double dxc[3], dxf[3];
+} hb2_amr_pair;
+
+/* Coarse-to-fine fill of the fine cells [lo, hi) (fine patch indices, ghost cells included): linear time interpolation
+ * between Uc_old and Uc_new (tfrac = (t - t_old)/(t_new - t_old); Uc_new = NULL: Uc_old alone), then
+ * "CONSERVATIVE_LINEAR_REFINE".  The coarse ghost cells the stencil reaches must be filled by the caller. */
+int hb2_amr_refine_dev(const hb2_amr_pair* pair, const double* const* Uc_old, const double* const* Uc_new, double tfrac,
+                       const int32_t lo[3], const int32_t hi[3], double* const* Uf, void* cuda_stream);
+/* "CONSERVATIVE_COARSEN": the coarse cells [lo, hi) (coarse patch indices, covered by the fine patch) become the
+ * volume-weighted averages of their fine cells. */
+int hb2_amr_coarsen_dev(const hb2_amr_pair* pair, const double* const* Uf, const int32_t lo[3], const int32_t hi[3],
+                        double* const* Uc, void* cuda_stream);
+/* upfluxsumside{2,3}d: fluxsum[(2 dir + side) * neq + e][tangential cell] += F_fine[dir * neq + e][face on that patch side].
+ * fluxsum arrays are dense over the tangential cells of the fine patch, lower direction fastest; zeroed by the caller on
+ * the first fine step of a coarse step (preprocessFluxAndSourceData, :2880-2960). */
+int hb2_amr_fluxsum_update_dev(const hb2_amr_pair* pair, const double* const* F_fine, double* const* fluxsum, void* cuda_stream);
+/* The coarse side flux on every face of the fine patch's boundary := area-weighted average of the fine flux integrals. */
+int hb2_amr_coarsen_fluxsum_dev(const hb2_amr_pair* pair, const double* const* fluxsum, double* const* F_coarse, void* cuda_stream);
+/* BDRY_COND::BASIC::FLOW (BasicCartesianBoundaryUtilities2.cpp:310-345): the ghost cells beyond face (dir, side) of the
+ * plan's patch copy the adjacent interior cell; the other directions run over the interior (fill periodic / other
+ * boundaries afterwards). */
+int hb2_fill_ghosts_extrapolate_dev(hb2_plan_t plan, double* const* U, int32_t dir, int32_t side);
+
 #ifdef __cplusplus
 }
 #endif

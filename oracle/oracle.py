@@ -27,6 +27,8 @@ FOUR_EQN_CONSERVATIVE = 2
 # SSP-RK3 default table, RungeKuttaLevelIntegrator.cpp:3894-3929
 SSPRK3_ALPHA = np.array([[1.0, 0.0, 0.0], [3.0 / 4.0, 1.0 / 4.0, 0.0], [1.0 / 3.0, 0.0, 2.0 / 3.0]])
 SSPRK3_BETA = np.array([[1.0, 0.0, 0.0], [0.0, 1.0 / 4.0, 0.0], [0.0, 0.0, 2.0 / 3.0]])
+# weights of the flux / source sums of a whole step (RungeKuttaLevelIntegrator.cpp:3894-3929), used by the AMR flux correction
+SSPRK3_GAMMA = np.array([[1.0 / 6.0, 0.0, 0.0], [0.0, 1.0 / 6.0, 0.0], [0.0, 0.0, 2.0 / 3.0]])
 
 
 class _Desc(C.Structure):

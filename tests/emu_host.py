@@ -202,3 +202,72 @@ def diff_max_spectral_radius(desc, tr, c_p_eos, Q):
     f.restype = C.c_double
     rho = np.ascontiguousarray(Q[0])
     return f(C.byref(d), C.c_double(c_p_eos), rho.ctypes.data_as(C.POINTER(C.c_double)))
+
+
+# ---- AMR operator kernels (tests/host_emu/emu_amr.cpp) --------------------------------------------------------
+_ASO = os.path.join(_HERE, "host_emu", "libhb2_emu_amr.so")
+_ASRC = os.path.join(_HERE, "host_emu", "emu_amr.cpp")
+_ACORE = os.path.join(_HERE, "..", "hamers_b200", "csrc", "hb2_amr.cuh")
+_ALIB = None
+
+
+class EmuPair(C.Structure):
+    _fields_ = [("dim", C.c_int), ("nc", C.c_int * 3), ("nf", C.c_int * 3), ("ratio", C.c_int * 3), ("origin", C.c_int * 3),
+                ("ghosts_c", C.c_int), ("ghosts_f", C.c_int), ("ncomp", C.c_int), ("neq", C.c_int),
+                ("dxc", C.c_double * 3), ("dxf", C.c_double * 3)]
+
+
+def alib():
+    global _ALIB
+    if _ALIB is None:
+        stale = (not os.path.exists(_ASO)) or any(os.path.getmtime(s) > os.path.getmtime(_ASO) for s in (_ASRC, _ACORE))
+        if stale:
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                                   "-o", _ASO, _ASRC])
+        _ALIB = C.CDLL(_ASO)
+    return _ALIB
+
+
+def amr_pair(dim, nc, nf, ratio, origin, dxc, dxf, ncomp, neq, g=4):
+    p = EmuPair()
+    p.dim = dim
+    for a in range(dim):
+        p.nc[a], p.nf[a], p.ratio[a], p.origin[a], p.dxc[a], p.dxf[a] = nc[a], nf[a], ratio[a], origin[a], dxc[a], dxf[a]
+    p.ghosts_c = p.ghosts_f = g
+    p.ncomp, p.neq = ncomp, neq
+    return p
+
+
+def _i3(v, dim, fill):
+    return (C.c_int * 3)(*[int(v[a]) if a < dim else fill for a in range(3)])
+
+
+def amr_refine(p, Uold, Unew, tfrac, lo, hi, Uf, reverse=False):
+    new = _pp([Unew[c] for c in range(p.ncomp)]) if Unew is not None else None
+    rc = alib().emu_amr_refine(C.byref(p), _pp([Uold[c] for c in range(p.ncomp)]), new, C.c_double(tfrac), _i3(lo, p.dim, 0),
+                               _i3(hi, p.dim, 1), _pp([Uf[c] for c in range(p.ncomp)]), 1 if reverse else 0)
+    assert rc == 0
+
+
+def amr_coarsen(p, Uf, lo, hi, Uc):
+    rc = alib().emu_amr_coarsen(C.byref(p), _pp([Uf[c] for c in range(p.ncomp)]), _i3(lo, p.dim, 0), _i3(hi, p.dim, 1),
+                                _pp([Uc[c] for c in range(p.ncomp)]))
+    assert rc == 0
+
+
+def amr_fluxsum(p, F, fsum):
+    """F: list per direction of (neq, ...) side arrays; fsum: list [2 dir + side] of (neq, ...) arrays, updated in place."""
+    rc = alib().emu_amr_fluxsum(C.byref(p), _pp([F[d][e] for d in range(p.dim) for e in range(p.neq)]),
+                                _pp([fsum[k][e] for k in range(2 * p.dim) for e in range(p.neq)]))
+    assert rc == 0
+
+
+def amr_coarsen_fluxsum(p, fsum, Fc):
+    rc = alib().emu_amr_coarsen_fluxsum(C.byref(p), _pp([fsum[k][e] for k in range(2 * p.dim) for e in range(p.neq)]),
+                                        _pp([Fc[d][e] for d in range(p.dim) for e in range(p.neq)]))
+    assert rc == 0
+
+
+def amr_extrapolate(dim, n, g, U, direction, side):
+    rc = alib().emu_amr_extrapolate(dim, _i3(n, dim, 1), g, U.shape[0], _pp([U[c] for c in range(U.shape[0])]), direction, side)
+    assert rc == 0
