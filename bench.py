@@ -179,6 +179,120 @@ def single_box_replica(args, Nglob, flow_model, gam, math, scheme, n_total_steps
     return out
 
 
+def secondary_measurements(args, torch, dist, rank, world, local_rank):
+    """Numbers next to the headline, same timing rules (CUDA events, 3 warm-up steps, max over ranks):
+      ns     BASELINE.json config 5: 3-D single-species Navier-Stokes Taylor-Green vortex (Re 1600, M 0.1), box-partitioned
+             over the ranks, WCNS5-JS + SIXTH_ORDER diffusive flux, fast route (N = 1: also WCNS6_LD, the shipped deck's choice)
+      shock  N = 1: the branch-coverage state M2 of SURVEY.md 8d at 256^3 (random state + Mach-3 slab: sensor fires, HLL
+             blend and first-order fallback are executed) -- one fused stage, repeated on the same state
+      fe     N = 1: config 3 at 384^3 (five-equation Allaire model)"""
+    from hamers_b200 import abi
+    from hamers_b200.level import PROCESS_GRIDS
+    from hamers_b200.ns_level import NavierStokesLevel
+
+    out = {}
+
+    def timed(fn, steps, warm=3):
+        for _ in range(warm):
+            fn()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]) / steps
+
+    # ---- Navier-Stokes Taylor-Green vortex ---------------------------------------------------------------------------------
+    n = args.ns_size
+    grid = PROCESS_GRIDS[3][world]
+    for scheme_name, scheme in (("WCNS5_JS", abi.WCNS5_JS),) + ((("WCNS6_LD", abi.WCNS6_LD),) if world == 1 else ()):
+        lvl = NavierStokesLevel(3, (n, n, n), species_gamma=1.4, species_R=1.0, species_mu=1.0 / 1600.0, species_mu_v=0.0,
+                                species_c_p=3.5, species_Pr=0.71, domain=(0.0, 2.0 * np.pi), math=abi.MATH_FAST, scheme=scheme)
+        x, y, z = [torch.as_tensor(c, dtype=torch.float64, device="cuda") for c in lvl.coordinates()]
+        X, Y, Z = x[None, None, :], y[None, :, None], z[:, None, None]
+        M0 = 0.1
+        u = torch.sin(X) * torch.cos(Y) * torch.cos(Z)
+        v = -torch.cos(X) * torch.sin(Y) * torch.cos(Z)
+        p = 1.0 / (1.4 * M0 * M0) + (torch.cos(2 * X) + torch.cos(2 * Y)) * (torch.cos(2 * Z) + 2.0) / 16.0
+        rho = torch.ones_like(u)
+        inter = lvl.interior()
+        for c, f in enumerate([rho, rho * u, rho * v, torch.zeros_like(u), p / 0.4 + 0.5 * rho * (u * u + v * v)]):
+            inter[c].copy_(f.expand_as(inter[c]))
+        del u, v, p, rho
+        dt = 0.2 * lvl.dx[0] / (1.0 + 1.0 / M0)
+        l0 = lvl.launch_count
+        ms = timed(lambda: lvl.rk_step(dt), args.ns_steps)
+        state = lvl.S[lvl.cur][lvl._interior_slices()]
+        ke = (0.5 * (state[1] ** 2 + state[2] ** 2 + state[3] ** 2) / state[0]).sum().reshape(1)
+        cks = torch.tensor([bit_checksum(state)], dtype=torch.int64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(ke, op=dist.ReduceOp.SUM)
+            dist.all_reduce(cks, op=dist.ReduceOp.SUM)
+        key = "ns" if scheme == abi.WCNS5_JS else "ns_wcns6ld"
+        out[key] = {"workload": f"3D single-species Navier-Stokes, Taylor-Green vortex Re=1600 M=0.1, periodic {n}^3 over "
+                                f"{world} box(es) {list(grid)}, {scheme_name}_HLLC_HLL + SIXTH_ORDER, SSP-RK3, fast route",
+                    "value": float(n) ** 3 * 3 / (ms * 1e-3), "unit": "cell-updates/s", "ms_per_step": ms, "steps": args.ns_steps,
+                    "gpu_launches_per_step": (lvl.launch_count - l0) / (args.ns_steps + 3),
+                    "mean_kinetic_energy": float(ke[0]) / float(n) ** 3, "checksum": int(cks[0]) & 0xFFFFFFFFFFFFFFFF,
+                    "finite": bool(torch.isfinite(state).all())}
+        lvl.close()
+        del lvl, state
+        torch.cuda.empty_cache()
+    if world > 1:
+        return out
+
+    # ---- shocked field -------------------------------------------------------------------------------------------------------
+    from hamers_b200 import problems as pb
+
+    for model, name in ((abi.SINGLE_SPECIES, "shock"),):
+        n = args.shock_size
+        U, dx, gam = pb.random_state(3, (n, n, n), model=model, seed=20261017, shock=True)
+        plan = abi.Plan(3, (n, n, n), flow_model=model, species_gamma=gam, dx=dx, math=abi.MATH_FAST).use_torch_stream()
+        Q = torch.from_numpy(pb.pad_periodic(U)).cuda()
+        out_t = torch.zeros_like(Q)
+        dtq = 1.0e-3 * dx[0]
+        ms = timed(lambda: plan.fused_stage([1.0], [1.0], [Q], dtq, out_t), 10)
+        # how many faces take the data-dependent branches: the sensor decisions of the plan (one byte per cell, bit d = HLLC-HLL
+        # on the low face in direction d) are not exported; count them with the oracle-free criterion instead: faces whose
+        # fused result differs from a run with the HLL blend disabled cannot be had here, so report the state's statistics
+        out[name] = {"workload": f"3D single-species Euler, WCNS5_JS_HLLC_HLL, one fused stage on the random + Mach-3-slab state "
+                                 f"(SURVEY 8d M2) at {n}^3, fast build", "value": float(n) ** 3 / (ms * 1e-3),
+                     "unit": "cell-updates/s", "ms_per_stage": ms, "finite": bool(torch.isfinite(out_t[:, 4:-4, 4:-4, 4:-4]).all())}
+        # the same size on the smooth field, for the ratio
+        Us, dxs, gs = pb.convergence_single_species(3, n)
+        Q.copy_(torch.from_numpy(pb.pad_periodic(Us)))
+        ms_s = timed(lambda: plan.fused_stage([1.0], [1.0], [Q], dtq, out_t), 10)
+        out[name]["smooth_same_size_value"] = float(n) ** 3 / (ms_s * 1e-3)
+        out[name]["shock_over_smooth"] = ms_s / ms
+        plan.close()
+        del Q, out_t
+        torch.cuda.empty_cache()
+
+    # ---- five-equation model ---------------------------------------------------------------------------------------------------
+    from hamers_b200.level import UniformLevel
+
+    n = args.fe_size
+    lv = UniformLevel(3, (n, n, n), flow_model=abi.FIVE_EQN_ALLAIRE, species_gamma=(8.0 / 5.0, 7.0 / 5.0), math=abi.MATH_FAST,
+                      distributed=False)
+    make_ic_device(lv, "fe")
+    dtf = 0.001 * lv.dx[0]
+    ms = timed(lambda: lv.rk_step(dtf), 5)
+    out["fe"] = {"workload": f"3D five-equation Allaire, WCNS5_JS_HLLC_HLL, SSP-RK3, periodic {n}^3 (config 3 scaled up), fast build",
+                 "value": float(n) ** 3 * 3 / (ms * 1e-3), "unit": "cell-updates/s", "ms_per_step": ms,
+                 "fp64_frac_of_5.6kFLOP_roofline": None, "finite": bool(torch.isfinite(lv.interior()).all())}
+    lv.close()
+    del lv
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     """CPU arm: the oracle (reference-structured restatement, gcc -O3, one OpenMP thread per core standing in
     for one MPI rank, 32^3 patches) on a bounded sample of the same workload."""
@@ -391,6 +505,14 @@ def run_ours(args):
             "sanity": {"finite": finite, "rho_min": rho_min, "rho_max": rho_max}, "parity": parity,
         }
 
+    # ---- secondary measurements (config 5, shocked field, config 3) -----------------------------------
+    if not args.no_secondary:
+        sec = secondary_measurements(args, torch, dist, rank, world, local_rank)
+        if rank == 0:
+            if "fe" in sec:
+                sec["fe"]["fp64_frac_of_5.6kFLOP_roofline"] = ALGO["fe"]["flops"] * sec["fe"]["value"] / 1e12 / line["roofline"]["peak"]
+            line["secondary"] = sec
+
     # ---- end-to-end: host buffers through the C ABI (N = 1: advanceLevel on host memory) ----------
     if world == 1 and not args.no_e2e:
         n = args.e2e_size
@@ -500,10 +622,17 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary measurements (Navier-Stokes, shocked field, five-eqn)")
+    ap.add_argument("--ns-size", type=int, default=0, help="Navier-Stokes Taylor-Green level size (default: --size, at most 512)")
+    ap.add_argument("--ns-steps", type=int, default=5)
+    ap.add_argument("--shock-size", type=int, default=256)
+    ap.add_argument("--fe-size", type=int, default=384)
     ap.add_argument("--no-replica", action="store_true", help="N > 1: skip the one-box replica behind parity.matches_n1")
     args = ap.parse_args()
     if args.e2e_size <= 0:
         args.e2e_size = args.size
+    if args.ns_size <= 0:
+        args.ns_size = min(args.size, 512)
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 3)   # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
