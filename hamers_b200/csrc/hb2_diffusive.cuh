@@ -193,25 +193,14 @@ HB2D_HD double diff_reconstruct(const double* p, long long stride, double dt)
  * the y / z copies: per direction and equation zero, then "+=" term by term, x-, y-, then z-derivative terms).  The three
  * directions draw on the same twelve (2-D: six) first derivatives, so each is evaluated once -- like the reference's
  * derivatives_*_computed maps do -- and used up to three times.  P[v]: primitive scratch arrays on the ghost box. */
+/* node fluxes of all directions from the velocity and the (DIM + 1) x DIM first derivatives of the node */
 template <int DIM>
-HB2D_HD void diff_node_flux_all(const DiffGeom& G, const DiffConsts& K, const double* const* P, long long x,
-                                double (&Fn)[DIM][DIM + 2])
+HB2D_HD void diff_node_flux_from_derivatives(const DiffConsts& K, const double (&vel)[3], const double (&der)[DIM + 1][DIM],
+                                             double (&Fn)[DIM][DIM + 2])
 {
     using TT = DiffTerms<DIM>;
-    double vel[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-    for (int a = 0; a < DIM; a++) vel[a] = P[a][x];
     double D[TT::ND];
     diff_diffusivities<DIM>(vel, K, D);
-    double der[DIM + 1][DIM];
-#pragma unroll
-    for (int v = 0; v < DIM + 1; v++) {
-#pragma unroll
-        for (int d = 0; d < DIM; d++) {
-            /* dT/dx_d enters the energy flux of direction d only; every velocity derivative is used by some direction */
-            der[v][d] = diff_first_derivative(P[v] + x, G.cs[d], G.dx_inv[d]);
-        }
-    }
 #pragma unroll
     for (int f = 0; f < DIM; f++) {
 #pragma unroll
@@ -227,6 +216,48 @@ HB2D_HD void diff_node_flux_all(const DiffGeom& G, const DiffConsts& K, const do
             Fn[f][e] = acc;
         }
     }
+}
+
+template <int DIM>
+HB2D_HD void diff_node_flux_all(const DiffGeom& G, const DiffConsts& K, const double* const* P, long long x,
+                                double (&Fn)[DIM][DIM + 2])
+{
+    double vel[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int a = 0; a < DIM; a++) vel[a] = P[a][x];
+    double der[DIM + 1][DIM];
+#pragma unroll
+    for (int v = 0; v < DIM + 1; v++) {
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            /* dT/dx_d enters the energy flux of direction d only; every velocity derivative is used by some direction */
+            der[v][d] = diff_first_derivative(P[v] + x, G.cs[d], G.dx_inv[d]);
+        }
+    }
+    diff_node_flux_from_derivatives<DIM>(K, vel, der, Fn);
+}
+
+/* the same derivative from six values (tiled kernels: register ring along the marching direction) */
+HB2D_HD double diff_first_derivative6(double m3, double m2, double m1, double p1, double p2, double p3, double dx_inv)
+{
+    const double a_n = 3.0 / 4.0;
+    const double b_n = -(3.0 / 20.0);
+    const double c_n = 1.0 / 60.0;
+    return (a_n * (p1 - m1) + b_n * (p2 - m2) + c_n * (p3 - m3)) * dx_inv;
+}
+
+/* face flux from six node values LLL, LL, L, R, RR, RRR (diff_reconstruct with p[-3..2]) */
+HB2D_HD double diff_reconstruct6(double lll, double ll, double l, double r, double rr, double rrr, double dt)
+{
+    const double a_n = 3.0 / 4.0;
+    const double b_n = -(3.0 / 20.0);
+    const double c_n = 1.0 / 60.0;
+    const double a_r = a_n + b_n + c_n;
+    const double b_r = b_n + c_n;
+    const double c_r = c_n;
+    double F = 0.0;
+    F += dt * (a_r * (l + r) + b_r * (ll + rr) + c_r * (lll + rrr));
+    return F;
 }
 
 /* ---- one thread of each kernel (the kernels of hb2_diffusive.cu are grid-stride loops over these; the host emulation

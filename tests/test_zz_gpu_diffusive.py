@@ -24,7 +24,7 @@ def _state(dim, N, seed=5):
     return orc.PatchDesc(dim=dim, n=N, gamma=gam, dx=dx), U
 
 
-@pytest.mark.parametrize("dim,N", [(2, (24, 17)), (3, (13, 10, 12)), (2, (1, 1)), (3, (7, 1, 3)), (3, (64, 48, 40)), (2, (300, 200))])
+@pytest.mark.parametrize("dim,N", [(2, (24, 17)), (3, (13, 10, 12)), (2, (1, 1)), (3, (7, 1, 3)), (3, (64, 48, 40)), (2, (300, 200)), (3, (70, 23, 19)), (3, (27, 3, 2))])
 def test_diffusive_flux_device_and_host_entry_points(dim, N, product_lib):
     import torch
 
@@ -204,7 +204,7 @@ def test_navier_stokes_level_steps_match_the_oracle_composition(dim, N, math, pr
     lvl.close()
 
 
-@pytest.mark.parametrize("dim,N,g", [(2, (24, 17), 6), (3, (13, 10, 12), 6), (3, (40, 33, 20), 4)])
+@pytest.mark.parametrize("dim,N,g", [(2, (24, 17), 6), (3, (13, 10, 12), 6), (3, (40, 33, 20), 4), (3, (70, 23, 19), 6), (3, (33, 9, 4), 6)])
 def test_flux_free_divergence_update(dim, N, g, product_lib):
     """hb2_diffusive_divergence_accumulate_dev == hb2_compute_diffusive_flux_dev + hb2_diffusive_accumulate_dev bit for bit,
     and both equal U + beta (-div F_d) formed from the oracle's side fluxes to round-off."""
