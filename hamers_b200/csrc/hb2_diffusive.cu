@@ -49,7 +49,8 @@ struct hb2_diff_plan_s {
     double* stF[15];
     long long nside[3];
     long long launches;
-    int tiled;                    /* 3-D: marching tiled kernels (default); HB2_DIFF_TILED=0 selects the grid-stride forms */
+    int tiled;                    /* 3-D: marching tiled kernels, HB2_DIFF_TILED=1 (measured slower than the grid-stride forms) */
+    int bricks;                   /* 3-D: 32 x 4 x 2 brick index map of the grid-stride kernels (HB2_DIFF_BRICKS, default 1) */
 };
 
 namespace {
@@ -71,6 +72,48 @@ __global__ void __launch_bounds__(256) k_diff_node_all(const __grid_constant__ D
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride)
         diff_node_all_thread<DIM>(G, K, A, t);
+}
+
+/* (defined before its users below) */
+/* The same threads with a block-tiled index map (3-D): a block of 256 threads owns a 32 x 4 x 2 brick of the index space, so
+ * that the y- and z-neighbours of the sixth-order stencils are loaded by the same block and hit in L1 (a linear map gives a
+ * block one x-row: every y / z neighbour comes from L2).  ext: extents of the index space the thread function decodes. */
+constexpr int BX = 32, BY = 4, BZ = 2;
+__device__ __forceinline__ bool brick_index(long long brick, int e0, int e1, int e2, long long& t)
+{
+    const int b0 = (e0 + BX - 1) / BX, b1 = (e1 + BY - 1) / BY;
+    const int bz = (int)(brick / ((long long)b0 * b1));
+    const int r = (int)(brick % ((long long)b0 * b1));
+    const int i = (r % b0) * BX + (threadIdx.x & 31);
+    const int j = (r / b0) * BY + ((threadIdx.x >> 5) & 3);
+    const int k = bz * BZ + (threadIdx.x >> 7);
+    t = i + (long long)e0 * (j + (long long)e1 * k);
+    return i < e0 && j < e1 && k < e2;
+}
+__host__ __device__ inline long long brick_count(int e0, int e1, int e2)
+{
+    return (long long)((e0 + BX - 1) / BX) * ((e1 + BY - 1) / BY) * ((e2 + BZ - 1) / BZ);
+}
+
+__global__ void __launch_bounds__(256) k_diff_node_all_bricks(const __grid_constant__ DiffGeom G, const __grid_constant__ DiffConsts K,
+                                                              const __grid_constant__ DiffAllPtrs A)
+{
+    const int e0 = G.n[0] + 6, e1 = G.n[1] + 6, e2 = G.n[2] + 6;
+    const long long nb = brick_count(e0, e1, e2);
+    for (long long b = blockIdx.x; b < nb; b += gridDim.x) {
+        long long t;
+        if (brick_index(b, e0, e1, e2, t)) diff_node_all_thread<3>(G, K, A, t);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_diff_divergence_accumulate_bricks(const __grid_constant__ NsDivArgs A)
+{
+    const int e0 = A.G6.n[0], e1 = A.G6.n[1], e2 = A.G6.n[2];
+    const long long nb = brick_count(e0, e1, e2);
+    for (long long b = blockIdx.x; b < nb; b += gridDim.x) {
+        long long t;
+        if (brick_index(b, e0, e1, e2, t)) diff_divergence_accumulate_thread<3>(A, t);
+    }
 }
 
 template <int DIM, int FDIR>
@@ -402,7 +445,12 @@ int node_stage(hb2_diff_plan_t p, const double* const* Q)
         }
     }
     k_diff_primitives<DIM><<<grid_for(p->G.ncell_g, p->sm_count), 256, 0, p->stream>>>(p->G, p->K, A);
-    k_diff_node_all<DIM><<<grid_for(diff_node_all_count<DIM>(p->G), p->sm_count), 256, 0, p->stream>>>(p->G, p->K, N);
+    if (DIM == 3 && p->bricks) {
+        const long long nb = brick_count(p->G.n[0] + 6, p->G.n[1] + 6, p->G.n[2] + 6);
+        k_diff_node_all_bricks<<<(unsigned)(nb < p->sm_count * 8LL ? nb : p->sm_count * 8LL), 256, 0, p->stream>>>(p->G, p->K, N);
+    } else {
+        k_diff_node_all<DIM><<<grid_for(diff_node_all_count<DIM>(p->G), p->sm_count), 256, 0, p->stream>>>(p->G, p->K, N);
+    }
     p->launches += 2;
     HB2D_CUDA(cudaGetLastError());
     return 0;
@@ -446,6 +494,9 @@ int run_divergence(hb2_diff_plan_t p, const double* const* Q, double dt, int num
     if (DIM == 3 && p->tiled) {
         dim3 grid((p->G.n[0] + TX - 1) / TX, (p->G.n[1] + TY - 1) / TY);
         k_diff_div_tiled<<<grid, 256, 0, p->stream>>>(D);
+    } else if (DIM == 3 && p->bricks) {
+        const long long nb = brick_count(p->G.n[0], p->G.n[1], p->G.n[2]);
+        k_diff_divergence_accumulate_bricks<<<(unsigned)(nb < p->sm_count * 8LL ? nb : p->sm_count * 8LL), 256, 0, p->stream>>>(D);
     } else {
         k_diff_divergence_accumulate<DIM><<<grid_for(total, p->sm_count), 256, 0, p->stream>>>(D);
     }
@@ -493,7 +544,9 @@ int hb2_diffusive_plan_create(const hb2_diffusive_desc* d, hb2_diff_plan_t* out)
     p->stream = nullptr;
     {
         const char* v = getenv("HB2_DIFF_TILED");
-        p->tiled = (v && *v) ? atoi(v) : 1;
+        p->tiled = (v && *v) ? atoi(v) : 0;
+        v = getenv("HB2_DIFF_BRICKS");
+        p->bricks = (v && *v) ? atoi(v) : 1;
     }
     for (int a = 0; a < 3; a++) {
         long long s = 1;

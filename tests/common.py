@@ -68,10 +68,57 @@ def rel_err_field(a, b):
     return np.abs(a - b) / (np.abs(b) + scale)
 
 
-def assert_fast_parity(a, b, what="", outlier_fraction=OUTLIER_FRACTION):
+def pure_rel_err(a, b, floor=1.0e-3):
+    """max and 99.9th percentile of the PURE pointwise relative error |a-b|/|b| over the entries whose magnitude is at
+    least `floor` of their component's maximum (where a flux crosses zero a pointwise ratio measures nothing)."""
+    a, b = np.asarray(a), np.asarray(b)
+    axes = tuple(range(1, b.ndim))
+    scale = np.abs(b).max(axis=axes, keepdims=True) if b.ndim > 1 else np.abs(b).max()
+    m = np.abs(b) >= floor * np.where(scale == 0.0, 1.0, scale)
+    if not m.any():
+        return 0.0, 0.0
+    r = np.abs(a - b)[m] / np.abs(b)[m]
+    return float(r.max()), float(np.quantile(r, 0.999))
+
+
+class OracleSpread:
+    """Conditioning of the oracle at every output entry: how far the reference's own formulas move when every input value
+    is perturbed by at most one ulp.  fn(U) -> list of output arrays (U: the level interior; the periodic ghost fill is
+    part of fn so that the perturbed state stays periodic).  An entry of the fast build that misses the 1e-12 tolerance is
+    EXPLAINED when the oracle itself moves by a comparable amount there: that covers both classes of legitimate outliers --
+    (i) a data-dependent branch that sits within an ulp of its threshold (sensor s > 0.65, s* > 0, a bounds flag, the
+    WCNS6-LD R_tau switch: the perturbed oracle flips it too, the entry jumps by O(1)) and (ii) ill-conditioned faces
+    (HLLC-HLL blend weights from nearly coinciding one-sided interpolants, nonlinear weights on stencils whose smoothness
+    indicators are at the epsilon = 1e-15 level).  Anything else is a wrong formula and fails."""
+
+    def __init__(self, fn, U, trials=8, seed=12345):
+        rng = np.random.default_rng(seed)
+        self.base = [np.asarray(x).copy() for x in fn(U)]
+        self.spread = [np.zeros_like(x) for x in self.base]
+        eps = np.finfo(np.float64).eps
+        for _ in range(trials):
+            Up = U * (1.0 + eps * rng.integers(-1, 2, U.shape))
+            for k, x in enumerate(fn(Up)):
+                self.spread[k] = np.maximum(self.spread[k], np.abs(np.asarray(x) - self.base[k]))
+
+
+def assert_fast_parity(a, b, what="", outlier_fraction=OUTLIER_FRACTION, spread=None, factor=16.0):
+    """Fast-build criterion.  Entries within RTOL (relative, regularised by the component's scale) pass.  With `spread`
+    (an array from OracleSpread, same shape as b) every entry beyond RTOL must be EXPLAINED by the oracle's own
+    conditioning (error <= factor * the oracle's movement under 1-ulp input perturbations); without it the outliers are
+    only counted (at most `outlier_fraction` of the entries) -- in both cases none may exceed OUTLIER_RTOL.
+    Returns (max regularised error, number of entries beyond RTOL, number of those that are unexplained)."""
     r = rel_err_field(a, b)
     assert np.isfinite(r).all(), f"{what}: non-finite entries"
-    n_out = int((r > RTOL).sum())
+    out = r > RTOL
+    n_out = int(out.sum())
     assert n_out <= max(8, int(outlier_fraction * r.size)), f"{what}: {n_out} of {r.size} entries exceed {RTOL}, max {r.max():.3e}"
     assert r.max() <= OUTLIER_RTOL, f"{what}: max relative error {r.max():.3e}"
-    return float(r.max()), n_out
+    n_bad = 0
+    if spread is not None and n_out:
+        err = np.abs(np.asarray(a) - np.asarray(b))
+        bad = out & (err > factor * spread)
+        n_bad = int(bad.sum())
+        assert n_bad == 0, (f"{what}: {n_bad} of the {n_out} entries beyond {RTOL} are NOT explained by the oracle's conditioning "
+                            f"(worst: error {err[bad].max():.3e} where the oracle moves {spread[bad][np.argmax(err[bad])]:.3e})")
+    return float(r.max()), n_out, n_bad

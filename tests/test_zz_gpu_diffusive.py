@@ -39,7 +39,7 @@ def test_diffusive_flux_device_and_host_entry_points(dim, N, product_lib):
     torch.cuda.synchronize()
     for a in range(dim):
         assert np.array_equal(Fd[a].cpu().numpy(), Fo[a]), f"dir {a}"
-    assert plan.launch_count == 2 + dim          # primitives, one-pass node fluxes, one face kernel per direction
+    assert plan.launch_count in (1 + dim, 2 + dim)     # (primitives,) one-pass node fluxes, one face kernel per direction
     Fh = plan.compute_diffusive_flux_host(Q, dt)
     for a in range(dim):
         assert np.array_equal(Fh[a], Fo[a]), f"host entry point, dir {a}"
