@@ -122,3 +122,15 @@ def assert_fast_parity(a, b, what="", outlier_fraction=OUTLIER_FRACTION, spread=
         assert n_bad == 0, (f"{what}: {n_bad} of the {n_out} entries beyond {RTOL} are NOT explained by the oracle's conditioning "
                             f"(worst: error {err[bad].max():.3e} where the oracle moves {spread[bad][np.argmax(err[bad])]:.3e})")
     return float(r.max()), n_out, n_bad
+
+
+def flux_source_spread(oracle_lib, desc, U, dt, S0=None, trials=8):
+    """OracleSpread of computeConvectiveFluxAndSourceOnPatch + one forward-Euler fused stage on the periodic level U:
+    outputs [F_0, .., F_{dim-1}, S, U_new interior]."""
+    def fn(Ui):
+        Q = pb.pad_periodic(Ui)
+        F, S = oracle_lib.compute_flux_and_source(desc, Q, dt, source=None if S0 is None else S0.copy())
+        F1, S1 = (F, S) if S0 is None else oracle_lib.compute_flux_and_source(desc, Q, dt)
+        Un = oracle_lib.advance_stage(desc, [1.0], [1.0], [Q], [F1], [S1])
+        return list(F) + [S, interior(desc, Un)]
+    return OracleSpread(fn, U, trials=trials)
