@@ -1,0 +1,401 @@
+/*
+ * hb2_level.cu -- device-resident patch level: the C side of "seam 2" (SURVEY.md 8b).
+ *
+ * RungeKuttaLevelIntegrator::advanceLevel (src/algs/integrator/RungeKuttaLevelIntegrator.cpp:1457-1929) walks the patches of
+ * one level per RK stage: xfer::RefineSchedule::fillData (:1568, :1701), then RungeKuttaPatchStrategy::
+ * computeFluxesAndSourcesOnPatch + advanceSingleStepOnPatch per patch (:1724-1739).  With the patch data resident in HBM
+ * the same loop runs here for ALL patches a rank owns on one level (boxes of any sizes, in level index space): the
+ * conservative variables of every patch are registered once (three state buffers per patch: U^n and the two intermediate
+ * states of SSP-RK3), the same-level ghost fill between the rank's patches -- periodic images included -- is ONE kernel
+ * launch over a descriptor table built at registration, and every patch advances with the fused stage of its shape's plan
+ * (hb2_fused_stage_dev).  Host memory is touched only by hb2_level_upload_patch / hb2_level_download_patch.
+ * The entry points are declared in include/hamers_b200.h; the C++ class RungeKuttaPatchStrategyB200
+ * (hamers_b200/host) drives them with the reference's method names.
+ */
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "hamers_b200.h"
+
+namespace hb2 {
+int set_error(int code, const std::string& msg);
+}
+using hb2::set_error;
+
+#define HB2L_CUDA(call)                                                                           \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return set_error(-100 - (int)e_, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+namespace {
+
+struct CopyDesc {
+    int dst, src;              /* patch indices */
+    int ext[3];
+    long long dst_off, src_off; /* ghost-box index of the region's first cell in the destination / source patch */
+    long long dst_cs[2], src_cs[2];
+};
+
+struct LevelPatch {
+    int lo[3], n[3];
+    int shape;
+    long long ncell_g;
+    double* S[3];              /* three state buffers, each ncomp * ncell_g doubles */
+};
+
+/* grid: (x, descriptor); one descriptor = one box-to-box copy of every component */
+__global__ void __launch_bounds__(256) k_level_fill(const CopyDesc* __restrict__ D, double* const* __restrict__ ptrs, int ncomp)
+{
+    const CopyDesc d = D[blockIdx.y];
+    const long long nb = (long long)d.ext[0] * d.ext[1] * d.ext[2];
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < nb * ncomp; id += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(id / nb);
+        const long long r = id % nb;
+        const int i = (int)(r % d.ext[0]), j = (int)((r / d.ext[0]) % d.ext[1]), k = (int)(r / ((long long)d.ext[0] * d.ext[1]));
+        ptrs[d.dst * ncomp + c][d.dst_off + i + d.dst_cs[0] * j + d.dst_cs[1] * k] =
+            ptrs[d.src * ncomp + c][d.src_off + i + d.src_cs[0] * j + d.src_cs[1] * k];
+    }
+}
+
+}  // namespace
+
+struct hb2_level_s {
+    hb2_patch_desc model;
+    int dim, ncomp, neq, g, device;
+    int level_n[3], periodic_mask;
+    std::vector<LevelPatch> patches;
+    std::vector<hb2_plan_t> plans;              /* one per distinct patch shape */
+    std::vector<std::vector<int>> shapes;
+    int where[3];                               /* buffer index of U^(0), U^(1), U^(2) of the running step; where[0] = current */
+    CopyDesc* d_desc;
+    int ndesc;
+    double** d_ptrs[3];                         /* device pointer tables [patch * ncomp + c], one per buffer */
+    cudaStream_t stream;
+    long long launches;
+    double* d_sr;                               /* 4 doubles per patch: spectral radii */
+};
+
+namespace {
+
+int build_fill_table(hb2_level_t L)
+{
+    const int dim = L->dim, g = L->g;
+    std::vector<CopyDesc> D;
+    const int np = (int)L->patches.size();
+    for (int p = 0; p < np; p++) {
+        const LevelPatch& P = L->patches[p];
+        int shift[3];
+        for (shift[2] = (dim == 3 ? -1 : 0); shift[2] <= (dim == 3 ? 1 : 0); shift[2]++)
+            for (shift[1] = -1; shift[1] <= 1; shift[1]++)
+                for (shift[0] = -1; shift[0] <= 1; shift[0]++) {
+                    bool ok = true;
+                    for (int a = 0; a < dim; a++)
+                        if (shift[a] != 0 && !((L->periodic_mask >> a) & 1)) ok = false;
+                    if (!ok) continue;
+                    for (int q = 0; q < np; q++) {
+                        const LevelPatch& Q = L->patches[q];
+                        if (q == p && !shift[0] && !shift[1] && !shift[2]) continue;
+                        CopyDesc d;
+                        memset(&d, 0, sizeof d);
+                        bool empty = false;
+                        int rlo[3] = {0, 0, 0};
+                        for (int a = 0; a < 3; a++) {
+                            if (a >= dim) {
+                                d.ext[a] = 1;
+                                continue;
+                            }
+                            const int qlo = Q.lo[a] + shift[a] * L->level_n[a], qhi = qlo + Q.n[a];
+                            const int glo = P.lo[a] - g, ghi = P.lo[a] + P.n[a] + g;
+                            const int lo = qlo > glo ? qlo : glo, hi = qhi < ghi ? qhi : ghi;
+                            if (hi <= lo) empty = true;
+                            rlo[a] = lo;
+                            d.ext[a] = hi - lo;
+                        }
+                        if (empty) continue;
+                        d.dst = p;
+                        d.src = q;
+                        const long long pcs1 = P.n[0] + 2 * g, pcs2 = pcs1 * (P.n[1] + 2 * g);
+                        const long long qcs1 = Q.n[0] + 2 * g, qcs2 = qcs1 * (Q.n[1] + 2 * g);
+                        d.dst_cs[0] = pcs1;
+                        d.dst_cs[1] = dim == 3 ? pcs2 : 0;
+                        d.src_cs[0] = qcs1;
+                        d.src_cs[1] = dim == 3 ? qcs2 : 0;
+                        d.dst_off = (rlo[0] - P.lo[0] + g) + pcs1 * (rlo[1] - P.lo[1] + g) + (dim == 3 ? pcs2 * (rlo[2] - P.lo[2] + g) : 0);
+                        const int s0 = rlo[0] - shift[0] * L->level_n[0] - Q.lo[0], s1 = rlo[1] - shift[1] * L->level_n[1] - Q.lo[1];
+                        const int s2 = dim == 3 ? rlo[2] - shift[2] * L->level_n[2] - Q.lo[2] : 0;
+                        d.src_off = (s0 + g) + qcs1 * (s1 + g) + (dim == 3 ? qcs2 * (s2 + g) : 0);
+                        D.push_back(d);
+                    }
+                }
+    }
+    L->ndesc = (int)D.size();
+    if (L->ndesc) {
+        HB2L_CUDA(cudaMalloc(&L->d_desc, sizeof(CopyDesc) * D.size()));
+        HB2L_CUDA(cudaMemcpy(L->d_desc, D.data(), sizeof(CopyDesc) * D.size(), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hb2_level_create(const hb2_patch_desc* model, int32_t npatch, const int32_t* lo, const int32_t* hi, const int32_t level_n[3],
+                     int32_t periodic_mask, hb2_level_t* out)
+{
+    if (!model || !lo || !hi || !level_n || !out) return set_error(-1, "hb2_level_create: null argument");
+    if (npatch < 1) return set_error(-40, "hb2_level_create: a level needs at least one patch");
+    int32_t neq = 0, ncomp = 0;
+    hb2_patch_desc probe = *model;
+    for (int a = 0; a < 3; a++) probe.n[a] = 1;
+    if (hb2_num_eqn(&probe, &neq) || hb2_num_comp(&probe, &ncomp)) return -1;
+    hb2_level_t L = new hb2_level_s();
+    L->model = *model;
+    L->dim = model->dim;
+    L->neq = neq;
+    L->ncomp = ncomp;
+    L->g = model->num_ghosts > 0 ? model->num_ghosts : HB2_GHOSTS;
+    L->periodic_mask = periodic_mask;
+    L->d_desc = nullptr;
+    L->d_sr = nullptr;
+    L->launches = 0;
+    for (int b = 0; b < 3; b++) {
+        L->where[b] = b;
+        L->d_ptrs[b] = nullptr;
+    }
+    for (int a = 0; a < 3; a++) L->level_n[a] = a < L->dim ? level_n[a] : 1;
+    for (int a = 0; a < L->dim; a++)
+        if (((periodic_mask >> a) & 1) && L->level_n[a] < L->g) {
+            delete L;
+            return set_error(-41, "hb2_level_create: a periodic direction must be at least one ghost width long");
+        }
+    L->device = model->device;
+    if (L->device < 0) HB2L_CUDA(cudaGetDevice(&L->device));
+    HB2L_CUDA(cudaSetDevice(L->device));
+    HB2L_CUDA(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
+    std::map<std::vector<int>, int> shape_of;
+    for (int p = 0; p < npatch; p++) {
+        LevelPatch P;
+        memset(&P, 0, sizeof P);
+        std::vector<int> shp(3, 1);
+        P.ncell_g = 1;
+        for (int a = 0; a < 3; a++) {
+            P.lo[a] = a < L->dim ? lo[3 * p + a] : 0;
+            P.n[a] = a < L->dim ? hi[3 * p + a] - lo[3 * p + a] : 1;
+            if (P.n[a] < 1) {
+                hb2_level_destroy(L);
+                return set_error(-3, "hb2_level_create: empty patch box");
+            }
+            shp[a] = P.n[a];
+            P.ncell_g *= (a < L->dim) ? P.n[a] + 2 * L->g : 1;
+        }
+        auto it = shape_of.find(shp);
+        if (it == shape_of.end()) {
+            hb2_patch_desc d = *model;
+            for (int a = 0; a < 3; a++) d.n[a] = shp[a];
+            d.device = L->device;
+            hb2_plan_t plan = nullptr;
+            int rc = hb2_plan_create(&d, &plan);
+            if (rc) {
+                hb2_level_destroy(L);
+                return rc;
+            }
+            hb2_plan_set_stream(plan, (void*)L->stream);
+            L->plans.push_back(plan);
+            L->shapes.push_back(shp);
+            it = shape_of.insert(std::make_pair(shp, (int)L->plans.size() - 1)).first;
+        }
+        P.shape = it->second;
+        for (int b = 0; b < 3; b++) {
+            HB2L_CUDA(cudaMalloc(&P.S[b], sizeof(double) * (size_t)P.ncell_g * L->ncomp));
+            HB2L_CUDA(cudaMemsetAsync(P.S[b], 0, sizeof(double) * (size_t)P.ncell_g * L->ncomp, L->stream));
+        }
+        L->patches.push_back(P);
+    }
+    for (int b = 0; b < 3; b++) {
+        std::vector<double*> tab((size_t)npatch * L->ncomp);
+        for (int p = 0; p < npatch; p++)
+            for (int c = 0; c < L->ncomp; c++) tab[(size_t)p * L->ncomp + c] = L->patches[p].S[b] + (size_t)c * L->patches[p].ncell_g;
+        HB2L_CUDA(cudaMalloc(&L->d_ptrs[b], sizeof(double*) * tab.size()));
+        HB2L_CUDA(cudaMemcpy(L->d_ptrs[b], tab.data(), sizeof(double*) * tab.size(), cudaMemcpyHostToDevice));
+    }
+    HB2L_CUDA(cudaMalloc(&L->d_sr, sizeof(double) * 4 * (size_t)npatch));
+    int rc = build_fill_table(L);
+    if (rc) {
+        hb2_level_destroy(L);
+        return rc;
+    }
+    *out = L;
+    return 0;
+}
+
+int hb2_level_destroy(hb2_level_t L)
+{
+    if (!L) return 0;
+    cudaSetDevice(L->device);
+    if (L->stream) cudaStreamSynchronize(L->stream);
+    for (auto& P : L->patches)
+        for (int b = 0; b < 3; b++) cudaFree(P.S[b]);
+    for (auto plan : L->plans) hb2_plan_destroy(plan);
+    for (int b = 0; b < 3; b++) cudaFree(L->d_ptrs[b]);
+    cudaFree(L->d_desc);
+    cudaFree(L->d_sr);
+    if (L->stream) cudaStreamDestroy(L->stream);
+    delete L;
+    return 0;
+}
+
+int hb2_level_num_patches(hb2_level_t L) { return L ? (int)L->patches.size() : -1; }
+
+int64_t hb2_level_launch_count(hb2_level_t L)
+{
+    if (!L) return -1;
+    long long n = L->launches;
+    for (auto plan : L->plans) n += hb2_plan_launch_count(plan);
+    return n;
+}
+
+int hb2_level_synchronize(hb2_level_t L)
+{
+    if (!L) return set_error(-1, "null level");
+    HB2L_CUDA(cudaSetDevice(L->device));
+    HB2L_CUDA(cudaStreamSynchronize(L->stream));
+    return 0;
+}
+
+/* host -> device: the INTERIOR of the patch's current state from ghost-box host arrays (SAMRAI CellData pointers) */
+int hb2_level_upload_patch(hb2_level_t L, int32_t patch, const double* const* U_host)
+{
+    if (!L || !U_host) return set_error(-1, "hb2_level_upload_patch: null argument");
+    if (patch < 0 || patch >= (int)L->patches.size()) return set_error(-42, "patch index out of range");
+    HB2L_CUDA(cudaSetDevice(L->device));
+    const LevelPatch& P = L->patches[patch];
+    /* the whole ghost box travels (one contiguous copy per component); the ghosts are refilled on the device anyway */
+    for (int c = 0; c < L->ncomp; c++)
+        HB2L_CUDA(cudaMemcpyAsync(P.S[L->where[0]] + (size_t)c * P.ncell_g, U_host[c], sizeof(double) * (size_t)P.ncell_g,
+                                  cudaMemcpyHostToDevice, L->stream));
+    return 0;
+}
+
+int hb2_level_download_patch(hb2_level_t L, int32_t patch, double* const* U_host)
+{
+    if (!L || !U_host) return set_error(-1, "hb2_level_download_patch: null argument");
+    if (patch < 0 || patch >= (int)L->patches.size()) return set_error(-42, "patch index out of range");
+    HB2L_CUDA(cudaSetDevice(L->device));
+    const LevelPatch& P = L->patches[patch];
+    for (int c = 0; c < L->ncomp; c++)
+        HB2L_CUDA(cudaMemcpyAsync(U_host[c], P.S[L->where[0]] + (size_t)c * P.ncell_g, sizeof(double) * (size_t)P.ncell_g,
+                                  cudaMemcpyDeviceToHost, L->stream));
+    HB2L_CUDA(cudaStreamSynchronize(L->stream));
+    return 0;
+}
+
+int hb2_level_patch_state_dev(hb2_level_t L, int32_t patch, int32_t state, double** U_dev)
+{
+    if (!L || !U_dev) return set_error(-1, "hb2_level_patch_state_dev: null argument");
+    if (patch < 0 || patch >= (int)L->patches.size() || state < 0 || state > 2) return set_error(-42, "patch / state index out of range");
+    const LevelPatch& P = L->patches[patch];
+    for (int c = 0; c < L->ncomp; c++) U_dev[c] = P.S[L->where[state]] + (size_t)c * P.ncell_g;
+    return 0;
+}
+
+/* same-level ghost fill of intermediate state `state` (0 = current) of every patch, periodic images included */
+int hb2_level_fill_ghosts(hb2_level_t L, int32_t state)
+{
+    if (!L) return set_error(-1, "null level");
+    if (state < 0 || state > 2) return set_error(-42, "state index out of range");
+    if (!L->ndesc) return 0;
+    HB2L_CUDA(cudaSetDevice(L->device));
+    dim3 grid(8, (unsigned)L->ndesc);
+    k_level_fill<<<grid, 256, 0, L->stream>>>(L->d_desc, L->d_ptrs[L->where[state]], L->ncomp);
+    L->launches++;
+    HB2L_CUDA(cudaGetLastError());
+    return 0;
+}
+
+/* One RK stage of the whole level: computeFluxesAndSourcesOnPatch + advanceSingleStepOnPatch of every patch (fused), the
+ * new state U^(ncoef) written to the buffer that no coefficient of this stage reads.  Ghosts of U^(ncoef - 1) must be
+ * filled (hb2_level_fill_ghosts(L, ncoef - 1)). */
+int hb2_level_advance_stage(hb2_level_t L, int32_t ncoef, const double* alpha, const double* beta, double dt, int32_t last_stage)
+{
+    if (!L || !alpha || !beta) return set_error(-1, "hb2_level_advance_stage: null argument");
+    if (ncoef < 1 || ncoef > 3) return set_error(-15, "hb2_level_advance_stage: ncoef must be 1..3 (SSP-RK3)");
+    HB2L_CUDA(cudaSetDevice(L->device));
+    /* output buffer: U^(ncoef) takes buffer where[ncoef] for ncoef < 3; the last stage of a three-stage scheme overwrites the
+     * buffer of the first state whose alpha is zero and that is not the flux state (SSP-RK3: U^(1)) */
+    int out = -1;
+    if (ncoef < 3) {
+        out = L->where[ncoef];
+    } else {
+        for (int m = 0; m < ncoef - 1; m++)
+            if (alpha[m] == 0.0) out = L->where[m];
+        if (out < 0) return set_error(-43, "hb2_level_advance_stage: a third stage needs one alpha == 0 among the older states (three buffers)");
+    }
+    for (size_t pi = 0; pi < L->patches.size(); pi++) {
+        const LevelPatch& P = L->patches[pi];
+        const double* Uint[3 * HB2_MAX_COMP];
+        double* Uout[HB2_MAX_COMP];
+        for (int m = 0; m < ncoef; m++)
+            for (int c = 0; c < L->ncomp; c++) Uint[m * L->ncomp + c] = P.S[L->where[m]] + (size_t)c * P.ncell_g;
+        for (int c = 0; c < L->ncomp; c++) Uout[c] = P.S[out] + (size_t)c * P.ncell_g;
+        int rc = hb2_fused_stage_dev(L->plans[P.shape], ncoef, alpha, beta, Uint, dt, Uout);
+        if (rc) return rc;
+    }
+    if (last_stage) {
+        /* the new state becomes the current one; the other two buffers are free */
+        int rest[2], k = 0;
+        for (int b = 0; b < 3; b++)
+            if (b != out) rest[k++] = b;
+        L->where[0] = out;
+        L->where[1] = rest[0];
+        L->where[2] = rest[1];
+    }
+    return 0;
+}
+
+/* RungeKuttaLevelIntegrator::advanceLevel for the whole level: per stage the ghost fill, then every patch (alpha / beta:
+ * row-major [nstages][nstages]) */
+int hb2_level_advance(hb2_level_t L, int32_t nstages, const double* alpha, const double* beta, double dt)
+{
+    if (!L || !alpha || !beta) return set_error(-1, "hb2_level_advance: null argument");
+    if (nstages < 1 || nstages > 3) return set_error(-20, "hb2_level_advance supports 1..3 stages");
+    for (int sn = 0; sn < nstages; sn++) {
+        int rc = hb2_level_fill_ghosts(L, sn);
+        if (rc) return rc;
+        rc = hb2_level_advance_stage(L, sn + 1, alpha + sn * nstages, beta + sn * nstages, dt, sn == nstages - 1);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+/* Euler::computeSpectralRadiusesAndStableDtOnPatch over the rank's patches: out_host[0..2] = max spectral radius per
+ * direction, out_host[3] = max of their sum (stable dt = CFL / out_host[3]); MAX-all-reduce across ranks is the caller's. */
+int hb2_level_max_wave_speed(hb2_level_t L, double out_host[4])
+{
+    if (!L || !out_host) return set_error(-1, "hb2_level_max_wave_speed: null argument");
+    HB2L_CUDA(cudaSetDevice(L->device));
+    const size_t np = L->patches.size();
+    for (size_t pi = 0; pi < np; pi++) {
+        const LevelPatch& P = L->patches[pi];
+        const double* Q[HB2_MAX_COMP];
+        for (int c = 0; c < L->ncomp; c++) Q[c] = P.S[L->where[0]] + (size_t)c * P.ncell_g;
+        int rc = hb2_max_wave_speed_dev(L->plans[P.shape], Q, L->d_sr + 4 * pi);
+        if (rc) return rc;
+    }
+    std::vector<double> h(4 * np);
+    HB2L_CUDA(cudaMemcpyAsync(h.data(), L->d_sr, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, L->stream));
+    HB2L_CUDA(cudaStreamSynchronize(L->stream));
+    for (int k = 0; k < 4; k++) {
+        out_host[k] = 0.0;
+        for (size_t pi = 0; pi < np; pi++) out_host[k] = h[4 * pi + k] > out_host[k] ? h[4 * pi + k] : out_host[k];
+    }
+    return 0;
+}
+
+}  // extern "C"

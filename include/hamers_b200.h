@@ -348,6 +348,37 @@ int hb2_amr_coarsen_fluxsum_dev(const hb2_amr_pair* pair, const double* const* f
  * boundaries afterwards). */
 int hb2_fill_ghosts_extrapolate_dev(hb2_plan_t plan, double* const* U, int32_t dir, int32_t side);
 
+/* ---- device-resident patch level: the loop of RungeKuttaLevelIntegrator::advanceLevel over ALL patches a rank owns -----
+ * (RungeKuttaLevelIntegrator.cpp:1672-1745; RungeKuttaPatchStrategy.hpp:149-190).  The conservative variables of every
+ * patch are registered once and stay in HBM (three state buffers per patch); boxes may have any sizes; the same-level
+ * ghost fill between the rank's patches (periodic images included) is one kernel launch; every patch advances with the
+ * fused stage.  `model`: flow model, species, dx, math, scheme, num_ghosts, device (n is ignored).  lo / hi: npatch x 3
+ * box corners in LEVEL index space, hi exclusive.  level_n: cells of the level (periodic wrap).  A level spread over
+ * several ranks exchanges the ghosts that belong to other ranks through hb2_pack_boxes_dev / NCCL on the states returned
+ * by hb2_level_patch_state_dev, like hamers_b200/level.py does for one box per rank. */
+typedef struct hb2_level_s* hb2_level_t;
+int hb2_level_create(const hb2_patch_desc* model, int32_t npatch, const int32_t* lo, const int32_t* hi, const int32_t level_n[3],
+                     int32_t periodic_mask, hb2_level_t* level);
+int hb2_level_destroy(hb2_level_t level);
+int hb2_level_num_patches(hb2_level_t level);
+int64_t hb2_level_launch_count(hb2_level_t level);
+int hb2_level_synchronize(hb2_level_t level);
+/* HOST ghost-box arrays (SAMRAI CellData::getPointer(c)) <-> the patch's current state in HBM */
+int hb2_level_upload_patch(hb2_level_t level, int32_t patch, const double* const* U_host);
+int hb2_level_download_patch(hb2_level_t level, int32_t patch, double* const* U_host);
+/* device pointers (num_comp of them) of intermediate state `state` (0 = current) of a patch */
+int hb2_level_patch_state_dev(hb2_level_t level, int32_t patch, int32_t state, double** U_dev);
+/* xfer::RefineSchedule::fillData, same level: every ghost cell of state `state` covered by a patch of this level (or a
+ * periodic image of one) is copied from it */
+int hb2_level_fill_ghosts(hb2_level_t level, int32_t state);
+/* computeFluxesAndSourcesOnPatch + advanceSingleStepOnPatch of every patch for RK stage ncoef - 1 (coefficient rows of
+ * length ncoef); last_stage != 0: the result becomes the current state */
+int hb2_level_advance_stage(hb2_level_t level, int32_t ncoef, const double* alpha, const double* beta, double dt, int32_t last_stage);
+/* the stage loop of advanceLevel: alpha / beta row-major [nstages][nstages] */
+int hb2_level_advance(hb2_level_t level, int32_t nstages, const double* alpha, const double* beta, double dt);
+/* max over the rank's patches of the spectral radii (hb2_max_wave_speed_dev per patch); out_host: 4 doubles */
+int hb2_level_max_wave_speed(hb2_level_t level, double out_host[4]);
+
 #ifdef __cplusplus
 }
 #endif
