@@ -319,36 +319,46 @@ int hb2_level_fill_ghosts(hb2_level_t L, int32_t state)
     return 0;
 }
 
-/* One RK stage of the whole level: computeFluxesAndSourcesOnPatch + advanceSingleStepOnPatch of every patch (fused), the
- * new state U^(ncoef) written to the buffer that no coefficient of this stage reads.  Ghosts of U^(ncoef - 1) must be
- * filled (hb2_level_fill_ghosts(L, ncoef - 1)). */
-int hb2_level_advance_stage(hb2_level_t L, int32_t ncoef, const double* alpha, const double* beta, double dt, int32_t last_stage)
+namespace {
+/* output buffer of stage ncoef - 1: U^(ncoef) takes buffer where[ncoef] for ncoef < 3; the last stage of a three-stage
+ * scheme overwrites the buffer of the older state whose alpha is zero (SSP-RK3: U^(1)) */
+int stage_output_buffer(hb2_level_t L, int ncoef, const double* alpha)
 {
-    if (!L || !alpha || !beta) return set_error(-1, "hb2_level_advance_stage: null argument");
-    if (ncoef < 1 || ncoef > 3) return set_error(-15, "hb2_level_advance_stage: ncoef must be 1..3 (SSP-RK3)");
-    HB2L_CUDA(cudaSetDevice(L->device));
-    /* output buffer: U^(ncoef) takes buffer where[ncoef] for ncoef < 3; the last stage of a three-stage scheme overwrites the
-     * buffer of the first state whose alpha is zero and that is not the flux state (SSP-RK3: U^(1)) */
+    if (ncoef < 3) return L->where[ncoef];
     int out = -1;
-    if (ncoef < 3) {
-        out = L->where[ncoef];
-    } else {
-        for (int m = 0; m < ncoef - 1; m++)
-            if (alpha[m] == 0.0) out = L->where[m];
-        if (out < 0) return set_error(-43, "hb2_level_advance_stage: a third stage needs one alpha == 0 among the older states (three buffers)");
-    }
-    for (size_t pi = 0; pi < L->patches.size(); pi++) {
-        const LevelPatch& P = L->patches[pi];
-        const double* Uint[3 * HB2_MAX_COMP];
-        double* Uout[HB2_MAX_COMP];
-        for (int m = 0; m < ncoef; m++)
-            for (int c = 0; c < L->ncomp; c++) Uint[m * L->ncomp + c] = P.S[L->where[m]] + (size_t)c * P.ncell_g;
-        for (int c = 0; c < L->ncomp; c++) Uout[c] = P.S[out] + (size_t)c * P.ncell_g;
-        int rc = hb2_fused_stage_dev(L->plans[P.shape], ncoef, alpha, beta, Uint, dt, Uout);
-        if (rc) return rc;
-    }
+    for (int m = 0; m < ncoef - 1; m++)
+        if (alpha[m] == 0.0) out = L->where[m];
+    return out;
+}
+}  // namespace
+
+/* computeFluxesAndSourcesOnPatch + advanceSingleStepOnPatch of ONE patch for RK stage ncoef - 1 (fused; the flux is taken of
+ * U^(ncoef - 1), whose ghosts must be filled: hb2_level_fill_ghosts(L, ncoef - 1)) */
+int hb2_level_advance_stage_patch(hb2_level_t L, int32_t patch, int32_t ncoef, const double* alpha, const double* beta, double dt)
+{
+    if (!L || !alpha || !beta) return set_error(-1, "hb2_level_advance_stage_patch: null argument");
+    if (ncoef < 1 || ncoef > 3) return set_error(-15, "hb2_level_advance_stage_patch: ncoef must be 1..3 (SSP-RK3)");
+    if (patch < 0 || patch >= (int)L->patches.size()) return set_error(-42, "patch index out of range");
+    HB2L_CUDA(cudaSetDevice(L->device));
+    const int out = stage_output_buffer(L, ncoef, alpha);
+    if (out < 0) return set_error(-43, "a third stage needs one alpha == 0 among the older states (three buffers per patch)");
+    const LevelPatch& P = L->patches[patch];
+    const double* Uint[3 * HB2_MAX_COMP];
+    double* Uout[HB2_MAX_COMP];
+    for (int m = 0; m < ncoef; m++)
+        for (int c = 0; c < L->ncomp; c++) Uint[m * L->ncomp + c] = P.S[L->where[m]] + (size_t)c * P.ncell_g;
+    for (int c = 0; c < L->ncomp; c++) Uout[c] = P.S[out] + (size_t)c * P.ncell_g;
+    return hb2_fused_stage_dev(L->plans[P.shape], ncoef, alpha, beta, Uint, dt, Uout);
+}
+
+/* after every patch has advanced through stage ncoef - 1: U^(ncoef) is where stage_output_buffer says; after the last stage it
+ * becomes the current state and the other two buffers are free */
+int hb2_level_end_stage(hb2_level_t L, int32_t ncoef, const double* alpha, int32_t last_stage)
+{
+    if (!L || !alpha) return set_error(-1, "hb2_level_end_stage: null argument");
+    const int out = stage_output_buffer(L, ncoef, alpha);
+    if (out < 0) return set_error(-43, "a third stage needs one alpha == 0 among the older states (three buffers per patch)");
     if (last_stage) {
-        /* the new state becomes the current one; the other two buffers are free */
         int rest[2], k = 0;
         for (int b = 0; b < 3; b++)
             if (b != out) rest[k++] = b;
@@ -357,6 +367,16 @@ int hb2_level_advance_stage(hb2_level_t L, int32_t ncoef, const double* alpha, c
         L->where[2] = rest[1];
     }
     return 0;
+}
+
+int hb2_level_advance_stage(hb2_level_t L, int32_t ncoef, const double* alpha, const double* beta, double dt, int32_t last_stage)
+{
+    if (!L) return set_error(-1, "null level");
+    for (int pi = 0; pi < (int)L->patches.size(); pi++) {
+        int rc = hb2_level_advance_stage_patch(L, pi, ncoef, alpha, beta, dt);
+        if (rc) return rc;
+    }
+    return hb2_level_end_stage(L, ncoef, alpha, last_stage);
 }
 
 /* RungeKuttaLevelIntegrator::advanceLevel for the whole level: per stage the ghost fill, then every patch (alpha / beta:

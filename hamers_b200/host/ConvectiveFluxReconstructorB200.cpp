@@ -27,8 +27,15 @@ FlowModel::FlowModel(const std::string& object_name, const tbox::Dimension& dim,
         d_cons.push_back(HAMERS_SHARED_PTR<pdat::CellVariable<double> >(new pdat::CellVariable<double>(dim, "momentum", d)));
         d_cons.push_back(HAMERS_SHARED_PTR<pdat::CellVariable<double> >(new pdat::CellVariable<double>(dim, "total energy", 1)));
         d_cons.push_back(HAMERS_SHARED_PTR<pdat::CellVariable<double> >(new pdat::CellVariable<double>(dim, "volume fractions", num_species)));
+    } else if (type == FLOW_MODEL::FOUR_EQN_CONSERVATIVE) {
+        /* FlowModelFourEqnConservative.cpp:29, registerConservativeVariables :608-645; species_R is read where
+         * the plans are created */
+        d_num_eqn = d + 1 + num_species;
+        d_cons.push_back(HAMERS_SHARED_PTR<pdat::CellVariable<double> >(new pdat::CellVariable<double>(dim, "partial densities", num_species)));
+        d_cons.push_back(HAMERS_SHARED_PTR<pdat::CellVariable<double> >(new pdat::CellVariable<double>(dim, "momentum", d)));
+        d_cons.push_back(HAMERS_SHARED_PTR<pdat::CellVariable<double> >(new pdat::CellVariable<double>(dim, "total energy", 1)));
     } else {
-        TBOX_ERROR(d_object_name << ": the B200 convective-flux path is built for SINGLE_SPECIES and FIVE_EQN_ALLAIRE." << std::endl);
+        TBOX_ERROR(d_object_name << ": unknown flow model." << std::endl);
     }
 }
 
@@ -137,9 +144,16 @@ hb2_plan_t ConvectiveFluxReconstructorWCNS5_JS_HLLC_HLL_B200::getPlan(const hier
         desc.n[a] = a < dim ? interior_dims[a] : 1;
         desc.dx[a] = a < dim ? dx[a] : 1.0;
     }
-    desc.flow_model = d_flow_model_type == FLOW_MODEL::SINGLE_SPECIES ? HB2_SINGLE_SPECIES : HB2_FIVE_EQN_ALLAIRE;
+    desc.flow_model = d_flow_model_type == FLOW_MODEL::SINGLE_SPECIES
+                          ? HB2_SINGLE_SPECIES
+                          : (d_flow_model_type == FLOW_MODEL::FIVE_EQN_ALLAIRE ? HB2_FIVE_EQN_ALLAIRE : HB2_FOUR_EQN_CONSERVATIVE);
     desc.num_species = d_flow_model->getNumberOfSpecies();
     for (int s = 0; s < desc.num_species && s < HB2_MAX_SPECIES; s++) desc.species_gamma[s] = d_flow_model->getSpeciesGamma()[s];
+    if (desc.flow_model == HB2_FOUR_EQN_CONSERVATIVE) {
+        /* Equation_of_state_mixing_rules { species_R } (EquationOfStateMixingRulesIdealGas.cpp:60-100) */
+        const std::vector<double> R = d_flow_model->getFlowModelDatabase()->getDoubleVector("species_R");
+        for (int s = 0; s < desc.num_species && s < HB2_MAX_SPECIES && s < (int)R.size(); s++) desc.species_R[s] = R[s];
+    }
     desc.weno_p = d_constant_p;
     desc.scheme = d_scheme;
     desc.weno_q = d_constant_q;

@@ -374,6 +374,10 @@ int hb2_level_fill_ghosts(hb2_level_t level, int32_t state);
 /* computeFluxesAndSourcesOnPatch + advanceSingleStepOnPatch of every patch for RK stage ncoef - 1 (coefficient rows of
  * length ncoef); last_stage != 0: the result becomes the current state */
 int hb2_level_advance_stage(hb2_level_t level, int32_t ncoef, const double* alpha, const double* beta, double dt, int32_t last_stage);
+/* the same patch by patch (the reference calls the patch strategy once per patch and stage, RungeKuttaLevelIntegrator.cpp:
+ * 1709-1741): advance one patch through stage ncoef - 1; then, once per stage, hb2_level_end_stage */
+int hb2_level_advance_stage_patch(hb2_level_t level, int32_t patch, int32_t ncoef, const double* alpha, const double* beta, double dt);
+int hb2_level_end_stage(hb2_level_t level, int32_t ncoef, const double* alpha, int32_t last_stage);
 /* the stage loop of advanceLevel: alpha / beta row-major [nstages][nstages] */
 int hb2_level_advance(hb2_level_t level, int32_t nstages, const double* alpha, const double* beta, double dt);
 /* max over the rank's patches of the spectral radii (hb2_max_wave_speed_dev per patch); out_host: 4 doubles */
