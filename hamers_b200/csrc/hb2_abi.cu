@@ -75,6 +75,7 @@ struct hb2_plan_s {
     long long ws_bytes;
     int seg_len[3];
     int sensor_seg_len;
+    int bulk_ok;               /* geometry admits the bulk-copy staging (and HB2_BULK_STAGE != 0) */
     /* per-kernel-kind device timing (CUDA events on the launching stream) */
     int profiling;
     struct ProfRec {
@@ -405,6 +406,11 @@ void base_args(hb2_plan_t p, const double* const* Q, double dt, DirArgs* A)
     A->hyb = p->hyb;
     A->dt = dt;
     A->T = p->T;
+    /* bulk-copy staging needs 16-byte aligned rows (hb2_sweep.cuh): even n[0] and ghost width, aligned component pointers;
+     * the x sweep also an even segment length (checked where seg_len is set) */
+    A->bulk = p->bulk_ok;
+    for (int c = 0; c < p->ncomp; c++)
+        if (((uintptr_t)Q[c]) & 15u) A->bulk = 0;
 }
 
 int run_sensor(hb2_plan_t p, const double* const* Q)
@@ -570,6 +576,9 @@ int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* out)
         if (forced > 0) sl = forced;
         p->seg_len[a] = sl;
     }
+    /* bulk-copy staging of the load phase (hb2_sweep.cuh): rows must start and end on 16-byte boundaries */
+    p->bulk_ok = env_int("HB2_BULK_STAGE", 1) != 0 && (p->G.n[0] % 2 == 0) && (p->G.g[0] % 2 == 0) &&
+                 (p->seg_len[0] % 2 == 0 || p->seg_len[0] >= p->G.n[0]);
     {
         /* sensor pass: 61 x 8 tiles marching along z; enough segments for ~4 waves of 2 resident blocks per SM, at
          * least 16 planes each (every segment re-reads 3 planes) */

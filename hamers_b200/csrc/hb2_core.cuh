@@ -127,6 +127,7 @@ struct DirArgs {
      * is also stored into the ghost box of every neighbour that needs it.  NULL table: no push; NULL entry: no
      * neighbour there.  The table lives in device memory. */
     double* const* push;
+    int bulk;                  /* 1: the load phase stages whole rows with cp.async.bulk (hb2_sweep.cuh), 0: per-thread cp.async */
 };
 /* Fast build: nterm = HB2_NTERM_QREC + k means "k states in Ut are loaded from HBM and the flux state itself enters
  * the RK combination with alpha_q, rebuilt from the primitive-variable ring" -- 40 B/cell less HBM traffic in the last

@@ -89,7 +89,9 @@ struct SweepShape {
     static constexpr int OFF_Q = OFF_M + NMID * CS;
     /* the push addresses of the fused ghost fill (DirArgs::push), 27 neighbours x components */
     static constexpr int OFF_P = OFF_Q + Tr::NCOMP * NT;
-    static constexpr int SMEM_DOUBLES = OFF_P + 27 * Tr::NCOMP;
+    /* mbarrier of the bulk-copy staging (one 64-bit word) */
+    static constexpr int OFF_B = OFF_P + 27 * Tr::NCOMP + ((OFF_P + 27 * Tr::NCOMP) & 1);
+    static constexpr int SMEM_DOUBLES = OFF_B + 2;
     HB2_HD static int slot(int pp, int s) { return (DIR == 0) ? pp * RING + (s & (RING - 1)) : (s & (RING - 1)) * 32 + pp; }
     /* primitive-variable ring: r = ring position in [0, RINGV) */
     HB2_HD static int slotv(int pp, int r) { return (DIR == 0) ? pp * RINGV + r : r * 32 + pp; }
@@ -225,6 +227,125 @@ HB2_HD void phase_commit(const DirArgs& A, double* smem, const PencilCtx& c, int
         const int sl = Sh::slot(c.pp, s);
 #pragma unroll
         for (int e = 0; e < NEQ; e++) sN[e * Sh::CS + sl] = Fn[e];
+    }
+}
+
+/* ---- bulk-copy staging (DirArgs::bulk): the conservative variables of a whole chunk travel as ROWS with cp.async.bulk
+ * (SASS UBLKCP, the TMA unit's non-tensor form), issued by the lanes of warp 0 and completed on one mbarrier -- instead of
+ * five 8-byte LDGSTS plus their address arithmetic in EVERY thread (in kernels where each non-FP64 instruction competes
+ * with the FP64 issue slot).  A row is the chunk's cells of one (component, sweep position) -- y / z sweeps: 32 pencils
+ * contiguous in x (256 B) -- or of one (component, pencil) -- x sweep: 16 cells (128 B); the staging slots keep the layout
+ * [component][thread].  The iteration order changes with it: the copy of chunk t+1 is issued at the TOP of iteration t
+ * (after the barrier that ends iteration t-1: every thread has read its slot by then) and consumed at the END of
+ * iteration t, behind the face and update phases; face(t) never needs chunk t+1 (it reads cells up to c0 + (t+1)C - 5).
+ * Needs 16-byte aligned rows: even n[0], even ghost width, 16-byte aligned component pointers, even segment length in x
+ * (the host checks; otherwise the LDGSTS path runs). */
+template <class Tr, int DIR, int MATH>
+HB2_HD void bulk_rows(const PencilCtx& c, const Geom& G, int t, int& nrow, int& rowlen)
+{
+    using Sh = SweepShape<Tr, DIR, MATH>;
+    const int s0 = c.c0 - 4 + t * Sh::C;
+    int along = c.c1 + 4 - s0;                           /* cells of the chunk that exist */
+    along = along < 0 ? 0 : (along > Sh::C ? Sh::C : along);
+    if (DIR == 0) {
+        const int across = G.n[1] - (c.j - c.pp);        /* pencils (rows) of the block that exist */
+        nrow = across > Sh::P ? Sh::P : across;
+        rowlen = along;
+    } else {
+        const int across = G.n[0] - (c.i - c.pp);
+        nrow = along;
+        rowlen = across > 32 ? 32 : across;
+    }
+    if (nrow < 0) nrow = 0;
+}
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(mbar),
+        "r"(parity)
+        : "memory");
+}
+#endif
+
+/* top of iteration t - 1 (and of the prologue's successor): stage chunk t.  Every thread calls it; warp 0 works. */
+template <class Tr, int DIR, int MATH>
+HB2_HD void pipeline_issue(const DirArgs& A, double* smem, const PencilCtx& c, int t, unsigned mbar)
+{
+    using Sh = SweepShape<Tr, DIR, MATH>;
+    if (c.tid >= 32) return;
+    int nrow, rowlen;
+    bulk_rows<Tr, DIR, MATH>(c, A.G, t, nrow, rowlen);
+    if (nrow <= 0 || rowlen <= 0) return;
+    const int s0 = c.c0 - 4 + t * Sh::C;
+    double* sQ = smem + Sh::OFF_Q;
+#if defined(__CUDA_ARCH__)
+    if (c.tid == 0) mbar_expect_tx(mbar, (unsigned)(rowlen * 8 * nrow * Tr::NCOMP));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    const unsigned sq0 = (unsigned)__cvta_generic_to_shared(sQ);
+#else
+    (void)mbar;
+#endif
+    for (int r = c.tid; r < nrow * Tr::NCOMP; r += 32) {
+        const int cix = r / nrow, rr = r - cix * nrow;
+        long long x;
+        int slot;
+        if (DIR == 0) {
+            x = c.base + (long long)(rr - c.pp) * A.G.cs[1] + s0;
+            slot = cix * Sh::NT + rr * Sh::C;
+        } else {
+            x = (c.base - c.pp) + (long long)(s0 + rr) * c.st;
+            slot = cix * Sh::NT + rr * 32;
+        }
+#if defined(__CUDA_ARCH__)
+        bulk_g2s(sq0 + (unsigned)(slot * sizeof(double)), A.Q[cix] + x, (unsigned)(rowlen * 8), mbar);
+#else
+        for (int q = 0; q < rowlen; q++) sQ[slot + q] = A.Q[cix][x + q];
+#endif
+    }
+}
+
+/* end of iteration t: chunk t + 1 has landed (mbarrier phase), every thread takes its own cell and commits it */
+template <class Tr, int DIR, int MATH>
+HB2_HD void pipeline_consume(const DirArgs& A, double* smem, const PencilCtx& c, int t, unsigned mbar, unsigned& parity)
+{
+    int nrow, rowlen;
+    bulk_rows<Tr, DIR, MATH>(c, A.G, t, nrow, rowlen);
+    if (nrow <= 0 || rowlen <= 0) return;                /* block-uniform: nothing was issued */
+#if defined(__CUDA_ARCH__)
+    mbar_wait(mbar, parity);
+#else
+    (void)mbar;
+#endif
+    parity ^= 1u;
+    int s;
+    if (load_wanted<Tr, DIR, MATH>(c, t, s)) {
+        double q[Tr::NCOMP];
+        staged_cons<Tr, DIR, MATH>(smem, c, q);
+        phase_commit<Tr, DIR, MATH>(A, smem, c, s, q);
     }
 }
 
@@ -478,6 +599,8 @@ struct PipeRegs {
     int have;
     unsigned int flag;    /* sensor byte of the NEXT face phase (32-bit: a byte would be packed with `have`, which
                              makes the pack instruction wait for the load) */
+    unsigned int parity;  /* bulk staging: phase parity of the mbarrier */
+    unsigned int mbar;    /* bulk staging, device: shared-window address of the mbarrier */
 };
 
 template <class Tr, int DIR, int MATH>
@@ -494,22 +617,29 @@ HB2_HD void pipeline_prologue(const DirArgs& A, double* smem, const PencilCtx& c
         load_cons<Tr>(A, c.base + (long long)s * c.st, q);
         phase_commit<Tr, DIR, MATH>(A, smem, c, s, q);
     }
-    pr.have = load_wanted<Tr, DIR, MATH>(c, 1, pr.s);
-    if (pr.have) stage_cons<Tr, DIR, MATH>(A, smem, c, c.base + (long long)pr.s * c.st);
+    pr.parity = 0u;
+    if (A.bulk) {
+        pr.have = 0;                     /* chunk 1 is issued at the top of iteration 0 (pipeline_issue) */
+    } else {
+        pr.have = load_wanted<Tr, DIR, MATH>(c, 1, pr.s);
+        if (pr.have) stage_cons<Tr, DIR, MATH>(A, smem, c, c.base + (long long)pr.s * c.st);
+    }
     pr.flag = face_flag_fetch<Tr, DIR, MATH>(A, c, 0);
 }
 
 template <class Tr, int DIR, int MATH, int NTERM>
 HB2_HD void pipeline_iteration(const DirArgs& A, double* smem, const PencilCtx& c, int t, int nsteps, PipeRegs<Tr>& pr)
 {
-    if (pr.have) {
-        double q[Tr::NCOMP];
-        stage_wait_all();
-        staged_cons<Tr, DIR, MATH>(smem, c, q);
-        phase_commit<Tr, DIR, MATH>(A, smem, c, pr.s, q);
+    if (!A.bulk) {
+        if (pr.have) {
+            double q[Tr::NCOMP];
+            stage_wait_all();
+            staged_cons<Tr, DIR, MATH>(smem, c, q);
+            phase_commit<Tr, DIR, MATH>(A, smem, c, pr.s, q);
+        }
+        pr.have = load_wanted<Tr, DIR, MATH>(c, t + 2, pr.s);
+        if (pr.have) stage_cons<Tr, DIR, MATH>(A, smem, c, c.base + (long long)pr.s * c.st);
     }
-    pr.have = load_wanted<Tr, DIR, MATH>(c, t + 2, pr.s);
-    if (pr.have) stage_cons<Tr, DIR, MATH>(A, smem, c, c.base + (long long)pr.s * c.st);
     int cc;
     const bool do_update = update_wanted<Tr, DIR, MATH>(c, t - 1, cc);
     UpdateIn<Tr> uin;
@@ -532,6 +662,7 @@ HB2_HD void pipeline_iteration(const DirArgs& A, double* smem, const PencilCtx& 
     if (t < nsteps) phase_face<Tr, DIR, MATH>(A, smem, c, t, flag);
     if (!HB2_PREFETCH_R && do_update) update_fetch<Tr, DIR, FUSED>(A, c, cc, uin);
     if (do_update) phase_update<Tr, DIR, MATH, NTERM>(A, smem, c, cc, uin);
+    if (A.bulk) pipeline_consume<Tr, DIR, MATH>(A, smem, c, t + 1, pr.mbar, pr.parity);
 }
 
 }  // namespace hb2

@@ -74,9 +74,15 @@ __global__ void __launch_bounds__(256, (MATH == 1 && Tr::MODEL == SS && HB2_SCHE
     c.sq = (unsigned)__cvta_generic_to_shared(smem + Sh::OFF_Q + threadIdx.x);
     const int nsteps = Sh::nsteps(c.c1 - c.c0);
     PipeRegs<Tr> pr;
+    pr.mbar = (unsigned)__cvta_generic_to_shared(smem + Sh::OFF_B);
+    if (A.bulk && threadIdx.x == 0) {
+        mbar_init(pr.mbar, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     pipeline_prologue<Tr, DIR, MATH>(A, smem, c, pr);
     __syncthreads();
     for (int t = 0; t <= nsteps; t++) {
+        if (A.bulk) pipeline_issue<Tr, DIR, MATH>(A, smem, c, t + 1, pr.mbar);
         pipeline_iteration<Tr, DIR, MATH, NTERM>(A, smem, c, t, nsteps, pr);
         __syncthreads();
     }

@@ -79,11 +79,19 @@ static void run_dir_n(const DirArgs& A)
                     const int tid = rev ? Sh::NT - 1 - n : n;
                     pipeline_prologue<Tr, DIR, MATH>(A, smem.data(), pencil_ctx<Tr, DIR, MATH>(A, b, tid), regs[tid]);
                 }
-                for (int t = 0; t <= nsteps; t++)
+                for (int t = 0; t <= nsteps; t++) {
+                    /* bulk staging: warp 0 issues the copy of chunk t + 1 at the top of the iteration; the mbarrier wait of
+                     * the consumers orders it before their reads, whatever the thread order */
+                    if (A.bulk)
+                        for (int n = 0; n < Sh::NT; n++) {
+                            const int tid = rev ? Sh::NT - 1 - n : n;
+                            pipeline_issue<Tr, DIR, MATH>(A, smem.data(), pencil_ctx<Tr, DIR, MATH>(A, b, tid), t + 1, 0u);
+                        }
                     for (int n = 0; n < Sh::NT; n++) {
                         const int tid = rev ? Sh::NT - 1 - n : n;
                         pipeline_iteration<Tr, DIR, MATH, NTERM>(A, smem.data(), pencil_ctx<Tr, DIR, MATH>(A, b, tid), t, nsteps, regs[tid]);
                     }
+                }
             }
 }
 
@@ -169,6 +177,12 @@ static void run_sweeps(DirArgs A0, int sensor_seg_len, int seg_len, double* cons
             for (int e = 0; e < Tr::NEQ; e++) A.F[e] = F_all[dir * Tr::NEQ + e];
         if (dir != Tr::DIM - 1) A.ncoef = 0;
         A.seg_len = seg_len > 0 ? seg_len : G.n[dir];
+        {
+            /* the library's condition for the bulk-copy staging (hb2_abi.cu: bulk_ok) */
+            const char* v = getenv("HB2_BULK_STAGE");
+            const int x_seg = seg_len > 0 ? seg_len : G.n[0];
+            A.bulk = (!v || atoi(v) != 0) && (G.n[0] % 2 == 0) && (G.g[0] % 2 == 0) && (x_seg % 2 == 0 || x_seg >= G.n[0]);
+        }
         if (dir == 0)
             run_dir<Tr, 0, MATH>(A);
         else if (dir == 1)
