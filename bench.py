@@ -478,22 +478,28 @@ def run_ours(args):
             "kernels": kern,
         }
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
-        # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of this workload
+        # DRAM traffic of the dominant kernel per launch: NOT measured in this run (ncu is never attached to a bench run); the
+        # value is read from the committed ncu --set full capture of the same workload and labelled as such
+        design_bytes = {"xsweep": 80.0, "ysweep": 120.0, "zsweep": 160.0}     # bytes per cell the three-sweep DESIGN moves
         try:
             with open(os.path.join(ROOT, "profiles", "r01_n_traffic.json")) as fh:
                 tr = json.load(fh)
             if tr["size"] == args.size and tr["model"] == args.model and tr["math"] == args.math and world == 1:
                 roofline["traffic"] = tr["dram_bytes_per_launch"][dom]
                 roofline["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)"
-                roofline["traffic_source"] = tr["source"]
-                roofline["algorithmic_bytes_per_launch"] = {"xsweep": 80.0, "ysweep": 120.0, "zsweep": 160.0}[dom] * ncell_local
+                roofline["traffic_source"] = "from committed capture, not measured in this run: " + tr["source"]
         except Exception:
             pass
-        # the same dominant kernel against the HBM roof (the secondary roof of this FP64-bound path): algorithmic bytes
-        # of the launch (x 80, y 120, z 160 B/cell with the R round trips of the three-sweep design) / its time
-        dom_bytes = {"xsweep": 80.0, "ysweep": 120.0, "zsweep": 160.0}[dom] * ncell_local
+        roofline["design_bytes_per_launch"] = design_bytes[dom] * ncell_local
+        # algorithmic traffic of a whole STAGE (fused, no flux materialisation) is 80 / 120 / 120 B per cell for
+        # stages 0 / 1 / 2; the three-sweep design adds the R round trips between the sweeps and two more reads of the state
+        roofline["algorithmic_bytes_per_stage"] = {"stage0": 80.0 * ncell_local, "stage1": 120.0 * ncell_local, "stage2": 120.0 * ncell_local}
+        # the same dominant kernel against the HBM roof (the secondary roof of this FP64-bound path): bytes the DESIGN moves in
+        # that launch (x 80, y 120, z 160 B/cell with the R round trips) / its time
+        dom_bytes = design_bytes[dom] * ncell_local
         roofline_hbm = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                        "unit": "GB/s", "peak_source": hbm_src, "traffic": roofline.get("traffic")}
+                        "unit": "GB/s", "peak_source": hbm_src, "traffic": roofline.get("traffic"),
+                        "bytes": "design bytes of the launch (not SURVEY 8d's algorithmic stage bytes, given in roofline.algorithmic_bytes_per_stage)"}
         roofline_hbm["frac"] = roofline_hbm["achieved"] / roofline_hbm["peak"]
         line = {
             "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world,

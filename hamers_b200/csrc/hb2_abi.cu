@@ -577,7 +577,11 @@ int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* out)
         p->seg_len[a] = sl;
     }
     /* bulk-copy staging of the load phase (hb2_sweep.cuh): rows must start and end on 16-byte boundaries */
-    p->bulk_ok = env_int("HB2_BULK_STAGE", 1) != 0 && (p->G.n[0] % 2 == 0) && (p->G.g[0] % 2 == 0) &&
+    /* measured on B200 at 512^3 (profiles/r02_h_bulk_stage_ab.txt): x / y / z sweep 9.03 / 7.55 / 8.01 ms with the bulk
+     * copies against 6.78 / 6.98 / 7.50 ms with the per-thread cp.async -- the chunk is consumed behind the update phase, right
+     * in front of the barrier, where the conversion's divide / sqrt chain has nothing to hide behind, and the x sweep issues
+     * 80 copies of 128 B per iteration from one warp.  Off by default; HB2_BULK_STAGE=1 selects it. */
+    p->bulk_ok = env_int("HB2_BULK_STAGE", 0) != 0 && (p->G.n[0] % 2 == 0) && (p->G.g[0] % 2 == 0) &&
                  (p->seg_len[0] % 2 == 0 || p->seg_len[0] >= p->G.n[0]);
     {
         /* sensor pass: 61 x 8 tiles marching along z; enough segments for ~4 waves of 2 resident blocks per SM, at

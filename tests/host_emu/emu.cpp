@@ -181,7 +181,7 @@ static void run_sweeps(DirArgs A0, int sensor_seg_len, int seg_len, double* cons
             /* the library's condition for the bulk-copy staging (hb2_abi.cu: bulk_ok) */
             const char* v = getenv("HB2_BULK_STAGE");
             const int x_seg = seg_len > 0 ? seg_len : G.n[0];
-            A.bulk = (!v || atoi(v) != 0) && (G.n[0] % 2 == 0) && (G.g[0] % 2 == 0) && (x_seg % 2 == 0 || x_seg >= G.n[0]);
+            A.bulk = (v && atoi(v) != 0) && (G.n[0] % 2 == 0) && (G.g[0] % 2 == 0) && (x_seg % 2 == 0 || x_seg >= G.n[0]);
         }
         if (dir == 0)
             run_dir<Tr, 0, MATH>(A);

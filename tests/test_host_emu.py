@@ -206,3 +206,20 @@ def test_emulated_sweeps_on_a_six_ghost_layout(name, math, oracle_lib):
     if math == 0:
         Fo, So = oracle_lib.compute_flux_and_source(desc, Q4, dt)
         assert all(np.array_equal(F6[a], Fo[a]) for a in range(desc.dim))
+
+
+@pytest.mark.parametrize("name", ["ss2d", "fe2d"])
+def test_emulated_bulk_copy_staging_path(name, oracle_lib, monkeypatch):
+    """The bulk-copy staging of the load phase (hb2_sweep.cuh: rows issued by warp 0 at the top of an iteration, consumed at
+    its end; HB2_BULK_STAGE=1, off by default because it measured slower) produces the same bits as the per-thread cp.async
+    path: fluxes and the fused stage against the oracle, long pencils with several segments included."""
+    monkeypatch.setenv("HB2_BULK_STAGE", "1")
+    desc, U = make_case(name, "random")
+    Q = pb.pad_periodic(U)
+    Fo, So = oracle_lib.compute_flux_and_source(desc, Q, 1.0e-3)
+    Fe, Se = emu_host.flux_and_source(desc, Q, 1.0e-3, math=0)
+    for a in range(desc.dim):
+        assert np.array_equal(Fe[a], Fo[a])
+    Uo = oracle_lib.advance_stage(desc, [1.0], [1.0], [Q], [Fo], [So])
+    Ue = emu_host.fused_stage(desc, [1.0], [1.0], [Q], 1.0e-3, math=0, seg_len=8)
+    assert np.array_equal(interior(desc, Ue), interior(desc, Uo))
