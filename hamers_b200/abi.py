@@ -46,7 +46,7 @@ SYMBOLS = [
     "hb2_level_create", "hb2_level_destroy", "hb2_level_num_patches", "hb2_level_launch_count", "hb2_level_synchronize",
     "hb2_level_upload_patch", "hb2_level_download_patch", "hb2_level_patch_state_dev", "hb2_level_fill_ghosts",
     "hb2_level_advance_stage", "hb2_level_advance", "hb2_level_max_wave_speed", "hb2_level_advance_stage_patch",
-    "hb2_level_end_stage",
+    "hb2_level_end_stage", "hb2_level_advance_host",
 ]
 
 WCNS5_JS, WCNS5_Z, WCNS6_LD = 0, 1, 2

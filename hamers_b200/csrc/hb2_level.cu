@@ -79,6 +79,11 @@ struct hb2_level_s {
     cudaStream_t stream;
     long long launches;
     double* d_sr;                               /* 4 doubles per patch: spectral radii */
+    /* pipelined host-memory advance (hb2_level_advance_host) */
+    std::vector<int> desc_begin;                /* descriptors of destination patch p: [desc_begin[p], desc_begin[p + 1]) */
+    std::vector<std::vector<int>> sources;      /* patches whose data the ghost fill of patch p reads */
+    cudaStream_t copy_in, copy_out;
+    std::vector<cudaEvent_t> ev_up, ev_done;
 };
 
 namespace {
@@ -134,6 +139,17 @@ int build_fill_table(hb2_level_t L)
                     }
                 }
     }
+    /* descriptors were generated destination by destination: remember the ranges and who feeds whom */
+    L->desc_begin.assign(np + 1, 0);
+    L->sources.assign(np, std::vector<int>());
+    for (size_t k = 0; k < D.size(); k++) {
+        L->desc_begin[D[k].dst + 1] = (int)k + 1;
+        bool seen = false;
+        for (int q : L->sources[D[k].dst]) seen = seen || q == D[k].src;
+        if (!seen) L->sources[D[k].dst].push_back(D[k].src);
+    }
+    for (int p = 0; p < np; p++)
+        if (L->desc_begin[p + 1] < L->desc_begin[p]) L->desc_begin[p + 1] = L->desc_begin[p];
     L->ndesc = (int)D.size();
     if (L->ndesc) {
         HB2L_CUDA(cudaMalloc(&L->d_desc, sizeof(CopyDesc) * D.size()));
@@ -142,6 +158,18 @@ int build_fill_table(hb2_level_t L)
     return 0;
 }
 
+}  // namespace
+
+namespace {
+/* what travels between host and device for one component of a patch: the planes (rows in 2-D) of the slowest direction
+ * that hold interior cells -- one contiguous range of the ghost-box array; the ghost planes beyond are filled on the device */
+void transfer_range(hb2_level_t L, const LevelPatch& P, long long* off, long long* cnt)
+{
+    long long plane = 1;
+    for (int a = 0; a < L->dim - 1; a++) plane *= P.n[a] + 2 * L->g;
+    *off = plane * L->g;
+    *cnt = plane * P.n[L->dim - 1];
+}
 }  // namespace
 
 extern "C" {
@@ -165,6 +193,7 @@ int hb2_level_create(const hb2_patch_desc* model, int32_t npatch, const int32_t*
     L->d_desc = nullptr;
     L->d_sr = nullptr;
     L->launches = 0;
+    L->copy_in = L->copy_out = nullptr;
     for (int b = 0; b < 3; b++) {
         L->where[b] = b;
         L->d_ptrs[b] = nullptr;
@@ -179,6 +208,8 @@ int hb2_level_create(const hb2_patch_desc* model, int32_t npatch, const int32_t*
     if (L->device < 0) HB2L_CUDA(cudaGetDevice(&L->device));
     HB2L_CUDA(cudaSetDevice(L->device));
     HB2L_CUDA(cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking));
+    HB2L_CUDA(cudaStreamCreateWithFlags(&L->copy_in, cudaStreamNonBlocking));
+    HB2L_CUDA(cudaStreamCreateWithFlags(&L->copy_out, cudaStreamNonBlocking));
     std::map<std::vector<int>, int> shape_of;
     for (int p = 0; p < npatch; p++) {
         LevelPatch P;
@@ -226,6 +257,12 @@ int hb2_level_create(const hb2_patch_desc* model, int32_t npatch, const int32_t*
         HB2L_CUDA(cudaMemcpy(L->d_ptrs[b], tab.data(), sizeof(double*) * tab.size(), cudaMemcpyHostToDevice));
     }
     HB2L_CUDA(cudaMalloc(&L->d_sr, sizeof(double) * 4 * (size_t)npatch));
+    L->ev_up.resize(npatch);
+    L->ev_done.resize(npatch);
+    for (int p = 0; p < npatch; p++) {
+        HB2L_CUDA(cudaEventCreateWithFlags(&L->ev_up[p], cudaEventDisableTiming));
+        HB2L_CUDA(cudaEventCreateWithFlags(&L->ev_done[p], cudaEventDisableTiming));
+    }
     int rc = build_fill_table(L);
     if (rc) {
         hb2_level_destroy(L);
@@ -246,6 +283,10 @@ int hb2_level_destroy(hb2_level_t L)
     for (int b = 0; b < 3; b++) cudaFree(L->d_ptrs[b]);
     cudaFree(L->d_desc);
     cudaFree(L->d_sr);
+    for (auto e : L->ev_up) cudaEventDestroy(e);
+    for (auto e : L->ev_done) cudaEventDestroy(e);
+    if (L->copy_in) cudaStreamDestroy(L->copy_in);
+    if (L->copy_out) cudaStreamDestroy(L->copy_out);
     if (L->stream) cudaStreamDestroy(L->stream);
     delete L;
     return 0;
@@ -276,9 +317,10 @@ int hb2_level_upload_patch(hb2_level_t L, int32_t patch, const double* const* U_
     if (patch < 0 || patch >= (int)L->patches.size()) return set_error(-42, "patch index out of range");
     HB2L_CUDA(cudaSetDevice(L->device));
     const LevelPatch& P = L->patches[patch];
-    /* the whole ghost box travels (one contiguous copy per component); the ghosts are refilled on the device anyway */
+    long long off, cnt;
+    transfer_range(L, P, &off, &cnt);
     for (int c = 0; c < L->ncomp; c++)
-        HB2L_CUDA(cudaMemcpyAsync(P.S[L->where[0]] + (size_t)c * P.ncell_g, U_host[c], sizeof(double) * (size_t)P.ncell_g,
+        HB2L_CUDA(cudaMemcpyAsync(P.S[L->where[0]] + (size_t)c * P.ncell_g + off, U_host[c] + off, sizeof(double) * (size_t)cnt,
                                   cudaMemcpyHostToDevice, L->stream));
     return 0;
 }
@@ -289,8 +331,10 @@ int hb2_level_download_patch(hb2_level_t L, int32_t patch, double* const* U_host
     if (patch < 0 || patch >= (int)L->patches.size()) return set_error(-42, "patch index out of range");
     HB2L_CUDA(cudaSetDevice(L->device));
     const LevelPatch& P = L->patches[patch];
+    long long off, cnt;
+    transfer_range(L, P, &off, &cnt);
     for (int c = 0; c < L->ncomp; c++)
-        HB2L_CUDA(cudaMemcpyAsync(U_host[c], P.S[L->where[0]] + (size_t)c * P.ncell_g, sizeof(double) * (size_t)P.ncell_g,
+        HB2L_CUDA(cudaMemcpyAsync(U_host[c] + off, P.S[L->where[0]] + (size_t)c * P.ncell_g + off, sizeof(double) * (size_t)cnt,
                                   cudaMemcpyDeviceToHost, L->stream));
     HB2L_CUDA(cudaStreamSynchronize(L->stream));
     return 0;
@@ -391,6 +435,84 @@ int hb2_level_advance(hb2_level_t L, int32_t nstages, const double* alpha, const
         rc = hb2_level_advance_stage(L, sn + 1, alpha + sn * nstages, beta + sn * nstages, dt, sn == nstages - 1);
         if (rc) return rc;
     }
+    return 0;
+}
+
+/* advanceLevel on HOST memory, pipelined over the patches.  U_host[p * num_comp + c]: ghost-box array of component c of
+ * patch p (pinned memory gives asynchronous copies); on return it holds the new state (interior planes of the slowest
+ * direction are transferred, like hb2_level_upload_patch / _download_patch).  Patches are uploaded in index order on a copy
+ * stream; the FIRST stage of a patch starts as soon as the patch and the patches its ghost cells come from have arrived
+ * (events), so the upload of the rest overlaps it; in the LAST stage every patch is downloaded on a second copy stream as soon
+ * as it is done, so the download overlaps the other patches' last stage.  A time step on a host level is PCIe-bound (two
+ * transfers of the whole state); this removes the compute of the first and last stage from the critical path. */
+int hb2_level_advance_host(hb2_level_t L, int32_t nstages, const double* alpha, const double* beta, double dt,
+                           double* const* U_host)
+{
+    if (!L || !alpha || !beta || !U_host) return set_error(-1, "hb2_level_advance_host: null argument");
+    if (nstages < 1 || nstages > 3) return set_error(-20, "hb2_level_advance_host supports 1..3 stages");
+    HB2L_CUDA(cudaSetDevice(L->device));
+    const int np = (int)L->patches.size();
+    /* uploads */
+    for (int p = 0; p < np; p++) {
+        const LevelPatch& P = L->patches[p];
+        long long off, cnt;
+        transfer_range(L, P, &off, &cnt);
+        for (int c = 0; c < L->ncomp; c++)
+            HB2L_CUDA(cudaMemcpyAsync(P.S[L->where[0]] + (size_t)c * P.ncell_g + off, U_host[(size_t)p * L->ncomp + c] + off,
+                                      sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice, L->copy_in));
+        HB2L_CUDA(cudaEventRecord(L->ev_up[p], L->copy_in));
+    }
+    /* order of the first stage: by the upload position of the last patch each one waits for */
+    std::vector<int> order(np), ready(np);
+    for (int p = 0; p < np; p++) {
+        order[p] = p;
+        ready[p] = p;
+        for (int q : L->sources[p]) ready[p] = q > ready[p] ? q : ready[p];
+    }
+    for (int i = 1; i < np; i++)
+        for (int j = i; j > 0 && ready[order[j]] < ready[order[j - 1]]; j--) std::swap(order[j], order[j - 1]);
+    for (int sn = 0; sn < nstages; sn++) {
+        const double* a = alpha + sn * nstages;
+        const double* b = beta + sn * nstages;
+        const bool first = sn == 0, last = sn == nstages - 1;
+        if (!first && L->ndesc) {
+            dim3 grid(8, (unsigned)L->ndesc);
+            k_level_fill<<<grid, 256, 0, L->stream>>>(L->d_desc, L->d_ptrs[L->where[sn]], L->ncomp);
+            L->launches++;
+        }
+        const int out = stage_output_buffer(L, sn + 1, a);
+        if (out < 0) return set_error(-43, "a third stage needs one alpha == 0 among the older states (three buffers per patch)");
+        for (int i = 0; i < np; i++) {
+            const int p = first ? order[i] : i;
+            if (first) {
+                HB2L_CUDA(cudaStreamWaitEvent(L->stream, L->ev_up[p], 0));
+                for (int q : L->sources[p]) HB2L_CUDA(cudaStreamWaitEvent(L->stream, L->ev_up[q], 0));
+                const int nd = L->desc_begin[p + 1] - L->desc_begin[p];
+                if (nd > 0) {
+                    dim3 grid(8, (unsigned)nd);
+                    k_level_fill<<<grid, 256, 0, L->stream>>>(L->d_desc + L->desc_begin[p], L->d_ptrs[L->where[0]], L->ncomp);
+                    L->launches++;
+                }
+            }
+            int rc = hb2_level_advance_stage_patch(L, p, sn + 1, a, b, dt);
+            if (rc) return rc;
+            if (last) {
+                const LevelPatch& P = L->patches[p];
+                long long off, cnt;
+                transfer_range(L, P, &off, &cnt);
+                HB2L_CUDA(cudaEventRecord(L->ev_done[p], L->stream));
+                HB2L_CUDA(cudaStreamWaitEvent(L->copy_out, L->ev_done[p], 0));
+                for (int c = 0; c < L->ncomp; c++)
+                    HB2L_CUDA(cudaMemcpyAsync(U_host[(size_t)p * L->ncomp + c] + off, P.S[out] + (size_t)c * P.ncell_g + off,
+                                              sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, L->copy_out));
+            }
+        }
+        int rc = hb2_level_end_stage(L, sn + 1, a, last ? 1 : 0);
+        if (rc) return rc;
+    }
+    HB2L_CUDA(cudaGetLastError());
+    HB2L_CUDA(cudaStreamSynchronize(L->copy_out));
+    HB2L_CUDA(cudaStreamSynchronize(L->stream));
     return 0;
 }
 

@@ -380,6 +380,11 @@ int hb2_level_advance_stage_patch(hb2_level_t level, int32_t patch, int32_t ncoe
 int hb2_level_end_stage(hb2_level_t level, int32_t ncoef, const double* alpha, int32_t last_stage);
 /* the stage loop of advanceLevel: alpha / beta row-major [nstages][nstages] */
 int hb2_level_advance(hb2_level_t level, int32_t nstages, const double* alpha, const double* beta, double dt);
+/* advanceLevel on HOST memory, pipelined over the patches: U_host[patch * num_comp + c] are ghost-box host arrays (pinned
+ * memory for asynchronous copies), new state on return.  The upload of later patches overlaps the first stage of the
+ * patches that have arrived, the download of finished patches overlaps the last stage of the others. */
+int hb2_level_advance_host(hb2_level_t level, int32_t nstages, const double* alpha, const double* beta, double dt,
+                           double* const* U_host);
 /* max over the rank's patches of the spectral radii (hb2_max_wave_speed_dev per patch); out_host: 4 doubles */
 int hb2_level_max_wave_speed(hb2_level_t level, double out_host[4]);
 
