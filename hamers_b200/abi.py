@@ -98,6 +98,8 @@ def load_library():
         lib = C.CDLL(SO)
         lib.hb2_last_error.restype = C.c_char_p
         lib.hb2_version.restype = C.c_char_p
+        lib.hb2_level_launch_count.restype = C.c_int64
+        lib.hb2_level_launch_count.argtypes = [C.c_void_p]
         for f in ("hb2_cell_ghost_size", "hb2_cell_size", "hb2_side_size", "hb2_plan_launch_count",
                   "hb2_plan_workspace_bytes"):
             getattr(lib, f).restype = C.c_int64
@@ -595,6 +597,91 @@ class AmrPair:
         _check(self.lib.hb2_amr_coarsen_fluxsum_dev(C.byref(self.desc), _ptr_table(_dev_ptrs(fluxsum, self.neq)),
                                                     _ptr_table(_dev_ptrs(F_coarse, self.neq)), self._stream()),
                "hb2_amr_coarsen_fluxsum_dev")
+
+
+class DeviceLevel:
+    """Device-resident multi-patch level (mirrors hb2_level_t): all patches of one rank registered once.  boxes: list of
+    (lo, hi) in level index space, hi exclusive."""
+
+    def __init__(self, dim, boxes, level_n, periodic_mask=None, flow_model=SINGLE_SPECIES, species_gamma=(1.4,), species_R=(),
+                 dx=(1.0, 1.0, 1.0), math=MATH_EXACT, scheme=0):
+        self.lib = load_library()
+        d = PatchDescC()
+        d.dim = dim
+        for a in range(3):
+            d.n[a] = 1
+            d.dx[a] = float(dx[a]) if a < dim else 1.0
+        d.flow_model = flow_model
+        d.num_species = len(species_gamma) if flow_model != SINGLE_SPECIES else 1
+        for i, g in enumerate(species_gamma):
+            d.species_gamma[i] = float(g)
+        for i, r in enumerate(species_R):
+            d.species_R[i] = float(r)
+        d.weno_p, d.math, d.device, d.scheme = 2, math, -1, int(scheme)
+        self.dim, self.boxes = dim, [(tuple(lo), tuple(hi)) for lo, hi in boxes]
+        np_ = len(self.boxes)
+        lo = (C.c_int32 * (3 * np_))(*[int(b[0][a]) if a < dim else 0 for b in self.boxes for a in range(3)])
+        hi = (C.c_int32 * (3 * np_))(*[int(b[1][a]) if a < dim else 1 for b in self.boxes for a in range(3)])
+        ln = (C.c_int32 * 3)(*[int(level_n[a]) if a < dim else 1 for a in range(3)])
+        mask = (1 << dim) - 1 if periodic_mask is None else int(periodic_mask)
+        self._h = C.c_void_p()
+        _check(self.lib.hb2_level_create(C.byref(d), np_, lo, hi, ln, mask, C.byref(self._h)), "hb2_level_create")
+        neq, ncomp = C.c_int32(), C.c_int32()
+        self.lib.hb2_num_comp(C.byref(d), C.byref(ncomp))
+        self.lib.hb2_num_eqn(C.byref(d), C.byref(neq))
+        self.ncomp, self.neq = ncomp.value, neq.value
+
+    def ghost_shape(self, p):
+        lo, hi = self.boxes[p]
+        return tuple(hi[a] - lo[a] + 2 * GHOSTS for a in reversed(range(self.dim)))
+
+    def close(self):
+        if self._h:
+            self.lib.hb2_level_destroy(self._h)
+            self._h = None
+
+    def _host_table(self, arrays):
+        """arrays: list per patch of C-contiguous float64 numpy arrays (ncomp, *ghost_shape)"""
+        tab = (C.c_void_p * (len(arrays) * self.ncomp))()
+        for p, a in enumerate(arrays):
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.shape == (self.ncomp,) + self.ghost_shape(p)
+            stride = a[0].size * 8
+            for c in range(self.ncomp):
+                tab[p * self.ncomp + c] = a.ctypes.data + c * stride
+        return tab
+
+    def upload(self, arrays):
+        tab = self._host_table(arrays)
+        for p in range(len(arrays)):
+            sub = (C.c_void_p * self.ncomp)(*[tab[p * self.ncomp + c] for c in range(self.ncomp)])
+            _check(self.lib.hb2_level_upload_patch(self._h, p, sub), "hb2_level_upload_patch")
+
+    def download(self, arrays):
+        tab = self._host_table(arrays)
+        for p in range(len(arrays)):
+            sub = (C.c_void_p * self.ncomp)(*[tab[p * self.ncomp + c] for c in range(self.ncomp)])
+            _check(self.lib.hb2_level_download_patch(self._h, p, sub), "hb2_level_download_patch")
+
+    def advance(self, dt, alpha=None, beta=None):
+        a = np.ascontiguousarray(SSPRK3_ALPHA if alpha is None else alpha, dtype=np.float64)
+        b = np.ascontiguousarray(SSPRK3_BETA if beta is None else beta, dtype=np.float64)
+        _check(self.lib.hb2_level_advance(self._h, a.shape[0], a.ctypes.data_as(C.POINTER(C.c_double)),
+                                          b.ctypes.data_as(C.POINTER(C.c_double)), C.c_double(dt)), "hb2_level_advance")
+
+    def advance_host(self, arrays, dt, alpha=None, beta=None):
+        """One RK step on host arrays (pinned memory for asynchronous copies), pipelined over the patches; in place."""
+        a = np.ascontiguousarray(SSPRK3_ALPHA if alpha is None else alpha, dtype=np.float64)
+        b = np.ascontiguousarray(SSPRK3_BETA if beta is None else beta, dtype=np.float64)
+        _check(self.lib.hb2_level_advance_host(self._h, a.shape[0], a.ctypes.data_as(C.POINTER(C.c_double)),
+                                               b.ctypes.data_as(C.POINTER(C.c_double)), C.c_double(dt), self._host_table(arrays)),
+               "hb2_level_advance_host")
+
+    def synchronize(self):
+        _check(self.lib.hb2_level_synchronize(self._h), "hb2_level_synchronize")
+
+    @property
+    def launch_count(self):
+        return int(self.lib.hb2_level_launch_count(self._h))
 
 
 class DeviceArray:
