@@ -440,11 +440,14 @@ int hb2_level_advance(hb2_level_t L, int32_t nstages, const double* alpha, const
 
 /* advanceLevel on HOST memory, pipelined over the patches.  U_host[p * num_comp + c]: ghost-box array of component c of
  * patch p (pinned memory gives asynchronous copies); on return it holds the new state (interior planes of the slowest
- * direction are transferred, like hb2_level_upload_patch / _download_patch).  Patches are uploaded in index order on a copy
- * stream; the FIRST stage of a patch starts as soon as the patch and the patches its ghost cells come from have arrived
- * (events), so the upload of the rest overlaps it; in the LAST stage every patch is downloaded on a second copy stream as soon
- * as it is done, so the download overlaps the other patches' last stage.  A time step on a host level is PCIe-bound (two
- * transfers of the whole state); this removes the compute of the first and last stage from the critical path. */
+ * direction are transferred, like hb2_level_upload_patch / _download_patch).
+ * A time step on host memory is PCIe-bound (the whole state goes in and comes out), but PCIe is full duplex and a patch
+ * depends on its neighbours only: stage s of patch p needs stage s - 1 of p and of the patches its ghost cells come from.
+ * So the patches are uploaded on one copy stream, every (patch, stage) task is enqueued on the compute stream in the order in
+ * which the uploads make it runnable (a wavefront that trails the upload by a few patches), and a patch is downloaded on a
+ * second copy stream as soon as its last stage is done -- the download of the early patches runs while the late ones are
+ * still being uploaded.  Buffers: stage outputs rotate like in hb2_level_advance; a patch overwrites U^(1) in its last stage
+ * only after every neighbour's second stage (which read it) is done, because its own last stage depends on those. */
 int hb2_level_advance_host(hb2_level_t L, int32_t nstages, const double* alpha, const double* beta, double dt,
                            double* const* U_host)
 {
@@ -452,8 +455,15 @@ int hb2_level_advance_host(hb2_level_t L, int32_t nstages, const double* alpha, 
     if (nstages < 1 || nstages > 3) return set_error(-20, "hb2_level_advance_host supports 1..3 stages");
     HB2L_CUDA(cudaSetDevice(L->device));
     const int np = (int)L->patches.size();
-    /* uploads */
-    for (int p = 0; p < np; p++) {
+    /* upload order: index order, except that a last patch that feeds the first one (periodic stack of slabs) goes first */
+    std::vector<int> uorder, pos(np);
+    bool wrap = false;
+    for (int q : L->sources[0]) wrap = wrap || (q == np - 1 && np > 2);
+    if (wrap) uorder.push_back(np - 1);
+    for (int p = 0; p < np - (wrap ? 1 : 0); p++) uorder.push_back(p);
+    for (int i = 0; i < np; i++) pos[uorder[i]] = i;
+    for (int i = 0; i < np; i++) {
+        const int p = uorder[i];
         const LevelPatch& P = L->patches[p];
         long long off, cnt;
         transfer_range(L, P, &off, &cnt);
@@ -462,57 +472,69 @@ int hb2_level_advance_host(hb2_level_t L, int32_t nstages, const double* alpha, 
                                       sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice, L->copy_in));
         HB2L_CUDA(cudaEventRecord(L->ev_up[p], L->copy_in));
     }
-    /* order of the first stage: by the upload position of the last patch each one waits for */
-    std::vector<int> order(np), ready(np);
-    for (int p = 0; p < np; p++) {
-        order[p] = p;
-        ready[p] = p;
-        for (int q : L->sources[p]) ready[p] = q > ready[p] ? q : ready[p];
-    }
-    for (int i = 1; i < np; i++)
-        for (int j = i; j > 0 && ready[order[j]] < ready[order[j - 1]]; j--) std::swap(order[j], order[j - 1]);
+    /* readiness of every (patch, stage) task in units of upload positions, then the enqueue order */
+    std::vector<std::vector<int>> ready(nstages, std::vector<int>(np, 0));
+    for (int sn = 0; sn < nstages; sn++)
+        for (int p = 0; p < np; p++) {
+            int r = sn == 0 ? pos[p] : ready[sn - 1][p];
+            for (int q : L->sources[p]) {
+                const int rq = sn == 0 ? pos[q] : ready[sn - 1][q];
+                r = rq > r ? rq : r;
+            }
+            ready[sn][p] = r;
+        }
+    struct Task {
+        int r, sn, p;
+    };
+    std::vector<Task> tasks;
+    for (int sn = 0; sn < nstages; sn++)
+        for (int p = 0; p < np; p++) tasks.push_back(Task{ready[sn][p], sn, p});
+    for (size_t i = 1; i < tasks.size(); i++)
+        for (size_t j = i; j > 0; j--) {
+            const Task &x = tasks[j], &y = tasks[j - 1];
+            const bool less = x.r < y.r || (x.r == y.r && (x.sn < y.sn || (x.sn == y.sn && x.p < y.p)));
+            if (!less) break;
+            std::swap(tasks[j], tasks[j - 1]);
+        }
+    int out_of_stage[3];
     for (int sn = 0; sn < nstages; sn++) {
+        out_of_stage[sn] = stage_output_buffer(L, sn + 1, alpha + sn * nstages);
+        if (out_of_stage[sn] < 0) return set_error(-43, "a third stage needs one alpha == 0 among the older states (three buffers per patch)");
+    }
+    for (const Task& t : tasks) {
+        const int p = t.p, sn = t.sn;
         const double* a = alpha + sn * nstages;
         const double* b = beta + sn * nstages;
-        const bool first = sn == 0, last = sn == nstages - 1;
-        if (!first && L->ndesc) {
-            dim3 grid(8, (unsigned)L->ndesc);
-            k_level_fill<<<grid, 256, 0, L->stream>>>(L->d_desc, L->d_ptrs[L->where[sn]], L->ncomp);
+        if (sn == 0) {
+            HB2L_CUDA(cudaStreamWaitEvent(L->stream, L->ev_up[p], 0));
+            for (int q : L->sources[p]) HB2L_CUDA(cudaStreamWaitEvent(L->stream, L->ev_up[q], 0));
+        }
+        const int nd = L->desc_begin[p + 1] - L->desc_begin[p];
+        if (nd > 0) {
+            dim3 grid(8, (unsigned)nd);
+            k_level_fill<<<grid, 256, 0, L->stream>>>(L->d_desc + L->desc_begin[p], L->d_ptrs[L->where[sn]], L->ncomp);
             L->launches++;
         }
-        const int out = stage_output_buffer(L, sn + 1, a);
-        if (out < 0) return set_error(-43, "a third stage needs one alpha == 0 among the older states (three buffers per patch)");
-        for (int i = 0; i < np; i++) {
-            const int p = first ? order[i] : i;
-            if (first) {
-                HB2L_CUDA(cudaStreamWaitEvent(L->stream, L->ev_up[p], 0));
-                for (int q : L->sources[p]) HB2L_CUDA(cudaStreamWaitEvent(L->stream, L->ev_up[q], 0));
-                const int nd = L->desc_begin[p + 1] - L->desc_begin[p];
-                if (nd > 0) {
-                    dim3 grid(8, (unsigned)nd);
-                    k_level_fill<<<grid, 256, 0, L->stream>>>(L->d_desc + L->desc_begin[p], L->d_ptrs[L->where[0]], L->ncomp);
-                    L->launches++;
-                }
-            }
-            int rc = hb2_level_advance_stage_patch(L, p, sn + 1, a, b, dt);
-            if (rc) return rc;
-            if (last) {
-                const LevelPatch& P = L->patches[p];
-                long long off, cnt;
-                transfer_range(L, P, &off, &cnt);
-                HB2L_CUDA(cudaEventRecord(L->ev_done[p], L->stream));
-                HB2L_CUDA(cudaStreamWaitEvent(L->copy_out, L->ev_done[p], 0));
-                for (int c = 0; c < L->ncomp; c++)
-                    HB2L_CUDA(cudaMemcpyAsync(U_host[(size_t)p * L->ncomp + c] + off, P.S[out] + (size_t)c * P.ncell_g + off,
-                                              sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, L->copy_out));
-            }
-        }
-        int rc = hb2_level_end_stage(L, sn + 1, a, last ? 1 : 0);
+        int rc = hb2_level_advance_stage_patch(L, p, sn + 1, a, b, dt);
         if (rc) return rc;
+        if (sn == nstages - 1) {
+            const LevelPatch& P = L->patches[p];
+            long long off, cnt;
+            transfer_range(L, P, &off, &cnt);
+            HB2L_CUDA(cudaEventRecord(L->ev_done[p], L->stream));
+            HB2L_CUDA(cudaStreamWaitEvent(L->copy_out, L->ev_done[p], 0));
+            for (int c = 0; c < L->ncomp; c++)
+                HB2L_CUDA(cudaMemcpyAsync(U_host[(size_t)p * L->ncomp + c] + off, P.S[out_of_stage[sn]] + (size_t)c * P.ncell_g + off,
+                                          sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, L->copy_out));
+        }
     }
     HB2L_CUDA(cudaGetLastError());
     HB2L_CUDA(cudaStreamSynchronize(L->copy_out));
     HB2L_CUDA(cudaStreamSynchronize(L->stream));
+    for (int sn = 0; sn < nstages; sn++) {
+        int rc = hb2_level_end_stage(L, sn + 1, alpha + sn * nstages, sn == nstages - 1 ? 1 : 0);
+        if (rc) return rc;
+    }
     return 0;
 }
 
