@@ -655,7 +655,7 @@ def main():
     ap.add_argument("--ref-size", type=int, default=128)
     ap.add_argument("--e2e-size", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-patches", type=int, default=8, help="N = 1 e2e: cut the host box into this many z slabs (1: one patch, unpipelined)")
+    ap.add_argument("--e2e-patches", type=int, default=16, help="N = 1 e2e: cut the host box into this many z slabs (1: one patch, unpipelined)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
