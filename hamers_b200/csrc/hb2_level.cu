@@ -462,11 +462,40 @@ int hb2_level_advance_host(hb2_level_t L, int32_t nstages, const double* alpha, 
     if (wrap) uorder.push_back(np - 1);
     for (int p = 0; p < np - (wrap ? 1 : 0); p++) uorder.push_back(p);
     for (int i = 0; i < np; i++) pos[uorder[i]] = i;
+    /* When every patch spans the level in all but the slowest direction (a stack of slabs), a patch's ghost cells come from
+     * the FIRST and LAST g interior planes of its neighbours only: those few planes of every patch are uploaded first, so the
+     * first stage of a patch waits for its own bulk alone and the wavefront trails the upload by one slab per stage less. */
+    bool slabs = np > 1;
+    for (int p = 0; p < np && slabs; p++)
+        for (int a = 0; a < L->dim - 1; a++) slabs = slabs && L->patches[p].n[a] == L->level_n[a];
+    for (int p = 0; p < np && slabs; p++) slabs = L->patches[p].n[L->dim - 1] > 2 * L->g;
+    if (slabs) {
+        for (int p = 0; p < np; p++) {
+            const LevelPatch& P = L->patches[p];
+            long long off, cnt;
+            transfer_range(L, P, &off, &cnt);
+            const long long plane = cnt / P.n[L->dim - 1], edge = plane * L->g;
+            for (int c = 0; c < L->ncomp; c++) {
+                double* dst = P.S[L->where[0]] + (size_t)c * P.ncell_g;
+                const double* src = U_host[(size_t)p * L->ncomp + c];
+                HB2L_CUDA(cudaMemcpyAsync(dst + off, src + off, sizeof(double) * (size_t)edge, cudaMemcpyHostToDevice, L->copy_in));
+                HB2L_CUDA(cudaMemcpyAsync(dst + off + cnt - edge, src + off + cnt - edge, sizeof(double) * (size_t)edge,
+                                          cudaMemcpyHostToDevice, L->copy_in));
+            }
+        }
+        HB2L_CUDA(cudaEventRecord(L->ev_done[0], L->copy_in));        /* borrowed as "all edge planes are on the device" */
+        HB2L_CUDA(cudaStreamWaitEvent(L->stream, L->ev_done[0], 0));
+    }
     for (int i = 0; i < np; i++) {
         const int p = uorder[i];
         const LevelPatch& P = L->patches[p];
         long long off, cnt;
         transfer_range(L, P, &off, &cnt);
+        if (slabs) {
+            const long long edge = cnt / P.n[L->dim - 1] * L->g;
+            off += edge;
+            cnt -= 2 * edge;
+        }
         for (int c = 0; c < L->ncomp; c++)
             HB2L_CUDA(cudaMemcpyAsync(P.S[L->where[0]] + (size_t)c * P.ncell_g + off, U_host[(size_t)p * L->ncomp + c] + off,
                                       sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice, L->copy_in));
@@ -477,10 +506,11 @@ int hb2_level_advance_host(hb2_level_t L, int32_t nstages, const double* alpha, 
     for (int sn = 0; sn < nstages; sn++)
         for (int p = 0; p < np; p++) {
             int r = sn == 0 ? pos[p] : ready[sn - 1][p];
-            for (int q : L->sources[p]) {
-                const int rq = sn == 0 ? pos[q] : ready[sn - 1][q];
-                r = rq > r ? rq : r;
-            }
+            if (sn > 0 || !slabs)
+                for (int q : L->sources[p]) {
+                    const int rq = sn == 0 ? pos[q] : ready[sn - 1][q];
+                    r = rq > r ? rq : r;
+                }
             ready[sn][p] = r;
         }
     struct Task {
@@ -507,7 +537,8 @@ int hb2_level_advance_host(hb2_level_t L, int32_t nstages, const double* alpha, 
         const double* b = beta + sn * nstages;
         if (sn == 0) {
             HB2L_CUDA(cudaStreamWaitEvent(L->stream, L->ev_up[p], 0));
-            for (int q : L->sources[p]) HB2L_CUDA(cudaStreamWaitEvent(L->stream, L->ev_up[q], 0));
+            if (!slabs)
+                for (int q : L->sources[p]) HB2L_CUDA(cudaStreamWaitEvent(L->stream, L->ev_up[q], 0));
         }
         const int nd = L->desc_begin[p + 1] - L->desc_begin[p];
         if (nd > 0) {
