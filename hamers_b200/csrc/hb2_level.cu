@@ -14,6 +14,7 @@
  */
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -84,6 +85,11 @@ struct hb2_level_s {
     std::vector<std::vector<int>> sources;      /* patches whose data the ghost fill of patch p reads */
     cudaStream_t copy_in, copy_out;
     std::vector<cudaEvent_t> ev_up, ev_done;
+    /* second compute stream with its own plans (a plan owns the running right-hand side and the sensor bytes of the stage in
+     * flight): tasks of even / odd patches alternate between the two, so that the tails of the small grids of thin slabs overlap */
+    cudaStream_t stream2;
+    std::vector<hb2_plan_t> plans2;
+    std::vector<cudaEvent_t> ev_task;           /* [stage * npatch + patch] */
 };
 
 namespace {
@@ -194,6 +200,7 @@ int hb2_level_create(const hb2_patch_desc* model, int32_t npatch, const int32_t*
     L->d_sr = nullptr;
     L->launches = 0;
     L->copy_in = L->copy_out = nullptr;
+    L->stream2 = nullptr;
     for (int b = 0; b < 3; b++) {
         L->where[b] = b;
         L->d_ptrs[b] = nullptr;
@@ -283,6 +290,9 @@ int hb2_level_destroy(hb2_level_t L)
     for (int b = 0; b < 3; b++) cudaFree(L->d_ptrs[b]);
     cudaFree(L->d_desc);
     cudaFree(L->d_sr);
+    for (auto e : L->ev_task) cudaEventDestroy(e);
+    for (auto plan : L->plans2) hb2_plan_destroy(plan);
+    if (L->stream2) cudaStreamDestroy(L->stream2);
     for (auto e : L->ev_up) cudaEventDestroy(e);
     for (auto e : L->ev_done) cudaEventDestroy(e);
     if (L->copy_in) cudaStreamDestroy(L->copy_in);
@@ -299,6 +309,7 @@ int64_t hb2_level_launch_count(hb2_level_t L)
     if (!L) return -1;
     long long n = L->launches;
     for (auto plan : L->plans) n += hb2_plan_launch_count(plan);
+    for (auto plan : L->plans2) n += hb2_plan_launch_count(plan);
     return n;
 }
 
@@ -378,6 +389,19 @@ int stage_output_buffer(hb2_level_t L, int ncoef, const double* alpha)
 
 /* computeFluxesAndSourcesOnPatch + advanceSingleStepOnPatch of ONE patch for RK stage ncoef - 1 (fused; the flux is taken of
  * U^(ncoef - 1), whose ghosts must be filled: hb2_level_fill_ghosts(L, ncoef - 1)) */
+static int advance_stage_patch_on(hb2_level_t L, int patch, int ncoef, const double* alpha, const double* beta, double dt, hb2_plan_t plan)
+{
+    const int out = stage_output_buffer(L, ncoef, alpha);
+    if (out < 0) return set_error(-43, "a third stage needs one alpha == 0 among the older states (three buffers per patch)");
+    const LevelPatch& P = L->patches[patch];
+    const double* Uint[3 * HB2_MAX_COMP];
+    double* Uout[HB2_MAX_COMP];
+    for (int m = 0; m < ncoef; m++)
+        for (int c = 0; c < L->ncomp; c++) Uint[m * L->ncomp + c] = P.S[L->where[m]] + (size_t)c * P.ncell_g;
+    for (int c = 0; c < L->ncomp; c++) Uout[c] = P.S[out] + (size_t)c * P.ncell_g;
+    return hb2_fused_stage_dev(plan, ncoef, alpha, beta, Uint, dt, Uout);
+}
+
 int hb2_level_advance_stage_patch(hb2_level_t L, int32_t patch, int32_t ncoef, const double* alpha, const double* beta, double dt)
 {
     if (!L || !alpha || !beta) return set_error(-1, "hb2_level_advance_stage_patch: null argument");
@@ -531,28 +555,63 @@ int hb2_level_advance_host(hb2_level_t L, int32_t nstages, const double* alpha, 
         out_of_stage[sn] = stage_output_buffer(L, sn + 1, alpha + sn * nstages);
         if (out_of_stage[sn] < 0) return set_error(-43, "a third stage needs one alpha == 0 among the older states (three buffers per patch)");
     }
+    /* two compute streams (HB2_LEVEL_STREAMS=1 keeps one): the second one with its own plans, created on first use */
+    static const int nstreams = [] {
+        const char* v = getenv("HB2_LEVEL_STREAMS");
+        return (v && *v) ? atoi(v) : 2;
+    }();
+    const bool two = nstreams > 1 && np > 1;
+    if (two && !L->stream2) {
+        HB2L_CUDA(cudaStreamCreateWithFlags(&L->stream2, cudaStreamNonBlocking));
+        for (size_t k = 0; k < L->shapes.size(); k++) {
+            hb2_patch_desc d = L->model;
+            for (int a = 0; a < 3; a++) d.n[a] = L->shapes[k][a];
+            d.device = L->device;
+            hb2_plan_t plan = nullptr;
+            int rc = hb2_plan_create(&d, &plan);
+            if (rc) return rc;
+            hb2_plan_set_stream(plan, (void*)L->stream2);
+            L->plans2.push_back(plan);
+        }
+        L->ev_task.resize((size_t)3 * np);
+        for (auto& e : L->ev_task) HB2L_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        if (slabs) HB2L_CUDA(cudaStreamWaitEvent(L->stream2, L->ev_done[0], 0));
+    } else if (two && slabs) {
+        HB2L_CUDA(cudaStreamWaitEvent(L->stream2, L->ev_done[0], 0));
+    }
     for (const Task& t : tasks) {
         const int p = t.p, sn = t.sn;
         const double* a = alpha + sn * nstages;
         const double* b = beta + sn * nstages;
+        const bool second = two && (p & 1);
+        cudaStream_t st = second ? L->stream2 : L->stream;
         if (sn == 0) {
-            HB2L_CUDA(cudaStreamWaitEvent(L->stream, L->ev_up[p], 0));
+            HB2L_CUDA(cudaStreamWaitEvent(st, L->ev_up[p], 0));
             if (!slabs)
-                for (int q : L->sources[p]) HB2L_CUDA(cudaStreamWaitEvent(L->stream, L->ev_up[q], 0));
+                for (int q : L->sources[p]) HB2L_CUDA(cudaStreamWaitEvent(st, L->ev_up[q], 0));
+        } else if (two) {
+            /* stage sn of patch p reads stage sn - 1 of p and of its sources; those on the other stream need an event */
+            for (int q : L->sources[p])
+                if (((q & 1) != 0) != second) HB2L_CUDA(cudaStreamWaitEvent(st, L->ev_task[(size_t)(sn - 1) * np + q], 0));
+        }
+        if (two && sn == nstages - 1 && nstages == 3) {
+            /* the last stage overwrites U^(1) of p, which the second stage of p's neighbours read (ghost fill): those on the
+             * same stream are ordered, those on the other stream are the sources handled above (stage sn - 1 = second stage) */
         }
         const int nd = L->desc_begin[p + 1] - L->desc_begin[p];
         if (nd > 0) {
             dim3 grid(8, (unsigned)nd);
-            k_level_fill<<<grid, 256, 0, L->stream>>>(L->d_desc + L->desc_begin[p], L->d_ptrs[L->where[sn]], L->ncomp);
+            k_level_fill<<<grid, 256, 0, st>>>(L->d_desc + L->desc_begin[p], L->d_ptrs[L->where[sn]], L->ncomp);
             L->launches++;
         }
-        int rc = hb2_level_advance_stage_patch(L, p, sn + 1, a, b, dt);
+        int rc = advance_stage_patch_on(L, p, sn + 1, a, b, dt, second ? L->plans2[L->patches[p].shape] : L->plans[L->patches[p].shape]);
         if (rc) return rc;
+        if (two) HB2L_CUDA(cudaEventRecord(L->ev_task[(size_t)sn * np + p], st));
         if (sn == nstages - 1) {
             const LevelPatch& P = L->patches[p];
             long long off, cnt;
             transfer_range(L, P, &off, &cnt);
-            HB2L_CUDA(cudaEventRecord(L->ev_done[p], L->stream));
+            HB2L_CUDA(cudaEventRecord(L->ev_done[p], st));
             HB2L_CUDA(cudaStreamWaitEvent(L->copy_out, L->ev_done[p], 0));
             for (int c = 0; c < L->ncomp; c++)
                 HB2L_CUDA(cudaMemcpyAsync(U_host[(size_t)p * L->ncomp + c] + off, P.S[out_of_stage[sn]] + (size_t)c * P.ncell_g + off,
@@ -562,6 +621,7 @@ int hb2_level_advance_host(hb2_level_t L, int32_t nstages, const double* alpha, 
     HB2L_CUDA(cudaGetLastError());
     HB2L_CUDA(cudaStreamSynchronize(L->copy_out));
     HB2L_CUDA(cudaStreamSynchronize(L->stream));
+    if (L->stream2) HB2L_CUDA(cudaStreamSynchronize(L->stream2));
     for (int sn = 0; sn < nstages; sn++) {
         int rc = hb2_level_end_stage(L, sn + 1, alpha + sn * nstages, sn == nstages - 1 ? 1 : 0);
         if (rc) return rc;

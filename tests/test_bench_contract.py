@@ -49,3 +49,25 @@ def test_committed_gpu_line_has_the_contract_keys():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
     assert d["gpu_launches"] > 0 and d["clocks"]["reasons"] == []
+
+
+def test_committed_round_2_lines_carry_parity_and_secondary():
+    """Round 2: every line has a `parity` block (error norms against the exact solution + bit checksum); multi-GPU lines say
+    whether the checksum equals the one-box replica's; the N = 1 line carries the secondary measurements."""
+    def load(name):
+        with open(os.path.join(ROOT, "profiles", name)) as fh:
+            return json.loads(fh.read().strip().splitlines()[-1])
+
+    one = load("r02_d_bench_512.json")
+    assert BASE_KEYS <= set(one) and one["n_gpus"] == 1
+    assert {"ns", "ns_wcns6ld", "shock", "fe"} <= set(one["secondary"])
+    assert one["parity"]["matches_n1"] is True and one["parity"]["L1_error"] < 1e-12
+    for name, n in (("r02_b_bench_512_2gpu.json", 2), ("r02_m_bench_512_4gpu.json", 4), ("r02_f_bench_512_8gpu.json", 8)):
+        d = load(name)
+        assert d["n_gpus"] == n and d["scaling"] == "strong"
+        p = d["parity"]
+        assert p["matches_n1"] is True and p["checksum"] == p["n1_checksum"] == one["parity"]["checksum"]
+        assert p["L1_error"] == one["parity"]["L1_error"]
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["clocks"]["reasons"] == []
+    eight = load("r02_f_bench_512_8gpu.json")
+    assert eight["secondary"]["ns"]["checksum"] == one["secondary"]["ns"]["checksum"]      # Navier-Stokes: same bits on 8 GPUs
