@@ -538,7 +538,20 @@ def run_ours(args):
         torch.cuda.empty_cache()
         hnp = host.numpy()
         dte = 0.001 * domain_len / n
-        npz = args.e2e_patches if (args.e2e_patches > 1 and n % args.e2e_patches == 0 and n // args.e2e_patches >= 16) else 1
+        # slab thicknesses along z.  0 (default): graded -- thick slabs where the wavefront runs freely, thin ones around the
+        # periodic seam (the slabs uploaded last and their neighbours finish after the upload has ended: their download is the
+        # tail of the step, so they are cut thin); K > 1: K equal slabs; 1: one patch through hb2_advance_level_host
+        if args.e2e_patches == 0 and n % 32 == 0 and (n - 5 * (n // 32)) % 6 == 0 and n // 32 >= 12:
+            thin = n // 32
+            thick = (n - 5 * thin) // 6
+            sizes = [thin] + [thick] * 6 + [thin] * 4
+        elif args.e2e_patches > 1 and n % args.e2e_patches == 0 and n // args.e2e_patches >= 16:
+            sizes = [n // args.e2e_patches] * args.e2e_patches
+        elif args.e2e_patches == 0 and n % 8 == 0 and n // 8 >= 16:
+            sizes = [n // 8] * 8
+        else:
+            sizes = [n]
+        npz = len(sizes)
         if npz == 1:
             for _ in range(1):
                 plan.advance_level_host(hnp, dte)
@@ -555,14 +568,14 @@ def run_ours(args):
             # the host box as npz slabs along z (what a SAMRAI level of several patches per rank looks like): the uploads of the
             # later slabs overlap the first stage of the earlier ones, the downloads overlap the last stage (hb2_level_advance_host)
             plan.close()
-            nzp = n // npz
-            boxes = [((0, 0, k * nzp), (n, n, (k + 1) * nzp)) for k in range(npz)]
+            zlo = [sum(sizes[:k]) for k in range(npz)]
+            boxes = [((0, 0, zlo[k]), (n, n, zlo[k] + sizes[k])) for k in range(npz)]
             lvl = abi.DeviceLevel(3, boxes, (n, n, n), flow_model=flow_model, species_gamma=gam, dx=(domain_len / n,) * 3, math=math,
                                   scheme=scheme)
             slabs = []
             for k in range(npz):
-                t = torch.empty((ncomp, nzp + 8, n + 8, n + 8), dtype=torch.float64).pin_memory()
-                t[:, 4:-4].copy_(host[:, 4 + k * nzp:4 + (k + 1) * nzp])
+                t = torch.empty((ncomp, sizes[k] + 8, n + 8, n + 8), dtype=torch.float64).pin_memory()
+                t[:, 4:-4].copy_(host[:, 4 + zlo[k]:4 + zlo[k] + sizes[k]])
                 slabs.append(t)
             del host, hnp
             arrs = [t.numpy() for t in slabs]
@@ -574,8 +587,9 @@ def run_ours(args):
             el = time.perf_counter() - t0
             nbytes = ncomp * n * (n + 8) * (n + 8) * 8
             launches = lvl.launch_count - k0
-            api = (f"hb2_level_advance_host: the host box as {npz} z-slab patches in pinned memory; per step H2D of every slab, 3 stages "
-                   "on the device-resident level, D2H of every slab; uploads overlap the first stage, downloads the last")
+            api = (f"hb2_level_advance_host: the host box as {npz} z-slab patches (planes per slab: {sizes}) in pinned memory; per step "
+                   "H2D of every slab, 3 stages on the device-resident level as a wavefront of (slab, stage) tasks behind the uploads, "
+                   "D2H of every slab as soon as it is done (full-duplex PCIe)")
             fin = all(bool(np.isfinite(a[:, 4:-4, 4:-4, 4:-4]).all()) for a in arrs[:1])
             lvl.close()
         line["e2e"] = {"value": n ** 3 * 3 * args.e2e_steps / el, "unit": "cell-updates/s",
@@ -655,7 +669,8 @@ def main():
     ap.add_argument("--ref-size", type=int, default=128)
     ap.add_argument("--e2e-size", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-patches", type=int, default=16, help="N = 1 e2e: cut the host box into this many z slabs (1: one patch, unpipelined)")
+    ap.add_argument("--e2e-patches", type=int, default=0,
+                    help="N = 1 e2e: 0 = graded z slabs (thin around the periodic seam), K > 1 = K equal slabs, 1 = one patch, unpipelined")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
