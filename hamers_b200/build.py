@@ -37,7 +37,7 @@ UNITS = [
     ("hb2_amr.o", "hb2_amr.cu", ["-fmad=false"]),
     ("hb2_level.o", "hb2_level.cu", ["-fmad=false"]),
 ]
-DEPS = ["hb2_core.cuh", "hb2_fast.cuh", "hb2_sweep.cuh", "hb2_sensor.cuh", "hb2_ops.h", "hb2_sweeps.cu", "hb2_abi.cu", "hb2_diffusive.cu", "hb2_diffusive.cuh", "hb2_amr.cu", "hb2_amr.cuh", "hb2_level.cu", os.path.join(ROOT, "include", "hamers_b200.h")]
+DEPS = ["hb2_diffusive_march.cuh", "hb2_core.cuh", "hb2_fast.cuh", "hb2_sweep.cuh", "hb2_sensor.cuh", "hb2_ops.h", "hb2_sweeps.cu", "hb2_abi.cu", "hb2_diffusive.cu", "hb2_diffusive.cuh", "hb2_amr.cu", "hb2_amr.cuh", "hb2_level.cu", os.path.join(ROOT, "include", "hamers_b200.h")]
 
 
 def _mtime(p):

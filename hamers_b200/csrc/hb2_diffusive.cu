@@ -18,6 +18,7 @@
  */
 #include "../../include/hamers_b200.h"
 #include "hb2_diffusive.cuh"
+#include "hb2_diffusive_march.cuh"
 
 #include <cuda_runtime.h>
 #include <cstdlib>
@@ -49,7 +50,9 @@ struct hb2_diff_plan_s {
     double* stF[15];
     long long nside[3];
     long long launches;
-    int tiled;                    /* 3-D: marching tiled kernels, HB2_DIFF_TILED=1 (measured slower than the grid-stride forms) */
+    int math;                     /* arithmetic of the flux-free route: HB2_MATH_EXACT (default) / HB2_MATH_FAST */
+    int marching;                 /* 3-D: marching kernels with an asynchronous load pipeline (hb2_diffusive_march.cuh; HB2_DIFF_MARCH,
+                                     default 1); 0: the grid-stride forms */
     int bricks;                   /* 3-D: 32 x 4 x 2 brick index map of the grid-stride kernels (HB2_DIFF_BRICKS, default 1) */
 };
 
@@ -133,12 +136,41 @@ __global__ void __launch_bounds__(256) k_advance_ns(const __grid_constant__ NsAr
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) advance_ns_thread<DIM>(A, t);
 }
 
+/* ghost cells only: the 2 g_z full planes, then the 2 g_y rows of every interior plane, then the 2 g_x cells of every interior
+ * row (a loop over the whole ghost box spends most of its threads on interior cells: 0.14 ms at 256^3 for 3 % of the cells) */
+__host__ __device__ inline long long fill_ghost_count(const DiffGeom& G)
+{
+    return 2LL * G.g[2] * G.gd[0] * G.gd[1] + (long long)G.n[2] * 2 * G.g[1] * G.gd[0] + (long long)G.n[2] * G.n[1] * 2 * G.g[0];
+}
 __global__ void __launch_bounds__(256) k_diff_fill_periodic(const __grid_constant__ DiffGeom G, const __grid_constant__ DiffStatePtrs A,
                                                             int ncomp, int mask)
 {
+    const long long nz = 2LL * G.g[2] * G.gd[0] * G.gd[1], ny = (long long)G.n[2] * 2 * G.g[1] * G.gd[0];
+    const long long total = fill_ghost_count(G);
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < G.ncell_g; t += stride)
-        diff_fill_periodic_thread(G, A, ncomp, mask, t);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        int i, j, k;                                     /* ghost-box indices */
+        if (t < nz) {
+            const int p = (int)(t / ((long long)G.gd[0] * G.gd[1]));
+            const int r = (int)(t % ((long long)G.gd[0] * G.gd[1]));
+            k = p < G.g[2] ? p : p + G.n[2];
+            j = r / G.gd[0];
+            i = r % G.gd[0];
+        } else if (t < nz + ny) {
+            const long long u = t - nz;
+            const int r = (int)((u / G.gd[0]) % (2 * G.g[1]));
+            k = G.g[2] + (int)(u / ((long long)2 * G.g[1] * G.gd[0]));
+            j = r < G.g[1] ? r : r + G.n[1];
+            i = (int)(u % G.gd[0]);
+        } else {
+            const long long u = t - nz - ny;
+            const int c = (int)(u % (2 * G.g[0]));
+            k = G.g[2] + (int)(u / ((long long)2 * G.g[0] * G.n[1]));
+            j = G.g[1] + (int)((u / (2 * G.g[0])) % G.n[1]);
+            i = c < G.g[0] ? c : c + G.n[0];
+        }
+        diff_fill_periodic_thread(G, A, ncomp, mask, i + G.cs[1] * j + G.cs[2] * k);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_diff_extract_view(const __grid_constant__ DiffGeom Gs, const __grid_constant__ DiffGeom Gd,
@@ -166,224 +198,6 @@ __global__ void __launch_bounds__(256) k_diff_divergence_accumulate(const __grid
         diff_divergence_accumulate_thread<DIM>(A, t);
 }
 
-/* ---- tiled 3-D kernels of the node stage and of the flux-free update -------------------------------------------------------
- * The grid-stride forms above leave every stencil load to L1/L2 (ncu, 256^3: k_diff_node_all 1.06 ms at 44 % of HBM,
- * k_diff_divergence_accumulate 1.50 ms at 28 %, both > 75 % long-scoreboard stalls).  Here a 32 x 8 thread block owns a
- * 32 x 8 column of nodes (cells) and MARCHES along z: values along z live in a per-thread register ring of seven planes,
- * values of the current plane in a shared-memory tile with a halo of three, the next plane's global loads are issued
- * before the current plane is processed.  Same operations in the same order as the grid-stride kernels: bit-identical.
- *
- * k_diff_node_tiled: conservative variables in (the primitives never reach HBM: k_diff_primitives is fused away), the
- * twelve node-flux arrays out.  Algorithmic traffic 40 B read (+ halo re-reads from L2) + 96 B written per node. */
-constexpr int TX = 32, TY = 8, HALO = 3;
-constexpr int SX = TX + 2 * HALO, SY = TY + 2 * HALO;          /* 38 x 14 halo tile */
-constexpr int NHALO = SX * SY - TX * TY;                       /* 276 halo cells per plane */
-
-__device__ __forceinline__ void halo_cell(int h, int& hx, int& hy)
-{
-    /* h-th halo cell of the 38 x 14 tile: the three full rows below, the three above, then the side columns */
-    if (h < HALO * SX) {
-        hx = h % SX;
-        hy = h / SX;
-    } else if (h < 2 * HALO * SX) {
-        const int q = h - HALO * SX;
-        hx = q % SX;
-        hy = TY + HALO + q / SX;
-    } else {
-        const int q = h - 2 * HALO * SX;
-        const int row = q / (2 * HALO), c = q % (2 * HALO);
-        hy = HALO + row;
-        hx = (c < HALO) ? c : TX + c;
-    }
-}
-
-__global__ void __launch_bounds__(256, 2) k_diff_node_tiled(const __grid_constant__ DiffGeom G, const __grid_constant__ DiffConsts K,
-                                                            const __grid_constant__ DiffPtrs Q, const __grid_constant__ DiffAllPtrs A)
-{
-    __shared__ double sP[4][SY][SX];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    /* node coordinates of the tile origin in the domain extended by three (nodes -3 .. n + 2) */
-    const int i0 = (int)blockIdx.x * TX - 3, j0 = (int)blockIdx.y * TY - 3;
-    const int i = i0 + tx, j = j0 + ty;
-    const bool own = i < G.n[0] + 3 && j < G.n[1] + 3;           /* the node exists */
-    const bool cell = i < G.n[0] + 6 && j < G.n[1] + 6;          /* the cell exists (a neighbour of an existing node may not be a node) */
-    const int kz_lo = -3, kz_hi = G.n[2] + 3;
-    const long long col = (i + G.g[0]) + G.cs[1] * (j + G.g[1]);
-    /* halo cells this thread converts: h = tid and tid + 256 */
-    int hx[2], hy[2];
-    bool hok[2];
-    long long hcol[2];
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-        const int h = (int)threadIdx.x + 256 * r;
-        hok[r] = h < NHALO;
-        hx[r] = hy[r] = 0;
-        if (hok[r]) halo_cell(h, hx[r], hy[r]);
-        const int ci = i0 - HALO + hx[r], cj = j0 - HALO + hy[r];
-        hok[r] = hok[r] && ci < G.n[0] + 6 && cj < G.n[1] + 6;      /* inside the ghost box (>= -6 by construction) */
-        hcol[r] = (ci + G.g[0]) + G.cs[1] * (cj + G.g[1]);
-    }
-    auto load_prims = [&](long long x, double (&P)[4]) {
-        double q[5];
-#pragma unroll
-        for (int c = 0; c < 5; c++) q[c] = Q.Q[c][x];
-        diff_primitives<3>(q, K, P);
-    };
-    /* register ring: ring[v][m] = primitive v of the own column at plane kz - 3 + m */
-    double ring[4][7];
-#pragma unroll
-    for (int v = 0; v < 4; v++)
-#pragma unroll
-        for (int m = 0; m < 7; m++) ring[v][m] = 0.0;
-    if (cell) {
-#pragma unroll
-        for (int m = 1; m < 7; m++) {           /* planes kz_lo - 3 + (m - 1) .. : after the first shift they sit at m - 1 */
-            double P[4];
-            load_prims(col + G.cs[2] * (kz_lo - 3 + (m - 1) + G.g[2]), P);
-#pragma unroll
-            for (int v = 0; v < 4; v++) ring[v][m] = P[v];
-        }
-    }
-    for (int kz = kz_lo; kz < kz_hi; kz++) {
-        /* shift the ring and take in plane kz + 3 */
-#pragma unroll
-        for (int v = 0; v < 4; v++)
-#pragma unroll
-            for (int m = 0; m < 6; m++) ring[v][m] = ring[v][m + 1];
-        if (cell) {
-            double P[4];
-            load_prims(col + G.cs[2] * (kz + 3 + G.g[2]), P);
-#pragma unroll
-            for (int v = 0; v < 4; v++) ring[v][6] = P[v];
-        }
-        /* the plane of the nodes: own cell from the ring, halo cells from global memory */
-        if (cell) {
-#pragma unroll
-            for (int v = 0; v < 4; v++) sP[v][ty + HALO][tx + HALO] = ring[v][3];
-        }
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            if (hok[r]) {
-                double P[4];
-                load_prims(hcol[r] + G.cs[2] * (kz + G.g[2]), P);
-#pragma unroll
-                for (int v = 0; v < 4; v++) sP[v][hy[r]][hx[r]] = P[v];
-            }
-        }
-        __syncthreads();
-        if (own) {
-            double der[4][3];
-#pragma unroll
-            for (int v = 0; v < 4; v++) {
-                const double* c = &sP[v][ty + HALO][tx + HALO];
-                der[v][0] = diff_first_derivative6(c[-3], c[-2], c[-1], c[1], c[2], c[3], G.dx_inv[0]);
-                der[v][1] = diff_first_derivative6(c[-3 * SX], c[-2 * SX], c[-SX], c[SX], c[2 * SX], c[3 * SX], G.dx_inv[1]);
-                der[v][2] = diff_first_derivative6(ring[v][0], ring[v][1], ring[v][2], ring[v][4], ring[v][5], ring[v][6], G.dx_inv[2]);
-            }
-            const double vel[3] = {ring[0][3], ring[1][3], ring[2][3]};
-            double Fn[3][5];
-            diff_node_flux_from_derivatives<3>(K, vel, der, Fn);
-            const long long x = col + G.cs[2] * (kz + G.g[2]);
-#pragma unroll
-            for (int f = 0; f < 3; f++)
-#pragma unroll
-                for (int e = 1; e < 5; e++) A.Fn[f][e][x] = Fn[f][e];
-        }
-        __syncthreads();
-    }
-}
-
-/* k_diff_div_tiled: U += beta (-div F_d) from the node fluxes of the three directions; F^z along z in a register ring,
- * F^x / F^y of the current plane in shared-memory tiles with a halo of three along their own direction.  Algorithmic
- * traffic 96 B of node fluxes + 64 B read-modify-write of the state per cell. */
-__global__ void __launch_bounds__(256, 2) k_diff_div_tiled(const __grid_constant__ NsDivArgs A)
-{
-    __shared__ double sX[4][TY][SX];
-    __shared__ double sY[4][SY][TX];
-    const DiffGeom &G = A.G6, &GU = A.GU;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int i0 = (int)blockIdx.x * TX, j0 = (int)blockIdx.y * TY;
-    const int i = i0 + tx, j = j0 + ty;
-    const bool own = i < G.n[0] && j < G.n[1];
-    const bool cx_ok = i < G.n[0] + 3 && j < G.n[1];             /* nodes beside the last cells are somebody's neighbours */
-    const bool cy_ok = i < G.n[0] && j < G.n[1] + 3;
-    const long long col = (i + G.g[0]) + G.cs[1] * (j + G.g[1]);
-    const long long colU = (i + GU.g[0]) + GU.cs[1] * (j + GU.g[1]);
-    /* halo loads of this thread: x halo 6 x 8 = 48 cells (threads 0..47), y halo 6 x 32 = 192 cells (threads 48..239) */
-    const int t = (int)threadIdx.x;
-    const bool hx_on = t < 2 * HALO * TY;
-    const int hxr = t / (2 * HALO), hxc = t % (2 * HALO);                  /* row, column index 0..5 */
-    const int hx_s = (hxc < HALO) ? hxc : TX + hxc;                          /* position in the 38-wide row */
-    const int hx_i = i0 - HALO + hx_s, hx_j = j0 + hxr;
-    const bool hx_ok = hx_on && hx_i < G.n[0] + 3 && hx_j < G.n[1];
-    const long long hx_col = (hx_i + G.g[0]) + G.cs[1] * (hx_j + G.g[1]);
-    const int u = t - 2 * HALO * TY;
-    const bool hy_on = u >= 0 && u < 2 * HALO * TX;
-    const int hyr = hy_on ? u / TX : 0, hyc = hy_on ? u % TX : 0;           /* halo row 0..5, column */
-    const int hy_s = (hyr < HALO) ? hyr : TY + hyr;                          /* position in the 14-high column */
-    const int hy_i = i0 + hyc, hy_j = j0 - HALO + hy_s;
-    const bool hy_ok = hy_on && hy_i < G.n[0] && hy_j < G.n[1] + 3;
-    const long long hy_col = (hy_i + G.g[0]) + G.cs[1] * (hy_j + G.g[1]);
-
-    double ring[4][7];                       /* F^z of equation e + 1 at planes k - 3 + m */
-#pragma unroll
-    for (int e = 0; e < 4; e++)
-#pragma unroll
-        for (int m = 0; m < 7; m++) ring[e][m] = 0.0;
-    if (own) {
-#pragma unroll
-        for (int m = 1; m < 7; m++)
-#pragma unroll
-            for (int e = 0; e < 4; e++) ring[e][m] = A.Fn[2][e + 1][col + G.cs[2] * (-3 + (m - 1) + G.g[2])];
-    }
-    for (int k = 0; k < G.n[2]; k++) {
-        const long long zoff = G.cs[2] * (k + G.g[2]);
-#pragma unroll
-        for (int e = 0; e < 4; e++)
-#pragma unroll
-            for (int m = 0; m < 6; m++) ring[e][m] = ring[e][m + 1];
-        if (own) {
-#pragma unroll
-            for (int e = 0; e < 4; e++) ring[e][6] = A.Fn[2][e + 1][col + G.cs[2] * (k + 3 + G.g[2])];
-        }
-        if (cx_ok) {
-#pragma unroll
-            for (int e = 0; e < 4; e++) sX[e][ty][tx + HALO] = A.Fn[0][e + 1][col + zoff];
-        }
-        if (cy_ok) {
-#pragma unroll
-            for (int e = 0; e < 4; e++) sY[e][ty + HALO][tx] = A.Fn[1][e + 1][col + zoff];
-        }
-        if (hx_ok) {
-#pragma unroll
-            for (int e = 0; e < 4; e++) sX[e][hxr][hx_s] = A.Fn[0][e + 1][hx_col + zoff];
-        }
-        if (hy_ok) {
-#pragma unroll
-            for (int e = 0; e < 4; e++) sY[e][hy_s][hyc] = A.Fn[1][e + 1][hy_col + zoff];
-        }
-        __syncthreads();
-        if (own) {
-            const long long xu = colU + GU.cs[2] * (k + GU.g[2]);
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const double* cx = &sX[e][ty][tx + HALO];
-                const double* cy = &sY[e][ty + HALO][tx];
-                const double FxL = diff_reconstruct6(cx[-3], cx[-2], cx[-1], cx[0], cx[1], cx[2], A.dt);
-                const double FxR = diff_reconstruct6(cx[-2], cx[-1], cx[0], cx[1], cx[2], cx[3], A.dt);
-                const double FyB = diff_reconstruct6(cy[-3 * TX], cy[-2 * TX], cy[-TX], cy[0], cy[TX], cy[2 * TX], A.dt);
-                const double FyT = diff_reconstruct6(cy[-2 * TX], cy[-TX], cy[0], cy[TX], cy[2 * TX], cy[3 * TX], A.dt);
-                double div = -(FxR - FxL) / G.dx[0] - (FyT - FyB) / G.dx[1];
-                const double FzB = diff_reconstruct6(ring[e][0], ring[e][1], ring[e][2], ring[e][3], ring[e][4], ring[e][5], A.dt);
-                const double FzF = diff_reconstruct6(ring[e][1], ring[e][2], ring[e][3], ring[e][4], ring[e][5], ring[e][6], A.dt);
-                div -= (FzF - FzB) / G.dx[2];
-                A.U[e + 1][xu] += A.beta * div;
-            }
-        }
-        __syncthreads();
-    }
-}
-
 /* max over the ghost box of the diffusive spectral radius.  Non-negative doubles order like their bit patterns. */
 template <int DIM>
 __global__ void __launch_bounds__(256) k_diff_spectral_radius(const __grid_constant__ DiffGeom G, const __grid_constant__ DiffConsts K,
@@ -395,6 +209,21 @@ __global__ void __launch_bounds__(256) k_diff_spectral_radius(const __grid_const
         m = fmax(m, diff_spectral_radius_cell<DIM>(G, K, c_p_eos, rho[x]));
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+/* dynamic shared memory of the marching kernels (function attributes are per device) */
+cudaError_t march_attr(int dev)
+{
+    static unsigned long long attr_set = 0;
+    if ((attr_set >> (dev & 63)) & 1ull) return cudaSuccess;
+    const int nb = (int)(march::NODE_SMEM_DOUBLES * sizeof(double)), db = (int)(march::DIV_SMEM_DOUBLES * sizeof(double));
+    cudaError_t e = cudaFuncSetAttribute(march::k_diff_node_march<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, nb);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(march::k_diff_node_march<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, nb);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(march::k_diff_div_march<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, db);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(march::k_diff_div_march<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, db);
+    if (e != cudaSuccess) return e;
+    attr_set |= 1ull << (dev & 63);
+    return cudaSuccess;
 }
 
 int grid_for(long long work, int sm_count)
@@ -417,7 +246,7 @@ int launch_dir(hb2_diff_plan_t p, const DiffPtrs& A, double dt)
 /* primitives, then the node fluxes of all directions in one pass (every derivative evaluated once) into the plan's
  * per-direction scratch sets */
 template <int DIM>
-int node_stage(hb2_diff_plan_t p, const double* const* Q)
+int node_stage(hb2_diff_plan_t p, const double* const* Q, bool fast = false)
 {
     const size_t bytes = sizeof(double) * (size_t)p->G.ncell_g;
     for (int f = 0; f < DIM; f++)
@@ -436,9 +265,18 @@ int node_stage(hb2_diff_plan_t p, const double* const* Q)
     for (int f = 0; f < DIM; f++)
         for (int e = 0; e < DIM + 2; e++) N.Fn[f][e] = p->FnDir[f][e];
     if constexpr (DIM == 3) {
-        if (p->tiled) {
-            dim3 grid((p->G.n[0] + 6 + TX - 1) / TX, (p->G.n[1] + 6 + TY - 1) / TY);
-            k_diff_node_tiled<<<grid, 256, 0, p->stream>>>(p->G, p->K, A, N);
+        if (p->marching) {
+            using namespace march;
+            HB2D_CUDA(march_attr(p->device));
+            dim3 grid((p->G.n[0] + 9 + TX - 1) / TX, (p->G.n[1] + 6 + TY - 1) / TY);
+            const int seg = march_seg_len((long long)grid.x * grid.y, p->G.n[2] + 6, p->sm_count);
+            grid.z = (p->G.n[2] + 6 + seg - 1) / seg;
+            DiffFast FK;
+            make_diff_fast(p->G, p->K, 0.0, 0.0, &FK);
+            if (fast)
+                k_diff_node_march<1><<<grid, NT, NODE_SMEM_DOUBLES * sizeof(double), p->stream>>>(p->G, p->K, FK, A, N, seg);
+            else
+                k_diff_node_march<0><<<grid, NT, NODE_SMEM_DOUBLES * sizeof(double), p->stream>>>(p->G, p->K, FK, A, N, seg);
             p->launches += 1;
             HB2D_CUDA(cudaGetLastError());
             return 0;
@@ -479,7 +317,8 @@ namespace {
 template <int DIM>
 int run_divergence(hb2_diff_plan_t p, const double* const* Q, double dt, int num_ghosts, double beta, double* const* U)
 {
-    int rc = node_stage<DIM>(p, Q);
+    const bool fast = DIM == 3 && p->marching && p->math == HB2_MATH_FAST;
+    int rc = node_stage<DIM>(p, Q, fast);
     if (rc) return rc;
     NsDivArgs D{};
     D.G6 = p->G;
@@ -491,9 +330,18 @@ int run_divergence(hb2_diff_plan_t p, const double* const* Q, double dt, int num
         for (int e = 0; e < DIM + 2; e++) D.Fn[f][e] = p->FnDir[f][e];
     for (int e = 0; e < DIM + 2; e++) D.U[e] = U[e];
     const long long total = (long long)p->G.n[0] * p->G.n[1] * p->G.n[2];
-    if (DIM == 3 && p->tiled) {
+    if (DIM == 3 && p->marching) {
+        using namespace march;
+        HB2D_CUDA(march_attr(p->device));
         dim3 grid((p->G.n[0] + TX - 1) / TX, (p->G.n[1] + TY - 1) / TY);
-        k_diff_div_tiled<<<grid, 256, 0, p->stream>>>(D);
+        const int seg = march_seg_len((long long)grid.x * grid.y, p->G.n[2], p->sm_count);
+        grid.z = (p->G.n[2] + seg - 1) / seg;
+        DiffFast FK;
+        make_diff_fast(p->G, p->K, dt, beta, &FK);
+        if (fast)
+            k_diff_div_march<1><<<grid, NT, DIV_SMEM_DOUBLES * sizeof(double), p->stream>>>(D, FK, seg);
+        else
+            k_diff_div_march<0><<<grid, NT, DIV_SMEM_DOUBLES * sizeof(double), p->stream>>>(D, FK, seg);
     } else if (DIM == 3 && p->bricks) {
         const long long nb = brick_count(p->G.n[0], p->G.n[1], p->G.n[2]);
         k_diff_divergence_accumulate_bricks<<<(unsigned)(nb < p->sm_count * 8LL ? nb : p->sm_count * 8LL), 256, 0, p->stream>>>(D);
@@ -542,9 +390,10 @@ int hb2_diffusive_plan_create(const hb2_diffusive_desc* d, hb2_diff_plan_t* out)
     p->K.kappa = d->species_c_p * d->species_mu / d->species_Pr;      /* EquationOfThermalConductivityPrandtl.cpp:309 */
     p->neq = d->dim + 2;
     p->stream = nullptr;
+    p->math = HB2_MATH_EXACT;
     {
-        const char* v = getenv("HB2_DIFF_TILED");
-        p->tiled = (v && *v) ? atoi(v) : 0;
+        const char* v = getenv("HB2_DIFF_MARCH");
+        p->marching = (v && *v) ? atoi(v) : 1;
         v = getenv("HB2_DIFF_BRICKS");
         p->bricks = (v && *v) ? atoi(v) : 1;
     }
@@ -582,6 +431,14 @@ int hb2_diffusive_plan_set_stream(hb2_diff_plan_t p, void* stream)
 {
     if (!p) return set_error(-1, "null plan");
     p->stream = (cudaStream_t)stream;
+    return 0;
+}
+
+int hb2_diffusive_plan_set_math(hb2_diff_plan_t p, int32_t math)
+{
+    if (!p) return set_error(-1, "null plan");
+    if (math != HB2_MATH_EXACT && math != HB2_MATH_FAST) return set_error(-32, "math must be HB2_MATH_EXACT or HB2_MATH_FAST");
+    p->math = math;
     return 0;
 }
 
@@ -684,7 +541,7 @@ int hb2_diffusive_fill_ghosts_periodic_dev(hb2_diff_plan_t p, double* const* U, 
     HB2D_CUDA(cudaSetDevice(p->device));
     DiffStatePtrs A{};
     for (int c = 0; c < p->neq; c++) A.U[c] = U[c];
-    k_diff_fill_periodic<<<grid_for(p->G.ncell_g, p->sm_count), 256, 0, p->stream>>>(p->G, A, p->neq, periodic_mask);
+    k_diff_fill_periodic<<<grid_for(fill_ghost_count(p->G), p->sm_count), 256, 0, p->stream>>>(p->G, A, p->neq, periodic_mask);
     p->launches++;
     HB2D_CUDA(cudaGetLastError());
     return 0;

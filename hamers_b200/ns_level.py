@@ -57,6 +57,8 @@ class NavierStokesLevel:
                               num_ghosts=abi.DIFF_GHOSTS).use_torch_stream()
         self.dplan = abi.DiffusivePlan(dim, self.n, self.dx, species_gamma, c_v, species_mu, species_mu_v, species_c_p,
                                        species_Pr).use_torch_stream()
+        if math == abi.MATH_FAST:
+            self.dplan.set_math(abi.MATH_FAST)      # the flux-free update in re-associated arithmetic (<= 1e-12)
         self.device = device            # "cuda"; the CPU test suite drives the same loop over emulation-backed plans
         f64 = dict(dtype=torch.float64, device=device)
         g6 = tuple(x + 12 for x in reversed(self.n))

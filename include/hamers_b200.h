@@ -262,6 +262,12 @@ int hb2_diffusive_plan_create(const hb2_diffusive_desc* desc, hb2_diff_plan_t* p
 int hb2_diffusive_plan_destroy(hb2_diff_plan_t plan);
 int hb2_diffusive_plan_set_stream(hb2_diff_plan_t plan, void* cuda_stream);
 int hb2_diffusive_plan_launches(hb2_diff_plan_t plan, int64_t* launches);
+/* Arithmetic of the flux-free route (hb2_diffusive_divergence_accumulate_dev), like hb2_patch_desc::math of the convective
+ * plan: HB2_MATH_EXACT (default) keeps the reference's operations in the reference's order (bit-identical to the oracle);
+ * HB2_MATH_FAST re-associates them (one reciprocal per cell, coefficients pre-multiplied by 1/dx, explicit FMAs, the energy
+ * flux assembled from the momentum fluxes, the two faces of a cell differenced analytically): <= 1e-12 relative, 3-D only
+ * (2-D patches keep the exact arithmetic).  The materialised side flux (hb2_compute_diffusive_flux_*) is always exact. */
+int hb2_diffusive_plan_set_math(hb2_diff_plan_t plan, int32_t math);
 
 /* DiffusiveFluxReconstructor::computeDiffusiveFluxOnPatch
  * (include/flow/diffusive_flux_reconstructors/DiffusiveFluxReconstructor.hpp; called from NavierStokes.cpp:1153-1160).

@@ -196,6 +196,17 @@ def diff_divergence_accumulate(desc, tr, Q, dt, g, beta, U):
     return U
 
 
+def diff_divergence_accumulate_fast(desc, tr, Q, dt, g, beta, U):
+    """the same update in the re-associated arithmetic of the HB2_MATH_FAST route (3-D)"""
+    d = _ddesc(desc, tr)
+    Q = np.ascontiguousarray(Q)
+    assert U.flags["C_CONTIGUOUS"]
+    rc = dlib().emu_diff_divergence_accumulate_fast(C.byref(d), _pp([Q[c] for c in range(desc.neq)]), C.c_double(dt), C.c_int(g),
+                                                    C.c_double(beta), _pp([U[e] for e in range(desc.neq)]))
+    assert rc == 0
+    return U
+
+
 def diff_max_spectral_radius(desc, tr, c_p_eos, Q):
     d = _ddesc(desc, tr)
     f = dlib().emu_diff_max_spectral_radius

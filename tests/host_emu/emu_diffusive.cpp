@@ -180,6 +180,62 @@ extern "C" int emu_diff_divergence_accumulate(const EmuDiffDesc* d, const double
     return d->dim == 2 ? run_div<2>(d, Q, dt, g, beta, U) : run_div<3>(d, Q, dt, g, beta, U);
 }
 
+/* The re-associated arithmetic of the flux-free route (HB2_MATH_FAST; the point functions the marching kernels of
+ * hb2_diffusive_march.cuh call with MATH = 1), 3-D, from plain loops: primitives on the ghost box, node fluxes on the interior
+ * extended by three, then the update of every interior cell. */
+extern "C" int emu_diff_divergence_accumulate_fast(const EmuDiffDesc* d, const double* const* Q, double dt, int g, double beta,
+                                                   double* const* U)
+{
+    if (d->dim != 3) return -1;
+    DiffGeom G, GU;
+    make_diff_geom(3, d->n, d->dx, HB2_DIFF_G, &G);
+    make_diff_geom(3, d->n, d->dx, g, &GU);
+    DiffConsts K{d->gamma, d->c_v, d->mu, d->mu_v, d->c_p * d->mu / d->Pr};
+    DiffFast F;
+    make_diff_fast(G, K, dt, beta, &F);
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    std::vector<std::vector<double>> P(4, std::vector<double>((size_t)G.ncell_g, nan)), Fn(15, std::vector<double>((size_t)G.ncell_g, nan));
+    for (long long x = 0; x < G.ncell_g; x++) {
+        const double q[5] = {Q[0][x], Q[1][x], Q[2][x], Q[3][x], Q[4][x]};
+        double p[4];
+        diff_primitives_fast(q, F, p);
+        for (int v = 0; v < 4; v++) P[v][(size_t)x] = p[v];
+    }
+    for (int k = -3; k < G.n[2] + 3; k++)
+        for (int j = -3; j < G.n[1] + 3; j++)
+            for (int i = -3; i < G.n[0] + 3; i++) {
+                const long long x = (i + G.g[0]) + G.cs[1] * (j + G.g[1]) + G.cs[2] * (k + G.g[2]);
+                double der[4][3];
+                for (int v = 0; v < 4; v++)
+                    for (int a = 0; a < 3; a++) {
+                        const double* c = P[v].data() + x;
+                        const long long s = G.cs[a];
+                        der[v][a] = diff_first_derivative6_fast(c[-3 * s], c[-2 * s], c[-s], c[s], c[2 * s], c[3 * s], F.cd[a]);
+                    }
+                const double vel[3] = {P[0][(size_t)x], P[1][(size_t)x], P[2][(size_t)x]};
+                double fn[3][5];
+                diff_node_flux_fast(F, vel, der, fn);
+                for (int f = 0; f < 3; f++)
+                    for (int e = 1; e < 5; e++) Fn[f * 5 + e][(size_t)x] = fn[f][e];
+            }
+    for (int k = 0; k < G.n[2]; k++)
+        for (int j = 0; j < G.n[1]; j++)
+            for (int i = 0; i < G.n[0]; i++) {
+                const long long x = (i + G.g[0]) + G.cs[1] * (j + G.g[1]) + G.cs[2] * (k + G.g[2]);
+                const long long xu = (i + GU.g[0]) + GU.cs[1] * (j + GU.g[1]) + GU.cs[2] * (k + GU.g[2]);
+                for (int e = 1; e < 5; e++) {
+                    double acc = U[e][xu];
+                    for (int a = 0; a < 3; a++) {
+                        const double* c = Fn[a * 5 + e].data() + x;
+                        const long long s = G.cs[a];
+                        acc = diff_divergence_fast(acc, c[-3 * s], c[-2 * s], c[-s], c[s], c[2 * s], c[3 * s], F.kd[a]);
+                    }
+                    U[e][xu] = acc;
+                }
+            }
+    return 0;
+}
+
 extern "C" double emu_diff_max_spectral_radius(const EmuDiffDesc* d, double c_p_eos, const double* rho)
 {
     DiffGeom G;

@@ -44,6 +44,9 @@ class EmuDiffusivePlan:
         self.tr = orc.Transport(mu=species_mu, mu_v=species_mu_v, c_p=species_c_p, c_v=species_c_v, Pr=species_Pr)
         self.dim, self.n, self.neq, self.launch_count = dim, tuple(n), dim + 2, 0
 
+    def set_math(self, math):            # the emulation keeps the reference-order arithmetic (inside the fast tolerance)
+        return self
+
     def use_torch_stream(self):
         return self
 

@@ -13,6 +13,14 @@ pytestmark = pytest.mark.gpu
 TR = orc.Transport(mu=0.05, mu_v=0.02, c_p=3.5, c_v=2.5, Pr=0.72)
 
 
+@pytest.fixture(autouse=True, params=[1, 0], ids=["march", "gridstride"])
+def diff_kernel_form(request, monkeypatch):
+    """Every test runs over both forms of the 3-D kernels: the marching ones with the asynchronous load pipeline
+    (hb2_diffusive_march.cuh, the default) and the grid-stride ones; a plan reads HB2_DIFF_MARCH when it is created."""
+    monkeypatch.setenv("HB2_DIFF_MARCH", str(request.param))
+    return request.param
+
+
 def _plan(desc):
     from hamers_b200 import abi
 
@@ -24,7 +32,7 @@ def _state(dim, N, seed=5):
     return orc.PatchDesc(dim=dim, n=N, gamma=gam, dx=dx), U
 
 
-@pytest.mark.parametrize("dim,N", [(2, (24, 17)), (3, (13, 10, 12)), (2, (1, 1)), (3, (7, 1, 3)), (3, (64, 48, 40)), (2, (300, 200)), (3, (70, 23, 19)), (3, (27, 3, 2))])
+@pytest.mark.parametrize("dim,N", [(2, (24, 17)), (3, (13, 10, 12)), (2, (1, 1)), (3, (7, 1, 3)), (3, (64, 48, 40)), (2, (300, 200)), (3, (70, 23, 19)), (3, (27, 3, 2)), (3, (40, 20, 100)), (3, (5, 9, 70))])
 def test_diffusive_flux_device_and_host_entry_points(dim, N, product_lib):
     import torch
 
@@ -204,7 +212,7 @@ def test_navier_stokes_level_steps_match_the_oracle_composition(dim, N, math, pr
     lvl.close()
 
 
-@pytest.mark.parametrize("dim,N,g", [(2, (24, 17), 6), (3, (13, 10, 12), 6), (3, (40, 33, 20), 4), (3, (70, 23, 19), 6), (3, (33, 9, 4), 6)])
+@pytest.mark.parametrize("dim,N,g", [(2, (24, 17), 6), (3, (13, 10, 12), 6), (3, (40, 33, 20), 4), (3, (70, 23, 19), 6), (3, (33, 9, 4), 6), (3, (40, 20, 100), 6), (3, (5, 9, 70), 4)])
 def test_flux_free_divergence_update(dim, N, g, product_lib):
     """hb2_diffusive_divergence_accumulate_dev == hb2_compute_diffusive_flux_dev + hb2_diffusive_accumulate_dev bit for bit,
     and both equal U + beta (-div F_d) formed from the oracle's side fluxes to round-off."""
@@ -232,6 +240,41 @@ def test_flux_free_divergence_update(dim, N, g, product_lib):
     got = one.cpu().numpy()
     assert np.abs(got[inner] - want).max() <= 1.0e-13 * max(1.0, np.abs(want).max())
     outside = got.copy()
+    outside[inner] = base[inner]
+    assert np.array_equal(outside, base)                     # ghosts untouched
+    plan.close()
+
+
+@pytest.mark.parametrize("N,g", [((13, 10, 12), 6), ((40, 33, 20), 4), ((70, 23, 19), 6), ((40, 20, 100), 6), ((5, 9, 70), 6)])
+def test_flux_free_divergence_fast_math(N, g, diff_kernel_form, product_lib):
+    """hb2_diffusive_plan_set_math(HB2_MATH_FAST): the re-associated update agrees with the reference-order one to 1e-12 of
+    the update's magnitude (plus the rounding of U + update); 3-D marching kernels only -- the grid-stride form keeps the
+    exact arithmetic and must stay bit-identical."""
+    import torch
+
+    from hamers_b200 import abi
+
+    desc, U = _state(3, N)
+    Q6 = pb.pad_periodic(U, orc.GD)
+    rng = np.random.default_rng(2)
+    base = rng.standard_normal((desc.neq,) + tuple(n + 2 * g for n in reversed(N)))
+    dt, beta = 3.0e-4, 2.0 / 3.0
+    plan = _plan(desc)
+    Qd = torch.from_numpy(Q6).cuda()
+    exact, fast = torch.from_numpy(base).cuda(), torch.from_numpy(base).cuda()
+    plan.divergence_accumulate(Qd, dt, g, beta, exact)
+    plan.set_math(abi.MATH_FAST)
+    plan.divergence_accumulate(Qd, dt, g, beta, fast)
+    torch.cuda.synchronize()
+    ex, fa = exact.cpu().numpy(), fast.cpu().numpy()
+    if not diff_kernel_form:
+        assert np.array_equal(ex, fa)
+    upd = ex - base
+    assert np.abs(upd[1:]).max() > 0.0 and np.array_equal(fa[0], base[0])
+    for e in range(1, desc.neq):
+        assert np.abs(fa[e] - ex[e]).max() <= 1.0e-12 * np.abs(upd[e]).max() + 2.0 * np.finfo(float).eps * np.abs(base[e]).max(), e
+    inner = (slice(None),) + (slice(g, -g),) * 3
+    outside = fa.copy()
     outside[inner] = base[inner]
     assert np.array_equal(outside, base)                     # ghosts untouched
     plan.close()
