@@ -133,9 +133,9 @@ int validate_desc(const hb2_patch_desc* d)
     if (d->flow_model == HB2_SINGLE_SPECIES) {
         if (d->num_species != 1) return fail(-5, "SINGLE_SPECIES requires num_species = 1");
     } else if (d->flow_model == HB2_FIVE_EQN_ALLAIRE) {
-        if (d->num_species != 2) return fail(-6, "FIVE_EQN_ALLAIRE is built for num_species = 2");
+        if (d->num_species != 2 && d->num_species != 3) return fail(-6, "FIVE_EQN_ALLAIRE is built for num_species = 2 or 3");
     } else if (d->flow_model == HB2_FOUR_EQN_CONSERVATIVE) {
-        if (d->num_species != 2) return fail(-6, "FOUR_EQN_CONSERVATIVE is built for num_species = 2");
+        if (d->num_species != 2 && d->num_species != 3) return fail(-6, "FOUR_EQN_CONSERVATIVE is built for num_species = 2 or 3");
         for (int s = 0; s < d->num_species; s++)
             if (!(d->species_R[s] > 0.0)) return fail(-26, "FOUR_EQN_CONSERVATIVE needs species_R > 0 for every species");
     } else {
@@ -552,8 +552,8 @@ int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* out)
     if (d->scheme == HB2_WCNS5_Z) p->ops = (d->math == HB2_MATH_FAST && p->d.weno_p == 2) ? ops_fast_z() : ops_exact_z();
     if (d->scheme == HB2_WCNS6_LD)
         p->ops = (d->math == HB2_MATH_FAST && p->d.weno_p == 2 && p->K.weno_q == 4) ? ops_fast_ld() : ops_exact_ld();
-    /* the four-eqn conservative model has reference-order kernels only */
-    if (d->flow_model == HB2_FOUR_EQN_CONSERVATIVE)
+    /* the four-eqn conservative model and the three-species models have reference-order kernels only */
+    if (d->flow_model == HB2_FOUR_EQN_CONSERVATIVE || d->num_species > 2)
         p->ops = d->scheme == HB2_WCNS5_Z ? ops_exact_z() : (d->scheme == HB2_WCNS6_LD ? ops_exact_ld() : ops_exact());
     p->ncell_i = (long long)p->G.n[0] * p->G.n[1] * p->G.n[2];
     for (int a = 0; a < 3; a++) {
@@ -1021,10 +1021,15 @@ int hb2_max_wave_speed_dev(hb2_plan_t p, const double* const* Q, double* out_dev
     unsigned long long* o = (unsigned long long*)out_dev;
     if (p->cfg.model == SS && p->cfg.dim == 2) k_wave_speed<Traits<SS, 2, 1>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
     if (p->cfg.model == SS && p->cfg.dim == 3) k_wave_speed<Traits<SS, 3, 1>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
-    if (p->cfg.model == FE && p->cfg.dim == 2) k_wave_speed<Traits<FE, 2, 2>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
-    if (p->cfg.model == FE && p->cfg.dim == 3) k_wave_speed<Traits<FE, 3, 2>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
-    if (p->cfg.model == FC && p->cfg.dim == 2) k_wave_speed<Traits<FC, 2, 2>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
-    if (p->cfg.model == FC && p->cfg.dim == 3) k_wave_speed<Traits<FC, 3, 2>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
+    const int ns = p->cfg.ns;
+    if (p->cfg.model == FE && p->cfg.dim == 2 && ns == 2) k_wave_speed<Traits<FE, 2, 2>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
+    if (p->cfg.model == FE && p->cfg.dim == 3 && ns == 2) k_wave_speed<Traits<FE, 3, 2>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
+    if (p->cfg.model == FC && p->cfg.dim == 2 && ns == 2) k_wave_speed<Traits<FC, 2, 2>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
+    if (p->cfg.model == FC && p->cfg.dim == 3 && ns == 2) k_wave_speed<Traits<FC, 3, 2>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
+    if (p->cfg.model == FE && p->cfg.dim == 2 && ns == 3) k_wave_speed<Traits<FE, 2, 3>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
+    if (p->cfg.model == FE && p->cfg.dim == 3 && ns == 3) k_wave_speed<Traits<FE, 3, 3>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
+    if (p->cfg.model == FC && p->cfg.dim == 2 && ns == 3) k_wave_speed<Traits<FC, 2, 3>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
+    if (p->cfg.model == FC && p->cfg.dim == 3 && ns == 3) k_wave_speed<Traits<FC, 3, 3>><<<grid, 256, 0, p->stream>>>(p->G, t, p->K, o);
     p->launches++;
     HB2_CUDA(cudaGetLastError());
     return 0;

@@ -58,12 +58,27 @@
 
 namespace hb2 {
 
+/* shared memory of a block of nt threads (doubles): rings of NV primitive, NN node-flux and NMID midpoint-flux components,
+ * the staging slots and the push table (the layout of SweepShape below) */
+template <class Tr, int DIR, int MATH>
+constexpr int sweep_smem_doubles(int nt)
+{
+    const int nv = Tr::NEQ + 1 + ((MATH == 1 && Tr::MODEL == FE) ? 1 : 0), nn = (MATH == 0) ? Tr::NEQ : 0;
+    const int nmid = Tr::NEQ + (Tr::ADV ? 1 : 0);
+    const int p = (DIR == 0) ? nt / HB2_XC : nt / 8;
+    const int ring = (DIR == 0) ? 4 * HB2_XC : 32, dup = (DIR == 0) ? 8 : 5;
+    return nv * (ring + dup) * p + (nn + nmid) * ring * p + Tr::NCOMP * nt + 27 * Tr::NCOMP + 3;
+}
+
 template <class Tr, int DIR, int MATH>
 struct SweepShape {
-    static constexpr int NT = 256;
+    /* 256 threads; models with so many equations that the rings of a 256-thread block exceed the 227 KB of shared memory
+     * (five-eqn with three species, reference-order build: 273 KB) run COMPACT blocks of 128 threads with half the pencils --
+     * y / z sweeps: 16 consecutive x per row (two rows per warp), x sweep: 8 rows */
+    static constexpr int NT = (sweep_smem_doubles<Tr, DIR, MATH>(256) * 8 <= 227 * 1024) ? 256 : 128;
     static constexpr int NW = NT / 32;
-    static constexpr int P = (DIR == 0) ? NT / HB2_XC : 32;   /* pencils per block */
-    static constexpr int C = (DIR == 0) ? HB2_XC : NW;        /* cells per chunk along the sweep axis */
+    static constexpr int P = (DIR == 0) ? NT / HB2_XC : NT / 8;   /* pencils per block */
+    static constexpr int C = (DIR == 0) ? HB2_XC : 8;             /* cells per chunk along the sweep axis */
     /* ring slots along the sweep axis: one iteration touches 3C+5 consecutive cells and 2C+3 consecutive faces */
     static constexpr int RING = (DIR == 0) ? 4 * HB2_XC : 32;
     static constexpr int CS = RING * P;                /* doubles per ring component (midpoint flux, node flux) */
@@ -72,7 +87,7 @@ struct SweepShape {
     static constexpr int DUP = (DIR == 0) ? 8 : 5;
     static constexpr int RINGV = RING + DUP;
     static constexpr int CSV = RINGV * P;              /* doubles per component of the primitive-variable ring */
-    static constexpr int MS = (DIR == 0) ? 1 : 32;     /* stride between consecutive cells of a pencil */
+    static constexpr int MS = (DIR == 0) ? 1 : P;      /* stride between consecutive cells of a pencil */
     /* primitive variables + sound speed (+ total energy for the five-eqn model, whose node flux needs the stored one) */
     static constexpr int IC = Tr::NEQ;                 /* sound speed */
     static constexpr int IE = Tr::NEQ + 1;             /* total energy (five-eqn only) */
@@ -92,9 +107,9 @@ struct SweepShape {
     /* mbarrier of the bulk-copy staging (one 64-bit word) */
     static constexpr int OFF_B = OFF_P + 27 * Tr::NCOMP + ((OFF_P + 27 * Tr::NCOMP) & 1);
     static constexpr int SMEM_DOUBLES = OFF_B + 2;
-    HB2_HD static int slot(int pp, int s) { return (DIR == 0) ? pp * RING + (s & (RING - 1)) : (s & (RING - 1)) * 32 + pp; }
+    HB2_HD static int slot(int pp, int s) { return (DIR == 0) ? pp * RING + (s & (RING - 1)) : (s & (RING - 1)) * P + pp; }
     /* primitive-variable ring: r = ring position in [0, RINGV) */
-    HB2_HD static int slotv(int pp, int r) { return (DIR == 0) ? pp * RINGV + r : r * 32 + pp; }
+    HB2_HD static int slotv(int pp, int r) { return (DIR == 0) ? pp * RINGV + r : r * P + pp; }
     HB2_HD static int nsteps(int ncells) { return (ncells + 8 + C - 1) / C; }
 };
 
@@ -124,22 +139,21 @@ HB2_HD PencilCtx pencil_ctx(const DirArgs& A, const BlockId& b, int tid)
     using Sh = SweepShape<Tr, DIR, MATH>;
     const Geom& G = A.G;
     PencilCtx c;
-    const int lane = tid & 31, w = tid >> 5;
     c.tid = tid;
     c.sq = 0;
-    c.pp = (DIR == 0) ? tid / Sh::C : lane;
-    c.o = (DIR == 0) ? tid % Sh::C : w;
+    c.pp = (DIR == 0) ? tid / Sh::C : tid % Sh::P;      /* y / z: lanes along x (a full warp row, or two half rows when compact) */
+    c.o = (DIR == 0) ? tid % Sh::C : tid / Sh::P;
     c.i = c.j = c.k = 0;
     if (DIR == 0) {
         c.j = b.x * Sh::P + c.pp;
         c.k = b.y;
         c.valid = c.j < G.n[1];
     } else if (DIR == 1) {
-        c.i = b.x * 32 + c.pp;
+        c.i = b.x * Sh::P + c.pp;
         c.k = b.y;
         c.valid = c.i < G.n[0];
     } else {
-        c.i = b.x * 32 + c.pp;
+        c.i = b.x * Sh::P + c.pp;
         c.j = b.y;
         c.valid = c.i < G.n[0];
     }
@@ -254,7 +268,7 @@ HB2_HD void bulk_rows(const PencilCtx& c, const Geom& G, int t, int& nrow, int& 
     } else {
         const int across = G.n[0] - (c.i - c.pp);
         nrow = along;
-        rowlen = across > 32 ? 32 : across;
+        rowlen = across > Sh::P ? Sh::P : across;
     }
     if (nrow < 0) nrow = 0;
 }
@@ -318,7 +332,7 @@ HB2_HD void pipeline_issue(const DirArgs& A, double* smem, const PencilCtx& c, i
             slot = cix * Sh::NT + rr * Sh::C;
         } else {
             x = (c.base - c.pp) + (long long)(s0 + rr) * c.st;
-            slot = cix * Sh::NT + rr * 32;
+            slot = cix * Sh::NT + rr * Sh::P;
         }
 #if defined(__CUDA_ARCH__)
         bulk_g2s(sq0 + (unsigned)(slot * sizeof(double)), A.Q[cix] + x, (unsigned)(rowlen * 8), mbar);

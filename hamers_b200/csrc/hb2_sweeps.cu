@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(384, 2) k_sensor(const __grid_constant__ Senso
 #endif
 
 template <class Tr, int DIR, int NTERM>
-__global__ void __launch_bounds__(256, (MATH == 1 && Tr::MODEL == SS && HB2_SCHEME != HB2_WCNS6_LD) ? HB2_MINB : 1) k_sweep(const __grid_constant__ DirArgs A)
+__global__ void __launch_bounds__((SweepShape<Tr, DIR, MATH>::NT), (MATH == 1 && Tr::MODEL == SS && HB2_SCHEME != HB2_WCNS6_LD) ? HB2_MINB : 1) k_sweep(const __grid_constant__ DirArgs A)
 {
     using Sh = SweepShape<Tr, DIR, MATH>;
     extern __shared__ double smem[];
@@ -200,10 +200,10 @@ int launch_dir_n(const DirArgs& A, cudaStream_t st)
         grid.x = (G.n[1] + Sh::P - 1) / Sh::P;
         grid.y = (Tr::DIM == 3) ? G.n[2] : 1;
     } else if (DIR == 1) {
-        grid.x = (G.n[0] + 31) / 32;
+        grid.x = (G.n[0] + Sh::P - 1) / Sh::P;
         grid.y = (Tr::DIM == 3) ? G.n[2] : 1;
     } else {
-        grid.x = (G.n[0] + 31) / 32;
+        grid.x = (G.n[0] + Sh::P - 1) / Sh::P;
         grid.y = G.n[1];
     }
     k_sweep<Tr, DIR, NTERM><<<grid, Sh::NT, smem, st>>>(A);
@@ -240,11 +240,16 @@ int launch_sweep_t(const LaunchCfg&, int dir, const DirArgs& A, cudaStream_t st)
     return launch_dir<Tr, (Tr::DIM == 3 ? 2 : 1)>(A, st);
 }
 
-/* the four-eqn conservative model exists in the reference-order translation units only */
+/* the four-eqn conservative model and the models with three species exist in the reference-order translation
+ * units only (the reference is generic in d_num_species, FlowModelFiveEqnAllaire.cpp:29; its shipped decks use two) */
 #if HB2_MATH == 0
 #define HB2_DISPATCH_FC(cfg, CALL)                                                    \
     if ((cfg).model == FC && (cfg).dim == 2 && (cfg).ns == 2) { using Tr = Traits<FC, 2, 2>; CALL; } \
-    if ((cfg).model == FC && (cfg).dim == 3 && (cfg).ns == 2) { using Tr = Traits<FC, 3, 2>; CALL; }
+    if ((cfg).model == FC && (cfg).dim == 3 && (cfg).ns == 2) { using Tr = Traits<FC, 3, 2>; CALL; } \
+    if ((cfg).model == FC && (cfg).dim == 2 && (cfg).ns == 3) { using Tr = Traits<FC, 2, 3>; CALL; } \
+    if ((cfg).model == FC && (cfg).dim == 3 && (cfg).ns == 3) { using Tr = Traits<FC, 3, 3>; CALL; } \
+    if ((cfg).model == FE && (cfg).dim == 2 && (cfg).ns == 3) { using Tr = Traits<FE, 2, 3>; CALL; } \
+    if ((cfg).model == FE && (cfg).dim == 3 && (cfg).ns == 3) { using Tr = Traits<FE, 3, 3>; CALL; }
 #else
 #define HB2_DISPATCH_FC(cfg, CALL)
 #endif

@@ -188,6 +188,37 @@ def random_state_four_eqn(dim: int, N, seed=20261017, shock=True):
     return np.ascontiguousarray(U.astype(np.float64)), dx, gam, R
 
 
+def random_state_three_species(dim: int, N, model, seed=20261017, shock=True):
+    """The branch-coverage state of random_state with THREE species (the reference's flow models are generic in
+    d_num_species; its shipped decks use two).  model = FIVE_EQN_ALLAIRE: U = [Z1 rho1, Z2 rho2, Z3 rho3, rho u.., E, Z1, Z2,
+    Z3] (the last volume fraction is the stored, derived component); returns (U, dx, gammas).  Any other model value is taken
+    as FOUR_EQN_CONSERVATIVE: U = [rho Y1, rho Y2, rho Y3, rho u.., E]; returns (U, dx, gammas, Rs)."""
+    U1, dx, _ = random_state(dim, N, model=SINGLE_SPECIES, seed=seed, shock=shock)
+    rng = np.random.default_rng(seed + 2)
+    gam = (1.6, 1.4, 1.25)
+    rho = U1[0]
+    vel = [U1[1 + a] / rho for a in range(dim)]
+    ke = sum(v * v for v in vel)
+    p = 0.4 * (U1[dim + 1] - 0.5 * rho * ke)
+    w = rng.uniform(0.05, 1.0, (3,) + rho.shape)
+    frac = w / w.sum(axis=0)                       # three fractions in (0, 1) that sum to one
+    if model == FIVE_EQN_ALLAIRE:
+        Z = [frac[0], frac[1], 1.0 - frac[0] - frac[1]]
+        r = [rho * rng.uniform(0.8, 1.2, rho.shape), rho * rng.uniform(0.4, 0.8, rho.shape), rho * rng.uniform(1.1, 1.5, rho.shape)]
+        Zr = [Z[i] * r[i] for i in range(3)]
+        rho_m = Zr[0] + Zr[1] + Zr[2]
+        gamma_m = 1.0 / sum(Z[i] / (gam[i] - 1.0) for i in range(3)) + 1.0
+        E = p / (gamma_m - 1.0) + 0.5 * rho_m * ke
+        U = np.stack(Zr + [rho_m * v for v in vel] + [E] + Z)
+        return np.ascontiguousarray(U.astype(np.float64)), dx, gam
+    R = (0.7, 1.3, 1.0)
+    Y = [frac[0], frac[1], 1.0 - frac[0] - frac[1]]
+    g = mixture_gamma_mass_fractions(Y, gam, R)
+    E = p / (g - 1.0) + 0.5 * rho * ke
+    U = np.stack([rho * y for y in Y] + [rho * v for v in vel] + [E])
+    return np.ascontiguousarray(U.astype(np.float64)), dx, gam, R
+
+
 # species 0: SF6, species 1: air (input_2D_Richtmyer_Meshkov_instability.txt:21-22)
 RMI_GAMMA = (1.09312, 1.39909)
 RMI_R = (56.927, 296.803)

@@ -53,7 +53,7 @@ extern "C" {
 #define HB2_FIVE_EQN_ALLAIRE 1  /* FlowModelManager.cpp:44 "FIVE_EQN_ALLAIRE" */
 /* FlowModelManager.cpp "FOUR_EQN_CONSERVATIVE" (src/flow/flow_models/four-eqn_conservative/): partial densities
  * rho Y_1..rho Y_ns, momentum, total energy (num_comp = num_eqn = dim + 1 + ns), all equations conservative; mixture of
- * ideal gases closed by mass fractions (species_gamma AND species_R are needed).  Built for num_species = 2; runs the
+ * ideal gases closed by mass fractions (species_gamma AND species_R are needed).  Built for num_species = 2 and 3; runs the
  * reference-order kernels whatever `math` says. */
 #define HB2_FOUR_EQN_CONSERVATIVE 2
 
@@ -65,7 +65,9 @@ typedef struct hb2_patch_desc {
     int32_t dim;                              /* 2 or 3 */
     int32_t n[3];                             /* interior cells of the patch */
     int32_t flow_model;                       /* HB2_SINGLE_SPECIES | HB2_FIVE_EQN_ALLAIRE */
-    int32_t num_species;                      /* 1, or 2 for five-eqn */
+    int32_t num_species;                      /* 1; 2 or 3 for the five-eqn and four-eqn models (the reference is generic in
+                                                 d_num_species, FlowModelFiveEqnAllaire.cpp:29; three species run the
+                                                 reference-order kernels whatever `math` says) */
     double species_gamma[HB2_MAX_SPECIES];    /* Equation_of_state_mixing_rules{species_gamma} */
     double dx[3];                             /* CartesianPatchGeometry::getDx() */
     int32_t weno_p;                           /* Convective_flux_reconstructor{constant_p}, default 2 */

@@ -57,10 +57,10 @@ static void run_dir_n(const DirArgs& A)
         gx = (G.n[1] + Sh::P - 1) / Sh::P;
         gy = (Tr::DIM == 3) ? G.n[2] : 1;
     } else if (DIR == 1) {
-        gx = (G.n[0] + 31) / 32;
+        gx = (G.n[0] + Sh::P - 1) / Sh::P;
         gy = (Tr::DIM == 3) ? G.n[2] : 1;
     } else {
-        gx = (G.n[0] + 31) / 32;
+        gx = (G.n[0] + Sh::P - 1) / Sh::P;
         gy = G.n[1];
     }
     std::vector<double> smem(Sh::SMEM_DOUBLES);
@@ -196,6 +196,10 @@ static void run_sweeps(DirArgs A0, int sensor_seg_len, int seg_len, double* cons
     do {                                                                                          \
         if ((d)->model == SS && (d)->dim == 2) { using Tr = Traits<SS, 2, 1>; if ((d)->math == 0) { constexpr int MATH = 0; CALL; } else { constexpr int MATH = 1; CALL; } return 0; } \
         if ((d)->model == SS && (d)->dim == 3) { using Tr = Traits<SS, 3, 1>; if ((d)->math == 0) { constexpr int MATH = 0; CALL; } else { constexpr int MATH = 1; CALL; } return 0; } \
+        if ((d)->model == FE && (d)->dim == 2 && (d)->ns == 3) { using Tr = Traits<FE, 2, 3>; constexpr int MATH = 0; CALL; return 0; } \
+        if ((d)->model == FE && (d)->dim == 3 && (d)->ns == 3) { using Tr = Traits<FE, 3, 3>; constexpr int MATH = 0; CALL; return 0; } \
+        if ((d)->model == FC && (d)->dim == 2 && (d)->ns == 3) { using Tr = Traits<FC, 2, 3>; constexpr int MATH = 0; CALL; return 0; } \
+        if ((d)->model == FC && (d)->dim == 3 && (d)->ns == 3) { using Tr = Traits<FC, 3, 3>; constexpr int MATH = 0; CALL; return 0; } \
         if ((d)->model == FE && (d)->dim == 2) { using Tr = Traits<FE, 2, 2>; if ((d)->math == 0) { constexpr int MATH = 0; CALL; } else { constexpr int MATH = 1; CALL; } return 0; } \
         if ((d)->model == FE && (d)->dim == 3) { using Tr = Traits<FE, 3, 2>; if ((d)->math == 0) { constexpr int MATH = 0; CALL; } else { constexpr int MATH = 1; CALL; } return 0; } \
         /* four-eqn conservative: reference-order kernels only, like the product library */ \

@@ -406,7 +406,7 @@ def test_error_behaviour(product_lib):
     with pytest.raises(abi.HamersB200Error):
         abi.Plan(1, (8,), species_gamma=(1.4,))          # the 1D branch is not on this path
     with pytest.raises(abi.HamersB200Error):
-        abi.Plan(3, (8, 8, 8), flow_model=abi.FIVE_EQN_ALLAIRE, species_gamma=(1.6, 1.4, 1.3))
+        abi.Plan(3, (8, 8, 8), flow_model=abi.FIVE_EQN_ALLAIRE, species_gamma=(1.6, 1.4, 1.3, 1.2))     # built for 2 and 3 species
     plan = abi.Plan(2, (8, 8), species_gamma=(1.4,)).use_torch_stream()
     U = [torch.ones((4, 16, 16), dtype=torch.float64, device="cuda") for _ in range(2)]
     out = torch.ones((4, 16, 16), dtype=torch.float64, device="cuda")
