@@ -584,9 +584,9 @@ int hb2_plan_create(const hb2_patch_desc* d, hb2_plan_t* out)
     p->bulk_ok = env_int("HB2_BULK_STAGE", 0) != 0 && (p->G.n[0] % 2 == 0) && (p->G.g[0] % 2 == 0) &&
                  (p->seg_len[0] % 2 == 0 || p->seg_len[0] >= p->G.n[0]);
     {
-        /* sensor pass: 61 x 8 tiles marching along z; enough segments for ~4 waves of 2 resident blocks per SM, at
+        /* sensor pass: HB2_SENSOR_TX x HB2_SENSOR_TY tiles marching along z; enough segments for ~4 waves of 2 resident blocks per SM, at
          * least 16 planes each (every segment re-reads 3 planes) */
-        const long long tiles = (long long)((p->G.n[0] + 3 + 60) / 61) * ((p->G.n[1] + 3 + 7) / 8);
+        const long long tiles = (long long)((p->G.n[0] + 3 + HB2_SENSOR_TX - 1) / HB2_SENSOR_TX) * ((p->G.n[1] + 3 + HB2_SENSOR_TY - 1) / HB2_SENSOR_TY);
         long long nseg = (148LL * 2 * 4 + tiles - 1) / tiles;
         const long long planes = p->G.n[2] + 3;
         const long long maxseg = planes / 16 > 0 ? planes / 16 : 1;

@@ -32,12 +32,26 @@ struct SensorArgs {
     int seg_len;        /* planes per marching segment (3D) */
 };
 
+/* thread layout of the sensor pass: NX threads along x, 384 / NX rows of threads, VY rows of the velocity tile.
+ *   64 x 6 threads, 11 rows: a 61 x 8 tile of decisions from 64 x 11 velocities (69 %), second row pass 5/6 busy
+ *   48 x 8 threads, 16 rows: a 45 x 13 tile from 48 x 16 velocities (76 %), both row passes full; 259 = 256 + 3 cells of a
+ *                            256-cell box take 6 x 20 tiles with 4 % / 0.4 % idle columns / rows (61 x 8: 15 % / 2 %) */
+#ifndef HB2_SENSOR_NX
+#define HB2_SENSOR_NX 48
+#endif
+#ifndef HB2_SENSOR_VY
+#define HB2_SENSOR_VY 16
+#endif
+#define HB2_SENSOR_TX (HB2_SENSOR_NX - 3)
+#define HB2_SENSOR_TY (HB2_SENSOR_VY - 3)
+
 template <class Tr>
 struct SensorShape {
     static constexpr int NT = 384;
-    static constexpr int NX = 64, NY = NT / NX;    /* thread layout: tx = tid % 64 along x, ty = tid / 64 (6 rows) */
-    static constexpr int VX = NX, VY = 11;         /* velocity tile: cells i0-2 .. i0+TX, one row of threads wide */
-    static constexpr int TX = VX - 3, TY = VY - 3; /* cells whose decisions the block produces per plane (61 x 8) */
+    static constexpr int NX = HB2_SENSOR_NX, NY = NT / NX; /* thread layout: tx = tid % NX along x, ty = tid / NX */
+    static constexpr int VX = NX, VY = HB2_SENSOR_VY;      /* velocity tile: cells i0-2 .. i0+TX, one row of threads wide */
+    static constexpr int TX = VX - 3, TY = VY - 3; /* cells whose decisions the block produces per plane */
+    static_assert(NT % NX == 0, "whole rows of threads");
     static constexpr int SX = TX + 1, SY = TY + 1; /* theta/Omega tile: cells i0-1 .. i0+TX-1 */
     static constexpr int VP = VX * VY, SP = SX * SY;
     static constexpr int KY = (VY + NY - 1) / NY;  /* rows per thread */
