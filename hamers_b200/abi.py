@@ -22,6 +22,7 @@ FIVE_EQN_ALLAIRE = 1
 FOUR_EQN_CONSERVATIVE = 2      # SURVEY row f3 (needs species_R; reference-order kernels only)
 MATH_EXACT = 0
 MATH_FAST = 1
+DIFF_NODE_SIXTH_ORDER, DIFF_MIDPOINT_SIXTH_ORDER = 0, 1
 
 # every symbol include/hamers_b200.h declares (tests check the library exports them all)
 SYMBOLS = [
@@ -35,7 +36,7 @@ SYMBOLS = [
     "hb2_compute_flux_and_source_host", "hb2_fused_stage_host", "hb2_probe_fp64_peak", "hb2_probe_hbm_bandwidth",
     "hb2_plan_set_profiling", "hb2_plan_get_profile", "hb2_advance_level_dev", "hb2_advance_level_host",
     # diffusive flux of the single-species Navier-Stokes application
-    "hb2_diffusive_plan_create", "hb2_diffusive_plan_destroy", "hb2_diffusive_plan_set_stream", "hb2_diffusive_plan_launches", "hb2_diffusive_plan_set_math",
+    "hb2_diffusive_plan_create", "hb2_diffusive_plan_destroy", "hb2_diffusive_plan_set_stream", "hb2_diffusive_plan_launches", "hb2_diffusive_plan_set_math", "hb2_diffusive_plan_set_reconstructor",
     "hb2_compute_diffusive_flux_dev", "hb2_compute_diffusive_flux_host", "hb2_advance_stage_ns_dev",
     "hb2_diffusive_fill_ghosts_periodic_dev", "hb2_diffusive_extract_view_dev", "hb2_diffusive_accumulate_dev",
     "hb2_diffusive_divergence_accumulate_dev", "hb2_diffusive_max_spectral_radius_dev",
@@ -433,6 +434,12 @@ class DiffusivePlan:
 
         _check(self.lib.hb2_diffusive_plan_set_stream(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
                "hb2_diffusive_plan_set_stream")
+        return self
+
+    def set_reconstructor(self, reconstructor: int):
+        """DIFF_NODE_SIXTH_ORDER ("SIXTH_ORDER", default) or DIFF_MIDPOINT_SIXTH_ORDER ("MIDPOINT_SIXTH_ORDER")"""
+        _check(self.lib.hb2_diffusive_plan_set_reconstructor(self._h, C.c_int32(int(reconstructor))),
+               "hb2_diffusive_plan_set_reconstructor")
         return self
 
     def set_math(self, math: int):

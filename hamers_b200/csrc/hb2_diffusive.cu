@@ -50,6 +50,7 @@ struct hb2_diff_plan_s {
     double* stF[15];
     long long nside[3];
     long long launches;
+    int reconstructor;            /* HB2_DIFF_NODE_SIXTH_ORDER (default) / HB2_DIFF_MIDPOINT_SIXTH_ORDER */
     int math;                     /* arithmetic of the flux-free route: HB2_MATH_EXACT (default) / HB2_MATH_FAST */
     int marching;                 /* 3-D: marching kernels with an asynchronous load pipeline (hb2_diffusive_march.cuh; HB2_DIFF_MARCH,
                                      default 1); 0: the grid-stride forms */
@@ -126,6 +127,25 @@ __global__ void __launch_bounds__(256) k_diff_face(const __grid_constant__ DiffG
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride)
         diff_face_thread<DIM, FDIR>(G, A, dt, t);
+}
+
+template <int DIM, int FDIR>
+__global__ void __launch_bounds__(256) k_diff_mid_flux(const __grid_constant__ DiffGeom G, const __grid_constant__ DiffConsts K,
+                                                       const __grid_constant__ DiffMidPtrs A)
+{
+    const long long total = diff_mid_count<DIM, FDIR>(G);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride)
+        diff_mid_flux_thread<DIM, FDIR>(G, K, A, t);
+}
+
+template <int DIM, int FDIR>
+__global__ void __launch_bounds__(256) k_diff_mid_face(const __grid_constant__ DiffGeom G, const __grid_constant__ DiffMidPtrs A, double dt)
+{
+    const long long total = diff_face_count<DIM, FDIR>(G);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride)
+        diff_mid_face_thread<DIM, FDIR>(G, A, dt, t);
 }
 
 template <int DIM>
@@ -294,9 +314,42 @@ int node_stage(hb2_diff_plan_t p, const double* const* Q, bool fast = false)
     return 0;
 }
 
+/* midpoint family: primitives, then per direction the midpoint flux of every equation (plan scratch) and the faces */
+template <int DIM, int FDIR>
+int launch_mid_dir(hb2_diff_plan_t p, double dt, double* const* flux)
+{
+    DiffMidPtrs A{};
+    for (int v = 0; v < DIM + 1; v++) A.P[v] = p->P[v];
+    for (int e = 0; e < DIM + 2; e++) {
+        A.Fm[e] = p->Fn[e];
+        A.F[e] = flux[FDIR * (DIM + 2) + e];
+    }
+    k_diff_mid_flux<DIM, FDIR><<<grid_for(diff_mid_count<DIM, FDIR>(p->G), p->sm_count), 256, 0, p->stream>>>(p->G, p->K, A);
+    k_diff_mid_face<DIM, FDIR><<<grid_for(p->nside[FDIR], p->sm_count), 256, 0, p->stream>>>(p->G, A, dt);
+    p->launches += 2;
+    HB2D_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int DIM>
+int run_flux_midpoint(hb2_diff_plan_t p, const double* const* Q, double dt, double* const* flux)
+{
+    DiffPtrs A{};
+    for (int c = 0; c < DIM + 2; c++) A.Q[c] = Q[c];
+    for (int v = 0; v < DIM + 1; v++) A.P[v] = p->P[v];
+    k_diff_primitives<DIM><<<grid_for(p->G.ncell_g, p->sm_count), 256, 0, p->stream>>>(p->G, p->K, A);
+    p->launches += 1;
+    HB2D_CUDA(cudaGetLastError());
+    int rc = launch_mid_dir<DIM, 0>(p, dt, flux);
+    if (!rc) rc = launch_mid_dir<DIM, 1>(p, dt, flux);
+    if (!rc && DIM == 3) rc = launch_mid_dir<DIM, (DIM == 3 ? 2 : 1)>(p, dt, flux);
+    return rc;
+}
+
 template <int DIM>
 int run_flux(hb2_diff_plan_t p, const double* const* Q, double dt, double* const* flux)
 {
+    if (p->reconstructor == HB2_DIFF_MIDPOINT_SIXTH_ORDER) return run_flux_midpoint<DIM>(p, Q, dt, flux);
     int rc = node_stage<DIM>(p, Q);
     if (rc) return rc;
     for (int f = 0; f < DIM; f++) {
@@ -391,6 +444,7 @@ int hb2_diffusive_plan_create(const hb2_diffusive_desc* d, hb2_diff_plan_t* out)
     p->neq = d->dim + 2;
     p->stream = nullptr;
     p->math = HB2_MATH_EXACT;
+    p->reconstructor = HB2_DIFF_NODE_SIXTH_ORDER;
     {
         const char* v = getenv("HB2_DIFF_MARCH");
         p->marching = (v && *v) ? atoi(v) : 1;
@@ -439,6 +493,15 @@ int hb2_diffusive_plan_set_math(hb2_diff_plan_t p, int32_t math)
     if (!p) return set_error(-1, "null plan");
     if (math != HB2_MATH_EXACT && math != HB2_MATH_FAST) return set_error(-32, "math must be HB2_MATH_EXACT or HB2_MATH_FAST");
     p->math = math;
+    return 0;
+}
+
+int hb2_diffusive_plan_set_reconstructor(hb2_diff_plan_t p, int32_t reconstructor)
+{
+    if (!p) return set_error(-1, "null plan");
+    if (reconstructor != HB2_DIFF_NODE_SIXTH_ORDER && reconstructor != HB2_DIFF_MIDPOINT_SIXTH_ORDER)
+        return set_error(-33, "reconstructor must be HB2_DIFF_NODE_SIXTH_ORDER or HB2_DIFF_MIDPOINT_SIXTH_ORDER");
+    p->reconstructor = reconstructor;
     return 0;
 }
 
@@ -515,6 +578,9 @@ int hb2_diffusive_divergence_accumulate_dev(hb2_diff_plan_t p, const double* con
 {
     if (!p || !Q || !U) return set_error(-1, "null argument");
     if (num_ghosts < 0) return set_error(-31, "num_ghosts must be >= 0");
+    if (p->reconstructor != HB2_DIFF_NODE_SIXTH_ORDER)
+        return set_error(-34, "the flux-free update exists for the node reconstructor; use hb2_compute_diffusive_flux_dev + "
+                              "hb2_diffusive_accumulate_dev with the midpoint one");
     HB2D_CUDA(cudaSetDevice(p->device));
     return p->d.dim == 2 ? run_divergence<2>(p, Q, dt, num_ghosts, beta, U) : run_divergence<3>(p, Q, dt, num_ghosts, beta, U);
 }

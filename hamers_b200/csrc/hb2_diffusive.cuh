@@ -260,6 +260,190 @@ HB2D_HD double diff_reconstruct6(double lll, double ll, double l, double r, doub
     return F;
 }
 
+/* ---- midpoint family: DiffusiveFluxReconstructorMidpointSixthOrder ("MIDPOINT_SIXTH_ORDER"; no shipped deck selects it) ----
+ *   driver   src/flow/diffusive_flux_reconstructors/midpoint/DiffusiveFluxReconstructorMidpoint.cpp:38-2330
+ *   kernels  .../midpoint/DiffusiveFluxReconstructorMidpointSixthOrder.cpp:68-1799 (reads the cells within 5 of the interior)
+ *   side diffusivities  FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp:2365-2797, 2799-3657
+ * The flux is formed AT THE MIDPOINTS (faces) of the flux direction f: derivatives along f by a staggered sixth-order
+ * difference of the node values, derivatives along the other directions by sixth-order node derivatives interpolated along f,
+ * diffusivities from mu, mu_v, kappa and the velocity interpolated along f; a face flux is a five-midpoint combination,
+ * times dt.  The reference stages every intermediate in its own patch-sized array; here one thread forms the midpoint flux
+ * of all equations from the primitive scratch (every value is the same function of the same inputs: bit-identical). */
+
+/* DiffusiveFluxReconstructorMidpointSixthOrder.cpp:80-82, 219-222: p points at node R (the cell on the high side) */
+HB2D_HD double diff_mid_derivative(const double* p, long long s, double dx_inv)
+{
+    const double a_n = 75.0 / 64.0;
+    const double b_n = -(25.0 / 384.0);
+    const double c_n = 3.0 / 640.0;
+    return (a_n * (p[0] - p[-s]) + b_n * (p[s] - p[-2 * s]) + c_n * (p[2 * s] - p[-3 * s])) * dx_inv;
+}
+
+/* :962-964, 1101-1104: six values R, L, RR, LL, RRR, LLL in the order the reference adds them */
+HB2D_HD double diff_mid_interpolate6(double r, double l, double rr, double ll, double rrr, double lll)
+{
+    const double a_n = 75.0 / 128.0;
+    const double b_n = -(25.0 / 256.0);
+    const double c_n = 3.0 / 256.0;
+    return (a_n * (r + l) + b_n * (rr + ll) + c_n * (rrr + lll));
+}
+HB2D_HD double diff_mid_interpolate(const double* p, long long s)
+{
+    return diff_mid_interpolate6(p[0], p[-s], p[s], p[-2 * s], p[2 * s], p[-3 * s]);
+}
+
+/* :1400-1406, 1552-1556: face value from the midpoint fluxes LL, L, own, R, RR; p points at the face's own midpoint */
+HB2D_HD double diff_mid_reconstruct(const double* p, long long s, double dt)
+{
+    const double a_m = 75.0 / 64.0;
+    const double b_m = -(25.0 / 384.0);
+    const double c_m = 3.0 / 640.0;
+    const double a_r = a_m + b_m + c_m;
+    const double b_r = b_m + c_m;
+    const double c_r = c_m;
+    double F = 0.0;                              /* diffusive_flux->fillAll(0), then "+=" */
+    F += dt * (a_r * (p[0]) + b_r * (p[-s] + p[s]) + c_r * (p[-2 * s] + p[2 * s]));
+    return F;
+}
+
+/* side diffusivities of direction FDIR (FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp:2682-2691, 2725-2734, 2768-2777;
+ * 2-D :2581-2589, 2615-2623) from the interpolated coefficients and velocity */
+template <int DIM, int FDIR>
+HB2D_HD void diff_side_diffusivities(double mu, double mu_v, double kappa, const double (&vel)[3], double (&D)[8])
+{
+    const double un = vel[FDIR];
+    D[0] = -(4.0 / 3.0 * mu + mu_v);
+    D[1] = 2.0 / 3.0 * mu - mu_v;
+    D[2] = -mu;
+    D[3] = -un * (4.0 / 3.0 * mu + mu_v);
+    D[4] = un * (2.0 / 3.0 * mu - mu_v);
+    int m = 5;
+#pragma unroll
+    for (int a = 0; a < DIM; a++)
+        if (a != FDIR) D[m++] = -vel[a] * mu;
+    D[m] = -kappa;
+    if (DIM == 2) D[7] = 0.0;
+}
+
+/* index of the side diffusivity of term ti of (flux direction, derivative direction, equation); the variables are those of
+ * DiffTerms (getCellDataOfDiffusiveFluxVariablesForDerivative serves both families); :2799-3657 */
+template <int DIM>
+HB2D_HD constexpr int diff_side_index(int f, int d, int e, int ti)
+{
+    if (DIM == 3) {
+        constexpr signed char T[3][3][5][4] = {
+            {{{-1, -1, -1, -1}, {0, -1, -1, -1}, {2, -1, -1, -1}, {2, -1, -1, -1}, {3, 5, 6, 7}},
+             {{-1, -1, -1, -1}, {1, -1, -1, -1}, {2, -1, -1, -1}, {-1, -1, -1, -1}, {5, 4, -1, -1}},
+             {{-1, -1, -1, -1}, {1, -1, -1, -1}, {-1, -1, -1, -1}, {2, -1, -1, -1}, {6, 4, -1, -1}}},
+            {{{-1, -1, -1, -1}, {2, -1, -1, -1}, {1, -1, -1, -1}, {-1, -1, -1, -1}, {4, 5, -1, -1}},
+             {{-1, -1, -1, -1}, {2, -1, -1, -1}, {0, -1, -1, -1}, {2, -1, -1, -1}, {5, 3, 6, 7}},
+             {{-1, -1, -1, -1}, {-1, -1, -1, -1}, {1, -1, -1, -1}, {2, -1, -1, -1}, {6, 4, -1, -1}}},
+            {{{-1, -1, -1, -1}, {2, -1, -1, -1}, {-1, -1, -1, -1}, {1, -1, -1, -1}, {4, 5, -1, -1}},
+             {{-1, -1, -1, -1}, {-1, -1, -1, -1}, {2, -1, -1, -1}, {1, -1, -1, -1}, {4, 6, -1, -1}},
+             {{-1, -1, -1, -1}, {2, -1, -1, -1}, {2, -1, -1, -1}, {0, -1, -1, -1}, {5, 6, 3, 7}}}};
+        return T[f][d][e][ti];
+    } else {
+        constexpr signed char T[2][2][4][4] = {
+            {{{-1, -1, -1, -1}, {0, -1, -1, -1}, {2, -1, -1, -1}, {3, 5, 6, -1}},
+             {{-1, -1, -1, -1}, {1, -1, -1, -1}, {2, -1, -1, -1}, {5, 4, -1, -1}}},
+            {{{-1, -1, -1, -1}, {2, -1, -1, -1}, {1, -1, -1, -1}, {4, 5, -1, -1}},
+             {{-1, -1, -1, -1}, {2, -1, -1, -1}, {0, -1, -1, -1}, {5, 3, 6, -1}}}};
+        return T[f][d][e][ti];
+    }
+}
+
+/* does the flux of direction f use the derivative of variable v in direction d? */
+template <int DIM>
+HB2D_HD constexpr bool diff_mid_uses(int f, int v, int d)
+{
+    for (int e = 1; e < DIM + 2; e++) {
+        const DiffTermList tl = DiffTerms<DIM>::get(f, d, e);
+        for (int ti = 0; ti < tl.n; ti++)
+            if (tl.t[ti].var == v) return true;
+    }
+    return false;
+}
+
+struct DiffMidPtrs {
+    const double* P[4];      /* velocity components, temperature on the ghost box */
+    double* Fm[5];           /* midpoint flux of the current direction: ghost-box layout, midpoint i (the face between cells
+                                i - 1 and i) at cell index i; equation 0 unused */
+    double* F[5];            /* side flux of the current direction (ghost 0) */
+};
+
+template <int DIM, int FDIR>
+HB2D_HD long long diff_mid_count(const DiffGeom& G)
+{
+    return (long long)(G.n[0] + (FDIR == 0 ? 5 : 0)) * (G.n[1] + (FDIR == 1 ? 5 : 0)) * (G.n[2] + (FDIR == 2 ? 5 : 0));
+}
+
+/* midpoint t of direction FDIR: midpoints -2 .. n + 2 along FDIR, interior cells of the other directions
+ * (DiffusiveFluxReconstructorMidpoint.cpp:1466-1470) */
+template <int DIM, int FDIR>
+HB2D_HD void diff_mid_flux_thread(const DiffGeom& G, const DiffConsts& K, const DiffMidPtrs& A, long long t)
+{
+    using TT = DiffTerms<DIM>;
+    const int e0 = G.n[0] + (FDIR == 0 ? 5 : 0), e1 = G.n[1] + (FDIR == 1 ? 5 : 0);
+    const int i = (int)(t % e0) - (FDIR == 0 ? 2 : 0), j = (int)((t / e0) % e1) - (FDIR == 1 ? 2 : 0);
+    const int k = (int)(t / ((long long)e0 * e1)) - (FDIR == 2 ? 2 : 0);
+    const long long x = (i + G.g[0]) + G.cs[1] * (j + G.g[1]) + G.cs[2] * (k + G.g[2]);
+    const long long s = G.cs[FDIR];
+    /* the transport coefficients are cell data like any other: interpolated, not copied (the weights do not sum to one in
+     * floating point) */
+    const double mu_m = diff_mid_interpolate6(K.mu, K.mu, K.mu, K.mu, K.mu, K.mu);
+    const double mu_v_m = diff_mid_interpolate6(K.mu_v, K.mu_v, K.mu_v, K.mu_v, K.mu_v, K.mu_v);
+    const double kappa_m = diff_mid_interpolate6(K.kappa, K.kappa, K.kappa, K.kappa, K.kappa, K.kappa);
+    double vel[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int a = 0; a < DIM; a++) vel[a] = diff_mid_interpolate(A.P[a] + x, s);
+    double D[8];
+    diff_side_diffusivities<DIM, FDIR>(mu_m, mu_v_m, kappa_m, vel, D);
+    double der[DIM + 1][DIM];
+#pragma unroll
+    for (int v = 0; v < DIM + 1; v++) {
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            der[v][d] = 0.0;
+            if (!diff_mid_uses<DIM>(FDIR, v, d)) continue;
+            const double* p = A.P[v] + x;
+            if (d == FDIR) {
+                der[v][d] = diff_mid_derivative(p, s, G.dx_inv[d]);
+            } else {
+                /* node derivatives in direction d at the six nodes along FDIR, then the interpolation to the midpoint */
+                const long long sd = G.cs[d];
+                const double inv = G.dx_inv[d];
+                der[v][d] = diff_mid_interpolate6(diff_first_derivative(p, sd, inv), diff_first_derivative(p - s, sd, inv),
+                                                  diff_first_derivative(p + s, sd, inv), diff_first_derivative(p - 2 * s, sd, inv),
+                                                  diff_first_derivative(p + 2 * s, sd, inv), diff_first_derivative(p - 3 * s, sd, inv));
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 1; e < DIM + 2; e++) {
+        double acc = 0.0;                        /* fillAll(0), then "+=" term by term: x-, y-, z-derivative terms */
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+            const DiffTermList tl = TT::get(FDIR, d, e);
+#pragma unroll
+            for (int ti = 0; ti < 4; ti++)
+                if (ti < tl.n) acc += D[diff_side_index<DIM>(FDIR, d, e, ti)] * der[tl.t[ti].var][d];
+        }
+        A.Fm[e][x] = acc;
+    }
+}
+
+/* face t of direction FDIR (side-data order) from the five midpoint fluxes around it */
+template <int DIM, int FDIR>
+HB2D_HD void diff_mid_face_thread(const DiffGeom& G, const DiffMidPtrs& A, double dt, long long t)
+{
+    const int f0 = G.n[0] + (FDIR == 0), f1 = G.n[1] + (FDIR == 1);
+    const int i = (int)(t % f0), j = (int)((t / f0) % f1), k = (int)(t / ((long long)f0 * f1));
+    const long long x = (i + G.g[0]) + G.cs[1] * (j + G.g[1]) + G.cs[2] * (k + G.g[2]);
+    A.F[0][t] = 0.0;                             /* the midpoint flux of the continuity equation is the fillAll(0) */
+#pragma unroll
+    for (int e = 1; e < DIM + 2; e++) A.F[e][t] = diff_mid_reconstruct(A.Fm[e] + x, G.cs[FDIR], dt);
+}
+
 /* ---- re-associated arithmetic of the flux-free route (HB2_MATH_FAST; hb2_diffusive_plan_set_math): the same terms with
  * fewer FP64 instructions -- one reciprocal per cell instead of five divisions (T = epsilon/c_v: the (gamma - 1) rho of the
  * pressure cancels), derivative and reconstruction coefficients pre-multiplied by 1/dx and by -beta dt/dx, explicit FMAs,

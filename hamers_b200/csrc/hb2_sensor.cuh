@@ -33,14 +33,15 @@ struct SensorArgs {
 };
 
 /* thread layout of the sensor pass: NX threads along x, 384 / NX rows of threads, VY rows of the velocity tile.
- *   64 x 6 threads, 11 rows: a 61 x 8 tile of decisions from 64 x 11 velocities (69 %), second row pass 5/6 busy
- *   48 x 8 threads, 16 rows: a 45 x 13 tile from 48 x 16 velocities (76 %), both row passes full; 259 = 256 + 3 cells of a
- *                            256-cell box take 6 x 20 tiles with 4 % / 0.4 % idle columns / rows (61 x 8: 15 % / 2 %) */
+ *   64 x 6 threads, 11 rows (default): a 61 x 8 tile of decisions from 64 x 11 velocities (69 %), second row pass 5/6 busy
+ *   48 x 8 threads, 16 rows: a 45 x 13 tile from 48 x 16 velocities (76 %), both row passes full, fewer idle columns on a
+ *     256-cell box (4 % instead of 15 %) -- measured SLOWER on B200: 2.05 vs 1.73 ms at 512^3, 0.290 vs 0.264 ms at 256^3
+ *     (rows of 48 threads straddle the warps: 1.5 warps per row, and the tile rows are no longer bank-aligned) */
 #ifndef HB2_SENSOR_NX
-#define HB2_SENSOR_NX 48
+#define HB2_SENSOR_NX 64
 #endif
 #ifndef HB2_SENSOR_VY
-#define HB2_SENSOR_VY 16
+#define HB2_SENSOR_VY 11
 #endif
 #define HB2_SENSOR_TX (HB2_SENSOR_NX - 3)
 #define HB2_SENSOR_TY (HB2_SENSOR_VY - 3)

@@ -270,6 +270,18 @@ int hb2_diffusive_plan_launches(hb2_diff_plan_t plan, int64_t* launches);
  * flux assembled from the momentum fluxes, the two faces of a cell differenced analytically): <= 1e-12 relative, 3-D only
  * (2-D patches keep the exact arithmetic).  The materialised side flux (hb2_compute_diffusive_flux_*) is always exact. */
 int hb2_diffusive_plan_set_math(hb2_diff_plan_t plan, int32_t math);
+/* Which reconstructor of the reference's DiffusiveFluxReconstructorManager (DiffusiveFluxReconstructorManager.cpp:13-92)
+ * hb2_compute_diffusive_flux_* stands for:
+ *   HB2_DIFF_NODE_SIXTH_ORDER      "SIXTH_ORDER"          DiffusiveFluxReconstructorNodeSixthOrder (default; every shipped deck)
+ *   HB2_DIFF_MIDPOINT_SIXTH_ORDER  "MIDPOINT_SIXTH_ORDER" DiffusiveFluxReconstructorMidpointSixthOrder
+ *       (src/flow/diffusive_flux_reconstructors/midpoint/DiffusiveFluxReconstructorMidpoint.cpp:38-2330,
+ *       DiffusiveFluxReconstructorMidpointSixthOrder.cpp:68-1799): the flux is formed at the midpoints of the flux direction
+ *       from staggered derivatives, interpolated node derivatives and interpolated diffusivities
+ *       (FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp:2365-3657).  Same six-ghost layout of Q (the cells within 5 of
+ *       the interior are read); the flux-free update exists for the node reconstructor only. */
+#define HB2_DIFF_NODE_SIXTH_ORDER 0
+#define HB2_DIFF_MIDPOINT_SIXTH_ORDER 1
+int hb2_diffusive_plan_set_reconstructor(hb2_diff_plan_t plan, int32_t reconstructor);
 
 /* DiffusiveFluxReconstructor::computeDiffusiveFluxOnPatch
  * (include/flow/diffusive_flux_reconstructors/DiffusiveFluxReconstructor.hpp; called from NavierStokes.cpp:1153-1160).

@@ -868,6 +868,158 @@ extern "C" void ref_diff_dt_point(int dim, const double in[9], double out[3])
 """
 
 
+def midpoint_kernels() -> str:
+    """SURVEY row f4, midpoint family: the twelve kernels of DiffusiveFluxReconstructorMidpointSixthOrder
+    (computeFirstDerivativesIn{X,Y,Z}AtMidpoint{X,Y,Z}, computeFirstDerivativesIn{X,Y,Z}AtNode,
+    interpolateDataFromNodeToMidpoint{X,Y,Z}, reconstructFlux{X,Y,Z};
+    DiffusiveFluxReconstructorMidpointSixthOrder.cpp:68-1799) compiled verbatim as members of a stub class and driven over
+    the whole range their stencils allow on a ghost box of width g; the reference's statements for the side diffusivities
+    (FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp:2581-2589, 2615-2623, 2682-2691, 2725-2734, 2768-2777); and
+    FlowModelDiffusiveFluxUtilitiesSingleSpecies::getSideDataOfDiffusiveFluxDiffusivities (:2799-3657: which side diffusivity
+    multiplies which derivative in which equation) compiled verbatim as a member of a stub class."""
+    def rd(rel):
+        with open(os.path.join(REF, rel)) as fh:
+            return fh.read()
+    cls = "DiffusiveFluxReconstructorMidpointSixthOrder"
+    src = rd("src/flow/diffusive_flux_reconstructors/midpoint/DiffusiveFluxReconstructorMidpointSixthOrder.cpp")
+    XYZ = "XYZ"
+    der_mid = [f"computeFirstDerivativesIn{c}AtMidpoint{c}" for c in XYZ]
+    der_node = [f"computeFirstDerivativesIn{c}AtNode" for c in XYZ]
+    interp = [f"interpolateDataFromNodeToMidpoint{c}" for c in XYZ]
+    recon = [f"reconstructFlux{c}" for c in XYZ]
+    names = der_mid + der_node + interp + recon
+    bodies = "\n\n".join(void_member_function(src, cls, n) for n in names)
+    iv = "const hier::IntVector&"
+    sig_der = f"(double*, const double* const, {iv}, {iv}, {iv}, {iv}, {iv}, {iv}, const double&) const;"
+    sig_int = f"(double*, const double* const, {iv}, {iv}, {iv}, {iv}, {iv}, {iv}) const;"
+    sig_rec = f"(double*, const double* const, {iv}, {iv}, {iv}, {iv}, {iv}, const double&) const;"
+    decls = "\n".join(f"    void {n}{sig_der if 'Derivatives' in n else (sig_int if 'interpolate' in n else sig_rec)}" for n in names)
+    du = rd("src/flow/flow_models/single-species/FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp")
+
+    def side_block(first, last, nd):
+        blk = line_range(du, first, last)
+        return "\n        ".join(statement(blk, r"D_%02d\[idx_diffusivities\] = " % m) for m in range(nd))
+    S3 = [side_block(2680, 2692, 8), side_block(2723, 2735, 8), side_block(2766, 2778, 8)]
+    S2 = [side_block(2579, 2590, 7), side_block(2613, 2624, 7)]
+    fside = void_member_function(du, "FlowModelDiffusiveFluxUtilitiesSingleSpecies", "getSideDataOfDiffusiveFluxDiffusivities")
+    return f"""
+namespace ref_mid {{
+namespace hier {{ struct IntVector {{ int v[3]; int operator[](int i) const {{ return v[i]; }} }}; }}
+namespace tbox {{ struct Dimension {{ int d; explicit Dimension(int d_) : d(d_) {{}}
+                  bool operator==(const Dimension& o) const {{ return d == o.d; }} }}; }}
+struct {cls} {{
+    tbox::Dimension d_dim;
+    explicit {cls}(int dim) : d_dim(dim) {{}}
+{decls}
+}};
+{bodies}
+}}
+
+/* kind 0: derivative along dir at the midpoints of dir (midpoints 3 - g .. n + g - 3 of dir, all cells of the ghost box in the
+ * other directions); kind 1: derivative along dir at the nodes (nodes 3 - g .. n + g - 4 of dir); kind 2: interpolation
+ * along dir from the nodes to the midpoints of dir.  Midpoint arrays have one more entry along dir than the ghost box. */
+extern "C" void ref_mid_kernel(int kind, int dim, int dir, int g, const double* u, const int* n, double dx_inv, double* out)
+{{
+    using namespace ref_mid;
+    {cls} k(dim);
+    hier::IntVector ng = {{{{g, g, dim == 3 ? g : 0}}}}, dims = {{{{n[0] + 2 * g, n[1] + 2 * g, dim == 3 ? n[2] + 2 * g : 1}}}};
+    hier::IntVector lo = {{{{-g, -g, dim == 3 ? -g : 0}}}}, dd = dims;
+    lo.v[dir] += 3;
+    dd.v[dir] -= (kind == 1) ? 6 : 5;
+    if (kind == 0) {{
+        if (dir == 0) k.computeFirstDerivativesInXAtMidpointX(out, u, ng, ng, dims, dims, lo, dd, dx_inv);
+        if (dir == 1) k.computeFirstDerivativesInYAtMidpointY(out, u, ng, ng, dims, dims, lo, dd, dx_inv);
+        if (dir == 2) k.computeFirstDerivativesInZAtMidpointZ(out, u, ng, ng, dims, dims, lo, dd, dx_inv);
+    }} else if (kind == 1) {{
+        if (dir == 0) k.computeFirstDerivativesInXAtNode(out, u, ng, ng, dims, dims, lo, dd, dx_inv);
+        if (dir == 1) k.computeFirstDerivativesInYAtNode(out, u, ng, ng, dims, dims, lo, dd, dx_inv);
+        if (dir == 2) k.computeFirstDerivativesInZAtNode(out, u, ng, ng, dims, dims, lo, dd, dx_inv);
+    }} else {{
+        if (dir == 0) k.interpolateDataFromNodeToMidpointX(out, u, ng, ng, dims, dims, lo, dd);
+        if (dir == 1) k.interpolateDataFromNodeToMidpointY(out, u, ng, ng, dims, dims, lo, dd);
+        if (dir == 2) k.interpolateDataFromNodeToMidpointZ(out, u, ng, ng, dims, dims, lo, dd);
+    }}
+}}
+
+/* faces 0 .. n of dir from the midpoint fluxes (a midpoint array on the ghost box of width g); F_face is "+=" on the caller's
+ * zeros like the reference's fillAll(0) */
+extern "C" void ref_mid_reconstruct(int dim, int dir, int g, const double* F_mid, const int* n, double dt, double* F_face)
+{{
+    using namespace ref_mid;
+    {cls} k(dim);
+    hier::IntVector ng = {{{{g, g, dim == 3 ? g : 0}}}}, dims = {{{{n[0] + 2 * g, n[1] + 2 * g, dim == 3 ? n[2] + 2 * g : 1}}}};
+    hier::IntVector lo = {{{{0, 0, 0}}}}, interior = {{{{n[0], n[1], dim == 3 ? n[2] : 1}}}}, dd = interior;
+    dd.v[dir]++;
+    if (dir == 0) k.reconstructFluxX(F_face, F_mid, ng, dims, lo, dd, interior, dt);
+    if (dir == 1) k.reconstructFluxY(F_face, F_mid, ng, dims, lo, dd, interior, dt);
+    if (dir == 2) k.reconstructFluxZ(F_face, F_mid, ng, dims, lo, dd, interior, dt);
+}}
+
+/* side diffusivities of direction dir from the values interpolated to a midpoint; in: mu, mu_v, kappa, u, v, w */
+extern "C" void ref_mid_side_diffusivities(int dim, int dir, const double in[6], double out[8])
+{{
+    const int idx_diffusivities = 0, idx_var_data = 0;
+    double D_00[1], D_01[1], D_02[1], D_03[1], D_04[1], D_05[1], D_06[1], D_07[1] = {{0.0}};
+    const double mu_x[1] = {{in[0]}}, mu_v_x[1] = {{in[1]}}, kappa_x[1] = {{in[2]}}, u_x[1] = {{in[3]}}, v_x[1] = {{in[4]}}, w_x[1] = {{in[5]}};
+    const double *mu_y = mu_x, *mu_v_y = mu_v_x, *kappa_y = kappa_x, *u_y = u_x, *v_y = v_x, *w_y = w_x;
+    const double *mu_z = mu_x, *mu_v_z = mu_v_x, *kappa_z = kappa_x, *u_z = u_x, *v_z = v_x, *w_z = w_x;
+    (void)w_x; (void)w_y; (void)mu_z; (void)mu_v_z; (void)kappa_z; (void)u_z; (void)v_z; (void)w_z;
+    if (dim == 3) {{
+        if (dir == 0) {{ {S3[0]} }}
+        if (dir == 1) {{ {S3[1]} }}
+        if (dir == 2) {{ {S3[2]} }}
+    }} else {{
+        if (dir == 0) {{ {S2[0]} }}
+        if (dir == 1) {{ {S2[1]} }}
+    }}
+    const double* D[8] = {{D_00, D_01, D_02, D_03, D_04, D_05, D_06, D_07}};
+    for (int m = 0; m < (dim == 3 ? 8 : 7); m++) out[m] = D[m][0];
+}}
+
+namespace ref_diff_side_tables {{
+#define HAMERS_SHARED_PTR std::shared_ptr
+namespace tbox {{ struct Dimension {{ int d; explicit Dimension(int d_) : d(d_) {{}}
+                  bool operator==(const Dimension& o) const {{ return d == o.d; }} }}; }}
+namespace pdat {{ template <class T> struct SideData {{ int tag; }}; }}
+namespace DIRECTION {{ enum TYPE {{ X_DIRECTION = 0, Y_DIRECTION = 1, Z_DIRECTION = 2 }}; }}
+struct FlowModel {{ bool hasRegisteredPatch() const {{ return true; }} }};
+struct FlowModelDiffusiveFluxUtilitiesSingleSpecies {{
+    std::weak_ptr<FlowModel> d_flow_model;
+    std::string d_object_name;
+    tbox::Dimension d_dim;
+    int d_num_eqn;
+    bool d_side_data_diffusivities_computed;
+    std::shared_ptr<pdat::SideData<double> > d_side_data_diffusivities;
+    explicit FlowModelDiffusiveFluxUtilitiesSingleSpecies(int dim) : d_object_name("ref"), d_dim(dim), d_num_eqn(dim + 2), d_side_data_diffusivities_computed(true) {{}}
+    void getSideDataOfDiffusiveFluxDiffusivities(std::vector<std::vector<std::shared_ptr<pdat::SideData<double> > > >&,
+                                                 std::vector<std::vector<int> >&, const DIRECTION::TYPE&, const DIRECTION::TYPE&);
+}};
+{fside}
+}}
+
+/* indices of the side diffusivities that multiply the derivatives in direction ddir in equation e of the flux in direction
+ * fdir, in the reference's order (the variables are those of ref_diff_terms: one function serves both reconstructor families) */
+extern "C" int ref_diff_side_terms(int dim, int fdir, int ddir, int e, int diff[4])
+{{
+    using namespace ref_diff_side_tables;
+    std::shared_ptr<FlowModel> fm(new FlowModel());
+    FlowModelDiffusiveFluxUtilitiesSingleSpecies u(dim);
+    u.d_flow_model = fm;
+    u.d_side_data_diffusivities.reset(new pdat::SideData<double>());
+    std::vector<std::vector<std::shared_ptr<pdat::SideData<double> > > > ddata;
+    std::vector<std::vector<int> > didx;
+    u.getSideDataOfDiffusiveFluxDiffusivities(ddata, didx, (DIRECTION::TYPE)fdir, (DIRECTION::TYPE)ddir);
+    if (ddata[e].size() != didx[e].size()) return -1;
+    const int n = (int)ddata[e].size();
+    for (int i = 0; i < n && i < 4; i++) {{
+        if (ddata[e][i] != u.d_side_data_diffusivities) return -1;
+        diff[i] = didx[e][i];
+    }}
+    return n;
+}}
+"""
+
+
 def static_inline_functions(text: str) -> str:
     """Return the concatenation of every `static inline ...` function definition in text."""
     out = []
@@ -1239,6 +1391,7 @@ def main() -> int:
     parts.append(diffusive_kernels())
     parts.append(diffusive_term_tables())
     parts.append(diffusive_dt_statements())
+    parts.append(midpoint_kernels())
     gen = os.path.join(OUT, "_generated_ref_kernels.cpp")
     with open(gen, "w") as fh:
         fh.write("\n".join(parts))

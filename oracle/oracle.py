@@ -398,6 +398,45 @@ def compute_diffusive_flux(desc: PatchDesc, tr: Transport, Q: np.ndarray, dt: fl
     return F
 
 
+def compute_diffusive_flux_midpoint(desc: PatchDesc, tr: Transport, Q: np.ndarray, dt: float):
+    """DiffusiveFluxReconstructorMidpointSixthOrder ("MIDPOINT_SIXTH_ORDER"); same arguments as compute_diffusive_flux (the
+    cells within 5 of the interior are read)."""
+    Q = np.ascontiguousarray(Q, dtype=np.float64)
+    assert Q.shape == (desc.neq,) + diff_ghost_shape(desc), (Q.shape, diff_ghost_shape(desc))
+    neq, dim = desc.neq, desc.dim
+    F = [np.full((neq,) + desc.side_shape(a), np.nan) for a in range(dim)]
+    d, t = desc.c(), tr.c()
+    L = lib()
+    L.orc_compute_diffusive_flux_midpoint.restype = C.c_int
+    rc = L.orc_compute_diffusive_flux_midpoint(C.byref(d), C.byref(t), _pp([Q[c] for c in range(neq)]), C.c_double(dt),
+                                               _pp([F[a][e] for a in range(dim) for e in range(neq)]))
+    assert rc == 0
+    return F
+
+
+def mid_point_kernels(u6, dx_inv, F5, dt):
+    """(staggered derivative, interpolation) of six node values around a midpoint, face value of five midpoint fluxes"""
+    L = lib()
+    for f in (L.orc_mid_derivative, L.orc_mid_interpolate, L.orc_mid_reconstruct):
+        f.restype = C.c_double
+    u = (C.c_double * 6)(*[float(x) for x in u6])
+    F = (C.c_double * 5)(*[float(x) for x in F5])
+    return (L.orc_mid_derivative(u, C.c_double(dx_inv)), L.orc_mid_interpolate(u), L.orc_mid_reconstruct(F, C.c_double(dt)))
+
+
+def mid_side_diffusivities(dim, direction, mu, mu_v, kappa, vel):
+    D = (C.c_double * 8)()
+    v = (C.c_double * 3)(*[float(x) for x in list(vel) + [0.0] * (3 - len(vel))])
+    lib().orc_mid_side_diffusivities(int(dim), int(direction), C.c_double(mu), C.c_double(mu_v), C.c_double(kappa), v, D)
+    return np.array(D[:8 if dim == 3 else 7])
+
+
+def mid_side_terms(dim, fdir, ddir, e):
+    n, var, diff = C.c_int(), (C.c_int * 4)(), (C.c_int * 4)()
+    lib().orc_mid_side_terms(int(dim), int(fdir), int(ddir), int(e), C.byref(n), var, diff)
+    return [(var[i], diff[i]) for i in range(n.value)]
+
+
 def advance_stage_ns(desc: PatchDesc, g: int, alpha, beta, U_int, Fc_int, Fd_int, S_int):
     """One NavierStokes::advanceSingleStepOnPatch (conservative diffusive flux).  U_int[m]: (neq, *shape with ghost g)."""
     ncoef, neq, dim = len(alpha), desc.neq, desc.dim

@@ -262,6 +262,194 @@ int orc_compute_diffusive_flux(const orc_desc* d, const orc_transport* tr, const
     return 0;
 }
 
+
+/* ====================================================================================================================
+ * Midpoint family: DiffusiveFluxReconstructorMidpointSixthOrder ("MIDPOINT_SIXTH_ORDER"; no shipped deck selects it).
+ *   driver   src/flow/diffusive_flux_reconstructors/midpoint/DiffusiveFluxReconstructorMidpoint.cpp:38-2330
+ *   kernels  .../midpoint/DiffusiveFluxReconstructorMidpointSixthOrder.cpp:68-1799 (5 ghost cells, :24-30)
+ *   side diffusivities  FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp:2365-2797 (what is interpolated, the D of a
+ *            direction), :2799-3657 (which D multiplies which derivative)
+ * The flux is formed AT THE MIDPOINTS (faces) of the flux direction f: derivatives along f by a staggered sixth-order
+ * difference of the node values, derivatives along the other directions by sixth-order node derivatives interpolated along
+ * f, diffusivities from mu, mu_v, kappa and the velocity interpolated along f; the face flux is a five-midpoint
+ * combination, times dt.  Arrays staged like the reference stages them (every intermediate is its own array).
+ * Parity status: the twelve kernels, the side-diffusivity statements and the side term table are pinned against the
+ * reference's own code compiled verbatim (oracle/build_ref.py: midpoint_kernels; tests/test_oracle_diffusive_midpoint.py);
+ * loop ranges and the order of the derivative groups are restated from the driver.
+ * Midpoint arrays here use the ghost-box layout: midpoint i of direction f (the face between cells i - 1 and i) is stored
+ * at cell index i. */
+
+/* DiffusiveFluxReconstructorMidpointSixthOrder.cpp:80-82 / :962-964 / :1400-1406 */
+static const double a_dm = 75.0 / 64.0, b_dm = -(25.0 / 384.0), c_dm = 3.0 / 640.0;
+static const double a_im = 75.0 / 128.0, b_im = -(25.0 / 256.0), c_im = 3.0 / 256.0;
+
+/* u[0..5] = nodes LLL, LL, L, R, RR, RRR around the midpoint */
+double orc_mid_derivative(const double u[6], double dx_inv)
+{
+    return (a_dm * (u[3] - u[2]) + b_dm * (u[4] - u[1]) + c_dm * (u[5] - u[0])) * dx_inv;
+}
+double orc_mid_interpolate(const double u[6])
+{
+    return (a_im * (u[3] + u[2]) + b_im * (u[4] + u[1]) + c_im * (u[5] + u[0]));
+}
+/* F[0..4] = midpoints LL, L, the face's own, R, RR */
+double orc_mid_reconstruct(const double F[5], double dt)
+{
+    const double a_r = a_dm + b_dm + c_dm;
+    const double b_r = b_dm + c_dm;
+    const double c_r = c_dm;
+    return dt * (a_r * (F[2]) + b_r * (F[1] + F[3]) + c_r * (F[0] + F[4]));
+}
+
+/* FlowModelDiffusiveFluxUtilitiesSingleSpecies.cpp:2682-2691 (x), 2725-2734 (y), 2768-2777 (z); 2-D :2581-2589, 2615-2623 */
+void orc_mid_side_diffusivities(int dim, int dir, double mu, double mu_v, double kappa, const double* vel, double* D)
+{
+    const double un = vel[dir];
+    D[0] = -(4.0 / 3.0 * mu + mu_v);
+    D[1] = 2.0 / 3.0 * mu - mu_v;
+    D[2] = -mu;
+    D[3] = -un * (4.0 / 3.0 * mu + mu_v);
+    D[4] = un * (2.0 / 3.0 * mu - mu_v);
+    int m = 5;
+    for (int a = 0; a < dim; a++)
+        if (a != dir) D[m++] = -vel[a] * mu;
+    D[m] = -kappa;
+}
+
+/* index of the side diffusivity of term ti of (flux direction, derivative direction, equation); the variables are those of
+ * terms3 / terms2 (one function of the reference serves both reconstructor families) */
+static const signed char side3[3][3][5][4] = {
+    {{{-1, -1, -1, -1}, {0, -1, -1, -1}, {2, -1, -1, -1}, {2, -1, -1, -1}, {3, 5, 6, 7}},
+     {{-1, -1, -1, -1}, {1, -1, -1, -1}, {2, -1, -1, -1}, {-1, -1, -1, -1}, {5, 4, -1, -1}},
+     {{-1, -1, -1, -1}, {1, -1, -1, -1}, {-1, -1, -1, -1}, {2, -1, -1, -1}, {6, 4, -1, -1}}},
+    {{{-1, -1, -1, -1}, {2, -1, -1, -1}, {1, -1, -1, -1}, {-1, -1, -1, -1}, {4, 5, -1, -1}},
+     {{-1, -1, -1, -1}, {2, -1, -1, -1}, {0, -1, -1, -1}, {2, -1, -1, -1}, {5, 3, 6, 7}},
+     {{-1, -1, -1, -1}, {-1, -1, -1, -1}, {1, -1, -1, -1}, {2, -1, -1, -1}, {6, 4, -1, -1}}},
+    {{{-1, -1, -1, -1}, {2, -1, -1, -1}, {-1, -1, -1, -1}, {1, -1, -1, -1}, {4, 5, -1, -1}},
+     {{-1, -1, -1, -1}, {-1, -1, -1, -1}, {2, -1, -1, -1}, {1, -1, -1, -1}, {4, 6, -1, -1}},
+     {{-1, -1, -1, -1}, {2, -1, -1, -1}, {2, -1, -1, -1}, {0, -1, -1, -1}, {5, 6, 3, 7}}}};
+static const signed char side2[2][2][4][4] = {
+    {{{-1, -1, -1, -1}, {0, -1, -1, -1}, {2, -1, -1, -1}, {3, 5, 6, -1}},
+     {{-1, -1, -1, -1}, {1, -1, -1, -1}, {2, -1, -1, -1}, {5, 4, -1, -1}}},
+    {{{-1, -1, -1, -1}, {2, -1, -1, -1}, {1, -1, -1, -1}, {4, 5, -1, -1}},
+     {{-1, -1, -1, -1}, {2, -1, -1, -1}, {0, -1, -1, -1}, {5, 3, 6, -1}}}};
+
+void orc_mid_side_terms(int dim, int fdir, int ddir, int e, int* n, int var[4], int diff[4])
+{
+    const term_list* tl = terms_of(dim, fdir, ddir, e);
+    *n = tl->n;
+    for (int i = 0; i < tl->n; i++) {
+        var[i] = tl->t[i].var;
+        diff[i] = dim == 3 ? side3[fdir][ddir][e][i] : side2[fdir][ddir][e][i];
+    }
+}
+
+int orc_compute_diffusive_flux_midpoint(const orc_desc* d, const orc_transport* tr, const double* const* Q, double dt,
+                                        double* const* F)
+{
+    if (d->model != ORC_SINGLE_SPECIES || (d->dim != 2 && d->dim != 3)) return 1;
+    const int dim = d->dim, neq = dim + 2;
+    const int n[3] = {d->n[0], d->n[1], dim == 3 ? d->n[2] : 1};
+    const int g2 = dim == 3 ? GD : 0;
+    const long e0 = n[0] + 2 * GD, e1 = n[1] + 2 * GD;
+    const long cs[3] = {1, e0, e0 * e1};
+    const long ncell = orc_diff_ghost_size(d);
+#define CIDX(i, j, k) ((long)((i) + GD) + e0 * ((long)((j) + GD) + e1 * (long)((k) + g2)))
+    /* cell data on the ghost box: velocity, temperature, and the three transport coefficients (constant, but interpolated
+     * like any other cell data: the interpolation weights do not sum to one in floating point) */
+    double* var[4];
+    for (int a = 0; a <= dim; a++) var[a] = (double*)malloc(sizeof(double) * (size_t)ncell);
+    const double kappa = orc_diff_conductivity(tr->c_p, tr->mu, tr->Pr);
+    for (long x = 0; x < ncell; x++) {
+        const double rho = Q[0][x];
+        double ke = 0.0;
+        for (int a = 0; a < dim; a++) {
+            const double v = Q[1 + a][x] / rho;
+            ke = (a == 0) ? v * v : ke + v * v;
+            var[a][x] = v;
+        }
+        const double epsilon = Q[dim + 1][x] / rho - 1.0 / 2.0 * ke;
+        const double p = (d->gamma[0] - 1.0) * rho * epsilon;
+        var[dim][x] = orc_diff_temperature(d->gamma[0], tr->c_v, rho, p);
+    }
+    /* node derivatives of every variable in every direction (DiffusiveFluxReconstructorMidpoint.cpp:3013-3136: the whole
+     * ghost box shrunk by three along the derivative direction) */
+    double* dnode[4][3];
+    for (int a = 0; a <= dim; a++)
+        for (int dd = 0; dd < dim; dd++) {
+            dnode[a][dd] = (double*)calloc((size_t)ncell, sizeof(double));
+            orc_diff_derivative_array(dim, dd, var[a], d->n, 1.0 / d->dx[dd], dnode[a][dd]);
+        }
+    double* dmid = (double*)malloc(sizeof(double) * (size_t)ncell);
+    double* Fm = (double*)malloc(sizeof(double) * (size_t)ncell);
+    double* Dm[8];
+    for (int m = 0; m < 8; m++) Dm[m] = (double*)malloc(sizeof(double) * (size_t)ncell);
+    const double cmu[6] = {tr->mu, tr->mu, tr->mu, tr->mu, tr->mu, tr->mu};
+    const double cmv[6] = {tr->mu_v, tr->mu_v, tr->mu_v, tr->mu_v, tr->mu_v, tr->mu_v};
+    const double cka[6] = {kappa, kappa, kappa, kappa, kappa, kappa};
+    const double mu_m = orc_mid_interpolate(cmu), mu_v_m = orc_mid_interpolate(cmv), kappa_m = orc_mid_interpolate(cka);
+    for (int f = 0; f < dim; f++) {
+        /* midpoints -2 .. n_f + 2 of the flux direction, interior cells of the others (:1466-1470) */
+        int lo[3] = {0, 0, 0}, hi[3] = {n[0], n[1], n[2]};
+        lo[f] = -2;
+        hi[f] = n[f] + 3;
+#define FOR_MIDPOINTS for (int k = lo[2]; k < hi[2]; k++) for (int j = lo[1]; j < hi[1]; j++) for (int i = lo[0]; i < hi[0]; i++)
+        /* side diffusivities of direction f from the interpolated transport coefficients and velocity */
+        FOR_MIDPOINTS {
+            const long x = CIDX(i, j, k);
+            double vel[3] = {0.0, 0.0, 0.0}, Dx[8], s[6];
+            for (int a = 0; a < dim; a++) {
+                for (int m = 0; m < 6; m++) s[m] = var[a][x + (m - 3) * cs[f]];
+                vel[a] = orc_mid_interpolate(s);
+            }
+            orc_mid_side_diffusivities(dim, f, mu_m, mu_v_m, kappa_m, vel, Dx);
+            for (int m = 0; m < (dim == 3 ? 8 : 7); m++) Dm[m][x] = Dx[m];
+        }
+        for (int e = 0; e < neq; e++) {
+            memset(Fm, 0, sizeof(double) * (size_t)ncell);
+            for (int dd = 0; dd < dim; dd++) {
+                int nt, tv[4], td[4];
+                orc_mid_side_terms(dim, f, dd, e, &nt, tv, td);
+                for (int ti = 0; ti < nt; ti++) {
+                    const double* src = (dd == f) ? var[tv[ti]] : dnode[tv[ti]][dd];
+                    FOR_MIDPOINTS {
+                        const long x = CIDX(i, j, k);
+                        double s[6];
+                        for (int m = 0; m < 6; m++) s[m] = src[x + (m - 3) * cs[f]];
+                        dmid[x] = (dd == f) ? orc_mid_derivative(s, 1.0 / d->dx[f]) : orc_mid_interpolate(s);
+                    }
+                    const double* mu = Dm[td[ti]];
+                    FOR_MIDPOINTS {
+                        const long x = CIDX(i, j, k);
+                        Fm[x] += mu[x] * dmid[x];
+                    }
+                }
+            }
+            double* Fs = F[f * neq + e];
+            const int fn[3] = {n[0] + (f == 0), n[1] + (f == 1), n[2] + (f == 2)};
+            for (int k = 0; k < fn[2]; k++)
+                for (int j = 0; j < fn[1]; j++)
+                    for (int i = 0; i < fn[0]; i++) {
+                        const long x = CIDX(i, j, k);
+                        double s[5];
+                        for (int m = 0; m < 5; m++) s[m] = Fm[x + (m - 2) * cs[f]];
+                        double v = 0.0;                                   /* fillAll(0), then "+=" */
+                        v += orc_mid_reconstruct(s, dt);
+                        Fs[i + (long)fn[0] * ((long)j + (long)fn[1] * (long)k)] = v;
+                    }
+        }
+#undef FOR_MIDPOINTS
+    }
+    for (int m = 0; m < 8; m++) free(Dm[m]);
+    free(Fm);
+    free(dmid);
+    for (int a = 0; a <= dim; a++)
+        for (int dd = 0; dd < dim; dd++) free(dnode[a][dd]);
+    for (int a = 0; a <= dim; a++) free(var[a]);
+#undef CIDX
+    return 0;
+}
+
 /* FlowModelSingleSpecies.cpp:4661-4665: MAX_DIFFUSIVITY = max(mu/rho, mu_v/rho, kappa/(rho c_p)), c_p the isobaric specific
  * heat of the equation of state (gamma/(gamma - 1) R, EquationOfStateMixingRulesIdealGas.cpp:113) */
 double orc_diff_max_diffusivity(double mu, double mu_v, double kappa, double c_p_eos, double rho)

@@ -55,6 +55,16 @@ void orc_diff_diffusivities(int dim, double mu, double mu_v, double kappa, const
 /* the terms of equation e of the node flux in direction fdir that carry a derivative in direction ddir */
 void orc_diff_terms(int dim, int fdir, int ddir, int e, int* n, int var[4], int diff[4]);
 
+/* ---- midpoint family: DiffusiveFluxReconstructorMidpointSixthOrder ("MIDPOINT_SIXTH_ORDER") ----
+ * same argument meaning as orc_compute_diffusive_flux; reads the cells within 5 of the interior */
+int orc_compute_diffusive_flux_midpoint(const orc_desc* d, const orc_transport* tr, const double* const* Q, double dt,
+                                        double* const* F);
+double orc_mid_derivative(const double u[6], double dx_inv);
+double orc_mid_interpolate(const double u[6]);
+double orc_mid_reconstruct(const double F[5], double dt);
+void orc_mid_side_diffusivities(int dim, int dir, double mu, double mu_v, double kappa, const double* vel, double* D);
+void orc_mid_side_terms(int dim, int fdir, int ddir, int e, int* n, int var[4], int diff[4]);
+
 #ifdef __cplusplus
 }
 #endif

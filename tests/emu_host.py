@@ -133,6 +133,18 @@ def diffusive_flux(desc, tr, Q, dt):
     return F
 
 
+def diffusive_flux_midpoint(desc, tr, Q, dt):
+    """the midpoint family (DiffusiveFluxReconstructorMidpointSixthOrder) through the product's thread functions"""
+    neq, dim = desc.neq, desc.dim
+    F = [np.full((neq,) + desc.side_shape(a), np.nan) for a in range(dim)]
+    Q = np.ascontiguousarray(Q)
+    d = _ddesc(desc, tr)
+    rc = dlib().emu_diffusive_flux_midpoint(C.byref(d), _pp([Q[c] for c in range(neq)]), C.c_double(dt),
+                                            _pp([F[a][e] for a in range(dim) for e in range(neq)]))
+    assert rc == 0
+    return F
+
+
 def advance_stage_ns(desc, tr, g, alpha, beta, U_int, Fc_int, Fd_int, S_int):
     ncoef, neq, dim = len(alpha), desc.neq, desc.dim
     U_out = np.full_like(np.ascontiguousarray(U_int[0]), np.nan)

@@ -180,6 +180,44 @@ extern "C" int emu_diff_divergence_accumulate(const EmuDiffDesc* d, const double
     return d->dim == 2 ? run_div<2>(d, Q, dt, g, beta, U) : run_div<3>(d, Q, dt, g, beta, U);
 }
 
+/* midpoint family: the thread functions of k_diff_primitives / k_diff_mid_flux / k_diff_mid_face from plain loops */
+template <int DIM, int FDIR>
+static void run_mid_dir(const DiffGeom& G, const DiffConsts& K, std::vector<std::vector<double>>& P, std::vector<std::vector<double>>& Fm,
+                        double dt, double* const* F)
+{
+    DiffMidPtrs A{};
+    for (int v = 0; v < DIM + 1; v++) A.P[v] = P[v].data();
+    for (int e = 0; e < DIM + 2; e++) {
+        A.Fm[e] = Fm[e].data();
+        A.F[e] = F[FDIR * (DIM + 2) + e];
+    }
+    for (long long t = 0; t < diff_mid_count<DIM, FDIR>(G); t++) diff_mid_flux_thread<DIM, FDIR>(G, K, A, t);
+    for (long long t = 0; t < diff_face_count<DIM, FDIR>(G); t++) diff_mid_face_thread<DIM, FDIR>(G, A, dt, t);
+}
+
+template <int DIM>
+static int run_mid(const EmuDiffDesc* d, const double* const* Q, double dt, double* const* F)
+{
+    DiffGeom G;
+    make_diff_geom(d->dim, d->n, d->dx, HB2_DIFF_G, &G);
+    DiffConsts K{d->gamma, d->c_v, d->mu, d->mu_v, d->c_p * d->mu / d->Pr};
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    std::vector<std::vector<double>> P(DIM + 1, std::vector<double>((size_t)G.ncell_g, nan)), Fm(DIM + 2, std::vector<double>((size_t)G.ncell_g, nan));
+    DiffPtrs A{};
+    for (int c = 0; c < DIM + 2; c++) A.Q[c] = Q[c];
+    for (int v = 0; v < DIM + 1; v++) A.P[v] = P[v].data();
+    for (long long x = 0; x < G.ncell_g; x++) diff_primitives_thread<DIM>(K, A, x);
+    run_mid_dir<DIM, 0>(G, K, P, Fm, dt, F);
+    run_mid_dir<DIM, 1>(G, K, P, Fm, dt, F);
+    if (DIM == 3) run_mid_dir<DIM, (DIM == 3 ? 2 : 1)>(G, K, P, Fm, dt, F);
+    return 0;
+}
+
+extern "C" int emu_diffusive_flux_midpoint(const EmuDiffDesc* d, const double* const* Q, double dt, double* const* F)
+{
+    return d->dim == 2 ? run_mid<2>(d, Q, dt, F) : run_mid<3>(d, Q, dt, F);
+}
+
 /* The re-associated arithmetic of the flux-free route (HB2_MATH_FAST; the point functions the marching kernels of
  * hb2_diffusive_march.cuh call with MATH = 1), 3-D, from plain loops: primitives on the ghost box, node fluxes on the interior
  * extended by three, then the update of every interior cell. */

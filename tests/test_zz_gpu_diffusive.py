@@ -54,6 +54,44 @@ def test_diffusive_flux_device_and_host_entry_points(dim, N, product_lib):
     plan.close()
 
 
+@pytest.mark.parametrize("dim,N", [(2, (24, 17)), (3, (13, 10, 12)), (2, (1, 1)), (3, (7, 1, 3)), (3, (64, 48, 40)), (2, (300, 200)), (3, (27, 3, 2))])
+def test_midpoint_reconstructor_flux(dim, N, product_lib):
+    """hb2_diffusive_plan_set_reconstructor(HB2_DIFF_MIDPOINT_SIXTH_ORDER): DiffusiveFluxReconstructorMidpointSixthOrder
+    through the C ABI against the oracle, bit for bit; the flux-free route refuses the midpoint reconstructor; switching back
+    gives the node flux again."""
+    import torch
+
+    from hamers_b200 import abi
+
+    desc, U = _state(dim, N)
+    Q = pb.pad_periodic(U, orc.GD)
+    dt = 1.0e-3
+    Fo = orc.compute_diffusive_flux_midpoint(desc, TR, Q, dt)
+    plan = _plan(desc).set_reconstructor(abi.DIFF_MIDPOINT_SIXTH_ORDER)
+    Qd = torch.from_numpy(Q).cuda()
+    Fd = [torch.full((desc.neq,) + desc.side_shape(a), float("nan"), dtype=torch.float64, device="cuda") for a in range(dim)]
+    l0 = plan.launch_count
+    plan.compute_diffusive_flux(Qd, dt, Fd)
+    torch.cuda.synchronize()
+    for a in range(dim):
+        assert np.array_equal(Fd[a].cpu().numpy(), Fo[a]), f"dir {a}"
+    assert plan.launch_count - l0 == 1 + 2 * dim
+    Fh = plan.compute_diffusive_flux_host(Q, dt)
+    for a in range(dim):
+        assert np.array_equal(Fh[a], Fo[a]), f"host entry point, dir {a}"
+    with pytest.raises(abi.HamersB200Error):
+        plan.divergence_accumulate(Qd, dt, 6, 1.0, torch.zeros_like(Qd))
+    with pytest.raises(abi.HamersB200Error):
+        plan.set_reconstructor(7)
+    plan.set_reconstructor(abi.DIFF_NODE_SIXTH_ORDER)
+    plan.compute_diffusive_flux(Qd, dt, Fd)
+    torch.cuda.synchronize()
+    Fn = orc.compute_diffusive_flux(desc, TR, Q, dt)
+    for a in range(dim):
+        assert np.array_equal(Fd[a].cpu().numpy(), Fn[a]), f"node again, dir {a}"
+    plan.close()
+
+
 @pytest.mark.parametrize("dim,g", [(2, 6), (3, 6), (3, 4)])
 def test_ns_stage_update(dim, g, product_lib):
     import torch
