@@ -44,6 +44,10 @@
 #ifndef HB2_PREFETCH_R
 #define HB2_PREFETCH_R 0
 #endif
+/* steady-state variant of the iteration body (no "wanted" tests) for the interior iterations of full blocks; 0 = off */
+#ifndef HB2_STEADY
+#define HB2_STEADY 1
+#endif
 /* L2 prefetch distance (iterations) of the update phase's HBM inputs; 0 = off */
 #ifndef HB2_PREFETCH_L2
 #define HB2_PREFETCH_L2 1
@@ -125,6 +129,7 @@ struct PencilCtx {
     int pp;          /* pencil index inside the block */
     int o;           /* position inside the chunk */
     bool valid;      /* pencil exists */
+    bool full;       /* every pencil of the block exists (block-uniform) */
     int c0, c1;      /* segment [c0, c1) of cells along the sweep axis */
     int i, j, k;     /* coordinates of sweep cell 0 of the pencil */
     long long base;  /* ghost-box index of sweep cell 0 */
@@ -148,14 +153,17 @@ HB2_HD PencilCtx pencil_ctx(const DirArgs& A, const BlockId& b, int tid)
         c.j = b.x * Sh::P + c.pp;
         c.k = b.y;
         c.valid = c.j < G.n[1];
+        c.full = (b.x + 1) * Sh::P <= G.n[1];
     } else if (DIR == 1) {
         c.i = b.x * Sh::P + c.pp;
         c.k = b.y;
         c.valid = c.i < G.n[0];
+        c.full = (b.x + 1) * Sh::P <= G.n[0];
     } else {
         c.i = b.x * Sh::P + c.pp;
         c.j = b.y;
         c.valid = c.i < G.n[0];
+        c.full = (b.x + 1) * Sh::P <= G.n[0];
     }
     const int N = G.n[DIR];
     c.c0 = b.z * A.seg_len;
@@ -373,21 +381,23 @@ HB2_HD bool face_wanted(const PencilCtx& c, int t, int& f)
 }
 
 /* the shock-sensor decision byte of the face's right cell (fetched one iteration ahead) */
-template <class Tr, int DIR, int MATH>
+template <class Tr, int DIR, int MATH, bool STEADY = false>
 HB2_HD unsigned int face_flag_fetch(const DirArgs& A, const PencilCtx& c, int t)
 {
     int f;
-    if (!face_wanted<Tr, DIR, MATH>(c, t, f)) return 0;
+    const bool wanted = face_wanted<Tr, DIR, MATH>(c, t, f);
+    if (!STEADY && !wanted) return 0;
     return A.hyb[c.base + (long long)f * c.st];
 }
 
-template <class Tr, int DIR, int MATH>
+template <class Tr, int DIR, int MATH, bool STEADY = false>
 HB2_HD void phase_face(const DirArgs& A, double* smem, const PencilCtx& c, int t, unsigned int flag)
 {
     using Sh = SweepShape<Tr, DIR, MATH>;
     constexpr int NEQ = Tr::NEQ;
     int f;
-    if (!face_wanted<Tr, DIR, MATH>(c, t, f)) return;
+    const bool wanted = face_wanted<Tr, DIR, MATH>(c, t, f);
+    if (!STEADY && !wanted) return;
     const bool hybrid = (flag >> DIR) & 1;
     double* sM = smem + Sh::OFF_M;
     /* stencil window: cells f-3..f+2 at win[comp*CSV + m*MS] */
@@ -641,21 +651,37 @@ HB2_HD void pipeline_prologue(const DirArgs& A, double* smem, const PencilCtx& c
     pr.flag = face_flag_fetch<Tr, DIR, MATH>(A, c, 0);
 }
 
-template <class Tr, int DIR, int MATH, int NTERM>
+/* STEADY iterations: the block has all its pencils and iteration t lies in steady_range() -- every thread loads, commits,
+ * computes a face and updates a cell, so the per-phase "is it wanted" tests (and the basic-block boundaries they put between
+ * the phases) are compiled out.  Same arithmetic on the same data: the variant only removes tests that are known to pass. */
+template <class Tr, int DIR, int MATH>
+HB2_HD void steady_range(const PencilCtx& c, int& t_lo, int& t_hi)
+{
+    using Sh = SweepShape<Tr, DIR, MATH>;
+    const int len = c.c1 - c.c0;
+    t_lo = 1 + (8 + Sh::C - 1) / Sh::C;          /* update(t - 1) starts at cell c0: (t - 1) C >= 8 */
+    t_hi = (len + 8) / Sh::C - 3;                /* load(t + 2) still inside the pencil for every position of the chunk:
+                                                    (t + 3) C <= len + 8; implies face(t), face(t + 1), update(t - 1), update(t) */
+}
+
+template <class Tr, int DIR, int MATH, int NTERM, bool STEADY = false>
 HB2_HD void pipeline_iteration(const DirArgs& A, double* smem, const PencilCtx& c, int t, int nsteps, PipeRegs<Tr>& pr)
 {
-    if (!A.bulk) {
-        if (pr.have) {
+    using Sh = SweepShape<Tr, DIR, MATH>;
+    if (STEADY || !A.bulk) {
+        if (STEADY || pr.have) {
             double q[Tr::NCOMP];
             stage_wait_all();
             staged_cons<Tr, DIR, MATH>(smem, c, q);
             phase_commit<Tr, DIR, MATH>(A, smem, c, pr.s, q);
         }
-        pr.have = load_wanted<Tr, DIR, MATH>(c, t + 2, pr.s);
+        const bool have = load_wanted<Tr, DIR, MATH>(c, t + 2, pr.s);
+        pr.have = STEADY ? 1 : have;
         if (pr.have) stage_cons<Tr, DIR, MATH>(A, smem, c, c.base + (long long)pr.s * c.st);
     }
     int cc;
-    const bool do_update = update_wanted<Tr, DIR, MATH>(c, t - 1, cc);
+    const bool upd = update_wanted<Tr, DIR, MATH>(c, t - 1, cc);
+    const bool do_update = STEADY ? true : upd;
     UpdateIn<Tr> uin;
     constexpr bool FUSED = (NTERM != HB2_NTERM_EMIT);
     /* The HBM inputs of the update phase (running right-hand side, RK states) are loaded where they are consumed: held
@@ -663,20 +689,33 @@ HB2_HD void pipeline_iteration(const DirArgs& A, double* smem, const PencilCtx& 
      * latency is taken out one iteration ahead with L2 prefetches instead (no register, no shared memory): HB2_PREFETCH_L2. */
     if (HB2_PREFETCH_L2 && FUSED) {
         int cn;
-        if (update_wanted<Tr, DIR, MATH>(c, t + HB2_PREFETCH_L2 - 1, cn)) update_prefetch<Tr, DIR, NTERM>(A, c, cn);
+        const bool pre = update_wanted<Tr, DIR, MATH>(c, t + HB2_PREFETCH_L2 - 1, cn);
+        if (STEADY || pre) update_prefetch<Tr, DIR, NTERM>(A, c, cn);
     }
     if (HB2_PREFETCH_R && do_update) update_fetch<Tr, DIR, FUSED>(A, c, cc, uin);
     unsigned int flag;
     if (HB2_PREFETCH_FLAG) {
         flag = pr.flag;
-        pr.flag = (t + 1 < nsteps) ? face_flag_fetch<Tr, DIR, MATH>(A, c, t + 1) : 0u;
+        pr.flag = (STEADY || t + 1 < nsteps) ? face_flag_fetch<Tr, DIR, MATH, STEADY>(A, c, t + 1) : 0u;
     } else {
-        flag = (t < nsteps) ? face_flag_fetch<Tr, DIR, MATH>(A, c, t) : 0u;
+        flag = (STEADY || t < nsteps) ? face_flag_fetch<Tr, DIR, MATH, STEADY>(A, c, t) : 0u;
     }
-    if (t < nsteps) phase_face<Tr, DIR, MATH>(A, smem, c, t, flag);
+    if (STEADY || t < nsteps) phase_face<Tr, DIR, MATH, STEADY>(A, smem, c, t, flag);
     if (!HB2_PREFETCH_R && do_update) update_fetch<Tr, DIR, FUSED>(A, c, cc, uin);
     if (do_update) phase_update<Tr, DIR, MATH, NTERM>(A, smem, c, cc, uin);
-    if (A.bulk) pipeline_consume<Tr, DIR, MATH>(A, smem, c, t + 1, pr.mbar, pr.parity);
+    if (!STEADY && A.bulk) pipeline_consume<Tr, DIR, MATH>(A, smem, c, t + 1, pr.mbar, pr.parity);
+}
+
+/* one iteration, steady or general (block-uniform choice): what the kernel and the host emulation both call */
+template <class Tr, int DIR, int MATH, int NTERM>
+HB2_HD void pipeline_step(const DirArgs& A, double* smem, const PencilCtx& c, int t, int nsteps, int t_lo, int t_hi, PipeRegs<Tr>& pr)
+{
+#if HB2_STEADY
+    if (c.full && !A.bulk && t >= t_lo && t <= t_hi)
+        pipeline_iteration<Tr, DIR, MATH, NTERM, true>(A, smem, c, t, nsteps, pr);
+    else
+#endif
+        pipeline_iteration<Tr, DIR, MATH, NTERM, false>(A, smem, c, t, nsteps, pr);
 }
 
 }  // namespace hb2

@@ -80,10 +80,12 @@ __global__ void __launch_bounds__((SweepShape<Tr, DIR, MATH>::NT), (MATH == 1 &&
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     pipeline_prologue<Tr, DIR, MATH>(A, smem, c, pr);
+    int t_lo, t_hi;
+    steady_range<Tr, DIR, MATH>(c, t_lo, t_hi);
     __syncthreads();
     for (int t = 0; t <= nsteps; t++) {
         if (A.bulk) pipeline_issue<Tr, DIR, MATH>(A, smem, c, t + 1, pr.mbar);
-        pipeline_iteration<Tr, DIR, MATH, NTERM>(A, smem, c, t, nsteps, pr);
+        pipeline_step<Tr, DIR, MATH, NTERM>(A, smem, c, t, nsteps, t_lo, t_hi, pr);
         __syncthreads();
     }
 }

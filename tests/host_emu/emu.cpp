@@ -74,6 +74,8 @@ static void run_dir_n(const DirArgs& A)
                 for (auto& v : smem) v = std::nan("");
                 const PencilCtx c0 = pencil_ctx<Tr, DIR, MATH>(A, b, 0);
                 const int nsteps = Sh::nsteps(c0.c1 - c0.c0);
+                int t_lo, t_hi;
+                steady_range<Tr, DIR, MATH>(c0, t_lo, t_hi);
                 const bool rev = (nblock & 1);
                 for (int n = 0; n < Sh::NT; n++) {
                     const int tid = rev ? Sh::NT - 1 - n : n;
@@ -89,7 +91,7 @@ static void run_dir_n(const DirArgs& A)
                         }
                     for (int n = 0; n < Sh::NT; n++) {
                         const int tid = rev ? Sh::NT - 1 - n : n;
-                        pipeline_iteration<Tr, DIR, MATH, NTERM>(A, smem.data(), pencil_ctx<Tr, DIR, MATH>(A, b, tid), t, nsteps, regs[tid]);
+                        pipeline_step<Tr, DIR, MATH, NTERM>(A, smem.data(), pencil_ctx<Tr, DIR, MATH>(A, b, tid), t, nsteps, t_lo, t_hi, regs[tid]);
                     }
                 }
             }

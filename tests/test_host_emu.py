@@ -91,6 +91,40 @@ def test_emulated_ring_wraparound(model, dim, N, seg_len, oracle_lib):
             assert_fast_parity(interior(desc, Ue), interior(desc, Uo))
 
 
+@pytest.mark.parametrize("model,dim,N", [(0, 3, (64, 6, 50)), (1, 2, (64, 70)), (0, 2, (100, 32))])
+def test_emulated_steady_iterations(model, dim, N, oracle_lib):
+    """Blocks that have all their pencils run the interior iterations of a march through the STEADY variant of the iteration
+    body (no per-phase "wanted" tests, hb2_sweep.cuh: pipeline_step); blocks with missing pencils and the first / last
+    iterations run the general one.  All three SSP-RK3 rows with the fused ghost push, both arithmetic variants."""
+    U, dx, gam = pb.random_state(dim, N, model=model, seed=23, shock=True)
+    desc = oracle_lib.PatchDesc(dim=dim, n=N, model=model, ns=len(gam), gamma=gam, dx=dx)
+    Q = pb.pad_periodic(U)
+    dt = 1.0e-3
+    Fo, So = oracle_lib.compute_flux_and_source(desc, Q, dt)
+    Fe, Se = emu_host.flux_and_source(desc, Q, dt, math=0)
+    for a in range(dim):
+        assert np.array_equal(Fe[a], Fo[a]), f"dir {a}"
+    assert np.array_equal(Se, So)
+    for alpha, beta in (([1.0], [1.0]), ([0.75, 0.25], [0.0, 0.25]), ([1.0 / 3.0, 0.0, 2.0 / 3.0], [0.0, 0.0, 2.0 / 3.0])):
+        m = len(alpha)
+        older = []
+        for k in range(m - 1):
+            V = U * (1.0 + 0.01 * k)
+            if model == 1:
+                V[-2:] = U[-2:]
+            older.append(pb.pad_periodic(V))
+        states = older + [Q]
+        none = [None] * (m - 1)
+        Uo = oracle_lib.advance_stage(desc, alpha, beta, states, none + [Fo], none + [So])
+        for math in (0, 1):
+            Ue = emu_host.fused_stage(desc, alpha, beta, states, dt, math=math, push=True)
+            if math == 0:
+                assert np.array_equal(interior(desc, Ue), interior(desc, Uo))
+            else:
+                assert_fast_parity(interior(desc, Ue), interior(desc, Uo))
+            assert np.array_equal(Ue, pb.pad_periodic(np.ascontiguousarray(interior(desc, Ue))))
+
+
 @pytest.mark.parametrize("name", ["ss2d", "ss3d", "fe3d"])
 def test_emulated_push_fills_the_ghosts(name, oracle_lib):
     """Ghost fill fused into the update (push_cell): with the patch as its own periodic neighbour every ghost cell of
