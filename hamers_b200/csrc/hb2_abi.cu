@@ -404,7 +404,7 @@ void base_args(hb2_plan_t p, const double* const* Q, double dt, DirArgs* A)
     A->K = p->K;
     for (int c = 0; c < p->ncomp; c++) A->Q[c] = Q[c];
     A->hyb = p->hyb;
-    A->dt = dt;
+    dir_args_set_dt(A, dt);
     A->T = p->T;
     /* bulk-copy staging needs 16-byte aligned rows (hb2_sweep.cuh): even n[0] and ghost width, aligned component pointers;
      * the x sweep also an even segment length (checked where seg_len is set) */

@@ -536,8 +536,7 @@ HB2_HD void phase_update(const DirArgs& A, const double* smem, const PencilCtx& 
         node_flux_prim<Tr, DIR, Sh::CSV>(sV + v_m1, sV[(Sh::NV - 1) * Sh::CSV + v_m1], A.K, Nm);
         if (fused) {
             /* difference form: F[c+1] - F[c] = dt (3/2 (M[c+1]-M[c]) + 1/30 (M[c+2]-M[c-1]) - 3/10 (N[c+1]-N[c-1])) */
-            const double k0 = A.dt / dxd;
-            const double k1 = 1.5 * k0, k2 = (1.0 / 30.0) * k0, k3 = (3.0 / 10.0) * k0;
+            const double k1 = A.kf[DIR][0], k2 = A.kf[DIR][1], k3 = A.kf[DIR][2];
 #pragma unroll
             for (int e = 0; e < NEQ; e++) {
                 const double* M = sM + e * Sh::CS;
@@ -706,14 +705,58 @@ HB2_HD void pipeline_iteration(const DirArgs& A, double* smem, const PencilCtx& 
     if (!STEADY && A.bulk) pipeline_consume<Tr, DIR, MATH>(A, smem, c, t + 1, pr.mbar, pr.parity);
 }
 
+/* SKEWED steady iteration: the phases of one iteration only read what EARLIER iterations wrote to the rings, so a warp may run
+ * them in any order.  Odd warps run [commit, stage, update] before [face], even warps the other way round: at any time half
+ * the warps of a block are in the FP64-dense face phase and half in the memory / integer-heavy ones, instead of all sixteen
+ * warps of an SM hitting the FP64 pipe together and leaving it idle together.  The two parts exist once in the code; a
+ * two-trip loop with a warp-uniform test picks the order. */
+#ifndef HB2_SKEW
+#define HB2_SKEW 0
+#endif
+template <class Tr, int DIR, int MATH, int NTERM>
+HB2_HD void pipeline_iteration_skewed(const DirArgs& A, double* smem, const PencilCtx& c, int t, int nsteps, PipeRegs<Tr>& pr)
+{
+    constexpr bool FUSED = (NTERM != HB2_NTERM_EMIT);
+    const bool face_first = ((c.tid >> 5) & 1) == 0;
+#pragma unroll 1
+    for (int part = 0; part < 2; part++) {
+        if ((part == 0) == face_first) {
+            const unsigned int flag = pr.flag;
+            pr.flag = face_flag_fetch<Tr, DIR, MATH, true>(A, c, t + 1);
+            phase_face<Tr, DIR, MATH, true>(A, smem, c, t, flag);
+        } else {
+            double q[Tr::NCOMP];
+            stage_wait_all();
+            staged_cons<Tr, DIR, MATH>(smem, c, q);
+            phase_commit<Tr, DIR, MATH>(A, smem, c, pr.s, q);
+            load_wanted<Tr, DIR, MATH>(c, t + 2, pr.s);
+            pr.have = 1;
+            stage_cons<Tr, DIR, MATH>(A, smem, c, c.base + (long long)pr.s * c.st);
+            int cc, cn;
+            update_wanted<Tr, DIR, MATH>(c, t - 1, cc);
+            if (HB2_PREFETCH_L2 && FUSED) {
+                update_wanted<Tr, DIR, MATH>(c, t + HB2_PREFETCH_L2 - 1, cn);
+                update_prefetch<Tr, DIR, NTERM>(A, c, cn);
+            }
+            UpdateIn<Tr> uin;
+            update_fetch<Tr, DIR, FUSED>(A, c, cc, uin);
+            phase_update<Tr, DIR, MATH, NTERM>(A, smem, c, cc, uin);
+        }
+    }
+    (void)nsteps;
+}
+
 /* one iteration, steady or general (block-uniform choice): what the kernel and the host emulation both call */
 template <class Tr, int DIR, int MATH, int NTERM>
 HB2_HD void pipeline_step(const DirArgs& A, double* smem, const PencilCtx& c, int t, int nsteps, int t_lo, int t_hi, PipeRegs<Tr>& pr)
 {
 #if HB2_STEADY
-    if (c.full && !A.bulk && t >= t_lo && t <= t_hi)
-        pipeline_iteration<Tr, DIR, MATH, NTERM, true>(A, smem, c, t, nsteps, pr);
-    else
+    if (c.full && !A.bulk && t >= t_lo && t <= t_hi) {
+        if (HB2_SKEW)
+            pipeline_iteration_skewed<Tr, DIR, MATH, NTERM>(A, smem, c, t, nsteps, pr);
+        else
+            pipeline_iteration<Tr, DIR, MATH, NTERM, true>(A, smem, c, t, nsteps, pr);
+    } else
 #endif
         pipeline_iteration<Tr, DIR, MATH, NTERM, false>(A, smem, c, t, nsteps, pr);
 }

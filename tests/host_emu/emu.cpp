@@ -226,7 +226,7 @@ static void fill_common(const EmuDesc* d, DirArgs* A, const double* const* Q, do
     A->K.weno_alpha_tau = d->weno_alpha_tau > 0.0 ? d->weno_alpha_tau : 35.0;
     const int ncomp = emu_ncomp(d);
     for (int c = 0; c < ncomp; c++) A->Q[c] = Q[c];
-    A->dt = dt;
+    dir_args_set_dt(A, dt);
     T.assign((size_t)A->G.n[0] * A->G.n[1] * A->G.n[2], 0.0);
     A->T = T.data();
 }
