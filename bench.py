@@ -538,13 +538,13 @@ def run_ours(args):
         torch.cuda.empty_cache()
         hnp = host.numpy()
         dte = 0.001 * domain_len / n
-        # slab thicknesses along z.  0 (default): graded -- thick slabs where the wavefront runs freely, thin ones around the
-        # periodic seam (the slabs uploaded last and their neighbours finish after the upload has ended: their download is the
-        # tail of the step, so they are cut thin); K > 1: K equal slabs; 1: one patch through hb2_advance_level_host
-        if args.e2e_patches == 0 and n % 32 == 0 and (n - 5 * (n // 32)) % 6 == 0 and n // 32 >= 12:
+        # slab thicknesses along z.  0 (default): 14 slabs of n/16 planes between two pairs of n/32 (the download of a slab
+        # trails its upload by two slabs plus three stages, so thin slabs start the download stream early; the slabs around
+        # the periodic seam finish after the upload has ended -- their download is the tail of the step -- and are thinner
+        # still); K > 1: K equal slabs; 1: one patch through hb2_advance_level_host
+        if args.e2e_patches == 0 and n % 32 == 0 and n // 32 >= 12:
             thin = n // 32
-            thick = (n - 5 * thin) // 6
-            sizes = [thin] + [thick] * 6 + [thin] * 4
+            sizes = [thin, thin] + [2 * thin] * 14 + [thin, thin]
         elif args.e2e_patches > 1 and n % args.e2e_patches == 0 and n // args.e2e_patches >= 16:
             sizes = [n // args.e2e_patches] * args.e2e_patches
         elif args.e2e_patches == 0 and n % 8 == 0 and n // 8 >= 16:

@@ -14,6 +14,7 @@
  */
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -50,18 +51,29 @@ struct LevelPatch {
     double* S[3];              /* three state buffers, each ncomp * ncell_g doubles */
 };
 
-/* grid: (x, descriptor); one descriptor = one box-to-box copy of every component */
+/* grid: (x, descriptor); one descriptor = one box-to-box copy of every component.  32-bit index arithmetic (a box has fewer
+ * than 2^31 cells), components in the outer loop; gridDim.x is sized by the largest box of the launch (fill_blocks): with a
+ * fixed 8 blocks per descriptor the z-ghost planes of a 512 x 512 slab took 2.2 ms per launch -- more than the four kernels of
+ * the slab's stage together. */
 __global__ void __launch_bounds__(256) k_level_fill(const CopyDesc* __restrict__ D, double* const* __restrict__ ptrs, int ncomp)
 {
     const CopyDesc d = D[blockIdx.y];
-    const long long nb = (long long)d.ext[0] * d.ext[1] * d.ext[2];
-    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < nb * ncomp; id += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(id / nb);
-        const long long r = id % nb;
-        const int i = (int)(r % d.ext[0]), j = (int)((r / d.ext[0]) % d.ext[1]), k = (int)(r / ((long long)d.ext[0] * d.ext[1]));
-        ptrs[d.dst * ncomp + c][d.dst_off + i + d.dst_cs[0] * j + d.dst_cs[1] * k] =
-            ptrs[d.src * ncomp + c][d.src_off + i + d.src_cs[0] * j + d.src_cs[1] * k];
+    const unsigned e0 = (unsigned)d.ext[0], e1 = (unsigned)d.ext[1];
+    const unsigned nb = e0 * e1 * (unsigned)d.ext[2];
+    for (unsigned r = blockIdx.x * blockDim.x + threadIdx.x; r < nb; r += gridDim.x * blockDim.x) {
+        const unsigned q = r / e0, i = r - q * e0;
+        const unsigned k = q / e1, j = q - k * e1;
+        const long long xd = d.dst_off + i + d.dst_cs[0] * j + d.dst_cs[1] * k;
+        const long long xs = d.src_off + i + d.src_cs[0] * j + d.src_cs[1] * k;
+        for (int c = 0; c < ncomp; c++) ptrs[d.dst * ncomp + c][xd] = ptrs[d.src * ncomp + c][xs];
     }
+}
+
+/* blocks along x for a launch whose largest box has max_cells cells: 8 cells per thread, between 8 and 1024 blocks */
+inline unsigned fill_blocks(long long max_cells)
+{
+    long long b = (max_cells + 256 * 8 - 1) / (256 * 8);
+    return (unsigned)(b < 8 ? 8 : (b > 1024 ? 1024 : b));
 }
 
 }  // namespace
@@ -82,14 +94,18 @@ struct hb2_level_s {
     double* d_sr;                               /* 4 doubles per patch: spectral radii */
     /* pipelined host-memory advance (hb2_level_advance_host) */
     std::vector<int> desc_begin;                /* descriptors of destination patch p: [desc_begin[p], desc_begin[p + 1]) */
+    std::vector<long long> desc_max_cells;      /* largest box among the descriptors of destination patch p; [npatch] = level-wide */
     std::vector<std::vector<int>> sources;      /* patches whose data the ghost fill of patch p reads */
     cudaStream_t copy_in, copy_out;
-    std::vector<cudaEvent_t> ev_up, ev_done;
+    std::vector<cudaEvent_t> ev_up, ev_done, ev_lo;   /* ev_lo[p]: the first g interior planes of slab p are on the device */
     /* second compute stream with its own plans (a plan owns the running right-hand side and the sensor bytes of the stage in
      * flight): tasks of even / odd patches alternate between the two, so that the tails of the small grids of thin slabs overlap */
     cudaStream_t stream2;
     std::vector<hb2_plan_t> plans2;
     std::vector<cudaEvent_t> ev_task;           /* [stage * npatch + patch] */
+    /* HB2_LEVEL_TRACE=1: timed events of the pipelined host advance (start, upload, every task, download per patch), printed
+     * to stderr after the step */
+    std::vector<cudaEvent_t> tr;
 };
 
 namespace {
@@ -156,6 +172,12 @@ int build_fill_table(hb2_level_t L)
     }
     for (int p = 0; p < np; p++)
         if (L->desc_begin[p + 1] < L->desc_begin[p]) L->desc_begin[p + 1] = L->desc_begin[p];
+    L->desc_max_cells.assign(np + 1, 0);
+    for (size_t k = 0; k < D.size(); k++) {
+        const long long cells = (long long)D[k].ext[0] * D[k].ext[1] * D[k].ext[2];
+        if (cells > L->desc_max_cells[D[k].dst]) L->desc_max_cells[D[k].dst] = cells;
+        if (cells > L->desc_max_cells[np]) L->desc_max_cells[np] = cells;
+    }
     L->ndesc = (int)D.size();
     if (L->ndesc) {
         HB2L_CUDA(cudaMalloc(&L->d_desc, sizeof(CopyDesc) * D.size()));
@@ -265,9 +287,11 @@ int hb2_level_create(const hb2_patch_desc* model, int32_t npatch, const int32_t*
     }
     HB2L_CUDA(cudaMalloc(&L->d_sr, sizeof(double) * 4 * (size_t)npatch));
     L->ev_up.resize(npatch);
+    L->ev_lo.resize(npatch);
     L->ev_done.resize(npatch);
     for (int p = 0; p < npatch; p++) {
         HB2L_CUDA(cudaEventCreateWithFlags(&L->ev_up[p], cudaEventDisableTiming));
+        HB2L_CUDA(cudaEventCreateWithFlags(&L->ev_lo[p], cudaEventDisableTiming));
         HB2L_CUDA(cudaEventCreateWithFlags(&L->ev_done[p], cudaEventDisableTiming));
     }
     int rc = build_fill_table(L);
@@ -294,6 +318,7 @@ int hb2_level_destroy(hb2_level_t L)
     for (auto plan : L->plans2) hb2_plan_destroy(plan);
     if (L->stream2) cudaStreamDestroy(L->stream2);
     for (auto e : L->ev_up) cudaEventDestroy(e);
+    for (auto e : L->ev_lo) cudaEventDestroy(e);
     for (auto e : L->ev_done) cudaEventDestroy(e);
     if (L->copy_in) cudaStreamDestroy(L->copy_in);
     if (L->copy_out) cudaStreamDestroy(L->copy_out);
@@ -367,7 +392,7 @@ int hb2_level_fill_ghosts(hb2_level_t L, int32_t state)
     if (state < 0 || state > 2) return set_error(-42, "state index out of range");
     if (!L->ndesc) return 0;
     HB2L_CUDA(cudaSetDevice(L->device));
-    dim3 grid(8, (unsigned)L->ndesc);
+    dim3 grid(fill_blocks(L->desc_max_cells[L->patches.size()]), (unsigned)L->ndesc);
     k_level_fill<<<grid, 256, 0, L->stream>>>(L->d_desc, L->d_ptrs[L->where[state]], L->ncomp);
     L->launches++;
     HB2L_CUDA(cudaGetLastError());
@@ -479,51 +504,104 @@ int hb2_level_advance_host(hb2_level_t L, int32_t nstages, const double* alpha, 
     if (nstages < 1 || nstages > 3) return set_error(-20, "hb2_level_advance_host supports 1..3 stages");
     HB2L_CUDA(cudaSetDevice(L->device));
     const int np = (int)L->patches.size();
-    /* upload order: index order, except that a last patch that feeds the first one (periodic stack of slabs) goes first */
-    std::vector<int> uorder, pos(np);
-    bool wrap = false;
-    for (int q : L->sources[0]) wrap = wrap || (q == np - 1 && np > 2);
-    if (wrap) uorder.push_back(np - 1);
-    for (int p = 0; p < np - (wrap ? 1 : 0); p++) uorder.push_back(p);
-    for (int i = 0; i < np; i++) pos[uorder[i]] = i;
+    static const bool trace = [] {
+        const char* v = getenv("HB2_LEVEL_TRACE");
+        return v && *v && atoi(v) != 0;
+    }();
+    /* tr[0] start; tr[1 + p] upload of p done; tr[1 + np + sn * np + p] task done; tr[1 + 4 np + p] download of p done;
+     * tr[1 + 5 np + sn * np + p] task started (behind its stream's waits) */
+    if (trace && L->tr.empty()) {
+        L->tr.resize((size_t)1 + 8 * np);
+        for (auto& e : L->tr) HB2L_CUDA(cudaEventCreate(&e));
+    }
+    if (trace) HB2L_CUDA(cudaEventRecord(L->tr[0], L->copy_in));
     /* When every patch spans the level in all but the slowest direction (a stack of slabs), a patch's ghost cells come from
-     * the FIRST and LAST g interior planes of its neighbours only: those few planes of every patch are uploaded first, so the
-     * first stage of a patch waits for its own bulk alone and the wavefront trails the upload by one slab per stage less. */
+     * the FIRST and LAST g interior planes of its neighbours only. */
     bool slabs = np > 1;
     for (int p = 0; p < np && slabs; p++)
         for (int a = 0; a < L->dim - 1; a++) slabs = slabs && L->patches[p].n[a] == L->level_n[a];
     for (int p = 0; p < np && slabs; p++) slabs = L->patches[p].n[L->dim - 1] > 2 * L->g;
-    if (slabs) {
-        for (int p = 0; p < np; p++) {
-            const LevelPatch& P = L->patches[p];
-            long long off, cnt;
-            transfer_range(L, P, &off, &cnt);
-            const long long plane = cnt / P.n[L->dim - 1], edge = plane * L->g;
-            for (int c = 0; c < L->ncomp; c++) {
-                double* dst = P.S[L->where[0]] + (size_t)c * P.ncell_g;
-                const double* src = U_host[(size_t)p * L->ncomp + c];
-                HB2L_CUDA(cudaMemcpyAsync(dst + off, src + off, sizeof(double) * (size_t)edge, cudaMemcpyHostToDevice, L->copy_in));
-                HB2L_CUDA(cudaMemcpyAsync(dst + off + cnt - edge, src + off + cnt - edge, sizeof(double) * (size_t)edge,
-                                          cudaMemcpyHostToDevice, L->copy_in));
-            }
-        }
-        HB2L_CUDA(cudaEventRecord(L->ev_done[0], L->copy_in));        /* borrowed as "all edge planes are on the device" */
-        HB2L_CUDA(cudaStreamWaitEvent(L->stream, L->ev_done[0], 0));
+    /* HB2_LEVEL_EDGES=all: the edge planes of EVERY slab go up before any bulk (the first form of this schedule: with 18 slabs
+     * that is 28 % of the data in front of the first stage).  Default: the slabs go up whole, in the order of the slowest
+     * direction, low edge first; the first stage of a slab waits for its own planes and for the low edge of the next slab
+     * (the very next copy); only the high edge of the LAST slab, which the first slab needs across the periodic seam, goes
+     * up ahead of everything. */
+    static const bool edges_all = [] {
+        const char* v = getenv("HB2_LEVEL_EDGES");
+        return v && std::string(v) == "all";
+    }();
+    const int zd = L->dim - 1;
+    std::vector<int> uorder, pos(np), znext(np, -1);
+    bool seam = false;
+    if (slabs && !edges_all) {
+        for (int p = 0; p < np; p++) uorder.push_back(p);
+        for (int i = 1; i < np; i++)
+            for (int j = i; j > 0 && L->patches[uorder[j]].lo[zd] < L->patches[uorder[j - 1]].lo[zd]; j--) std::swap(uorder[j], uorder[j - 1]);
+        for (int i = 0; i + 1 < np; i++) znext[uorder[i]] = uorder[i + 1];
+        const LevelPatch &first = L->patches[uorder[0]], &last = L->patches[uorder[np - 1]];
+        seam = ((L->periodic_mask >> zd) & 1) && first.lo[zd] == 0 && last.lo[zd] + last.n[zd] == L->level_n[zd];
+        if (seam) znext[uorder[np - 1]] = uorder[0];
+    } else {
+        /* index order, except that a last patch that feeds the first one (periodic stack of slabs) goes first */
+        bool wrap = false;
+        for (int q : L->sources[0]) wrap = wrap || (q == np - 1 && np > 2);
+        if (wrap) uorder.push_back(np - 1);
+        for (int p = 0; p < np - (wrap ? 1 : 0); p++) uorder.push_back(p);
     }
-    for (int i = 0; i < np; i++) {
-        const int p = uorder[i];
+    for (int i = 0; i < np; i++) pos[uorder[i]] = i;
+    auto copy_planes = [&](int p, long long first_plane_off, long long count) -> int {
         const LevelPatch& P = L->patches[p];
-        long long off, cnt;
-        transfer_range(L, P, &off, &cnt);
-        if (slabs) {
-            const long long edge = cnt / P.n[L->dim - 1] * L->g;
-            off += edge;
-            cnt -= 2 * edge;
-        }
         for (int c = 0; c < L->ncomp; c++)
-            HB2L_CUDA(cudaMemcpyAsync(P.S[L->where[0]] + (size_t)c * P.ncell_g + off, U_host[(size_t)p * L->ncomp + c] + off,
-                                      sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice, L->copy_in));
-        HB2L_CUDA(cudaEventRecord(L->ev_up[p], L->copy_in));
+            HB2L_CUDA(cudaMemcpyAsync(P.S[L->where[0]] + (size_t)c * P.ncell_g + first_plane_off, U_host[(size_t)p * L->ncomp + c] + first_plane_off,
+                                      sizeof(double) * (size_t)count, cudaMemcpyHostToDevice, L->copy_in));
+        return 0;
+    };
+    if (slabs && !edges_all) {
+        if (seam) {
+            const int p = uorder[np - 1];
+            long long off, cnt;
+            transfer_range(L, L->patches[p], &off, &cnt);
+            const long long edge = cnt / L->patches[p].n[zd] * L->g;
+            if (copy_planes(p, off + cnt - edge, edge)) return -1;
+        }
+        HB2L_CUDA(cudaEventRecord(L->ev_done[0], L->copy_in));        /* borrowed as "the seam planes are on the device" */
+        HB2L_CUDA(cudaStreamWaitEvent(L->stream, L->ev_done[0], 0));
+        for (int i = 0; i < np; i++) {
+            const int p = uorder[i];
+            long long off, cnt;
+            transfer_range(L, L->patches[p], &off, &cnt);
+            const long long edge = cnt / L->patches[p].n[zd] * L->g;
+            if (copy_planes(p, off, edge)) return -1;
+            HB2L_CUDA(cudaEventRecord(L->ev_lo[p], L->copy_in));
+            const long long rest = cnt - edge - ((seam && i == np - 1) ? edge : 0);
+            if (copy_planes(p, off + edge, rest)) return -1;
+            HB2L_CUDA(cudaEventRecord(L->ev_up[p], L->copy_in));
+            if (trace) HB2L_CUDA(cudaEventRecord(L->tr[1 + p], L->copy_in));
+        }
+    } else {
+        if (slabs) {
+            for (int p = 0; p < np; p++) {
+                long long off, cnt;
+                transfer_range(L, L->patches[p], &off, &cnt);
+                const long long edge = cnt / L->patches[p].n[zd] * L->g;
+                if (copy_planes(p, off, edge) || copy_planes(p, off + cnt - edge, edge)) return -1;
+            }
+            HB2L_CUDA(cudaEventRecord(L->ev_done[0], L->copy_in));        /* borrowed as "all edge planes are on the device" */
+            HB2L_CUDA(cudaStreamWaitEvent(L->stream, L->ev_done[0], 0));
+        }
+        for (int i = 0; i < np; i++) {
+            const int p = uorder[i];
+            long long off, cnt;
+            transfer_range(L, L->patches[p], &off, &cnt);
+            if (slabs) {
+                const long long edge = cnt / L->patches[p].n[zd] * L->g;
+                off += edge;
+                cnt -= 2 * edge;
+            }
+            if (copy_planes(p, off, cnt)) return -1;
+            HB2L_CUDA(cudaEventRecord(L->ev_up[p], L->copy_in));
+            if (trace) HB2L_CUDA(cudaEventRecord(L->tr[1 + p], L->copy_in));
+        }
     }
     /* readiness of every (patch, stage) task in units of upload positions, then the enqueue order */
     std::vector<std::vector<int>> ready(nstages, std::vector<int>(np, 0));
@@ -587,6 +665,7 @@ int hb2_level_advance_host(hb2_level_t L, int32_t nstages, const double* alpha, 
         cudaStream_t st = second ? L->stream2 : L->stream;
         if (sn == 0) {
             HB2L_CUDA(cudaStreamWaitEvent(st, L->ev_up[p], 0));
+            if (slabs && !edges_all && znext[p] >= 0) HB2L_CUDA(cudaStreamWaitEvent(st, L->ev_lo[znext[p]], 0));
             if (!slabs)
                 for (int q : L->sources[p]) HB2L_CUDA(cudaStreamWaitEvent(st, L->ev_up[q], 0));
         } else if (two) {
@@ -598,15 +677,17 @@ int hb2_level_advance_host(hb2_level_t L, int32_t nstages, const double* alpha, 
             /* the last stage overwrites U^(1) of p, which the second stage of p's neighbours read (ghost fill): those on the
              * same stream are ordered, those on the other stream are the sources handled above (stage sn - 1 = second stage) */
         }
+        if (trace) HB2L_CUDA(cudaEventRecord(L->tr[(size_t)1 + 5 * np + (size_t)sn * np + p], st));
         const int nd = L->desc_begin[p + 1] - L->desc_begin[p];
         if (nd > 0) {
-            dim3 grid(8, (unsigned)nd);
+            dim3 grid(fill_blocks(L->desc_max_cells[p]), (unsigned)nd);
             k_level_fill<<<grid, 256, 0, st>>>(L->d_desc + L->desc_begin[p], L->d_ptrs[L->where[sn]], L->ncomp);
             L->launches++;
         }
         int rc = advance_stage_patch_on(L, p, sn + 1, a, b, dt, second ? L->plans2[L->patches[p].shape] : L->plans[L->patches[p].shape]);
         if (rc) return rc;
         if (two) HB2L_CUDA(cudaEventRecord(L->ev_task[(size_t)sn * np + p], st));
+        if (trace) HB2L_CUDA(cudaEventRecord(L->tr[(size_t)1 + np + (size_t)sn * np + p], st));
         if (sn == nstages - 1) {
             const LevelPatch& P = L->patches[p];
             long long off, cnt;
@@ -616,12 +697,25 @@ int hb2_level_advance_host(hb2_level_t L, int32_t nstages, const double* alpha, 
             for (int c = 0; c < L->ncomp; c++)
                 HB2L_CUDA(cudaMemcpyAsync(U_host[(size_t)p * L->ncomp + c] + off, P.S[out_of_stage[sn]] + (size_t)c * P.ncell_g + off,
                                           sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, L->copy_out));
+            if (trace) HB2L_CUDA(cudaEventRecord(L->tr[(size_t)1 + 4 * np + p], L->copy_out));
         }
     }
     HB2L_CUDA(cudaGetLastError());
     HB2L_CUDA(cudaStreamSynchronize(L->copy_out));
     HB2L_CUDA(cudaStreamSynchronize(L->stream));
     if (L->stream2) HB2L_CUDA(cudaStreamSynchronize(L->stream2));
+    if (trace) {
+        fprintf(stderr, "[hb2_level_advance_host trace] ms since the first upload was issued: patch planes upload_done stage_done... download_done\n");
+        for (int p = 0; p < np; p++) {
+            float up = 0.f, dl = 0.f, tk[3] = {0.f, 0.f, 0.f}, ts[3] = {0.f, 0.f, 0.f};
+            for (int sn = 0; sn < nstages; sn++) cudaEventElapsedTime(&ts[sn], L->tr[0], L->tr[(size_t)1 + 5 * np + (size_t)sn * np + p]);
+            cudaEventElapsedTime(&up, L->tr[0], L->tr[1 + p]);
+            for (int sn = 0; sn < nstages; sn++) cudaEventElapsedTime(&tk[sn], L->tr[0], L->tr[(size_t)1 + np + (size_t)sn * np + p]);
+            cudaEventElapsedTime(&dl, L->tr[0], L->tr[(size_t)1 + 4 * np + p]);
+            fprintf(stderr, "  %2d %4d  up %7.2f  s0 %7.2f-%7.2f  s1 %7.2f-%7.2f  s2 %7.2f-%7.2f  dl %7.2f\n", p, L->patches[p].n[L->dim - 1], up,
+                    ts[0], tk[0], ts[1], tk[1], ts[2], tk[2], dl);
+        }
+    }
     for (int sn = 0; sn < nstages; sn++) {
         int rc = hb2_level_end_stage(L, sn + 1, alpha + sn * nstages, sn == nstages - 1 ? 1 : 0);
         if (rc) return rc;
