@@ -60,6 +60,33 @@
 #define HB2_XC 16
 #endif
 
+/* Threads per block of the fast sweeps (single-species / multi-species models), per sweep direction.  The resident warps
+ * per SM stay the same (shared memory and the 128-register limit allow 16, five-eqn 8), but smaller blocks are more
+ * independent barrier domains whose FP64-heavy face phases and load / update phases interleave.  Measured on B200, ms per
+ * sweep x / y / z (profiles/r02_ak_ss_compact_ab.txt, r02_aj_fe_compact_ab.txt):
+ *   single-species 512^3:  256 threads 6.50 / 6.69 / 7.19   128: 6.20 / 6.41 / 6.95   64: 5.92 / 6.62 / 9.90 (x at 32: 5.94)
+ *   five-eqn 384^3:        256 threads 5.96 / 6.56 / 6.58   128: 5.45 / 5.78 / 6.03   64: 5.42 / 5.47 / 6.81 (x at 32: 6.55)
+ * (y / z blocks of 64 threads own rows of 8 cells = 64 B: the z sweep's plane-strided accesses no longer fill DRAM bursts).
+ * Reference-order (MATH == 0) kernels keep 256 threads, or 128 where the rings of 256 do not fit. */
+#ifndef HB2_NT_SS_X
+#define HB2_NT_SS_X 64
+#endif
+#ifndef HB2_NT_SS_Y
+#define HB2_NT_SS_Y 128
+#endif
+#ifndef HB2_NT_SS_Z
+#define HB2_NT_SS_Z 128
+#endif
+#ifndef HB2_NT_MS_X
+#define HB2_NT_MS_X 64
+#endif
+#ifndef HB2_NT_MS_Y
+#define HB2_NT_MS_Y 64
+#endif
+#ifndef HB2_NT_MS_Z
+#define HB2_NT_MS_Z 128
+#endif
+
 namespace hb2 {
 
 /* shared memory of a block of nt threads (doubles): rings of NV primitive, NN node-flux and NMID midpoint-flux components,
@@ -79,7 +106,11 @@ struct SweepShape {
     /* 256 threads; models with so many equations that the rings of a 256-thread block exceed the 227 KB of shared memory
      * (five-eqn with three species, reference-order build: 273 KB) run COMPACT blocks of 128 threads with half the pencils --
      * y / z sweeps: 16 consecutive x per row (two rows per warp), x sweep: 8 rows */
-    static constexpr int NT = (sweep_smem_doubles<Tr, DIR, MATH>(256) * 8 <= 227 * 1024) ? 256 : 128;
+    static constexpr int NT_FIT = (sweep_smem_doubles<Tr, DIR, MATH>(256) * 8 <= 227 * 1024) ? 256 : 128;
+    static constexpr int NT_CAP = (MATH != 1) ? 256
+        : (Tr::MODEL == SS) ? ((DIR == 0) ? HB2_NT_SS_X : (DIR == 1) ? HB2_NT_SS_Y : HB2_NT_SS_Z)
+                            : ((DIR == 0) ? HB2_NT_MS_X : (DIR == 1) ? HB2_NT_MS_Y : HB2_NT_MS_Z);
+    static constexpr int NT = (NT_FIT < NT_CAP) ? NT_FIT : NT_CAP;
     static constexpr int NW = NT / 32;
     static constexpr int P = (DIR == 0) ? NT / HB2_XC : NT / 8;   /* pencils per block */
     static constexpr int C = (DIR == 0) ? HB2_XC : 8;             /* cells per chunk along the sweep axis */

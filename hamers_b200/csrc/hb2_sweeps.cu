@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(384, 2) k_sensor(const __grid_constant__ Senso
 #endif
 
 template <class Tr, int DIR, int NTERM>
-__global__ void __launch_bounds__((SweepShape<Tr, DIR, MATH>::NT), (MATH == 1 && Tr::MODEL == SS && HB2_SCHEME != HB2_WCNS6_LD) ? HB2_MINB : 1) k_sweep(const __grid_constant__ DirArgs A)
+__global__ void __launch_bounds__((SweepShape<Tr, DIR, MATH>::NT), (MATH == 1 && Tr::MODEL == SS && HB2_SCHEME != HB2_WCNS6_LD) ? HB2_MINB * 256 / (SweepShape<Tr, DIR, MATH>::NT) : 1) k_sweep(const __grid_constant__ DirArgs A)
 {
     using Sh = SweepShape<Tr, DIR, MATH>;
     extern __shared__ double smem[];
