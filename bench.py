@@ -345,10 +345,28 @@ def workload_config(args, sample_override=None):
     return cfg
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity), so that the pinned host boxes of the
+    e2e leg are first-touched on the GPU's own NUMA node (torchrun does not bind ranks).  Returns the previous affinity (to be
+    restored for the CPU baseline, which uses every core) or None when NVML cannot say."""
+    if os.environ.get("HB2_BENCH_AFFINITY", "1") == "0":
+        return None
+    try:
+        import pynvml
+
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        return before
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
 
     rank, local_rank, world = env_rank()
+    affinity_before = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:

@@ -51,10 +51,30 @@ def needs_build() -> bool:
     return newest > _mtime(SO)
 
 
+def unit_deps(src: str) -> set:
+    """The files a translation unit depends on: its source and, recursively, every quoted include found under csrc/ or
+    include/ (so that a change of one header rebuilds only the units that see it)."""
+    import re
+
+    seen, todo = set(), [os.path.join(CSRC, src)]
+    while todo:
+        f = todo.pop()
+        if f in seen or not os.path.exists(f):
+            continue
+        seen.add(f)
+        for inc in re.findall(r'#\s*include\s+"([^"]+)"', open(f).read()):
+            for d in (os.path.dirname(f), CSRC, os.path.join(ROOT, "include")):
+                if os.path.exists(os.path.join(d, inc)):
+                    todo.append(os.path.join(d, inc))
+                    break
+    return seen
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return SO
     os.makedirs(BUILD, exist_ok=True)
+    stale = [u for u in UNITS if force or max(_mtime(d) for d in unit_deps(u[1])) > _mtime(os.path.join(BUILD, u[0]))]
+    if not stale and os.path.exists(SO) and all(_mtime(os.path.join(BUILD, u[0])) <= _mtime(SO) for u in UNITS):
+        return SO
 
     def compile_one(unit):
         obj, src, flags = unit
@@ -65,7 +85,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return r.stderr
 
     with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
-        logs = list(ex.map(compile_one, UNITS))
+        logs = list(ex.map(compile_one, stale))
     if verbose:
         for lg in logs:
             print(lg)

@@ -33,6 +33,19 @@ __device__ __forceinline__ void cp_async8(unsigned dst_shared, const double* src
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_shared), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+/* all but the most recent group of the thread's copies have landed */
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+/* planes of loads a block keeps in flight (HB2_DIFF_DEPTH = 1: the next plane only, staged behind the barrier of the current
+ * one; 2: two planes, one commit group each, three tile sets).  Measured on B200, Navier-Stokes 512^3: 91.06 ms per step with
+ * one plane, 91.10 with two (diffusive calls alone 28.2 / 29.0 ms; profiles/r02_ap_ns_depth.txt) -- the kernels are not
+ * waiting for a plane that was requested too late, so the default stays 1 (less shared memory). */
+#ifndef HB2_DIFF_DEPTH
+#define HB2_DIFF_DEPTH 1
+#endif
+constexpr int DEPTH = HB2_DIFF_DEPTH;
+static_assert(DEPTH == 1 || DEPTH == 2, "one or two planes in flight");
 
 /* the halo cell of a thread: position (hx, hy) in the 38 x 14 tile; returns false for threads without one */
 __device__ __forceinline__ bool halo_of_thread(int t, int& hx, int& hy)
@@ -58,7 +71,7 @@ __device__ __forceinline__ bool halo_of_thread(int t, int& hx, int& hy)
  * Algorithmic traffic 40 B read (+ halo re-reads served by L2) + 96 B written per node.
  * Tile origin: ghost-box cell (32 bx, 8 by + 3), so that rows start on 256-byte boundaries of the arrays' rows; the nodes are the
  * cells of the interior extended by three (node coordinate = ghost-box index - 6). */
-constexpr int NODE_SMEM_DOUBLES = 2 * 4 * SY * SX + 5 * NT + 5 * NT;
+constexpr int NODE_SMEM_DOUBLES = 2 * 4 * SY * SX + DEPTH * (5 * NT + 5 * NT);
 
 template <int MATH>
 __global__ void __launch_bounds__(NT, 2) k_diff_node_march(const __grid_constant__ DiffGeom G, const __grid_constant__ DiffConsts K,
@@ -73,8 +86,8 @@ __global__ void __launch_bounds__(NT, 2) k_diff_node_march(const __grid_constant
     };
     extern __shared__ double smem[];
     double* sP = smem;                                  /* [2][4][SY][SX] primitives of the node plane */
-    double* sQo = smem + 2 * 4 * SY * SX;               /* [5][NT] staged own cell, plane kz + 3 */
-    double* sQh = sQo + 5 * NT;                         /* [5][NT] staged halo cell, plane kz */
+    double* sQo = smem + 2 * 4 * SY * SX;               /* [DEPTH][5][NT] staged own cell, plane kz + 3 */
+    double* sQh = sQo + DEPTH * 5 * NT;                 /* [DEPTH][5][NT] staged halo cell, plane kz */
     const int t = (int)threadIdx.x, tx = t & 31, ty = t >> 5;
     const int i = (int)blockIdx.x * TX - 6 + tx, j = (int)blockIdx.y * TY - 3 + ty;      /* node coordinates */
     const bool cell = i < G.n[0] + 6 && j < G.n[1] + 6;                                  /* the cell exists (i >= -6, j >= -3) */
@@ -107,31 +120,42 @@ __global__ void __launch_bounds__(NT, 2) k_diff_node_march(const __grid_constant
             for (int v = 0; v < 4; v++) ring[v][m] = P[v];
         }
     }
-    auto stage = [&](int kz) {
-        if (cell) {
-            const long long x = col + G.cs[2] * (kz + 3 + G.g[2]);
+    /* the copies of plane kz go to staging slot sb; one commit group per plane (empty behind the last plane) */
+    auto stage = [&](int kz, int sb) {
+        if (kz < kz_hi) {
+            const unsigned off = (unsigned)(sb * 5 * NT * sizeof(double));
+            if (cell) {
+                const long long x = col + G.cs[2] * (kz + 3 + G.g[2]);
 #pragma unroll
-            for (int c = 0; c < 5; c++) cp_async8(so + (unsigned)(c * NT * sizeof(double)), Q.Q[c] + x);
-        }
-        if (hok) {
-            const long long x = hcol + G.cs[2] * (kz + G.g[2]);
+                for (int c = 0; c < 5; c++) cp_async8(so + off + (unsigned)(c * NT * sizeof(double)), Q.Q[c] + x);
+            }
+            if (hok) {
+                const long long x = hcol + G.cs[2] * (kz + G.g[2]);
 #pragma unroll
-            for (int c = 0; c < 5; c++) cp_async8(sh + (unsigned)(c * NT * sizeof(double)), Q.Q[c] + x);
+                for (int c = 0; c < 5; c++) cp_async8(sh + off + (unsigned)(c * NT * sizeof(double)), Q.Q[c] + x);
+            }
         }
+        cp_async_commit();
     };
-    stage(kz_lo);
+    stage(kz_lo, 0);
+    if (DEPTH == 2) stage(kz_lo + 1, 1);
     int b = 0;
     for (int kz = kz_lo; kz < kz_hi; kz++, b ^= 1) {
         double* P_b = sP + b * (4 * SY * SX);
+        const int sb = (DEPTH == 2) ? b : 0;            /* staging slot of plane kz */
 #pragma unroll
         for (int v = 0; v < 4; v++)
 #pragma unroll
             for (int m = 0; m < 6; m++) ring[v][m] = ring[v][m + 1];
-        cp_async_wait_all();                            /* the thread's own copies: no barrier needed to read them back */
+        /* the thread's own copies: no barrier needed to read them back */
+        if (DEPTH == 2)
+            cp_async_wait_but_one();
+        else
+            cp_async_wait_all();
         if (cell) {
             double q[5], P[4];
 #pragma unroll
-            for (int c = 0; c < 5; c++) q[c] = sQo[c * NT + t];
+            for (int c = 0; c < 5; c++) q[c] = sQo[(sb * 5 + c) * NT + t];
             prims(q, P);
 #pragma unroll
             for (int v = 0; v < 4; v++) {
@@ -142,12 +166,12 @@ __global__ void __launch_bounds__(NT, 2) k_diff_node_march(const __grid_constant
         if (hok) {
             double q[5], P[4];
 #pragma unroll
-            for (int c = 0; c < 5; c++) q[c] = sQh[c * NT + t];
+            for (int c = 0; c < 5; c++) q[c] = sQh[(sb * 5 + c) * NT + t];
             prims(q, P);
 #pragma unroll
             for (int v = 0; v < 4; v++) P_b[(v * SY + hy) * SX + hx] = P[v];
         }
-        if (kz + 1 < kz_hi) stage(kz + 1);              /* in flight while this plane is processed */
+        stage(kz + DEPTH, sb);                          /* the slot just read back; in flight while DEPTH planes are processed */
         __syncthreads();
         if (own) {
             double der[4][3];
@@ -185,7 +209,8 @@ __global__ void __launch_bounds__(NT, 2) k_diff_node_march(const __grid_constant
  * The high z face of a cell is the low z face of the next one: reconstructed once and carried.  Algorithmic traffic 96 B of
  * node fluxes + 64 B read-modify-write of the state per cell. */
 constexpr int DIV_X = 4 * TY * SX, DIV_Y = 4 * SY * TX;       /* doubles per tile set */
-constexpr int DIV_SMEM_DOUBLES = 2 * (DIV_X + DIV_Y);
+constexpr int DIV_NBUF = DEPTH + 1;                           /* tile sets: the one being read + DEPTH in flight */
+constexpr int DIV_SMEM_DOUBLES = DIV_NBUF * (DIV_X + DIV_Y);
 
 template <int MATH>
 __global__ void __launch_bounds__(NT, 2) k_diff_div_march(const __grid_constant__ NsDivArgs A, const __grid_constant__ DiffFast FK, int seg_len)
@@ -214,24 +239,29 @@ __global__ void __launch_bounds__(NT, 2) k_diff_div_march(const __grid_constant_
     const unsigned s0 = (unsigned)__cvta_generic_to_shared(smem);
     const int ox = ty * SX + tx + HALO, oy = DIV_X + (ty + HALO) * TX + tx;             /* own slots, equation 0 */
 
+    /* one commit group per plane (empty behind the last plane) */
     auto stage = [&](int k, int b) {
-        const long long zoff = G.cs[2] * (k + G.g[2]);
-        const unsigned base = s0 + (unsigned)(b * (DIV_X + DIV_Y) * sizeof(double));
-        if (cx_ok) {
+        if (k < k1) {
+            const long long zoff = G.cs[2] * (k + G.g[2]);
+            const unsigned base = s0 + (unsigned)(b * (DIV_X + DIV_Y) * sizeof(double));
+            if (cx_ok) {
 #pragma unroll
-            for (int e = 0; e < 4; e++) cp_async8(base + (unsigned)((ox + e * TY * SX) * sizeof(double)), A.Fn[0][e + 1] + col + zoff);
-        }
-        if (cy_ok) {
+                for (int e = 0; e < 4; e++) cp_async8(base + (unsigned)((ox + e * TY * SX) * sizeof(double)), A.Fn[0][e + 1] + col + zoff);
+            }
+            if (cy_ok) {
 #pragma unroll
-            for (int e = 0; e < 4; e++) cp_async8(base + (unsigned)((oy + e * SY * TX) * sizeof(double)), A.Fn[1][e + 1] + col + zoff);
-        }
-        if (hok) {
+                for (int e = 0; e < 4; e++) cp_async8(base + (unsigned)((oy + e * SY * TX) * sizeof(double)), A.Fn[1][e + 1] + col + zoff);
+            }
+            if (hok) {
 #pragma unroll
-            for (int e = 0; e < 4; e++) cp_async8(base + (unsigned)((h_off + e * h_es) * sizeof(double)), h_src[e + 1] + hcol + zoff);
+                for (int e = 0; e < 4; e++) cp_async8(base + (unsigned)((h_off + e * h_es) * sizeof(double)), h_src[e + 1] + hcol + zoff);
+            }
         }
+        cp_async_commit();
     };
     if (k0 >= k1) return;
     stage(k0, 0);
+    if (DEPTH == 2) stage(k0 + 1, 1);
     double ring[4][7];                       /* F^z of equation e + 1 at planes k - 3 + m */
     double fz_next[4], fzf[4];
 #pragma unroll
@@ -260,7 +290,7 @@ __global__ void __launch_bounds__(NT, 2) k_diff_div_march(const __grid_constant_
         for (int e = 0; e < 4; e++) un[e] = A.U[e + 1][colU + GU.cs[2] * (k0 + GU.g[2])];
     }
     int b = 0;
-    for (int k = k0; k < k1; k++, b ^= 1) {
+    for (int k = k0; k < k1; k++, b = (b + 1 == DIV_NBUF) ? 0 : b + 1) {
 #pragma unroll
         for (int e = 0; e < 4; e++) {
 #pragma unroll
@@ -270,9 +300,12 @@ __global__ void __launch_bounds__(NT, 2) k_diff_div_march(const __grid_constant_
         double uo[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) uo[e] = un[e];
-        cp_async_wait_all();
-        __syncthreads();                     /* plane k has landed in buffer b; every thread is done with buffer b ^ 1 */
-        if (k + 1 < k1) stage(k + 1, b ^ 1);
+        if (DEPTH == 2)
+            cp_async_wait_but_one();
+        else
+            cp_async_wait_all();
+        __syncthreads();                     /* plane k has landed in buffer b; every thread is done with the buffer of plane k - 1 */
+        stage(k + DEPTH, (b + DEPTH) % DIV_NBUF);   /* = the buffer of plane k - 1 */
         const long long xu = colU + GU.cs[2] * (k + GU.g[2]);
         if (own) {
             if (k + 1 < k1) {

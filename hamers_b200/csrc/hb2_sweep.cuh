@@ -44,6 +44,11 @@
 #ifndef HB2_PREFETCH_R
 #define HB2_PREFETCH_R 0
 #endif
+/* ... and per direction once the blocks became smaller (64 / 128 / 128 threads, below): at 512^3 R=1 measures
+ * x 5.92 / y 6.15 / z 6.64 ms against 5.88 / 6.30 / 6.84 with R=0 (profiles/r02_am_flags_ab.txt): x keeps 0, y and z take 1 */
+#ifndef HB2_PREFETCH_R_YZ
+#define HB2_PREFETCH_R_YZ 1
+#endif
 /* steady-state variant of the iteration body (no "wanted" tests) for the interior iterations of full blocks; 0 = off */
 #ifndef HB2_STEADY
 #define HB2_STEADY 1
@@ -722,7 +727,8 @@ HB2_HD void pipeline_iteration(const DirArgs& A, double* smem, const PencilCtx& 
         const bool pre = update_wanted<Tr, DIR, MATH>(c, t + HB2_PREFETCH_L2 - 1, cn);
         if (STEADY || pre) update_prefetch<Tr, DIR, NTERM>(A, c, cn);
     }
-    if (HB2_PREFETCH_R && do_update) update_fetch<Tr, DIR, FUSED>(A, c, cc, uin);
+    constexpr bool PREFETCH_R = (DIR == 0) ? (HB2_PREFETCH_R != 0) : (HB2_PREFETCH_R_YZ != 0);
+    if (PREFETCH_R && do_update) update_fetch<Tr, DIR, FUSED>(A, c, cc, uin);
     unsigned int flag;
     if (HB2_PREFETCH_FLAG) {
         flag = pr.flag;
@@ -731,7 +737,7 @@ HB2_HD void pipeline_iteration(const DirArgs& A, double* smem, const PencilCtx& 
         flag = (STEADY || t < nsteps) ? face_flag_fetch<Tr, DIR, MATH, STEADY>(A, c, t) : 0u;
     }
     if (STEADY || t < nsteps) phase_face<Tr, DIR, MATH, STEADY>(A, smem, c, t, flag);
-    if (!HB2_PREFETCH_R && do_update) update_fetch<Tr, DIR, FUSED>(A, c, cc, uin);
+    if (!PREFETCH_R && do_update) update_fetch<Tr, DIR, FUSED>(A, c, cc, uin);
     if (do_update) phase_update<Tr, DIR, MATH, NTERM>(A, smem, c, cc, uin);
     if (!STEADY && A.bulk) pipeline_consume<Tr, DIR, MATH>(A, smem, c, t + 1, pr.mbar, pr.parity);
 }

@@ -63,9 +63,18 @@ __global__ void __launch_bounds__(384, 2) k_sensor(const __grid_constant__ Senso
 #ifndef HB2_MINB
 #define HB2_MINB 2
 #endif
+/* resident warps per SM the WCNS6-LD fast sweeps are compiled for (8: up to 255 registers; 12: 168; 16: 128).  Measured at
+ * 512^3, ms per sweep x / y / z (profiles/r02_ao_ld_warps_ab.txt): 8 warps 16.5 / 15.7 / 16.5, 12 warps 22.5 (spills) / 14.9 /
+ * 15.5, 16 warps 20.8 / 15.0 / 16.2 */
+#ifndef HB2_WARPS_LD
+#define HB2_WARPS_LD 12
+#endif
+#ifndef HB2_WARPS_LD_X
+#define HB2_WARPS_LD_X 8
+#endif
 
 template <class Tr, int DIR, int NTERM>
-__global__ void __launch_bounds__((SweepShape<Tr, DIR, MATH>::NT), (MATH == 1 && Tr::MODEL == SS && HB2_SCHEME != HB2_WCNS6_LD) ? HB2_MINB * 256 / (SweepShape<Tr, DIR, MATH>::NT) : 1) k_sweep(const __grid_constant__ DirArgs A)
+__global__ void __launch_bounds__((SweepShape<Tr, DIR, MATH>::NT), (MATH == 1 && Tr::MODEL == SS) ? ((HB2_SCHEME != HB2_WCNS6_LD) ? HB2_MINB * 8 : (DIR == 0) ? HB2_WARPS_LD_X : HB2_WARPS_LD) * 32 / (SweepShape<Tr, DIR, MATH>::NT) : 1) k_sweep(const __grid_constant__ DirArgs A)
 {
     using Sh = SweepShape<Tr, DIR, MATH>;
     extern __shared__ double smem[];
