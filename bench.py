@@ -500,7 +500,7 @@ def run_ours(args):
         # value is read from the committed ncu --set full capture of the same workload and labelled as such
         design_bytes = {"xsweep": 80.0, "ysweep": 120.0, "zsweep": 160.0}     # bytes per cell the three-sweep DESIGN moves
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_n_traffic.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", "r02_as_traffic.json")) as fh:
                 tr = json.load(fh)
             if tr["size"] == args.size and tr["model"] == args.model and tr["math"] == args.math and world == 1:
                 roofline["traffic"] = tr["dram_bytes_per_launch"][dom]

@@ -72,7 +72,11 @@
  *   single-species 512^3:  256 threads 6.50 / 6.69 / 7.19   128: 6.20 / 6.41 / 6.95   64: 5.92 / 6.62 / 9.90 (x at 32: 5.94)
  *   five-eqn 384^3:        256 threads 5.96 / 6.56 / 6.58   128: 5.45 / 5.78 / 6.03   64: 5.42 / 5.47 / 6.81 (x at 32: 6.55)
  * (y / z blocks of 64 threads own rows of 8 cells = 64 B: the z sweep's plane-strided accesses no longer fill DRAM bursts).
- * Reference-order (MATH == 0) kernels keep 256 threads, or 128 where the rings of 256 do not fit. */
+ * Reference-order (MATH == 0) kernels: 128 threads (HB2_NT_EXACT), three resident blocks where the rings allow
+ * (hb2_sweeps.cu: HB2_WARPS_EXACT). */
+#ifndef HB2_NT_EXACT
+#define HB2_NT_EXACT 128
+#endif
 #ifndef HB2_NT_SS_X
 #define HB2_NT_SS_X 64
 #endif
@@ -112,7 +116,7 @@ struct SweepShape {
      * (five-eqn with three species, reference-order build: 273 KB) run COMPACT blocks of 128 threads with half the pencils --
      * y / z sweeps: 16 consecutive x per row (two rows per warp), x sweep: 8 rows */
     static constexpr int NT_FIT = (sweep_smem_doubles<Tr, DIR, MATH>(256) * 8 <= 227 * 1024) ? 256 : 128;
-    static constexpr int NT_CAP = (MATH != 1) ? 256
+    static constexpr int NT_CAP = (MATH != 1) ? HB2_NT_EXACT
         : (Tr::MODEL == SS) ? ((DIR == 0) ? HB2_NT_SS_X : (DIR == 1) ? HB2_NT_SS_Y : HB2_NT_SS_Z)
                             : ((DIR == 0) ? HB2_NT_MS_X : (DIR == 1) ? HB2_NT_MS_Y : HB2_NT_MS_Z);
     static constexpr int NT = (NT_FIT < NT_CAP) ? NT_FIT : NT_CAP;

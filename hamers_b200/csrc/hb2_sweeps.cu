@@ -63,6 +63,20 @@ __global__ void __launch_bounds__(384, 2) k_sensor(const __grid_constant__ Senso
 #ifndef HB2_MINB
 #define HB2_MINB 2
 #endif
+/* resident warps per SM the other sweeps (reference-order build, multi-species fast) are compiled for, where their shared
+ * memory allows as many; 0: one block.  Reference-order single-species sweeps at 384^3, ms x / y / z
+ * (profiles/r02_ar_exact_blocks_ab.txt): 256 threads, one block 14.0 / 14.5 / 15.0; 128 threads, as many blocks as fit at
+ * <= 255 registers 16.2 / 14.7 / 15.6; 128 threads compiled for 12 warps (168 registers, three blocks) 12.5 / 12.0 / 13.1 */
+#ifndef HB2_WARPS_EXACT
+#define HB2_WARPS_EXACT 12
+#endif
+/* resident warps per SM the WCNS5 fast single-species sweeps are compiled for (16: 128 registers; 12: 168) */
+#ifndef HB2_WARPS_X
+#define HB2_WARPS_X (HB2_MINB * 8)
+#endif
+#ifndef HB2_WARPS_YZ
+#define HB2_WARPS_YZ (HB2_MINB * 8)
+#endif
 /* resident warps per SM the WCNS6-LD fast sweeps are compiled for (8: up to 255 registers; 12: 168; 16: 128).  Measured at
  * 512^3, ms per sweep x / y / z (profiles/r02_ao_ld_warps_ab.txt): 8 warps 16.5 / 15.7 / 16.5, 12 warps 22.5 (spills) / 14.9 /
  * 15.5, 16 warps 20.8 / 15.0 / 16.2 */
@@ -73,8 +87,24 @@ __global__ void __launch_bounds__(384, 2) k_sensor(const __grid_constant__ Senso
 #define HB2_WARPS_LD_X 8
 #endif
 
+/* minimum resident blocks per SM a sweep kernel is compiled for (its register budget): the warps asked for by the switches
+ * above, but never more blocks than the shared memory of the SM holds */
+template <class Tr, int DIR>
+constexpr int sweep_min_blocks()
+{
+    using Sh = SweepShape<Tr, DIR, MATH>;
+    const int warps = (MATH == 1 && Tr::MODEL == SS)
+                          ? ((HB2_SCHEME != HB2_WCNS6_LD) ? ((DIR == 0) ? HB2_WARPS_X : HB2_WARPS_YZ) : ((DIR == 0) ? HB2_WARPS_LD_X : HB2_WARPS_LD))
+                          : (MATH == 0 && HB2_SCHEME == HB2_WCNS6_LD) ? 8 /* the WCNS6-LD reference-order kernels spill at 168 registers */
+                          : HB2_WARPS_EXACT;
+    const int by_warps = warps * 32 / Sh::NT;
+    const int by_smem = (227 * 1024) / (Sh::SMEM_DOUBLES * 8 + 1024);
+    const int b = (by_warps < by_smem) ? by_warps : by_smem;
+    return b > 0 ? b : 1;
+}
+
 template <class Tr, int DIR, int NTERM>
-__global__ void __launch_bounds__((SweepShape<Tr, DIR, MATH>::NT), (MATH == 1 && Tr::MODEL == SS) ? ((HB2_SCHEME != HB2_WCNS6_LD) ? HB2_MINB * 8 : (DIR == 0) ? HB2_WARPS_LD_X : HB2_WARPS_LD) * 32 / (SweepShape<Tr, DIR, MATH>::NT) : 1) k_sweep(const __grid_constant__ DirArgs A)
+__global__ void __launch_bounds__((SweepShape<Tr, DIR, MATH>::NT), (sweep_min_blocks<Tr, DIR>())) k_sweep(const __grid_constant__ DirArgs A)
 {
     using Sh = SweepShape<Tr, DIR, MATH>;
     extern __shared__ double smem[];
