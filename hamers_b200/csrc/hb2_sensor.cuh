@@ -36,7 +36,10 @@ struct SensorArgs {
  *   64 x 6 threads, 11 rows (default): a 61 x 8 tile of decisions from 64 x 11 velocities (69 %), second row pass 5/6 busy
  *   48 x 8 threads, 16 rows: a 45 x 13 tile from 48 x 16 velocities (76 %), both row passes full, fewer idle columns on a
  *     256-cell box (4 % instead of 15 %) -- measured SLOWER on B200: 2.05 vs 1.73 ms at 512^3, 0.290 vs 0.264 ms at 256^3
- *     (rows of 48 threads straddle the warps: 1.5 warps per row, and the tile rows are no longer bank-aligned) */
+ *     (rows of 48 threads straddle the warps: 1.5 warps per row, and the tile rows are no longer bank-aligned)
+ *   32 x 12 threads, 24 rows: a 29 x 21 tile from 32 x 24 velocities (79 %), one warp per row -- SLOWER as well: 2.03 vs 1.82 ms
+ *     at 512^3, 0.284 vs 0.264 ms at 256^3; 32 x 12 threads, 12 rows (29 x 9, one row per thread): 1.93 ms
+ *     (profiles/r02_au_sensor_tiles_ab.txt).  256-byte rows that start 29 cells apart are never sector-aligned. */
 #ifndef HB2_SENSOR_NX
 #define HB2_SENSOR_NX 64
 #endif
