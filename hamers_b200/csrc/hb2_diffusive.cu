@@ -263,6 +263,16 @@ int launch_dir(hb2_diff_plan_t p, const DiffPtrs& A, double dt)
     return 0;
 }
 
+/* Re-associated 3-D route: F^f of momentum a < f shares the array of F^a of momentum f (symmetric stress, bit for bit; see
+ * k_diff_node_march<1>).  Fn[f][e]: e = 1 + a. */
+template <class T>
+void diff_alias_symmetric(T (&Fn)[3][5])
+{
+    Fn[1][1] = Fn[0][2];
+    Fn[2][1] = Fn[0][3];
+    Fn[2][2] = Fn[1][3];
+}
+
 /* primitives, then the node fluxes of all directions in one pass (every derivative evaluated once) into the plan's
  * per-direction scratch sets */
 template <int DIM>
@@ -293,6 +303,7 @@ int node_stage(hb2_diff_plan_t p, const double* const* Q, bool fast = false)
             grid.z = (p->G.n[2] + 6 + seg - 1) / seg;
             DiffFast FK;
             make_diff_fast(p->G, p->K, 0.0, 0.0, &FK);
+            if (fast) diff_alias_symmetric(N.Fn);
             if (fast)
                 k_diff_node_march<1><<<grid, NT, NODE_SMEM_DOUBLES * sizeof(double), p->stream>>>(p->G, p->K, FK, A, N, seg);
             else
@@ -391,6 +402,7 @@ int run_divergence(hb2_diff_plan_t p, const double* const* Q, double dt, int num
         grid.z = (p->G.n[2] + seg - 1) / seg;
         DiffFast FK;
         make_diff_fast(p->G, p->K, dt, beta, &FK);
+        if (fast) diff_alias_symmetric(D.Fn);
         if (fast)
             k_diff_div_march<1><<<grid, NT, DIV_SMEM_DOUBLES * sizeof(double), p->stream>>>(D, FK, seg);
         else

@@ -198,7 +198,13 @@ __global__ void __launch_bounds__(NT, 2) k_diff_node_march(const __grid_constant
 #pragma unroll
             for (int f = 0; f < 3; f++)
 #pragma unroll
-                for (int e = 1; e < 5; e++) A.Fn[f][e][x] = Fn[f][e];
+                for (int e = 1; e < 5; e++) {
+                    /* re-associated route: the viscous stress is symmetric BIT FOR BIT (D2 (d_a u_f + d_f u_a), an IEEE sum
+                     * commutes), so F^f of momentum a < f is the array F^a of momentum f -- the host aliases the pointers
+                     * (diff_alias_symmetric), nine arrays are written and read instead of twelve */
+                    if (MATH == 1 && e <= 3 && e - 1 < f) continue;
+                    A.Fn[f][e][x] = Fn[f][e];
+                }
         }
         /* the tile written next is the other one; this one is rewritten two iterations on, behind the next barrier */
     }
