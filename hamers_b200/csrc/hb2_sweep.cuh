@@ -72,10 +72,15 @@
  *   single-species 512^3:  256 threads 6.50 / 6.69 / 7.19   128: 6.20 / 6.41 / 6.95   64: 5.92 / 6.62 / 9.90 (x at 32: 5.94)
  *   five-eqn 384^3:        256 threads 5.96 / 6.56 / 6.58   128: 5.45 / 5.78 / 6.03   64: 5.42 / 5.47 / 6.81 (x at 32: 6.55)
  * (y / z blocks of 64 threads own rows of 8 cells = 64 B: the z sweep's plane-strided accesses no longer fill DRAM bursts).
+ * ..._Z is the LAST direction of the model's dimension (the sweep with the RK update): the 2-D five-eqn y sweep takes 5.22 ms
+ * with 128 threads against 6.25 with 64 at 8192^2.
  * Reference-order (MATH == 0) kernels: 128 threads (HB2_NT_EXACT), three resident blocks where the rings allow
  * (hb2_sweeps.cu: HB2_WARPS_EXACT). */
 #ifndef HB2_NT_EXACT
 #define HB2_NT_EXACT 128
+#endif
+#ifndef HB2_NT_EXACT_X
+#define HB2_NT_EXACT_X HB2_NT_EXACT
 #endif
 #ifndef HB2_NT_SS_X
 #define HB2_NT_SS_X 64
@@ -116,9 +121,9 @@ struct SweepShape {
      * (five-eqn with three species, reference-order build: 273 KB) run COMPACT blocks of 128 threads with half the pencils --
      * y / z sweeps: 16 consecutive x per row (two rows per warp), x sweep: 8 rows */
     static constexpr int NT_FIT = (sweep_smem_doubles<Tr, DIR, MATH>(256) * 8 <= 227 * 1024) ? 256 : 128;
-    static constexpr int NT_CAP = (MATH != 1) ? HB2_NT_EXACT
-        : (Tr::MODEL == SS) ? ((DIR == 0) ? HB2_NT_SS_X : (DIR == 1) ? HB2_NT_SS_Y : HB2_NT_SS_Z)
-                            : ((DIR == 0) ? HB2_NT_MS_X : (DIR == 1) ? HB2_NT_MS_Y : HB2_NT_MS_Z);
+    static constexpr int NT_CAP = (MATH != 1) ? ((DIR == 0) ? HB2_NT_EXACT_X : HB2_NT_EXACT)
+        : (Tr::MODEL == SS) ? ((DIR == 0) ? HB2_NT_SS_X : (DIR != Tr::DIM - 1) ? HB2_NT_SS_Y : HB2_NT_SS_Z)
+                            : ((DIR == 0) ? HB2_NT_MS_X : (DIR != Tr::DIM - 1) ? HB2_NT_MS_Y : HB2_NT_MS_Z);
     static constexpr int NT = (NT_FIT < NT_CAP) ? NT_FIT : NT_CAP;
     static constexpr int NW = NT / 32;
     static constexpr int P = (DIR == 0) ? NT / HB2_XC : NT / 8;   /* pencils per block */
