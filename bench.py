@@ -241,7 +241,10 @@ def secondary_measurements(args, torch, dist, rank, world, local_rank):
                     "value": float(n) ** 3 * 3 / (ms * 1e-3), "unit": "cell-updates/s", "ms_per_step": ms, "steps": args.ns_steps,
                     "gpu_launches_per_step": (lvl.launch_count - l0) / (args.ns_steps + 3),
                     "mean_kinetic_energy": float(ke[0]) / float(n) ** 3, "checksum": int(cks[0]) & 0xFFFFFFFFFFFFFFFF,
-                    "finite": bool(torch.isfinite(state).all())}
+                    "finite": bool(torch.isfinite(state).all()),
+                    "ghost_fill": ("periodic fill kernel" if world == 1 else
+                                   "hb2_push_boxes_dev: six-wide halos stored into the neighbours' arrays over CUDA IPC / NVLink"
+                                   if lvl.push else "pack -> NCCL send/recv -> unpack")}
         lvl.close()
         del lvl, state
         torch.cuda.empty_cache()

@@ -31,6 +31,7 @@ SYMBOLS = [
     "hb2_plan_set_stream", "hb2_plan_use_own_stream", "hb2_plan_synchronize", "hb2_plan_launch_count", "hb2_plan_workspace_bytes",
     "hb2_compute_flux_and_source_dev", "hb2_advance_stage_dev", "hb2_fused_stage_dev",
     "hb2_fill_ghosts_periodic_dev", "hb2_pack_box_dev", "hb2_unpack_box_dev", "hb2_pack_boxes_dev", "hb2_unpack_boxes_dev",
+    "hb2_push_boxes_dev",
     "hb2_max_wave_speed_dev", "hb2_fused_stage_push_dev", "hb2_device_malloc", "hb2_device_free", "hb2_ipc_export",
     "hb2_ipc_open", "hb2_ipc_close",
     "hb2_compute_flux_and_source_host", "hb2_fused_stage_host", "hb2_probe_fp64_peak", "hb2_probe_hbm_bandwidth",
@@ -366,6 +367,27 @@ class Plan:
         n, lo, hi, off = table
         _check(self.lib.hb2_unpack_boxes_dev(self._h, _ptr_table(_dev_ptrs(U, self.ncomp)), n, lo, hi, off,
                                              C.c_void_p(buffer.data_ptr())), "hb2_unpack_boxes_dev")
+
+    def peer_box_table(self, boxes, bases, shifts):
+        """ctypes tables for push_boxes: boxes = [(lo, hi)], bases[b] = device address of component 0 of the destination
+        state array (this GPU's or an IPC-opened peer's, same ghost-box geometry), shifts[b] = cell offset subtracted."""
+        n = len(boxes)
+        lo = (C.c_int32 * (3 * n))()
+        hi = (C.c_int32 * (3 * n))()
+        sh = (C.c_int32 * (3 * n))()
+        for b, (l, h) in enumerate(boxes):
+            for a in range(3):
+                lo[3 * b + a] = int(l[a]) if a < self.dim else 0
+                hi[3 * b + a] = int(h[a]) if a < self.dim else 1
+                sh[3 * b + a] = int(shifts[b][a]) if a < self.dim else 0
+        dst = (C.c_void_p * n)(*[int(x) for x in bases])
+        return n, lo, hi, dst, sh
+
+    def push_boxes(self, U, table):
+        """Store the boxes of U straight into the neighbouring patches' state arrays (hb2_push_boxes_dev)."""
+        n, lo, hi, dst, sh = table
+        _check(self.lib.hb2_push_boxes_dev(self._h, _ptr_table(_dev_ptrs(U, self.ncomp)), n, lo, hi, dst, sh,
+                                           C.c_int64(int(np.prod(self.ghost_shape)))), "hb2_push_boxes_dev")
 
     def max_wave_speed(self, Q, out):
         _check(self.lib.hb2_max_wave_speed_dev(self._h, _ptr_table(_dev_ptrs(Q, self.ncomp)),

@@ -313,6 +313,36 @@ __global__ void __launch_bounds__(256) k_multibox(const __grid_constant__ Geom G
     }
 }
 
+/* several boxes per launch stored straight into OTHER state arrays (neighbouring patches of the same size, on this or on
+ * a peer GPU opened over CUDA IPC): cell (i, j, k) of box b lands on cell (i, j, k) - shift[b] of the array at dst[b] */
+struct PeerBoxArgs {
+    int nbox;
+    int lo[HB2_MAX_BOXES][3], ext[HB2_MAX_BOXES][3], shift[HB2_MAX_BOXES][3];
+    long long first[HB2_MAX_BOXES + 1];
+    double* dst[HB2_MAX_BOXES];
+    long long comp_stride;
+};
+
+__global__ void __launch_bounds__(256) k_peerbox(const __grid_constant__ Geom G, const __grid_constant__ CPtrTab U, int ncomp,
+                                                 const __grid_constant__ PeerBoxArgs B)
+{
+    const long long total = B.first[B.nbox];
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total;
+         id += (long long)gridDim.x * blockDim.x) {
+        int b = 0;
+        while (b + 1 < B.nbox && id >= B.first[b + 1]) b++;
+        const long long r0 = id - B.first[b];
+        const long long nb = (long long)B.ext[b][0] * B.ext[b][1] * B.ext[b][2];
+        const int q = (int)(r0 / nb);
+        const long long r = r0 % nb;
+        const int i = (int)(r % B.ext[b][0]) + B.lo[b][0];
+        const int j = (int)((r / B.ext[b][0]) % B.ext[b][1]) + B.lo[b][1];
+        const int k = (int)(r / ((long long)B.ext[b][0] * B.ext[b][1])) + B.lo[b][2];
+        B.dst[b][q * B.comp_stride + cidx(G, i - B.shift[b][0], j - B.shift[b][1], k - B.shift[b][2])] =
+            U.p[q][cidx(G, i, j, k)];
+    }
+}
+
 /* max over the interior of (|u_d| + c)/dx_d (FlowModelSingleSpecies.cpp:3884-4388 MAX_WAVE_SPEED_d;
  * Euler.cpp:489-900).  Non-negative doubles order like their bit patterns. */
 template <class Tr>
@@ -1007,6 +1037,50 @@ int hb2_unpack_boxes_dev(hb2_plan_t p, double* const* U, int32_t nbox, const int
                          const int64_t* offsets, const double* buffer)
 {
     return multibox(p, U, nbox, lo, hi, offsets, const_cast<double*>(buffer), false);
+}
+
+int hb2_push_boxes_dev(hb2_plan_t p, const double* const* U, int32_t nbox, const int32_t* lo, const int32_t* hi,
+                       double* const* dst, const int32_t* shift, int64_t comp_stride)
+{
+    if (!p || !U || !lo || !hi || !dst || !shift) return fail(-1, "null argument");
+    if (nbox < 1 || nbox > HB2_MAX_BOXES) return fail(-23, "nbox must be in 1..HB2_MAX_BOXES");
+    if (comp_stride < p->G.ncell_g) return fail(-24, "component stride smaller than the ghost box");
+    HB2_CUDA(cudaSetDevice(p->device));
+    PeerBoxArgs M;
+    memset(&M, 0, sizeof(M));
+    M.nbox = nbox;
+    M.comp_stride = comp_stride;
+    for (int b = 0; b < nbox; b++) {
+        if (!dst[b]) return fail(-1, "null destination");
+        BoxArgs B, D;
+        int rc = box_args(p, lo + 3 * b, hi + 3 * b, &B);
+        if (rc) return rc;
+        /* the image of the box has to lie inside the (equally sized) destination ghost box */
+        int32_t dlo[3], dhi[3];
+        for (int a = 0; a < 3; a++) {
+            const int sh = (a < p->d.dim) ? shift[3 * b + a] : 0;
+            dlo[a] = lo[3 * b + a] - sh;
+            dhi[a] = hi[3 * b + a] - sh;
+            M.shift[b][a] = sh;
+        }
+        rc = box_args(p, dlo, dhi, &D);
+        if (rc) return rc;
+        for (int a = 0; a < 3; a++) {
+            M.lo[b][a] = B.lo[a];
+            M.ext[b][a] = B.ext[a];
+        }
+        M.first[b + 1] = M.first[b] + (long long)B.ext[0] * B.ext[1] * B.ext[2] * p->ncomp;
+        M.dst[b] = dst[b];
+    }
+    CPtrTab t;
+    memset(&t, 0, sizeof(t));
+    for (int c = 0; c < p->ncomp; c++) t.p[c] = U[c];
+    {
+        ProfScope ps(p, 6);
+        k_peerbox<<<grid_for(M.first[nbox], 256), 256, 0, p->stream>>>(p->G, t, p->ncomp, M);
+    }
+    HB2_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int hb2_max_wave_speed_dev(hb2_plan_t p, const double* const* Q, double* out_dev)

@@ -24,9 +24,27 @@ import numpy as np
 G = 4
 
 PROCESS_GRIDS = {
-    3: {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)},
+    # 3-D: x is never split.  Ghost slabs next to an x face are 4- or 6-cell rows (32 / 48 bytes) that make poor NVLink
+    # stores; y / z faces are whole rows.  Measured at 512^3 on 8 B200s: (1, 2, 4) 48.2e9 cell-updates/s and
+    # Navier-Stokes 34.9e9 against 46.8e9 / 33.0e9 with (2, 2, 2) (profiles/r02_bc_grid_ab_8gpu.txt); the periodic x
+    # images are the box's own and are filled locally.
+    3: {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (1, 2, 4)},
     2: {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)},
 }
+
+
+def _grid_override():
+    """HB2_PROCESS_GRID="gx,gy,gz" (or "gx,gy"): replaces the default process grid of that many ranks (measurements of
+    other box shapes; every rank of a job must see the same value)."""
+    import os
+
+    env = os.environ.get("HB2_PROCESS_GRID", "")
+    if env:
+        g = tuple(int(x) for x in env.split(","))
+        PROCESS_GRIDS[len(g)][int(np.prod(g))] = g
+
+
+_grid_override()
 
 
 @dataclass
@@ -161,6 +179,24 @@ def oneshot_schedule(dec: "BoxDecomposition", ncomp: int, ghosts: int = G):
         return out
 
     return finish(sends), finish(recvs), local_mask
+
+
+def push_boxes_of(dec: "BoxDecomposition", ghosts: int = G):
+    """The sends of oneshot_schedule as direct stores (hb2_push_boxes_dev): (boxes, peers, shifts) -- box b = my
+    interior cells next to the face / edge / corner in direction o, owned as ghosts by rank peers[b], whose box sees
+    them at cell index - shifts[b] (shifts[b] = o * n; every box of the decomposition has the same size)."""
+    import itertools
+
+    dim, n, grid = dec.dim, dec.n, dec.grid
+    boxes, peers, shifts = [], [], []
+    for o in itertools.product((-1, 0, 1), repeat=dim):
+        if not any(o) or any(o[a] != 0 and grid[a] == 1 for a in range(dim)):
+            continue
+        peers.append(dec.rank_of([dec.coords[a] + o[a] for a in range(dim)]))
+        boxes.append((tuple(n[a] - ghosts if o[a] > 0 else 0 for a in range(dim)),
+                      tuple(ghosts if o[a] < 0 else n[a] for a in range(dim))))
+        shifts.append(tuple(o[a] * n[a] for a in range(dim)))
+    return boxes, peers, shifts
 
 
 def exchange_halos_oneshot(schedule, ncomp: int, pack_many: Callable, unpack_many: Callable, fill_local: Callable,

@@ -12,8 +12,11 @@ src/apps/Navier-Stokes/NavierStokes.cpp: per stage
 The state carries six ghost cells (max of the convective 4 and the diffusive 6, NavierStokes.cpp ctor) and both
 reconstructors read the same arrays (the convective plan is created with num_ghosts = 6), like SAMRAI hands them the
 same allocation.  One patch per rank: with torch.distributed initialised the periodic level is split into boxes like the
-Euler level (hamers_b200/level.py: BoxDecomposition) and the six-wide halos travel in the single-phase schedule (one NCCL
-message per neighbour, multi-box pack / unpack kernels); no other collective.  Two routes per stage:
+Euler level (hamers_b200/level.py: BoxDecomposition).  The six-wide halos of a stage's new state are stored straight into
+the neighbouring boxes' state arrays (peer-GPU memory opened over CUDA IPC, hb2_push_boxes_dev: one launch, NVLink
+stores, no pack / NCCL send-recv / unpack), ordered against the next stage by one tiny stream-ordered all-reduce; the
+single-phase NCCL schedule (one message per neighbour, multi-box pack / unpack kernels) fills a freshly set state and is
+the whole exchange with push=False (HB2_NS_PUSH=0).  Two routes per stage:
 
   math = MATH_EXACT  both side fluxes materialised and combined by hb2_advance_stage_ns_dev in the reference's
                      association: a step is bit-identical to the oracle's composition of the same calls;
@@ -29,14 +32,16 @@ from typing import Sequence, Tuple
 import numpy as np
 
 from . import abi
-from .level import BoxDecomposition, exchange_halos_oneshot, oneshot_schedule
+from .level import BoxDecomposition, exchange_halos_oneshot, oneshot_schedule, push_boxes_of
 
 
 class NavierStokesLevel:
     def __init__(self, dim: int, N: Sequence[int], species_gamma: float = 1.4, species_R: float = 1.0,
                  species_mu: float = 1.0e-3, species_mu_v: float = 0.0, species_c_p: float = 3.5, species_Pr: float = 0.72,
                  domain: Tuple[float, float] = (0.0, 1.0), math: int = abi.MATH_EXACT, scheme: int = 0, grid=None,
-                 distributed: bool = True, device: str = "cuda"):
+                 distributed: bool = True, device: str = "cuda", push=None):
+        import os
+
         import torch
         import torch.distributed as dist
 
@@ -62,7 +67,18 @@ class NavierStokesLevel:
         self.device = device            # "cuda"; the CPU test suite drives the same loop over emulation-backed plans
         f64 = dict(dtype=torch.float64, device=device)
         g6 = tuple(x + 12 for x in reversed(self.n))
-        self.S = [torch.zeros((self.neq,) + g6, **f64) for _ in range(3)]           # U0 and the two intermediate states
+        if push is None:
+            push = os.environ.get("HB2_NS_PUSH", "1") != "0"
+        self.push = bool(push) and self.dist is not None and device == "cuda"
+        self._arrays, self._opened, self.push_tables = [], [], None
+        if self.push:
+            # IPC-shareable state buffers (U0 and the two intermediate states); the neighbours' are opened below
+            self._arrays = [abi.DeviceArray((self.neq,) + g6) for _ in range(3)]
+            self.S = [torch.as_tensor(a, device="cuda") for a in self._arrays]
+            for t in self.S:
+                t.zero_()
+        else:
+            self.S = [torch.zeros((self.neq,) + g6, **f64) for _ in range(3)]       # U0 and the two intermediate states
         if math == abi.MATH_EXACT:
             self.Fd = [torch.zeros((self.neq,) + self.dplan.side_shape(a), **f64) for a in range(dim)]
             self.Fc = [torch.zeros((self.neq,) + self.dplan.side_shape(a), **f64) for a in range(dim)]
@@ -74,11 +90,40 @@ class NavierStokesLevel:
         self._tables, self._bufs = {}, {}
         if self.dist is not None:
             assert all(n >= abi.DIFF_GHOSTS for n in self.n), "boxes must be at least one halo width wide"
-            self.dist.barrier()
+        if self.push:
+            self._open_peers(rank, nranks)
+        if self.dist is not None:
+            self.dist.barrier()     # every rank has opened its neighbours' buffers before anyone steps
+
+    def _open_peers(self, rank, nranks):
+        """Per state buffer, the table of hb2_push_boxes_dev: my interior slab next to face / edge / corner o goes to
+        the ghost box of the neighbour at o, which sees it shifted by o * n (all boxes of the decomposition are equal)."""
+        handles = [None] * nranks
+        self.dist.all_gather_object(handles, [abi.ipc_export(a.ptr) for a in self._arrays])
+        bases = {rank: [a.ptr for a in self._arrays]}
+        boxes, peers, shifts = push_boxes_of(self.decomp, abi.DIFF_GHOSTS)
+        for peer in peers:
+            if peer not in bases:
+                ptrs = [abi.ipc_open(h) for h in handles[peer]]
+                self._opened += ptrs
+                bases[peer] = ptrs
+        self.push_tables = [self.cplan.peer_box_table(boxes, [bases[peer][b] for peer in peers], shifts) for b in range(3)]
+        self._flag = self.torch.zeros(1, dtype=self.torch.float32, device="cuda")
 
     def close(self):
         self.cplan.close()
         self.dplan.close()
+        if self._opened or self._arrays:
+            self.torch.cuda.synchronize()
+            self.dist.barrier()     # nobody unmaps or frees a buffer a neighbour may still be writing into
+        for p in self._opened:
+            abi.ipc_close(p)
+        self._opened = []
+        if self._arrays:
+            self.S = []
+        for a in self._arrays:
+            a.free()
+        self._arrays = []
 
     def _interior_slices(self):
         return (slice(None),) + (slice(6, -6),) * self.dim
@@ -107,9 +152,19 @@ class NavierStokesLevel:
             self._tables[key] = t
         return t
 
-    def fill_ghosts(self, U):
+    def fill_ghosts(self, U, buffer=None):
+        """Same-level ghost fill of the state U.  buffer = index of U in self.S on the stage path: with push the halos
+        are stored straight into the neighbours' copies of that buffer (every rank calls this in the same stage)."""
         if self.dist is None:
             self.dplan.fill_ghosts_periodic(U)
+            return
+        if self.push and buffer is not None:
+            self.cplan.push_boxes(U, self.push_tables[buffer])
+            # orders "every rank's stores into my ghosts are complete" before anything reads them (stream-ordered); a
+            # rank can be at most one stage ahead of a neighbour, and consecutive stages write different buffers
+            self.dist.all_reduce(self._flag)
+            if self.oneshot[2]:
+                self.dplan.fill_ghosts_periodic(U, self.oneshot[2])
             return
         exchange_halos_oneshot(self.oneshot, self.neq,
                                pack_many=lambda boxes, off, b: self.cplan.pack_boxes(U, self._table("s", boxes, off), b),
@@ -136,7 +191,7 @@ class NavierStokesLevel:
         else:
             self.cplan.fused_stage(alpha, beta, [S[i] for i in states], dt, S[out])
             self.dplan.divergence_accumulate(newest, dt, 6, float(beta[-1]), S[out])
-        self.fill_ghosts(S[out])
+        self.fill_ghosts(S[out], out)
 
     def stable_dt(self, cfl: float = 1.0) -> float:
         """Level-wide stable time step: NavierStokes::computeSpectralRadiusesAndStableDtOnPatch per box (acoustic radii of

@@ -210,6 +210,16 @@ int hb2_pack_boxes_dev(hb2_plan_t plan, const double* const* U, int32_t nbox, co
 int hb2_unpack_boxes_dev(hb2_plan_t plan, double* const* U, int32_t nbox, const int32_t* lo,
                          const int32_t* hi, const int64_t* offsets, const double* buffer);
 
+/* Same-level ghost fill between equally sized patches WITHOUT message buffers: box b of this patch's state is stored
+ * straight into the state array of a neighbouring patch -- dst[b] is component 0 of that array (components comp_stride
+ * doubles apart; the same ghost-box geometry as the plan's), on this GPU or on a peer GPU whose allocation was opened
+ * with hb2_ipc_open -- at cell (i, j, k) - shift[3b..3b+2].  For a periodic neighbour at offset o, lo / hi is the
+ * interior slab next to face o and shift = o * n: what xfer::RefineSchedule::fillData
+ * (RungeKuttaLevelIntegrator.cpp:1568/1701) copies, travelling as NVLink stores instead of pack -> message -> unpack.
+ * The caller orders "all ranks' stores have landed" before the ghosts are read (one stream-ordered all-reduce). */
+int hb2_push_boxes_dev(hb2_plan_t plan, const double* const* U, int32_t nbox, const int32_t* lo,
+                       const int32_t* hi, double* const* dst, const int32_t* shift, int64_t comp_stride);
+
 /* Euler::computeSpectralRadiusesAndStableDtOnPatch (Euler.cpp:489-900) without source terms, with
  * MAX_WAVE_SPEED_d = |u_d| + c (FlowModelSingleSpecies.cpp:3884-4388) evaluated on the fly:
  *   out_dev[a]   = max over the interior of (|u_a| + c)/dx_a, a < dim   (the reference also visits the ghost cells,

@@ -4,7 +4,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         tests/multi_gpu_ns_check.py [--size 40] [--steps 2]
 
-Every rank advances its box with six-wide halos exchanged in the single-phase schedule (NCCL P2P over NVLink); rank 0 also
+Every rank advances its box with six-wide halos stored straight into the neighbours' state arrays (hb2_push_boxes_dev over
+CUDA IPC / NVLink; HB2_NS_PUSH=0: the single-phase NCCL schedule, which also fills the freshly set state); rank 0 also
 advances the WHOLE level as one box and the gathered boxes are compared with it: bit-identical in the exact build (a box
 boundary must be invisible), <= 1e-12 in the fast build.  Exit code 0 on success."""
 import argparse
@@ -68,11 +69,11 @@ def main():
             one_lvl.close()
             if math == abi.MATH_EXACT:
                 same = np.array_equal(full, one)
-                print(f"[multi_gpu_ns_check] world {world} exact: bit-identical = {same}, max diff {np.abs(full - one).max():.3e}")
+                print(f"[multi_gpu_ns_check] world {world} push={lvl.push} exact: bit-identical = {same}, max diff {np.abs(full - one).max():.3e}")
                 ok &= same
             else:
                 err = float((np.abs(full - one) / (np.abs(one) + np.abs(one).max(axis=(1, 2, 3), keepdims=True))).max())
-                print(f"[multi_gpu_ns_check] world {world} fast: max relative difference {err:.3e}")
+                print(f"[multi_gpu_ns_check] world {world} push={lvl.push} fast: max relative difference {err:.3e}")
                 ok &= err <= 1e-12
         lvl.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")

@@ -108,7 +108,7 @@ def test_halo_exchange_gloo(dim, N, world, oneshot):
         assert ok, f"rank {rank}: ghost box differs from the periodic image ({nans} cells never filled)"
 
 
-@pytest.mark.parametrize("dim,N,world", [(3, (16, 12, 8), 2), (2, (24, 12), 4)])
+@pytest.mark.parametrize("dim,N,world", [(3, (8, 12, 16), 2), (2, (24, 12), 4)])
 def test_six_wide_halo_exchange_gloo(dim, N, world):
     """The single-phase schedule with the Navier-Stokes halo width (six ghost cells)."""
     import torch.multiprocessing as mp
@@ -171,3 +171,48 @@ def test_decomposition_covers_level_once():
                     nb = BoxDecomposition(dim, N, world, d.neighbour(a, side))
                     assert nb.coords[a] == (d.coords[a] + (1 if side else -1)) % d.grid[a]
         assert (seen == 1).all()
+
+
+@pytest.mark.parametrize("dim,N,world,ghosts", [(2, (16, 12), 2, 6), (2, (16, 16), 4, 4), (3, (12, 14, 16), 2, 6),
+                                                (3, (16, 12, 14), 4, 6), (3, (12, 12, 24), 8, 6), (3, (12, 12, 16), 8, 4)])
+def test_push_boxes_fill_every_ghost(dim, N, world, ghosts):
+    """push_boxes_of (the table of hb2_push_boxes_dev, the Navier-Stokes level's six-wide direct ghost stores): every
+    rank stores its slabs at index - shift into the owner's array, then fills the directions it owns alone locally
+    (ghost-inclusive in the exchanged ones): all ghosts -- faces, edges, corners -- equal the periodic image."""
+    from hamers_b200.level import push_boxes_of
+
+    g = ghosts
+    rng = np.random.default_rng(11)
+    full = rng.standard_normal((2,) + tuple(reversed(N)))
+    decs = [BoxDecomposition(dim, N, world, r) for r in range(world)]
+    arrays = []
+    for dec in decs:
+        U = np.full((2,) + tuple(x + 2 * g for x in reversed(dec.n)), np.nan)
+        box = tuple(slice(dec.lo[a], dec.lo[a] + dec.n[a]) for a in reversed(range(dim)))
+        U[(slice(None),) + tuple(slice(g, -g) for _ in range(dim))] = full[(slice(None),) + box]
+        arrays.append(U)
+
+    def region(lo, hi):
+        return (slice(None),) + tuple(slice(lo[a] + g, hi[a] + g) for a in reversed(range(dim)))
+
+    for dec, U in zip(decs, arrays):
+        boxes, peers, shifts = push_boxes_of(dec, g)
+        sends = oneshot_schedule(dec, 2, g)[0]
+        assert sorted(set(peers)) == [t.peer for t in sends] and len(boxes) == sum(len(t.boxes) for t in sends)
+        for (lo, hi), peer, sh in zip(boxes, peers, shifts):
+            assert peer != dec.rank
+            dlo = tuple(lo[a] - sh[a] for a in range(dim))
+            dhi = tuple(hi[a] - sh[a] for a in range(dim))
+            assert all(-g <= dlo[a] and dhi[a] <= dec.n[a] + g for a in range(dim))
+            arrays[peer][region(dlo, dhi)] = U[region(lo, hi)]
+    for dec, U in zip(decs, arrays):
+        mask = oneshot_schedule(dec, 2, g)[2]
+        for a in range(dim):
+            if (mask >> a) & 1:     # ghost-inclusive in the other directions
+                ax = U.ndim - 1 - a
+                n = dec.n[a]
+                idx = (np.arange(-g, n + g) % n) + g
+                U[...] = np.take(U, idx, axis=ax)
+        want = np.pad(full, [(0, 0)] + [(g, g)] * dim, mode="wrap")
+        box = tuple(slice(dec.lo[a], dec.lo[a] + dec.n[a] + 2 * g) for a in reversed(range(dim)))
+        assert np.array_equal(U, want[(slice(None),) + box])
