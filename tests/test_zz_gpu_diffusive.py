@@ -318,9 +318,12 @@ def test_flux_free_divergence_fast_math(N, g, diff_kernel_form, product_lib):
     plan.close()
 
 
-def test_two_gpu_navier_stokes_level_matches_single_box():
-    """Box boundaries are invisible: two ranks with six-wide halos over NCCL against the one-box run (skipped on one GPU;
-    the schedule is covered on CPU by tests/test_level_gloo.py::test_six_wide_halo_exchange_gloo)."""
+@pytest.mark.parametrize("push", ["1", "0"])
+def test_two_gpu_navier_stokes_level_matches_single_box(push):
+    """Box boundaries are invisible: two ranks with six-wide halos -- stored straight into the neighbour's state array
+    (hb2_push_boxes_dev over CUDA IPC / NVLink, push = 1) or exchanged over NCCL (push = 0) -- against the one-box run
+    (skipped on one GPU; the schedule is covered on CPU by tests/test_level_gloo.py::test_six_wide_halo_exchange_gloo and
+    ::test_push_boxes_fill_every_ghost, the store kernel on one GPU by tests/test_zz_gpu_push_boxes.py)."""
     import os
     import subprocess
     import sys
@@ -332,9 +335,9 @@ def test_two_gpu_navier_stokes_level_matches_single_box():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29537", os.path.join(root, "tests", "multi_gpu_ns_check.py"), "--size", "40"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, HB2_NS_PUSH=push))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "bit-identical = True" in r.stdout
+    assert "bit-identical = True" in r.stdout and f"push={push == '1'}" in r.stdout
 
 
 @pytest.mark.parametrize("math", [100, 101])
